@@ -1,0 +1,66 @@
+"""Shared comparison helpers for the parity tests (tolerances are stated here, once).
+
+FLOW_RTOL = 1e-4 is BASELINE.json north_star's bar for flow vectors and the rigid transform:
+|a-b| <= FLOW_RTOL * max(|b|, scale) elementwise, where `scale` is the largest magnitude of the
+reference tensor for that frame pair (so near-zero components are judged against the vector's size).
+Integer / index outputs are compared exactly.
+"""
+import os
+
+import torch
+
+FLOW_RTOL = 1e-4
+THRESH_GUARD = 1e-4      # points whose static score is this close to stat_thres may flip mask legitimately
+
+
+def rel_err(a, b, per_pair=True):
+    """max over elements of |a-b| / max(|b|, per-pair max|b|)."""
+    a, b = a.double(), b.double()
+    if per_pair and b.dim() >= 2:
+        scale = b.abs().flatten(1).max(1)[0].clamp_min(1e-30).view(-1, *([1] * (b.dim() - 1)))
+    else:
+        scale = b.abs().max().clamp_min(1e-30)
+    return ((a - b).abs() / scale).max().item()
+
+
+def load_golden(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), map_location="cpu", weights_only=True)
+
+
+def case_inputs(meta, **kw):
+    from cmflow_b200.synth import make_pairs
+    return make_pairs(meta["B"], meta["N"], seed=meta["data_seed"], **kw)
+
+
+def case_weights(meta, golden_dir):
+    from cmflow_b200.synth import synthetic_state_dict
+    if "weights" in meta:
+        for p in (os.path.join(golden_dir, "_weights", os.path.basename(os.path.dirname(os.path.dirname(meta["weights"]))) + ".t7"),
+                  os.path.join("/root/reference", meta["weights"])):
+            if os.path.exists(p):
+                return torch.load(p, map_location="cpu", weights_only=True)
+        return None
+    return synthetic_state_dict(meta["weight_seed"], temporal=(meta["model"] == "cmflow_t"))
+
+
+def knn_sets_equal(idx, ref_sorted):
+    """idx (B,N,k) any order vs reference sets sorted ascending (int16)."""
+    return torch.equal(idx.long().sort(-1)[0], ref_sorted.long())
+
+
+def check_outputs(out, gold, rtol=FLOW_RTOL, stat_thres=0.5):
+    """Compare a forward result dict with a golden dict; returns dict of measured errors and asserts the bars."""
+    cls_g = gold["stat_cls"]
+    safe = ((cls_g - stat_thres).abs() > THRESH_GUARD).squeeze(1)            # (B,N)
+    errs = {}
+    errs["stat_cls"] = (out["stat_cls"].double() - cls_g.double()).abs().max().item()
+    errs["pre_trans"] = rel_err(out["pre_trans"][:, :3, :], gold["pre_trans"][:, :3, :])
+    m_ok = (out["mask"].bool() == gold["mask"].bool()) | ~safe
+    errs["mask_mismatch"] = int((~m_ok).sum())
+    a = torch.where(safe.unsqueeze(1), out["sf_agg"].double(), gold["sf_agg"].double())
+    errs["sf_agg"] = rel_err(a, gold["sf_agg"])
+    assert errs["mask_mismatch"] == 0, errs
+    assert errs["stat_cls"] <= rtol, errs            # probabilities in [0,1]: absolute == relative to range
+    assert errs["pre_trans"] <= rtol, errs
+    assert errs["sf_agg"] <= rtol, errs
+    return errs
