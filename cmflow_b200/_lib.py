@@ -1,0 +1,89 @@
+"""ctypes binding of libcmflow_b200.so (the C ABI of include/cmflow_b200.h).
+
+No fallback: if the library is missing, `lib()` raises -- the product path must fail loudly rather
+than silently compute somewhere else.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcmflow_b200.so")
+_lib = None
+
+_vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/cmflow_b200.h
+SIGNATURES = {
+    "cmf_last_error": [],
+    "cmf_version": [],
+    "cmf_device_check": [],
+    "cmf_ball_query": [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp],
+    "cmf_group_points": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "cmf_group_points_grad": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "cmf_gather_points": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "cmf_gather_points_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "cmf_furthest_point_sampling": [_i, _i, _i, _vp, _vp, _vp, _vp],
+    "cmf_knn": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "cmf_three_nn": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "cmf_three_interpolate": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "cmf_three_interpolate_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "cmf_knn_point": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "cmf_ball_query_ms": [_i, _i, _vp, _vp, _vp],
+    "cmf_kabsch_refine": [_i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp],
+    "cmf_weighted_kabsch": [_i, _i, _vp, _vp, _vp, _vp, _vp],
+    "cmf_model_blob_floats": [_i],
+    "cmf_model_create": [ctypes.POINTER(_vp), _vp, _sz, _i, _f],
+    "cmf_model_destroy": [_vp],
+    "cmf_model_workspace_bytes": [_vp],
+    "cmf_model_launches_per_forward": [_vp],
+    "cmf_model_forward": [_vp, _i, _i] + [_vp] * 11,
+    "cmf_model_forward_host": [_vp, _i, _i] + [_vp] * 11,
+    "cmf_model_tap": [_vp, ctypes.c_char_p],
+}
+_RESTYPES = {"cmf_last_error": ctypes.c_char_p, "cmf_version": ctypes.c_char_p, "cmf_model_blob_floats": _sz,
+             "cmf_model_destroy": None, "cmf_model_workspace_bytes": _sz, "cmf_model_tap": _vp}
+
+
+class CmfError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CmfError(f"{LIB_PATH} is not built -- run `python -m cmflow_b200.build` "
+                           "(nvcc, sm_100a). There is no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(L, name)           # AttributeError if the header and the .so ever disagree
+            fn.argtypes = args
+            fn.restype = _RESTYPES.get(name, ctypes.c_int)
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise CmfError(lib().cmf_last_error().decode())
+
+
+def stream_ptr():
+    """The current torch CUDA stream as a cudaStream_t (the reference enqueues on
+    at::cuda::getCurrentCUDAStream(), e.g. lib/src/ball_query.cpp:22)."""
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dptr(t, dtype=None):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    if not t.is_cuda:
+        raise CmfError("expected a CUDA tensor (this library has no CPU path)")
+    if not t.is_contiguous():
+        raise CmfError("expected a contiguous tensor")
+    if dtype is not None and t.dtype != dtype:
+        raise CmfError(f"expected dtype {dtype}, got {t.dtype}")
+    return ctypes.c_void_p(t.data_ptr())

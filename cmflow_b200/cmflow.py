@@ -1,0 +1,184 @@
+"""CMFlow / CMFlow_T with the reference's constructor, forward signature, return values and state_dict
+key layout (models/cmflow.py:9-197, models/cmflow_t.py:10-211), running on the B200 engine.
+
+    net = CMFlow(args).cuda(); net.load_state_dict(torch.load("checkpoints/cmflow_cvpr/models/model.best.t7"))
+    sf_agg, stat_cls, pre_trans, mask = net(pc1, pc2, feature1, feature2, None, 'test')
+
+Only the inference path is implemented (label_m=None or mode != 'train'); the training branch that feeds
+pseudo labels to the Kabsch head (cmflow.py:181-182) is out of scope and raises.  There is no CPU path.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import weights as _weights
+from ._lib import CmfError, check, dptr, lib, stream_ptr
+
+
+class _SetConv(nn.Module):        # parameter container mirroring PointLocalFeature (radarflow_util.py:121-142)
+    def __init__(self, in_channel, mlp, mlp2):
+        super().__init__()
+        self.mlp_convs, self.mlp_bns = nn.ModuleList(), nn.ModuleList()
+        self.mlp2_convs, self.mlp2_bns = nn.ModuleList(), nn.ModuleList()
+        last = in_channel + 3
+        for co in mlp:
+            self.mlp_convs.append(nn.Conv2d(last, co, 1, bias=False)); self.mlp_bns.append(nn.BatchNorm2d(co)); last = co
+        for co in mlp2:
+            self.mlp2_convs.append(nn.Conv2d(last, co, 1, bias=False)); self.mlp2_bns.append(nn.BatchNorm2d(co)); last = co
+
+
+class _MultiScale(nn.Module):     # MultiScaleEncoder (radarflow_util.py:101-118)
+    def __init__(self, in_channel, mlp, mlp2):
+        super().__init__()
+        self.ms_ls = nn.ModuleList([_SetConv(in_channel, mlp, mlp2) for _ in range(4)])
+
+
+class _WeightNet(nn.Module):      # WeightNet (radarflow_util.py:288-305); BN modules exist but are unused (bn=False)
+    def __init__(self):
+        super().__init__()
+        dims = [(3, 8), (8, 8), (8, 512)]
+        self.mlp_convs = nn.ModuleList([nn.Conv2d(ci, co, 1) for ci, co in dims])
+        self.mlp_bns = nn.ModuleList([nn.BatchNorm2d(co) for _, co in dims])
+
+
+class _Correlator(nn.Module):     # FeatureCorrelator (radarflow_util.py:164-183)
+    def __init__(self):
+        super().__init__()
+        self.mlp_convs = nn.ModuleList([nn.Conv2d(1027, 512, 1), nn.Conv2d(512, 512, 1), nn.Conv2d(512, 512, 1)])
+        self.weightnet1, self.weightnet2 = _WeightNet(), _WeightNet()
+
+
+class _Head(nn.Module):           # FlowHead / MotionHead (radarflow_util.py:240-285)
+    def __init__(self, cout):
+        super().__init__()
+        self.sf_mlp = nn.ModuleList()
+        last = 512
+        for co in (256, 128, 64):
+            self.sf_mlp.append(nn.Sequential(nn.Conv2d(last, co, 1, bias=False), nn.BatchNorm2d(co), nn.ReLU(inplace=False)))
+            last = co
+        self.conv2 = nn.Conv2d(64, cout, 1, bias=False)
+
+
+class _EngineModel(nn.Module):
+    _temporal = False
+
+    def __init__(self, args):
+        super().__init__()
+        self.npoints = args.num_points
+        self.stat_thres = 0.5 if self._temporal else args.stat_thres      # cmflow_t.py:18 hard-codes 0.50
+        self.mse_layer = _MultiScale(3, (32, 32, 64), (64, 64, 64))
+        self.fc_layer = _Correlator()
+        self.mse_layer2 = _MultiScale(1027, (512, 256, 64), (64, 64, 64))
+        if self._temporal:
+            self.gru = nn.GRU(input_size=256, hidden_size=256, num_layers=1)
+        self.fp, self.mp = _Head(3), _Head(1)
+        self._handle = None
+        self.eval()
+
+    # ---- engine lifecycle ------------------------------------------------------------------------
+    def _drop_engine(self):
+        if getattr(self, "_handle", None):
+            lib().cmf_model_destroy(self._handle)
+        self._handle = None
+
+    def load_state_dict(self, *a, **k):
+        self._drop_engine()
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._drop_engine()
+        return super()._apply(fn, *a, **k)
+
+    def __del__(self):
+        try:
+            self._drop_engine()
+        except Exception:
+            pass
+
+    def _engine(self, device):
+        if self._handle is None:
+            blob = _weights.pack(self.state_dict(), temporal=self._temporal)
+            L = lib()
+            assert blob.size == L.cmf_model_blob_floats(int(self._temporal))
+            h = ctypes.c_void_p()
+            with torch.cuda.device(device):
+                check(L.cmf_model_create(ctypes.byref(h), blob.ctypes.data_as(ctypes.c_void_p), blob.size,
+                                         int(self._temporal), float(self.stat_thres)))
+            self._handle = h
+        return self._handle
+
+    def launches_per_forward(self):
+        return lib().cmf_model_launches_per_forward(self._handle) if self._handle else 0
+
+    def workspace_bytes(self):
+        return lib().cmf_model_workspace_bytes(self._handle) if self._handle else 0
+
+    def tap(self, name, shape, dtype=torch.float32):
+        """Copy of an engine workspace buffer of the last forward chunk (tests only)."""
+        p = lib().cmf_model_tap(self._handle, name.encode())
+        if not p:
+            raise KeyError(name)
+
+        class _Raw:          # zero-copy view of a raw device pointer through the CUDA array interface
+            __cuda_array_interface__ = {"shape": tuple(shape), "typestr": {torch.float32: "<f4", torch.int32: "<i4"}[dtype],
+                                        "data": (int(p), False), "version": 2}
+
+        torch.cuda.synchronize()
+        return torch.as_tensor(_Raw(), device="cuda").clone()
+
+    def _run(self, pc1, pc2, feature1, feature2, label_m, mode, gfeat):
+        if mode == 'train' and label_m is not None:
+            raise NotImplementedError("cmflow_b200 implements the inference path only (label_m=None)")
+        ins = [t.float().contiguous() for t in (pc1, pc2, feature1, feature2)]
+        if not ins[0].is_cuda:
+            raise CmfError("cmflow_b200 has no CPU path: inputs must be CUDA tensors")
+        B, _, N = ins[0].shape
+        dev = ins[0].device
+        h = self._engine(dev)
+        sf = torch.empty(B, 3, N, device=dev); cls = torch.empty(B, 1, N, device=dev)
+        T = torch.empty(B, 4, 4, device=dev); mask = torch.empty(B, N, dtype=torch.uint8, device=dev)
+        gout = torch.empty(B, 256, device=dev) if self._temporal else None
+        gprev = gfeat.float().contiguous() if (self._temporal and gfeat is not None) else None
+        with torch.cuda.device(dev):
+            check(lib().cmf_model_forward(h, B, N, dptr(ins[0]), dptr(ins[1]), dptr(ins[2]), dptr(ins[3]), dptr(gprev),
+                                          dptr(sf), dptr(cls), dptr(T), dptr(mask), dptr(gout), stream_ptr()))
+        return sf, cls, T, mask.bool(), gout
+
+    def forward_host(self, pc1, pc2, feature1, feature2, gfeat=None, out=None):
+        """End-to-end call on HOST tensors (pinned for full speed): H2D, forward, D2H, synchronise
+        (cmf_model_forward_host).  Returns CPU tensors; pass `out` (dict of pinned tensors) to reuse buffers."""
+        ins = [t.float().contiguous() for t in (pc1, pc2, feature1, feature2)]
+        if ins[0].is_cuda:
+            raise CmfError("forward_host takes host tensors")
+        B, _, N = ins[0].shape
+        dev = torch.device("cuda", torch.cuda.current_device())
+        h = self._engine(dev)
+        if out is None:
+            out = {"sf_agg": torch.empty(B, 3, N).pin_memory(), "stat_cls": torch.empty(B, 1, N).pin_memory(),
+                   "pre_trans": torch.empty(B, 4, 4).pin_memory(), "mask": torch.empty(B, N, dtype=torch.uint8).pin_memory(),
+                   "gfeat": torch.empty(B, 256).pin_memory()}
+        hp = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+        gprev = gfeat.float().contiguous() if (self._temporal and gfeat is not None) else None
+        check(lib().cmf_model_forward_host(h, B, N, hp(ins[0]), hp(ins[1]), hp(ins[2]), hp(ins[3]), hp(gprev),
+                                           hp(out["sf_agg"]), hp(out["stat_cls"]), hp(out["pre_trans"]), hp(out["mask"]),
+                                           hp(out["gfeat"]), stream_ptr()))
+        return out
+
+
+class CMFlow(_EngineModel):
+    """models/cmflow.py:9 -- forward(pc1, pc2, feature1, feature2, label_m, mode) -> (sf_agg, stat_cls, pre_trans, mask)."""
+    _temporal = False
+
+    def forward(self, pc1, pc2, feature1, feature2, label_m, mode):
+        sf, cls, T, mask, _ = self._run(pc1, pc2, feature1, feature2, label_m, mode, None)
+        return sf, cls, T, mask
+
+
+class CMFlow_T(_EngineModel):
+    """models/cmflow_t.py:10 -- forward(..., label_m, mode, gfeat) -> (sf_agg, stat_cls, pre_trans, mask, gfeat)."""
+    _temporal = True
+
+    def forward(self, pc1, pc2, feature1, feature2, label_m, mode, gfeat):
+        return self._run(pc1, pc2, feature1, feature2, label_m, mode, gfeat)

@@ -1,0 +1,442 @@
+// engine.cu -- Part 3 of the C ABI: the whole-forward engine behind CMFlow.forward (models/cmflow.py:171-197)
+// and CMFlow_T.forward (models/cmflow_t.py:185-211).
+//
+// The engine owns (a) the packed weights on the device, (b) one workspace arena sized for a CHUNK of frame
+// pairs, and (c) the launch sequence.  Pairs are independent in eval mode (BatchNorm uses running statistics),
+// so a batch is processed as consecutive chunks of pairs: the arena stays a few GB regardless of B and N,
+// and a chunk's activations are mostly L2-resident between the kernels that produce and consume them.
+//
+// Algebra (exact in real arithmetic, differs from the reference only in fp32 summation order):
+//  * BatchNorm (eval) is folded into the preceding 1x1 conv on the host in fp64 (cmflow_b200/weights.py).
+//  * conv(cat[...]) is split by column blocks.  Blocks that multiply a per-cloud constant (the broadcast
+//    global max feature, cmflow.py:76-81) become a per-pair bias; blocks that multiply a gathered neighbour
+//    feature are applied ONCE PER POINT before the gather (the 1x1 conv commutes with the gather):
+//       set-conv #2 layer 1:   8.1 GMAC/pair -> 0.41 GMAC/pair   (SURVEY.md section 7 "first-layer hoisting")
+//       flow-embedding layer 1: 1.08 GMAC/pair -> 0.07 GMAC/pair
+//  * mse_layer and mse_layer2 query the same cloud with the same radii (cmflow.py:21-24,35-39), so the
+//    reference's 12 ball queries are 8, and each cloud's four radii are answered in one pass.
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "model_kernels.cuh"
+
+namespace {
+
+constexpr int HDR = 512;                 // header floats (int32 view): magic, nseg, temporal, then (off, rows, cols) per segment
+constexpr int MAGIC = 0x434D4642;        // "CMFB"
+constexpr int KS[4] = {4, 8, 16, 32};
+constexpr int KOFF[4] = {0, 4, 12, 28};
+constexpr int E_LD = 776;                // embedding row: [f1 256 | cor 512 | ft 3 | pad 5]
+
+// ---- segment table (order is the contract with cmflow_b200/weights.py) ---------------------------
+enum {
+    M1_BASE = 0,          // 4 scales x 12: W1[32x8] B1 W2[32x32] B2 W3[64x32] B3 V1[64x64] C1 V2 C2 V3 C3
+    FC_WC = 48, FC_WCG, FC_WN, FC_WNG, FC_WD, FC_B1, FC_W2, FC_B2, FC_W3, FC_B3,
+    WN1_BASE = 58,        // A1[8x4] a1[8] A2[8x8] a2[8] A3[512x8] a3[512]
+    WN2_BASE = 64,
+    M2_WP = 70, M2_WG, M2_T1, M2_WX,
+    M2_BASE = 74,         // 4 scales x 10: W2[256x512] T2 W3[64x256] T3 V1 C1 V2 C2 V3 C3
+    HD_W1 = 114, HD_W1G, HD_T1, HD_W2F, HD_T2F, HD_W2M, HD_T2M, HD_W3F, HD_T3F, HD_W3M, HD_T3M, HD_W4,
+    GRU_WIH = 126, GRU_WHH, GRU_BIH, GRU_BHH,
+    NSEG_STATIC = 126, NSEG_TEMPORAL = 130
+};
+
+struct SegShape { int rows, cols; };
+
+std::vector<SegShape> expected_shapes(int temporal) {
+    std::vector<SegShape> v;
+    for (int s = 0; s < 4; ++s) {
+        v.push_back({32, 8}); v.push_back({1, 32}); v.push_back({32, 32}); v.push_back({1, 32});
+        v.push_back({64, 32}); v.push_back({1, 64});
+        for (int l = 0; l < 3; ++l) { v.push_back({64, 64}); v.push_back({1, 64}); }
+    }
+    v.push_back({512, 256}); v.push_back({512, 256}); v.push_back({512, 256}); v.push_back({512, 256});
+    v.push_back({512, 4}); v.push_back({1, 512}); v.push_back({512, 512}); v.push_back({1, 512});
+    v.push_back({512, 512}); v.push_back({1, 512});
+    for (int w = 0; w < 2; ++w) {
+        v.push_back({8, 4}); v.push_back({1, 8}); v.push_back({8, 8}); v.push_back({1, 8});
+        v.push_back({512, 8}); v.push_back({1, 512});
+    }
+    v.push_back({2048, E_LD}); v.push_back({2048, 256}); v.push_back({1, 2048}); v.push_back({2048, 4});
+    for (int s = 0; s < 4; ++s) {
+        v.push_back({256, 512}); v.push_back({1, 256}); v.push_back({64, 256}); v.push_back({1, 64});
+        for (int l = 0; l < 3; ++l) { v.push_back({64, 64}); v.push_back({1, 64}); }
+    }
+    v.push_back({512, 256}); v.push_back({512, 256}); v.push_back({1, 512});
+    v.push_back({128, 256}); v.push_back({1, 128}); v.push_back({128, 256}); v.push_back({1, 128});
+    v.push_back({64, 128}); v.push_back({1, 64}); v.push_back({64, 128}); v.push_back({1, 64});
+    v.push_back({4, 64});
+    if (temporal) { v.push_back({768, 256}); v.push_back({768, 256}); v.push_back({1, 768}); v.push_back({1, 768}); }
+    return v;
+}
+
+size_t pad4(size_t x) { return (x + 3) & ~(size_t)3; }
+
+struct Arena {
+    char *base = nullptr;
+    size_t off = 0;
+    template <typename T> T *take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+struct Work {
+    float *X1T, *X2T; int *BQ1, *BQ2, *KNN12, *KNN11;
+    float *E, *F2, *G1, *G2;
+    float *X0, *T32a, *T32b, *T64, *M64, *Q1, *Q2;
+    float *PB1, *PB2, *U1, *U2, *H1, *H2, *COST1;
+    float *PBM, *P, *Y1, *Y2, *Y3, *PROP, *GP, *GI, *GH, *GNEW, *ZERO;
+    float *PBH, *HD1, *HD2, *HD3, *FLOW;
+};
+
+void carve(Arena &a, Work &w, int bc, int n) {
+    const size_t bn = (size_t)bc * n;
+    w.X1T = a.take<float>(bn * 3); w.X2T = a.take<float>(bn * 3);
+    w.BQ1 = a.take<int>(bn * 60); w.BQ2 = a.take<int>(bn * 60);
+    w.KNN12 = a.take<int>(bn * 8); w.KNN11 = a.take<int>(bn * 8);
+    w.E = a.take<float>(bn * E_LD); w.F2 = a.take<float>(bn * 256);
+    w.G1 = a.take<float>((size_t)bc * 256); w.G2 = a.take<float>((size_t)bc * 256);
+    w.X0 = a.take<float>(bn * 60 * 8); w.T32a = a.take<float>(bn * 60 * 32); w.T32b = a.take<float>(bn * 60 * 32);
+    w.T64 = a.take<float>(bn * 60 * 64);
+    w.M64 = a.take<float>(bn * 256); w.Q1 = a.take<float>(bn * 256); w.Q2 = a.take<float>(bn * 256);
+    w.PB1 = a.take<float>((size_t)bc * 512); w.PB2 = a.take<float>((size_t)bc * 512);
+    w.U1 = a.take<float>(bn * 512); w.U2 = a.take<float>(bn * 512);
+    w.H1 = a.take<float>(bn * 8 * 512); w.H2 = a.take<float>(bn * 8 * 512);
+    w.COST1 = a.take<float>(bn * 512);
+    w.PBM = a.take<float>((size_t)bc * 2048); w.P = a.take<float>(bn * 2048);
+    w.Y1 = a.take<float>(bn * 32 * 512); w.Y2 = a.take<float>(bn * 32 * 256); w.Y3 = a.take<float>(bn * 32 * 64);
+    w.PROP = a.take<float>(bn * 256); w.GP = a.take<float>((size_t)bc * 256);
+    w.GI = a.take<float>((size_t)bc * 768); w.GH = a.take<float>((size_t)bc * 768);
+    w.GNEW = a.take<float>((size_t)bc * 256); w.ZERO = a.take<float>((size_t)bc * 256);
+    w.PBH = a.take<float>((size_t)bc * 512);
+    w.HD1 = a.take<float>(bn * 512); w.HD2 = a.take<float>(bn * 256); w.HD3 = a.take<float>(bn * 128);
+    w.FLOW = a.take<float>(bn * 3);
+}
+
+}  // namespace
+
+struct cmf_model {
+    int temporal = 0;
+    float stat_thres = 0.5f;
+    float *d_blob = nullptr;
+    std::vector<const float *> seg;
+    std::vector<SegShape> shape;
+    char *ws = nullptr; size_t ws_bytes = 0; int cap_bc = 0, cap_n = 0;
+    Work w{};
+    // staging for the host entry point
+    float *d_in = nullptr, *d_out = nullptr; size_t d_in_floats = 0, d_out_bytes = 0;
+    int launches = 0;
+    int last_b = 0, last_n = 0;
+};
+
+static GemmArgs mk(const float *W, int ldw, const float *X, int ldx, float *Out, int ldo, const float *bias,
+                   int M, int K, long long cols, int act, const float *pbias = nullptr, int pb_ld = 0, int cpp = 1) {
+    GemmArgs g;
+    g.W = W; g.X = X; g.Out = Out; g.bias = bias; g.pbias = pbias;
+    g.ldw = ldw; g.ldx = ldx; g.ldo = ldo; g.pb_ld = pb_ld; g.cols_per_pair = cpp;
+    g.M = M; g.K = K; g.cols = (int)cols; g.act = act;
+    return g;
+}
+
+#define RUN(call)                    \
+    do {                             \
+        int rc_ = (call);            \
+        if (rc_ != CMF_OK) return rc_; \
+        ++m->launches;               \
+    } while (0)
+
+static size_t chunk_bytes(int bc, int n) {
+    Arena a; Work w;
+    carve(a, w, bc, n);
+    return a.off + 256;
+}
+
+static int ensure_workspace(cmf_model *m, int b, int n) {
+    // chunk size: as many pairs as fit a ~3 GiB arena (override with CMF_CHUNK_PAIRS), at most b
+    size_t budget = (size_t)3 << 30;
+    int bc = b;
+    const char *env = getenv("CMF_CHUNK_PAIRS");
+    if (env && atoi(env) > 0) bc = atoi(env) < b ? atoi(env) : b;
+    else {
+        const size_t per = chunk_bytes(1, n);
+        size_t fit = budget / per;
+        if (fit < 1) fit = 1;
+        if ((size_t)bc > fit) bc = (int)fit;
+    }
+    if (m->ws && m->cap_n == n && m->cap_bc >= bc) return CMF_OK;
+    if (m->ws && m->cap_n == n && m->cap_bc < bc && !env) { /* grow */ }
+    if (m->ws) { cudaFree(m->ws); m->ws = nullptr; }
+    const size_t bytes = chunk_bytes(bc, n);
+    cudaError_t e = cudaMalloc(&m->ws, bytes);
+    if (e != cudaSuccess) {
+        cmf_set_error("cmf_model: workspace cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        m->cap_bc = m->cap_n = 0; m->ws_bytes = 0;
+        return CMF_ERR_NOMEM;
+    }
+    m->ws_bytes = bytes; m->cap_bc = bc; m->cap_n = n;
+    Arena a; a.base = m->ws;
+    carve(a, m->w, bc, n);
+    CMF_CUDA(cudaMemset(m->w.ZERO, 0, (size_t)bc * 256 * sizeof(float)));
+    return CMF_OK;
+}
+
+// set-conv over a small-channel cloud (mse_layer, C=3): PointLocalFeature x 4 scales (radarflow_util.py:144-162)
+static int run_mse_layer(cmf_model *m, int bc, int n, const float *pc, const float *ft, const int *bq,
+                         float *dest, int ldd, float *G, cudaStream_t st) {
+    Work &w = m->w;
+    const long long bn = (long long)bc * n;
+    RUN(cmf_launch_build_x0(bc, n, pc, ft, bq, w.X0, st));
+    GemmBatch gb;
+    gb.count = 4;
+    for (int s = 0; s < 4; ++s) {
+        const int sb = M1_BASE + s * 12;
+        gb.g[s] = mk(m->seg[sb + 0], 8, w.X0 + (size_t)bn * KOFF[s] * 8, 8, w.T32a + (size_t)bn * KOFF[s] * 32, 32,
+                     m->seg[sb + 1], 32, 8, bn * KS[s], CMF_ACT_RELU);
+    }
+    RUN(cmf_launch_gemm(gb, st));
+    for (int s = 0; s < 4; ++s) {
+        const int sb = M1_BASE + s * 12;
+        gb.g[s] = mk(m->seg[sb + 2], 32, w.T32a + (size_t)bn * KOFF[s] * 32, 32, w.T32b + (size_t)bn * KOFF[s] * 32, 32,
+                     m->seg[sb + 3], 32, 32, bn * KS[s], CMF_ACT_RELU);
+    }
+    RUN(cmf_launch_gemm(gb, st));
+    for (int s = 0; s < 4; ++s) {
+        const int sb = M1_BASE + s * 12;
+        gb.g[s] = mk(m->seg[sb + 4], 32, w.T32b + (size_t)bn * KOFF[s] * 32, 32, w.T64 + (size_t)bn * KOFF[s] * 64, 64,
+                     m->seg[sb + 5], 64, 32, bn * KS[s], CMF_ACT_RELU);
+    }
+    RUN(cmf_launch_gemm(gb, st));
+    for (int s = 0; s < 4; ++s)
+        RUN(cmf_launch_maxk(bn, KS[s], 64, w.T64 + (size_t)bn * KOFF[s] * 64, 64, w.M64 + s * 64, 256, st));
+    const float *src[3] = {w.M64, w.Q1, w.Q2};
+    float *dst[3] = {w.Q1, w.Q2, dest};
+    const int lds[3] = {256, 256, 256}, ldo[3] = {256, 256, ldd};
+    for (int l = 0; l < 3; ++l) {
+        for (int s = 0; s < 4; ++s) {
+            const int sb = M1_BASE + s * 12 + 6 + l * 2;
+            gb.g[s] = mk(m->seg[sb], 64, src[l] + s * 64, lds[l], dst[l] + s * 64, ldo[l], m->seg[sb + 1], 64, 64, bn, CMF_ACT_RELU);
+        }
+        RUN(cmf_launch_gemm(gb, st));
+    }
+    RUN(cmf_launch_globalmax(bc, n, 256, dest, ldd, G, st));
+    return CMF_OK;
+}
+
+static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const float *pc2, const float *ft1,
+                         const float *ft2, const float *gprev, float *sf_agg, float *stat_cls, float *pre_trans,
+                         uint8_t *mask, float *gfeat_out, cudaStream_t st) {
+    Work &w = m->w;
+    const long long bn = (long long)bc * n;
+    auto S = [&](int i) { return m->seg[i]; };
+
+    // neighbour search
+    RUN(cmf_launch_transpose3(bc, n, pc1, w.X1T, st));
+    RUN(cmf_launch_transpose3(bc, n, pc2, w.X2T, st));
+    RUN(cmf_launch_ball_query_ms(bc, n, pc1, w.BQ1, st));
+    RUN(cmf_launch_ball_query_ms(bc, n, pc2, w.BQ2, st));
+    RUN(cmf_launch_knn_point8(bc, n, w.X2T, w.X1T, w.KNN12, st));
+    RUN(cmf_launch_knn_point8(bc, n, w.X1T, w.X1T, w.KNN11, st));
+
+    // multi-scale encoders (cmflow.py:72-77); cloud 1 writes straight into the embedding rows E[:, 0:256]
+    { int rc = run_mse_layer(m, bc, n, pc1, ft1, w.BQ1, w.E, E_LD, w.G1, st); if (rc) return rc; }
+    { int rc = run_mse_layer(m, bc, n, pc2, ft2, w.BQ2, w.F2, 256, w.G2, st); if (rc) return rc; }
+    RUN(cmf_launch_scatter_ft(bc, n, ft1, w.E, E_LD, 768, 5, st));
+
+    // flow embedding (FeatureCorrelator, radarflow_util.py:185-237)
+    RUN(cmf_launch_gemm1(mk(S(FC_WCG), 256, w.G1, 256, w.PB1, 512, S(FC_B1), 512, 256, bc, CMF_ACT_NONE), st));
+    RUN(cmf_launch_gemm1(mk(S(FC_WNG), 256, w.G2, 256, w.PB2, 512, nullptr, 512, 256, bc, CMF_ACT_NONE), st));
+    RUN(cmf_launch_gemm1(mk(S(FC_WC), 256, w.E, E_LD, w.U1, 512, nullptr, 512, 256, bn, CMF_ACT_NONE, w.PB1, 512, n), st));
+    RUN(cmf_launch_gemm1(mk(S(FC_WN), 256, w.F2, 256, w.U2, 512, nullptr, 512, 256, bn, CMF_ACT_NONE, w.PB2, 512, n), st));
+    RUN(cmf_launch_fc_build_h1(bc, n, pc1, pc2, w.KNN12, w.U1, w.U2, S(FC_WD), w.H1, st));
+    RUN(cmf_launch_gemm1(mk(S(FC_W2), 512, w.H1, 512, w.H2, 512, S(FC_B2), 512, 512, bn * 8, CMF_ACT_LEAKY), st));
+    RUN(cmf_launch_gemm1(mk(S(FC_W3), 512, w.H2, 512, w.H1, 512, S(FC_B3), 512, 512, bn * 8, CMF_ACT_LEAKY), st));
+    WeightNetP wn1{S(WN1_BASE), S(WN1_BASE + 1), S(WN1_BASE + 2), S(WN1_BASE + 3), S(WN1_BASE + 4), S(WN1_BASE + 5)};
+    WeightNetP wn2{S(WN2_BASE), S(WN2_BASE + 1), S(WN2_BASE + 2), S(WN2_BASE + 3), S(WN2_BASE + 4), S(WN2_BASE + 5)};
+    RUN(cmf_launch_fc_reduce(bc, n, pc1, pc2, w.KNN12, wn1, w.H1, 0, w.COST1, 512, st));
+    RUN(cmf_launch_fc_reduce(bc, n, pc1, pc1, w.KNN11, wn2, w.COST1, 1, w.E + 256, E_LD, st));
+
+    // set-conv #2 (mse_layer2, cmflow.py:87-89)
+    RUN(cmf_launch_gemm1(mk(S(M2_WG), 256, w.G1, 256, w.PBM, 2048, S(M2_T1), 2048, 256, bc, CMF_ACT_NONE), st));
+    RUN(cmf_launch_gemm1(mk(S(M2_WP), E_LD, w.E, E_LD, w.P, 2048, nullptr, 2048, E_LD, bn, CMF_ACT_NONE, w.PBM, 2048, n), st));
+    for (int s = 0; s < 4; ++s) {
+        const int sb = M2_BASE + s * 10;
+        RUN(cmf_launch_mse2_build_y1(bc, n, KS[s], KOFF[s], pc1, w.BQ1, w.P, 2048, s * 512, S(M2_WX) + (size_t)s * 512 * 4, w.Y1, st));
+        RUN(cmf_launch_gemm1(mk(S(sb), 512, w.Y1, 512, w.Y2, 256, S(sb + 1), 256, 512, bn * KS[s], CMF_ACT_RELU), st));
+        RUN(cmf_launch_gemm1(mk(S(sb + 2), 256, w.Y2, 256, w.Y3, 64, S(sb + 3), 64, 256, bn * KS[s], CMF_ACT_RELU), st));
+        RUN(cmf_launch_maxk(bn, KS[s], 64, w.Y3, 64, w.M64 + s * 64, 256, st));
+    }
+    {
+        GemmBatch gb; gb.count = 4;
+        const float *src[3] = {w.M64, w.Q1, w.Q2};
+        float *dst[3] = {w.Q1, w.Q2, w.PROP};
+        for (int l = 0; l < 3; ++l) {
+            for (int s = 0; s < 4; ++s) {
+                const int sb = M2_BASE + s * 10 + 4 + l * 2;
+                gb.g[s] = mk(S(sb), 64, src[l] + s * 64, 256, dst[l] + s * 64, 256, S(sb + 1), 64, 64, bn, CMF_ACT_RELU);
+            }
+            RUN(cmf_launch_gemm(gb, st));
+        }
+    }
+    RUN(cmf_launch_globalmax(bc, n, 256, w.PROP, 256, w.GP, st));
+    const float *gvec = w.GP;
+    if (m->temporal) {            // CMFlow-T: GRU over the global feature (cmflow_t.py:94-105)
+        RUN(cmf_launch_gemm1(mk(S(GRU_WIH), 256, w.GP, 256, w.GI, 768, S(GRU_BIH), 768, 256, bc, CMF_ACT_NONE), st));
+        RUN(cmf_launch_gemm1(mk(S(GRU_WHH), 256, gprev ? gprev : w.ZERO, 256, w.GH, 768, S(GRU_BHH), 768, 256, bc, CMF_ACT_NONE), st));
+        float *gnew = gfeat_out ? gfeat_out : w.GNEW;
+        RUN(cmf_launch_gru_gates(bc, w.GI, w.GH, gprev, gnew, st));
+        gvec = gnew;
+    }
+
+    // heads (FlowHead / MotionHead, radarflow_util.py:240-285), first layer stacked [fp ; mp]
+    RUN(cmf_launch_gemm1(mk(S(HD_W1G), 256, gvec, 256, w.PBH, 512, S(HD_T1), 512, 256, bc, CMF_ACT_NONE), st));
+    RUN(cmf_launch_gemm1(mk(S(HD_W1), 256, w.PROP, 256, w.HD1, 512, nullptr, 512, 256, bn, CMF_ACT_RELU, w.PBH, 512, n), st));
+    {
+        GemmBatch gb; gb.count = 2;
+        gb.g[0] = mk(S(HD_W2F), 256, w.HD1, 512, w.HD2, 256, S(HD_T2F), 128, 256, bn, CMF_ACT_RELU);
+        gb.g[1] = mk(S(HD_W2M), 256, w.HD1 + 256, 512, w.HD2 + 128, 256, S(HD_T2M), 128, 256, bn, CMF_ACT_RELU);
+        RUN(cmf_launch_gemm(gb, st));
+        gb.g[0] = mk(S(HD_W3F), 128, w.HD2, 256, w.HD3, 128, S(HD_T3F), 64, 128, bn, CMF_ACT_RELU);
+        gb.g[1] = mk(S(HD_W3M), 128, w.HD2 + 128, 256, w.HD3 + 64, 128, S(HD_T3M), 64, 128, bn, CMF_ACT_RELU);
+        RUN(cmf_launch_gemm(gb, st));
+    }
+    RUN(cmf_launch_head_final(bc, n, w.HD3, 128, S(HD_W4), S(HD_W4) + 192, w.FLOW, stat_cls, st));
+    // ego-motion head + refinement (cmflow.py:96-125); CMFlow-T omits the +1e-4 (cmflow_t.py:119)
+    RUN(cmf_launch_kabsch(bc, n, pc1, w.FLOW, 1, stat_cls, 1, m->temporal ? 0.f : 1e-4f, m->stat_thres, pre_trans, sf_agg, mask, st));
+    return CMF_OK;
+}
+
+extern "C" size_t cmf_model_blob_floats(int temporal) {
+    size_t tot = HDR;
+    for (const SegShape &s : expected_shapes(temporal)) tot += pad4((size_t)s.rows * s.cols);
+    return tot;
+}
+
+extern "C" int cmf_model_create(cmf_model **out, const float *blob, size_t blob_floats, int temporal, float stat_thres) {
+    CMF_REQUIRE(out && blob, "null pointer");
+    *out = nullptr;
+    if (cmf_device_check() != CMF_OK) return CMF_ERR_STATE;
+    const int *hdr = reinterpret_cast<const int *>(blob);
+    const std::vector<SegShape> exp = expected_shapes(temporal);
+    CMF_REQUIRE(blob_floats == cmf_model_blob_floats(temporal), "blob size does not match cmf_model_blob_floats()");
+    CMF_REQUIRE(hdr[0] == MAGIC, "bad blob magic");
+    CMF_REQUIRE(hdr[1] == (int)exp.size() && hdr[2] == (temporal ? 1 : 0), "blob segment count / model kind mismatch");
+    cmf_model *m = new cmf_model();
+    m->temporal = temporal ? 1 : 0;
+    m->stat_thres = stat_thres;
+    cudaError_t e = cudaMalloc(&m->d_blob, blob_floats * sizeof(float));
+    if (e != cudaSuccess) { delete m; cmf_set_error("cmf_model_create: cudaMalloc failed: %s", cudaGetErrorString(e)); return CMF_ERR_NOMEM; }
+    e = cudaMemcpy(m->d_blob, blob, blob_floats * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(m->d_blob); delete m; cmf_set_error("cmf_model_create: cudaMemcpy failed: %s", cudaGetErrorString(e)); return CMF_ERR_CUDA; }
+    size_t off = HDR;
+    for (size_t i = 0; i < exp.size(); ++i) {
+        const int so = hdr[3 + 3 * i], sr = hdr[4 + 3 * i], sc = hdr[5 + 3 * i];
+        if ((size_t)so != off || sr != exp[i].rows || sc != exp[i].cols) {
+            cmf_set_error("cmf_model_create: segment %zu is (off %d, %dx%d), expected (off %zu, %dx%d)", i, so, sr, sc, off, exp[i].rows, exp[i].cols);
+            cudaFree(m->d_blob); delete m;
+            return CMF_ERR_INVALID;
+        }
+        m->seg.push_back(m->d_blob + off);
+        off += pad4((size_t)sr * sc);
+    }
+    m->shape = exp;
+    *out = m;
+    return CMF_OK;
+}
+
+extern "C" void cmf_model_destroy(cmf_model *m) {
+    if (!m) return;
+    if (m->ws) cudaFree(m->ws);
+    if (m->d_blob) cudaFree(m->d_blob);
+    if (m->d_in) cudaFree(m->d_in);
+    if (m->d_out) cudaFree(m->d_out);
+    delete m;
+}
+
+extern "C" size_t cmf_model_workspace_bytes(const cmf_model *m) { return m ? m->ws_bytes : 0; }
+extern "C" int cmf_model_launches_per_forward(const cmf_model *m) { return m ? m->launches : 0; }
+
+extern "C" int cmf_model_forward(cmf_model *m, int b, int n, const float *pc1, const float *pc2, const float *ft1,
+                                 const float *ft2, const float *gfeat_prev, float *sf_agg, float *stat_cls,
+                                 float *pre_trans, uint8_t *mask, float *gfeat_out, void *stream) {
+    CMF_REQUIRE(m, "null model");
+    CMF_REQUIRE(b >= 0 && n >= 0, "negative size");
+    if (b == 0) return CMF_OK;
+    CMF_REQUIRE(n >= 8, "need at least 8 points per cloud (knn_point(8, ...): torch.topk raises below that)");
+    CMF_REQUIRE((long long)n * 32 * 512 < 2147483647LL / 2, "N too large for 32-bit column indices");
+    CMF_REQUIRE(pc1 && pc2 && ft1 && ft2 && sf_agg && stat_cls && pre_trans && mask, "null pointer");
+    CMF_REQUIRE(!m->temporal || gfeat_out, "CMFlow-T needs gfeat_out");
+    int rc = ensure_workspace(m, b, n);
+    if (rc != CMF_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    m->launches = 0;
+    m->last_b = b < m->cap_bc ? b : m->cap_bc; m->last_n = n;
+    const size_t pn = (size_t)3 * n;
+    for (int b0 = 0; b0 < b; b0 += m->cap_bc) {
+        const int bc = (b - b0) < m->cap_bc ? (b - b0) : m->cap_bc;
+        rc = forward_chunk(m, bc, n, pc1 + b0 * pn, pc2 + b0 * pn, ft1 + b0 * pn, ft2 + b0 * pn,
+                           gfeat_prev ? gfeat_prev + (size_t)b0 * 256 : nullptr,
+                           sf_agg + b0 * pn, stat_cls + (size_t)b0 * n, pre_trans + (size_t)b0 * 16, mask + (size_t)b0 * n,
+                           gfeat_out ? gfeat_out + (size_t)b0 * 256 : nullptr, st);
+        if (rc != CMF_OK) return rc;
+    }
+    return CMF_OK;
+}
+
+extern "C" int cmf_model_forward_host(cmf_model *m, int b, int n, const float *pc1, const float *pc2, const float *ft1,
+                                      const float *ft2, const float *gfeat_prev, float *sf_agg, float *stat_cls,
+                                      float *pre_trans, uint8_t *mask, float *gfeat_out, void *stream) {
+    CMF_REQUIRE(m, "null model");
+    CMF_REQUIRE(b >= 0 && n >= 0, "negative size");
+    if (b == 0) return CMF_OK;
+    CMF_REQUIRE(pc1 && pc2 && ft1 && ft2 && sf_agg && stat_cls && pre_trans && mask, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t pn = (size_t)b * 3 * n;
+    const size_t in_floats = 4 * pn + (size_t)b * 256;
+    const size_t out_bytes = (pn + (size_t)b * n + (size_t)b * 16 + (size_t)b * 256) * sizeof(float) + (size_t)b * n;
+    if (m->d_in_floats < in_floats) {
+        if (m->d_in) cudaFree(m->d_in);
+        m->d_in = nullptr; m->d_in_floats = 0;
+        CMF_CUDA(cudaMalloc(&m->d_in, in_floats * sizeof(float)));
+        m->d_in_floats = in_floats;
+    }
+    if (m->d_out_bytes < out_bytes) {
+        if (m->d_out) cudaFree(m->d_out);
+        m->d_out = nullptr; m->d_out_bytes = 0;
+        CMF_CUDA(cudaMalloc(&m->d_out, out_bytes));
+        m->d_out_bytes = out_bytes;
+    }
+    float *d_pc1 = m->d_in, *d_pc2 = d_pc1 + pn, *d_ft1 = d_pc2 + pn, *d_ft2 = d_ft1 + pn, *d_g = d_ft2 + pn;
+    float *d_sf = m->d_out, *d_cls = d_sf + pn, *d_tr = d_cls + (size_t)b * n, *d_go = d_tr + (size_t)b * 16;
+    uint8_t *d_mask = reinterpret_cast<uint8_t *>(d_go + (size_t)b * 256);
+    CMF_CUDA(cudaMemcpyAsync(d_pc1, pc1, pn * sizeof(float), cudaMemcpyHostToDevice, st));
+    CMF_CUDA(cudaMemcpyAsync(d_pc2, pc2, pn * sizeof(float), cudaMemcpyHostToDevice, st));
+    CMF_CUDA(cudaMemcpyAsync(d_ft1, ft1, pn * sizeof(float), cudaMemcpyHostToDevice, st));
+    CMF_CUDA(cudaMemcpyAsync(d_ft2, ft2, pn * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (gfeat_prev) CMF_CUDA(cudaMemcpyAsync(d_g, gfeat_prev, (size_t)b * 256 * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = cmf_model_forward(m, b, n, d_pc1, d_pc2, d_ft1, d_ft2, gfeat_prev ? d_g : nullptr, d_sf, d_cls, d_tr, d_mask, d_go, st);
+    if (rc != CMF_OK) return rc;
+    CMF_CUDA(cudaMemcpyAsync(sf_agg, d_sf, pn * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CMF_CUDA(cudaMemcpyAsync(stat_cls, d_cls, (size_t)b * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CMF_CUDA(cudaMemcpyAsync(pre_trans, d_tr, (size_t)b * 16 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CMF_CUDA(cudaMemcpyAsync(mask, d_mask, (size_t)b * n, cudaMemcpyDeviceToHost, st));
+    if (m->temporal && gfeat_out) CMF_CUDA(cudaMemcpyAsync(gfeat_out, d_go, (size_t)b * 256 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CMF_CUDA(cudaStreamSynchronize(st));
+    return CMF_OK;
+}
+
+extern "C" const void *cmf_model_tap(const cmf_model *m, const char *name) {
+    if (!m || !m->ws || !name) return nullptr;
+    const Work &w = m->w;
+    struct { const char *n; const void *p; } tab[] = {
+        {"E", w.E}, {"f2", w.F2}, {"g1", w.G1}, {"g2", w.G2}, {"prop", w.PROP}, {"flow", w.FLOW},
+        {"bq1", w.BQ1}, {"bq2", w.BQ2}, {"knn12", w.KNN12}, {"knn11", w.KNN11}, {"gp", w.GP}, {"P", w.P},
+        {"cost1", w.COST1}, {"u1", w.U1}, {"u2", w.U2}, {"hd3", w.HD3}};
+    for (auto &t : tab)
+        if (!strcmp(t.n, name)) return t.p;
+    return nullptr;
+}

@@ -1,0 +1,679 @@
+// model_kernels.cu -- model-path kernels of the strict-fp32 pipeline (see DESIGN.md "Pipeline").
+//
+// Everything here is exact-fp32 (FMA) arithmetic; this is the parity build of the hot path.  The big
+// 1x1-conv stacks go through one generic NT GEMM (activations are kept POINT-MAJOR, i.e. one row of C
+// contiguous channels per point, so a neighbour gather is one coalesced 2 KB row read and GEMM outputs
+// chain without transposes).
+#include <float.h>
+#include <limits.h>
+#include <math.h>
+
+#include "model_kernels.cuh"
+
+// =================================================================================================
+// Generic fp32 NT GEMM: Out[c][m] = act(sum_k W[m][k] X[c][k] + bias[m] + pbias[pair(c)][m])
+// 256 threads, BM x 128 tile, BK = 16, 2-stage smem ring with register prefetch; thread (tm,tc) owns
+// rows {tm*4..+3, 64+tm*4..+3} x cols {tc*4..+3, 64+tc*4..+3} (split-4 layout: conflict-free LDS.128,
+// 256-byte coalesced stores along m).
+// =================================================================================================
+constexpr int G_BN = 128;
+constexpr int G_BK = 16;
+
+template <int BM>
+__global__ void __launch_bounds__(256)
+gemm_nt_kernel(const GemmBatch gb) {
+    const GemmArgs &g = gb.g[blockIdx.z];
+    const int m0 = blockIdx.y * BM;
+    const int c0 = blockIdx.x * G_BN;
+    if (m0 >= g.M || c0 >= g.cols) return;
+    constexpr int TMG = BM / 64;                  // groups of 4 rows per thread (2 for BM=128, 1 for BM=64)
+    constexpr int TM = TMG * 4;
+    __shared__ __align__(16) float As[2][G_BK][BM + 4];
+    __shared__ __align__(16) float Bs[2][G_BK][G_BN + 4];
+
+    const int tid = threadIdx.x;
+    const int tm = tid & 15, tc = tid >> 4;
+    const int lrow = tid >> 2, lkq = (tid & 3) * 4;     // loader mapping: 64 rows x 4 k-quads per pass
+
+    float acc[TM][8];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    const int ktiles = (g.K + G_BK - 1) / G_BK;
+    float4 ra[TMG], rb[2];
+
+    auto gload = [&](int kt) {
+        const int k = kt * G_BK + lkq;
+        const bool kok = k < g.K;
+#pragma unroll
+        for (int r = 0; r < TMG; ++r) {
+            const int m = m0 + lrow + 64 * r;
+            ra[r] = (kok && m < g.M) ? __ldg(reinterpret_cast<const float4 *>(g.W + (size_t)m * g.ldw + k))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int c = c0 + lrow + 64 * r;
+            rb[r] = (kok && c < g.cols) ? __ldg(reinterpret_cast<const float4 *>(g.X + (size_t)c * g.ldx + k))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int r = 0; r < TMG; ++r) {
+            As[buf][lkq + 0][lrow + 64 * r] = ra[r].x; As[buf][lkq + 1][lrow + 64 * r] = ra[r].y;
+            As[buf][lkq + 2][lrow + 64 * r] = ra[r].z; As[buf][lkq + 3][lrow + 64 * r] = ra[r].w;
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            Bs[buf][lkq + 0][lrow + 64 * r] = rb[r].x; Bs[buf][lkq + 1][lrow + 64 * r] = rb[r].y;
+            Bs[buf][lkq + 2][lrow + 64 * r] = rb[r].z; Bs[buf][lkq + 3][lrow + 64 * r] = rb[r].w;
+        }
+    };
+
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (int kt = 0; kt < ktiles; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < ktiles) gload(kt + 1);
+#pragma unroll
+        for (int k = 0; k < G_BK; ++k) {
+            float a[TM], b[8];
+#pragma unroll
+            for (int r = 0; r < TMG; ++r) {
+                const float4 v = *reinterpret_cast<const float4 *>(&As[buf][k][tm * 4 + 64 * r]);
+                a[r * 4 + 0] = v.x; a[r * 4 + 1] = v.y; a[r * 4 + 2] = v.z; a[r * 4 + 3] = v.w;
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const float4 v = *reinterpret_cast<const float4 *>(&Bs[buf][k][tc * 4 + 64 * r]);
+                b[r * 4 + 0] = v.x; b[r * 4 + 1] = v.y; b[r * 4 + 2] = v.z; b[r * 4 + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (kt + 1 < ktiles) sstore(buf ^ 1);
+        __syncthreads();
+    }
+
+    // epilogue
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = c0 + (j < 4 ? tc * 4 + j : 64 + tc * 4 + (j - 4));
+        if (c >= g.cols) continue;
+        const float *pb = g.pbias ? g.pbias + (size_t)(c / g.cols_per_pair) * g.pb_ld : nullptr;
+#pragma unroll
+        for (int r = 0; r < TMG; ++r) {
+            const int m = m0 + 64 * r + tm * 4;
+            if (m >= g.M) continue;
+            float4 v = make_float4(acc[r * 4 + 0][j], acc[r * 4 + 1][j], acc[r * 4 + 2][j], acc[r * 4 + 3][j]);
+            if (g.bias) {
+                const float4 bb = __ldg(reinterpret_cast<const float4 *>(g.bias + m));
+                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+            }
+            if (pb) {
+                const float4 bb = __ldg(reinterpret_cast<const float4 *>(pb + m));
+                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+            }
+            if (g.act == CMF_ACT_RELU) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            } else if (g.act == CMF_ACT_LEAKY) {
+                v.x = v.x > 0.f ? v.x : 0.1f * v.x; v.y = v.y > 0.f ? v.y : 0.1f * v.y;
+                v.z = v.z > 0.f ? v.z : 0.1f * v.z; v.w = v.w > 0.f ? v.w : 0.1f * v.w;
+            }
+            *reinterpret_cast<float4 *>(g.Out + (size_t)c * g.ldo + m) = v;
+        }
+    }
+}
+
+int cmf_launch_gemm(const GemmBatch &gb, cudaStream_t st) {
+    int maxM = 0, maxC = 0;
+    for (int i = 0; i < gb.count; ++i) {
+        const GemmArgs &g = gb.g[i];
+        if ((g.K & 3) || (g.ldw & 3) || (g.ldx & 3) || (g.ldo & 3) || (g.M & 3)) {
+            cmf_set_error("gemm: K/ld/M must be multiples of 4 (K=%d ldw=%d ldx=%d ldo=%d M=%d)", g.K, g.ldw, g.ldx, g.ldo, g.M);
+            return CMF_ERR_INVALID;
+        }
+        if (g.M > maxM) maxM = g.M;
+        if (g.cols > maxC) maxC = g.cols;
+    }
+    if (maxM == 0 || maxC == 0) return CMF_OK;
+    if (maxM <= 64) {
+        dim3 grid(cmf_divup(maxC, G_BN), cmf_divup(maxM, 64), gb.count);
+        gemm_nt_kernel<64><<<grid, 256, 0, st>>>(gb);
+    } else {
+        dim3 grid(cmf_divup(maxC, G_BN), cmf_divup(maxM, 128), gb.count);
+        gemm_nt_kernel<128><<<grid, 256, 0, st>>>(gb);
+    }
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
+int cmf_launch_gemm1(const GemmArgs &g, cudaStream_t st) {
+    GemmBatch gb;
+    gb.g[0] = g;
+    gb.count = 1;
+    return cmf_launch_gemm(gb, st);
+}
+
+// =================================================================================================
+// small layout kernels
+// =================================================================================================
+__global__ void transpose3_kernel(int n, const float *__restrict__ planar, float *__restrict__ aos) {
+    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *p = planar + (size_t)b * 3 * n;
+    float *o = aos + ((size_t)b * n + i) * 3;
+    o[0] = __ldg(p + i); o[1] = __ldg(p + n + i); o[2] = __ldg(p + 2 * n + i);
+}
+int cmf_launch_transpose3(int b, int n, const float *planar, float *aos, cudaStream_t st) {
+    transpose3_kernel<<<dim3(cmf_divup(n, 256), b), 256, 0, st>>>(n, planar, aos);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
+// ---- multi-radius ball query: one pass over the candidates for all four CMFlow scales -------------
+// (models/cmflow.py:21-22; semantics per scale = lib/src/ball_query_gpu.cu:9-45)
+constexpr int MS_CHUNK = 2048;
+constexpr int MS_QPW = 2;
+__constant__ float c_ms_r2[4] = {4.0f, 16.0f, 64.0f, 256.0f};     // radius*radius for 2,4,8,16 (exact in fp32)
+
+__global__ void __launch_bounds__(256)
+ball_query_ms_kernel(int n, const float *__restrict__ xyz, int *__restrict__ idx60) {
+    __shared__ float sx[MS_CHUNK], sy[MS_CHUNK], sz[MS_CHUNK];
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const float *px = xyz + (size_t)b * 3 * n, *py = px + n, *pz = py + n;
+    const int q0 = (blockIdx.x * 8 + warp) * MS_QPW;
+    constexpr int KS[4] = {4, 8, 16, 32};
+    constexpr int OFF[4] = {0, 4, 12, 28};
+    float qx[MS_QPW], qy[MS_QPW], qz[MS_QPW];
+    int cnt[MS_QPW][4], first[MS_QPW][4];
+    bool all_done = true;
+#pragma unroll
+    for (int t = 0; t < MS_QPW; ++t) {
+        const int q = q0 + t;
+        const bool valid = q < n;
+        qx[t] = __ldg(px + (valid ? q : 0)); qy[t] = __ldg(py + (valid ? q : 0)); qz[t] = __ldg(pz + (valid ? q : 0));
+#pragma unroll
+        for (int s = 0; s < 4; ++s) { cnt[t][s] = valid ? 0 : KS[s]; first[t][s] = -1; }
+        all_done = all_done && !valid;
+    }
+    for (int base = 0; base < n; base += MS_CHUNK) {
+        if (__syncthreads_and(all_done)) break;
+        const int cn = min(MS_CHUNK, n - base);
+        for (int i = threadIdx.x; i < cn; i += blockDim.x) {
+            sx[i] = __ldg(px + base + i); sy[i] = __ldg(py + base + i); sz[i] = __ldg(pz + base + i);
+        }
+        __syncthreads();
+        if (all_done) continue;
+        for (int j = 0; j < cn; j += 32) {
+            const int k = j + lane;
+            const bool in = k < cn;
+            const float cx = in ? sx[k] : 0.f, cy = in ? sy[k] : 0.f, cz = in ? sz[k] : 0.f;
+            bool any_open = false;
+#pragma unroll
+            for (int t = 0; t < MS_QPW; ++t) {
+                const float d2 = cmf_sqdist_ref(qx[t], qy[t], qz[t], cx, cy, cz);
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    if (cnt[t][s] >= KS[s]) continue;               // warp-uniform
+                    const bool hit = in && (d2 < c_ms_r2[s]);
+                    const unsigned mask = __ballot_sync(0xffffffffu, hit);
+                    if (mask) {
+                        if (first[t][s] < 0) first[t][s] = base + j + __ffs(mask) - 1;
+                        const int pos = cnt[t][s] + __popc(mask & lt);
+                        if (hit && pos < KS[s]) idx60[((size_t)b * n + q0 + t) * 60 + OFF[s] + pos] = base + k;
+                        cnt[t][s] += __popc(mask);
+                    }
+                    any_open = any_open || (cnt[t][s] < KS[s]);
+                }
+            }
+            if (!any_open) { all_done = true; break; }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < MS_QPW; ++t) {
+        if (q0 + t >= n) continue;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            int *row = idx60 + ((size_t)b * n + q0 + t) * 60 + OFF[s];
+            // a cloud queried against itself always hits itself, but keep the reference's "no hit -> 0" rule
+            const int fill = first[t][s] >= 0 ? first[t][s] : 0;
+            const int from = first[t][s] >= 0 ? cnt[t][s] : 0;
+            for (int l = from + lane; l < KS[s]; l += 32) row[l] = fill;
+        }
+    }
+}
+int cmf_launch_ball_query_ms(int b, int n, const float *xyz_planar, int *idx60, cudaStream_t st) {
+    ball_query_ms_kernel<<<dim3(cmf_divup(n, 8 * MS_QPW), b), 256, 0, st>>>(n, xyz_planar, idx60);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+extern "C" int cmf_ball_query_ms(int b, int n, const float *xyz_planar, int *idx60, void *stream) {
+    CMF_REQUIRE(b >= 0 && n >= 0, "negative size");
+    if (b == 0 || n == 0) return CMF_OK;
+    CMF_REQUIRE(xyz_planar && idx60, "null pointer");
+    CMF_REQUIRE(b <= 65535, "batch > 65535");
+    return cmf_launch_ball_query_ms(b, n, xyz_planar, idx60, (cudaStream_t)stream);
+}
+
+int cmf_launch_knn_point8(int b, int n, const float *cand_aos, const float *query_aos, int *idx, cudaStream_t st) {
+    return cmf_knn_point(b, n, n, 8, cand_aos, query_aos, idx, nullptr, (void *)st);
+}
+
+// ---- mse_layer (C=3) input rows -----------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+build_x0_kernel(int bn_total, int n, const float *__restrict__ xyz, const float *__restrict__ ft,
+                const int *__restrict__ idx60, float *__restrict__ x0) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)bn_total * 60) return;
+    const int slot = (int)(t % 60);
+    const int bi = (int)(t / 60);
+    const int b = bi / n, i = bi - b * n;
+    const int s = slot < 4 ? 0 : (slot < 12 ? 1 : (slot < 28 ? 2 : 3));
+    const int off = s == 0 ? 0 : (s == 1 ? 4 : (s == 2 ? 12 : 28));
+    const int K = 4 << s;
+    const int kk = slot - off;
+    const int j = __ldg(idx60 + (size_t)bi * 60 + slot);
+    const float *px = xyz + (size_t)b * 3 * n, *pf = ft + (size_t)b * 3 * n;
+    float4 v0, v1;
+    v0.x = __fsub_rn(__ldg(px + j), __ldg(px + i));
+    v0.y = __fsub_rn(__ldg(px + n + j), __ldg(px + n + i));
+    v0.z = __fsub_rn(__ldg(px + 2 * n + j), __ldg(px + 2 * n + i));
+    v0.w = __ldg(pf + j);
+    v1.x = __ldg(pf + n + j); v1.y = __ldg(pf + 2 * n + j); v1.z = 0.f; v1.w = 0.f;
+    float *row = x0 + ((size_t)bn_total * off + (size_t)bi * K + kk) * 8;
+    reinterpret_cast<float4 *>(row)[0] = v0;
+    reinterpret_cast<float4 *>(row)[1] = v1;
+}
+int cmf_launch_build_x0(int b, int n, const float *xyz_planar, const float *ft_planar, const int *idx60,
+                        float *x0, cudaStream_t st) {
+    const long long tot = (long long)b * n * 60;
+    build_x0_kernel<<<cmf_divup(tot, 256), 256, 0, st>>>(b * n, n, xyz_planar, ft_planar, idx60, x0);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
+__global__ void __launch_bounds__(256)
+maxk_kernel(long long points, int K, int C4, const float *__restrict__ Y, int ldy, float *__restrict__ out, int ldo) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= points * C4) return;
+    const int c4 = (int)(t % C4);
+    const long long p = t / C4;
+    const float *src = Y + (size_t)p * K * ldy + c4 * 4;
+    float4 m = __ldg(reinterpret_cast<const float4 *>(src));
+    for (int kk = 1; kk < K; ++kk) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(src + (size_t)kk * ldy));
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+    *reinterpret_cast<float4 *>(out + (size_t)p * ldo + c4 * 4) = m;
+}
+int cmf_launch_maxk(long long points, int K, int C, const float *Y, int ldy, float *out, int ldo, cudaStream_t st) {
+    maxk_kernel<<<cmf_divup(points * (C / 4), 256), 256, 0, st>>>(points, K, C / 4, Y, ldy, out, ldo);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
+__global__ void __launch_bounds__(256)
+globalmax_kernel(int n, int C, const float *__restrict__ F, int ldf, float *__restrict__ G) {
+    __shared__ float red[4][64];
+    const int b = blockIdx.x, c = blockIdx.y * 64 + (threadIdx.x & 63), rg = threadIdx.x >> 6;
+    float m = -FLT_MAX;
+    if (c < C)
+        for (int i = rg; i < n; i += 4) m = fmaxf(m, __ldg(F + ((size_t)b * n + i) * ldf + c));
+    red[rg][threadIdx.x & 63] = m;
+    __syncthreads();
+    if (rg == 0 && c < C) G[(size_t)b * C + c] = fmaxf(fmaxf(red[0][threadIdx.x], red[1][threadIdx.x]), fmaxf(red[2][threadIdx.x], red[3][threadIdx.x]));
+}
+int cmf_launch_globalmax(int b, int n, int C, const float *F, int ldf, float *G, cudaStream_t st) {
+    globalmax_kernel<<<dim3(b, cmf_divup(C, 64)), 256, 0, st>>>(n, C, F, ldf, G);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
+__global__ void scatter_ft_kernel(int n, const float *__restrict__ ft, float *__restrict__ E, int lde, int off, int pad) {
+    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *p = ft + (size_t)b * 3 * n;
+    float *o = E + ((size_t)b * n + i) * lde + off;
+    o[0] = __ldg(p + i); o[1] = __ldg(p + n + i); o[2] = __ldg(p + 2 * n + i);
+    for (int d = 0; d < pad; ++d) o[3 + d] = 0.f;
+}
+int cmf_launch_scatter_ft(int b, int n, const float *ft_planar, float *E, int lde, int off, int pad, cudaStream_t st) {
+    scatter_ft_kernel<<<dim3(cmf_divup(n, 256), b), 256, 0, st>>>(n, ft_planar, E, lde, off, pad);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
+// =================================================================================================
+// FeatureCorrelator (radarflow_util.py:185-237) after hoisting conv0 over the concat:
+//   conv0([f1_i ; g1 ; f2_j ; g2 ; dir]) = U1[i] + U2[j] + Wd.dir      (U1,U2 carry the per-cloud constants and the bias)
+// =================================================================================================
+__device__ __forceinline__ float4 ld4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float leaky01(float v) { return v > 0.f ? v : 0.1f * v; }
+
+__global__ void __launch_bounds__(128)
+fc_build_h1_kernel(int n, const float *__restrict__ xyz1, const float *__restrict__ xyz2, const int *__restrict__ knn12,
+                   const float *__restrict__ U1, const float *__restrict__ U2, const float *__restrict__ Wd,
+                   float *__restrict__ H1) {
+    const int bi = blockIdx.x, b = bi / n, i = bi - b * n, t = threadIdx.x;
+    const float *p1 = xyz1 + (size_t)b * 3 * n, *p2 = xyz2 + (size_t)b * 3 * n;
+    const float qx = __ldg(p1 + i), qy = __ldg(p1 + n + i), qz = __ldg(p1 + 2 * n + i);
+    const float4 u1 = ld4(U1 + (size_t)bi * 512 + t * 4);
+    const float4 w0 = ld4(Wd + (t * 4 + 0) * 4), w1 = ld4(Wd + (t * 4 + 1) * 4), w2 = ld4(Wd + (t * 4 + 2) * 4), w3 = ld4(Wd + (t * 4 + 3) * 4);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int j = __ldg(knn12 + (size_t)bi * 8 + k);
+        const float dx = __fsub_rn(__ldg(p2 + j), qx), dy = __fsub_rn(__ldg(p2 + n + j), qy), dz = __fsub_rn(__ldg(p2 + 2 * n + j), qz);
+        const float4 u2 = ld4(U2 + ((size_t)b * n + j) * 512 + t * 4);
+        float4 v;
+        v.x = leaky01(u1.x + u2.x + fmaf(w0.z, dz, fmaf(w0.y, dy, w0.x * dx)));
+        v.y = leaky01(u1.y + u2.y + fmaf(w1.z, dz, fmaf(w1.y, dy, w1.x * dx)));
+        v.z = leaky01(u1.z + u2.z + fmaf(w2.z, dz, fmaf(w2.y, dy, w2.x * dx)));
+        v.w = leaky01(u1.w + u2.w + fmaf(w3.z, dz, fmaf(w3.y, dy, w3.x * dx)));
+        *reinterpret_cast<float4 *>(H1 + ((size_t)bi * 8 + k) * 512 + t * 4) = v;
+    }
+}
+int cmf_launch_fc_build_h1(int b, int n, const float *xyz1_planar, const float *xyz2_planar, const int *knn12,
+                           const float *U1, const float *U2, const float *Wd, float *H1, cudaStream_t st) {
+    fc_build_h1_kernel<<<b * n, 128, 0, st>>>(n, xyz1_planar, xyz2_planar, knn12, U1, U2, Wd, H1);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
+// out[i][c] = sum_k WeightNet(dir_ik)[c] * src_row(i,k)[c]     (radarflow_util.py:223-225 and 233-235)
+__global__ void __launch_bounds__(128)
+fc_reduce_kernel(int n, const float *__restrict__ xyzq, const float *__restrict__ xyzc, const int *__restrict__ knn,
+                 WeightNetP wn, const float *__restrict__ src, int gather, float *__restrict__ out, int ldo) {
+    __shared__ float h1[8][8], h2[8][8];
+    __shared__ int sj[8];
+    const int bi = blockIdx.x, b = bi / n, i = bi - b * n, t = threadIdx.x;
+    const float *pq = xyzq + (size_t)b * 3 * n, *pc = xyzc + (size_t)b * 3 * n;
+    if (t < 64) {
+        const int k = t >> 3, u = t & 7;
+        const int j = __ldg(knn + (size_t)bi * 8 + k);
+        if (u == 0) sj[k] = j;
+        const float dx = __fsub_rn(__ldg(pc + j), __ldg(pq + i)), dy = __fsub_rn(__ldg(pc + n + j), __ldg(pq + n + i)),
+                    dz = __fsub_rn(__ldg(pc + 2 * n + j), __ldg(pq + 2 * n + i));
+        const float4 a = ld4(wn.A1 + u * 4);
+        h1[k][u] = fmaxf(fmaf(a.z, dz, fmaf(a.y, dy, fmaf(a.x, dx, __ldg(wn.a1 + u)))), 0.f);
+    }
+    __syncthreads();
+    if (t < 64) {
+        const int k = t >> 3, u = t & 7;
+        float s = __ldg(wn.a2 + u);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) s = fmaf(__ldg(wn.A2 + u * 8 + v), h1[k][v], s);
+        h2[k][u] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    float4 A3[4][2];
+    float a3[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        A3[c][0] = ld4(wn.A3 + (t * 4 + c) * 8); A3[c][1] = ld4(wn.A3 + (t * 4 + c) * 8 + 4);
+        a3[c] = __ldg(wn.a3 + t * 4 + c);
+    }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float4 s = gather ? ld4(src + ((size_t)b * n + sj[k]) * 512 + t * 4) : ld4(src + ((size_t)bi * 8 + k) * 512 + t * 4);
+        const float sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float w = a3[c];
+            w = fmaf(A3[c][0].x, h2[k][0], w); w = fmaf(A3[c][0].y, h2[k][1], w); w = fmaf(A3[c][0].z, h2[k][2], w); w = fmaf(A3[c][0].w, h2[k][3], w);
+            w = fmaf(A3[c][1].x, h2[k][4], w); w = fmaf(A3[c][1].y, h2[k][5], w); w = fmaf(A3[c][1].z, h2[k][6], w); w = fmaf(A3[c][1].w, h2[k][7], w);
+            acc[c] = fmaf(fmaxf(w, 0.f), sv[c], acc[c]);
+        }
+    }
+    *reinterpret_cast<float4 *>(out + (size_t)bi * ldo + t * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+int cmf_launch_fc_reduce(int b, int n, const float *xyzq_planar, const float *xyzc_planar, const int *knn,
+                         WeightNetP wn, const float *src, int gather, float *out, int ldo, cudaStream_t st) {
+    fc_reduce_kernel<<<b * n, 128, 0, st>>>(n, xyzq_planar, xyzc_planar, knn, wn, src, gather, out, ldo);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
+// =================================================================================================
+// set-conv #2 (mse_layer2) first layer after hoisting the 1027-channel conv over the gather
+// =================================================================================================
+__global__ void __launch_bounds__(128)
+mse2_build_y1_kernel(int n, int K, int koff, const float *__restrict__ xyz, const int *__restrict__ idx60,
+                     const float *__restrict__ P, int ldp, int poff, const float *__restrict__ Wx, float *__restrict__ Y1) {
+    const int bi = blockIdx.x, b = bi / n, i = bi - b * n, t = threadIdx.x;
+    const float *px = xyz + (size_t)b * 3 * n;
+    const float qx = __ldg(px + i), qy = __ldg(px + n + i), qz = __ldg(px + 2 * n + i);
+    const float4 w0 = ld4(Wx + (t * 4 + 0) * 4), w1 = ld4(Wx + (t * 4 + 1) * 4), w2 = ld4(Wx + (t * 4 + 2) * 4), w3 = ld4(Wx + (t * 4 + 3) * 4);
+    for (int kk = 0; kk < K; ++kk) {
+        const int j = __ldg(idx60 + (size_t)bi * 60 + koff + kk);
+        const float dx = __fsub_rn(__ldg(px + j), qx), dy = __fsub_rn(__ldg(px + n + j), qy), dz = __fsub_rn(__ldg(px + 2 * n + j), qz);
+        const float4 p = ld4(P + ((size_t)b * n + j) * ldp + poff + t * 4);
+        float4 v;
+        v.x = fmaxf(p.x + fmaf(w0.z, dz, fmaf(w0.y, dy, w0.x * dx)), 0.f);
+        v.y = fmaxf(p.y + fmaf(w1.z, dz, fmaf(w1.y, dy, w1.x * dx)), 0.f);
+        v.z = fmaxf(p.z + fmaf(w2.z, dz, fmaf(w2.y, dy, w2.x * dx)), 0.f);
+        v.w = fmaxf(p.w + fmaf(w3.z, dz, fmaf(w3.y, dy, w3.x * dx)), 0.f);
+        *reinterpret_cast<float4 *>(Y1 + ((size_t)bi * K + kk) * 512 + t * 4) = v;
+    }
+}
+int cmf_launch_mse2_build_y1(int b, int n, int K, int koff, const float *xyz_planar, const int *idx60,
+                             const float *P, int ldp, int poff, const float *Wx, float *Y1, cudaStream_t st) {
+    mse2_build_y1_kernel<<<b * n, 128, 0, st>>>(n, K, koff, xyz_planar, idx60, P, ldp, poff, Wx, Y1);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
+// =================================================================================================
+// heads' last 1x1 conv (radarflow_util.py:248,259 / 276,283): 64 -> 3 and 64 -> 1 + sigmoid
+// =================================================================================================
+__global__ void __launch_bounds__(128)
+head_final_kernel(int n, const float *__restrict__ H3, int ldh, const float *__restrict__ W4f, const float *__restrict__ W4m,
+                  float *__restrict__ flow, float *__restrict__ cls) {
+    __shared__ float w[4][64];
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) w[t >> 6][t & 63] = (t < 192) ? __ldg(W4f + t) : __ldg(W4m + (t - 192));
+    __syncthreads();
+    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *h = H3 + ((size_t)b * n + i) * ldh;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < 64; c += 4) {
+        const float4 f = ld4(h + c), m = ld4(h + 64 + c);
+        a0 = fmaf(w[0][c], f.x, a0); a0 = fmaf(w[0][c + 1], f.y, a0); a0 = fmaf(w[0][c + 2], f.z, a0); a0 = fmaf(w[0][c + 3], f.w, a0);
+        a1 = fmaf(w[1][c], f.x, a1); a1 = fmaf(w[1][c + 1], f.y, a1); a1 = fmaf(w[1][c + 2], f.z, a1); a1 = fmaf(w[1][c + 3], f.w, a1);
+        a2 = fmaf(w[2][c], f.x, a2); a2 = fmaf(w[2][c + 1], f.y, a2); a2 = fmaf(w[2][c + 2], f.z, a2); a2 = fmaf(w[2][c + 3], f.w, a2);
+        a3 = fmaf(w[3][c], m.x, a3); a3 = fmaf(w[3][c + 1], m.y, a3); a3 = fmaf(w[3][c + 2], m.z, a3); a3 = fmaf(w[3][c + 3], m.w, a3);
+    }
+    float *fo = flow + (size_t)b * 3 * n;
+    fo[i] = a0; fo[n + i] = a1; fo[2 * n + i] = a2;
+    cls[(size_t)b * n + i] = 1.0f / (1.0f + expf(-a3));
+}
+int cmf_launch_head_final(int b, int n, const float *H3, int ldh, const float *W4f, const float *W4m,
+                          float *flow_planar, float *cls, cudaStream_t st) {
+    head_final_kernel<<<dim3(cmf_divup(n, 128), b), 128, 0, st>>>(n, H3, ldh, W4f, W4m, flow_planar, cls);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
+// =================================================================================================
+// GRU gates (nn.GRU one step, gate order r,z,n; models/cmflow_t.py:46,101)
+// =================================================================================================
+__global__ void gru_gates_kernel(int total, const float *__restrict__ gi, const float *__restrict__ gh,
+                                 const float *__restrict__ h_prev, float *__restrict__ h_new) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int b = t >> 8, u = t & 255;
+    const float *i_ = gi + (size_t)b * 768, *h_ = gh + (size_t)b * 768;
+    const float r = 1.0f / (1.0f + expf(-(i_[u] + h_[u])));
+    const float z = 1.0f / (1.0f + expf(-(i_[256 + u] + h_[256 + u])));
+    const float nn = tanhf(i_[512 + u] + r * h_[512 + u]);
+    const float hp = h_prev ? h_prev[t] : 0.f;
+    h_new[t] = (1.0f - z) * nn + z * hp;
+}
+int cmf_launch_gru_gates(int b, const float *gi, const float *gh, const float *h_prev, float *h_new, cudaStream_t st) {
+    gru_gates_kernel<<<cmf_divup(b * 256, 256), 256, 0, st>>>(b * 256, gi, gh, h_prev, h_new);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
+// =================================================================================================
+// Weighted Kabsch + refine (models/cmflow.py:96-169, 112-125): one CTA per frame pair.
+// Moments are accumulated in fp64 in a single pass; the 3x3 SVD is a one-sided Jacobi in fp64, so the
+// rotation is the polar factor V U^T to ~1e-15 -- the reference's fp32 cuSOLVER/LAPACK result agrees with
+// it to fp32 rounding.  The reflection rule reproduces the reference's quirk: ROW 2 of V is negated
+// (cmflow.py:162), i.e. R = diag(1,1,-1) V U^T when det(V U^T) < 0.
+// =================================================================================================
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+__device__ void polar_rotation_3x3(const double H[3][3], double R[3][3]) {
+    double A[3][3], V[3][3];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) { A[r][c] = H[r][c]; V[r][c] = (r == c) ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double offn = 0.0;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                double al = 0, be = 0, ga = 0;
+                for (int r = 0; r < 3; ++r) { al += A[r][p] * A[r][p]; be += A[r][q] * A[r][q]; ga += A[r][p] * A[r][q]; }
+                if (fabs(ga) <= 1e-18 * sqrt(al * be) || ga == 0.0) continue;
+                offn += fabs(ga);
+                const double zeta = (be - al) / (2.0 * ga);
+                const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
+                for (int r = 0; r < 3; ++r) {
+                    double x = A[r][p], y = A[r][q];
+                    A[r][p] = cs * x - sn * y; A[r][q] = sn * x + cs * y;
+                    x = V[r][p]; y = V[r][q];
+                    V[r][p] = cs * x - sn * y; V[r][q] = sn * x + cs * y;
+                }
+            }
+        if (offn == 0.0) break;
+    }
+    // A = U S (columns); normalise to U, repairing a (near-)null column by a cross product
+    double nrm[3], U[3][3];
+    double nmax = 0;
+    for (int c = 0; c < 3; ++c) { nrm[c] = sqrt(A[0][c] * A[0][c] + A[1][c] * A[1][c] + A[2][c] * A[2][c]); nmax = fmax(nmax, nrm[c]); }
+    int bad = -1, nbad = 0;
+    for (int c = 0; c < 3; ++c) {
+        if (nrm[c] > 1e-13 * nmax && nrm[c] > 0) { for (int r = 0; r < 3; ++r) U[r][c] = A[r][c] / nrm[c]; }
+        else { bad = c; ++nbad; }
+    }
+    if (nbad == 1) {
+        const int a = (bad + 1) % 3, b2 = (bad + 2) % 3;
+        double cx = U[1][a] * U[2][b2] - U[2][a] * U[1][b2], cy = U[2][a] * U[0][b2] - U[0][a] * U[2][b2], cz = U[0][a] * U[1][b2] - U[1][a] * U[0][b2];
+        // choose the sign that makes det(U) = det(V) (so that V U^T is a proper rotation)
+        double detV = V[0][0] * (V[1][1] * V[2][2] - V[1][2] * V[2][1]) - V[0][1] * (V[1][0] * V[2][2] - V[1][2] * V[2][0]) + V[0][2] * (V[1][0] * V[2][1] - V[1][1] * V[2][0]);
+        U[0][bad] = cx; U[1][bad] = cy; U[2][bad] = cz;      // det(U) = +1 with (a,b,bad) cyclic
+        if (detV < 0) { U[0][bad] = -cx; U[1][bad] = -cy; U[2][bad] = -cz; }
+    } else if (nbad >= 2) {                                  // rank <= 1: rotation undefined; return identity-like V V^T
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) U[r][c] = V[r][c];
+    }
+    double Z[3][3];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) Z[r][c] = V[r][0] * U[c][0] + V[r][1] * U[c][1] + V[r][2] * U[c][2];
+    const double det = Z[0][0] * (Z[1][1] * Z[2][2] - Z[1][2] * Z[2][1]) - Z[0][1] * (Z[1][0] * Z[2][2] - Z[1][2] * Z[2][0]) + Z[0][2] * (Z[1][0] * Z[2][1] - Z[1][1] * Z[2][0]);
+    const double s2 = det < 0 ? -1.0 : 1.0;                  // cmflow.py:157-162: negate ROW 2 of V
+    for (int c = 0; c < 3; ++c) { R[0][c] = Z[0][c]; R[1][c] = Z[1][c]; R[2][c] = s2 * Z[2][c]; }
+}
+
+__global__ void __launch_bounds__(256)
+kabsch_kernel(int n, const float *__restrict__ pc1, const float *__restrict__ second, int second_is_flow,
+              const float *__restrict__ w, int normalise, float eps, float stat_thres,
+              float *__restrict__ trans, float *__restrict__ sf_agg, uint8_t *__restrict__ mask) {
+    __shared__ double red[8][16];
+    __shared__ float sT[12];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *pa = pc1 + (size_t)b * 3 * n, *ps = second + (size_t)b * 3 * n, *pw = w + (size_t)b * n;
+    double m[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m[i] = 0.0;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float ax = pa[i], ay = pa[n + i], az = pa[2 * n + i];
+        float bx = ps[i], by = ps[n + i], bz = ps[2 * n + i];
+        if (second_is_flow) { bx = __fadd_rn(ax, bx); by = __fadd_rn(ay, by); bz = __fadd_rn(az, bz); }   // pc1_warp = pc1 + flow (cmflow.py:102)
+        const double wi = normalise ? (double)__fadd_rn(pw[i], eps) : (double)pw[i];
+        const double A[3] = {ax, ay, az}, Bv[3] = {bx, by, bz};
+        m[0] += wi;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            m[1 + r] += wi * A[r];
+            m[4 + r] += wi * Bv[r];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) m[7 + r * 3 + c] += wi * A[r] * Bv[c];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m[i] = warp_sum_d(m[i]);
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) red[warp][i] = m[i];
+    __syncthreads();
+    if (tid == 0) {
+        double t[16];
+        for (int i = 0; i < 16; ++i) { t[i] = 0; for (int wv = 0; wv < 8; ++wv) t[i] += red[wv][i]; }
+        double sw = t[0];
+        if (normalise) { for (int i = 1; i < 16; ++i) t[i] /= sw; sw = 1.0; }
+        const double cA[3] = {t[1], t[2], t[3]}, cB[3] = {t[4], t[5], t[6]};
+        double H[3][3], R[3][3];
+        // H = sum w (a-cA)(b-cB)^T with cA = sum w a, cB = sum w b (no division by sum w: cmflow.py:138-151)
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) H[r][c] = t[7 + r * 3 + c] - (2.0 - sw) * cA[r] * cB[c];
+        polar_rotation_3x3(H, R);
+        for (int r = 0; r < 3; ++r) {
+            const double tr = -(R[r][0] * cA[0] + R[r][1] * cA[1] + R[r][2] * cA[2]) + cB[r];
+            sT[r * 4 + 0] = (float)R[r][0]; sT[r * 4 + 1] = (float)R[r][1]; sT[r * 4 + 2] = (float)R[r][2]; sT[r * 4 + 3] = (float)tr;
+        }
+    }
+    __syncthreads();
+    if (tid < 16) trans[(size_t)b * 16 + tid] = tid < 12 ? sT[tid] : (tid == 15 ? 1.f : 0.f);
+    if (!sf_agg) return;
+    // refine_with_transform (cmflow.py:112-125): static points take the rigid flow T.[p;1] - p
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float x = pa[i], y = pa[n + i], z = pa[2 * n + i];
+        const bool st = pw[i] > stat_thres;                      // mask = scores > stat_thres (cmflow.py:188)
+        float o[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float rg = __fsub_rn(fmaf(sT[r * 4 + 2], z, fmaf(sT[r * 4 + 1], y, fmaf(sT[r * 4 + 0], x, sT[r * 4 + 3]))), r == 0 ? x : (r == 1 ? y : z));
+            o[r] = st ? rg : ps[r * n + i];
+        }
+        float *so = sf_agg + (size_t)b * 3 * n;
+        so[i] = o[0]; so[n + i] = o[1]; so[2 * n + i] = o[2];
+        if (mask) mask[(size_t)b * n + i] = st ? 1 : 0;
+    }
+}
+
+int cmf_launch_kabsch(int b, int n, const float *pc1, const float *pc_or_flow, int second_is_flow, const float *w,
+                      int normalise, float eps, float stat_thres, float *trans, float *sf_agg, uint8_t *mask,
+                      cudaStream_t st) {
+    kabsch_kernel<<<b, 256, 0, st>>>(n, pc1, pc_or_flow, second_is_flow, w, normalise, eps, stat_thres, trans, sf_agg, mask);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
+extern "C" int cmf_kabsch_refine(int b, int n, const float *pc1, const float *flow, const float *score,
+                                 float eps, float stat_thres, float *trans, float *sf_agg, uint8_t *mask, void *stream) {
+    CMF_REQUIRE(b >= 0 && n >= 1, "need b >= 0, n >= 1");
+    if (b == 0) return CMF_OK;
+    CMF_REQUIRE(pc1 && flow && score && trans && sf_agg, "null pointer");
+    return cmf_launch_kabsch(b, n, pc1, flow, 1, score, 1, eps, stat_thres, trans, sf_agg, mask, (cudaStream_t)stream);
+}
+
+extern "C" int cmf_weighted_kabsch(int b, int n, const float *A, const float *Bp, const float *W, float *trans, void *stream) {
+    CMF_REQUIRE(b >= 0 && n >= 1, "need b >= 0, n >= 1");
+    if (b == 0) return CMF_OK;
+    CMF_REQUIRE(A && Bp && W && trans, "null pointer");
+    return cmf_launch_kabsch(b, n, A, Bp, 0, W, 0, 0.f, 0.f, trans, nullptr, nullptr, (cudaStream_t)stream);
+}

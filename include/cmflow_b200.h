@@ -1,0 +1,169 @@
+/*
+ * cmflow_b200.h -- C ABI of libcmflow_b200.so (B200 / sm_100a).
+ *
+ * Plain pointers, sizes and a stream; no torch types.  Every entry point returns 0 on success or a
+ * non-zero CMF_ERR_* code (the reference prints to stderr and calls exit(-1) instead, e.g.
+ * lib/src/ball_query_gpu.cu:62-66 -- a library must not kill its host).  cmf_last_error() returns a
+ * thread-local human-readable message for the last failure.  All device pointers must be contiguous
+ * fp32 / int32 buffers with the layouts stated; `stream` is a cudaStream_t passed as void* (0 = the
+ * legacy default stream).  Nothing here allocates device memory except cmf_model_* (workspace owned
+ * by the handle) and nothing synchronises the stream except the *_host entry point.
+ *
+ * Part 1 replaces, one for one, the launchers the reference's pybind module `pointnet2_cuda` binds
+ * (lib/src/pointnet2_api.cpp:11-24); file:line of the replaced launcher prototype is given per entry.
+ * Part 2 is the model-path operators of utils/model_utils/radarflow_util.py and models/cmflow.py.
+ * Part 3 is the whole-forward engine behind models/cmflow.py:171-197 / models/cmflow_t.py:185-211.
+ * Paths are relative to the upstream tree (Toytiny/CMFlow @ 16a095a).
+ */
+#ifndef CMFLOW_B200_H
+#define CMFLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMF_OK 0
+#define CMF_ERR_INVALID 1   /* bad argument (null pointer, negative size, k out of range ...) */
+#define CMF_ERR_CUDA 2      /* a CUDA runtime call or kernel launch failed                     */
+#define CMF_ERR_NOMEM 3     /* workspace allocation failed                                     */
+#define CMF_ERR_STATE 4     /* handle used before weights were uploaded, etc.                  */
+
+const char *cmf_last_error(void);
+const char *cmf_version(void);                 /* "cmflow_b200 x.y.z sm_100a" */
+int cmf_device_check(void);                    /* CMF_OK iff the current device is compute capability 10.x */
+
+/* ------------------------------------------------------------------------------------------------
+ * Part 1 -- pointnet2_cuda operator set
+ * ---------------------------------------------------------------------------------------------- */
+
+/* replaces ball_query_kernel_launcher_fast (lib/src/ball_query_gpu.h:12-13, ball_query_gpu.cu:48-67).
+ * new_xyz (B,M,3), xyz (B,N,3) -> idx (B,M,nsample) int32, PRE-ZEROED by the caller
+ * (lib/pointnet2_utils.py:246). First nsample indices in index order with d2 < radius^2 (strict),
+ * remainder padded with the first hit, rows without a hit untouched. */
+int cmf_ball_query(int b, int n, int m, float radius, int nsample,
+                   const float *new_xyz, const float *xyz, int *idx, void *stream);
+
+/* replaces group_points_kernel_launcher_fast (lib/src/group_points_gpu.h:13-14).
+ * points (B,C,N), idx (B,npoints,nsample) -> out (B,C,npoints,nsample) */
+int cmf_group_points(int b, int c, int n, int npoints, int nsample,
+                     const float *points, const int *idx, float *out, void *stream);
+
+/* replaces group_points_grad_kernel_launcher_fast (lib/src/group_points_gpu.h:19-20).
+ * grad_out (B,C,npoints,nsample), idx -> grad_points (B,C,N), accumulated (caller zeroes). */
+int cmf_group_points_grad(int b, int c, int n, int npoints, int nsample,
+                          const float *grad_out, const int *idx, float *grad_points, void *stream);
+
+/* replaces gather_points_kernel_launcher_fast (lib/src/sampling_gpu.h:12-13).
+ * points (B,C,N), idx (B,npoints) -> out (B,C,npoints) */
+int cmf_gather_points(int b, int c, int n, int npoints,
+                      const float *points, const int *idx, float *out, void *stream);
+
+/* replaces gather_points_grad_kernel_launcher_fast (lib/src/sampling_gpu.h:19-20). */
+int cmf_gather_points_grad(int b, int c, int n, int npoints,
+                           const float *grad_out, const int *idx, float *grad_points, void *stream);
+
+/* replaces furthest_point_sampling_kernel_launcher (lib/src/sampling_gpu.h:26-27).
+ * dataset (B,N,3), temp (B,N) in/out (caller fills 1e10, lib/pointnet2_utils.py:26), idxs (B,M) int32.
+ * Tie-breaking reproduces the reference's block-size-dependent tree (sampling_gpu.cu:86-209). */
+int cmf_furthest_point_sampling(int b, int n, int m,
+                                const float *dataset, float *temp, int *idxs, void *stream);
+
+/* replaces knn_kernel_launcher_fast (lib/src/interpolate_gpu.h:19-20, interpolate_gpu.cu:9-57).
+ * unknown (B,N,3) queries, known (B,M,3) candidates -> dist2 (B,N,k) f32 SQUARED distances,
+ * idx (B,N,k) int32; ascending, ties keep the lower index; 1 <= k <= 200 as in the reference. */
+int cmf_knn(int b, int n, int m, int k, const float *unknown, const float *known,
+            float *dist2, int *idx, void *stream);
+
+/* replaces three_nn_kernel_launcher_fast (lib/src/interpolate_gpu.h:13-14). */
+int cmf_three_nn(int b, int n, int m, const float *unknown, const float *known,
+                 float *dist2, int *idx, void *stream);
+
+/* replaces three_interpolate_kernel_launcher_fast (lib/src/interpolate_gpu.h:26-27).
+ * points (B,C,M), idx (B,N,3), weight (B,N,3) -> out (B,C,N) */
+int cmf_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
+                          const float *weight, float *out, void *stream);
+
+/* replaces three_interpolate_grad_kernel_launcher_fast (lib/src/interpolate_gpu.h:33-34). */
+int cmf_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                               const float *weight, float *grad_points, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Part 2 -- model-path operators
+ * ---------------------------------------------------------------------------------------------- */
+
+/* knn_point + square_distance (utils/model_utils/radarflow_util.py:88-99, 8-30): the k nearest
+ * candidates of every query under the reference's EXPANDED float32 distance
+ *   d = max(((-2*dot(q,x)) + |q|^2) + |x|^2, 0),  dot = fma(qz,xz, fma(qy,xy, qx*xx))
+ * xyz (B,N,3) candidates, new_xyz (B,S,3) queries -> idx (B,S,k) int32 ascending by (d, index)
+ * (torch.topk(sorted=False) leaves the order unspecified), optional dist (B,S,k) or NULL. 1<=k<=32. */
+int cmf_knn_point(int b, int n, int s, int k, const float *xyz, const float *new_xyz,
+                  int *idx, float *dist, void *stream);
+
+/* Multi-radius ball query of a cloud against itself, all four CMFlow scales in ONE pass over the
+ * candidates (models/cmflow.py:21-22,35-36: r = 2,4,8,16; K = 4,8,16,32; QueryAndGroup.forward,
+ * lib/pointnet2_utils.py:277).  xyz_planar (B,3,N) (the model's input layout) -> idx (B,N,60) int32:
+ * per point the 4 rows concatenated [K=4 | K=8 | K=16 | K=32], each with cmf_ball_query semantics. */
+int cmf_ball_query_ms(int b, int n, const float *xyz_planar, int *idx60, void *stream);
+
+/* CMFlow.WeightedKabsch + refine_with_transform (models/cmflow.py:96-169, 112-125), one launch:
+ * pc1 (B,3,N), flow (B,3,N), score (B,N) (stat_cls), eps added to the score before normalising
+ * (1e-4 for CMFlow, cmflow.py:105; 0 for CMFlow-T, cmflow_t.py:119), stat_thres ->
+ * trans (B,4,4), sf_agg (B,3,N), mask (B,N) uint8.  3x3 SVD in fp64 Jacobi; reproduces the
+ * reference's row-2 flip of V (cmflow.py:162). */
+int cmf_kabsch_refine(int b, int n, const float *pc1, const float *flow, const float *score,
+                      float eps, float stat_thres, float *trans, float *sf_agg, uint8_t *mask, void *stream);
+
+/* Weighted Kabsch alone (models/cmflow.py:128-169): A,Bp (B,3,N), W (B,N) normalised weights -> trans (B,4,4). */
+int cmf_weighted_kabsch(int b, int n, const float *A, const float *Bp, const float *W, float *trans, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Part 3 -- whole-forward engine (models/cmflow.py:171-197, models/cmflow_t.py:185-211)
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct cmf_model cmf_model;
+
+/* Number of floats of the packed-weight blob for (temporal ? CMFlow_T : CMFlow); layout documented in
+ * cmflow_b200/weights.py (BatchNorm folded into conv scale/bias in float64 on the host). */
+size_t cmf_model_blob_floats(int temporal);
+
+/* Create an engine on the current device.  `blob` is a HOST pointer to cmf_model_blob_floats() floats;
+ * it is copied to the device.  stat_thres as models/cmflow.py:18. */
+int cmf_model_create(cmf_model **out, const float *blob, size_t blob_floats, int temporal, float stat_thres);
+void cmf_model_destroy(cmf_model *m);
+
+/* Workspace bytes the engine holds for the largest (B,N) seen so far (diagnostic). */
+size_t cmf_model_workspace_bytes(const cmf_model *m);
+
+/* Number of kernels one forward launches (for bench.py's gpu_launches). */
+int cmf_model_launches_per_forward(const cmf_model *m);
+
+/* Device-resident forward. pc1,pc2,ft1,ft2 (B,3,N) fp32.  gfeat_prev (B,256) or NULL (CMFlow-T only;
+ * NULL = zeros, cmflow_t.py:97-98).  Outputs: sf_agg (B,3,N), stat_cls (B,N) [the reference's (B,1,N)],
+ * pre_trans (B,4,4), mask (B,N) uint8, gfeat_out (B,256) (CMFlow-T only, else may be NULL).
+ * Enqueues on `stream`, does not synchronise. */
+int cmf_model_forward(cmf_model *m, int b, int n,
+                      const float *pc1, const float *pc2, const float *ft1, const float *ft2,
+                      const float *gfeat_prev,
+                      float *sf_agg, float *stat_cls, float *pre_trans, uint8_t *mask, float *gfeat_out,
+                      void *stream);
+
+/* Same with HOST buffers (pinned for full speed): copies inputs H2D, runs the forward, copies the four
+ * outputs D2H and synchronises `stream`.  This is the end-to-end call bench.py times as `e2e`. */
+int cmf_model_forward_host(cmf_model *m, int b, int n,
+                           const float *pc1, const float *pc2, const float *ft1, const float *ft2,
+                           const float *gfeat_prev,
+                           float *sf_agg, float *stat_cls, float *pre_trans, uint8_t *mask, float *gfeat_out,
+                           void *stream);
+
+/* Debug taps (device pointers into the workspace of the last forward; NULL if not produced):
+ * "f1","f2" (B,N,256) | "g1","g2" (B,256) | "cor" (B,N,512) | "prop" (B,N,256) | "flow" (B,3,N)
+ * | "bq1","bq2" (B,N,60) int32 | "knn12","knn11" (B,N,8) int32. */
+const void *cmf_model_tap(const cmf_model *m, const char *name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMFLOW_B200_H */

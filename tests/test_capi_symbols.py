@@ -1,0 +1,45 @@
+"""The C-ABI library loads on a CPU-only box and exports every entry point include/cmflow_b200.h declares.
+No compute is called here (no GPU)."""
+import ctypes
+import os
+import re
+
+from cmflow_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "cmflow_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cmf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_table_agree():
+    assert header_functions() == sorted(_lib.SIGNATURES)
+
+
+def test_library_exports_every_symbol():
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in header_functions():
+        assert hasattr(L, name), name
+
+
+def test_version_and_error_plumbing_without_gpu():
+    L = _lib.lib()
+    assert b"sm_100a" in L.cmf_version()
+    # invalid arguments are rejected before any CUDA call
+    rc = L.cmf_knn(1, 4, 4, 500, None, None, None, None, None)
+    assert rc == 1 and b"k must be" in L.cmf_last_error()
+    rc = L.cmf_ball_query(1, 4, 4, 1.0, 2, None, None, None, None)
+    assert rc == 1 and b"null pointer" in L.cmf_last_error()
+    assert L.cmf_ball_query(0, 4, 4, 1.0, 2, None, None, None, None) == 0     # empty batch is a no-op
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "cmflow_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f

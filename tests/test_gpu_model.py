@@ -1,0 +1,169 @@
+"""GPU parity of the whole-forward engine (Part 3 of the C ABI) against the golden vectors produced by the
+unmodified reference, the CPU oracle, and the stage-by-stage emulator."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from cmflow_b200 import weights   # noqa: E402
+from cmflow_b200._lib import check, dptr, lib, stream_ptr   # noqa: E402
+from cmflow_b200.cmflow import CMFlow, CMFlow_T   # noqa: E402
+from cmflow_b200.synth import make_pairs, synthetic_state_dict   # noqa: E402
+from oracle import cmflow_oracle as O   # noqa: E402
+from tests.helpers import case_inputs, case_weights, check_outputs, knn_sets_equal, load_golden, rel_err   # noqa: E402
+from tests.pipeline_emulator import emulate   # noqa: E402
+
+DEV = "cuda"
+
+
+class Args:
+    num_points = 256
+    stat_thres = 0.5
+
+
+def build(meta, golden_dir):
+    sd = case_weights(meta, golden_dir)
+    if sd is None:
+        pytest.skip("reference checkpoint not available")
+    net = (CMFlow_T if meta["model"] == "cmflow_t" else CMFlow)(Args())
+    net.load_state_dict(sd, strict=True)
+    return net.to(DEV), sd
+
+
+def run(net, inp, g=None):
+    pc1, pc2, ft1, ft2 = (t.to(DEV) for t in inp[:4])
+    with torch.no_grad():
+        if isinstance(net, CMFlow_T):
+            sf, cls, T, mask, g = net(pc1, pc2, ft1, ft2, None, "test", g)
+        else:
+            sf, cls, T, mask = net(pc1, pc2, ft1, ft2, None, "test")
+    return {"sf_agg": sf.cpu(), "stat_cls": cls.cpu(), "pre_trans": T.cpu(), "mask": mask.cpu(), "gfeat": g}
+
+
+CASES = ["cmflow_synth_b2_n256.pt", "cmflow_synth_w1_b2_n256.pt", "cmflow_synth_b3_n200.pt", "cmflow_synth_b2_n40.pt",
+         "cmflow_ckpt_b2_n256.pt"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_matches_reference_golden(golden_dir, name):
+    gold = load_golden(golden_dir, name)
+    net, sd = build(gold["meta"], golden_dir)
+    inp = case_inputs(gold["meta"])
+    out = run(net, inp)
+    B, N = gold["meta"]["B"], gold["meta"]["N"]
+    # integer work: neighbour sets identical to the reference's own torch.topk sets
+    assert knn_sets_equal(net.tap("knn12", (B, N, 8), torch.int32).cpu(), gold["knn12"])
+    assert knn_sets_equal(net.tap("knn11", (B, N, 8), torch.int32).cpu(), gold["knn11"])
+    E = net.tap("E", (B, N, 776)).cpu()
+    assert rel_err(E[0, ::4, 0:256].t(), gold["f1_sub"], per_pair=False) <= 1e-4
+    assert rel_err(E[0, ::4, 256:768].t(), gold["cor_sub"], per_pair=False) <= 1e-4
+    assert rel_err(net.tap("f2", (B, N, 256)).cpu()[0, ::4].t(), gold["f2_sub"], per_pair=False) <= 1e-4
+    assert rel_err(net.tap("prop", (B, N, 256)).cpu()[0, ::4].t(), gold["prop_sub"], per_pair=False) <= 1e-4
+    errs = check_outputs(out, gold)
+    print(name, errs)
+    assert out["sf_agg"].shape == (B, 3, N) and out["stat_cls"].shape == (B, 1, N)
+    assert out["pre_trans"].shape == (B, 4, 4) and out["mask"].dtype == torch.bool
+
+
+def test_temporal_clip_matches_reference_golden(golden_dir):
+    gold = load_golden(golden_dir, "cmflow_t_synth_b2_n256.pt")
+    net, sd = build(gold["meta"], golden_dir)
+    inp = case_inputs(gold["meta"])
+    g = None
+    for step in gold["steps"]:
+        out = run(net, inp, g)
+        check_outputs(out, step)
+        assert rel_err(out["gfeat"].cpu(), step["gfeat"]) <= 1e-4
+        g = out["gfeat"]
+
+
+def test_stage_taps_match_fp64_emulation(golden_dir):
+    """Every stage boundary vs an fp64 replay of the same pipeline on the same packed weights: isolates
+    kernel arithmetic error (summation order only) from everything else."""
+    gold = load_golden(golden_dir, "cmflow_synth_b2_n256.pt")
+    net, sd = build(gold["meta"], golden_dir)
+    inp = case_inputs(gold["meta"])
+    out = run(net, inp)
+    B, N = 2, 256
+    em = emulate(weights.pack(sd, False), *inp[:4], dtype=torch.float64)
+    assert torch.equal(net.tap("bq1", (B, N, 60), torch.int32).cpu().long(), em["bq1"])
+    assert torch.equal(net.tap("bq2", (B, N, 60), torch.int32).cpu().long(), em["bq2"])
+    assert torch.equal(net.tap("knn12", (B, N, 8), torch.int32).cpu().long(), em["knn12"])
+    assert torch.equal(net.tap("knn11", (B, N, 8), torch.int32).cpu().long(), em["knn11"])
+    E = net.tap("E", (B, N, 776)).cpu()
+    for name, got, want in (("f1", E[..., 0:256], em["f1"]), ("f2", net.tap("f2", (B, N, 256)).cpu(), em["f2"]),
+                            ("cor", E[..., 256:768], em["cor"]), ("prop", net.tap("prop", (B, N, 256)).cpu(), em["prop"]),
+                            ("flow", net.tap("flow", (B, 3, N)).cpu(), em["flow"])):
+        e = rel_err(got, want)
+        print(name, e)
+        assert e <= 2e-5, (name, e)
+    assert (out["stat_cls"].double() - em["stat_cls"]).abs().max() <= 2e-5
+
+
+def test_chunked_batch_equals_single_chunk(golden_dir, monkeypatch):
+    gold = load_golden(golden_dir, "cmflow_synth_b3_n200.pt")
+    net, sd = build(gold["meta"], golden_dir)
+    inp = case_inputs(gold["meta"])
+    whole = run(net, inp)
+    monkeypatch.setenv("CMF_CHUNK_PAIRS", "1")
+    net2, _ = build(gold["meta"], golden_dir)
+    parts = run(net2, inp)
+    for k in ("sf_agg", "stat_cls", "pre_trans", "mask"):
+        assert torch.equal(whole[k], parts[k]), k            # pairs are independent: bitwise identical
+
+
+def test_host_entry_point_equals_device_entry_point(golden_dir):
+    gold = load_golden(golden_dir, "cmflow_synth_b2_n256.pt")
+    net, sd = build(gold["meta"], golden_dir)
+    inp = case_inputs(gold["meta"])
+    dev = run(net, inp)
+    host = net.forward_host(*[t.pin_memory() for t in inp[:4]])
+    assert torch.equal(host["sf_agg"], dev["sf_agg"]) and torch.equal(host["stat_cls"], dev["stat_cls"])
+    assert torch.equal(host["pre_trans"], dev["pre_trans"]) and torch.equal(host["mask"].bool(), dev["mask"])
+
+
+def test_kabsch_matches_reference_golden(golden_dir):
+    gold = load_golden(golden_dir, "kabsch_n128.pt")
+    A, Bp, W = gold["A"].to(DEV), gold["B"].to(DEV), gold["W"].to(DEV)
+    T = torch.empty(4, 4, 4, device=DEV)
+    check(lib().cmf_weighted_kabsch(4, 128, dptr(A), dptr(Bp), dptr(W), dptr(T), stream_ptr()))
+    assert rel_err(T.cpu()[:, :3], gold["T"][:, :3]) <= 1e-4
+    assert torch.equal(T.cpu()[:, 3], torch.tensor([0., 0, 0, 1]).expand(4, 4))
+    assert torch.linalg.det(T[3, :3, :3].cpu()) > 0.99          # reflected case handled as the reference does
+
+
+def test_batch256_properties():
+    """BASELINE.json configs[1] size (N=256, batch=256): size-independent properties instead of an oracle run --
+    rotations orthonormal with det +1, static points carry exactly the rigid flow, outputs finite, and the first
+    two pairs equal a B=2 run of the same inputs (batch independence)."""
+    sd = synthetic_state_dict(0)
+    net = CMFlow(Args()); net.load_state_dict(sd); net = net.to(DEV)
+    inp = make_pairs(256, 256, seed=7)
+    out = run(net, inp)
+    R = out["pre_trans"][:, :3, :3].double()
+    assert (R @ R.transpose(1, 2) - torch.eye(3, dtype=torch.float64)).abs().max() < 1e-5
+    assert (torch.linalg.det(R) - 1).abs().max() < 1e-5
+    assert all(torch.isfinite(v).all() for k, v in out.items() if k in ("sf_agg", "stat_cls", "pre_trans"))
+    pc1 = inp[0].double()
+    rigid = (out["pre_trans"].double()[:, :3, :3] @ pc1 + out["pre_trans"].double()[:, :3, 3:]) - pc1
+    m = out["mask"].unsqueeze(1).expand(-1, 3, -1)
+    assert (out["sf_agg"].double() - rigid)[m].abs().max() < 1e-3
+    small = run(net, tuple(t[:2] for t in inp))
+    for k in ("sf_agg", "stat_cls", "pre_trans", "mask"):
+        assert torch.equal(small[k], out[k][:2]), k
+
+
+def test_dense_cloud_config_runs_and_matches_oracle_prefix():
+    """BASELINE.json configs[4] shape class (N=4096) at B=1: integer stages exact vs the C oracle, outputs finite."""
+    from oracle import pointops as P
+    sd = synthetic_state_dict(0)
+    net = CMFlow(Args()); net.load_state_dict(sd); net = net.to(DEV)
+    inp = make_pairs(1, 4096, seed=3, dense=True)
+    out = run(net, inp)
+    x1t = inp[0].permute(0, 2, 1).contiguous(); x2t = inp[1].permute(0, 2, 1).contiguous()
+    want = torch.cat([P.ball_query(r, k, x1t, x1t) for r, k in ((2.0, 4), (4.0, 8), (8.0, 16), (16.0, 32))], -1)
+    assert torch.equal(net.tap("bq1", (1, 4096, 60), torch.int32).cpu(), want)
+    assert torch.equal(net.tap("knn12", (1, 4096, 8), torch.int32).cpu(), P.knn_point(8, x2t, x1t)[0])
+    assert torch.isfinite(out["sf_agg"]).all()
