@@ -1,0 +1,265 @@
+#!/usr/bin/env python
+"""bench.py -- frame-pairs/s of the CMFlow forward hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 256] [--points 256] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one CMFlow.forward over a batch of synthetic radar frame pairs (BASELINE.json configs[1]:
+N=256 points, batch=256 per GPU; weak scaling: every rank runs its own 256 pairs, no data-path collective --
+SURVEY.md 8e).  Rank 0 prints ONE JSON line.
+
+  value  : device-resident throughput (inputs in HBM before the timed region), CUDA events, max over ranks
+  e2e    : same metric through the public host-buffer call (cmf_model_forward_host): pinned H2D of the four
+           input tensors + forward + D2H of the four outputs inside the timed region, every step
+  roofline / kernels : per-kernel-category device time measured live with CUDA events on the launching stream
+           in a separate profiled pass of the same workload (event pairs around every launch)
+  cpu_baseline : the oracle (CPU port of the reference's PyTorch path) on a bounded sample, rank 0, N=1 only
+  --impl reference : the reference arm = that same CPU port timed with all host threads (the reference's
+           Python cannot travel to the GPU box and ships no CPU kernels of its own -- SURVEY.md 8c)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def time_cpu_port(pairs, points, steps, warmup, threads):
+    """The oracle (CPU port of the reference forward) on `pairs` synthetic pairs per step."""
+    from cmflow_b200.synth import make_pairs, synthetic_state_dict
+    from oracle import cmflow_oracle as O
+    torch.set_num_threads(threads)
+    sd = synthetic_state_dict(0)
+    pc1, pc2, ft1, ft2, _ = make_pairs(pairs, points, seed=1234)
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.cmflow_forward(sd, pc1, pc2, ft1, ft2)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.cmflow_forward(sd, pc1, pc2, ft1, ft2)
+        dt = time.perf_counter() - t0
+    return pairs * steps / dt, dt / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=256, help="frame pairs per GPU per step")
+    ap.add_argument("--points", type=int, default=256)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu", action="store_true", help="profiler harness: W+K device forwards only, prints no bench line")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    W = max(args.warmup, 3) if (args.impl == "ours" and not args.ncu) else args.warmup
+    K = args.steps
+    cores = os.cpu_count() or 1
+    workload = f"CMFlow forward, synthetic radar pairs N={args.points}, batch={args.batch}/GPU, {args.gpus}xB200"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample = 4
+        v, spp = time_cpu_port(sample, args.points, K, min(W, 1), cores)
+        print(json.dumps({
+            "impl": "reference", "metric": "frame-pairs/sec CMFlow forward", "value": v, "unit": "frame-pairs/s", "n_gpus": args.gpus,
+            "steps": K, "warmup": min(W, 1), "ms_per_step": spp * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic radar pairs, seeded random-init weights",
+            "config": {"workload": workload, "points": args.points, "pairs_per_step": sample},
+            "cpu_baseline": {"value": v, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} pairs/step x {K} steps, oracle/cmflow_oracle.py (CPU port of the reference forward), {cores} threads"},
+            "e2e": {"value": v, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (there is no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from cmflow_b200.cmflow import CMFlow
+    from cmflow_b200.synth import make_pairs, synthetic_state_dict
+
+    class A:
+        num_points = args.points
+        stat_thres = 0.5
+
+    net = CMFlow(A())
+    net.load_state_dict(synthetic_state_dict(0))
+    net = net.to(dev)
+    B, N = args.batch, args.points
+    NSETS = 4                                                  # rotate distinct input batches
+    host_sets = [tuple(t.pin_memory() for t in make_pairs(B, N, seed=1234 + 97 * rank + s)[:4]) for s in range(NSETS)]
+    dev_sets = [tuple(t.to(dev) for t in hs) for hs in host_sets]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def fwd_dev(i):
+        with torch.no_grad():
+            return net(*dev_sets[i % NSETS], None, "test")
+
+    out_host = None
+
+    def fwd_host(i):
+        nonlocal out_host
+        out_host = net.forward_host(*host_sets[i % NSETS], out=out_host)
+        return out_host
+
+    def timed(fn, steps):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for i in range(steps):
+            flush.zero_()                                       # L2 flush between timed iterations (outside the events)
+            ev[i][0].record()
+            fn(i)
+            ev[i][1].record()
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    for i in range(W):
+        fwd_dev(i)
+    torch.cuda.synchronize()
+    if args.ncu:                      # under a profiler: just run K more forwards and leave (never a bench value)
+        for i in range(K):
+            fwd_dev(i)
+        torch.cuda.synchronize()
+        print(json.dumps({"ncu_harness": True, "launches_per_step": net.launches_per_forward()}))
+        return
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev = timed(fwd_dev, K)
+    launches = net.launches_per_forward()
+    for i in range(W):
+        fwd_host(i)
+    ms_host = timed(fwd_host, K)
+    clocks = sampler.stop() if sampler else None
+    total_pairs = B * world
+
+    # profiled pass: per-category device time (CUDA events around every launch, same stream)
+    prof, cpu = None, None
+    if rank == 0:
+        net.set_profiling(True)
+        acc = {}
+        PR = 3
+        for i in range(PR):
+            flush.zero_()
+            fwd_dev(i)
+            for k, (ms, cnt, work) in net.read_profile().items():
+                a = acc.setdefault(k, [0.0, 0, 0.0])
+                a[0] += ms; a[1] += cnt; a[2] += work
+        net.set_profiling(False)
+        prof = {k: {"ms_per_step": v[0] / PR, "launches_per_step": v[1] // PR, "gflop_per_step": v[2] / PR / 1e9} for k, v in acc.items()}
+    if dist is not None:
+        dist.barrier()
+
+    if rank == 0:
+        peaks = load_peaks()
+        tot_ms = sum(v["ms_per_step"] for v in prof.values())
+        for v in prof.values():
+            v["share"] = v["ms_per_step"] / tot_ms
+            if v["gflop_per_step"] > 0:
+                v["tflops"] = v["gflop_per_step"] / v["ms_per_step"]
+        dom = "gemm_setconv2_l2"
+        d = prof[dom]
+        achieved = d["gflop_per_step"] / d["ms_per_step"]       # GFLOP/ms == TFLOP/s
+        roofline = {"kernel": "gemm_nt_kernel<128> (set-conv #2 layer 2, 512->256 over N*K neighbour columns)",
+                    "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"],
+                    "unit": "TFLOP/s", "frac": achieved / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]),
+                    "peak_source": peaks["source"] + " cuBLAS bf16 (sustained)", "traffic": None,
+                    "launches_per_step": d["launches_per_step"], "avg_launch_ms": d["ms_per_step"] / max(1, d["launches_per_step"]),
+                    "note": "strict-fp32 FMA build of the kernel (no tensor cores yet): the fp32 FMA ceiling of the chip is ~1/20 of this peak"}
+        if not args.no_cpu_baseline and world == 1:
+            v, spp = time_cpu_port(4, N, 2, 1, cores)
+            cpu = {"value": v, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
+                   "sample": f"4 pairs/step x 2 steps (N={N}), oracle/cmflow_oracle.py CPU port of the reference forward, {cores} threads"}
+        h2d = 4 * B * 3 * N * 4
+        d2h = B * 3 * N * 4 + B * N * 4 + B * 16 * 4 + B * N
+        line = {
+            "metric": "frame-pairs/sec CMFlow forward", "value": total_pairs * K / (ms_dev / 1e3), "unit": "frame-pairs/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic radar pairs (cmflow_b200/synth.py), seeded random-init weights of the CMFlow architecture",
+            "config": {"workload": workload, "points": N, "pairs_per_gpu": B, "global_batch": total_pairs, "parallelism": f"dp{world}",
+                       "l2": "256 MB flush between timed steps; 4 rotating input batches", "precision_mode": "strict-fp32"},
+            "e2e": {"value": total_pairs * K / (ms_host / 1e3), "unit": "frame-pairs/s", "ms_per_step": ms_host / K,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches * K, "launches_per_step": launches,
+            "clocks": clocks, "roofline": roofline, "kernels": prof, "cpu_baseline": cpu,
+            "workspace_bytes": net.workspace_bytes(),
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

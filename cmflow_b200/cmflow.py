@@ -112,6 +112,17 @@ class _EngineModel(nn.Module):
     def launches_per_forward(self):
         return lib().cmf_model_launches_per_forward(self._handle) if self._handle else 0
 
+    def set_profiling(self, enable):
+        check(lib().cmf_model_set_profiling(self._handle, int(bool(enable))))
+
+    def read_profile(self):
+        """{category: (device ms, launches, algorithmic FLOPs)} of the last forward (needs set_profiling(True))."""
+        L = lib()
+        n = L.cmf_model_profile_categories()
+        ms = (ctypes.c_float * n)(); cnt = (ctypes.c_int * n)(); work = (ctypes.c_double * n)()
+        check(L.cmf_model_read_profile(self._handle, ms, cnt, work))
+        return {L.cmf_model_profile_name(i).decode(): (ms[i], cnt[i], work[i]) for i in range(n)}
+
     def workspace_bytes(self):
         return lib().cmf_model_workspace_bytes(self._handle) if self._handle else 0
 

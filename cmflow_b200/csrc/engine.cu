@@ -132,7 +132,18 @@ struct cmf_model {
     float *d_in = nullptr, *d_out = nullptr; size_t d_in_floats = 0, d_out_bytes = 0;
     int launches = 0;
     int last_b = 0, last_n = 0;
+    // profiling
+    struct ProfRec { int cat; cudaEvent_t e0, e1; };
+    int profiling = 0;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> pool; size_t pool_used = 0;
+    double work[16] = {0}; int nlaunch[16] = {0}; float ms[16] = {0};
 };
+
+static void prof_events(cmf_model *m, cudaEvent_t *a, cudaEvent_t *b) {
+    while (m->pool.size() < m->pool_used + 2) { cudaEvent_t e; cudaEventCreate(&e); m->pool.push_back(e); }
+    *a = m->pool[m->pool_used++]; *b = m->pool[m->pool_used++];
+}
 
 static GemmArgs mk(const float *W, int ldw, const float *X, int ldx, float *Out, int ldo, const float *bias,
                    int M, int K, long long cols, int act, const float *pbias = nullptr, int pb_ld = 0, int cpp = 1) {
@@ -143,12 +154,26 @@ static GemmArgs mk(const float *W, int ldw, const float *X, int ldx, float *Out,
     return g;
 }
 
-#define RUN(call)                    \
-    do {                             \
-        int rc_ = (call);            \
-        if (rc_ != CMF_OK) return rc_; \
-        ++m->launches;               \
+// One launch: category (for the per-category device timers of cmf_model_read_profile) and its algorithmic
+// work (FLOPs for the GEMM categories, bytes for the others).
+#define RUN(cat_, work_, call)                                      \
+    do {                                                            \
+        cudaEvent_t e0_ = nullptr, e1_ = nullptr;                   \
+        if (m->profiling) { prof_events(m, &e0_, &e1_); cudaEventRecord(e0_, st); } \
+        int rc_ = (call);                                           \
+        if (rc_ != CMF_OK) return rc_;                              \
+        if (m->profiling) { cudaEventRecord(e1_, st); m->prof.push_back({(cat_), e0_, e1_}); } \
+        m->work[(cat_)] += (double)(work_);                         \
+        ++m->nlaunch[(cat_)];                                       \
+        ++m->launches;                                              \
     } while (0)
+
+enum { C_SEARCH = 0, C_GEMM_SC1, C_GEMM_FC_HOIST, C_GEMM_FC_MLP, C_GEMM_SC2_HOIST, C_GEMM_SC2_L2, C_GEMM_SC2_L3,
+       C_GEMM_POINTWISE, C_GATHER, C_REDUCE, C_HEAD_KABSCH, C_COUNT };
+static const char *const kCatNames[C_COUNT] = {"search", "gemm_setconv1", "gemm_flowembed_hoist", "gemm_flowembed_mlp",
+    "gemm_setconv2_hoist", "gemm_setconv2_l2", "gemm_setconv2_l3", "gemm_pointwise", "gather_build", "reduce", "head_kabsch"};
+static double gflops(const GemmArgs &g) { return 2.0 * g.M * (double)g.K * g.cols; }
+static double gflops(const GemmBatch &gb) { double f = 0; for (int i = 0; i < gb.count; ++i) f += gflops(gb.g[i]); return f; }
 
 static size_t chunk_bytes(int bc, int n) {
     Arena a; Work w;
@@ -190,7 +215,7 @@ static int run_mse_layer(cmf_model *m, int bc, int n, const float *pc, const flo
                          float *dest, int ldd, float *G, cudaStream_t st) {
     Work &w = m->w;
     const long long bn = (long long)bc * n;
-    RUN(cmf_launch_build_x0(bc, n, pc, ft, bq, w.X0, st));
+    RUN(C_GATHER, 0, cmf_launch_build_x0(bc, n, pc, ft, bq, w.X0, st));
     GemmBatch gb;
     gb.count = 4;
     for (int s = 0; s < 4; ++s) {
@@ -198,21 +223,21 @@ static int run_mse_layer(cmf_model *m, int bc, int n, const float *pc, const flo
         gb.g[s] = mk(m->seg[sb + 0], 8, w.X0 + (size_t)bn * KOFF[s] * 8, 8, w.T32a + (size_t)bn * KOFF[s] * 32, 32,
                      m->seg[sb + 1], 32, 8, bn * KS[s], CMF_ACT_RELU);
     }
-    RUN(cmf_launch_gemm(gb, st));
+    RUN(C_GEMM_SC1, gflops(gb), cmf_launch_gemm(gb, st));
     for (int s = 0; s < 4; ++s) {
         const int sb = M1_BASE + s * 12;
         gb.g[s] = mk(m->seg[sb + 2], 32, w.T32a + (size_t)bn * KOFF[s] * 32, 32, w.T32b + (size_t)bn * KOFF[s] * 32, 32,
                      m->seg[sb + 3], 32, 32, bn * KS[s], CMF_ACT_RELU);
     }
-    RUN(cmf_launch_gemm(gb, st));
+    RUN(C_GEMM_SC1, gflops(gb), cmf_launch_gemm(gb, st));
     for (int s = 0; s < 4; ++s) {
         const int sb = M1_BASE + s * 12;
         gb.g[s] = mk(m->seg[sb + 4], 32, w.T32b + (size_t)bn * KOFF[s] * 32, 32, w.T64 + (size_t)bn * KOFF[s] * 64, 64,
                      m->seg[sb + 5], 64, 32, bn * KS[s], CMF_ACT_RELU);
     }
-    RUN(cmf_launch_gemm(gb, st));
+    RUN(C_GEMM_SC1, gflops(gb), cmf_launch_gemm(gb, st));
     for (int s = 0; s < 4; ++s)
-        RUN(cmf_launch_maxk(bn, KS[s], 64, w.T64 + (size_t)bn * KOFF[s] * 64, 64, w.M64 + s * 64, 256, st));
+        RUN(C_REDUCE, 0, cmf_launch_maxk(bn, KS[s], 64, w.T64 + (size_t)bn * KOFF[s] * 64, 64, w.M64 + s * 64, 256, st));
     const float *src[3] = {w.M64, w.Q1, w.Q2};
     float *dst[3] = {w.Q1, w.Q2, dest};
     const int lds[3] = {256, 256, 256}, ldo[3] = {256, 256, ldd};
@@ -221,9 +246,9 @@ static int run_mse_layer(cmf_model *m, int bc, int n, const float *pc, const flo
             const int sb = M1_BASE + s * 12 + 6 + l * 2;
             gb.g[s] = mk(m->seg[sb], 64, src[l] + s * 64, lds[l], dst[l] + s * 64, ldo[l], m->seg[sb + 1], 64, 64, bn, CMF_ACT_RELU);
         }
-        RUN(cmf_launch_gemm(gb, st));
+        RUN(C_GEMM_POINTWISE, gflops(gb), cmf_launch_gemm(gb, st));
     }
-    RUN(cmf_launch_globalmax(bc, n, 256, dest, ldd, G, st));
+    RUN(C_REDUCE, 0, cmf_launch_globalmax(bc, n, 256, dest, ldd, G, st));
     return CMF_OK;
 }
 
@@ -235,40 +260,40 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
     auto S = [&](int i) { return m->seg[i]; };
 
     // neighbour search
-    RUN(cmf_launch_transpose3(bc, n, pc1, w.X1T, st));
-    RUN(cmf_launch_transpose3(bc, n, pc2, w.X2T, st));
-    RUN(cmf_launch_ball_query_ms(bc, n, pc1, w.BQ1, st));
-    RUN(cmf_launch_ball_query_ms(bc, n, pc2, w.BQ2, st));
-    RUN(cmf_launch_knn_point8(bc, n, w.X2T, w.X1T, w.KNN12, st));
-    RUN(cmf_launch_knn_point8(bc, n, w.X1T, w.X1T, w.KNN11, st));
+    RUN(C_SEARCH, 0, cmf_launch_transpose3(bc, n, pc1, w.X1T, st));
+    RUN(C_SEARCH, 0, cmf_launch_transpose3(bc, n, pc2, w.X2T, st));
+    RUN(C_SEARCH, 0, cmf_launch_ball_query_ms(bc, n, pc1, w.BQ1, st));
+    RUN(C_SEARCH, 0, cmf_launch_ball_query_ms(bc, n, pc2, w.BQ2, st));
+    RUN(C_SEARCH, 0, cmf_launch_knn_point8(bc, n, w.X2T, w.X1T, w.KNN12, st));
+    RUN(C_SEARCH, 0, cmf_launch_knn_point8(bc, n, w.X1T, w.X1T, w.KNN11, st));
 
     // multi-scale encoders (cmflow.py:72-77); cloud 1 writes straight into the embedding rows E[:, 0:256]
     { int rc = run_mse_layer(m, bc, n, pc1, ft1, w.BQ1, w.E, E_LD, w.G1, st); if (rc) return rc; }
     { int rc = run_mse_layer(m, bc, n, pc2, ft2, w.BQ2, w.F2, 256, w.G2, st); if (rc) return rc; }
-    RUN(cmf_launch_scatter_ft(bc, n, ft1, w.E, E_LD, 768, 5, st));
+    RUN(C_GATHER, 0, cmf_launch_scatter_ft(bc, n, ft1, w.E, E_LD, 768, 5, st));
 
     // flow embedding (FeatureCorrelator, radarflow_util.py:185-237)
-    RUN(cmf_launch_gemm1(mk(S(FC_WCG), 256, w.G1, 256, w.PB1, 512, S(FC_B1), 512, 256, bc, CMF_ACT_NONE), st));
-    RUN(cmf_launch_gemm1(mk(S(FC_WNG), 256, w.G2, 256, w.PB2, 512, nullptr, 512, 256, bc, CMF_ACT_NONE), st));
-    RUN(cmf_launch_gemm1(mk(S(FC_WC), 256, w.E, E_LD, w.U1, 512, nullptr, 512, 256, bn, CMF_ACT_NONE, w.PB1, 512, n), st));
-    RUN(cmf_launch_gemm1(mk(S(FC_WN), 256, w.F2, 256, w.U2, 512, nullptr, 512, 256, bn, CMF_ACT_NONE, w.PB2, 512, n), st));
-    RUN(cmf_launch_fc_build_h1(bc, n, pc1, pc2, w.KNN12, w.U1, w.U2, S(FC_WD), w.H1, st));
-    RUN(cmf_launch_gemm1(mk(S(FC_W2), 512, w.H1, 512, w.H2, 512, S(FC_B2), 512, 512, bn * 8, CMF_ACT_LEAKY), st));
-    RUN(cmf_launch_gemm1(mk(S(FC_W3), 512, w.H2, 512, w.H1, 512, S(FC_B3), 512, 512, bn * 8, CMF_ACT_LEAKY), st));
+    { const GemmArgs ga_ = mk(S(FC_WCG), 256, w.G1, 256, w.PB1, 512, S(FC_B1), 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
+    { const GemmArgs ga_ = mk(S(FC_WNG), 256, w.G2, 256, w.PB2, 512, nullptr, 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
+    { const GemmArgs ga_ = mk(S(FC_WC), 256, w.E, E_LD, w.U1, 512, nullptr, 512, 256, bn, CMF_ACT_NONE, w.PB1, 512, n); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
+    { const GemmArgs ga_ = mk(S(FC_WN), 256, w.F2, 256, w.U2, 512, nullptr, 512, 256, bn, CMF_ACT_NONE, w.PB2, 512, n); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
+    RUN(C_GATHER, 0, cmf_launch_fc_build_h1(bc, n, pc1, pc2, w.KNN12, w.U1, w.U2, S(FC_WD), w.H1, st));
+    { const GemmArgs ga_ = mk(S(FC_W2), 512, w.H1, 512, w.H2, 512, S(FC_B2), 512, 512, bn * 8, CMF_ACT_LEAKY); RUN(C_GEMM_FC_MLP, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
+    { const GemmArgs ga_ = mk(S(FC_W3), 512, w.H2, 512, w.H1, 512, S(FC_B3), 512, 512, bn * 8, CMF_ACT_LEAKY); RUN(C_GEMM_FC_MLP, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     WeightNetP wn1{S(WN1_BASE), S(WN1_BASE + 1), S(WN1_BASE + 2), S(WN1_BASE + 3), S(WN1_BASE + 4), S(WN1_BASE + 5)};
     WeightNetP wn2{S(WN2_BASE), S(WN2_BASE + 1), S(WN2_BASE + 2), S(WN2_BASE + 3), S(WN2_BASE + 4), S(WN2_BASE + 5)};
-    RUN(cmf_launch_fc_reduce(bc, n, pc1, pc2, w.KNN12, wn1, w.H1, 0, w.COST1, 512, st));
-    RUN(cmf_launch_fc_reduce(bc, n, pc1, pc1, w.KNN11, wn2, w.COST1, 1, w.E + 256, E_LD, st));
+    RUN(C_REDUCE, 0, cmf_launch_fc_reduce(bc, n, pc1, pc2, w.KNN12, wn1, w.H1, 0, w.COST1, 512, st));
+    RUN(C_REDUCE, 0, cmf_launch_fc_reduce(bc, n, pc1, pc1, w.KNN11, wn2, w.COST1, 1, w.E + 256, E_LD, st));
 
     // set-conv #2 (mse_layer2, cmflow.py:87-89)
-    RUN(cmf_launch_gemm1(mk(S(M2_WG), 256, w.G1, 256, w.PBM, 2048, S(M2_T1), 2048, 256, bc, CMF_ACT_NONE), st));
-    RUN(cmf_launch_gemm1(mk(S(M2_WP), E_LD, w.E, E_LD, w.P, 2048, nullptr, 2048, E_LD, bn, CMF_ACT_NONE, w.PBM, 2048, n), st));
+    { const GemmArgs ga_ = mk(S(M2_WG), 256, w.G1, 256, w.PBM, 2048, S(M2_T1), 2048, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_SC2_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
+    { const GemmArgs ga_ = mk(S(M2_WP), E_LD, w.E, E_LD, w.P, 2048, nullptr, 2048, E_LD, bn, CMF_ACT_NONE, w.PBM, 2048, n); RUN(C_GEMM_SC2_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     for (int s = 0; s < 4; ++s) {
         const int sb = M2_BASE + s * 10;
-        RUN(cmf_launch_mse2_build_y1(bc, n, KS[s], KOFF[s], pc1, w.BQ1, w.P, 2048, s * 512, S(M2_WX) + (size_t)s * 512 * 4, w.Y1, st));
-        RUN(cmf_launch_gemm1(mk(S(sb), 512, w.Y1, 512, w.Y2, 256, S(sb + 1), 256, 512, bn * KS[s], CMF_ACT_RELU), st));
-        RUN(cmf_launch_gemm1(mk(S(sb + 2), 256, w.Y2, 256, w.Y3, 64, S(sb + 3), 64, 256, bn * KS[s], CMF_ACT_RELU), st));
-        RUN(cmf_launch_maxk(bn, KS[s], 64, w.Y3, 64, w.M64 + s * 64, 256, st));
+        RUN(C_GATHER, 0, cmf_launch_mse2_build_y1(bc, n, KS[s], KOFF[s], pc1, w.BQ1, w.P, 2048, s * 512, S(M2_WX) + (size_t)s * 512 * 4, w.Y1, st));
+        { const GemmArgs ga_ = mk(S(sb), 512, w.Y1, 512, w.Y2, 256, S(sb + 1), 256, 512, bn * KS[s], CMF_ACT_RELU); RUN(C_GEMM_SC2_L2, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
+        { const GemmArgs ga_ = mk(S(sb + 2), 256, w.Y2, 256, w.Y3, 64, S(sb + 3), 64, 256, bn * KS[s], CMF_ACT_RELU); RUN(C_GEMM_SC2_L3, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
+        RUN(C_REDUCE, 0, cmf_launch_maxk(bn, KS[s], 64, w.Y3, 64, w.M64 + s * 64, 256, st));
     }
     {
         GemmBatch gb; gb.count = 4;
@@ -279,34 +304,34 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
                 const int sb = M2_BASE + s * 10 + 4 + l * 2;
                 gb.g[s] = mk(S(sb), 64, src[l] + s * 64, 256, dst[l] + s * 64, 256, S(sb + 1), 64, 64, bn, CMF_ACT_RELU);
             }
-            RUN(cmf_launch_gemm(gb, st));
+            RUN(C_GEMM_POINTWISE, gflops(gb), cmf_launch_gemm(gb, st));
         }
     }
-    RUN(cmf_launch_globalmax(bc, n, 256, w.PROP, 256, w.GP, st));
+    RUN(C_REDUCE, 0, cmf_launch_globalmax(bc, n, 256, w.PROP, 256, w.GP, st));
     const float *gvec = w.GP;
     if (m->temporal) {            // CMFlow-T: GRU over the global feature (cmflow_t.py:94-105)
-        RUN(cmf_launch_gemm1(mk(S(GRU_WIH), 256, w.GP, 256, w.GI, 768, S(GRU_BIH), 768, 256, bc, CMF_ACT_NONE), st));
-        RUN(cmf_launch_gemm1(mk(S(GRU_WHH), 256, gprev ? gprev : w.ZERO, 256, w.GH, 768, S(GRU_BHH), 768, 256, bc, CMF_ACT_NONE), st));
+        { const GemmArgs ga_ = mk(S(GRU_WIH), 256, w.GP, 256, w.GI, 768, S(GRU_BIH), 768, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_POINTWISE, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
+        { const GemmArgs ga_ = mk(S(GRU_WHH), 256, gprev ? gprev : w.ZERO, 256, w.GH, 768, S(GRU_BHH), 768, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_POINTWISE, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
         float *gnew = gfeat_out ? gfeat_out : w.GNEW;
-        RUN(cmf_launch_gru_gates(bc, w.GI, w.GH, gprev, gnew, st));
+        RUN(C_HEAD_KABSCH, 0, cmf_launch_gru_gates(bc, w.GI, w.GH, gprev, gnew, st));
         gvec = gnew;
     }
 
     // heads (FlowHead / MotionHead, radarflow_util.py:240-285), first layer stacked [fp ; mp]
-    RUN(cmf_launch_gemm1(mk(S(HD_W1G), 256, gvec, 256, w.PBH, 512, S(HD_T1), 512, 256, bc, CMF_ACT_NONE), st));
-    RUN(cmf_launch_gemm1(mk(S(HD_W1), 256, w.PROP, 256, w.HD1, 512, nullptr, 512, 256, bn, CMF_ACT_RELU, w.PBH, 512, n), st));
+    { const GemmArgs ga_ = mk(S(HD_W1G), 256, gvec, 256, w.PBH, 512, S(HD_T1), 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_POINTWISE, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
+    { const GemmArgs ga_ = mk(S(HD_W1), 256, w.PROP, 256, w.HD1, 512, nullptr, 512, 256, bn, CMF_ACT_RELU, w.PBH, 512, n); RUN(C_GEMM_POINTWISE, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     {
         GemmBatch gb; gb.count = 2;
         gb.g[0] = mk(S(HD_W2F), 256, w.HD1, 512, w.HD2, 256, S(HD_T2F), 128, 256, bn, CMF_ACT_RELU);
         gb.g[1] = mk(S(HD_W2M), 256, w.HD1 + 256, 512, w.HD2 + 128, 256, S(HD_T2M), 128, 256, bn, CMF_ACT_RELU);
-        RUN(cmf_launch_gemm(gb, st));
+        RUN(C_GEMM_POINTWISE, gflops(gb), cmf_launch_gemm(gb, st));
         gb.g[0] = mk(S(HD_W3F), 128, w.HD2, 256, w.HD3, 128, S(HD_T3F), 64, 128, bn, CMF_ACT_RELU);
         gb.g[1] = mk(S(HD_W3M), 128, w.HD2 + 128, 256, w.HD3 + 64, 128, S(HD_T3M), 64, 128, bn, CMF_ACT_RELU);
-        RUN(cmf_launch_gemm(gb, st));
+        RUN(C_GEMM_POINTWISE, gflops(gb), cmf_launch_gemm(gb, st));
     }
-    RUN(cmf_launch_head_final(bc, n, w.HD3, 128, S(HD_W4), S(HD_W4) + 192, w.FLOW, stat_cls, st));
+    RUN(C_HEAD_KABSCH, 0, cmf_launch_head_final(bc, n, w.HD3, 128, S(HD_W4), S(HD_W4) + 192, w.FLOW, stat_cls, st));
     // ego-motion head + refinement (cmflow.py:96-125); CMFlow-T omits the +1e-4 (cmflow_t.py:119)
-    RUN(cmf_launch_kabsch(bc, n, pc1, w.FLOW, 1, stat_cls, 1, m->temporal ? 0.f : 1e-4f, m->stat_thres, pre_trans, sf_agg, mask, st));
+    RUN(C_HEAD_KABSCH, 0, cmf_launch_kabsch(bc, n, pc1, w.FLOW, 1, stat_cls, 1, m->temporal ? 0.f : 1e-4f, m->stat_thres, pre_trans, sf_agg, mask, st));
     return CMF_OK;
 }
 
@@ -354,6 +379,7 @@ extern "C" void cmf_model_destroy(cmf_model *m) {
     if (m->d_blob) cudaFree(m->d_blob);
     if (m->d_in) cudaFree(m->d_in);
     if (m->d_out) cudaFree(m->d_out);
+    for (cudaEvent_t e : m->pool) cudaEventDestroy(e);
     delete m;
 }
 
@@ -374,6 +400,8 @@ extern "C" int cmf_model_forward(cmf_model *m, int b, int n, const float *pc1, c
     if (rc != CMF_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     m->launches = 0;
+    for (int i = 0; i < 16; ++i) { m->work[i] = 0; m->nlaunch[i] = 0; }
+    m->prof.clear(); m->pool_used = 0;
     m->last_b = b < m->cap_bc ? b : m->cap_bc; m->last_n = n;
     const size_t pn = (size_t)3 * n;
     for (int b0 = 0; b0 < b; b0 += m->cap_bc) {
@@ -426,6 +454,26 @@ extern "C" int cmf_model_forward_host(cmf_model *m, int b, int n, const float *p
     CMF_CUDA(cudaMemcpyAsync(mask, d_mask, (size_t)b * n, cudaMemcpyDeviceToHost, st));
     if (m->temporal && gfeat_out) CMF_CUDA(cudaMemcpyAsync(gfeat_out, d_go, (size_t)b * 256 * sizeof(float), cudaMemcpyDeviceToHost, st));
     CMF_CUDA(cudaStreamSynchronize(st));
+    return CMF_OK;
+}
+
+extern "C" int cmf_model_set_profiling(cmf_model *m, int enable) {
+    CMF_REQUIRE(m, "null model");
+    m->profiling = enable ? 1 : 0;
+    return CMF_OK;
+}
+extern "C" int cmf_model_profile_categories(void) { return C_COUNT; }
+extern "C" const char *cmf_model_profile_name(int cat) { return (cat >= 0 && cat < C_COUNT) ? kCatNames[cat] : ""; }
+
+extern "C" int cmf_model_read_profile(cmf_model *m, float *ms, int *launches, double *work) {
+    CMF_REQUIRE(m && ms && launches && work, "null pointer");
+    for (int i = 0; i < C_COUNT; ++i) { ms[i] = 0.f; launches[i] = m->nlaunch[i]; work[i] = m->work[i]; }
+    for (const auto &r : m->prof) {
+        CMF_CUDA(cudaEventSynchronize(r.e1));
+        float t = 0.f;
+        CMF_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+        ms[r.cat] += t;
+    }
     return CMF_OK;
 }
 

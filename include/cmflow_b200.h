@@ -158,9 +158,18 @@ int cmf_model_forward_host(cmf_model *m, int b, int n,
                            float *sf_agg, float *stat_cls, float *pre_trans, uint8_t *mask, float *gfeat_out,
                            void *stream);
 
+/* Per-category device timers.  When enabled, every launch of the next forwards is bracketed by CUDA events on
+ * the launching stream; cmf_model_read_profile() waits for the last forward and returns, per category
+ * (cmf_model_profile_categories() of them, named by cmf_model_profile_name()), the summed device time in ms,
+ * the launch count and the algorithmic work (FLOPs for gemm_* categories, 0 otherwise) of that forward. */
+int cmf_model_set_profiling(cmf_model *m, int enable);
+int cmf_model_profile_categories(void);
+const char *cmf_model_profile_name(int cat);
+int cmf_model_read_profile(cmf_model *m, float *ms, int *launches, double *work);
+
 /* Debug taps (device pointers into the workspace of the last forward; NULL if not produced):
- * "f1","f2" (B,N,256) | "g1","g2" (B,256) | "cor" (B,N,512) | "prop" (B,N,256) | "flow" (B,3,N)
- * | "bq1","bq2" (B,N,60) int32 | "knn12","knn11" (B,N,8) int32. */
+ * "E" (B,N,776) = [f1 256 | cor 512 | ft 3 | pad 5] | "f2" (B,N,256) | "g1","g2","gp" (B,256) | "prop" (B,N,256)
+ * | "flow" (B,3,N) | "bq1","bq2" (B,N,60) int32 | "knn12","knn11" (B,N,8) int32 | "P" (B,N,2048) | "cost1","u1","u2" (B,N,512). */
 const void *cmf_model_tap(const cmf_model *m, const char *name);
 
 #ifdef __cplusplus

@@ -43,12 +43,17 @@ def test_ball_query_bit_exact(B, N, M, radius, nsample):
 def test_knn_bit_exact(B, N, M, k):
     known, unk = cloud(B, N, 3, dup=min(8, N // 4)), cloud(B, M, 4)
     d2w, iw = P.knn(k, unk, known)
-    dist, idx = PU.knn(k, unk.to(DEV), known.to(DEV))
+    from cmflow_b200 import pointnet2_cuda as K
+    d2 = torch.empty(B, M, k, device=DEV)
+    idx = torch.empty(B, M, k, dtype=torch.int32, device=DEV)
+    K.knn_wrapper(B, M, N, k, unk.to(DEV), known.to(DEV), d2, idx)          # raw kernel output: squared distances
     assert torch.equal(idx.cpu(), iw)
-    assert torch.equal(dist.cpu(), torch.sqrt(d2w))                        # KNN.forward returns sqrt (pointnet2_utils.py:97)
+    assert torch.equal(d2.cpu(), d2w)
+    dist, idx2 = PU.knn(k, unk.to(DEV), known.to(DEV))                      # KNN.forward returns sqrt (pointnet2_utils.py:97)
+    assert torch.equal(idx2, idx) and torch.equal(dist, torch.sqrt(d2))
     if R.available():
         d2r, ir = R.knn(k, unk.to(DEV), known.to(DEV))
-        assert torch.equal(idx, ir) and torch.equal(dist, torch.sqrt(d2r))
+        assert torch.equal(idx, ir) and torch.equal(d2, d2r)
 
 
 @pytest.mark.parametrize("B,N,M", SHAPES)
@@ -56,7 +61,7 @@ def test_three_nn_and_interpolate_bit_exact(B, N, M):
     known, unk = cloud(B, N, 5), cloud(B, M, 6)
     d2w, iw = P.three_nn(unk, known)
     dist, idx = PU.three_nn(unk.to(DEV), known.to(DEV))
-    assert torch.equal(idx.cpu(), iw) and torch.equal(dist.cpu(), torch.sqrt(d2w))
+    assert torch.equal(idx.cpu(), iw) and torch.equal(dist, torch.sqrt(d2w.to(DEV)))
     g = torch.Generator().manual_seed(7)
     feats = torch.randn(B, 19, N, generator=g)
     w = torch.rand(B, M, 3, generator=g)
@@ -66,7 +71,7 @@ def test_three_nn_and_interpolate_bit_exact(B, N, M):
     if R.available():
         assert torch.equal(got, R.three_interpolate(feats.to(DEV), idx, w.to(DEV)))
         d2r, ir = R.three_nn(unk.to(DEV), known.to(DEV))
-        assert torch.equal(idx, ir) and torch.equal(dist, torch.sqrt(d2r))
+        assert torch.equal(idx, ir) and torch.equal(d2r.cpu(), d2w)
 
 
 @pytest.mark.parametrize("B,C,N,Pn,S", [(2, 6, 256, 256, 4), (3, 1027, 200, 200, 8), (1, 64, 4096, 4096, 32), (2, 3, 40, 7, 5)])
