@@ -107,10 +107,18 @@ class _EngineModel(nn.Module):
                 check(L.cmf_model_create(ctypes.byref(h), blob.ctypes.data_as(ctypes.c_void_p), blob.size,
                                          int(self._temporal), float(self.stat_thres)))
             self._handle = h
+            if getattr(self, "_mode", None) is not None:
+                check(L.cmf_model_set_mode(h, self._mode))
         return self._handle
 
     def launches_per_forward(self):
         return lib().cmf_model_launches_per_forward(self._handle) if self._handle else 0
+
+    def set_precision(self, mode):
+        """'fp32' = strict fp32 FMA kernels (parity build); 'tf32x3' = tcgen05 tensor cores, 3xTF32 split precision."""
+        self._mode = {"fp32": 0, "tf32x3": 1}[mode]
+        if self._handle is not None:
+            check(lib().cmf_model_set_mode(self._handle, self._mode))
 
     def set_profiling(self, enable):
         check(lib().cmf_model_set_profiling(self._handle, int(bool(enable))))

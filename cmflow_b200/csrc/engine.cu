@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "model_kernels.cuh"
+#include "tc_gemm.cuh"
 
 namespace {
 
@@ -28,7 +29,7 @@ constexpr int HDR = 512;                 // header floats (int32 view): magic, n
 constexpr int MAGIC = 0x434D4642;        // "CMFB"
 constexpr int KS[4] = {4, 8, 16, 32};
 constexpr int KOFF[4] = {0, 4, 12, 28};
-constexpr int E_LD = 776;                // embedding row: [f1 256 | cor 512 | ft 3 | pad 5]
+constexpr int E_LD = 800;                // embedding row: [f1 256 | cor 512 | ft 3 | zero pad 29] (K padded to a multiple of 32 for the tensor-core path)
 
 // ---- segment table (order is the contract with cmflow_b200/weights.py) ---------------------------
 enum {
@@ -132,6 +133,11 @@ struct cmf_model {
     float *d_in = nullptr, *d_out = nullptr; size_t d_in_floats = 0, d_out_bytes = 0;
     int launches = 0;
     int last_b = 0, last_n = 0;
+    // tensor-core (tcgen05, 3xTF32) mode: pre-tiled hi/lo copies of the big weight matrices
+    int tc = 0;
+    float *tc_buf = nullptr;
+    const float *t_fc_wc = nullptr, *t_fc_wn = nullptr, *t_fc_w2 = nullptr, *t_fc_w3 = nullptr, *t_m2_wp = nullptr,
+                *t_m2_w2[4] = {nullptr, nullptr, nullptr, nullptr}, *t_m2_w3[4] = {nullptr, nullptr, nullptr, nullptr}, *t_hd_w1 = nullptr;
     // profiling
     struct ProfRec { int cat; cudaEvent_t e0, e1; };
     int profiling = 0;
@@ -174,6 +180,42 @@ static const char *const kCatNames[C_COUNT] = {"search", "gemm_setconv1", "gemm_
     "gemm_setconv2_hoist", "gemm_setconv2_l2", "gemm_setconv2_l3", "gemm_pointwise", "gather_build", "reduce", "head_kabsch"};
 static double gflops(const GemmArgs &g) { return 2.0 * g.M * (double)g.K * g.cols; }
 static double gflops(const GemmBatch &gb) { double f = 0; for (int i = 0; i < gb.count; ++i) f += gflops(gb.g[i]); return f; }
+
+static TcArgs tc_plain(const float *Wt, int M, int K, const float *X, int ldx, float *Out, int ldo, const float *bias,
+                       long long cols, int act, const float *pbias = nullptr, int pb_ld = 0, int cpp = 1) {
+    TcArgs a{};
+    a.Wt = Wt; a.m_blocks = cmf_divup(M, 128); a.k_blocks = cmf_divup(K, 32); a.M = M; a.cols = cols;
+    a.prod = TC_PROD_PLAIN; a.X = X; a.ldx = ldx;
+    a.epi = TC_EPI_STORE; a.Out = Out; a.ldo = ldo; a.bias = bias; a.pbias = pbias; a.pb_ld = pb_ld; a.cols_per_pair = cpp; a.act = act;
+    a.ksamp = 1;
+    return a;
+}
+static double tflops(const TcArgs &a, int K) { return 2.0 * a.M * (double)K * (double)a.cols; }
+
+static int ensure_tc_weights(cmf_model *m) {
+    if (m->tc_buf) return CMF_OK;
+    struct Item { const float **dst; int seg, M, K, ldw; };
+    std::vector<Item> items = {
+        {&m->t_fc_wc, FC_WC, 512, 256, 256}, {&m->t_fc_wn, FC_WN, 512, 256, 256}, {&m->t_fc_w2, FC_W2, 512, 512, 512},
+        {&m->t_fc_w3, FC_W3, 512, 512, 512}, {&m->t_m2_wp, M2_WP, 2048, E_LD, E_LD}, {&m->t_hd_w1, HD_W1, 512, 256, 256}};
+    for (int s = 0; s < 4; ++s) {
+        items.push_back({&m->t_m2_w2[s], M2_BASE + s * 10, 256, 512, 512});
+        items.push_back({&m->t_m2_w3[s], M2_BASE + s * 10 + 2, 64, 256, 256});
+    }
+    size_t tot = 0;
+    for (auto &it : items) tot += cmf_tc_tiled_floats(it.M, it.K);
+    cudaError_t e = cudaMalloc(&m->tc_buf, tot * sizeof(float));
+    if (e != cudaSuccess) { cmf_set_error("tc weights cudaMalloc failed: %s", cudaGetErrorString(e)); return CMF_ERR_NOMEM; }
+    size_t off = 0;
+    for (auto &it : items) {
+        int rc = cmf_tc_tile_weights(m->seg[it.seg], it.ldw, it.M, it.K, m->tc_buf + off, 0);
+        if (rc) return rc;
+        *it.dst = m->tc_buf + off;
+        off += cmf_tc_tiled_floats(it.M, it.K);
+    }
+    CMF_CUDA(cudaDeviceSynchronize());
+    return CMF_OK;
+}
 
 static size_t chunk_bytes(int bc, int n) {
     Arena a; Work w;
@@ -270,16 +312,28 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
     // multi-scale encoders (cmflow.py:72-77); cloud 1 writes straight into the embedding rows E[:, 0:256]
     { int rc = run_mse_layer(m, bc, n, pc1, ft1, w.BQ1, w.E, E_LD, w.G1, st); if (rc) return rc; }
     { int rc = run_mse_layer(m, bc, n, pc2, ft2, w.BQ2, w.F2, 256, w.G2, st); if (rc) return rc; }
-    RUN(C_GATHER, 0, cmf_launch_scatter_ft(bc, n, ft1, w.E, E_LD, 768, 5, st));
+    RUN(C_GATHER, 0, cmf_launch_scatter_ft(bc, n, ft1, w.E, E_LD, 768, E_LD - 771, st));
 
     // flow embedding (FeatureCorrelator, radarflow_util.py:185-237)
     { const GemmArgs ga_ = mk(S(FC_WCG), 256, w.G1, 256, w.PB1, 512, S(FC_B1), 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     { const GemmArgs ga_ = mk(S(FC_WNG), 256, w.G2, 256, w.PB2, 512, nullptr, 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
+    if (m->tc) {
+        { const TcArgs ta_ = tc_plain(m->t_fc_wc, 512, 256, w.E, E_LD, w.U1, 512, nullptr, bn, CMF_ACT_NONE, w.PB1, 512, n); RUN(C_GEMM_FC_HOIST, tflops(ta_, 256), cmf_launch_tc_gemm(ta_, st)); }
+        { const TcArgs ta_ = tc_plain(m->t_fc_wn, 512, 256, w.F2, 256, w.U2, 512, nullptr, bn, CMF_ACT_NONE, w.PB2, 512, n); RUN(C_GEMM_FC_HOIST, tflops(ta_, 256), cmf_launch_tc_gemm(ta_, st)); }
+        {   // conv1 with the gather + hoisted conv0 epilogue fused into the B-operand producer (no H1 round trip)
+            TcArgs ta_ = tc_plain(m->t_fc_w2, 512, 512, nullptr, 0, w.H2, 512, S(FC_B2), bn * 8, CMF_ACT_LEAKY);
+            ta_.prod = TC_PROD_FC_H1; ta_.U1 = w.U1; ta_.U2 = w.U2; ta_.ld_u2 = 512; ta_.off_u2 = 0; ta_.Wsmall = S(FC_WD);
+            ta_.xyz_q = pc1; ta_.xyz_c = pc2; ta_.nbr = w.KNN12; ta_.nbr_ld = 8; ta_.nbr_off = 0; ta_.ksamp = 8; ta_.n_pts = n;
+            RUN(C_GEMM_FC_MLP, tflops(ta_, 512), cmf_launch_tc_gemm(ta_, st));
+        }
+        { const TcArgs ta_ = tc_plain(m->t_fc_w3, 512, 512, w.H2, 512, w.H1, 512, S(FC_B3), bn * 8, CMF_ACT_LEAKY); RUN(C_GEMM_FC_MLP, tflops(ta_, 512), cmf_launch_tc_gemm(ta_, st)); }
+    } else {
     { const GemmArgs ga_ = mk(S(FC_WC), 256, w.E, E_LD, w.U1, 512, nullptr, 512, 256, bn, CMF_ACT_NONE, w.PB1, 512, n); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     { const GemmArgs ga_ = mk(S(FC_WN), 256, w.F2, 256, w.U2, 512, nullptr, 512, 256, bn, CMF_ACT_NONE, w.PB2, 512, n); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     RUN(C_GATHER, 0, cmf_launch_fc_build_h1(bc, n, pc1, pc2, w.KNN12, w.U1, w.U2, S(FC_WD), w.H1, st));
     { const GemmArgs ga_ = mk(S(FC_W2), 512, w.H1, 512, w.H2, 512, S(FC_B2), 512, 512, bn * 8, CMF_ACT_LEAKY); RUN(C_GEMM_FC_MLP, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     { const GemmArgs ga_ = mk(S(FC_W3), 512, w.H2, 512, w.H1, 512, S(FC_B3), 512, 512, bn * 8, CMF_ACT_LEAKY); RUN(C_GEMM_FC_MLP, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
+    }
     WeightNetP wn1{S(WN1_BASE), S(WN1_BASE + 1), S(WN1_BASE + 2), S(WN1_BASE + 3), S(WN1_BASE + 4), S(WN1_BASE + 5)};
     WeightNetP wn2{S(WN2_BASE), S(WN2_BASE + 1), S(WN2_BASE + 2), S(WN2_BASE + 3), S(WN2_BASE + 4), S(WN2_BASE + 5)};
     RUN(C_REDUCE, 0, cmf_launch_fc_reduce(bc, n, pc1, pc2, w.KNN12, wn1, w.H1, 0, w.COST1, 512, st));
@@ -287,13 +341,34 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
 
     // set-conv #2 (mse_layer2, cmflow.py:87-89)
     { const GemmArgs ga_ = mk(S(M2_WG), 256, w.G1, 256, w.PBM, 2048, S(M2_T1), 2048, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_SC2_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
-    { const GemmArgs ga_ = mk(S(M2_WP), E_LD, w.E, E_LD, w.P, 2048, nullptr, 2048, E_LD, bn, CMF_ACT_NONE, w.PBM, 2048, n); RUN(C_GEMM_SC2_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
+    if (m->tc) {
+        const TcArgs ta_ = tc_plain(m->t_m2_wp, 2048, E_LD, w.E, E_LD, w.P, 2048, nullptr, bn, CMF_ACT_NONE, w.PBM, 2048, n);
+        RUN(C_GEMM_SC2_HOIST, tflops(ta_, 771), cmf_launch_tc_gemm(ta_, st));
+    } else {
+        const GemmArgs ga_ = mk(S(M2_WP), E_LD, w.E, E_LD, w.P, 2048, nullptr, 2048, E_LD, bn, CMF_ACT_NONE, w.PBM, 2048, n);
+        RUN(C_GEMM_SC2_HOIST, 2.0 * 2048 * 771.0 * bn, cmf_launch_gemm1(ga_, st));
+    }
     for (int s = 0; s < 4; ++s) {
         const int sb = M2_BASE + s * 10;
+        if (m->tc) {
+            {   // layer 2 (512->256): neighbour gather of the hoisted layer-1 rows + rel-xyz term + ReLU fused into the B producer
+                TcArgs ta_ = tc_plain(m->t_m2_w2[s], 256, 512, nullptr, 0, w.Y2, 256, S(sb + 1), bn * KS[s], CMF_ACT_RELU);
+                ta_.prod = TC_PROD_SC2_Y1; ta_.U1 = nullptr; ta_.U2 = w.P; ta_.ld_u2 = 2048; ta_.off_u2 = s * 512;
+                ta_.Wsmall = S(M2_WX) + (size_t)s * 512 * 4; ta_.xyz_q = pc1; ta_.xyz_c = pc1; ta_.nbr = w.BQ1; ta_.nbr_ld = 60;
+                ta_.nbr_off = KOFF[s]; ta_.ksamp = KS[s]; ta_.n_pts = n;
+                RUN(C_GEMM_SC2_L2, tflops(ta_, 512), cmf_launch_tc_gemm(ta_, st));
+            }
+            {   // layer 3 (256->64) with ReLU + max over the K neighbours fused into the TMEM epilogue
+                TcArgs ta_ = tc_plain(m->t_m2_w3[s], 64, 256, w.Y2, 256, w.M64 + s * 64, 256, S(sb + 3), bn * KS[s], CMF_ACT_RELU);
+                ta_.epi = TC_EPI_MAXK; ta_.ksamp = KS[s];
+                RUN(C_GEMM_SC2_L3, tflops(ta_, 256), cmf_launch_tc_gemm(ta_, st));
+            }
+        } else {
         RUN(C_GATHER, 0, cmf_launch_mse2_build_y1(bc, n, KS[s], KOFF[s], pc1, w.BQ1, w.P, 2048, s * 512, S(M2_WX) + (size_t)s * 512 * 4, w.Y1, st));
         { const GemmArgs ga_ = mk(S(sb), 512, w.Y1, 512, w.Y2, 256, S(sb + 1), 256, 512, bn * KS[s], CMF_ACT_RELU); RUN(C_GEMM_SC2_L2, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
         { const GemmArgs ga_ = mk(S(sb + 2), 256, w.Y2, 256, w.Y3, 64, S(sb + 3), 64, 256, bn * KS[s], CMF_ACT_RELU); RUN(C_GEMM_SC2_L3, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
         RUN(C_REDUCE, 0, cmf_launch_maxk(bn, KS[s], 64, w.Y3, 64, w.M64 + s * 64, 256, st));
+        }
     }
     {
         GemmBatch gb; gb.count = 4;
@@ -319,7 +394,13 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
 
     // heads (FlowHead / MotionHead, radarflow_util.py:240-285), first layer stacked [fp ; mp]
     { const GemmArgs ga_ = mk(S(HD_W1G), 256, gvec, 256, w.PBH, 512, S(HD_T1), 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_POINTWISE, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
-    { const GemmArgs ga_ = mk(S(HD_W1), 256, w.PROP, 256, w.HD1, 512, nullptr, 512, 256, bn, CMF_ACT_RELU, w.PBH, 512, n); RUN(C_GEMM_POINTWISE, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
+    if (m->tc) {
+        const TcArgs ta_ = tc_plain(m->t_hd_w1, 512, 256, w.PROP, 256, w.HD1, 512, nullptr, bn, CMF_ACT_RELU, w.PBH, 512, n);
+        RUN(C_GEMM_POINTWISE, tflops(ta_, 256), cmf_launch_tc_gemm(ta_, st));
+    } else {
+        const GemmArgs ga_ = mk(S(HD_W1), 256, w.PROP, 256, w.HD1, 512, nullptr, 512, 256, bn, CMF_ACT_RELU, w.PBH, 512, n);
+        RUN(C_GEMM_POINTWISE, gflops(ga_), cmf_launch_gemm1(ga_, st));
+    }
     {
         GemmBatch gb; gb.count = 2;
         gb.g[0] = mk(S(HD_W2F), 256, w.HD1, 512, w.HD2, 256, S(HD_T2F), 128, 256, bn, CMF_ACT_RELU);
@@ -370,6 +451,8 @@ extern "C" int cmf_model_create(cmf_model **out, const float *blob, size_t blob_
     }
     m->shape = exp;
     *out = m;
+    const char *env = getenv("CMF_MODE");            // "fp32" (default) | "tf32x3"
+    if (env && !strcmp(env, "tf32x3")) { int rc = cmf_model_set_mode(m, 1); if (rc) { cmf_model_destroy(m); *out = nullptr; return rc; } }
     return CMF_OK;
 }
 
@@ -379,6 +462,7 @@ extern "C" void cmf_model_destroy(cmf_model *m) {
     if (m->d_blob) cudaFree(m->d_blob);
     if (m->d_in) cudaFree(m->d_in);
     if (m->d_out) cudaFree(m->d_out);
+    if (m->tc_buf) cudaFree(m->tc_buf);
     for (cudaEvent_t e : m->pool) cudaEventDestroy(e);
     delete m;
 }
@@ -456,6 +540,15 @@ extern "C" int cmf_model_forward_host(cmf_model *m, int b, int n, const float *p
     CMF_CUDA(cudaStreamSynchronize(st));
     return CMF_OK;
 }
+
+extern "C" int cmf_model_set_mode(cmf_model *m, int mode) {
+    CMF_REQUIRE(m, "null model");
+    CMF_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (strict fp32 FMA) or 1 (tcgen05 3xTF32)");
+    if (mode == 1) { int rc = ensure_tc_weights(m); if (rc) return rc; }
+    m->tc = mode;
+    return CMF_OK;
+}
+extern "C" int cmf_model_get_mode(const cmf_model *m) { return m ? m->tc : -1; }
 
 extern "C" int cmf_model_set_profiling(cmf_model *m, int enable) {
     CMF_REQUIRE(m, "null model");

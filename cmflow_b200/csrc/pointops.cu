@@ -382,8 +382,10 @@ extern "C" int cmf_three_interpolate_grad(int b, int c, int n, int m, const floa
 // furthest point sampling   (reference: lib/src/sampling_gpu.cu:93-209)
 // One CTA per cloud with the reference's thread count bs = 2^floor(log2 n) (cuda_utils.h:9-13) so the
 // per-thread scan order is the reference's.  The reference's smem tree keeps the LOWER slot on ties
-// (__update, sampling_gpu.cu:86-91), i.e. the winner is (max value, then min tid); that rule is
-// associative, so a shuffle butterfly + one cross-warp step gives the identical index.
+// (__update, sampling_gpu.cu:86-91) at every level (half = bs/2, bs/4, ..., 1): the last level pits even
+// against odd thread ids, the one before it (tid mod 4) 0 against 2, ... so among equal maxima the winner is
+// the thread with the smallest BIT-REVERSED id.  (max value, then min bitrev(tid)) is a total order, hence
+// associative: a shuffle butterfly + one cross-warp step yields the identical index.
 // ------------------------------------------------------------------------------------------------
 static int fps_threads(int work_size) {
     const int pow_2 = (int)(std::log(static_cast<double>(work_size)) / std::log(2.0));   // same expression as the reference
@@ -397,7 +399,8 @@ __global__ void __launch_bounds__(1024)
 fps_kernel(int n, int m, const float *__restrict__ dataset, float *__restrict__ temp, int *__restrict__ idxs) {
     if (m <= 0) return;
     __shared__ float sv[32];
-    __shared__ int st[32], si[32];
+    __shared__ unsigned st[32];
+    __shared__ int si[32];
     __shared__ int s_old;
     const int b = blockIdx.x, tid = threadIdx.x, bs = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = (bs + 31) >> 5;
@@ -416,12 +419,12 @@ fps_kernel(int n, int m, const float *__restrict__ dataset, float *__restrict__ 
             if (d2 > best) { best = d2; besti = k; }
         }
         // reduce (best desc, tid asc) carrying besti
-        float v = best; int t = tid, bi = besti;
+        float v = best; unsigned t = __brev((unsigned)tid); int bi = besti;
         const unsigned full = (bs >= 32) ? 0xffffffffu : ((1u << bs) - 1u);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             float ov = __shfl_xor_sync(full, v, off);
-            int ot = __shfl_xor_sync(full, t, off);
+            unsigned ot = __shfl_xor_sync(full, t, off);
             int oi = __shfl_xor_sync(full, bi, off);
             bool valid = (lane ^ off) < bs;                        // bs < 32: partner may not exist
             if (valid && (ov > v || (ov == v && ot < t))) { v = ov; t = ot; bi = oi; }
@@ -430,11 +433,11 @@ fps_kernel(int n, int m, const float *__restrict__ dataset, float *__restrict__ 
         __syncthreads();
         if (warp == 0) {
             float v2 = lane < nwarp ? sv[lane] : -2.f;
-            int t2 = lane < nwarp ? st[lane] : INT_MAX, i2 = lane < nwarp ? si[lane] : 0;
+            unsigned t2 = lane < nwarp ? st[lane] : 0xffffffffu; int i2 = lane < nwarp ? si[lane] : 0;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 float ov = __shfl_xor_sync(full, v2, off);
-                int ot = __shfl_xor_sync(full, t2, off);
+                unsigned ot = __shfl_xor_sync(full, t2, off);
                 int oi = __shfl_xor_sync(full, i2, off);
                 bool valid = (lane ^ off) < bs;                    // bs < 32: only bs lanes exist
                 if (valid && (ov > v2 || (ov == v2 && ot < t2))) { v2 = ov; t2 = ot; i2 = oi; }

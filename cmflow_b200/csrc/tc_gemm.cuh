@@ -1,0 +1,29 @@
+// tc_gemm.cuh -- launch interface of the tcgen05 (5th-gen tensor core) GEMM used by the fast pipeline.
+#pragma once
+#include "cmf_common.cuh"
+
+enum { TC_PROD_PLAIN = 0, TC_PROD_FC_H1 = 1, TC_PROD_SC2_Y1 = 2 };
+enum { TC_EPI_STORE = 0, TC_EPI_MAXK = 1, TC_EPI_WSUM = 2 };
+
+// Out[c][m] = epi( sum_k W[m][k] * B[c][k] )   computed as 3xTF32 (W_hi*B_hi + W_hi*B_lo + W_lo*B_hi), fp32 accumulate in TMEM.
+struct TcArgs {
+    // A operand: weights pre-tiled by cmf_tc_tile_weights(): [m_block][k_block]{hi tile, lo tile}, tile = 128 x 32 fp32, 128B-swizzled
+    const float *Wt;
+    int m_blocks, k_blocks;      // 128-row blocks, 32-col blocks
+    int M;                       // true number of output channels (rows beyond M are zero padding)
+    long long cols;              // number of B rows (columns of the output)
+    // B operand producer
+    int prod;
+    const float *X; int ldx;                                     // PLAIN: row c = X + c*ldx
+    const float *U1, *U2, *Wsmall;                               // FC_H1: leaky(U1[i]+U2[j]+Wd.dir); SC2_Y1: relu(P[j]+Wx.rel) with U2=P, Wsmall=Wx/Wd (C x 4)
+    const float *xyz_q, *xyz_c; const int *nbr;                  // planar (B,3,N) clouds of the query / candidate points, neighbour table
+    int n_pts, ksamp, nbr_ld, nbr_off, ld_u2, off_u2;            // points per cloud, neighbours per point, table row stride/offset, gathered-row stride/offset
+    // epilogue
+    int epi;
+    float *Out; int ldo;
+    const float *bias, *pbias; int pb_ld, cols_per_pair, act;
+};
+
+size_t cmf_tc_tiled_floats(int M, int K);                                        // floats needed for the pre-tiled copy of an M x K matrix
+int cmf_tc_tile_weights(const float *W, int ldw, int M, int K, float *Wt, cudaStream_t st);
+int cmf_launch_tc_gemm(const TcArgs &a, cudaStream_t st);

@@ -16,7 +16,7 @@ import torch
 
 HDR = 512
 MAGIC = 0x434D4642
-E_LD = 776
+E_LD = 800
 BN_EPS = 1e-5
 
 

@@ -158,6 +158,12 @@ int cmf_model_forward_host(cmf_model *m, int b, int n,
                            float *sf_agg, float *stat_cls, float *pre_trans, uint8_t *mask, float *gfeat_out,
                            void *stream);
 
+/* Arithmetic mode of the big 1x1-conv GEMMs: 0 = strict fp32 FMA (parity build, default), 1 = tcgen05 tensor cores with
+ * 3xTF32 split precision (fp32 accumulate in TMEM; ~2^-22 relative per product).  The default can also be chosen with the
+ * environment variable CMF_MODE=fp32|tf32x3 read at cmf_model_create(). */
+int cmf_model_set_mode(cmf_model *m, int mode);
+int cmf_model_get_mode(const cmf_model *m);
+
 /* Per-category device timers.  When enabled, every launch of the next forwards is bracketed by CUDA events on
  * the launching stream; cmf_model_read_profile() waits for the last forward and returns, per category
  * (cmf_model_profile_categories() of them, named by cmf_model_profile_name()), the summed device time in ms,
@@ -168,9 +174,15 @@ const char *cmf_model_profile_name(int cat);
 int cmf_model_read_profile(cmf_model *m, float *ms, int *launches, double *work);
 
 /* Debug taps (device pointers into the workspace of the last forward; NULL if not produced):
- * "E" (B,N,776) = [f1 256 | cor 512 | ft 3 | pad 5] | "f2" (B,N,256) | "g1","g2","gp" (B,256) | "prop" (B,N,256)
+ * "E" (B,N,800) = [f1 256 | cor 512 | ft 3 | zero pad 29] | "f2" (B,N,256) | "g1","g2","gp" (B,256) | "prop" (B,N,256)
  * | "flow" (B,3,N) | "bq1","bq2" (B,N,60) int32 | "knn12","knn11" (B,N,8) int32 | "P" (B,N,2048) | "cost1","u1","u2" (B,N,512). */
 const void *cmf_model_tap(const cmf_model *m, const char *name);
+
+/* Test doorway: Out[c][m] = act(sum_k W[m][k] X[c][k] + bias[m]) through the tcgen05 3xTF32 GEMM alone.
+ * scratch_tiles: cmf_test_tc_tiled_floats(M,K) floats of device scratch; ldx must cover K rounded up to 32 (zero padded). */
+int cmf_test_tc_gemm(int M, int K, long long cols, const float *W, int ldw, const float *X, int ldx,
+                     const float *bias, int act, float *Out, int ldo, float *scratch_tiles, void *stream);
+size_t cmf_test_tc_tiled_floats(int M, int K);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ from oracle import pointops as P
 
 KS = (4, 8, 16, 32)
 KOFF = (0, 4, 12, 28)
-E_LD = 776
+E_LD = 800
 
 
 def read_segments(blob):

@@ -56,7 +56,7 @@ def test_forward_matches_reference_golden(golden_dir, name):
     # integer work: neighbour sets identical to the reference's own torch.topk sets
     assert knn_sets_equal(net.tap("knn12", (B, N, 8), torch.int32).cpu(), gold["knn12"])
     assert knn_sets_equal(net.tap("knn11", (B, N, 8), torch.int32).cpu(), gold["knn11"])
-    E = net.tap("E", (B, N, 776)).cpu()
+    E = net.tap("E", (B, N, 800)).cpu()
     assert rel_err(E[0, ::4, 0:256].t(), gold["f1_sub"], per_pair=False) <= 1e-4
     assert rel_err(E[0, ::4, 256:768].t(), gold["cor_sub"], per_pair=False) <= 1e-4
     assert rel_err(net.tap("f2", (B, N, 256)).cpu()[0, ::4].t(), gold["f2_sub"], per_pair=False) <= 1e-4
@@ -92,7 +92,7 @@ def test_stage_taps_match_fp64_emulation(golden_dir):
     assert torch.equal(net.tap("bq2", (B, N, 60), torch.int32).cpu().long(), em["bq2"])
     assert torch.equal(net.tap("knn12", (B, N, 8), torch.int32).cpu().long(), em["knn12"])
     assert torch.equal(net.tap("knn11", (B, N, 8), torch.int32).cpu().long(), em["knn11"])
-    E = net.tap("E", (B, N, 776)).cpu()
+    E = net.tap("E", (B, N, 800)).cpu()
     for name, got, want in (("f1", E[..., 0:256], em["f1"]), ("f2", net.tap("f2", (B, N, 256)).cpu(), em["f2"]),
                             ("cor", E[..., 256:768], em["cor"]), ("prop", net.tap("prop", (B, N, 256)).cpu(), em["prop"]),
                             ("flow", net.tap("flow", (B, 3, N)).cpu(), em["flow"])):

@@ -130,7 +130,8 @@ def test_knn_point_bit_exact(B, N, S, k):
     iw, dw = P.knn_point(k, xyz, q)
     idx = torch.empty(B, S, k, dtype=torch.int32, device=DEV)
     dist = torch.empty(B, S, k, device=DEV)
-    check(lib().cmf_knn_point(B, N, S, k, dptr(xyz.to(DEV)), dptr(q.to(DEV)), dptr(idx), dptr(dist), stream_ptr()))
+    xd, qd = xyz.to(DEV), q.to(DEV)                    # keep the device tensors alive across the raw-pointer call
+    check(lib().cmf_knn_point(B, N, S, k, dptr(xd), dptr(qd), dptr(idx), dptr(dist), stream_ptr()))
     assert torch.equal(idx.cpu(), iw) and torch.equal(dist.cpu(), dw)
 
 
