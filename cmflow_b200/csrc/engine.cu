@@ -107,10 +107,10 @@ void carve(Arena &a, Work &w, int bc, int n) {
     w.M64 = a.take<float>(bn * 256); w.Q1 = a.take<float>(bn * 256); w.Q2 = a.take<float>(bn * 256);
     w.PB1 = a.take<float>((size_t)bc * 512); w.PB2 = a.take<float>((size_t)bc * 512);
     w.U1 = a.take<float>(bn * 512); w.U2 = a.take<float>(bn * 512);
-    w.H1 = a.take<float>(bn * 8 * 512); w.H2 = a.take<float>(bn * 8 * 512);
+    w.H1 = a.take<float>(bn * 8 * 512); w.H2 = a.take<float>(cmf_tc_act_tiled_floats((long long)bn * 8, 512));   // H2: row-major (fp32 mode) or tiled hi/lo (tc mode)
     w.COST1 = a.take<float>(bn * 512);
     w.PBM = a.take<float>((size_t)bc * 2048); w.P = a.take<float>(bn * 2048);
-    w.Y1 = a.take<float>(bn * 32 * 512); w.Y2 = a.take<float>(bn * 32 * 256); w.Y3 = a.take<float>(bn * 32 * 64);
+    w.Y1 = a.take<float>(bn * 32 * 512); w.Y2 = a.take<float>(cmf_tc_act_tiled_floats((long long)bn * 32, 256)); w.Y3 = a.take<float>(bn * 32 * 64);
     w.PROP = a.take<float>(bn * 256); w.GP = a.take<float>((size_t)bc * 256);
     w.GI = a.take<float>((size_t)bc * 768); w.GH = a.take<float>((size_t)bc * 768);
     w.GNEW = a.take<float>((size_t)bc * 256); w.ZERO = a.take<float>((size_t)bc * 256);
@@ -324,9 +324,14 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
             TcArgs ta_ = tc_plain(m->t_fc_w2, 512, 512, nullptr, 0, w.H2, 512, S(FC_B2), bn * 8, CMF_ACT_LEAKY);
             ta_.prod = TC_PROD_FC_H1; ta_.U1 = w.U1; ta_.U2 = w.U2; ta_.ld_u2 = 512; ta_.off_u2 = 0; ta_.Wsmall = S(FC_WD);
             ta_.xyz_q = pc1; ta_.xyz_c = pc2; ta_.nbr = w.KNN12; ta_.nbr_ld = 8; ta_.nbr_off = 0; ta_.ksamp = 8; ta_.n_pts = n;
+            ta_.out_tiled = 1;                 // conv2's B operand is written TF32-split + swizzled, ready for a bulk copy
             RUN(C_GEMM_FC_MLP, tflops(ta_, 512), cmf_launch_tc_gemm(ta_, st));
         }
-        { const TcArgs ta_ = tc_plain(m->t_fc_w3, 512, 512, w.H2, 512, w.H1, 512, S(FC_B3), bn * 8, CMF_ACT_LEAKY); RUN(C_GEMM_FC_MLP, tflops(ta_, 512), cmf_launch_tc_gemm(ta_, st)); }
+        {
+            TcArgs ta_ = tc_plain(m->t_fc_w3, 512, 512, nullptr, 0, w.H1, 512, S(FC_B3), bn * 8, CMF_ACT_LEAKY);
+            ta_.prod = TC_PROD_TILED; ta_.Xt = w.H2;
+            RUN(C_GEMM_FC_MLP, tflops(ta_, 512), cmf_launch_tc_gemm(ta_, st));
+        }
     } else {
     { const GemmArgs ga_ = mk(S(FC_WC), 256, w.E, E_LD, w.U1, 512, nullptr, 512, 256, bn, CMF_ACT_NONE, w.PB1, 512, n); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     { const GemmArgs ga_ = mk(S(FC_WN), 256, w.F2, 256, w.U2, 512, nullptr, 512, 256, bn, CMF_ACT_NONE, w.PB2, 512, n); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
@@ -356,10 +361,12 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
                 ta_.prod = TC_PROD_SC2_Y1; ta_.U1 = nullptr; ta_.U2 = w.P; ta_.ld_u2 = 2048; ta_.off_u2 = s * 512;
                 ta_.Wsmall = S(M2_WX) + (size_t)s * 512 * 4; ta_.xyz_q = pc1; ta_.xyz_c = pc1; ta_.nbr = w.BQ1; ta_.nbr_ld = 60;
                 ta_.nbr_off = KOFF[s]; ta_.ksamp = KS[s]; ta_.n_pts = n;
+                ta_.out_tiled = 1;
                 RUN(C_GEMM_SC2_L2, tflops(ta_, 512), cmf_launch_tc_gemm(ta_, st));
             }
-            {   // layer 3 (256->64) with ReLU + max over the K neighbours fused into the TMEM epilogue
-                TcArgs ta_ = tc_plain(m->t_m2_w3[s], 64, 256, w.Y2, 256, w.M64 + s * 64, 256, S(sb + 3), bn * KS[s], CMF_ACT_RELU);
+            {   // layer 3 (256->64) with ReLU + max over the K neighbours fused into the TMEM epilogue; B operand bulk-copied
+                TcArgs ta_ = tc_plain(m->t_m2_w3[s], 64, 256, nullptr, 0, w.M64 + s * 64, 256, S(sb + 3), bn * KS[s], CMF_ACT_RELU);
+                ta_.prod = TC_PROD_TILED; ta_.Xt = w.Y2;
                 ta_.epi = TC_EPI_MAXK; ta_.ksamp = KS[s];
                 RUN(C_GEMM_SC2_L3, tflops(ta_, 256), cmf_launch_tc_gemm(ta_, st));
             }

@@ -23,7 +23,8 @@ constexpr int TILE_B_FLOATS = BN * BK;              // 8192 floats = 32 KB
 constexpr int STAGE_BYTES = (2 * TILE_A_FLOATS + 2 * TILE_B_FLOATS) * 4;   // 96 KB
 constexpr int NSTAGE = 2;
 constexpr int NTHREADS = 512;
-constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SMALL_BYTES = 512 * 16;               // rel-xyz / direction weights (C x 4 floats) of the gather producers
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + SMALL_BYTES;
 constexpr unsigned SPIN_LIMIT = 1u << 24;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -142,13 +143,13 @@ __device__ __forceinline__ void load_row(const RowCtx &r, int kb, float4 (&v)[8]
     for (int q = 0; q < 8; ++q) v[q] = __ldg(reinterpret_cast<const float4 *>(src) + q);
 }
 
-__device__ __forceinline__ float small_term(const float *Wsmall, int ch, const RowCtx &r) {
-    const float4 w = __ldg(reinterpret_cast<const float4 *>(Wsmall + (size_t)ch * 4));
+__device__ __forceinline__ float small_term(const float4 *sW, int ch, const RowCtx &r) {
+    const float4 w = sW[ch];                                   // shared-memory broadcast (all 32 lanes read the same channel)
     return fmaf(w.z, r.dz, fmaf(w.y, r.dy, w.x * r.dx));
 }
 
 template <int PROD>
-__device__ __forceinline__ void store_row(const TcArgs &a, const RowCtx &r, int kb, int row, float4 (&v)[8],
+__device__ __forceinline__ void store_row(const TcArgs &a, const float4 *sW, const RowCtx &r, int kb, int row, float4 (&v)[8],
                                           float *Bhi, float *Blo) {
     const int k0 = kb * BK;
     float *dh = Bhi + row * BK, *dl = Blo + row * BK;
@@ -162,10 +163,10 @@ __device__ __forceinline__ void store_row(const TcArgs &a, const RowCtx &r, int 
                 const float4 uq = __ldg(reinterpret_cast<const float4 *>(r.src0 + k0) + q);
                 const float uu[4] = {uq.x, uq.y, uq.z, uq.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) x[e] = act_apply(uu[e] + x[e] + small_term(a.Wsmall, k0 + q * 4 + e, r), 2);
+                for (int e = 0; e < 4; ++e) x[e] = act_apply(uu[e] + x[e] + small_term(sW, k0 + q * 4 + e, r), 2);
             } else if (PROD == TC_PROD_SC2_Y1) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e] + small_term(a.Wsmall, k0 + q * 4 + e, r), 0.f);
+                for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e] + small_term(sW, k0 + q * 4 + e, r), 0.f);
             }
         }
         float4 h, l;
@@ -190,6 +191,9 @@ tc_gemm_kernel(const TcArgs a) {
     auto tfull_bar = [&](int s) { return bar0 + 32 + 8 * s; };
     auto tempty_bar = [&](int s) { return bar0 + 48 + 8 * s; };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + NSTAGE * STAGE_BYTES + 64);
+    float4 *sW = reinterpret_cast<float4 *>(smem + NSTAGE * STAGE_BYTES + 256);
+    if (PROD != TC_PROD_PLAIN)
+        for (int i = threadIdx.x; i < a.k_blocks * BK; i += NTHREADS) sW[i] = __ldg(reinterpret_cast<const float4 *>(a.Wsmall) + i);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long col_tiles = (a.cols + BN - 1) / BN;
@@ -197,7 +201,7 @@ tc_gemm_kernel(const TcArgs a) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(full_bar(s), 1 + 8);        // bulk-copy issuer (expect_tx) + one arrive per producer warp
+            mbar_init(full_bar(s), PROD == TC_PROD_TILED ? 1 : 1 + 8);   // bulk-copy issuer (expect_tx) [+ one arrive per producer warp]
             mbar_init(empty_bar(s), 1);           // tcgen05.commit
             mbar_init(tfull_bar(s), 1);           // tcgen05.commit
             mbar_init(tempty_bar(s), 4);          // one arrive per epilogue warp
@@ -222,8 +226,16 @@ tc_gemm_kernel(const TcArgs a) {
                 for (int kb = 0; kb < a.k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const float *src = a.Wt + ((size_t)mb * a.k_blocks + kb) * (2 * TILE_A_FLOATS);
-                    mbar_arrive_expect_tx(full_bar(stage), 2 * TILE_A_FLOATS * 4);
-                    bulk_g2s(base + stage * STAGE_BYTES, src, 2 * TILE_A_FLOATS * 4, full_bar(stage));
+                    if (PROD == TC_PROD_TILED) {
+                        // B rows were written split + swizzled by the previous GEMM's epilogue: one 64 KB bulk copy stages hi and lo
+                        const float *bsrc = a.Xt + ((size_t)(t / a.m_blocks) * a.k_blocks + kb) * (2 * TILE_B_FLOATS);
+                        mbar_arrive_expect_tx(full_bar(stage), (2 * TILE_A_FLOATS + 2 * TILE_B_FLOATS) * 4);
+                        bulk_g2s(base + stage * STAGE_BYTES, src, 2 * TILE_A_FLOATS * 4, full_bar(stage));
+                        bulk_g2s(base + stage * STAGE_BYTES + 2 * TILE_A_FLOATS * 4, bsrc, 2 * TILE_B_FLOATS * 4, full_bar(stage));
+                    } else {
+                        mbar_arrive_expect_tx(full_bar(stage), 2 * TILE_A_FLOATS * 4);
+                        bulk_g2s(base + stage * STAGE_BYTES, src, 2 * TILE_A_FLOATS * 4, full_bar(stage));
+                    }
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
             }
@@ -268,21 +280,46 @@ tc_gemm_kernel(const TcArgs a) {
             const int m = mb * BM + q * 32 + lane;
             const bool m_ok = m < a.M;
             const float bias = (a.bias && m_ok) ? __ldg(a.bias + m) : 0.f;
+            // per-pair bias: track the pair of the current column incrementally (no division per element)
+            long long pair = 0, pair_end = 0x7fffffffffffffffLL;
+            float pb = 0.f;
+            if (a.pbias) {
+                pair = c0 / a.cols_per_pair; pair_end = (pair + 1) * (long long)a.cols_per_pair;
+                if (m_ok) pb = __ldg(a.pbias + (size_t)pair * a.pb_ld + m);
+            }
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
 #pragma unroll 1
             for (int cc = 0; cc < BN; cc += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cc, r);
-                if (a.epi == TC_EPI_STORE) {
+                if (a.epi == TC_EPI_STORE && a.out_tiled) {
+                    // next GEMM's B operand, already TF32-split and 128B-swizzled: tile (col_tile, k_block = m/32), row = column in tile
+                    float *tb = a.Out + ((size_t)(t / a.m_blocks) * (a.M >> 5) + (m >> 5)) * (2 * TILE_B_FLOATS);
 #pragma unroll
                     for (int e = 0; e < 32; ++e) {
                         const long long c = c0 + cc + e;
-                        if (c < a.cols && m_ok) {
-                            float v = __uint_as_float(r[e]) + bias;
-                            if (a.pbias) v += __ldg(a.pbias + (size_t)(c / a.cols_per_pair) * a.pb_ld + m);
-                            a.Out[(size_t)c * a.ldo + m] = act_apply(v, a.act);
+                        const int rr = cc + e;
+                        if (c >= pair_end) {
+                            ++pair; pair_end += a.cols_per_pair;
+                            if (c < a.cols) pb = __ldg(a.pbias + (size_t)pair * a.pb_ld + m);
                         }
+                        const float v = c < a.cols ? act_apply(__uint_as_float(r[e]) + bias + pb, a.act) : 0.f;
+                        float hi, lo;
+                        split_tf32(v, hi, lo);
+                        const int off = rr * BK + (((lane >> 2) ^ (rr & 7)) << 2) + (lane & 3);
+                        tb[off] = hi;
+                        tb[TILE_B_FLOATS + off] = lo;
+                    }
+                } else if (a.epi == TC_EPI_STORE) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const long long c = c0 + cc + e;
+                        if (c >= pair_end) {                                  // warp-uniform: crossed into the next frame pair
+                            ++pair; pair_end += a.cols_per_pair;
+                            if (m_ok && c < a.cols) pb = __ldg(a.pbias + (size_t)pair * a.pb_ld + m);
+                        }
+                        if (c < a.cols && m_ok) a.Out[(size_t)c * a.ldo + m] = act_apply(__uint_as_float(r[e]) + bias + pb, a.act);
                     }
                 } else if (a.epi == TC_EPI_MAXK) {
                     // relu(acc + bias) then max over each group of `ksamp` consecutive rows (one point's neighbours); ksamp | 32
@@ -297,26 +334,34 @@ tc_gemm_kernel(const TcArgs a) {
             if (lane == 0) mbar_arrive(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 8 && PROD != TC_PROD_TILED) {
         // ===== B operand producers: thread `row` builds activation row c0+row for every k-block =====
         const int row = threadIdx.x - 256;
         int stage = 0; uint32_t phase = 0;
-        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-            const long long c0 = (t / a.m_blocks) * BN;
-            const RowCtx rc = make_row(a, c0 + row);
+        long long t = blockIdx.x;
+        if (t < ntiles) {
+            RowCtx rc = make_row(a, (t / a.m_blocks) * BN + row);
             float4 v[8], vn[8];
             load_row<PROD>(rc, 0, v);
-            for (int kb = 0; kb < a.k_blocks; ++kb) {
-                if (kb + 1 < a.k_blocks) load_row<PROD>(rc, kb + 1, vn);      // in flight while we wait for the stage
-                mbar_wait(empty_bar(stage), phase ^ 1);
-                float *Bhi = reinterpret_cast<float *>(smem + stage * STAGE_BYTES + 2 * TILE_A_FLOATS * 4);
-                store_row<PROD>(a, rc, kb, row, v, Bhi, Bhi + TILE_B_FLOATS);
-                fence_async_smem();                                           // generic-proxy writes -> visible to the tensor core (async proxy)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full_bar(stage));
+            while (true) {
+                RowCtx rcn = rc;
+                const long long tn = t + gridDim.x;
+                for (int kb = 0; kb < a.k_blocks; ++kb) {
+                    // prefetch the next k-block's row slice (or the NEXT TILE's row context + first slice) while we wait for the stage
+                    if (kb + 1 < a.k_blocks) load_row<PROD>(rc, kb + 1, vn);
+                    else if (tn < ntiles) { rcn = make_row(a, (tn / a.m_blocks) * BN + row); load_row<PROD>(rcn, 0, vn); }
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    float *Bhi = reinterpret_cast<float *>(smem + stage * STAGE_BYTES + 2 * TILE_A_FLOATS * 4);
+                    store_row<PROD>(a, sW, rc, kb, row, v, Bhi, Bhi + TILE_B_FLOATS);
+                    fence_async_smem();                                       // generic-proxy writes -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full_bar(stage));
 #pragma unroll
-                for (int qq = 0; qq < 8; ++qq) v[qq] = vn[qq];
-                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    for (int qq = 0; qq < 8; ++qq) v[qq] = vn[qq];
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                if (tn >= ntiles) break;
+                t = tn; rc = rcn;
             }
         }
     }
@@ -349,6 +394,10 @@ __global__ void tile_weights_kernel(const float *__restrict__ W, int ldw, int M,
 
 }  // namespace
 
+size_t cmf_tc_act_tiled_floats(long long cols, int C) {
+    return (size_t)((cols + BN - 1) / BN) * (size_t)cmf_divup(C, BK) * 2 * TILE_B_FLOATS;
+}
+
 size_t cmf_tc_tiled_floats(int M, int K) {
     return (size_t)cmf_divup(M, BM) * cmf_divup(K, BK) * 2 * TILE_A_FLOATS;
 }
@@ -368,17 +417,20 @@ int cmf_launch_tc_gemm(const TcArgs &a, cudaStream_t st) {
         CMF_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TC_PROD_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         CMF_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TC_PROD_FC_H1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         CMF_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TC_PROD_SC2_Y1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CMF_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TC_PROD_TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         int dev = 0;
         CMF_CUDA(cudaGetDevice(&dev));
         CMF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         attr_set = true;
     }
     if (a.cols <= 0 || a.m_blocks <= 0) return CMF_OK;
+    if (a.out_tiled && ((a.M & 127) || a.epi != TC_EPI_STORE)) { cmf_set_error("tc_gemm: tiled output needs M % 128 == 0 and the STORE epilogue"); return CMF_ERR_INVALID; }
     if (a.epi == TC_EPI_MAXK && a.ksamp != 4 && a.ksamp != 8 && a.ksamp != 16 && a.ksamp != 32) { cmf_set_error("tc_gemm: MAXK needs ksamp | 32"); return CMF_ERR_INVALID; }
     const long long ntiles = ((a.cols + BN - 1) / BN) * a.m_blocks;
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
     if (a.prod == TC_PROD_PLAIN) tc_gemm_kernel<TC_PROD_PLAIN><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
     else if (a.prod == TC_PROD_FC_H1) tc_gemm_kernel<TC_PROD_FC_H1><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
+    else if (a.prod == TC_PROD_TILED) tc_gemm_kernel<TC_PROD_TILED><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
     else tc_gemm_kernel<TC_PROD_SC2_Y1><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
     CMF_LAUNCH_CHECK();
     return CMF_OK;

@@ -2,7 +2,7 @@
 #pragma once
 #include "cmf_common.cuh"
 
-enum { TC_PROD_PLAIN = 0, TC_PROD_FC_H1 = 1, TC_PROD_SC2_Y1 = 2 };
+enum { TC_PROD_PLAIN = 0, TC_PROD_FC_H1 = 1, TC_PROD_SC2_Y1 = 2, TC_PROD_TILED = 3 };
 enum { TC_EPI_STORE = 0, TC_EPI_MAXK = 1, TC_EPI_WSUM = 2 };
 
 // Out[c][m] = epi( sum_k W[m][k] * B[c][k] )   computed as 3xTF32 (W_hi*B_hi + W_hi*B_lo + W_lo*B_hi), fp32 accumulate in TMEM.
@@ -18,12 +18,15 @@ struct TcArgs {
     const float *U1, *U2, *Wsmall;                               // FC_H1: leaky(U1[i]+U2[j]+Wd.dir); SC2_Y1: relu(P[j]+Wx.rel) with U2=P, Wsmall=Wx/Wd (C x 4)
     const float *xyz_q, *xyz_c; const int *nbr;                  // planar (B,3,N) clouds of the query / candidate points, neighbour table
     int n_pts, ksamp, nbr_ld, nbr_off, ld_u2, off_u2;            // points per cloud, neighbours per point, table row stride/offset, gathered-row stride/offset
+    const float *Xt;                                             // TILED: activations already split + swizzled by a previous tc GEMM (out_tiled)
     // epilogue
     int epi;
+    int out_tiled;                                               // STORE only: write [col_tile][k_block]{hi,lo} 256x32 swizzled tiles instead of rows
     float *Out; int ldo;
     const float *bias, *pbias; int pb_ld, cols_per_pair, act;
 };
 
-size_t cmf_tc_tiled_floats(int M, int K);                                        // floats needed for the pre-tiled copy of an M x K matrix
+size_t cmf_tc_tiled_floats(int M, int K);
+size_t cmf_tc_act_tiled_floats(long long cols, int C);                          // floats of a tiled activation buffer (cols x C channels)                                        // floats needed for the pre-tiled copy of an M x K matrix
 int cmf_tc_tile_weights(const float *W, int ldw, int M, int K, float *Wt, cudaStream_t st);
 int cmf_launch_tc_gemm(const TcArgs &a, cudaStream_t st);
