@@ -192,7 +192,7 @@ tc_gemm_kernel(const TcArgs a) {
     auto tempty_bar = [&](int s) { return bar0 + 48 + 8 * s; };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + NSTAGE * STAGE_BYTES + 64);
     float4 *sW = reinterpret_cast<float4 *>(smem + NSTAGE * STAGE_BYTES + 256);
-    if (PROD != TC_PROD_PLAIN)
+    if (PROD == TC_PROD_FC_H1 || PROD == TC_PROD_SC2_Y1)
         for (int i = threadIdx.x; i < a.k_blocks * BK; i += NTHREADS) sW[i] = __ldg(reinterpret_cast<const float4 *>(a.Wsmall) + i);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
