@@ -5,23 +5,28 @@
 // * 3xTF32 split precision: every fp32 operand x is split as hi = rna_tf32(x), lo = x - hi and the product is
 //   accumulated as W_hi*B_hi + W_hi*B_lo + W_lo*B_hi in fp32 (TMEM) -- ~2^-22 relative per product, which keeps the
 //   forward inside the 1e-4 parity bar where single-pass TF32 (2^-11) would not.
-// * CTA tile = 128 output channels (one UMMA M) x 256 activation rows (UMMA N), K consumed in blocks of 32 floats
-//   (= one 128-byte swizzle atom).  A (weights) is pre-tiled in global memory in exactly the shared-memory image
-//   (128B swizzle, hi tile then lo tile), so one cp.async.bulk (TMA engine, UBLKCP) per tile stages it.
-//   B is PRODUCED by 8 warps, one thread per activation row: coalesced 128-byte row-slice loads (or the fused
-//   neighbour gather + first-layer epilogue of the set-conv / flow-embedding), hi/lo split, 128B-swizzled st.shared.
+// * CTA tile = 128 output channels (one UMMA M) x 256 activation rows (UMMA N), K consumed in stages of 16 floats
+//   (64-byte rows, 64B swizzle).  A (weights) is pre-tiled in global memory in exactly the shared-memory image
+//   (hi tile then lo tile), so one cp.async.bulk (TMA engine, UBLKCP) per stage brings it in.
+//   B is either PRODUCED by 8 warps, one thread per activation row (coalesced 128-byte row-slice loads, or the fused
+//   neighbour gather + first-layer epilogue of the set-conv / flow-embedding; hi/lo split; swizzled st.shared), or --
+//   when the previous tc GEMM's epilogue already wrote it split + swizzled ("tiled") -- bulk-copied like A.
 // * Warp roles (512 threads): w0 bulk-copy issuer, w1 MMA issuer (one elected lane), w2 TMEM allocator,
-//   w4-7 epilogue (TMEM lane quarter = warp%4), w8-15 B producers.  2-stage smem ring (2 x 96 KB), 2 TMEM accumulator
+//   w4-7 epilogue (TMEM lane quarter = warp%4), w8-15 B producers.  4-stage smem ring (4 x 48 KB), 2 TMEM accumulator
 //   stages (2 x 256 columns) so the epilogue of tile t overlaps the MMAs of tile t+1.  Persistent over tiles.
 #include "tc_gemm.cuh"
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 32;
-constexpr int TILE_A_FLOATS = BM * BK;              // 4096 floats = 16 KB
-constexpr int TILE_B_FLOATS = BN * BK;              // 8192 floats = 32 KB
-constexpr int STAGE_BYTES = (2 * TILE_A_FLOATS + 2 * TILE_B_FLOATS) * 4;   // 96 KB
-constexpr int NSTAGE = 2;
+// Geometry.  One pipeline STAGE holds K = 16 floats (64-byte rows, 64B swizzle): A 128x16 hi+lo (16 KB) + B 256x16 hi+lo (32 KB)
+// = 48 KB, four stages in flight (192 KB).  Finer stages than the swizzle-128 variant buy latency tolerance: the ring
+// holds the same bytes but a slot is recycled every 6 MMAs (768 clk) instead of every 12.
+// TcArgs.k_blocks counts 32-float blocks (what a producer thread handles per iteration = two stages).
+constexpr int BM = 128, BN = 256, SK = 16, PK = 32;
+constexpr int TILE_A_FLOATS = BM * SK;              // 2048 floats =  8 KB
+constexpr int TILE_B_FLOATS = BN * SK;              // 4096 floats = 16 KB
+constexpr int STAGE_BYTES = (2 * TILE_A_FLOATS + 2 * TILE_B_FLOATS) * 4;   // 48 KB
+constexpr int NSTAGE = 4;
 constexpr int NTHREADS = 512;
 constexpr int SMALL_BYTES = 512 * 16;               // rel-xyz / direction weights (C x 4 floats) of the gather producers
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + SMALL_BYTES;
@@ -82,10 +87,14 @@ __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
     lo = x - hi;
 }
 
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (tile base 1024-aligned).
-//   bits [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (=64) | [46,48) version=1 | [61,64) layout=2 (SWIZZLE_128B)
+// Float offset of element (row, kk) inside a K-major [rows x 16] tile with the 64-byte swizzle:
+// rows are 64 bytes, the 16-byte chunk index (2 bits) is XORed with address bits [7,9) = (row >> 1) & 3.
+__host__ __device__ __forceinline__ int sw_off(int row, int kk) { return row * SK + ((((kk >> 2) ^ ((row >> 1) & 3))) << 2) + (kk & 3); }
+
+// K-major, 64B-swizzled operand tile (tile base 1024-aligned): 8-row groups are 512 bytes apart.
+//   bits [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (=32) | [46,48) version=1 | [61,64) layout=4 (SWIZZLE_64B)
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
 }
 // kind::tf32, fp32 accumulate, A and B K-major, M=128, N=256:
 //   c_format[4,6)=1 (F32) | a_format[7,10)=2 (TF32) | b_format[10,13)=2 | n_dim[17,23)=N>>3 | m_dim[24,29)=M>>4
@@ -111,7 +120,7 @@ __device__ __forceinline__ void maxk_groups(const uint32_t (&r)[32], float bias,
 
 struct RowCtx {          // per-producer-thread description of its activation row for the current tile
     bool valid;
-    const float *src0, *src1;      // PLAIN: src0 ; FC_H1: src0 = U1 row, src1 = U2 row ; SC2_Y1: src1 = P row
+    const float *src0, *src1;      // PLAIN: src0 ; FC_H1: src0 = U1 row (centre point), src1 = U2 row (neighbour) ; SC2_Y1: src1 = P row
     float dx, dy, dz;
 };
 
@@ -134,13 +143,16 @@ __device__ __forceinline__ RowCtx make_row(const TcArgs &a, long long c) {
     return r;
 }
 
-// the 32 floats (one k-block) of this thread's row, BEFORE the tf32 split
+// One 32-float block of this thread's (gathered) row, BEFORE the tf32 split: 128 contiguous bytes.  For FC_H1 the
+// centre-point row is shared by the 8 consecutive rows of a point: each of those 8 lanes fetches one 16-byte chunk of it
+// (`u`) and the chunks are exchanged by shuffle at store time.
 template <int PROD>
-__device__ __forceinline__ void load_row(const RowCtx &r, int kb, float4 (&v)[8]) {
+__device__ __forceinline__ void load_row(const RowCtx &r, int kb, int sub, float4 (&v)[8], float4 &u) {
     if (!r.valid) return;
-    const float *src = (PROD == TC_PROD_PLAIN ? r.src0 : r.src1) + kb * BK;     // the (gathered) row slice: 128 contiguous bytes
+    const float *src = (PROD == TC_PROD_PLAIN ? r.src0 : r.src1) + kb * PK;
 #pragma unroll
     for (int q = 0; q < 8; ++q) v[q] = __ldg(reinterpret_cast<const float4 *>(src) + q);
+    if (PROD == TC_PROD_FC_H1) u = __ldg(reinterpret_cast<const float4 *>(r.src0 + kb * PK) + sub);
 }
 
 __device__ __forceinline__ float small_term(const float4 *sW, int ch, const RowCtx &r) {
@@ -148,32 +160,31 @@ __device__ __forceinline__ float small_term(const float4 *sW, int ch, const RowC
     return fmaf(w.z, r.dz, fmaf(w.y, r.dy, w.x * r.dx));
 }
 
+// transform + split + swizzled store of half a 32-block (chunks q0..q0+3) into one stage's B tiles
 template <int PROD>
-__device__ __forceinline__ void store_row(const TcArgs &a, const float4 *sW, const RowCtx &r, int kb, int row, float4 (&v)[8],
-                                          float *Bhi, float *Blo) {
-    const int k0 = kb * BK;
-    float *dh = Bhi + row * BK, *dl = Blo + row * BK;
+__device__ __forceinline__ void store_half(const float4 *sW, const RowCtx &r, int kb, int row, int lane, int half,
+                                           const float4 (&v)[8], const float4 &u, float *Bhi, float *Blo) {
+    const int k0 = kb * PK + half * SK;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        float x[4] = {0.f, 0.f, 0.f, 0.f};
-        if (r.valid) {
-            x[0] = v[q].x; x[1] = v[q].y; x[2] = v[q].z; x[3] = v[q].w;
-            if (PROD == TC_PROD_FC_H1) {
-                // centre-point row: shared by the 8 consecutive rows of one point -> L1-resident after the first touch
-                const float4 uq = __ldg(reinterpret_cast<const float4 *>(r.src0 + k0) + q);
-                const float uu[4] = {uq.x, uq.y, uq.z, uq.w};
+    for (int qq = 0; qq < 4; ++qq) {
+        const int q = half * 4 + qq;
+        float x[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+        if (PROD == TC_PROD_FC_H1) {
+            const int srcl = (lane & ~7) + q;                     // the lane of this point's group that holds chunk q of the centre row
+            const float uu[4] = {__shfl_sync(0xffffffffu, u.x, srcl), __shfl_sync(0xffffffffu, u.y, srcl),
+                                 __shfl_sync(0xffffffffu, u.z, srcl), __shfl_sync(0xffffffffu, u.w, srcl)};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) x[e] = act_apply(uu[e] + x[e] + small_term(sW, k0 + q * 4 + e, r), 2);
-            } else if (PROD == TC_PROD_SC2_Y1) {
+            for (int e = 0; e < 4; ++e) x[e] = act_apply(uu[e] + x[e] + small_term(sW, k0 + qq * 4 + e, r), 2);
+        } else if (PROD == TC_PROD_SC2_Y1) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e] + small_term(sW, k0 + q * 4 + e, r), 0.f);
-            }
+            for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e] + small_term(sW, k0 + qq * 4 + e, r), 0.f);
         }
+        if (!r.valid) { x[0] = x[1] = x[2] = x[3] = 0.f; }
         float4 h, l;
         split_tf32(x[0], h.x, l.x); split_tf32(x[1], h.y, l.y); split_tf32(x[2], h.z, l.z); split_tf32(x[3], h.w, l.w);
-        const int chunk = (q ^ (row & 7)) * 4;               // 128B swizzle: 16-byte chunk index XOR (row mod 8)
-        *reinterpret_cast<float4 *>(dh + chunk) = h;
-        *reinterpret_cast<float4 *>(dl + chunk) = l;
+        const int off = sw_off(row, qq * 4);
+        *reinterpret_cast<float4 *>(Bhi + off) = h;
+        *reinterpret_cast<float4 *>(Blo + off) = l;
     }
 }
 
@@ -182,27 +193,29 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t base = (raw + 1023u) & ~1023u;                    // 1024-byte alignment for the 128B swizzle
+    const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (base - raw);
-    // barriers live after the stages
     const uint32_t bar0 = base + NSTAGE * STAGE_BYTES;
     auto full_bar = [&](int s) { return bar0 + 8 * s; };
-    auto empty_bar = [&](int s) { return bar0 + 16 + 8 * s; };
-    auto tfull_bar = [&](int s) { return bar0 + 32 + 8 * s; };
-    auto tempty_bar = [&](int s) { return bar0 + 48 + 8 * s; };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + NSTAGE * STAGE_BYTES + 64);
+    auto empty_bar = [&](int s) { return bar0 + 32 + 8 * s; };
+    auto tfull_bar = [&](int s) { return bar0 + 64 + 8 * s; };
+    auto tempty_bar = [&](int s) { return bar0 + 80 + 8 * s; };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + NSTAGE * STAGE_BYTES + 128);
     float4 *sW = reinterpret_cast<float4 *>(smem + NSTAGE * STAGE_BYTES + 256);
     if (PROD == TC_PROD_FC_H1 || PROD == TC_PROD_SC2_Y1)
-        for (int i = threadIdx.x; i < a.k_blocks * BK; i += NTHREADS) sW[i] = __ldg(reinterpret_cast<const float4 *>(a.Wsmall) + i);
+        for (int i = threadIdx.x; i < a.k_blocks * PK; i += NTHREADS) sW[i] = __ldg(reinterpret_cast<const float4 *>(a.Wsmall) + i);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long col_tiles = (a.cols + BN - 1) / BN;
     const long long ntiles = col_tiles * a.m_blocks;
+    const int nks = a.k_blocks * 2;                               // 16-float stages per tile
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(full_bar(s), PROD == TC_PROD_TILED ? 1 : 1 + 8);   // bulk-copy issuer (expect_tx) [+ one arrive per producer warp]
             mbar_init(empty_bar(s), 1);           // tcgen05.commit
+        }
+        for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);           // tcgen05.commit
             mbar_init(tempty_bar(s), 4);          // one arrive per epilogue warp
         }
@@ -218,23 +231,24 @@ tc_gemm_kernel(const TcArgs a) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== A operand: one bulk copy per (tile, k-block): hi tile + lo tile are adjacent in the pre-tiled weights =====
+        // ===== bulk-copy issuer: A (pre-tiled weights) every stage; B too when the activations arrive pre-tiled =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
                 const int mb = (int)(t % a.m_blocks);
-                for (int kb = 0; kb < a.k_blocks; ++kb) {
+                const long long ct = t / a.m_blocks;
+                for (int ks = 0; ks < nks; ++ks) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
-                    const float *src = a.Wt + ((size_t)mb * a.k_blocks + kb) * (2 * TILE_A_FLOATS);
+                    const float *src = a.Wt + ((size_t)mb * nks + ks) * (2 * TILE_A_FLOATS);
+                    const uint32_t dst = base + stage * STAGE_BYTES;
                     if (PROD == TC_PROD_TILED) {
-                        // B rows were written split + swizzled by the previous GEMM's epilogue: one 64 KB bulk copy stages hi and lo
-                        const float *bsrc = a.Xt + ((size_t)(t / a.m_blocks) * a.k_blocks + kb) * (2 * TILE_B_FLOATS);
+                        const float *bsrc = a.Xt + ((size_t)ct * nks + ks) * (2 * TILE_B_FLOATS);
                         mbar_arrive_expect_tx(full_bar(stage), (2 * TILE_A_FLOATS + 2 * TILE_B_FLOATS) * 4);
-                        bulk_g2s(base + stage * STAGE_BYTES, src, 2 * TILE_A_FLOATS * 4, full_bar(stage));
-                        bulk_g2s(base + stage * STAGE_BYTES + 2 * TILE_A_FLOATS * 4, bsrc, 2 * TILE_B_FLOATS * 4, full_bar(stage));
+                        bulk_g2s(dst, src, 2 * TILE_A_FLOATS * 4, full_bar(stage));
+                        bulk_g2s(dst + 2 * TILE_A_FLOATS * 4, bsrc, 2 * TILE_B_FLOATS * 4, full_bar(stage));
                     } else {
                         mbar_arrive_expect_tx(full_bar(stage), 2 * TILE_A_FLOATS * 4);
-                        bulk_g2s(base + stage * STAGE_BYTES, src, 2 * TILE_A_FLOATS * 4, full_bar(stage));
+                        bulk_g2s(dst, src, 2 * TILE_A_FLOATS * 4, full_bar(stage));
                     }
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
@@ -248,7 +262,7 @@ tc_gemm_kernel(const TcArgs a) {
             mbar_wait(tempty_bar(acc), acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
-            for (int kb = 0; kb < a.k_blocks; ++kb) {
+            for (int ks = 0; ks < nks; ++ks) {
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
                 if (lane == 0) {
@@ -256,14 +270,14 @@ tc_gemm_kernel(const TcArgs a) {
                     const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + TILE_A_FLOATS * 4);
                     const uint64_t b_hi = make_desc(sa + 2 * TILE_A_FLOATS * 4), b_lo = make_desc(sa + 2 * TILE_A_FLOATS * 4 + TILE_B_FLOATS * 4);
 #pragma unroll
-                    for (int k8 = 0; k8 < BK / 8; ++k8) {
+                    for (int k8 = 0; k8 < SK / 8; ++k8) {
                         const uint64_t adv = (uint64_t)(k8 * 32 >> 4);      // 32 bytes per K=8 step inside the swizzle atom
-                        tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, IDESC, (kb | k8) ? 1u : 0u);
+                        tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, IDESC, (ks | k8) ? 1u : 0u);
                         tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
                         tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1u);
                     }
                     tc_commit(empty_bar(stage));                              // frees the smem stage when these MMAs retire
-                    if (kb == a.k_blocks - 1) tc_commit(tfull_bar(acc));      // accumulator complete
+                    if (ks == nks - 1) tc_commit(tfull_bar(acc));             // accumulator complete
                 }
                 __syncwarp();
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -276,7 +290,8 @@ tc_gemm_kernel(const TcArgs a) {
         int acc = 0; uint32_t acc_phase = 0;
         for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
             const int mb = (int)(t % a.m_blocks);
-            const long long c0 = (t / a.m_blocks) * BN;
+            const long long ct = t / a.m_blocks;
+            const long long c0 = ct * BN;
             const int m = mb * BM + q * 32 + lane;
             const bool m_ok = m < a.M;
             const float bias = (a.bias && m_ok) ? __ldg(a.bias + m) : 0.f;
@@ -294,12 +309,11 @@ tc_gemm_kernel(const TcArgs a) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cc, r);
                 if (a.epi == TC_EPI_STORE && a.out_tiled) {
-                    // next GEMM's B operand, already TF32-split and 128B-swizzled: tile (col_tile, k_block = m/32), row = column in tile
-                    float *tb = a.Out + ((size_t)(t / a.m_blocks) * (a.M >> 5) + (m >> 5)) * (2 * TILE_B_FLOATS);
+                    // next GEMM's B operand, already TF32-split and swizzled: tile (col_tile, 16-block = m/16), row = column in tile
+                    float *tb = a.Out + ((size_t)ct * (a.M >> 4) + (m >> 4)) * (2 * TILE_B_FLOATS);
 #pragma unroll
                     for (int e = 0; e < 32; ++e) {
                         const long long c = c0 + cc + e;
-                        const int rr = cc + e;
                         if (c >= pair_end) {
                             ++pair; pair_end += a.cols_per_pair;
                             if (c < a.cols) pb = __ldg(a.pbias + (size_t)pair * a.pb_ld + m);
@@ -307,7 +321,7 @@ tc_gemm_kernel(const TcArgs a) {
                         const float v = c < a.cols ? act_apply(__uint_as_float(r[e]) + bias + pb, a.act) : 0.f;
                         float hi, lo;
                         split_tf32(v, hi, lo);
-                        const int off = rr * BK + (((lane >> 2) ^ (rr & 7)) << 2) + (lane & 3);
+                        const int off = sw_off(cc + e, m & 15);
                         tb[off] = hi;
                         tb[TILE_B_FLOATS + off] = lo;
                     }
@@ -335,30 +349,35 @@ tc_gemm_kernel(const TcArgs a) {
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 8 && PROD != TC_PROD_TILED) {
-        // ===== B operand producers: thread `row` builds activation row c0+row for every k-block =====
+        // ===== B operand producers: thread `row` builds activation row c0+row; one iteration = 32 floats = two stages =====
         const int row = threadIdx.x - 256;
         int stage = 0; uint32_t phase = 0;
         long long t = blockIdx.x;
         if (t < ntiles) {
             RowCtx rc = make_row(a, (t / a.m_blocks) * BN + row);
             float4 v[8], vn[8];
-            load_row<PROD>(rc, 0, v);
+            float4 u = make_float4(0.f, 0.f, 0.f, 0.f), un = u;
+            load_row<PROD>(rc, 0, lane & 7, v, u);
             while (true) {
                 RowCtx rcn = rc;
                 const long long tn = t + gridDim.x;
                 for (int kb = 0; kb < a.k_blocks; ++kb) {
-                    // prefetch the next k-block's row slice (or the NEXT TILE's row context + first slice) while we wait for the stage
-                    if (kb + 1 < a.k_blocks) load_row<PROD>(rc, kb + 1, vn);
-                    else if (tn < ntiles) { rcn = make_row(a, (tn / a.m_blocks) * BN + row); load_row<PROD>(rcn, 0, vn); }
-                    mbar_wait(empty_bar(stage), phase ^ 1);
-                    float *Bhi = reinterpret_cast<float *>(smem + stage * STAGE_BYTES + 2 * TILE_A_FLOATS * 4);
-                    store_row<PROD>(a, sW, rc, kb, row, v, Bhi, Bhi + TILE_B_FLOATS);
-                    fence_async_smem();                                       // generic-proxy writes -> visible to the tensor core (async proxy)
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(full_bar(stage));
+                    // prefetch the next 32-block's row slice (or the NEXT TILE's row context + first slice) while we wait for the stages
+                    if (kb + 1 < a.k_blocks) load_row<PROD>(rc, kb + 1, lane & 7, vn, un);
+                    else if (tn < ntiles) { rcn = make_row(a, (tn / a.m_blocks) * BN + row); load_row<PROD>(rcn, 0, lane & 7, vn, un); }
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        mbar_wait(empty_bar(stage), phase ^ 1);
+                        float *Bhi = reinterpret_cast<float *>(smem + stage * STAGE_BYTES + 2 * TILE_A_FLOATS * 4);
+                        store_half<PROD>(sW, rc, kb, row, lane, half, v, u, Bhi, Bhi + TILE_B_FLOATS);
+                        fence_async_smem();                                   // generic-proxy writes -> visible to the tensor core (async proxy)
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(full_bar(stage));
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    }
 #pragma unroll
                     for (int qq = 0; qq < 8; ++qq) v[qq] = vn[qq];
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    u = un;
                 }
                 if (tn >= ntiles) break;
                 t = tn; rc = rcn;
@@ -373,20 +392,20 @@ tc_gemm_kernel(const TcArgs a) {
     }
 }
 
-// W (M x K, row-major, ld) -> tiles [mb][kb]{hi, lo}; tile element (r, kk) at r*32 + ((kk/4) ^ (r%8))*4 + kk%4
-__global__ void tile_weights_kernel(const float *__restrict__ W, int ldw, int M, int K, int m_blocks, int k_blocks, float *__restrict__ Wt) {
+// W (M x K, row-major, ld) -> tiles [m_block][16-block]{hi, lo}; tile element (r, kk) at sw_off(r, kk)
+__global__ void tile_weights_kernel(const float *__restrict__ W, int ldw, int M, int K, int m_blocks, int nks, float *__restrict__ Wt) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)m_blocks * k_blocks * TILE_A_FLOATS;
+    const long long total = (long long)m_blocks * nks * TILE_A_FLOATS;
     if (t >= total) return;
     const int e = (int)(t % TILE_A_FLOATS);
     const long long tile = t / TILE_A_FLOATS;
-    const int kb = (int)(tile % k_blocks), mb = (int)(tile / k_blocks);
-    const int r = e / BK, kk = e % BK;
-    const int m = mb * BM + r, k = kb * BK + kk;
+    const int ks = (int)(tile % nks), mb = (int)(tile / nks);
+    const int r = e / SK, kk = e % SK;
+    const int m = mb * BM + r, k = ks * SK + kk;
     const float x = (m < M && k < K) ? W[(size_t)m * ldw + k] : 0.f;
     float hi, lo;
     split_tf32(x, hi, lo);
-    const int off = r * BK + (((kk >> 2) ^ (r & 7)) << 2) + (kk & 3);
+    const int off = sw_off(r, kk);
     float *dst = Wt + (size_t)tile * (2 * TILE_A_FLOATS);
     dst[off] = hi;
     dst[TILE_A_FLOATS + off] = lo;
@@ -395,17 +414,17 @@ __global__ void tile_weights_kernel(const float *__restrict__ W, int ldw, int M,
 }  // namespace
 
 size_t cmf_tc_act_tiled_floats(long long cols, int C) {
-    return (size_t)((cols + BN - 1) / BN) * (size_t)cmf_divup(C, BK) * 2 * TILE_B_FLOATS;
+    return (size_t)((cols + BN - 1) / BN) * (size_t)(cmf_divup(C, PK) * 2) * 2 * TILE_B_FLOATS;
 }
 
 size_t cmf_tc_tiled_floats(int M, int K) {
-    return (size_t)cmf_divup(M, BM) * cmf_divup(K, BK) * 2 * TILE_A_FLOATS;
+    return (size_t)cmf_divup(M, BM) * (cmf_divup(K, PK) * 2) * 2 * TILE_A_FLOATS;
 }
 
 int cmf_tc_tile_weights(const float *W, int ldw, int M, int K, float *Wt, cudaStream_t st) {
-    const int mb = cmf_divup(M, BM), kb = cmf_divup(K, BK);
-    const long long total = (long long)mb * kb * TILE_A_FLOATS;
-    tile_weights_kernel<<<cmf_divup(total, 256), 256, 0, st>>>(W, ldw, M, K, mb, kb, Wt);
+    const int mb = cmf_divup(M, BM), nks = cmf_divup(K, PK) * 2;
+    const long long total = (long long)mb * nks * TILE_A_FLOATS;
+    tile_weights_kernel<<<cmf_divup(total, 256), 256, 0, st>>>(W, ldw, M, K, mb, nks, Wt);
     CMF_LAUNCH_CHECK();
     return CMF_OK;
 }
@@ -425,7 +444,8 @@ int cmf_launch_tc_gemm(const TcArgs &a, cudaStream_t st) {
     }
     if (a.cols <= 0 || a.m_blocks <= 0) return CMF_OK;
     if (a.out_tiled && ((a.M & 127) || a.epi != TC_EPI_STORE)) { cmf_set_error("tc_gemm: tiled output needs M % 128 == 0 and the STORE epilogue"); return CMF_ERR_INVALID; }
-    if (a.epi == TC_EPI_MAXK && a.ksamp != 4 && a.ksamp != 8 && a.ksamp != 16 && a.ksamp != 32) { cmf_set_error("tc_gemm: MAXK needs ksamp | 32"); return CMF_ERR_INVALID; }
+    if (a.epi == TC_EPI_MAXK && a.ksamp != 4 && a.ksamp != 8 && a.ksamp != 16 && a.ksamp != 32) { cmf_set_error("tc_gemm: MAXK needs ksamp in {4,8,16,32}"); return CMF_ERR_INVALID; }
+    if (a.prod == TC_PROD_FC_H1 && a.ksamp != 8) { cmf_set_error("tc_gemm: the flow-embedding producer assumes 8 neighbours per point"); return CMF_ERR_INVALID; }
     const long long ntiles = ((a.cols + BN - 1) / BN) * a.m_blocks;
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
     if (a.prod == TC_PROD_PLAIN) tc_gemm_kernel<TC_PROD_PLAIN><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
@@ -440,12 +460,12 @@ int cmf_launch_tc_gemm(const TcArgs &a, cudaStream_t st) {
 extern "C" int cmf_test_tc_gemm(int M, int K, long long cols, const float *W, int ldw, const float *X, int ldx,
                                 const float *bias, int act, float *Out, int ldo, float *scratch_tiles, void *stream) {
     CMF_REQUIRE(W && X && Out && scratch_tiles, "null pointer");
-    CMF_REQUIRE((ldx & 3) == 0 && ldx >= cmf_divup(K, BK) * BK, "ldx must be a multiple of 4 and cover K padded to 32");
+    CMF_REQUIRE((ldx & 3) == 0 && ldx >= cmf_divup(K, PK) * PK, "ldx must be a multiple of 4 and cover K padded to 32");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = cmf_tc_tile_weights(W, ldw, M, K, scratch_tiles, st);
     if (rc) return rc;
     TcArgs a{};
-    a.Wt = scratch_tiles; a.m_blocks = cmf_divup(M, BM); a.k_blocks = cmf_divup(K, BK); a.M = M; a.cols = cols;
+    a.Wt = scratch_tiles; a.m_blocks = cmf_divup(M, BM); a.k_blocks = cmf_divup(K, PK); a.M = M; a.cols = cols;
     a.prod = TC_PROD_PLAIN; a.X = X; a.ldx = ldx;
     a.epi = TC_EPI_STORE; a.Out = Out; a.ldo = ldo; a.bias = bias; a.pbias = nullptr; a.act = act; a.cols_per_pair = 1;
     return cmf_launch_tc_gemm(a, st);
