@@ -135,6 +135,7 @@ struct cmf_model {
     int last_b = 0, last_n = 0;
     // tensor-core (tcgen05, 3xTF32) mode: pre-tiled hi/lo copies of the big weight matrices
     int tc = 0;
+    int fused_sc1 = 1;           // CMF_FUSED_SC1=0 falls back to the unfused (GEMM-per-layer) set-conv #1 for A/B testing
     float *tc_buf = nullptr;
     const float *t_fc_wc = nullptr, *t_fc_wn = nullptr, *t_fc_w2 = nullptr, *t_fc_w3 = nullptr, *t_m2_wp = nullptr,
                 *t_m2_w2[4] = {nullptr, nullptr, nullptr, nullptr}, *t_m2_w3[4] = {nullptr, nullptr, nullptr, nullptr}, *t_hd_w1 = nullptr;
@@ -257,9 +258,16 @@ static int run_mse_layer(cmf_model *m, int bc, int n, const float *pc, const flo
                          float *dest, int ldd, float *G, cudaStream_t st) {
     Work &w = m->w;
     const long long bn = (long long)bc * n;
-    RUN(C_GATHER, 0, cmf_launch_build_x0(bc, n, pc, ft, bq, w.X0, st));
     GemmBatch gb;
     gb.count = 4;
+    if (m->fused_sc1) {
+        // gather + 3-layer MLP + max over neighbours in one kernel (all four scales)
+        const float *segs[24];
+        for (int s = 0; s < 4; ++s)
+            for (int k = 0; k < 6; ++k) segs[s * 6 + k] = m->seg[M1_BASE + s * 12 + k];
+        RUN(C_GEMM_SC1, 2.0 * 3264.0 * 60.0 * (double)bn, cmf_launch_setconv1_fused(bc, n, pc, ft, bq, segs, w.M64, st));
+    } else {
+    RUN(C_GATHER, 0, cmf_launch_build_x0(bc, n, pc, ft, bq, w.X0, st));
     for (int s = 0; s < 4; ++s) {
         const int sb = M1_BASE + s * 12;
         gb.g[s] = mk(m->seg[sb + 0], 8, w.X0 + (size_t)bn * KOFF[s] * 8, 8, w.T32a + (size_t)bn * KOFF[s] * 32, 32,
@@ -280,6 +288,7 @@ static int run_mse_layer(cmf_model *m, int bc, int n, const float *pc, const flo
     RUN(C_GEMM_SC1, gflops(gb), cmf_launch_gemm(gb, st));
     for (int s = 0; s < 4; ++s)
         RUN(C_REDUCE, 0, cmf_launch_maxk(bn, KS[s], 64, w.T64 + (size_t)bn * KOFF[s] * 64, 64, w.M64 + s * 64, 256, st));
+    }
     const float *src[3] = {w.M64, w.Q1, w.Q2};
     float *dst[3] = {w.Q1, w.Q2, dest};
     const int lds[3] = {256, 256, 256}, ldo[3] = {256, 256, ldd};
@@ -458,6 +467,8 @@ extern "C" int cmf_model_create(cmf_model **out, const float *blob, size_t blob_
     }
     m->shape = exp;
     *out = m;
+    const char *fe = getenv("CMF_FUSED_SC1");
+    if (fe && fe[0] == '0') m->fused_sc1 = 0;
     const char *env = getenv("CMF_MODE");            // "fp32" (default) | "tf32x3"
     if (env && !strcmp(env, "tf32x3")) { int rc = cmf_model_set_mode(m, 1); if (rc) { cmf_model_destroy(m); *out = nullptr; return rc; } }
     return CMF_OK;

@@ -301,6 +301,114 @@ int cmf_launch_build_x0(int b, int n, const float *xyz_planar, const float *ft_p
     return CMF_OK;
 }
 
+// ---- fused set-conv #1 (mse_layer, C=3): gather -> 6->32->32->64 (BN folded, ReLU) -> max over the K neighbours ----
+// PointLocalFeature up to the max (radarflow_util.py:147-155) for ONE scale per blockIdx.y.  One thread owns two neighbour
+// columns (c, c+128 of the CTA's 256), so every weight fetched from shared memory (128-bit broadcast) feeds 8 FMAs; the
+// three layers stay in registers; the max over a point's K consecutive lanes is an xor-shuffle butterfly.  Replaces
+// build_x0 + three GEMM launches + maxk and their 4.3 GB/cloud/step of activation round trips.
+struct SetConv1W { const float *W1, *b1, *W2, *b2, *W3, *b3; };      // per scale: 32x8, 32, 32x32, 32, 64x32, 64
+struct SetConv1Args { SetConv1W w[4]; };
+
+__global__ void __launch_bounds__(128)
+setconv1_fused_kernel(int n, const float *__restrict__ xyz, const float *__restrict__ ft, const int *__restrict__ idx60,
+                      const SetConv1Args args, float *__restrict__ out /* (B*N, 256) */) {
+    __shared__ __align__(16) float sW1[32 * 8], sW2[32 * 32], sW3[64 * 32], sb1[32], sb2[32], sb3[64];
+    const int s = blockIdx.y, b = blockIdx.z;
+    const int K = 4 << s, koff = (s == 0) ? 0 : (s == 1 ? 4 : (s == 2 ? 12 : 28));
+    const int total_cols = n * K;
+    if ((int)blockIdx.x * 256 >= total_cols) return;
+    const SetConv1W &w = args.w[s];
+    for (int i = threadIdx.x; i < 32 * 8; i += 128) sW1[i] = __ldg(w.W1 + i);
+    for (int i = threadIdx.x; i < 32 * 32; i += 128) sW2[i] = __ldg(w.W2 + i);
+    for (int i = threadIdx.x; i < 64 * 32; i += 128) sW3[i] = __ldg(w.W3 + i);
+    if (threadIdx.x < 32) { sb1[threadIdx.x] = __ldg(w.b1 + threadIdx.x); sb2[threadIdx.x] = __ldg(w.b2 + threadIdx.x); }
+    if (threadIdx.x < 64) sb3[threadIdx.x] = __ldg(w.b3 + threadIdx.x);
+    __syncthreads();
+
+    const float *px = xyz + (size_t)b * 3 * n, *pf = ft + (size_t)b * 3 * n;
+    float x0[2][6];
+    int pi[2]; bool ok[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int c = blockIdx.x * 256 + h * 128 + threadIdx.x;
+        ok[h] = c < total_cols;
+        const int i = ok[h] ? c / K : 0, kk = ok[h] ? c - i * K : 0;
+        pi[h] = i;
+        const int j = __ldg(idx60 + ((size_t)b * n + i) * 60 + koff + kk);
+        x0[h][0] = __fsub_rn(__ldg(px + j), __ldg(px + i));
+        x0[h][1] = __fsub_rn(__ldg(px + n + j), __ldg(px + n + i));
+        x0[h][2] = __fsub_rn(__ldg(px + 2 * n + j), __ldg(px + 2 * n + i));
+        x0[h][3] = __ldg(pf + j); x0[h][4] = __ldg(pf + n + j); x0[h][5] = __ldg(pf + 2 * n + j);
+    }
+    float h1[2][32], h2[2][32];
+#pragma unroll
+    for (int o = 0; o < 32; ++o) {
+        const float4 wa = *reinterpret_cast<const float4 *>(&sW1[o * 8]), wb = *reinterpret_cast<const float4 *>(&sW1[o * 8 + 4]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float a = sb1[o];
+            a = fmaf(wa.x, x0[h][0], a); a = fmaf(wa.y, x0[h][1], a); a = fmaf(wa.z, x0[h][2], a);
+            a = fmaf(wa.w, x0[h][3], a); a = fmaf(wb.x, x0[h][4], a); a = fmaf(wb.y, x0[h][5], a);
+            h1[h][o] = fmaxf(a, 0.f);
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < 32; ++o) {
+        float a0 = sb2[o], a1 = a0;
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) {
+            const float4 wv = *reinterpret_cast<const float4 *>(&sW2[o * 32 + k]);
+            a0 = fmaf(wv.x, h1[0][k], a0); a0 = fmaf(wv.y, h1[0][k + 1], a0); a0 = fmaf(wv.z, h1[0][k + 2], a0); a0 = fmaf(wv.w, h1[0][k + 3], a0);
+            a1 = fmaf(wv.x, h1[1][k], a1); a1 = fmaf(wv.y, h1[1][k + 1], a1); a1 = fmaf(wv.z, h1[1][k + 2], a1); a1 = fmaf(wv.w, h1[1][k + 3], a1);
+        }
+        h2[0][o] = fmaxf(a0, 0.f); h2[1][o] = fmaxf(a1, 0.f);
+    }
+    const int lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (int oc = 0; oc < 64; oc += 8) {
+        float r[2][8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            float a0 = sb3[oc + o], a1 = a0;
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) {
+                const float4 wv = *reinterpret_cast<const float4 *>(&sW3[(oc + o) * 32 + k]);
+                a0 = fmaf(wv.x, h2[0][k], a0); a0 = fmaf(wv.y, h2[0][k + 1], a0); a0 = fmaf(wv.z, h2[0][k + 2], a0); a0 = fmaf(wv.w, h2[0][k + 3], a0);
+                a1 = fmaf(wv.x, h2[1][k], a1); a1 = fmaf(wv.y, h2[1][k + 1], a1); a1 = fmaf(wv.z, h2[1][k + 2], a1); a1 = fmaf(wv.w, h2[1][k + 3], a1);
+            }
+            r[0][o] = fmaxf(a0, 0.f); r[1][o] = fmaxf(a1, 0.f);
+        }
+        // max over the K consecutive lanes of a point (K | 32, groups are lane-aligned because 128 and 256 are multiples of K)
+        for (int off = 1; off < K; off <<= 1)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int o = 0; o < 8; ++o) r[h][o] = fmaxf(r[h][o], __shfl_xor_sync(0xffffffffu, r[h][o], off));
+        if ((lane & (K - 1)) == 0) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (ok[h]) {
+                    float *dst = out + ((size_t)b * n + pi[h]) * 256 + s * 64 + oc;
+                    *reinterpret_cast<float4 *>(dst) = make_float4(r[h][0], r[h][1], r[h][2], r[h][3]);
+                    *reinterpret_cast<float4 *>(dst + 4) = make_float4(r[h][4], r[h][5], r[h][6], r[h][7]);
+                }
+        }
+    }
+}
+
+int cmf_launch_setconv1_fused(int b, int n, const float *xyz_planar, const float *ft_planar, const int *idx60,
+                              const float *const *seg12x4 /* 4 scales x {W1,b1,W2,b2,W3,b3} */, float *out, cudaStream_t st) {
+    SetConv1Args a;
+    for (int s = 0; s < 4; ++s) {
+        a.w[s].W1 = seg12x4[s * 6 + 0]; a.w[s].b1 = seg12x4[s * 6 + 1]; a.w[s].W2 = seg12x4[s * 6 + 2];
+        a.w[s].b2 = seg12x4[s * 6 + 3]; a.w[s].W3 = seg12x4[s * 6 + 4]; a.w[s].b3 = seg12x4[s * 6 + 5];
+    }
+    dim3 grid(cmf_divup((long long)n * 32, 256), 4, b);
+    setconv1_fused_kernel<<<grid, 128, 0, st>>>(n, xyz_planar, ft_planar, idx60, a, out);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
 __global__ void __launch_bounds__(256)
 maxk_kernel(long long points, int K, int C4, const float *__restrict__ Y, int ldy, float *__restrict__ out, int ldo) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;

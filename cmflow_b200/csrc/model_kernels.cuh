@@ -24,6 +24,9 @@ int cmf_launch_knn_point8(int b, int n, const float *cand_aos, const float *quer
 // mse_layer input rows: X0[scale s][(b*N+i)*K_s + kk][0..7] = [xyz_j - xyz_i, ft_j, 0, 0]
 int cmf_launch_build_x0(int b, int n, const float *xyz_planar, const float *ft_planar, const int *idx60,
                         float *x0 /* 4 scale segments, see engine */, cudaStream_t st);
+// fused set-conv #1 up to the max over neighbours: out (B*N, 256) = [scale0 64 | scale1 64 | scale2 64 | scale3 64]
+int cmf_launch_setconv1_fused(int b, int n, const float *xyz_planar, const float *ft_planar, const int *idx60,
+                              const float *const *seg12x4, float *out, cudaStream_t st);
 // out[(b*N+i)*ldo + c] = max_kk Y[((b*N+i)*K + kk)*ldy + c], c < C (C % 4 == 0)
 int cmf_launch_maxk(long long points, int K, int C, const float *Y, int ldy, float *out, int ldo, cudaStream_t st);
 // G[b][c] = max_i F[(b*N+i)*ldf + c]

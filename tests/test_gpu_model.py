@@ -167,3 +167,20 @@ def test_dense_cloud_config_runs_and_matches_oracle_prefix():
     assert torch.equal(net.tap("bq1", (1, 4096, 60), torch.int32).cpu(), want)
     assert torch.equal(net.tap("knn12", (1, 4096, 8), torch.int32).cpu(), P.knn_point(8, x2t, x1t)[0])
     assert torch.isfinite(out["sf_agg"]).all()
+
+
+def test_fused_setconv1_equals_layerwise(golden_dir, monkeypatch):
+    """The fused gather+MLP+max kernel of set-conv #1 against the GEMM-per-layer path (same fp32 FMAs, bias added first
+    instead of last): agreement to fp32 rounding."""
+    gold = load_golden(golden_dir, "cmflow_synth_b3_n200.pt")
+    inp = case_inputs(gold["meta"])
+    net, sd = build(gold["meta"], golden_dir)
+    out = run(net, inp)
+    f1 = net.tap("E", (3, 200, 800)).cpu()[..., :256]
+    f2 = net.tap("f2", (3, 200, 256)).cpu()
+    monkeypatch.setenv("CMF_FUSED_SC1", "0")
+    net0, _ = build(gold["meta"], golden_dir)
+    out0 = run(net0, inp)
+    assert rel_err(f1, net0.tap("E", (3, 200, 800)).cpu()[..., :256]) < 2e-6
+    assert rel_err(f2, net0.tap("f2", (3, 200, 256)).cpu()) < 2e-6
+    assert rel_err(out["sf_agg"], out0["sf_agg"]) < 2e-5
