@@ -91,7 +91,7 @@ struct Work {
     float *E, *F2, *G1, *G2;
     float *X0, *T32a, *T32b, *T64, *M64, *Q1, *Q2;
     float *PB1, *PB2, *U1, *U2, *H1, *H2, *COST1;
-    float *PBM, *P, *Q, *Y1, *Y2, *Y3, *PROP, *GP, *GI, *GH, *GNEW, *ZERO;
+    float *PBM, *P, *Y1, *Y2, *Y3, *PROP, *GP, *GI, *GH, *GNEW, *ZERO;
     float *PBH, *HD1, *HD2, *HD3, *FLOW;
 };
 
@@ -109,7 +109,7 @@ void carve(Arena &a, Work &w, int bc, int n) {
     w.U1 = a.take<float>(bn * 512); w.U2 = a.take<float>(bn * 512);
     w.H1 = a.take<float>(bn * 8 * 512); w.H2 = a.take<float>(cmf_tc_act_tiled_floats((long long)bn * 8, 512));   // H2: row-major (fp32 mode) or tiled hi/lo (tc mode)
     w.COST1 = a.take<float>(bn * 512);
-    w.PBM = a.take<float>((size_t)bc * 2048); w.P = a.take<float>(bn * 2048); w.Q = a.take<float>(bn * 2048);
+    w.PBM = a.take<float>((size_t)bc * 2048); w.P = a.take<float>(bn * 2048);
     w.Y1 = a.take<float>(bn * 32 * 512); w.Y2 = a.take<float>(cmf_tc_act_tiled_floats((long long)bn * 32, 256)); w.Y3 = a.take<float>(bn * 32 * 64);
     w.PROP = a.take<float>(bn * 256); w.GP = a.take<float>((size_t)bc * 256);
     w.GI = a.take<float>((size_t)bc * 768); w.GH = a.take<float>((size_t)bc * 768);
@@ -155,7 +155,6 @@ static void prof_events(cmf_model *m, cudaEvent_t *a, cudaEvent_t *b) {
 static GemmArgs mk(const float *W, int ldw, const float *X, int ldx, float *Out, int ldo, const float *bias,
                    int M, int K, long long cols, int act, const float *pbias = nullptr, int pb_ld = 0, int cpp = 1) {
     GemmArgs g;
-    g.xyz = nullptr; g.Wxyz = nullptr; g.xsign = 0.f; g.n_pts = 1;
     g.W = W; g.X = X; g.Out = Out; g.bias = bias; g.pbias = pbias;
     g.ldw = ldw; g.ldx = ldx; g.ldo = ldo; g.pb_ld = pb_ld; g.cols_per_pair = cpp;
     g.M = M; g.K = K; g.cols = (int)cols; g.act = act;
@@ -328,15 +327,12 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
     { const GemmArgs ga_ = mk(S(FC_WCG), 256, w.G1, 256, w.PB1, 512, S(FC_B1), 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     { const GemmArgs ga_ = mk(S(FC_WNG), 256, w.G2, 256, w.PB2, 512, nullptr, 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     if (m->tc) {
-        // conv0 hoisted per point; the direction columns Wd.(x2_j - x1_i) are split into +Wd.x2_j (in U2x) and -Wd.x1_i (in U1x)
-        { TcArgs ta_ = tc_plain(m->t_fc_wc, 512, 256, w.E, E_LD, w.U1, 512, nullptr, bn, CMF_ACT_NONE, w.PB1, 512, n);
-          ta_.xyz_epi = pc1; ta_.Wxyz = S(FC_WD); ta_.xsign = -1.f; ta_.xyz_n = n; RUN(C_GEMM_FC_HOIST, tflops(ta_, 256), cmf_launch_tc_gemm(ta_, st)); }
-        { TcArgs ta_ = tc_plain(m->t_fc_wn, 512, 256, w.F2, 256, w.U2, 512, nullptr, bn, CMF_ACT_NONE, w.PB2, 512, n);
-          ta_.xyz_epi = pc2; ta_.Wxyz = S(FC_WD); ta_.xsign = 1.f; ta_.xyz_n = n; RUN(C_GEMM_FC_HOIST, tflops(ta_, 256), cmf_launch_tc_gemm(ta_, st)); }
+        { const TcArgs ta_ = tc_plain(m->t_fc_wc, 512, 256, w.E, E_LD, w.U1, 512, nullptr, bn, CMF_ACT_NONE, w.PB1, 512, n); RUN(C_GEMM_FC_HOIST, tflops(ta_, 256), cmf_launch_tc_gemm(ta_, st)); }
+        { const TcArgs ta_ = tc_plain(m->t_fc_wn, 512, 256, w.F2, 256, w.U2, 512, nullptr, bn, CMF_ACT_NONE, w.PB2, 512, n); RUN(C_GEMM_FC_HOIST, tflops(ta_, 256), cmf_launch_tc_gemm(ta_, st)); }
         {   // conv1 with the gather + hoisted conv0 epilogue fused into the B-operand producer (no H1 round trip)
             TcArgs ta_ = tc_plain(m->t_fc_w2, 512, 512, nullptr, 0, w.H2, 512, S(FC_B2), bn * 8, CMF_ACT_LEAKY);
-            ta_.prod = TC_PROD_FC_H1; ta_.U1 = w.U1; ta_.ld_u1 = 512; ta_.off_u1 = 0; ta_.U2 = w.U2; ta_.ld_u2 = 512; ta_.off_u2 = 0;
-            ta_.nbr = w.KNN12; ta_.nbr_ld = 8; ta_.nbr_off = 0; ta_.ksamp = 8; ta_.n_pts = n;
+            ta_.prod = TC_PROD_FC_H1; ta_.U1 = w.U1; ta_.U2 = w.U2; ta_.ld_u2 = 512; ta_.off_u2 = 0; ta_.Wsmall = S(FC_WD);
+            ta_.xyz_q = pc1; ta_.xyz_c = pc2; ta_.nbr = w.KNN12; ta_.nbr_ld = 8; ta_.nbr_off = 0; ta_.ksamp = 8; ta_.n_pts = n;
             ta_.out_tiled = 1;                 // conv2's B operand is written TF32-split + swizzled, ready for a bulk copy
             RUN(C_GEMM_FC_MLP, tflops(ta_, 512), cmf_launch_tc_gemm(ta_, st));
         }
@@ -346,11 +342,9 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
             RUN(C_GEMM_FC_MLP, tflops(ta_, 512), cmf_launch_tc_gemm(ta_, st));
         }
     } else {
-    { GemmArgs ga_ = mk(S(FC_WC), 256, w.E, E_LD, w.U1, 512, nullptr, 512, 256, bn, CMF_ACT_NONE, w.PB1, 512, n);
-      ga_.xyz = pc1; ga_.Wxyz = S(FC_WD); ga_.xsign = -1.f; ga_.n_pts = n; RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
-    { GemmArgs ga_ = mk(S(FC_WN), 256, w.F2, 256, w.U2, 512, nullptr, 512, 256, bn, CMF_ACT_NONE, w.PB2, 512, n);
-      ga_.xyz = pc2; ga_.Wxyz = S(FC_WD); ga_.xsign = 1.f; ga_.n_pts = n; RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
-    RUN(C_GATHER, 0, cmf_launch_fc_build_h1(bc, n, w.KNN12, w.U1, w.U2, w.H1, st));
+    { const GemmArgs ga_ = mk(S(FC_WC), 256, w.E, E_LD, w.U1, 512, nullptr, 512, 256, bn, CMF_ACT_NONE, w.PB1, 512, n); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
+    { const GemmArgs ga_ = mk(S(FC_WN), 256, w.F2, 256, w.U2, 512, nullptr, 512, 256, bn, CMF_ACT_NONE, w.PB2, 512, n); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
+    RUN(C_GATHER, 0, cmf_launch_fc_build_h1(bc, n, pc1, pc2, w.KNN12, w.U1, w.U2, S(FC_WD), w.H1, st));
     { const GemmArgs ga_ = mk(S(FC_W2), 512, w.H1, 512, w.H2, 512, S(FC_B2), 512, 512, bn * 8, CMF_ACT_LEAKY); RUN(C_GEMM_FC_MLP, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     { const GemmArgs ga_ = mk(S(FC_W3), 512, w.H2, 512, w.H1, 512, S(FC_B3), 512, 512, bn * 8, CMF_ACT_LEAKY); RUN(C_GEMM_FC_MLP, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     }
@@ -361,24 +355,21 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
 
     // set-conv #2 (mse_layer2, cmflow.py:87-89)
     { const GemmArgs ga_ = mk(S(M2_WG), 256, w.G1, 256, w.PBM, 2048, S(M2_T1), 2048, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_SC2_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
-    // conv0 hoisted per point: Px[j] = W.[f1;cor;ft]_j + (per-pair part) + Wx.x_j ;  Qx[i] = Wx.x_i ;  layer-1 output = relu(Px[j] - Qx[i])
     if (m->tc) {
-        TcArgs ta_ = tc_plain(m->t_m2_wp, 2048, E_LD, w.E, E_LD, w.P, 2048, nullptr, bn, CMF_ACT_NONE, w.PBM, 2048, n);
-        ta_.xyz_epi = pc1; ta_.Wxyz = S(M2_WX); ta_.xsign = 1.f; ta_.xyz_n = n;
+        const TcArgs ta_ = tc_plain(m->t_m2_wp, 2048, E_LD, w.E, E_LD, w.P, 2048, nullptr, bn, CMF_ACT_NONE, w.PBM, 2048, n);
         RUN(C_GEMM_SC2_HOIST, tflops(ta_, 771), cmf_launch_tc_gemm(ta_, st));
     } else {
-        GemmArgs ga_ = mk(S(M2_WP), E_LD, w.E, E_LD, w.P, 2048, nullptr, 2048, E_LD, bn, CMF_ACT_NONE, w.PBM, 2048, n);
-        ga_.xyz = pc1; ga_.Wxyz = S(M2_WX); ga_.xsign = 1.f; ga_.n_pts = n;
+        const GemmArgs ga_ = mk(S(M2_WP), E_LD, w.E, E_LD, w.P, 2048, nullptr, 2048, E_LD, bn, CMF_ACT_NONE, w.PBM, 2048, n);
         RUN(C_GEMM_SC2_HOIST, 2.0 * 2048 * 771.0 * bn, cmf_launch_gemm1(ga_, st));
     }
-    RUN(C_GATHER, 0, cmf_launch_qxyz(bc, n, 2048, pc1, S(M2_WX), w.Q, st));
     for (int s = 0; s < 4; ++s) {
         const int sb = M2_BASE + s * 10;
         if (m->tc) {
             {   // layer 2 (512->256): neighbour gather of the hoisted layer-1 rows + rel-xyz term + ReLU fused into the B producer
                 TcArgs ta_ = tc_plain(m->t_m2_w2[s], 256, 512, nullptr, 0, w.Y2, 256, S(sb + 1), bn * KS[s], CMF_ACT_RELU);
-                ta_.prod = TC_PROD_SC2_Y1; ta_.U1 = w.Q; ta_.ld_u1 = 2048; ta_.off_u1 = s * 512; ta_.U2 = w.P; ta_.ld_u2 = 2048; ta_.off_u2 = s * 512;
-                ta_.nbr = w.BQ1; ta_.nbr_ld = 60; ta_.nbr_off = KOFF[s]; ta_.ksamp = KS[s]; ta_.n_pts = n;
+                ta_.prod = TC_PROD_SC2_Y1; ta_.U1 = nullptr; ta_.U2 = w.P; ta_.ld_u2 = 2048; ta_.off_u2 = s * 512;
+                ta_.Wsmall = S(M2_WX) + (size_t)s * 512 * 4; ta_.xyz_q = pc1; ta_.xyz_c = pc1; ta_.nbr = w.BQ1; ta_.nbr_ld = 60;
+                ta_.nbr_off = KOFF[s]; ta_.ksamp = KS[s]; ta_.n_pts = n;
                 ta_.out_tiled = 1;
                 RUN(C_GEMM_SC2_L2, tflops(ta_, 512), cmf_launch_tc_gemm(ta_, st));
             }
@@ -389,7 +380,7 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
                 RUN(C_GEMM_SC2_L3, tflops(ta_, 256), cmf_launch_tc_gemm(ta_, st));
             }
         } else {
-        RUN(C_GATHER, 0, cmf_launch_mse2_build_y1(bc, n, KS[s], KOFF[s], w.BQ1, w.P, w.Q, 2048, s * 512, w.Y1, st));
+        RUN(C_GATHER, 0, cmf_launch_mse2_build_y1(bc, n, KS[s], KOFF[s], pc1, w.BQ1, w.P, 2048, s * 512, S(M2_WX) + (size_t)s * 512 * 4, w.Y1, st));
         { const GemmArgs ga_ = mk(S(sb), 512, w.Y1, 512, w.Y2, 256, S(sb + 1), 256, 512, bn * KS[s], CMF_ACT_RELU); RUN(C_GEMM_SC2_L2, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
         { const GemmArgs ga_ = mk(S(sb + 2), 256, w.Y2, 256, w.Y3, 64, S(sb + 3), 64, 256, bn * KS[s], CMF_ACT_RELU); RUN(C_GEMM_SC2_L3, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
         RUN(C_REDUCE, 0, cmf_launch_maxk(bn, KS[s], 64, w.Y3, 64, w.M64 + s * 64, 256, st));

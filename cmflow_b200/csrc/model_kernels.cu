@@ -107,23 +107,11 @@ gemm_nt_kernel(const GemmBatch gb) {
         const int c = c0 + (j < 4 ? tc * 4 + j : 64 + tc * 4 + (j - 4));
         if (c >= g.cols) continue;
         const float *pb = g.pbias ? g.pbias + (size_t)(c / g.cols_per_pair) * g.pb_ld : nullptr;
-        float px = 0.f, py = 0.f, pz = 0.f;
-        if (g.xyz) {
-            const int bb = c / g.n_pts, ii = c - bb * g.n_pts;
-            const float *pp = g.xyz + (size_t)bb * 3 * g.n_pts + ii;
-            px = g.xsign * __ldg(pp); py = g.xsign * __ldg(pp + g.n_pts); pz = g.xsign * __ldg(pp + 2 * g.n_pts);
-        }
 #pragma unroll
         for (int r = 0; r < TMG; ++r) {
             const int m = m0 + 64 * r + tm * 4;
             if (m >= g.M) continue;
             float4 v = make_float4(acc[r * 4 + 0][j], acc[r * 4 + 1][j], acc[r * 4 + 2][j], acc[r * 4 + 3][j]);
-            if (g.xyz) {
-                const float4 w0 = __ldg(reinterpret_cast<const float4 *>(g.Wxyz + (size_t)(m + 0) * 4)), w1 = __ldg(reinterpret_cast<const float4 *>(g.Wxyz + (size_t)(m + 1) * 4));
-                const float4 w2 = __ldg(reinterpret_cast<const float4 *>(g.Wxyz + (size_t)(m + 2) * 4)), w3 = __ldg(reinterpret_cast<const float4 *>(g.Wxyz + (size_t)(m + 3) * 4));
-                v.x += fmaf(w0.z, pz, fmaf(w0.y, py, w0.x * px)); v.y += fmaf(w1.z, pz, fmaf(w1.y, py, w1.x * px));
-                v.z += fmaf(w2.z, pz, fmaf(w2.y, py, w2.x * px)); v.w += fmaf(w3.z, pz, fmaf(w3.y, py, w3.x * px));
-            }
             if (g.bias) {
                 const float4 bb = __ldg(reinterpret_cast<const float4 *>(g.bias + m));
                 v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
@@ -480,39 +468,30 @@ __device__ __forceinline__ float4 ld4(const float *p) { return __ldg(reinterpret
 __device__ __forceinline__ float leaky01(float v) { return v > 0.f ? v : 0.1f * v; }
 
 __global__ void __launch_bounds__(128)
-fc_build_h1_kernel(int n, const int *__restrict__ knn12, const float *__restrict__ U1, const float *__restrict__ U2, float *__restrict__ H1) {
-    const int bi = blockIdx.x, b = bi / n, t = threadIdx.x;
+fc_build_h1_kernel(int n, const float *__restrict__ xyz1, const float *__restrict__ xyz2, const int *__restrict__ knn12,
+                   const float *__restrict__ U1, const float *__restrict__ U2, const float *__restrict__ Wd,
+                   float *__restrict__ H1) {
+    const int bi = blockIdx.x, b = bi / n, i = bi - b * n, t = threadIdx.x;
+    const float *p1 = xyz1 + (size_t)b * 3 * n, *p2 = xyz2 + (size_t)b * 3 * n;
+    const float qx = __ldg(p1 + i), qy = __ldg(p1 + n + i), qz = __ldg(p1 + 2 * n + i);
     const float4 u1 = ld4(U1 + (size_t)bi * 512 + t * 4);
+    const float4 w0 = ld4(Wd + (t * 4 + 0) * 4), w1 = ld4(Wd + (t * 4 + 1) * 4), w2 = ld4(Wd + (t * 4 + 2) * 4), w3 = ld4(Wd + (t * 4 + 3) * 4);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int j = __ldg(knn12 + (size_t)bi * 8 + k);
+        const float dx = __fsub_rn(__ldg(p2 + j), qx), dy = __fsub_rn(__ldg(p2 + n + j), qy), dz = __fsub_rn(__ldg(p2 + 2 * n + j), qz);
         const float4 u2 = ld4(U2 + ((size_t)b * n + j) * 512 + t * 4);
         float4 v;
-        v.x = leaky01(u1.x + u2.x); v.y = leaky01(u1.y + u2.y); v.z = leaky01(u1.z + u2.z); v.w = leaky01(u1.w + u2.w);
+        v.x = leaky01(u1.x + u2.x + fmaf(w0.z, dz, fmaf(w0.y, dy, w0.x * dx)));
+        v.y = leaky01(u1.y + u2.y + fmaf(w1.z, dz, fmaf(w1.y, dy, w1.x * dx)));
+        v.z = leaky01(u1.z + u2.z + fmaf(w2.z, dz, fmaf(w2.y, dy, w2.x * dx)));
+        v.w = leaky01(u1.w + u2.w + fmaf(w3.z, dz, fmaf(w3.y, dy, w3.x * dx)));
         *reinterpret_cast<float4 *>(H1 + ((size_t)bi * 8 + k) * 512 + t * 4) = v;
     }
 }
-int cmf_launch_fc_build_h1(int b, int n, const int *knn12, const float *U1, const float *U2, float *H1, cudaStream_t st) {
-    fc_build_h1_kernel<<<b * n, 128, 0, st>>>(n, knn12, U1, U2, H1);
-    CMF_LAUNCH_CHECK();
-    return CMF_OK;
-}
-
-__global__ void __launch_bounds__(256)
-qxyz_kernel(int n, int M4, const float *__restrict__ xyz, const float *__restrict__ Wx, float *__restrict__ Q) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    if (t >= (long long)n * M4) return;
-    const int i = (int)(t / M4), m = (int)(t - (long long)i * M4) * 4;
-    const float *pp = xyz + (size_t)b * 3 * n + i;
-    const float x = __ldg(pp), y = __ldg(pp + n), z = __ldg(pp + 2 * n);
-    const float4 w0 = ld4(Wx + (size_t)m * 4), w1 = ld4(Wx + (size_t)(m + 1) * 4), w2 = ld4(Wx + (size_t)(m + 2) * 4), w3 = ld4(Wx + (size_t)(m + 3) * 4);
-    *reinterpret_cast<float4 *>(Q + ((size_t)b * n + i) * (size_t)(M4 * 4) + m) =
-        make_float4(fmaf(w0.z, z, fmaf(w0.y, y, w0.x * x)), fmaf(w1.z, z, fmaf(w1.y, y, w1.x * x)),
-                    fmaf(w2.z, z, fmaf(w2.y, y, w2.x * x)), fmaf(w3.z, z, fmaf(w3.y, y, w3.x * x)));
-}
-int cmf_launch_qxyz(int b, int n, int M, const float *xyz_planar, const float *Wx, float *Q, cudaStream_t st) {
-    qxyz_kernel<<<dim3(cmf_divup((long long)n * (M / 4), 256), b), 256, 0, st>>>(n, M / 4, xyz_planar, Wx, Q);
+int cmf_launch_fc_build_h1(int b, int n, const float *xyz1_planar, const float *xyz2_planar, const int *knn12,
+                           const float *U1, const float *U2, const float *Wd, float *H1, cudaStream_t st) {
+    fc_build_h1_kernel<<<b * n, 128, 0, st>>>(n, xyz1_planar, xyz2_planar, knn12, U1, U2, Wd, H1);
     CMF_LAUNCH_CHECK();
     return CMF_OK;
 }
@@ -576,20 +555,27 @@ int cmf_launch_fc_reduce(int b, int n, const float *xyzq_planar, const float *xy
 // set-conv #2 (mse_layer2) first layer after hoisting the 1027-channel conv over the gather
 // =================================================================================================
 __global__ void __launch_bounds__(128)
-mse2_build_y1_kernel(int n, int K, int koff, const int *__restrict__ idx60, const float *__restrict__ P, const float *__restrict__ Q,
-                     int ldp, int poff, float *__restrict__ Y1) {
-    const int bi = blockIdx.x, b = bi / n, t = threadIdx.x;
-    const float4 q = ld4(Q + (size_t)bi * ldp + poff + t * 4);
+mse2_build_y1_kernel(int n, int K, int koff, const float *__restrict__ xyz, const int *__restrict__ idx60,
+                     const float *__restrict__ P, int ldp, int poff, const float *__restrict__ Wx, float *__restrict__ Y1) {
+    const int bi = blockIdx.x, b = bi / n, i = bi - b * n, t = threadIdx.x;
+    const float *px = xyz + (size_t)b * 3 * n;
+    const float qx = __ldg(px + i), qy = __ldg(px + n + i), qz = __ldg(px + 2 * n + i);
+    const float4 w0 = ld4(Wx + (t * 4 + 0) * 4), w1 = ld4(Wx + (t * 4 + 1) * 4), w2 = ld4(Wx + (t * 4 + 2) * 4), w3 = ld4(Wx + (t * 4 + 3) * 4);
     for (int kk = 0; kk < K; ++kk) {
         const int j = __ldg(idx60 + (size_t)bi * 60 + koff + kk);
+        const float dx = __fsub_rn(__ldg(px + j), qx), dy = __fsub_rn(__ldg(px + n + j), qy), dz = __fsub_rn(__ldg(px + 2 * n + j), qz);
         const float4 p = ld4(P + ((size_t)b * n + j) * ldp + poff + t * 4);
-        *reinterpret_cast<float4 *>(Y1 + ((size_t)bi * K + kk) * 512 + t * 4) =
-            make_float4(fmaxf(p.x - q.x, 0.f), fmaxf(p.y - q.y, 0.f), fmaxf(p.z - q.z, 0.f), fmaxf(p.w - q.w, 0.f));
+        float4 v;
+        v.x = fmaxf(p.x + fmaf(w0.z, dz, fmaf(w0.y, dy, w0.x * dx)), 0.f);
+        v.y = fmaxf(p.y + fmaf(w1.z, dz, fmaf(w1.y, dy, w1.x * dx)), 0.f);
+        v.z = fmaxf(p.z + fmaf(w2.z, dz, fmaf(w2.y, dy, w2.x * dx)), 0.f);
+        v.w = fmaxf(p.w + fmaf(w3.z, dz, fmaf(w3.y, dy, w3.x * dx)), 0.f);
+        *reinterpret_cast<float4 *>(Y1 + ((size_t)bi * K + kk) * 512 + t * 4) = v;
     }
 }
-int cmf_launch_mse2_build_y1(int b, int n, int K, int koff, const int *idx60, const float *P, const float *Q, int ldp, int poff,
-                             float *Y1, cudaStream_t st) {
-    mse2_build_y1_kernel<<<b * n, 128, 0, st>>>(n, K, koff, idx60, P, Q, ldp, poff, Y1);
+int cmf_launch_mse2_build_y1(int b, int n, int K, int koff, const float *xyz_planar, const int *idx60,
+                             const float *P, int ldp, int poff, const float *Wx, float *Y1, cudaStream_t st) {
+    mse2_build_y1_kernel<<<b * n, 128, 0, st>>>(n, K, koff, xyz_planar, idx60, P, ldp, poff, Wx, Y1);
     CMF_LAUNCH_CHECK();
     return CMF_OK;
 }

@@ -8,13 +8,10 @@ enum { CMF_ACT_NONE = 0, CMF_ACT_RELU = 1, CMF_ACT_LEAKY = 2 };
 // W (M x K) row-major with leading dimension ldw; X rows of K contiguous floats, leading dim ldx;
 // Out rows of M floats, leading dim ldo.  K, ldw, ldx, ldo, M must be multiples of 4 and all base
 // pointers 16-byte aligned.  bias / pbias may be NULL.
-// Optional "xyz epilogue": Out[c][m] += xsign * (Wxyz[m][0..2] . xyz(point c)), xyz planar (B,3,n_pts), c = b*n_pts + i.
-// (Hoists the rel-xyz / direction columns of the first conv: W.(x_j - x_i) = W.x_j - W.x_i, each half added here in exact fp32.)
 struct GemmArgs {
     const float *W; const float *X; float *Out; const float *bias; const float *pbias;
     int ldw, ldx, ldo, pb_ld, cols_per_pair;
     int M, K, cols, act;
-    const float *xyz; const float *Wxyz; float xsign; int n_pts;
 };
 struct GemmBatch { GemmArgs g[4]; int count; };
 int cmf_launch_gemm(const GemmBatch &gb, cudaStream_t st);
@@ -38,17 +35,16 @@ int cmf_launch_globalmax(int b, int n, int C, const float *F, int ldf, float *G,
 int cmf_launch_scatter_ft(int b, int n, const float *ft_planar, float *E, int lde, int off, int pad, cudaStream_t st);
 
 // flow embedding (FeatureCorrelator) pieces
-// H1[(b*N+i)*8+k][c] = leaky(U1x[b*N+i][c] + U2x[b*N+knn12[i][k]][c])   (direction term already folded into U1x / U2x)
-int cmf_launch_fc_build_h1(int b, int n, const int *knn12, const float *U1, const float *U2, float *H1, cudaStream_t st);
-// Q[(b*N+i)][m] = Wx[m][0..2] . xyz(b,i)   for m < M (M % 4 == 0), Wx rows of 4 floats
-int cmf_launch_qxyz(int b, int n, int M, const float *xyz_planar, const float *Wx, float *Q, cudaStream_t st);
+int cmf_launch_fc_build_h1(int b, int n, const float *xyz1_planar, const float *xyz2_planar, const int *knn12,
+                           const float *U1, const float *U2, const float *Wd /*512x4*/, float *H1, cudaStream_t st);
 struct WeightNetP { const float *A1, *a1, *A2, *a2, *A3, *a3; };   // 8x4, 8, 8x8, 8, 512x8, 512
 int cmf_launch_fc_reduce(int b, int n, const float *xyzq_planar, const float *xyzc_planar, const int *knn,
                          WeightNetP wn, const float *src, int gather /*0: src rows (b*N+i)*8+k ; 1: src rows b*N+j*/,
                          float *out, int ldo, cudaStream_t st);
-// set-conv #2 first layer after hoisting: Y1[((b*N+i)*K + kk)][c] = relu(Px[(b*N+j)*ldp + poff + c] - Qx[(b*N+i)*ldp + poff + c])
-int cmf_launch_mse2_build_y1(int b, int n, int K, int koff, const int *idx60,
-                             const float *P, const float *Q, int ldp, int poff, float *Y1, cudaStream_t st);
+// set-conv #2 first layer after hoisting: Y1[((b*N+i)*K + kk)][c] = relu(P[(b*N+j)*ldp + poff + c] + Wx[c][0..2] . rel)
+int cmf_launch_mse2_build_y1(int b, int n, int K, int koff, const float *xyz_planar, const int *idx60,
+                             const float *P, int ldp, int poff, const float *Wx /*512x4 rows for this scale*/,
+                             float *Y1, cudaStream_t st);
 // heads' last layer: flow (B,3,N) = W4f . h[:, 0:64] ; cls (B,N) = sigmoid(W4m . h[:, 64:128])
 int cmf_launch_head_final(int b, int n, const float *H3, int ldh, const float *W4f, const float *W4m,
                           float *flow_planar, float *cls, cudaStream_t st);

@@ -28,7 +28,7 @@ constexpr int TILE_B_FLOATS = BN * SK;              // 4096 floats = 16 KB
 constexpr int STAGE_BYTES = (2 * TILE_A_FLOATS + 2 * TILE_B_FLOATS) * 4;   // 48 KB
 constexpr int NSTAGE = 4;
 constexpr int NTHREADS = 512;
-constexpr int SMALL_BYTES = 0;
+constexpr int SMALL_BYTES = 512 * 16;               // rel-xyz / direction weights (C x 4 floats) of the gather producers
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + SMALL_BYTES;
 constexpr unsigned SPIN_LIMIT = 1u << 24;
 
@@ -120,65 +120,64 @@ __device__ __forceinline__ void maxk_groups(const uint32_t (&r)[32], float bias,
 
 struct RowCtx {          // per-producer-thread description of its activation row for the current tile
     bool valid;
-    const float *src0, *src1;      // PLAIN: src0 = the row ; gather modes: src1 = gathered neighbour row, src0 = centre-point row
+    const float *src0, *src1;      // PLAIN: src0 ; FC_H1: src0 = U1 row (centre point), src1 = U2 row (neighbour) ; SC2_Y1: src1 = P row
+    float dx, dy, dz;
 };
 
 __device__ __forceinline__ RowCtx make_row(const TcArgs &a, long long c) {
     RowCtx r;
     r.valid = c < a.cols;
-    r.src0 = r.src1 = nullptr;
+    r.src0 = r.src1 = nullptr; r.dx = r.dy = r.dz = 0.f;
     if (!r.valid) return r;
     if (a.prod == TC_PROD_PLAIN) { r.src0 = a.X + (size_t)c * a.ldx; return r; }
     const long long bi = c / a.ksamp;
     const int kk = (int)(c - bi * a.ksamp);
-    const int b = (int)(bi / a.n_pts);
+    const int b = (int)(bi / a.n_pts), i = (int)(bi - (long long)b * a.n_pts);
     const int j = __ldg(a.nbr + (size_t)bi * a.nbr_ld + a.nbr_off + kk);
-    r.src0 = a.U1 + (size_t)bi * a.ld_u1 + a.off_u1;
+    const float *pq = a.xyz_q + (size_t)b * 3 * a.n_pts, *pc = a.xyz_c + (size_t)b * 3 * a.n_pts;
+    r.dx = __fsub_rn(__ldg(pc + j), __ldg(pq + i));
+    r.dy = __fsub_rn(__ldg(pc + a.n_pts + j), __ldg(pq + a.n_pts + i));
+    r.dz = __fsub_rn(__ldg(pc + 2 * a.n_pts + j), __ldg(pq + 2 * a.n_pts + i));
+    r.src0 = a.U1 ? a.U1 + (size_t)bi * 512 : nullptr;
     r.src1 = a.U2 + ((size_t)b * a.n_pts + j) * a.ld_u2 + a.off_u2;
     return r;
 }
 
-// One 32-float block of this thread's (gathered) row, BEFORE the tf32 split: 128 contiguous bytes.  In the gather modes the
-// centre-point row is shared by the `ksamp` consecutive rows (lanes) of a point: the lanes of a group split its eight 16-byte
-// chunks between them (`u0`,`u1`) and exchange them by shuffle at store time.
-//   ksamp == 4 : lane g (0..3) holds chunks 2g, 2g+1        ksamp >= 8 : lane g < 8 holds chunk g
+// One 32-float block of this thread's (gathered) row, BEFORE the tf32 split: 128 contiguous bytes.  For FC_H1 the
+// centre-point row is shared by the 8 consecutive rows of a point: each of those 8 lanes fetches one 16-byte chunk of it
+// (`u`) and the chunks are exchanged by shuffle at store time.
 template <int PROD>
-__device__ __forceinline__ void load_row(const RowCtx &r, int kb, int ksamp, int lane, float4 (&v)[8], float4 &u0, float4 &u1) {
+__device__ __forceinline__ void load_row(const RowCtx &r, int kb, int sub, float4 (&v)[8], float4 &u) {
     if (!r.valid) return;
     const float *src = (PROD == TC_PROD_PLAIN ? r.src0 : r.src1) + kb * PK;
 #pragma unroll
     for (int q = 0; q < 8; ++q) v[q] = __ldg(reinterpret_cast<const float4 *>(src) + q);
-    if (PROD == TC_PROD_FC_H1 || PROD == TC_PROD_SC2_Y1) {
-        const float4 *c4 = reinterpret_cast<const float4 *>(r.src0 + kb * PK);
-        const int g = lane & (ksamp - 1);
-        if (ksamp == 4) { u0 = __ldg(c4 + 2 * g); u1 = __ldg(c4 + 2 * g + 1); }
-        else if (g < 8) u0 = __ldg(c4 + g);
-    }
+    if (PROD == TC_PROD_FC_H1) u = __ldg(reinterpret_cast<const float4 *>(r.src0 + kb * PK) + sub);
 }
 
-// transform + split + swizzled store of half a 32-block (chunks 4*half .. 4*half+3) into one stage's B tiles
+__device__ __forceinline__ float small_term(const float4 *sW, int ch, const RowCtx &r) {
+    const float4 w = sW[ch];                                   // shared-memory broadcast (all 32 lanes read the same channel)
+    return fmaf(w.z, r.dz, fmaf(w.y, r.dy, w.x * r.dx));
+}
+
+// transform + split + swizzled store of half a 32-block (chunks q0..q0+3) into one stage's B tiles
 template <int PROD>
-__device__ __forceinline__ void store_half(const RowCtx &r, int row, int lane, int ksamp, int half,
-                                           const float4 (&v)[8], const float4 &u0, const float4 &u1, float *Bhi, float *Blo) {
+__device__ __forceinline__ void store_half(const float4 *sW, const RowCtx &r, int kb, int row, int lane, int half,
+                                           const float4 (&v)[8], const float4 &u, float *Bhi, float *Blo) {
+    const int k0 = kb * PK + half * SK;
 #pragma unroll
     for (int qq = 0; qq < 4; ++qq) {
         const int q = half * 4 + qq;
         float x[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
-        if (PROD == TC_PROD_FC_H1 || PROD == TC_PROD_SC2_Y1) {
-            const int gbase = lane & ~(ksamp - 1);
-            const int srcl = gbase + (ksamp == 4 ? (q >> 1) : q);
-            float uu[4];
-            // all 32 lanes execute the shuffles (invalid rows carry stale/zero values that are discarded); ksamp is kernel-uniform
-            if (ksamp == 4 && (q & 1)) {
-                uu[0] = __shfl_sync(0xffffffffu, u1.x, srcl); uu[1] = __shfl_sync(0xffffffffu, u1.y, srcl);
-                uu[2] = __shfl_sync(0xffffffffu, u1.z, srcl); uu[3] = __shfl_sync(0xffffffffu, u1.w, srcl);
-            } else {
-                uu[0] = __shfl_sync(0xffffffffu, u0.x, srcl); uu[1] = __shfl_sync(0xffffffffu, u0.y, srcl);
-                uu[2] = __shfl_sync(0xffffffffu, u0.z, srcl); uu[3] = __shfl_sync(0xffffffffu, u0.w, srcl);
-            }
+        if (PROD == TC_PROD_FC_H1) {
+            const int srcl = (lane & ~7) + q;                     // the lane of this point's group that holds chunk q of the centre row
+            const float uu[4] = {__shfl_sync(0xffffffffu, u.x, srcl), __shfl_sync(0xffffffffu, u.y, srcl),
+                                 __shfl_sync(0xffffffffu, u.z, srcl), __shfl_sync(0xffffffffu, u.w, srcl)};
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                x[e] = (PROD == TC_PROD_FC_H1) ? act_apply(uu[e] + x[e], 2) : fmaxf(x[e] - uu[e], 0.f);
+            for (int e = 0; e < 4; ++e) x[e] = act_apply(uu[e] + x[e] + small_term(sW, k0 + qq * 4 + e, r), 2);
+        } else if (PROD == TC_PROD_SC2_Y1) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e] + small_term(sW, k0 + qq * 4 + e, r), 0.f);
         }
         if (!r.valid) { x[0] = x[1] = x[2] = x[3] = 0.f; }
         float4 h, l;
@@ -202,6 +201,9 @@ tc_gemm_kernel(const TcArgs a) {
     auto tfull_bar = [&](int s) { return bar0 + 64 + 8 * s; };
     auto tempty_bar = [&](int s) { return bar0 + 80 + 8 * s; };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + NSTAGE * STAGE_BYTES + 128);
+    float4 *sW = reinterpret_cast<float4 *>(smem + NSTAGE * STAGE_BYTES + 256);
+    if (PROD == TC_PROD_FC_H1 || PROD == TC_PROD_SC2_Y1)
+        for (int i = threadIdx.x; i < a.k_blocks * PK; i += NTHREADS) sW[i] = __ldg(reinterpret_cast<const float4 *>(a.Wsmall) + i);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long col_tiles = (a.cols + BN - 1) / BN;
@@ -300,11 +302,6 @@ tc_gemm_kernel(const TcArgs a) {
                 pair = c0 / a.cols_per_pair; pair_end = (pair + 1) * (long long)a.cols_per_pair;
                 if (m_ok) pb = __ldg(a.pbias + (size_t)pair * a.pb_ld + m);
             }
-            float wx = 0.f, wy = 0.f, wz = 0.f;                   // xyz epilogue weights of this thread's channel
-            if (a.xyz_epi && m_ok) {
-                const float4 w4 = __ldg(reinterpret_cast<const float4 *>(a.Wxyz + (size_t)m * 4));
-                wx = a.xsign * w4.x; wy = a.xsign * w4.y; wz = a.xsign * w4.z;
-            }
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
 #pragma unroll 1
@@ -336,15 +333,7 @@ tc_gemm_kernel(const TcArgs a) {
                             ++pair; pair_end += a.cols_per_pair;
                             if (m_ok && c < a.cols) pb = __ldg(a.pbias + (size_t)pair * a.pb_ld + m);
                         }
-                        if (c < a.cols && m_ok) {
-                            float v = __uint_as_float(r[e]) + bias + pb;
-                            if (a.xyz_epi) {                                  // exact-fp32 W.xyz of the column's point (warp-uniform loads)
-                                const long long bb = c / a.xyz_n;
-                                const float *pp = a.xyz_epi + (size_t)bb * 3 * a.xyz_n + (c - bb * a.xyz_n);
-                                v += fmaf(wz, __ldg(pp + 2 * a.xyz_n), fmaf(wy, __ldg(pp + a.xyz_n), wx * __ldg(pp)));
-                            }
-                            a.Out[(size_t)c * a.ldo + m] = act_apply(v, a.act);
-                        }
+                        if (c < a.cols && m_ok) a.Out[(size_t)c * a.ldo + m] = act_apply(__uint_as_float(r[e]) + bias + pb, a.act);
                     }
                 } else if (a.epi == TC_EPI_MAXK) {
                     // relu(acc + bias) then max over each group of `ksamp` consecutive rows (one point's neighbours); ksamp | 32
@@ -367,22 +356,20 @@ tc_gemm_kernel(const TcArgs a) {
         if (t < ntiles) {
             RowCtx rc = make_row(a, (t / a.m_blocks) * BN + row);
             float4 v[8], vn[8];
-            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 u0 = z4, u1 = z4, un0 = z4, un1 = z4;
-            const int ksamp = (PROD == TC_PROD_PLAIN) ? 1 : a.ksamp;
-            load_row<PROD>(rc, 0, ksamp, lane, v, u0, u1);
+            float4 u = make_float4(0.f, 0.f, 0.f, 0.f), un = u;
+            load_row<PROD>(rc, 0, lane & 7, v, u);
             while (true) {
                 RowCtx rcn = rc;
                 const long long tn = t + gridDim.x;
                 for (int kb = 0; kb < a.k_blocks; ++kb) {
                     // prefetch the next 32-block's row slice (or the NEXT TILE's row context + first slice) while we wait for the stages
-                    if (kb + 1 < a.k_blocks) load_row<PROD>(rc, kb + 1, ksamp, lane, vn, un0, un1);
-                    else if (tn < ntiles) { rcn = make_row(a, (tn / a.m_blocks) * BN + row); load_row<PROD>(rcn, 0, ksamp, lane, vn, un0, un1); }
+                    if (kb + 1 < a.k_blocks) load_row<PROD>(rc, kb + 1, lane & 7, vn, un);
+                    else if (tn < ntiles) { rcn = make_row(a, (tn / a.m_blocks) * BN + row); load_row<PROD>(rcn, 0, lane & 7, vn, un); }
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         mbar_wait(empty_bar(stage), phase ^ 1);
                         float *Bhi = reinterpret_cast<float *>(smem + stage * STAGE_BYTES + 2 * TILE_A_FLOATS * 4);
-                        store_half<PROD>(rc, row, lane, ksamp, half, v, u0, u1, Bhi, Bhi + TILE_B_FLOATS);
+                        store_half<PROD>(sW, rc, kb, row, lane, half, v, u, Bhi, Bhi + TILE_B_FLOATS);
                         fence_async_smem();                                   // generic-proxy writes -> visible to the tensor core (async proxy)
                         __syncwarp();
                         if (lane == 0) mbar_arrive(full_bar(stage));
@@ -390,7 +377,7 @@ tc_gemm_kernel(const TcArgs a) {
                     }
 #pragma unroll
                     for (int qq = 0; qq < 8; ++qq) v[qq] = vn[qq];
-                    u0 = un0; u1 = un1;
+                    u = un;
                 }
                 if (tn >= ntiles) break;
                 t = tn; rc = rcn;
@@ -458,10 +445,7 @@ int cmf_launch_tc_gemm(const TcArgs &a, cudaStream_t st) {
     if (a.cols <= 0 || a.m_blocks <= 0) return CMF_OK;
     if (a.out_tiled && ((a.M & 127) || a.epi != TC_EPI_STORE)) { cmf_set_error("tc_gemm: tiled output needs M % 128 == 0 and the STORE epilogue"); return CMF_ERR_INVALID; }
     if (a.epi == TC_EPI_MAXK && a.ksamp != 4 && a.ksamp != 8 && a.ksamp != 16 && a.ksamp != 32) { cmf_set_error("tc_gemm: MAXK needs ksamp in {4,8,16,32}"); return CMF_ERR_INVALID; }
-    if ((a.prod == TC_PROD_FC_H1 || a.prod == TC_PROD_SC2_Y1) && a.ksamp != 4 && a.ksamp != 8 && a.ksamp != 16 && a.ksamp != 32) {
-        cmf_set_error("tc_gemm: gather producers need ksamp in {4,8,16,32}"); return CMF_ERR_INVALID;
-    }
-    if (a.xyz_epi && (a.epi != TC_EPI_STORE || a.out_tiled)) { cmf_set_error("tc_gemm: the xyz epilogue is only available with the row-major STORE epilogue"); return CMF_ERR_INVALID; }
+    if (a.prod == TC_PROD_FC_H1 && a.ksamp != 8) { cmf_set_error("tc_gemm: the flow-embedding producer assumes 8 neighbours per point"); return CMF_ERR_INVALID; }
     const long long ntiles = ((a.cols + BN - 1) / BN) * a.m_blocks;
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
     if (a.prod == TC_PROD_PLAIN) tc_gemm_kernel<TC_PROD_PLAIN><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);

@@ -15,16 +15,15 @@ struct TcArgs {
     // B operand producer
     int prod;
     const float *X; int ldx;                                     // PLAIN: row c = X + c*ldx
-    const float *U1, *U2;                                        // FC_H1: leaky(U1x[i] + U2x[j]);  SC2_Y1: relu(Px[j] - Qx[i]) with U2 = Px, U1 = Qx
-    const int *nbr;                                              // neighbour table
-    int n_pts, ksamp, nbr_ld, nbr_off, ld_u1, off_u1, ld_u2, off_u2;   // points per cloud, neighbours per point, table row stride/offset, centre / gathered row stride+offset
+    const float *U1, *U2, *Wsmall;                               // FC_H1: leaky(U1[i]+U2[j]+Wd.dir); SC2_Y1: relu(P[j]+Wx.rel) with U2=P, Wsmall=Wx/Wd (C x 4)
+    const float *xyz_q, *xyz_c; const int *nbr;                  // planar (B,3,N) clouds of the query / candidate points, neighbour table
+    int n_pts, ksamp, nbr_ld, nbr_off, ld_u2, off_u2;            // points per cloud, neighbours per point, table row stride/offset, gathered-row stride/offset
     const float *Xt;                                             // TILED: activations already split + swizzled by a previous tc GEMM (out_tiled)
     // epilogue
     int epi;
     int out_tiled;                                               // STORE only: write [col_tile][k_block]{hi,lo} 256x32 swizzled tiles instead of rows
     float *Out; int ldo;
     const float *bias, *pbias; int pb_ld, cols_per_pair, act;
-    const float *xyz_epi, *Wxyz; float xsign; int xyz_n;         // STORE: Out[c][m] += xsign * Wxyz[m][0..2] . xyz(point c)  (planar (B,3,xyz_n), exact fp32)
 };
 
 size_t cmf_tc_tiled_floats(int M, int K);
