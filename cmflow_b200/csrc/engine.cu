@@ -327,19 +327,19 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
     { const GemmArgs ga_ = mk(S(FC_WCG), 256, w.G1, 256, w.PB1, 512, S(FC_B1), 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     { const GemmArgs ga_ = mk(S(FC_WNG), 256, w.G2, 256, w.PB2, 512, nullptr, 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     if (m->tc) {
-        { const TcArgs ta_ = tc_plain(m->t_fc_wc, 512, 256, w.E, E_LD, w.U1, 512, nullptr, bn, CMF_ACT_NONE, w.PB1, 512, n); RUN(C_GEMM_FC_HOIST, tflops(ta_, 256), cmf_launch_tc_gemm(ta_, st)); }
-        { const TcArgs ta_ = tc_plain(m->t_fc_wn, 512, 256, w.F2, 256, w.U2, 512, nullptr, bn, CMF_ACT_NONE, w.PB2, 512, n); RUN(C_GEMM_FC_HOIST, tflops(ta_, 256), cmf_launch_tc_gemm(ta_, st)); }
+        { const TcArgs ta_ = tc_plain(m->t_fc_wc, 512, 256, w.E, E_LD, w.U1, 512, nullptr, bn, CMF_ACT_NONE, w.PB1, 512, n); RUN(C_GEMM_FC_HOIST, tflops(ta_, 256), cmf_launch_tc_auto(ta_, st)); }
+        { const TcArgs ta_ = tc_plain(m->t_fc_wn, 512, 256, w.F2, 256, w.U2, 512, nullptr, bn, CMF_ACT_NONE, w.PB2, 512, n); RUN(C_GEMM_FC_HOIST, tflops(ta_, 256), cmf_launch_tc_auto(ta_, st)); }
         {   // conv1 with the gather + hoisted conv0 epilogue fused into the B-operand producer (no H1 round trip)
             TcArgs ta_ = tc_plain(m->t_fc_w2, 512, 512, nullptr, 0, w.H2, 512, S(FC_B2), bn * 8, CMF_ACT_LEAKY);
             ta_.prod = TC_PROD_FC_H1; ta_.U1 = w.U1; ta_.U2 = w.U2; ta_.ld_u2 = 512; ta_.off_u2 = 0; ta_.Wsmall = S(FC_WD);
             ta_.xyz_q = pc1; ta_.xyz_c = pc2; ta_.nbr = w.KNN12; ta_.nbr_ld = 8; ta_.nbr_off = 0; ta_.ksamp = 8; ta_.n_pts = n;
             ta_.out_tiled = 1;                 // conv2's B operand is written TF32-split + swizzled, ready for a bulk copy
-            RUN(C_GEMM_FC_MLP, tflops(ta_, 512), cmf_launch_tc_gemm(ta_, st));
+            RUN(C_GEMM_FC_MLP, tflops(ta_, 512), cmf_launch_tc_auto(ta_, st));
         }
         {
             TcArgs ta_ = tc_plain(m->t_fc_w3, 512, 512, nullptr, 0, w.H1, 512, S(FC_B3), bn * 8, CMF_ACT_LEAKY);
             ta_.prod = TC_PROD_TILED; ta_.Xt = w.H2;
-            RUN(C_GEMM_FC_MLP, tflops(ta_, 512), cmf_launch_tc_gemm(ta_, st));
+            RUN(C_GEMM_FC_MLP, tflops(ta_, 512), cmf_launch_tc_auto(ta_, st));
         }
     } else {
     { const GemmArgs ga_ = mk(S(FC_WC), 256, w.E, E_LD, w.U1, 512, nullptr, 512, 256, bn, CMF_ACT_NONE, w.PB1, 512, n); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
@@ -357,7 +357,7 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
     { const GemmArgs ga_ = mk(S(M2_WG), 256, w.G1, 256, w.PBM, 2048, S(M2_T1), 2048, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_SC2_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     if (m->tc) {
         const TcArgs ta_ = tc_plain(m->t_m2_wp, 2048, E_LD, w.E, E_LD, w.P, 2048, nullptr, bn, CMF_ACT_NONE, w.PBM, 2048, n);
-        RUN(C_GEMM_SC2_HOIST, tflops(ta_, 771), cmf_launch_tc_gemm(ta_, st));
+        RUN(C_GEMM_SC2_HOIST, tflops(ta_, 771), cmf_launch_tc_auto(ta_, st));
     } else {
         const GemmArgs ga_ = mk(S(M2_WP), E_LD, w.E, E_LD, w.P, 2048, nullptr, 2048, E_LD, bn, CMF_ACT_NONE, w.PBM, 2048, n);
         RUN(C_GEMM_SC2_HOIST, 2.0 * 2048 * 771.0 * bn, cmf_launch_gemm1(ga_, st));
@@ -371,13 +371,13 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
                 ta_.Wsmall = S(M2_WX) + (size_t)s * 512 * 4; ta_.xyz_q = pc1; ta_.xyz_c = pc1; ta_.nbr = w.BQ1; ta_.nbr_ld = 60;
                 ta_.nbr_off = KOFF[s]; ta_.ksamp = KS[s]; ta_.n_pts = n;
                 ta_.out_tiled = 1;
-                RUN(C_GEMM_SC2_L2, tflops(ta_, 512), cmf_launch_tc_gemm(ta_, st));
+                RUN(C_GEMM_SC2_L2, tflops(ta_, 512), cmf_launch_tc_auto(ta_, st));
             }
             {   // layer 3 (256->64) with ReLU + max over the K neighbours fused into the TMEM epilogue; B operand bulk-copied
                 TcArgs ta_ = tc_plain(m->t_m2_w3[s], 64, 256, nullptr, 0, w.M64 + s * 64, 256, S(sb + 3), bn * KS[s], CMF_ACT_RELU);
                 ta_.prod = TC_PROD_TILED; ta_.Xt = w.Y2;
                 ta_.epi = TC_EPI_MAXK; ta_.ksamp = KS[s];
-                RUN(C_GEMM_SC2_L3, tflops(ta_, 256), cmf_launch_tc_gemm(ta_, st));
+                RUN(C_GEMM_SC2_L3, tflops(ta_, 256), cmf_launch_tc_auto(ta_, st));
             }
         } else {
         RUN(C_GATHER, 0, cmf_launch_mse2_build_y1(bc, n, KS[s], KOFF[s], pc1, w.BQ1, w.P, 2048, s * 512, S(M2_WX) + (size_t)s * 512 * 4, w.Y1, st));
@@ -412,7 +412,7 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
     { const GemmArgs ga_ = mk(S(HD_W1G), 256, gvec, 256, w.PBH, 512, S(HD_T1), 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_POINTWISE, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     if (m->tc) {
         const TcArgs ta_ = tc_plain(m->t_hd_w1, 512, 256, w.PROP, 256, w.HD1, 512, nullptr, bn, CMF_ACT_RELU, w.PBH, 512, n);
-        RUN(C_GEMM_POINTWISE, tflops(ta_, 256), cmf_launch_tc_gemm(ta_, st));
+        RUN(C_GEMM_POINTWISE, tflops(ta_, 256), cmf_launch_tc_auto(ta_, st));
     } else {
         const GemmArgs ga_ = mk(S(HD_W1), 256, w.PROP, 256, w.HD1, 512, nullptr, 512, 256, bn, CMF_ACT_RELU, w.PBH, 512, n);
         RUN(C_GEMM_POINTWISE, gflops(ga_), cmf_launch_gemm1(ga_, st));

@@ -1,0 +1,229 @@
+// tc_dev.cuh -- device helpers shared by the tcgen05 GEMM kernels (tc_gemm.cu: one CTA per tile; tc_gemm2.cu: CTA pairs).
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace tcdev {
+
+constexpr int BM = 128, BN = 256, SK = 16, PK = 32;
+constexpr unsigned SPIN_LIMIT = 1u << 24;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+                 "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    unsigned spins = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && ++spins > SPIN_LIMIT) __trap();        // never hang the GPU: fail the launch instead
+    }
+}
+// same, acquiring at cluster scope (the arrive came from the peer CTA)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    unsigned spins = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && ++spins > SPIN_LIMIT) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// hi = round-to-nearest TF32 (low 13 mantissa bits zero), lo = x - hi (exact)
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    lo = x - hi;
+}
+
+// Float offset of element (row, kk) inside a K-major [rows x 16] tile with the 64-byte swizzle:
+// rows are 64 bytes, the 16-byte chunk index (2 bits) is XORed with address bits [7,9) = (row >> 1) & 3.
+__host__ __device__ __forceinline__ int sw_off(int row, int kk) { return row * SK + ((((kk >> 2) ^ ((row >> 1) & 3))) << 2) + (kk & 3); }
+
+// K-major, 64B-swizzled operand tile (tile base 1024-aligned): 8-row groups are 512 bytes apart.
+//   bits [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (=32) | [46,48) version=1 | [61,64) layout=4 (SWIZZLE_64B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+// kind::tf32, fp32 accumulate, A and B K-major:
+//   c_format[4,6)=1 (F32) | a_format[7,10)=2 (TF32) | b_format[10,13)=2 | n_dim[17,23)=N>>3 | m_dim[24,29)=M>>4
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return v > 0.f ? v : 0.1f * v;
+    return v;
+}
+
+template <int KSAMP>
+__device__ __forceinline__ void maxk_groups(const uint32_t (&r)[32], float bias, long long cbase, int m, bool m_ok, const TcArgs &a) {
+#pragma unroll
+    for (int g0 = 0; g0 < 32; g0 += KSAMP) {
+        float mx = 0.f;                                            // relu output >= 0
+#pragma unroll
+        for (int e = 0; e < KSAMP; ++e) mx = fmaxf(mx, __uint_as_float(r[g0 + e]) + bias);
+        const long long c = cbase + g0;
+        if (c < a.cols && m_ok) a.Out[(size_t)(c / KSAMP) * a.ldo + m] = mx;
+    }
+}
+
+struct RowCtx {          // per-producer-thread description of its activation row for the current tile
+    bool valid;
+    const float *src0, *src1;      // PLAIN: src0 ; FC_H1: src0 = U1 row (centre point), src1 = U2 row (neighbour) ; SC2_Y1: src1 = P row
+    float dx, dy, dz;
+};
+
+__device__ __forceinline__ RowCtx make_row(const TcArgs &a, long long c) {
+    RowCtx r;
+    r.valid = c < a.cols;
+    r.src0 = r.src1 = nullptr; r.dx = r.dy = r.dz = 0.f;
+    if (!r.valid) return r;
+    if (a.prod == TC_PROD_PLAIN) { r.src0 = a.X + (size_t)c * a.ldx; return r; }
+    const long long bi = c / a.ksamp;
+    const int kk = (int)(c - bi * a.ksamp);
+    const int b = (int)(bi / a.n_pts), i = (int)(bi - (long long)b * a.n_pts);
+    const int j = __ldg(a.nbr + (size_t)bi * a.nbr_ld + a.nbr_off + kk);
+    const float *pq = a.xyz_q + (size_t)b * 3 * a.n_pts, *pc = a.xyz_c + (size_t)b * 3 * a.n_pts;
+    r.dx = __fsub_rn(__ldg(pc + j), __ldg(pq + i));
+    r.dy = __fsub_rn(__ldg(pc + a.n_pts + j), __ldg(pq + a.n_pts + i));
+    r.dz = __fsub_rn(__ldg(pc + 2 * a.n_pts + j), __ldg(pq + 2 * a.n_pts + i));
+    r.src0 = a.U1 ? a.U1 + (size_t)bi * 512 : nullptr;
+    r.src1 = a.U2 + ((size_t)b * a.n_pts + j) * a.ld_u2 + a.off_u2;
+    return r;
+}
+
+// One 32-float block of this thread's (gathered) row, BEFORE the tf32 split: 128 contiguous bytes.  For FC_H1 the
+// centre-point row is shared by the 8 consecutive rows of a point: each of those 8 lanes fetches one 16-byte chunk of it
+// (`u`) and the chunks are exchanged by shuffle at store time.
+template <int PROD>
+__device__ __forceinline__ void load_row(const RowCtx &r, int kb, int sub, float4 (&v)[8], float4 &u) {
+    if (!r.valid) return;
+    const float *src = (PROD == TC_PROD_PLAIN ? r.src0 : r.src1) + kb * PK;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = __ldg(reinterpret_cast<const float4 *>(src) + q);
+    if (PROD == TC_PROD_FC_H1) u = __ldg(reinterpret_cast<const float4 *>(r.src0 + kb * PK) + sub);
+}
+
+__device__ __forceinline__ float small_term(const float4 *sW, int ch, const RowCtx &r) {
+    const float4 w = sW[ch];                                   // shared-memory broadcast (all 32 lanes read the same channel)
+    return fmaf(w.z, r.dz, fmaf(w.y, r.dy, w.x * r.dx));
+}
+
+// transform + split + swizzled store of half a 32-block (chunks 4*half .. 4*half+3) into one stage's B tiles
+template <int PROD>
+__device__ __forceinline__ void store_half(const float4 *sW, const RowCtx &r, int kb, int row, int lane, int half,
+                                           const float4 (&v)[8], const float4 &u, float *Bhi, float *Blo) {
+    const int k0 = kb * PK + half * SK;
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+        const int q = half * 4 + qq;
+        float x[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+        if (PROD == TC_PROD_FC_H1) {
+            const int srcl = (lane & ~7) + q;                     // the lane of this point's group that holds chunk q of the centre row
+            const float uu[4] = {__shfl_sync(0xffffffffu, u.x, srcl), __shfl_sync(0xffffffffu, u.y, srcl),
+                                 __shfl_sync(0xffffffffu, u.z, srcl), __shfl_sync(0xffffffffu, u.w, srcl)};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = act_apply(uu[e] + x[e] + small_term(sW, k0 + qq * 4 + e, r), 2);
+        } else if (PROD == TC_PROD_SC2_Y1) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e] + small_term(sW, k0 + qq * 4 + e, r), 0.f);
+        }
+        if (!r.valid) { x[0] = x[1] = x[2] = x[3] = 0.f; }
+        float4 h, l;
+        split_tf32(x[0], h.x, l.x); split_tf32(x[1], h.y, l.y); split_tf32(x[2], h.z, l.z); split_tf32(x[3], h.w, l.w);
+        const int off = sw_off(row, qq * 4);
+        *reinterpret_cast<float4 *>(Bhi + off) = h;
+        *reinterpret_cast<float4 *>(Blo + off) = l;
+    }
+}
+
+// One epilogue pass over 32 accumulator columns held in r[] (this thread = output channel m): bias / per-pair bias / activation and
+// either a row-major store, a tiled (TF32-split, swizzled) store for the next GEMM, or the max over each point's ksamp neighbours.
+struct EpiState { long long pair, pair_end; float pb; };
+
+__device__ __forceinline__ void epilogue_chunk(const TcArgs &a, const uint32_t (&r)[32], long long ct, long long c0, int cc, int m, bool m_ok,
+                                               float bias, EpiState &es, int tile_b_floats) {
+    if (a.epi == TC_EPI_STORE && a.out_tiled) {
+        float *tb = a.Out + ((size_t)ct * (a.M >> 4) + (m >> 4)) * (2 * (size_t)tile_b_floats);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            const long long c = c0 + cc + e;
+            if (c >= es.pair_end) {
+                ++es.pair; es.pair_end += a.cols_per_pair;
+                if (c < a.cols) es.pb = __ldg(a.pbias + (size_t)es.pair * a.pb_ld + m);
+            }
+            const float v = c < a.cols ? act_apply(__uint_as_float(r[e]) + bias + es.pb, a.act) : 0.f;
+            float hi, lo;
+            split_tf32(v, hi, lo);
+            const int off = sw_off(cc + e, m & 15);
+            tb[off] = hi;
+            tb[tile_b_floats + off] = lo;
+        }
+    } else if (a.epi == TC_EPI_STORE) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            const long long c = c0 + cc + e;
+            if (c >= es.pair_end) {                                  // warp-uniform: crossed into the next frame pair
+                ++es.pair; es.pair_end += a.cols_per_pair;
+                if (m_ok && c < a.cols) es.pb = __ldg(a.pbias + (size_t)es.pair * a.pb_ld + m);
+            }
+            if (c < a.cols && m_ok) a.Out[(size_t)c * a.ldo + m] = act_apply(__uint_as_float(r[e]) + bias + es.pb, a.act);
+        }
+    } else if (a.epi == TC_EPI_MAXK) {
+        if (a.ksamp == 4) maxk_groups<4>(r, bias, c0 + cc, m, m_ok, a);
+        else if (a.ksamp == 8) maxk_groups<8>(r, bias, c0 + cc, m, m_ok, a);
+        else if (a.ksamp == 16) maxk_groups<16>(r, bias, c0 + cc, m, m_ok, a);
+        else maxk_groups<32>(r, bias, c0 + cc, m, m_ok, a);
+    }
+}
+
+__device__ __forceinline__ EpiState epi_begin(const TcArgs &a, long long c0, int m, bool m_ok) {
+    EpiState es{0, 0x7fffffffffffffffLL, 0.f};
+    if (a.pbias) {
+        es.pair = c0 / a.cols_per_pair; es.pair_end = (es.pair + 1) * (long long)a.cols_per_pair;
+        if (m_ok) es.pb = __ldg(a.pbias + (size_t)es.pair * a.pb_ld + m);
+    }
+    return es;
+}
+
+}  // namespace tcdev

@@ -14,6 +14,8 @@
 // * Warp roles (512 threads): w0 bulk-copy issuer, w1 MMA issuer (one elected lane), w2 TMEM allocator,
 //   w4-7 epilogue (TMEM lane quarter = warp%4), w8-15 B producers.  4-stage smem ring (4 x 48 KB), 2 TMEM accumulator
 //   stages (2 x 256 columns) so the epilogue of tile t overlaps the MMAs of tile t+1.  Persistent over tiles.
+#include <stdlib.h>
+
 #include "tc_gemm.cuh"
 
 namespace {
@@ -456,6 +458,13 @@ int cmf_launch_tc_gemm(const TcArgs &a, cudaStream_t st) {
     return CMF_OK;
 }
 
+int cmf_launch_tc_auto(const TcArgs &a, cudaStream_t st) {
+    static int use2 = -1;
+    if (use2 < 0) { const char *e = getenv("CMF_TC2"); use2 = (e && e[0] == '0') ? 0 : 1; }
+    if (use2 && (a.M & 255) == 0 && (a.m_blocks & 1) == 0) return cmf_launch_tc_gemm2(a, st);
+    return cmf_launch_tc_gemm(a, st);
+}
+
 // ---- test doorway: plain 3xTF32 GEMM through the C ABI (tests/test_gpu_tc_gemm.py) --------------------------------
 extern "C" int cmf_test_tc_gemm(int M, int K, long long cols, const float *W, int ldw, const float *X, int ldx,
                                 const float *bias, int act, float *Out, int ldo, float *scratch_tiles, void *stream) {
@@ -468,6 +477,6 @@ extern "C" int cmf_test_tc_gemm(int M, int K, long long cols, const float *W, in
     a.Wt = scratch_tiles; a.m_blocks = cmf_divup(M, BM); a.k_blocks = cmf_divup(K, PK); a.M = M; a.cols = cols;
     a.prod = TC_PROD_PLAIN; a.X = X; a.ldx = ldx;
     a.epi = TC_EPI_STORE; a.Out = Out; a.ldo = ldo; a.bias = bias; a.pbias = nullptr; a.act = act; a.cols_per_pair = 1;
-    return cmf_launch_tc_gemm(a, st);
+    return cmf_launch_tc_auto(a, st);
 }
 extern "C" size_t cmf_test_tc_tiled_floats(int M, int K) { return cmf_tc_tiled_floats(M, K); }

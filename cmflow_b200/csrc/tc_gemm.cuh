@@ -29,4 +29,6 @@ struct TcArgs {
 size_t cmf_tc_tiled_floats(int M, int K);
 size_t cmf_tc_act_tiled_floats(long long cols, int C);                          // floats of a tiled activation buffer (cols x C channels)                                        // floats needed for the pre-tiled copy of an M x K matrix
 int cmf_tc_tile_weights(const float *W, int ldw, int M, int K, float *Wt, cudaStream_t st);
-int cmf_launch_tc_gemm(const TcArgs &a, cudaStream_t st);
+int cmf_launch_tc_gemm(const TcArgs &a, cudaStream_t st);      // one CTA per 128 x 256 tile
+int cmf_launch_tc_gemm2(const TcArgs &a, cudaStream_t st);     // CTA pair (cta_group::2) per 256 x 256 tile; needs M % 256 == 0
+int cmf_launch_tc_auto(const TcArgs &a, cudaStream_t st);      // pair kernel when M % 256 == 0 (unless CMF_TC2=0), else the one-CTA kernel

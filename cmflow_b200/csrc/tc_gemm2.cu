@@ -1,0 +1,264 @@
+// tc_gemm2.cu -- CTA-PAIR (cta_group::2) variant of the tcgen05 3xTF32 GEMM for M % 256 == 0.
+//
+// Why: in the one-CTA kernel (tc_gemm.cu) every tcgen05.mma re-reads its A (4 KB) and B (8 KB) operand slices from shared
+// memory, the three split-precision MMAs of a K=8 step triple that, and the producers' swizzled stores, the bulk copies and
+// the gathers share the same 128 B/clk L1/shared-memory data path: ~2500 clk of that path per 32-deep K block against
+// 1536 clk of tensor-pipe time -- the kernel is shared-memory-bandwidth bound.  A CTA pair computes a 256(M) x 256(N) tile with
+// ONE instruction stream (tcgen05.mma.cta_group::2, M=256): each CTA holds its own 128 weight rows and only HALF of the
+// activation rows (128), the hardware feeds both tensor cores from both halves.  Per CTA that is 4+4 KB instead of 4+8 KB per MMA,
+// half the producer stores / gathers per MAC, and -- for M = 256 layers -- every activation row is produced exactly once.
+//
+// Cluster of 2 CTAs, 384 threads each: w0 bulk-copy issuer, w1 MMA issuer (leader CTA only), w2 TMEM allocator,
+// w3 forwarder (peer CTA only: relays "my half of stage s is full" to the leader), w4-7 epilogue (own 128 accumulator rows),
+// w8-11 producers (thread per activation row, 128 rows per CTA).  6-stage ring of 32 KB stages (K = 16 per stage).
+// Protocol (barriers at identical offsets in both CTAs):
+//   full_local[s]  : local  -- bulk copy expect_tx + 4 producer warps                      (count 1 + 4, or 1 when B is bulk-copied)
+//   peer_full[s]   : leader -- remote arrive by the peer's forwarder                        (count 1)
+//   empty[s]       : both   -- tcgen05.commit.cta_group::2 multicast from the leader        (count 1)
+//   tfull[a]       : both   -- commit multicast after the last K stage of a tile            (count 1)
+//   tempty[a]      : leader -- 4 local + 4 remote epilogue warps                            (count 8)
+#include "tc_dev.cuh"
+
+using namespace tcdev;
+
+namespace {
+
+constexpr int HALF_N = 128;                          // activation rows held by each CTA
+constexpr int TILE_A_FLOATS = BM * SK;               // 2048 floats = 8 KB
+constexpr int TILE_BH_FLOATS = HALF_N * SK;          // 2048 floats = 8 KB (local half of B)
+constexpr int TILE_B_FLOATS = BN * SK;               // 4096 floats: the 256-row tile of the tiled activation FORMAT in global memory
+constexpr int STAGE_BYTES = (2 * TILE_A_FLOATS + 2 * TILE_BH_FLOATS) * 4;   // 32 KB
+constexpr int NSTAGE = 6;
+constexpr int NTHREADS = 384;
+constexpr int SMALL_BYTES = 512 * 16;
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 + 256 + SMALL_BYTES;
+constexpr uint32_t IDESC2 = make_idesc(256, BN);
+
+__device__ __forceinline__ void tc_commit2_mc(uint32_t bar) {      // arrive on `bar` in BOTH CTAs when all prior MMAs of this thread retire
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_mma2_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <int PROD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+tc_gemm2_kernel(const TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *smem = smem_raw + (base - raw);
+    const uint32_t bar0 = base + NSTAGE * STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar0 + 8 * s; };
+    auto pfull_bar = [&](int s) { return bar0 + 48 + 8 * s; };
+    auto empty_bar = [&](int s) { return bar0 + 96 + 8 * s; };
+    auto tfull_bar = [&](int s) { return bar0 + 144 + 8 * s; };
+    auto tempty_bar = [&](int s) { return bar0 + 160 + 8 * s; };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + NSTAGE * STAGE_BYTES + 192);
+    float4 *sW = reinterpret_cast<float4 *>(smem + NSTAGE * STAGE_BYTES + 256);
+    if (PROD == TC_PROD_FC_H1 || PROD == TC_PROD_SC2_Y1)
+        for (int i = threadIdx.x; i < a.k_blocks * PK; i += NTHREADS) sW[i] = __ldg(reinterpret_cast<const float4 *>(a.Wsmall) + i);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const long long col_tiles = (a.cols + BN - 1) / BN;
+    const int m_pairs = a.m_blocks >> 1;
+    const long long ntiles = col_tiles * m_pairs;
+    const long long cl_id = blockIdx.x >> 1, n_cl = gridDim.x >> 1;
+    const int nks = a.k_blocks * 2;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(full_bar(s), PROD == TC_PROD_TILED ? 1 : 1 + 4);
+            mbar_init(pfull_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    cluster_sync_all();                         // both CTAs: barriers initialised, TMEM allocated, sW visible
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== bulk-copy issuer: this CTA's 128 weight rows (and, when pre-tiled, its half of the activation rows) =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (long long t = cl_id; t < ntiles; t += n_cl) {
+                const int mb = (int)(t % m_pairs) * 2 + (int)rank;
+                const long long ct = t / m_pairs;
+                for (int ks = 0; ks < nks; ++ks) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const float *src = a.Wt + ((size_t)mb * nks + ks) * (2 * TILE_A_FLOATS);
+                    const uint32_t dst = base + stage * STAGE_BYTES;
+                    if (PROD == TC_PROD_TILED) {
+                        const float *bsrc = a.Xt + ((size_t)ct * nks + ks) * (2 * TILE_B_FLOATS) + rank * TILE_BH_FLOATS;
+                        mbar_arrive_expect_tx(full_bar(stage), (2 * TILE_A_FLOATS + 2 * TILE_BH_FLOATS) * 4);
+                        bulk_g2s(dst, src, 2 * TILE_A_FLOATS * 4, full_bar(stage));
+                        bulk_g2s(dst + 2 * TILE_A_FLOATS * 4, bsrc, TILE_BH_FLOATS * 4, full_bar(stage));                                   // hi half
+                        bulk_g2s(dst + 2 * TILE_A_FLOATS * 4 + TILE_BH_FLOATS * 4, bsrc + TILE_B_FLOATS, TILE_BH_FLOATS * 4, full_bar(stage));  // lo half
+                    } else {
+                        mbar_arrive_expect_tx(full_bar(stage), 2 * TILE_A_FLOATS * 4);
+                        bulk_g2s(dst, src, 2 * TILE_A_FLOATS * 4, full_bar(stage));
+                    }
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only): one instruction stream drives both SMs' tensor cores =====
+        if (leader) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (long long t = cl_id; t < ntiles; t += n_cl) {
+                mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int ks = 0; ks < nks; ++ks) {
+                    mbar_wait(full_bar(stage), phase);                 // my half
+                    mbar_wait_cluster(pfull_bar(stage), phase);        // the peer's half (relayed)
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sa = base + stage * STAGE_BYTES;
+                        const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + TILE_A_FLOATS * 4);
+                        const uint64_t b_hi = make_desc(sa + 2 * TILE_A_FLOATS * 4), b_lo = make_desc(sa + 2 * TILE_A_FLOATS * 4 + TILE_BH_FLOATS * 4);
+#pragma unroll
+                        for (int k8 = 0; k8 < SK / 8; ++k8) {
+                            const uint64_t adv = (uint64_t)(k8 * 32 >> 4);
+                            tc_mma2_tf32(d_tmem, a_lo + adv, b_hi + adv, IDESC2, (ks | k8) ? 1u : 0u);
+                            tc_mma2_tf32(d_tmem, a_hi + adv, b_lo + adv, IDESC2, 1u);
+                            tc_mma2_tf32(d_tmem, a_hi + adv, b_hi + adv, IDESC2, 1u);
+                        }
+                        tc_commit2_mc(empty_bar(stage));
+                        if (ks == nks - 1) tc_commit2_mc(tfull_bar(acc));
+                    }
+                    __syncwarp();
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp == 3) {
+        // ===== forwarder (peer CTA only): tell the leader when this CTA's half of a stage is complete =====
+        if (!leader) {
+            int stage = 0; uint32_t phase = 0;
+            for (long long t = cl_id; t < ntiles; t += n_cl)
+                for (int ks = 0; ks < nks; ++ks) {
+                    mbar_wait(full_bar(stage), phase);
+                    if (lane == 0) mbar_arrive_remote(pfull_bar(stage), 0);
+                    __syncwarp();
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===== epilogue: this CTA's 128 accumulator rows x 256 columns =====
+        const int q = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (long long t = cl_id; t < ntiles; t += n_cl) {
+            const int mb = (int)(t % m_pairs) * 2 + (int)rank;
+            const long long ct = t / m_pairs;
+            const long long c0 = ct * BN;
+            const int m = mb * BM + q * 32 + lane;
+            const bool m_ok = m < a.M;
+            const float bias = (a.bias && m_ok) ? __ldg(a.bias + m) : 0.f;
+            EpiState es = epi_begin(a, c0, m, m_ok);
+            mbar_wait_cluster(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < BN; cc += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cc, r);
+                epilogue_chunk(a, r, ct, c0, cc, m, m_ok, bias, es, TILE_B_FLOATS);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote(tempty_bar(acc), 0); }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= 8 && PROD != TC_PROD_TILED) {
+        // ===== producers: thread `row` builds activation row ct*256 + rank*128 + row =====
+        const int row = threadIdx.x - 256;
+        int stage = 0; uint32_t phase = 0;
+        long long t = cl_id;
+        if (t < ntiles) {
+            RowCtx rc = make_row(a, (t / m_pairs) * BN + rank * HALF_N + row);
+            float4 v[8], vn[8];
+            float4 u = make_float4(0.f, 0.f, 0.f, 0.f), un = u;
+            load_row<PROD>(rc, 0, lane & 7, v, u);
+            while (true) {
+                RowCtx rcn = rc;
+                const long long tn = t + n_cl;
+                for (int kb = 0; kb < a.k_blocks; ++kb) {
+                    if (kb + 1 < a.k_blocks) load_row<PROD>(rc, kb + 1, lane & 7, vn, un);
+                    else if (tn < ntiles) { rcn = make_row(a, (tn / m_pairs) * BN + rank * HALF_N + row); load_row<PROD>(rcn, 0, lane & 7, vn, un); }
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        mbar_wait(empty_bar(stage), phase ^ 1);
+                        float *Bhi = reinterpret_cast<float *>(smem + stage * STAGE_BYTES + 2 * TILE_A_FLOATS * 4);
+                        store_half<PROD>(sW, rc, kb, row, lane, half, v, u, Bhi, Bhi + TILE_BH_FLOATS);
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(full_bar(stage));
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    }
+#pragma unroll
+                    for (int qq = 0; qq < 8; ++qq) v[qq] = vn[qq];
+                    u = un;
+                }
+                if (tn >= ntiles) break;
+                t = tn; rc = rcn;
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                         // nobody frees TMEM / exits while the pair still uses it
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+template <int PROD>
+int launch2(const TcArgs &a, int n_clusters, cudaStream_t st) {
+    tc_gemm2_kernel<PROD><<<2 * n_clusters, NTHREADS, SMEM_BYTES, st>>>(a);      // cluster shape comes from __cluster_dims__(2,1,1)
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
+}  // namespace
+
+int cmf_launch_tc_gemm2(const TcArgs &a, cudaStream_t st) {
+    static int num_sms = 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CMF_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<TC_PROD_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CMF_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<TC_PROD_FC_H1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CMF_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<TC_PROD_SC2_Y1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CMF_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<TC_PROD_TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        int dev = 0;
+        CMF_CUDA(cudaGetDevice(&dev));
+        CMF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        attr_set = true;
+    }
+    if (a.cols <= 0 || a.m_blocks <= 0) return CMF_OK;
+    if ((a.m_blocks & 1) || (a.M & 255)) { cmf_set_error("tc_gemm2: needs M %% 256 == 0"); return CMF_ERR_INVALID; }
+    if (a.out_tiled && a.epi != TC_EPI_STORE) { cmf_set_error("tc_gemm2: tiled output needs the STORE epilogue"); return CMF_ERR_INVALID; }
+    if (a.epi == TC_EPI_MAXK && a.ksamp != 4 && a.ksamp != 8 && a.ksamp != 16 && a.ksamp != 32) { cmf_set_error("tc_gemm2: MAXK needs ksamp in {4,8,16,32}"); return CMF_ERR_INVALID; }
+    if (a.prod == TC_PROD_FC_H1 && a.ksamp != 8) { cmf_set_error("tc_gemm2: the flow-embedding producer assumes 8 neighbours per point"); return CMF_ERR_INVALID; }
+    const long long ntiles = ((a.cols + BN - 1) / BN) * (a.m_blocks >> 1);
+    const int max_cl = num_sms / 2;
+    const int n_cl = (int)(ntiles < max_cl ? ntiles : max_cl);
+    if (a.prod == TC_PROD_PLAIN) return launch2<TC_PROD_PLAIN>(a, n_cl, st);
+    if (a.prod == TC_PROD_FC_H1) return launch2<TC_PROD_FC_H1>(a, n_cl, st);
+    if (a.prod == TC_PROD_TILED) return launch2<TC_PROD_TILED>(a, n_cl, st);
+    return launch2<TC_PROD_SC2_Y1>(a, n_cl, st);
+}

@@ -45,10 +45,12 @@ def test_tc_gemm_matches_fp64(M, K, cols):
     assert err < 1e-5, err
 
 
-def test_tc_gemm_identity_layout():
-    """W = I picks X apart element by element: catches any swizzle / descriptor / lane-mapping slip exactly."""
-    K = M = 128
-    X = torch.arange(256 * K, dtype=torch.float32).reshape(256, K) / 64.0     # exactly representable in TF32 hi+lo
+@pytest.mark.parametrize("M,cols", [(128, 256), (256, 256), (256, 700), (512, 1300)])
+def test_tc_gemm_identity_layout(M, cols):
+    """W = I picks X apart element by element: catches any swizzle / descriptor / lane-mapping slip exactly.
+    M = 128 runs the one-CTA kernel, M % 256 == 0 the CTA-pair (cta_group::2) kernel."""
+    K = M
+    X = torch.arange(cols * K, dtype=torch.float32).reshape(cols, K) / 64.0     # exactly representable in TF32 hi+lo
     got = tc_gemm(torch.eye(M), X.to(DEV), None, 0).cpu()
     assert torch.equal(got, X)
 
