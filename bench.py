@@ -106,7 +106,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="frame pairs per GPU per step")
     ap.add_argument("--points", type=int, default=256)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("CMF_BENCH_PRECISION", "fp32"), choices=["fp32", "tf32x3"],
+    ap.add_argument("--precision", default=os.environ.get("CMF_BENCH_PRECISION", "tf32x3"), choices=["fp32", "tf32x3"],
                     help="fp32 = strict fp32 FMA kernels; tf32x3 = tcgen05 tensor cores with 3xTF32 split precision (fp32-class accuracy)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu", action="store_true", help="profiler harness: W+K device forwards only, prints no bench line")
@@ -253,7 +253,7 @@ def main():
         line = {
             "metric": "frame-pairs/sec CMFlow forward", "value": total_pairs * K / (ms_dev / 1e3), "unit": "frame-pairs/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic radar pairs (cmflow_b200/synth.py), seeded random-init weights of the CMFlow architecture",
+            "vs_baseline": None, "dtype": ("f32 (3xTF32 split on tcgen05 tensor cores, fp32 accumulate)" if args.precision == "tf32x3" else "f32"), "data": "synthetic radar pairs (cmflow_b200/synth.py), seeded random-init weights of the CMFlow architecture",
             "config": {"workload": workload, "points": N, "pairs_per_gpu": B, "global_batch": total_pairs, "parallelism": f"dp{world}",
                        "l2": "256 MB flush between timed steps; 4 rotating input batches", "precision_mode": args.precision},
             "e2e": {"value": total_pairs * K / (ms_host / 1e3), "unit": "frame-pairs/s", "ms_per_step": ms_host / K,

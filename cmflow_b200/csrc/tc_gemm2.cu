@@ -8,11 +8,12 @@
 // activation rows (128), the hardware feeds both tensor cores from both halves.  Per CTA that is 4+4 KB instead of 4+8 KB per MMA,
 // half the producer stores / gathers per MAC, and -- for M = 256 layers -- every activation row is produced exactly once.
 //
-// Cluster of 2 CTAs, 384 threads each: w0 bulk-copy issuer, w1 MMA issuer (leader CTA only), w2 TMEM allocator,
+// Cluster of 2 CTAs, 512 threads each: w0 bulk-copy issuer, w1 MMA issuer (leader CTA only), w2 TMEM allocator,
 // w3 forwarder (peer CTA only: relays "my half of stage s is full" to the leader), w4-7 epilogue (own 128 accumulator rows),
-// w8-11 producers (thread per activation row, 128 rows per CTA).  6-stage ring of 32 KB stages (K = 16 per stage).
+// w8-15 producers (TWO threads per activation row, 128 rows per CTA: thread (row, hs) owns the 16-byte chunks 2hs, 2hs+1 of
+// every 16-float stage).  6-stage ring of 32 KB stages (K = 16 per stage).
 // Protocol (barriers at identical offsets in both CTAs):
-//   full_local[s]  : local  -- bulk copy expect_tx + 4 producer warps                      (count 1 + 4, or 1 when B is bulk-copied)
+//   full_local[s]  : local  -- bulk copy expect_tx + 8 producer warps                      (count 1 + 8, or 1 when B is bulk-copied)
 //   peer_full[s]   : leader -- remote arrive by the peer's forwarder                        (count 1)
 //   empty[s]       : both   -- tcgen05.commit.cta_group::2 multicast from the leader        (count 1)
 //   tfull[a]       : both   -- commit multicast after the last K stage of a tile            (count 1)
@@ -29,7 +30,7 @@ constexpr int TILE_BH_FLOATS = HALF_N * SK;          // 2048 floats = 8 KB (loca
 constexpr int TILE_B_FLOATS = BN * SK;               // 4096 floats: the 256-row tile of the tiled activation FORMAT in global memory
 constexpr int STAGE_BYTES = (2 * TILE_A_FLOATS + 2 * TILE_BH_FLOATS) * 4;   // 32 KB
 constexpr int NSTAGE = 6;
-constexpr int NTHREADS = 384;
+constexpr int NTHREADS = 512;
 constexpr int SMALL_BYTES = 512 * 16;
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 + 256 + SMALL_BYTES;
 constexpr uint32_t IDESC2 = make_idesc(256, BN);
@@ -73,7 +74,7 @@ tc_gemm2_kernel(const TcArgs a) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(full_bar(s), PROD == TC_PROD_TILED ? 1 : 1 + 4);
+            mbar_init(full_bar(s), PROD == TC_PROD_TILED ? 1 : 1 + 8);
             mbar_init(pfull_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
@@ -185,33 +186,67 @@ tc_gemm2_kernel(const TcArgs a) {
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 8 && PROD != TC_PROD_TILED) {
-        // ===== producers: thread `row` builds activation row ct*256 + rank*128 + row =====
-        const int row = threadIdx.x - 256;
+        // ===== producers: thread (row, hs) builds chunks {2hs, 2hs+1} of both 16-float stages of every 32-block of row ct*256 + rank*128 + row =====
+        const int p = threadIdx.x - 256;
+        const int row = p & 127, hs = p >> 7;
+        const int g = lane & 7;                                 // position inside the 8-lane group of one point (flow embedding)
         int stage = 0; uint32_t phase = 0;
         long long t = cl_id;
+        // chunk q (0..7 of the 32-block) handled at slot i: i=0,1 -> first stage, i=2,3 -> second stage
+        auto qof = [&](int i) { return (i >> 1) * 4 + 2 * hs + (i & 1); };
+        auto loadp = [&](const RowCtx &r, int kb, float4 (&v)[4], float4 &u) {
+            if (!r.valid) return;
+            const float4 *src = reinterpret_cast<const float4 *>((PROD == TC_PROD_PLAIN ? r.src0 : r.src1) + kb * PK);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = __ldg(src + qof(i));
+            if (PROD == TC_PROD_FC_H1 && g < 4) u = __ldg(reinterpret_cast<const float4 *>(r.src0 + kb * PK) + qof(g));
+        };
         if (t < ntiles) {
             RowCtx rc = make_row(a, (t / m_pairs) * BN + rank * HALF_N + row);
-            float4 v[8], vn[8];
+            float4 v[4], vn[4];
             float4 u = make_float4(0.f, 0.f, 0.f, 0.f), un = u;
-            load_row<PROD>(rc, 0, lane & 7, v, u);
+            loadp(rc, 0, v, u);
             while (true) {
                 RowCtx rcn = rc;
                 const long long tn = t + n_cl;
                 for (int kb = 0; kb < a.k_blocks; ++kb) {
-                    if (kb + 1 < a.k_blocks) load_row<PROD>(rc, kb + 1, lane & 7, vn, un);
-                    else if (tn < ntiles) { rcn = make_row(a, (tn / m_pairs) * BN + rank * HALF_N + row); load_row<PROD>(rcn, 0, lane & 7, vn, un); }
+                    if (kb + 1 < a.k_blocks) loadp(rc, kb + 1, vn, un);
+                    else if (tn < ntiles) { rcn = make_row(a, (tn / m_pairs) * BN + rank * HALF_N + row); loadp(rcn, 0, vn, un); }
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         mbar_wait(empty_bar(stage), phase ^ 1);
                         float *Bhi = reinterpret_cast<float *>(smem + stage * STAGE_BYTES + 2 * TILE_A_FLOATS * 4);
-                        store_half<PROD>(sW, rc, kb, row, lane, half, v, u, Bhi, Bhi + TILE_BH_FLOATS);
+                        float *Blo = Bhi + TILE_BH_FLOATS;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const int i = half * 2 + j;
+                            const int qq = 2 * hs + j;                          // chunk inside the 16-float stage
+                            const int k0 = kb * PK + half * SK + qq * 4;        // first channel of the chunk
+                            float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+                            if (PROD == TC_PROD_FC_H1) {
+                                const int srcl = (lane & ~7) + i;               // lane of this point's group that fetched centre chunk qof(i)
+                                const float uu[4] = {__shfl_sync(0xffffffffu, u.x, srcl), __shfl_sync(0xffffffffu, u.y, srcl),
+                                                     __shfl_sync(0xffffffffu, u.z, srcl), __shfl_sync(0xffffffffu, u.w, srcl)};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) x[e] = act_apply(uu[e] + x[e] + small_term(sW, k0 + e, rc), 2);
+                            } else if (PROD == TC_PROD_SC2_Y1) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e] + small_term(sW, k0 + e, rc), 0.f);
+                            }
+                            if (!rc.valid) { x[0] = x[1] = x[2] = x[3] = 0.f; }
+                            float4 h4, l4;
+                            split_tf32(x[0], h4.x, l4.x); split_tf32(x[1], h4.y, l4.y); split_tf32(x[2], h4.z, l4.z); split_tf32(x[3], h4.w, l4.w);
+                            const int off = sw_off(row, qq * 4);
+                            *reinterpret_cast<float4 *>(Bhi + off) = h4;
+                            *reinterpret_cast<float4 *>(Blo + off) = l4;
+                        }
                         fence_async_smem();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(full_bar(stage));
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                     }
 #pragma unroll
-                    for (int qq = 0; qq < 8; ++qq) v[qq] = vn[qq];
+                    for (int i = 0; i < 4; ++i) v[i] = vn[i];
                     u = un;
                 }
                 if (tn >= ntiles) break;
