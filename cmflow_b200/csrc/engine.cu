@@ -225,8 +225,12 @@ static size_t chunk_bytes(int bc, int n) {
 }
 
 static int ensure_workspace(cmf_model *m, int b, int n) {
-    // chunk size: as many pairs as fit a ~3 GiB arena (override with CMF_CHUNK_PAIRS), at most b
-    size_t budget = (size_t)3 << 30;
+    // chunk size: as many pairs as fit the workspace arena (default 24 GiB of the 180 GB; CMF_WS_GB / CMF_CHUNK_PAIRS override).
+    // Few large chunks amortise the per-launch prologue of the persistent tensor-core kernels (cluster launch, TMEM allocation,
+    // pipeline fill: ~40 us each, ~14 such launches per chunk).
+    size_t budget = (size_t)24 << 30;
+    const char *wsenv = getenv("CMF_WS_GB");
+    if (wsenv && atof(wsenv) > 0) budget = (size_t)(atof(wsenv) * (double)((size_t)1 << 30));
     int bc = b;
     const char *env = getenv("CMF_CHUNK_PAIRS");
     if (env && atoi(env) > 0) bc = atoi(env) < b ? atoi(env) : b;
