@@ -328,6 +328,7 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
     RUN(C_GATHER, 0, cmf_launch_scatter_ft(bc, n, ft1, w.E, E_LD, 768, E_LD - 771, st));
 
     // flow embedding (FeatureCorrelator, radarflow_util.py:185-237)
+    bool fused_wsum = false;
     { const GemmArgs ga_ = mk(S(FC_WCG), 256, w.G1, 256, w.PB1, 512, S(FC_B1), 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     { const GemmArgs ga_ = mk(S(FC_WNG), 256, w.G2, 256, w.PB2, 512, nullptr, 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     if (m->tc) {
@@ -340,9 +341,15 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
             ta_.out_tiled = 1;                 // conv2's B operand is written TF32-split + swizzled, ready for a bulk copy
             RUN(C_GEMM_FC_MLP, tflops(ta_, 512), cmf_launch_tc_auto(ta_, st));
         }
+        fused_wsum = cmf_tc_pair_enabled() && !getenv("CMF_NO_WSUM");
         {
-            TcArgs ta_ = tc_plain(m->t_fc_w3, 512, 512, nullptr, 0, w.H1, 512, S(FC_B3), bn * 8, CMF_ACT_LEAKY);
+            TcArgs ta_ = tc_plain(m->t_fc_w3, 512, 512, nullptr, 0, fused_wsum ? w.COST1 : w.H1, 512, S(FC_B3), bn * 8, CMF_ACT_LEAKY);
             ta_.prod = TC_PROD_TILED; ta_.Xt = w.H2;
+            if (fused_wsum) {        // conv2 + LeakyReLU + WeightNet1 weighting + sum over the 8 neighbours in the TMEM epilogue
+                ta_.epi = TC_EPI_WSUM; ta_.ksamp = 8; ta_.n_pts = n; ta_.xyz_q = pc1; ta_.xyz_c = pc2; ta_.nbr = w.KNN12; ta_.nbr_ld = 8; ta_.nbr_off = 0;
+                ta_.wnA1 = S(WN1_BASE); ta_.wna1 = S(WN1_BASE + 1); ta_.wnA2 = S(WN1_BASE + 2); ta_.wna2 = S(WN1_BASE + 3);
+                ta_.wnA3 = S(WN1_BASE + 4); ta_.wna3 = S(WN1_BASE + 5);
+            }
             RUN(C_GEMM_FC_MLP, tflops(ta_, 512), cmf_launch_tc_auto(ta_, st));
         }
     } else {
@@ -354,7 +361,7 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
     }
     WeightNetP wn1{S(WN1_BASE), S(WN1_BASE + 1), S(WN1_BASE + 2), S(WN1_BASE + 3), S(WN1_BASE + 4), S(WN1_BASE + 5)};
     WeightNetP wn2{S(WN2_BASE), S(WN2_BASE + 1), S(WN2_BASE + 2), S(WN2_BASE + 3), S(WN2_BASE + 4), S(WN2_BASE + 5)};
-    RUN(C_REDUCE, 0, cmf_launch_fc_reduce(bc, n, pc1, pc2, w.KNN12, wn1, w.H1, 0, w.COST1, 512, st));
+    if (!fused_wsum) RUN(C_REDUCE, 0, cmf_launch_fc_reduce(bc, n, pc1, pc2, w.KNN12, wn1, w.H1, 0, w.COST1, 512, st));
     RUN(C_REDUCE, 0, cmf_launch_fc_reduce(bc, n, pc1, pc1, w.KNN11, wn2, w.COST1, 1, w.E + 256, E_LD, st));
 
     // set-conv #2 (mse_layer2, cmflow.py:87-89)

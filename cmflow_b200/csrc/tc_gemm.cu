@@ -458,10 +458,14 @@ int cmf_launch_tc_gemm(const TcArgs &a, cudaStream_t st) {
     return CMF_OK;
 }
 
-int cmf_launch_tc_auto(const TcArgs &a, cudaStream_t st) {
+int cmf_tc_pair_enabled() {
     static int use2 = -1;
     if (use2 < 0) { const char *e = getenv("CMF_TC2"); use2 = (e && e[0] == '0') ? 0 : 1; }
-    if (use2 && (a.M & 255) == 0 && (a.m_blocks & 1) == 0) return cmf_launch_tc_gemm2(a, st);
+    return use2;
+}
+
+int cmf_launch_tc_auto(const TcArgs &a, cudaStream_t st) {
+    if (cmf_tc_pair_enabled() && (a.M & 255) == 0 && (a.m_blocks & 1) == 0) return cmf_launch_tc_gemm2(a, st);
     return cmf_launch_tc_gemm(a, st);
 }
 

@@ -24,6 +24,9 @@ struct TcArgs {
     int out_tiled;                                               // STORE only: write [col_tile][k_block]{hi,lo} 256x32 swizzled tiles instead of rows
     float *Out; int ldo;
     const float *bias, *pbias; int pb_ld, cols_per_pair, act;
+    // WSUM epilogue (flow embedding, radarflow_util.py:215-225): Out[point][m] = sum_k WeightNet(dir_ik)[m] * act(acc + bias)[column (point,k)]
+    // WeightNet = 3 -> 8 -> 8 -> C, ReLU after every layer; dir = xyz_c[nbr] - xyz_q[point]; ksamp neighbours per point (pair kernel, TILED producer only)
+    const float *wnA1, *wna1, *wnA2, *wna2, *wnA3, *wna3;
 };
 
 size_t cmf_tc_tiled_floats(int M, int K);
@@ -31,4 +34,5 @@ size_t cmf_tc_act_tiled_floats(long long cols, int C);                          
 int cmf_tc_tile_weights(const float *W, int ldw, int M, int K, float *Wt, cudaStream_t st);
 int cmf_launch_tc_gemm(const TcArgs &a, cudaStream_t st);      // one CTA per 128 x 256 tile
 int cmf_launch_tc_gemm2(const TcArgs &a, cudaStream_t st);     // CTA pair (cta_group::2) per 256 x 256 tile; needs M % 256 == 0
+int cmf_tc_pair_enabled();
 int cmf_launch_tc_auto(const TcArgs &a, cudaStream_t st);      // pair kernel when M % 256 == 0 (unless CMF_TC2=0), else the one-CTA kernel

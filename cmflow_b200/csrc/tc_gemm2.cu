@@ -32,7 +32,8 @@ constexpr int STAGE_BYTES = (2 * TILE_A_FLOATS + 2 * TILE_BH_FLOATS) * 4;   // 3
 constexpr int NSTAGE = 6;
 constexpr int NTHREADS = 512;
 constexpr int SMALL_BYTES = 512 * 16;
-constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 + 256 + SMALL_BYTES;
+constexpr int H2_BYTES = 2 * BN * 8 * 4;              // WSUM: WeightNet hidden vectors (8 floats) of the 256 columns, per accumulator stage
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 + 256 + SMALL_BYTES + H2_BYTES;
 constexpr uint32_t IDESC2 = make_idesc(256, BN);
 
 __device__ __forceinline__ void tc_commit2_mc(uint32_t bar) {      // arrive on `bar` in BOTH CTAs when all prior MMAs of this thread retire
@@ -58,7 +59,10 @@ tc_gemm2_kernel(const TcArgs a) {
     auto empty_bar = [&](int s) { return bar0 + 96 + 8 * s; };
     auto tfull_bar = [&](int s) { return bar0 + 144 + 8 * s; };
     auto tempty_bar = [&](int s) { return bar0 + 160 + 8 * s; };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + NSTAGE * STAGE_BYTES + 192);
+    auto h2full_bar = [&](int s) { return bar0 + 176 + 8 * s; };
+    auto h2empty_bar = [&](int s) { return bar0 + 208 + 8 * s; };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + NSTAGE * STAGE_BYTES + 240);
+    float *h2s = reinterpret_cast<float *>(smem + NSTAGE * STAGE_BYTES + 256 + SMALL_BYTES);
     float4 *sW = reinterpret_cast<float4 *>(smem + NSTAGE * STAGE_BYTES + 256);
     if (PROD == TC_PROD_FC_H1 || PROD == TC_PROD_SC2_Y1)
         for (int i = threadIdx.x; i < a.k_blocks * PK; i += NTHREADS) sW[i] = __ldg(reinterpret_cast<const float4 *>(a.Wsmall) + i);
@@ -78,7 +82,7 @@ tc_gemm2_kernel(const TcArgs a) {
             mbar_init(pfull_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); mbar_init(h2full_bar(s), 8); mbar_init(h2empty_bar(s), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -172,17 +176,44 @@ tc_gemm2_kernel(const TcArgs a) {
             const bool m_ok = m < a.M;
             const float bias = (a.bias && m_ok) ? __ldg(a.bias + m) : 0.f;
             EpiState es = epi_begin(a, c0, m, m_ok);
+            float4 w3a = make_float4(0.f, 0.f, 0.f, 0.f), w3b = w3a; float w3c = 0.f;
+            if (a.epi == TC_EPI_WSUM && m_ok) {                      // last WeightNet layer row of this thread's channel
+                w3a = __ldg(reinterpret_cast<const float4 *>(a.wnA3 + (size_t)m * 8)); w3b = __ldg(reinterpret_cast<const float4 *>(a.wnA3 + (size_t)m * 8 + 4));
+                w3c = __ldg(a.wna3 + m);
+            }
             mbar_wait_cluster(tfull_bar(acc), acc_phase);
+            if (a.epi == TC_EPI_WSUM) mbar_wait(h2full_bar(acc), acc_phase);
             tc_fence_after();
 #pragma unroll 1
             for (int cc = 0; cc < BN; cc += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cc, r);
-                epilogue_chunk(a, r, ct, c0, cc, m, m_ok, bias, es, TILE_B_FLOATS);
+                if (a.epi == TC_EPI_WSUM) {
+                    const float4 *hv = reinterpret_cast<const float4 *>(h2s + ((size_t)acc * BN + cc) * 8);
+#pragma unroll
+                    for (int g0 = 0; g0 < 32; g0 += 8) {             // one point = 8 consecutive columns
+                        float sum = 0.f;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float4 ha = hv[(g0 + e) * 2], hb = hv[(g0 + e) * 2 + 1];      // broadcast reads
+                            float w = w3c;
+                            w = fmaf(w3a.x, ha.x, w); w = fmaf(w3a.y, ha.y, w); w = fmaf(w3a.z, ha.z, w); w = fmaf(w3a.w, ha.w, w);
+                            w = fmaf(w3b.x, hb.x, w); w = fmaf(w3b.y, hb.y, w); w = fmaf(w3b.z, hb.z, w); w = fmaf(w3b.w, hb.w, w);
+                            sum = fmaf(fmaxf(w, 0.f), act_apply(__uint_as_float(r[g0 + e]) + bias, a.act), sum);
+                        }
+                        const long long c = c0 + cc + g0;
+                        if (c < a.cols && m_ok) a.Out[(size_t)(c >> 3) * a.ldo + m] = sum;
+                    }
+                } else {
+                    epilogue_chunk(a, r, ct, c0, cc, m, m_ok, bias, es, TILE_B_FLOATS);
+                }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote(tempty_bar(acc), 0); }
+            if (lane == 0) {
+                if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote(tempty_bar(acc), 0);
+                if (a.epi == TC_EPI_WSUM) mbar_arrive(h2empty_bar(acc));
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 8 && PROD != TC_PROD_TILED) {
@@ -254,6 +285,43 @@ tc_gemm2_kernel(const TcArgs a) {
             }
         }
     }
+    else if (warp >= 8 && PROD == TC_PROD_TILED && a.epi == TC_EPI_WSUM) {
+        // ===== WeightNet hidden layers for the WSUM epilogue: thread p owns column ct*256 + p of the tile (all 256 columns, both CTAs) =====
+        const int p = threadIdx.x - 256;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (long long t = cl_id; t < ntiles; t += n_cl) {
+            const long long c = (t / m_pairs) * BN + p;
+            float h2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (c < a.cols) {
+                const long long bi = c >> 3;
+                const int b = (int)(bi / a.n_pts), i = (int)(bi - (long long)b * a.n_pts);
+                const int j = __ldg(a.nbr + (size_t)bi * a.nbr_ld + a.nbr_off + (int)(c & 7));
+                const float *pq = a.xyz_q + (size_t)b * 3 * a.n_pts, *pc = a.xyz_c + (size_t)b * 3 * a.n_pts;
+                const float dx = __fsub_rn(__ldg(pc + j), __ldg(pq + i)), dy = __fsub_rn(__ldg(pc + a.n_pts + j), __ldg(pq + a.n_pts + i)),
+                            dz = __fsub_rn(__ldg(pc + 2 * a.n_pts + j), __ldg(pq + 2 * a.n_pts + i));
+                float h1[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 w = __ldg(reinterpret_cast<const float4 *>(a.wnA1) + u);
+                    h1[u] = fmaxf(fmaf(w.z, dz, fmaf(w.y, dy, fmaf(w.x, dx, __ldg(a.wna1 + u)))), 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    float sacc = __ldg(a.wna2 + u);
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) sacc = fmaf(__ldg(a.wnA2 + u * 8 + v), h1[v], sacc);
+                    h2[u] = fmaxf(sacc, 0.f);
+                }
+            }
+            mbar_wait(h2empty_bar(acc), acc_phase ^ 1);
+            float4 *dst = reinterpret_cast<float4 *>(h2s + ((size_t)acc * BN + p) * 8);
+            dst[0] = make_float4(h2[0], h2[1], h2[2], h2[3]);
+            dst[1] = make_float4(h2[4], h2[5], h2[6], h2[7]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(h2full_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
     tc_fence_before();
     cluster_sync_all();                         // nobody frees TMEM / exits while the pair still uses it
     if (warp == 2) {
@@ -289,6 +357,7 @@ int cmf_launch_tc_gemm2(const TcArgs &a, cudaStream_t st) {
     if (a.out_tiled && a.epi != TC_EPI_STORE) { cmf_set_error("tc_gemm2: tiled output needs the STORE epilogue"); return CMF_ERR_INVALID; }
     if (a.epi == TC_EPI_MAXK && a.ksamp != 4 && a.ksamp != 8 && a.ksamp != 16 && a.ksamp != 32) { cmf_set_error("tc_gemm2: MAXK needs ksamp in {4,8,16,32}"); return CMF_ERR_INVALID; }
     if (a.prod == TC_PROD_FC_H1 && a.ksamp != 8) { cmf_set_error("tc_gemm2: the flow-embedding producer assumes 8 neighbours per point"); return CMF_ERR_INVALID; }
+    if (a.epi == TC_EPI_WSUM && (a.prod != TC_PROD_TILED || a.ksamp != 8)) { cmf_set_error("tc_gemm2: WSUM needs the TILED producer and 8 neighbours per point"); return CMF_ERR_INVALID; }
     const long long ntiles = ((a.cols + BN - 1) / BN) * (a.m_blocks >> 1);
     const int max_cl = num_sms / 2;
     const int n_cl = (int)(ntiles < max_cl ? ntiles : max_cl);
