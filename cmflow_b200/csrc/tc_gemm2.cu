@@ -10,8 +10,8 @@
 //
 // Cluster of 2 CTAs, 512 threads each: w0 bulk-copy issuer, w1 MMA issuer (leader CTA only), w2 TMEM allocator,
 // w3 forwarder (peer CTA only: relays "my half of stage s is full" to the leader), w4-7 epilogue (own 128 accumulator rows),
-// w8-15 producers (TWO threads per activation row, 128 rows per CTA: thread (row, hs) owns the 16-byte chunks 2hs, 2hs+1 of
-// every 16-float stage).  6-stage ring of 32 KB stages (K = 16 per stage).
+// w8-15 producers (128 rows per CTA; lane = (row, 16-byte chunk) so that eight lanes read one 128-byte row slice: coalesced gathers).
+// 6-stage ring of 32 KB stages (K = 16 per stage).
 // Protocol (barriers at identical offsets in both CTAs):
 //   full_local[s]  : local  -- bulk copy expect_tx + 8 producer warps                      (count 1 + 8, or 1 when B is bulk-copied)
 //   peer_full[s]   : leader -- remote arrive by the peer's forwarder                        (count 1)
@@ -217,71 +217,89 @@ tc_gemm2_kernel(const TcArgs a) {
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 8 && PROD != TC_PROD_TILED) {
-        // ===== producers: thread (row, hs) builds chunks {2hs, 2hs+1} of both 16-float stages of every 32-block of row ct*256 + rank*128 + row =====
+        // ===== producers (256 threads): build this CTA's 128 activation rows, 32 floats (two stages) per iteration. =====
+        // Mapping: lane = (row-in-group-of-4, chunk): lane l handles 16-byte chunk q = l & 7 of rows  w*16 + 4*i + (l >> 3), i = 0..3.
+        // Eight lanes read one 128-byte row slice -> every LDG.128 is fully coalesced (4 lines per warp instruction instead of 32),
+        // and a thread's four channels are the same for all of its rows, so their rel-xyz weights are fetched once per iteration.
+        struct SCtx { const float *s1; const float *s0; float dx, dy, dz; int valid; };
+        SCtx *sctx = reinterpret_cast<SCtx *>(h2s);                 // overlays the WSUM buffer (WSUM implies the TILED producer)
         const int p = threadIdx.x - 256;
-        const int row = p & 127, hs = p >> 7;
-        const int g = lane & 7;                                 // position inside the 8-lane group of one point (flow embedding)
+        const int pw = p >> 5;                                     // producer warp 0..7 -> rows pw*16 .. pw*16+15
+        const int q = lane & 7, rsub = lane >> 3;
         int stage = 0; uint32_t phase = 0;
-        long long t = cl_id;
-        // chunk q (0..7 of the 32-block) handled at slot i: i=0,1 -> first stage, i=2,3 -> second stage
-        auto qof = [&](int i) { return (i >> 1) * 4 + 2 * hs + (i & 1); };
-        auto loadp = [&](const RowCtx &r, int kb, float4 (&v)[4], float4 &u) {
-            if (!r.valid) return;
-            const float4 *src = reinterpret_cast<const float4 *>((PROD == TC_PROD_PLAIN ? r.src0 : r.src1) + kb * PK);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = __ldg(src + qof(i));
-            if (PROD == TC_PROD_FC_H1 && g < 4) u = __ldg(reinterpret_cast<const float4 *>(r.src0 + kb * PK) + qof(g));
+        auto fill_ctx = [&](long long tt, int buf) {               // threads p < 128: one row each
+            if (p < HALF_N) {
+                const RowCtx rc = make_row(a, (tt / m_pairs) * BN + rank * HALF_N + p);
+                SCtx c;
+                c.s1 = (PROD == TC_PROD_PLAIN) ? rc.src0 : rc.src1; c.s0 = rc.src0; c.dx = rc.dx; c.dy = rc.dy; c.dz = rc.dz; c.valid = rc.valid ? 1 : 0;
+                sctx[buf * HALF_N + p] = c;
+            }
         };
+        auto loadp = [&](int buf, int kb, float4 (&v)[4], float4 (&u)[4]) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const SCtx &c = sctx[buf * HALF_N + pw * 16 + i * 4 + rsub];
+                if (c.valid) {
+                    v[i] = __ldg(reinterpret_cast<const float4 *>(c.s1 + kb * PK) + q);
+                    if (PROD == TC_PROD_FC_H1) u[i] = __ldg(reinterpret_cast<const float4 *>(c.s0 + kb * PK) + q);
+                }
+            }
+        };
+        long long t = cl_id;
         if (t < ntiles) {
-            RowCtx rc = make_row(a, (t / m_pairs) * BN + rank * HALF_N + row);
-            float4 v[4], vn[4];
-            float4 u = make_float4(0.f, 0.f, 0.f, 0.f), un = u;
-            loadp(rc, 0, v, u);
+            int buf = 0;
+            fill_ctx(t, 0);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            float4 v[4], vn[4], u[4], un[4];
+            loadp(0, 0, v, u);
             while (true) {
-                RowCtx rcn = rc;
                 const long long tn = t + n_cl;
+                if (tn < ntiles) fill_ctx(tn, buf ^ 1);             // next tile's row contexts (read after the barrier at the end of this tile)
                 for (int kb = 0; kb < a.k_blocks; ++kb) {
-                    if (kb + 1 < a.k_blocks) loadp(rc, kb + 1, vn, un);
-                    else if (tn < ntiles) { rcn = make_row(a, (tn / m_pairs) * BN + rank * HALF_N + row); loadp(rcn, 0, vn, un); }
+                    if (kb + 1 < a.k_blocks) loadp(buf, kb + 1, vn, un);
+                    // this thread's four channels of the 32-block and their rel-xyz weights
+                    float4 w4[4];
+                    if (PROD == TC_PROD_FC_H1 || PROD == TC_PROD_SC2_Y1) {
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        mbar_wait(empty_bar(stage), phase ^ 1);
-                        float *Bhi = reinterpret_cast<float *>(smem + stage * STAGE_BYTES + 2 * TILE_A_FLOATS * 4);
-                        float *Blo = Bhi + TILE_BH_FLOATS;
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const int i = half * 2 + j;
-                            const int qq = 2 * hs + j;                          // chunk inside the 16-float stage
-                            const int k0 = kb * PK + half * SK + qq * 4;        // first channel of the chunk
-                            float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-                            if (PROD == TC_PROD_FC_H1) {
-                                const int srcl = (lane & ~7) + i;               // lane of this point's group that fetched centre chunk qof(i)
-                                const float uu[4] = {__shfl_sync(0xffffffffu, u.x, srcl), __shfl_sync(0xffffffffu, u.y, srcl),
-                                                     __shfl_sync(0xffffffffu, u.z, srcl), __shfl_sync(0xffffffffu, u.w, srcl)};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) x[e] = act_apply(uu[e] + x[e] + small_term(sW, k0 + e, rc), 2);
-                            } else if (PROD == TC_PROD_SC2_Y1) {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e] + small_term(sW, k0 + e, rc), 0.f);
-                            }
-                            if (!rc.valid) { x[0] = x[1] = x[2] = x[3] = 0.f; }
-                            float4 h4, l4;
-                            split_tf32(x[0], h4.x, l4.x); split_tf32(x[1], h4.y, l4.y); split_tf32(x[2], h4.z, l4.z); split_tf32(x[3], h4.w, l4.w);
-                            const int off = sw_off(row, qq * 4);
-                            *reinterpret_cast<float4 *>(Bhi + off) = h4;
-                            *reinterpret_cast<float4 *>(Blo + off) = l4;
-                        }
-                        fence_async_smem();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(full_bar(stage));
-                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        for (int e = 0; e < 4; ++e) w4[e] = sW[kb * PK + q * 4 + e];
                     }
+                    const int st0 = stage, st1 = stage + 1;         // NSTAGE is even: a 32-block never wraps between its two stages
+                    mbar_wait(empty_bar(st0), phase ^ 1);
+                    mbar_wait(empty_bar(st1), phase ^ 1);
+                    float *Bhi = reinterpret_cast<float *>(smem + (q < 4 ? st0 : st1) * STAGE_BYTES + 2 * TILE_A_FLOATS * 4);
+                    float *Blo = Bhi + TILE_BH_FLOATS;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) v[i] = vn[i];
-                    u = un;
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = pw * 16 + i * 4 + rsub;
+                        const SCtx &c = sctx[buf * HALF_N + row];
+                        float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+                        if (PROD == TC_PROD_FC_H1) {
+                            const float uu[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) x[e] = act_apply(uu[e] + x[e] + fmaf(w4[e].z, c.dz, fmaf(w4[e].y, c.dy, w4[e].x * c.dx)), 2);
+                        } else if (PROD == TC_PROD_SC2_Y1) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e] + fmaf(w4[e].z, c.dz, fmaf(w4[e].y, c.dy, w4[e].x * c.dx)), 0.f);
+                        }
+                        if (!c.valid) { x[0] = x[1] = x[2] = x[3] = 0.f; }
+                        float4 h4, l4;
+                        split_tf32(x[0], h4.x, l4.x); split_tf32(x[1], h4.y, l4.y); split_tf32(x[2], h4.z, l4.z); split_tf32(x[3], h4.w, l4.w);
+                        const int off = sw_off(row, (q & 3) * 4);
+                        *reinterpret_cast<float4 *>(Bhi + off) = h4;
+                        *reinterpret_cast<float4 *>(Blo + off) = l4;
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(full_bar(st0)); mbar_arrive(full_bar(st1)); }
+                    stage += 2;
+                    if (stage == NSTAGE) { stage = 0; phase ^= 1; }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { v[i] = vn[i]; u[i] = un[i]; }
                 }
                 if (tn >= ntiles) break;
-                t = tn; rc = rcn;
+                asm volatile("bar.sync 1, 256;" ::: "memory");     // next tile's contexts complete; everyone finished reading this tile's
+                t = tn; buf ^= 1;
+                loadp(buf, 0, v, u);
             }
         }
     }
