@@ -46,12 +46,13 @@ SIGNATURES = {
     "cmf_model_get_mode": [_vp],
     "cmf_test_tc_gemm": [_i, _i, ctypes.c_longlong, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp],
     "cmf_test_tc_tiled_floats": [_i, _i],
+    "cmf_test_tc_set_dbg": [_vp],
     "cmf_model_profile_categories": [],
     "cmf_model_profile_name": [_i],
     "cmf_model_read_profile": [_vp, _vp, _vp, _vp],
 }
 _RESTYPES = {"cmf_last_error": ctypes.c_char_p, "cmf_version": ctypes.c_char_p, "cmf_model_blob_floats": _sz,
-             "cmf_model_destroy": None, "cmf_model_profile_name": ctypes.c_char_p, "cmf_test_tc_tiled_floats": _sz, "cmf_model_workspace_bytes": _sz, "cmf_model_tap": _vp}
+             "cmf_model_destroy": None, "cmf_test_tc_set_dbg": None, "cmf_model_profile_name": ctypes.c_char_p, "cmf_test_tc_tiled_floats": _sz, "cmf_model_workspace_bytes": _sz, "cmf_model_tap": _vp}
 
 
 class CmfError(RuntimeError):

@@ -470,6 +470,9 @@ int cmf_launch_tc_auto(const TcArgs &a, cudaStream_t st) {
 }
 
 // ---- test doorway: plain 3xTF32 GEMM through the C ABI (tests/test_gpu_tc_gemm.py) --------------------------------
+static long long *g_test_dbg = nullptr;
+extern "C" void cmf_test_tc_set_dbg(long long *dbg) { g_test_dbg = dbg; }      // device buffer long long[grid][8] or NULL
+
 extern "C" int cmf_test_tc_gemm(int M, int K, long long cols, const float *W, int ldw, const float *X, int ldx,
                                 const float *bias, int act, float *Out, int ldo, float *scratch_tiles, void *stream) {
     CMF_REQUIRE(W && X && Out && scratch_tiles, "null pointer");
@@ -481,6 +484,7 @@ extern "C" int cmf_test_tc_gemm(int M, int K, long long cols, const float *W, in
     a.Wt = scratch_tiles; a.m_blocks = cmf_divup(M, BM); a.k_blocks = cmf_divup(K, PK); a.M = M; a.cols = cols;
     a.prod = TC_PROD_PLAIN; a.X = X; a.ldx = ldx;
     a.epi = TC_EPI_STORE; a.Out = Out; a.ldo = ldo; a.bias = bias; a.pbias = nullptr; a.act = act; a.cols_per_pair = 1;
+    a.dbg = g_test_dbg;
     return cmf_launch_tc_auto(a, st);
 }
 extern "C" size_t cmf_test_tc_tiled_floats(int M, int K) { return cmf_tc_tiled_floats(M, K); }

@@ -27,6 +27,9 @@ struct TcArgs {
     // WSUM epilogue (flow embedding, radarflow_util.py:215-225): Out[point][m] = sum_k WeightNet(dir_ik)[m] * act(acc + bias)[column (point,k)]
     // WeightNet = 3 -> 8 -> 8 -> C, ReLU after every layer; dir = xyz_c[nbr] - xyz_q[point]; ksamp neighbours per point (pair kernel, TILED producer only)
     const float *wnA1, *wna1, *wnA2, *wna2, *wnA3, *wna3;
+    // optional wait-time instrumentation (pair kernel): long long[gridDim.x][8] cycles = {total, mma:tempty, mma:full, mma:peer_full,
+    // loader:empty, producer(warp 8):empty, epilogue(warp 4):tfull, tiles}; NULL in production
+    long long *dbg;
 };
 
 size_t cmf_tc_tiled_floats(int M, int K);

@@ -68,6 +68,9 @@ tc_gemm2_kernel(const TcArgs a) {
         for (int i = threadIdx.x; i < a.k_blocks * PK; i += NTHREADS) sW[i] = __ldg(reinterpret_cast<const float4 *>(a.Wsmall) + i);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t_start = a.dbg ? clock64() : 0;
+    long long dw0 = 0, dw1 = 0, dw2 = 0;                             // per-role accumulated wait cycles (instrumented runs only)
+#define TIMED(acc_, stmt_) do { if (a.dbg) { const long long c0_ = clock64(); stmt_; acc_ += clock64() - c0_; } else { stmt_; } } while (0)
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const long long col_tiles = (a.cols + BN - 1) / BN;
@@ -102,7 +105,7 @@ tc_gemm2_kernel(const TcArgs a) {
                 const int mb = (int)(t % m_pairs) * 2 + (int)rank;
                 const long long ct = t / m_pairs;
                 for (int ks = 0; ks < nks; ++ks) {
-                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    TIMED(dw0, mbar_wait(empty_bar(stage), phase ^ 1));
                     const float *src = a.Wt + ((size_t)mb * nks + ks) * (2 * TILE_A_FLOATS);
                     const uint32_t dst = base + stage * STAGE_BYTES;
                     if (PROD == TC_PROD_TILED) {
@@ -118,6 +121,7 @@ tc_gemm2_kernel(const TcArgs a) {
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
             }
+            if (a.dbg) a.dbg[(size_t)blockIdx.x * 8 + 4] = dw0;
         }
     } else if (warp == 1) {
         // ===== MMA issuer (leader CTA only): one instruction stream drives both SMs' tensor cores =====
@@ -125,12 +129,12 @@ tc_gemm2_kernel(const TcArgs a) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (long long t = cl_id; t < ntiles; t += n_cl) {
-                mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1);
+                TIMED(dw0, mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1));
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int ks = 0; ks < nks; ++ks) {
-                    mbar_wait(full_bar(stage), phase);                 // my half
-                    mbar_wait_cluster(pfull_bar(stage), phase);        // the peer's half (relayed)
+                    TIMED(dw1, mbar_wait(full_bar(stage), phase));                 // my half
+                    TIMED(dw2, mbar_wait_cluster(pfull_bar(stage), phase));        // the peer's half (relayed)
                     tc_fence_after();
                     if (lane == 0) {
                         const uint32_t sa = base + stage * STAGE_BYTES;
@@ -151,6 +155,7 @@ tc_gemm2_kernel(const TcArgs a) {
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+            if (a.dbg && lane == 0) { a.dbg[(size_t)blockIdx.x * 8 + 1] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 2] = dw1; a.dbg[(size_t)blockIdx.x * 8 + 3] = dw2; }
         }
     } else if (warp == 3) {
         // ===== forwarder (peer CTA only): tell the leader when this CTA's half of a stage is complete =====
@@ -175,13 +180,14 @@ tc_gemm2_kernel(const TcArgs a) {
             const int m = mb * BM + q * 32 + lane;
             const bool m_ok = m < a.M;
             const float bias = (a.bias && m_ok) ? __ldg(a.bias + m) : 0.f;
+            if (a.dbg && warp == 4 && lane == 0) dw1 += 1;                     // tiles processed
             EpiState es = epi_begin(a, c0, m, m_ok);
             float4 w3a = make_float4(0.f, 0.f, 0.f, 0.f), w3b = w3a; float w3c = 0.f;
             if (a.epi == TC_EPI_WSUM && m_ok) {                      // last WeightNet layer row of this thread's channel
                 w3a = __ldg(reinterpret_cast<const float4 *>(a.wnA3 + (size_t)m * 8)); w3b = __ldg(reinterpret_cast<const float4 *>(a.wnA3 + (size_t)m * 8 + 4));
                 w3c = __ldg(a.wna3 + m);
             }
-            mbar_wait_cluster(tfull_bar(acc), acc_phase);
+            TIMED(dw0, mbar_wait_cluster(tfull_bar(acc), acc_phase));
             if (a.epi == TC_EPI_WSUM) mbar_wait(h2full_bar(acc), acc_phase);
             tc_fence_after();
 #pragma unroll 1
@@ -216,6 +222,7 @@ tc_gemm2_kernel(const TcArgs a) {
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (a.dbg && warp == 4 && lane == 0) { a.dbg[(size_t)blockIdx.x * 8 + 6] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 7] = dw1; }
     } else if (warp >= 8 && PROD != TC_PROD_TILED) {
         // ===== producers (256 threads): build this CTA's 128 activation rows, 32 floats (two stages) per iteration. =====
         // Mapping: lane = (row-in-group-of-4, chunk): lane l handles 16-byte chunk q = l & 7 of rows  w*16 + 4*i + (l >> 3), i = 0..3.
@@ -264,8 +271,8 @@ tc_gemm2_kernel(const TcArgs a) {
                         for (int e = 0; e < 4; ++e) w4[e] = sW[kb * PK + q * 4 + e];
                     }
                     const int st0 = stage, st1 = stage + 1;         // NSTAGE is even: a 32-block never wraps between its two stages
-                    mbar_wait(empty_bar(st0), phase ^ 1);
-                    mbar_wait(empty_bar(st1), phase ^ 1);
+                    TIMED(dw0, mbar_wait(empty_bar(st0), phase ^ 1));
+                    TIMED(dw0, mbar_wait(empty_bar(st1), phase ^ 1));
                     float *Bhi = reinterpret_cast<float *>(smem + (q < 4 ? st0 : st1) * STAGE_BYTES + 2 * TILE_A_FLOATS * 4);
                     float *Blo = Bhi + TILE_BH_FLOATS;
 #pragma unroll
@@ -302,6 +309,7 @@ tc_gemm2_kernel(const TcArgs a) {
                 loadp(buf, 0, v, u);
             }
         }
+        if (a.dbg && warp == 8 && lane == 0) a.dbg[(size_t)blockIdx.x * 8 + 5] = dw0;
     }
     else if (warp >= 8 && PROD == TC_PROD_TILED && a.epi == TC_EPI_WSUM) {
         // ===== WeightNet hidden layers for the WSUM epilogue: thread p owns column ct*256 + p of the tile (all 256 columns, both CTAs) =====
@@ -340,6 +348,7 @@ tc_gemm2_kernel(const TcArgs a) {
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
+    if (a.dbg && threadIdx.x == 0) a.dbg[(size_t)blockIdx.x * 8 + 0] = clock64() - t_start;
     tc_fence_before();
     cluster_sync_all();                         // nobody frees TMEM / exits while the pair still uses it
     if (warp == 2) {

@@ -183,6 +183,8 @@ const void *cmf_model_tap(const cmf_model *m, const char *name);
 int cmf_test_tc_gemm(int M, int K, long long cols, const float *W, int ldw, const float *X, int ldx,
                      const float *bias, int act, float *Out, int ldo, float *scratch_tiles, void *stream);
 size_t cmf_test_tc_tiled_floats(int M, int K);
+/* Instrumented runs of cmf_test_tc_gemm: device buffer long long[grid][8] receiving per-role barrier wait cycles (NULL = off). */
+void cmf_test_tc_set_dbg(long long *dbg);
 
 #ifdef __cplusplus
 }
