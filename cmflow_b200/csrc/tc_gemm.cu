@@ -81,22 +81,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_fence(uint32_t (&r)[32]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(r[i]));
-}
-
 // hi = round-to-nearest TF32 (low 13 mantissa bits zero), lo = x - hi (exact)
 __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
     uint32_t h;
@@ -322,18 +306,10 @@ tc_gemm_kernel(const TcArgs a) {
             }
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            // software-pipelined TMEM loads: chunk cc+32 is in flight while chunk cc is processed
-            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-            uint32_t ra[32], rb[32];
-            tmem_ld32_issue(tbase, ra);
 #pragma unroll 1
-            for (int cc2 = 0; cc2 < BN; cc2 += 64) {
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int cc = cc2 + hh * 32;
-                    uint32_t (&r)[32] = hh ? rb : ra;
-                    tmem_ld_fence(r);
-                    if (cc + 32 < BN) tmem_ld32_issue(tbase + cc + 32, hh ? ra : rb);
+            for (int cc = 0; cc < BN; cc += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cc, r);
                 if (a.epi == TC_EPI_STORE && a.out_tiled) {
                     // next GEMM's B operand, already TF32-split and swizzled: tile (col_tile, 16-block = m/16), row = column in tile
                     float *tb = a.Out + ((size_t)ct * (a.M >> 4) + (m >> 4)) * (2 * TILE_B_FLOATS);
@@ -367,7 +343,6 @@ tc_gemm_kernel(const TcArgs a) {
                     else if (a.ksamp == 8) maxk_groups<8>(r, bias, c0 + cc, m, m_ok, a);
                     else if (a.ksamp == 16) maxk_groups<16>(r, bias, c0 + cc, m, m_ok, a);
                     else maxk_groups<32>(r, bias, c0 + cc, m, m_ok, a);
-                }
                 }
             }
             tc_fence_before();

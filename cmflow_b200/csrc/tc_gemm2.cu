@@ -13,8 +13,8 @@
 // w8-15 producers (128 rows per CTA; lane = (row, 16-byte chunk) so that eight lanes read one 128-byte row slice: coalesced gathers).
 // 6-stage ring of 32 KB stages (K = 16 per stage).
 // Protocol (barriers at identical offsets in both CTAs):
-//   full[s]        : local  -- bulk copy expect_tx + 8 producer warps (count 1 + 8, or 1 when B is bulk-copied);
-//                    the LEADER's additionally counts one remote arrive from the peer's forwarder ("my half is full too")
+//   full_local[s]  : local  -- bulk copy expect_tx + 8 producer warps                      (count 1 + 8, or 1 when B is bulk-copied)
+//   peer_full[s]   : leader -- remote arrive by the peer's forwarder                        (count 1)
 //   empty[s]       : both   -- tcgen05.commit.cta_group::2 multicast from the leader        (count 1)
 //   tfull[a]       : both   -- commit multicast after the last K stage of a tile            (count 1)
 //   tempty[a]      : leader -- 4 local + 4 remote epilogue warps                            (count 8)
@@ -80,9 +80,8 @@ tc_gemm2_kernel(const TcArgs a) {
     const int nks = a.k_blocks * 2;
 
     if (threadIdx.x == 0) {
-        const bool leader_init = cluster_ctarank() == 0;
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(full_bar(s), (PROD == TC_PROD_TILED ? 1 : 1 + 8) + (leader_init ? 1 : 0));   // the leader's also counts the peer's relay
+            mbar_init(full_bar(s), PROD == TC_PROD_TILED ? 1 : 1 + 8);
             mbar_init(pfull_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
@@ -134,7 +133,8 @@ tc_gemm2_kernel(const TcArgs a) {
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int ks = 0; ks < nks; ++ks) {
-                    TIMED(dw1, mbar_wait_cluster(full_bar(stage), phase));          // my half AND the peer's (its forwarder arrives here too)
+                    TIMED(dw1, mbar_wait(full_bar(stage), phase));                 // my half
+                    TIMED(dw2, mbar_wait_cluster(pfull_bar(stage), phase));        // the peer's half (relayed)
                     tc_fence_after();
                     if (lane == 0) {
                         const uint32_t sa = base + stage * STAGE_BYTES;
@@ -164,7 +164,7 @@ tc_gemm2_kernel(const TcArgs a) {
             for (long long t = cl_id; t < ntiles; t += n_cl)
                 for (int ks = 0; ks < nks; ++ks) {
                     mbar_wait(full_bar(stage), phase);
-                    if (lane == 0) mbar_arrive_remote(full_bar(stage), 0);
+                    if (lane == 0) mbar_arrive_remote(pfull_bar(stage), 0);
                     __syncwarp();
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
@@ -190,38 +190,28 @@ tc_gemm2_kernel(const TcArgs a) {
             TIMED(dw0, mbar_wait_cluster(tfull_bar(acc), acc_phase));
             if (a.epi == TC_EPI_WSUM) mbar_wait(h2full_bar(acc), acc_phase);
             tc_fence_after();
-            // TMEM -> registers, software-pipelined: the load of chunk cc+32 is in flight while chunk cc is processed
-            // (a blocking ld+wait per chunk exposes ~4k clk of TMEM latency each while the tensor core owns the TMEM ports).
-            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-            uint32_t ra[32], rb[32];
-            tmem_ld32_issue(tbase, ra);
 #pragma unroll 1
-            for (int cc2 = 0; cc2 < BN; cc2 += 64) {
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int cc = cc2 + hh * 32;
-                    uint32_t (&r)[32] = hh ? rb : ra;
-                    tmem_ld_fence(r);                                           // chunk cc has landed
-                    if (cc + 32 < BN) tmem_ld32_issue(tbase + cc + 32, hh ? ra : rb);
+            for (int cc = 0; cc < BN; cc += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cc, r);
                 if (a.epi == TC_EPI_WSUM) {
-                        const float4 *hv = reinterpret_cast<const float4 *>(h2s + ((size_t)acc * BN + cc) * 8);
+                    const float4 *hv = reinterpret_cast<const float4 *>(h2s + ((size_t)acc * BN + cc) * 8);
 #pragma unroll
-                        for (int g0 = 0; g0 < 32; g0 += 8) {             // one point = 8 consecutive columns
-                            float sum = 0.f;
+                    for (int g0 = 0; g0 < 32; g0 += 8) {             // one point = 8 consecutive columns
+                        float sum = 0.f;
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const float4 ha = hv[(g0 + e) * 2], hb = hv[(g0 + e) * 2 + 1];      // broadcast reads
-                                float w = w3c;
-                                w = fmaf(w3a.x, ha.x, w); w = fmaf(w3a.y, ha.y, w); w = fmaf(w3a.z, ha.z, w); w = fmaf(w3a.w, ha.w, w);
-                                w = fmaf(w3b.x, hb.x, w); w = fmaf(w3b.y, hb.y, w); w = fmaf(w3b.z, hb.z, w); w = fmaf(w3b.w, hb.w, w);
-                                sum = fmaf(fmaxf(w, 0.f), act_apply(__uint_as_float(r[g0 + e]) + bias, a.act), sum);
-                            }
-                            const long long c = c0 + cc + g0;
-                            if (c < a.cols && m_ok) a.Out[(size_t)(c >> 3) * a.ldo + m] = sum;
+                        for (int e = 0; e < 8; ++e) {
+                            const float4 ha = hv[(g0 + e) * 2], hb = hv[(g0 + e) * 2 + 1];      // broadcast reads
+                            float w = w3c;
+                            w = fmaf(w3a.x, ha.x, w); w = fmaf(w3a.y, ha.y, w); w = fmaf(w3a.z, ha.z, w); w = fmaf(w3a.w, ha.w, w);
+                            w = fmaf(w3b.x, hb.x, w); w = fmaf(w3b.y, hb.y, w); w = fmaf(w3b.z, hb.z, w); w = fmaf(w3b.w, hb.w, w);
+                            sum = fmaf(fmaxf(w, 0.f), act_apply(__uint_as_float(r[g0 + e]) + bias, a.act), sum);
                         }
-                    } else {
-                        epilogue_chunk(a, r, ct, c0, cc, m, m_ok, bias, es, TILE_B_FLOATS);
+                        const long long c = c0 + cc + g0;
+                        if (c < a.cols && m_ok) a.Out[(size_t)(c >> 3) * a.ldo + m] = sum;
                     }
+                } else {
+                    epilogue_chunk(a, r, ct, c0, cc, m, m_ok, bias, es, TILE_B_FLOATS);
                 }
             }
             tc_fence_before();
