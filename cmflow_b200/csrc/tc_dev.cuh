@@ -5,7 +5,7 @@
 namespace tcdev {
 
 constexpr int BM = 128, BN = 256, SK = 16, PK = 32;
-constexpr unsigned SPIN_LIMIT = 1u << 24;
+constexpr unsigned SPIN_LIMIT = 20000u;         // x 1 ms suspend hint = 20 s before a stuck wait traps
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -27,8 +27,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     unsigned spins = 0;
     while (!done) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
         if (!done && ++spins > SPIN_LIMIT) __trap();        // never hang the GPU: fail the launch instead
     }
 }
@@ -37,8 +37,8 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     uint32_t done = 0;
     unsigned spins = 0;
     while (!done) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
         if (!done && ++spins > SPIN_LIMIT) __trap();
     }
 }
