@@ -179,41 +179,84 @@ __device__ __forceinline__ void store_half(const float4 *sW, const RowCtx &r, in
 
 // One epilogue pass over 32 accumulator columns held in r[] (this thread = output channel m): bias / per-pair bias / activation and
 // either a row-major store, a tiled (TF32-split, swizzled) store for the next GEMM, or the max over each point's ksamp neighbours.
+// The common case -- the 32 columns are all valid and belong to one frame pair -- takes a branch-free fast path (~6 instructions per
+// element row-major, ~12 tiled); the generic path (bounds / pair-boundary checks per element) costs ~75 and is kept for edge tiles.
 struct EpiState { long long pair, pair_end; float pb; };
+
+// act as max(v, v*slope): slope 1 = identity, 0 = ReLU, 0.1 = LeakyReLU(0.1)
+__device__ __forceinline__ float act_slope(int act) { return act == 1 ? 0.f : (act == 2 ? 0.1f : 1.f); }
 
 __device__ __forceinline__ void epilogue_chunk(const TcArgs &a, const uint32_t (&r)[32], long long ct, long long c0, int cc, int m, bool m_ok,
                                                float bias, EpiState &es, int tile_b_floats) {
-    if (a.epi == TC_EPI_STORE && a.out_tiled) {
+    const long long cfirst = c0 + cc;
+    if (a.epi == TC_EPI_MAXK) {
+        if (a.ksamp == 4) maxk_groups<4>(r, bias, cfirst, m, m_ok, a);
+        else if (a.ksamp == 8) maxk_groups<8>(r, bias, cfirst, m, m_ok, a);
+        else if (a.ksamp == 16) maxk_groups<16>(r, bias, cfirst, m, m_ok, a);
+        else maxk_groups<32>(r, bias, cfirst, m, m_ok, a);
+        return;
+    }
+    // fast path test (warp-uniform): whole chunk in range and inside the current frame pair
+    while (cfirst >= es.pair_end) {                                  // advance the pair cursor to the chunk's first column
+        ++es.pair; es.pair_end += a.cols_per_pair;
+        if (m_ok && cfirst < a.cols) es.pb = __ldg(a.pbias + (size_t)es.pair * a.pb_ld + m);
+    }
+    const bool fast = (cfirst + 32 <= a.cols) && (cfirst + 32 <= es.pair_end) && (m_ok || a.out_tiled);
+    const float slope = act_slope(a.act);
+    if (fast) {
+        const float badd = bias + es.pb;
+        if (a.out_tiled) {
+            // tile (col_tile, 16-block m/16); element (row = column in tile, kk = m%16) at sw_off(row, kk); (row>>1)&3 == (e>>1)&3 since cc % 8 == 0
+            float *tb = a.Out + ((size_t)ct * (a.M >> 4) + (m >> 4)) * (2 * (size_t)tile_b_floats) + cc * SK + (m & 3);
+            const int kq = (m & 15) >> 2;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                float v = __uint_as_float(r[e]) + badd;
+                v = fmaxf(v, v * slope);
+                float hi, lo;
+                split_tf32(v, hi, lo);
+                const int off = e * SK + ((kq ^ ((e >> 1) & 3)) << 2);
+                tb[off] = hi;
+                tb[tile_b_floats + off] = lo;
+            }
+        } else {
+            float *o = a.Out + (size_t)cfirst * a.ldo + m;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                float v = __uint_as_float(r[e]) + badd;
+                o[(size_t)e * a.ldo] = fmaxf(v, v * slope);
+            }
+        }
+        return;
+    }
+    // generic path
+    if (a.out_tiled) {
         float *tb = a.Out + ((size_t)ct * (a.M >> 4) + (m >> 4)) * (2 * (size_t)tile_b_floats);
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-            const long long c = c0 + cc + e;
+            const long long c = cfirst + e;
             if (c >= es.pair_end) {
                 ++es.pair; es.pair_end += a.cols_per_pair;
                 if (c < a.cols) es.pb = __ldg(a.pbias + (size_t)es.pair * a.pb_ld + m);
             }
-            const float v = c < a.cols ? act_apply(__uint_as_float(r[e]) + bias + es.pb, a.act) : 0.f;
+            float v = __uint_as_float(r[e]) + bias + es.pb;
+            v = c < a.cols ? fmaxf(v, v * slope) : 0.f;
             float hi, lo;
             split_tf32(v, hi, lo);
             const int off = sw_off(cc + e, m & 15);
             tb[off] = hi;
             tb[tile_b_floats + off] = lo;
         }
-    } else if (a.epi == TC_EPI_STORE) {
+    } else {
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-            const long long c = c0 + cc + e;
-            if (c >= es.pair_end) {                                  // warp-uniform: crossed into the next frame pair
+            const long long c = cfirst + e;
+            if (c >= es.pair_end) {
                 ++es.pair; es.pair_end += a.cols_per_pair;
                 if (m_ok && c < a.cols) es.pb = __ldg(a.pbias + (size_t)es.pair * a.pb_ld + m);
             }
-            if (c < a.cols && m_ok) a.Out[(size_t)c * a.ldo + m] = act_apply(__uint_as_float(r[e]) + bias + es.pb, a.act);
+            if (c < a.cols && m_ok) { const float v = __uint_as_float(r[e]) + bias + es.pb; a.Out[(size_t)c * a.ldo + m] = fmaxf(v, v * slope); }
         }
-    } else if (a.epi == TC_EPI_MAXK) {
-        if (a.ksamp == 4) maxk_groups<4>(r, bias, c0 + cc, m, m_ok, a);
-        else if (a.ksamp == 8) maxk_groups<8>(r, bias, c0 + cc, m, m_ok, a);
-        else if (a.ksamp == 16) maxk_groups<16>(r, bias, c0 + cc, m, m_ok, a);
-        else maxk_groups<32>(r, bias, c0 + cc, m, m_ok, a);
     }
 }
 
