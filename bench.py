@@ -106,8 +106,9 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="frame pairs per GPU per step")
     ap.add_argument("--points", type=int, default=256)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("CMF_BENCH_PRECISION", "tf32x3"), choices=["fp32", "tf32x3"],
-                    help="fp32 = strict fp32 FMA kernels; tf32x3 = tcgen05 tensor cores with 3xTF32 split precision (fp32-class accuracy)")
+    ap.add_argument("--precision", default=os.environ.get("CMF_BENCH_PRECISION", "fp16x3"), choices=["fp32", "tf32x3", "fp16x3"],
+                    help="fp32 = strict fp32 FMA kernels; tf32x3 / fp16x3 = tcgen05 tensor cores with a 22-bit hi/lo operand split "
+                         "(3 MMAs per product, fp32 accumulate, fp32-class accuracy) in kind::tf32 or kind::f16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu", action="store_true", help="profiler harness: W+K device forwards only, prints no bench line")
     args = ap.parse_args()
@@ -237,14 +238,15 @@ def main():
         dom = "gemm_setconv2_l2"
         d = prof[dom]
         achieved = d["gflop_per_step"] / d["ms_per_step"]       # GFLOP/ms == TFLOP/s (algorithmic FLOPs: 2*M*K*cols, split passes not counted)
-        tc = args.precision == "tf32x3"
-        roofline = {"kernel": ("tc_gemm_kernel<SC2_Y1> tcgen05 3xTF32" if tc else "gemm_nt_kernel<128> fp32 FMA") +
+        tc = args.precision != "fp32"
+        split = {"tf32x3": ("3xTF32", 6), "fp16x3": ("3xFP16", 3)}.get(args.precision)
+        roofline = {"kernel": (f"tc_gemm2_kernel<SC2_Y1> tcgen05 {split[0]}" if tc else "gemm_nt_kernel<128> fp32 FMA") +
                               " (set-conv #2 layer 2, 512->256 over N*K neighbour columns, gather fused)" ,
                     "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"],
                     "unit": "TFLOP/s", "frac": achieved / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]),
                     "peak_source": peaks["source"] + " cuBLAS bf16 (sustained)", "traffic": None,
                     "launches_per_step": d["launches_per_step"], "avg_launch_ms": d["ms_per_step"] / max(1, d["launches_per_step"]),
-                    "note": ("3xTF32: three kind::tf32 MMAs (half the bf16 rate each) per algorithmic MAC => ceiling = bf16 peak / 6" if tc else
+                    "note": (f"{split[0]}: three MMAs per algorithmic MAC (kind::tf32 runs at half the bf16 rate) => ceiling = bf16 peak / {split[1]}" if tc else
                              "strict-fp32 FMA build (no tensor cores): the chip's fp32 FMA ceiling is 74.5 TFLOP/s, ~1/19 of this peak")}
         if not args.no_cpu_baseline and world == 1:
             v, spp = time_cpu_port(4, N, 2, 1, cores)
@@ -255,7 +257,7 @@ def main():
         line = {
             "metric": "frame-pairs/sec CMFlow forward", "value": total_pairs * K / (ms_dev / 1e3), "unit": "frame-pairs/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": ("f32 (3xTF32 split on tcgen05 tensor cores, fp32 accumulate)" if args.precision == "tf32x3" else "f32"), "data": "synthetic radar pairs (cmflow_b200/synth.py), seeded random-init weights of the CMFlow architecture",
+            "vs_baseline": None, "dtype": (f"f32 ({split[0]} split on tcgen05 tensor cores, fp32 accumulate)" if tc else "f32"), "data": "synthetic radar pairs (cmflow_b200/synth.py), seeded random-init weights of the CMFlow architecture",
             "config": {"workload": workload, "points": N, "pairs_per_gpu": B, "global_batch": total_pairs, "parallelism": f"dp{world}",
                        "l2": "256 MB flush between timed steps; 4 rotating input batches", "precision_mode": args.precision},
             "e2e": {"value": total_pairs * K / (ms_host / 1e3), "unit": "frame-pairs/s", "ms_per_step": ms_host / K,

@@ -45,6 +45,7 @@ SIGNATURES = {
     "cmf_model_set_mode": [_vp, _i],
     "cmf_model_get_mode": [_vp],
     "cmf_test_tc_gemm": [_i, _i, ctypes.c_longlong, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp],
+    "cmf_test_tc_gemm_fmt": [_i, _i, _i, ctypes.c_longlong, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp],
     "cmf_test_tc_tiled_floats": [_i, _i],
     "cmf_test_tc_set_dbg": [_vp],
     "cmf_model_profile_categories": [],

@@ -115,8 +115,9 @@ class _EngineModel(nn.Module):
         return lib().cmf_model_launches_per_forward(self._handle) if self._handle else 0
 
     def set_precision(self, mode):
-        """'fp32' = strict fp32 FMA kernels (parity build); 'tf32x3' = tcgen05 tensor cores, 3xTF32 split precision."""
-        self._mode = {"fp32": 0, "tf32x3": 1}[mode]
+        """'fp32' = strict fp32 FMA kernels (parity build); 'tf32x3' / 'fp16x3' = tcgen05 tensor cores with a 22-bit hi/lo operand
+        split (3 MMAs per product, fp32 accumulate): kind::tf32, or kind::f16 at twice the rate with power-of-two operand scaling."""
+        self._mode = {"fp32": 0, "tf32x3": 1, "fp16x3": 2}[mode]
         if self._handle is not None:
             check(lib().cmf_model_set_mode(self._handle, self._mode))
 

@@ -15,6 +15,7 @@
 //       flow-embedding layer 1: 1.08 GMAC/pair -> 0.07 GMAC/pair
 //  * mse_layer and mse_layer2 query the same cloud with the same radii (cmflow.py:21-24,35-39), so the
 //    reference's 12 ball queries are 8, and each cloud's four radii are answered in one pass.
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -93,7 +94,11 @@ struct Work {
     float *PB1, *PB2, *U1, *U2, *H1, *H2, *COST1;
     float *PBM, *P, *Y1, *Y2, *Y3, *PROP, *GP, *GI, *GH, *GNEW, *ZERO;
     float *PBH, *HD1, *HD2, *HD3, *FLOW;
+    unsigned int *AMAX;      // fp16x3 mode: per-pair max |x| of the tensors feeding a tensor-core GEMM (uint bit patterns of floats), AM_COUNT x bc
+    float *SCL;              // fp16x3 mode: per-pair scales of the tiled intermediates (H2, Y2 x 4 scales), SC_COUNT x bc
 };
+enum { AM_F1 = 0, AM_F2, AM_E, AM_PROP, AM_U1, AM_U2, AM_DIR, AM_P0, AM_COUNT = AM_P0 + 4 };
+enum { SC_H2 = 0, SC_Y2, SC_COUNT = SC_Y2 + 4 };
 
 void carve(Arena &a, Work &w, int bc, int n) {
     const size_t bn = (size_t)bc * n;
@@ -117,6 +122,7 @@ void carve(Arena &a, Work &w, int bc, int n) {
     w.PBH = a.take<float>((size_t)bc * 512);
     w.HD1 = a.take<float>(bn * 512); w.HD2 = a.take<float>(bn * 256); w.HD3 = a.take<float>(bn * 128);
     w.FLOW = a.take<float>(bn * 3);
+    w.AMAX = a.take<unsigned int>((size_t)AM_COUNT * bc); w.SCL = a.take<float>((size_t)SC_COUNT * bc);
 }
 
 }  // namespace
@@ -136,9 +142,12 @@ struct cmf_model {
     // tensor-core (tcgen05, 3xTF32) mode: pre-tiled hi/lo copies of the big weight matrices
     int tc = 0;
     int fused_sc1 = 1;           // CMF_FUSED_SC1=0 falls back to the unfused (GEMM-per-layer) set-conv #1 for A/B testing
-    float *tc_buf = nullptr;
-    const float *t_fc_wc = nullptr, *t_fc_wn = nullptr, *t_fc_w2 = nullptr, *t_fc_w3 = nullptr, *t_m2_wp = nullptr,
-                *t_m2_w2[4] = {nullptr, nullptr, nullptr, nullptr}, *t_m2_w3[4] = {nullptr, nullptr, nullptr, nullptr}, *t_hd_w1 = nullptr;
+    // pre-tiled weights per operand format (index 0: 3xTF32, 1: 3xFP16 with per-row scales a_inv)
+    struct TcW { const float *wt = nullptr, *ainv = nullptr; };
+    struct TcSet { float *buf = nullptr; TcW fc_wc, fc_wn, fc_w2, fc_w3, m2_wp, m2_w2[4], m2_w3[4], hd_w1; } tcw[2];
+    // host-side norms for the fp16x3 scale bounds: max row L1 of the rel-xyz / direction columns, max row L1 and max |bias| of the layers
+    // whose outputs are written pre-split (flow-embedding conv1, set-conv #2 layer 2)
+    float wd_l1 = 0.f, wx_l1[4] = {0.f, 0.f, 0.f, 0.f}, fc_w2_l1 = 0.f, fc_b2_max = 0.f, m2_w2_l1[4] = {0.f, 0.f, 0.f, 0.f}, m2_t2_max[4] = {0.f, 0.f, 0.f, 0.f};
     // profiling
     struct ProfRec { int cat; cudaEvent_t e0, e1; };
     int profiling = 0;
@@ -182,37 +191,55 @@ static const char *const kCatNames[C_COUNT] = {"search", "gemm_setconv1", "gemm_
 static double gflops(const GemmArgs &g) { return 2.0 * g.M * (double)g.K * g.cols; }
 static double gflops(const GemmBatch &gb) { double f = 0; for (int i = 0; i < gb.count; ++i) f += gflops(gb.g[i]); return f; }
 
-static TcArgs tc_plain(const float *Wt, int M, int K, const float *X, int ldx, float *Out, int ldo, const float *bias,
-                       long long cols, int act, const float *pbias = nullptr, int pb_ld = 0, int cpp = 1) {
+static TcArgs tc_plain(const cmf_model::TcW &W, int fmt, int M, int K, const float *X, int ldx, float *Out, int ldo, const float *bias,
+                       long long cols, int act, const float *pbias, int pb_ld, long long cpp) {
     TcArgs a{};
-    a.Wt = Wt; a.m_blocks = cmf_divup(M, 128); a.k_blocks = cmf_divup(K, 32); a.M = M; a.cols = cols;
+    a.fmt = fmt; a.a_inv = fmt ? W.ainv : nullptr; a.amax_group = 1 << 30;
+    a.Wt = W.wt; a.m_blocks = cmf_divup(M, 128); a.k_blocks = cmf_divup(K, 32); a.M = M; a.cols = cols;
     a.prod = TC_PROD_PLAIN; a.X = X; a.ldx = ldx;
-    a.epi = TC_EPI_STORE; a.Out = Out; a.ldo = ldo; a.bias = bias; a.pbias = pbias; a.pb_ld = pb_ld; a.cols_per_pair = cpp; a.act = act;
+    a.epi = TC_EPI_STORE; a.Out = Out; a.ldo = ldo; a.bias = bias; a.pbias = pbias; a.pb_ld = pb_ld; a.cols_per_pair = (int)cpp; a.act = act;
     a.ksamp = 1;
     return a;
 }
+// fp16x3: B-operand scale from a bound  const + sum coef_i * amax_i[pair]
+static void tc_bound(TcArgs &a, float c0, const unsigned int *s0, float k0, const unsigned int *s1 = nullptr, float k1 = 0.f,
+                     const unsigned int *s2 = nullptr, float k2 = 0.f) {
+    if (!a.fmt) return;
+    a.bs_mode = 1; a.bs_const = c0;
+    a.bs_src[0] = reinterpret_cast<const float *>(s0); a.bs_coef[0] = k0;
+    a.bs_src[1] = reinterpret_cast<const float *>(s1); a.bs_coef[1] = k1;
+    a.bs_src[2] = reinterpret_cast<const float *>(s2); a.bs_coef[2] = k2;
+}
+static void tc_scaled(TcArgs &a, const float *scale) {          // fp16x3: B operand pre-split by the previous GEMM with per-pair scale[]
+    if (!a.fmt) return;
+    a.bs_mode = 2; a.bs_src[0] = scale;
+}
 static double tflops(const TcArgs &a, int K) { return 2.0 * a.M * (double)K * (double)a.cols; }
 
-static int ensure_tc_weights(cmf_model *m) {
-    if (m->tc_buf) return CMF_OK;
-    struct Item { const float **dst; int seg, M, K, ldw; };
+static int ensure_tc_weights(cmf_model *m, int fmt) {
+    cmf_model::TcSet &S = m->tcw[fmt];
+    if (S.buf) return CMF_OK;
+    struct Item { cmf_model::TcW *dst; int seg, M, K, ldw; };
     std::vector<Item> items = {
-        {&m->t_fc_wc, FC_WC, 512, 256, 256}, {&m->t_fc_wn, FC_WN, 512, 256, 256}, {&m->t_fc_w2, FC_W2, 512, 512, 512},
-        {&m->t_fc_w3, FC_W3, 512, 512, 512}, {&m->t_m2_wp, M2_WP, 2048, E_LD, E_LD}, {&m->t_hd_w1, HD_W1, 512, 256, 256}};
+        {&S.fc_wc, FC_WC, 512, 256, 256}, {&S.fc_wn, FC_WN, 512, 256, 256}, {&S.fc_w2, FC_W2, 512, 512, 512},
+        {&S.fc_w3, FC_W3, 512, 512, 512}, {&S.m2_wp, M2_WP, 2048, E_LD, E_LD}, {&S.hd_w1, HD_W1, 512, 256, 256}};
     for (int s = 0; s < 4; ++s) {
-        items.push_back({&m->t_m2_w2[s], M2_BASE + s * 10, 256, 512, 512});
-        items.push_back({&m->t_m2_w3[s], M2_BASE + s * 10 + 2, 64, 256, 256});
+        items.push_back({&S.m2_w2[s], M2_BASE + s * 10, 256, 512, 512});
+        items.push_back({&S.m2_w3[s], M2_BASE + s * 10 + 2, 64, 256, 256});
     }
+    auto ainv_floats = [](int M) { return (size_t)cmf_divup(M, 128) * 128; };
     size_t tot = 0;
-    for (auto &it : items) tot += cmf_tc_tiled_floats(it.M, it.K);
-    cudaError_t e = cudaMalloc(&m->tc_buf, tot * sizeof(float));
-    if (e != cudaSuccess) { cmf_set_error("tc weights cudaMalloc failed: %s", cudaGetErrorString(e)); return CMF_ERR_NOMEM; }
+    for (auto &it : items) tot += cmf_tc_tiled_floats(it.M, it.K) + ainv_floats(it.M);
+    cudaError_t e = cudaMalloc(&S.buf, tot * sizeof(float));
+    if (e != cudaSuccess) { S.buf = nullptr; cmf_set_error("tc weights cudaMalloc failed: %s", cudaGetErrorString(e)); return CMF_ERR_NOMEM; }
     size_t off = 0;
     for (auto &it : items) {
-        int rc = cmf_tc_tile_weights(m->seg[it.seg], it.ldw, it.M, it.K, m->tc_buf + off, 0);
+        float *wt = S.buf + off, *ainv = wt + cmf_tc_tiled_floats(it.M, it.K);
+        int rc = fmt ? cmf_tc_tile_weights_f16(m->seg[it.seg], it.ldw, it.M, it.K, wt, ainv, 0)
+                     : cmf_tc_tile_weights(m->seg[it.seg], it.ldw, it.M, it.K, wt, 0);
         if (rc) return rc;
-        *it.dst = m->tc_buf + off;
-        off += cmf_tc_tiled_floats(it.M, it.K);
+        it.dst->wt = wt; it.dst->ainv = fmt ? ainv : nullptr;
+        off += cmf_tc_tiled_floats(it.M, it.K) + ainv_floats(it.M);
     }
     CMF_CUDA(cudaDeviceSynchronize());
     return CMF_OK;
@@ -313,6 +340,12 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
     Work &w = m->w;
     const long long bn = (long long)bc * n;
     auto S = [&](int i) { return m->seg[i]; };
+    const int F = m->tc == 2 ? 1 : 0;                                   // operand format of the tensor-core GEMMs (0: 3xTF32, 1: 3xFP16)
+    const cmf_model::TcSet &T = m->tcw[F];
+    auto AM = [&](int slot) { return w.AMAX + (size_t)slot * m->cap_bc; };
+    auto SC = [&](int slot) { return w.SCL + (size_t)slot * m->cap_bc; };
+    static const float RADII[4] = {2.f, 4.f, 8.f, 16.f};               // models/cmflow.py:21,35
+    if (F) CMF_CUDA(cudaMemsetAsync(w.AMAX, 0, (size_t)AM_COUNT * m->cap_bc * sizeof(unsigned int), st));
 
     // neighbour search
     RUN(C_SEARCH, 0, cmf_launch_transpose3(bc, n, pc1, w.X1T, st));
@@ -332,19 +365,36 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
     { const GemmArgs ga_ = mk(S(FC_WCG), 256, w.G1, 256, w.PB1, 512, S(FC_B1), 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     { const GemmArgs ga_ = mk(S(FC_WNG), 256, w.G2, 256, w.PB2, 512, nullptr, 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     if (m->tc) {
-        { const TcArgs ta_ = tc_plain(m->t_fc_wc, 512, 256, w.E, E_LD, w.U1, 512, nullptr, bn, CMF_ACT_NONE, w.PB1, 512, n); RUN(C_GEMM_FC_HOIST, tflops(ta_, 256), cmf_launch_tc_auto(ta_, st)); }
-        { const TcArgs ta_ = tc_plain(m->t_fc_wn, 512, 256, w.F2, 256, w.U2, 512, nullptr, bn, CMF_ACT_NONE, w.PB2, 512, n); RUN(C_GEMM_FC_HOIST, tflops(ta_, 256), cmf_launch_tc_auto(ta_, st)); }
+        if (F) {    // per-pair maxima of the GEMM inputs (fp16 scales): encoder features, kNN direction components
+            RUN(C_REDUCE, 0, cmf_launch_pair_absmax(bc, n, w.E, E_LD, 256, AM(AM_F1), st));
+            RUN(C_REDUCE, 0, cmf_launch_pair_absmax(bc, n, w.F2, 256, 256, AM(AM_F2), st));
+            RUN(C_REDUCE, 0, cmf_launch_pair_dirmax(bc, n, pc1, pc2, w.KNN12, 8, AM(AM_DIR), st));
+        }
+        {
+            TcArgs ta_ = tc_plain(T.fc_wc, F, 512, 256, w.E, E_LD, w.U1, 512, nullptr, bn, CMF_ACT_NONE, w.PB1, 512, n);
+            tc_bound(ta_, 0.f, AM(AM_F1), 1.f); if (F) { ta_.amax_out = AM(AM_U1); }
+            RUN(C_GEMM_FC_HOIST, tflops(ta_, 256), cmf_launch_tc_auto(ta_, st));
+        }
+        {
+            TcArgs ta_ = tc_plain(T.fc_wn, F, 512, 256, w.F2, 256, w.U2, 512, nullptr, bn, CMF_ACT_NONE, w.PB2, 512, n);
+            tc_bound(ta_, 0.f, AM(AM_F2), 1.f); if (F) { ta_.amax_out = AM(AM_U2); }
+            RUN(C_GEMM_FC_HOIST, tflops(ta_, 256), cmf_launch_tc_auto(ta_, st));
+        }
         {   // conv1 with the gather + hoisted conv0 epilogue fused into the B-operand producer (no H1 round trip)
-            TcArgs ta_ = tc_plain(m->t_fc_w2, 512, 512, nullptr, 0, w.H2, 512, S(FC_B2), bn * 8, CMF_ACT_LEAKY);
+            TcArgs ta_ = tc_plain(T.fc_w2, F, 512, 512, nullptr, 0, w.H2, 512, S(FC_B2), bn * 8, CMF_ACT_LEAKY, nullptr, 0, (long long)n * 8);
             ta_.prod = TC_PROD_FC_H1; ta_.U1 = w.U1; ta_.U2 = w.U2; ta_.ld_u2 = 512; ta_.off_u2 = 0; ta_.Wsmall = S(FC_WD);
             ta_.xyz_q = pc1; ta_.xyz_c = pc2; ta_.nbr = w.KNN12; ta_.nbr_ld = 8; ta_.nbr_off = 0; ta_.ksamp = 8; ta_.n_pts = n;
-            ta_.out_tiled = 1;                 // conv2's B operand is written TF32-split + swizzled, ready for a bulk copy
+            ta_.out_tiled = 1;                 // conv2's B operand is written split + swizzled, ready for a bulk copy
+            // |leaky(U1[i] + U2[j] + Wd.dir)| <= max|U1| + max|U2| + max_c |Wd[c]|_1 * max|dir component|
+            tc_bound(ta_, 0.f, AM(AM_U1), 1.f, AM(AM_U2), 1.f, AM(AM_DIR), m->wd_l1);
+            ta_.out_mul = m->fc_w2_l1; ta_.out_add = m->fc_b2_max; ta_.out_scale_store = F ? SC(SC_H2) : nullptr;
             RUN(C_GEMM_FC_MLP, tflops(ta_, 512), cmf_launch_tc_auto(ta_, st));
         }
         fused_wsum = cmf_tc_pair_enabled() && !getenv("CMF_NO_WSUM");
         {
-            TcArgs ta_ = tc_plain(m->t_fc_w3, 512, 512, nullptr, 0, fused_wsum ? w.COST1 : w.H1, 512, S(FC_B3), bn * 8, CMF_ACT_LEAKY);
+            TcArgs ta_ = tc_plain(T.fc_w3, F, 512, 512, nullptr, 0, fused_wsum ? w.COST1 : w.H1, 512, S(FC_B3), bn * 8, CMF_ACT_LEAKY, nullptr, 0, (long long)n * 8);
             ta_.prod = TC_PROD_TILED; ta_.Xt = w.H2;
+            tc_scaled(ta_, SC(SC_H2));
             if (fused_wsum) {        // conv2 + LeakyReLU + WeightNet1 weighting + sum over the 8 neighbours in the TMEM epilogue
                 ta_.epi = TC_EPI_WSUM; ta_.ksamp = 8; ta_.n_pts = n; ta_.xyz_q = pc1; ta_.xyz_c = pc2; ta_.nbr = w.KNN12; ta_.nbr_ld = 8; ta_.nbr_off = 0;
                 ta_.wnA1 = S(WN1_BASE); ta_.wna1 = S(WN1_BASE + 1); ta_.wnA2 = S(WN1_BASE + 2); ta_.wna2 = S(WN1_BASE + 3);
@@ -367,7 +417,10 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
     // set-conv #2 (mse_layer2, cmflow.py:87-89)
     { const GemmArgs ga_ = mk(S(M2_WG), 256, w.G1, 256, w.PBM, 2048, S(M2_T1), 2048, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_SC2_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     if (m->tc) {
-        const TcArgs ta_ = tc_plain(m->t_m2_wp, 2048, E_LD, w.E, E_LD, w.P, 2048, nullptr, bn, CMF_ACT_NONE, w.PBM, 2048, n);
+        if (F) RUN(C_REDUCE, 0, cmf_launch_pair_absmax(bc, n, w.E, E_LD, E_LD, AM(AM_E), st));
+        TcArgs ta_ = tc_plain(T.m2_wp, F, 2048, E_LD, w.E, E_LD, w.P, 2048, nullptr, bn, CMF_ACT_NONE, w.PBM, 2048, n);
+        tc_bound(ta_, 0.f, AM(AM_E), 1.f);
+        if (F) { ta_.amax_out = AM(AM_P0); ta_.amax_group = 512; ta_.amax_ld = m->cap_bc; }     // one maximum per scale's 512 channels
         RUN(C_GEMM_SC2_HOIST, tflops(ta_, 771), cmf_launch_tc_auto(ta_, st));
     } else {
         const GemmArgs ga_ = mk(S(M2_WP), E_LD, w.E, E_LD, w.P, 2048, nullptr, 2048, E_LD, bn, CMF_ACT_NONE, w.PBM, 2048, n);
@@ -377,16 +430,20 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
         const int sb = M2_BASE + s * 10;
         if (m->tc) {
             {   // layer 2 (512->256): neighbour gather of the hoisted layer-1 rows + rel-xyz term + ReLU fused into the B producer
-                TcArgs ta_ = tc_plain(m->t_m2_w2[s], 256, 512, nullptr, 0, w.Y2, 256, S(sb + 1), bn * KS[s], CMF_ACT_RELU);
+                TcArgs ta_ = tc_plain(T.m2_w2[s], F, 256, 512, nullptr, 0, w.Y2, 256, S(sb + 1), bn * KS[s], CMF_ACT_RELU, nullptr, 0, (long long)n * KS[s]);
                 ta_.prod = TC_PROD_SC2_Y1; ta_.U1 = nullptr; ta_.U2 = w.P; ta_.ld_u2 = 2048; ta_.off_u2 = s * 512;
                 ta_.Wsmall = S(M2_WX) + (size_t)s * 512 * 4; ta_.xyz_q = pc1; ta_.xyz_c = pc1; ta_.nbr = w.BQ1; ta_.nbr_ld = 60;
                 ta_.nbr_off = KOFF[s]; ta_.ksamp = KS[s]; ta_.n_pts = n;
                 ta_.out_tiled = 1;
+                // |relu(P[j] + Wx.rel)| <= max|P (this scale)| + max_c |Wx[c]|_1 * radius   (every rel component is below the ball radius)
+                tc_bound(ta_, m->wx_l1[s] * RADII[s], AM(AM_P0 + s), 1.f);
+                ta_.out_mul = m->m2_w2_l1[s]; ta_.out_add = m->m2_t2_max[s]; ta_.out_scale_store = F ? SC(SC_Y2 + s) : nullptr;
                 RUN(C_GEMM_SC2_L2, tflops(ta_, 512), cmf_launch_tc_auto(ta_, st));
             }
             {   // layer 3 (256->64) with ReLU + max over the K neighbours fused into the TMEM epilogue; B operand bulk-copied
-                TcArgs ta_ = tc_plain(m->t_m2_w3[s], 64, 256, nullptr, 0, w.M64 + s * 64, 256, S(sb + 3), bn * KS[s], CMF_ACT_RELU);
+                TcArgs ta_ = tc_plain(T.m2_w3[s], F, 64, 256, nullptr, 0, w.M64 + s * 64, 256, S(sb + 3), bn * KS[s], CMF_ACT_RELU, nullptr, 0, (long long)n * KS[s]);
                 ta_.prod = TC_PROD_TILED; ta_.Xt = w.Y2;
+                tc_scaled(ta_, SC(SC_Y2 + s));
                 ta_.epi = TC_EPI_MAXK; ta_.ksamp = KS[s];
                 RUN(C_GEMM_SC2_L3, tflops(ta_, 256), cmf_launch_tc_auto(ta_, st));
             }
@@ -422,7 +479,9 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
     // heads (FlowHead / MotionHead, radarflow_util.py:240-285), first layer stacked [fp ; mp]
     { const GemmArgs ga_ = mk(S(HD_W1G), 256, gvec, 256, w.PBH, 512, S(HD_T1), 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_POINTWISE, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     if (m->tc) {
-        const TcArgs ta_ = tc_plain(m->t_hd_w1, 512, 256, w.PROP, 256, w.HD1, 512, nullptr, bn, CMF_ACT_RELU, w.PBH, 512, n);
+        if (F) RUN(C_REDUCE, 0, cmf_launch_pair_absmax(bc, n, w.PROP, 256, 256, AM(AM_PROP), st));
+        TcArgs ta_ = tc_plain(T.hd_w1, F, 512, 256, w.PROP, 256, w.HD1, 512, nullptr, bn, CMF_ACT_RELU, w.PBH, 512, n);
+        tc_bound(ta_, 0.f, AM(AM_PROP), 1.f);
         RUN(C_GEMM_POINTWISE, tflops(ta_, 256), cmf_launch_tc_auto(ta_, st));
     } else {
         const GemmArgs ga_ = mk(S(HD_W1), 256, w.PROP, 256, w.HD1, 512, nullptr, 512, 256, bn, CMF_ACT_RELU, w.PBH, 512, n);
@@ -477,11 +536,30 @@ extern "C" int cmf_model_create(cmf_model **out, const float *blob, size_t blob_
         off += pad4((size_t)sr * sc);
     }
     m->shape = exp;
+    {   // norms behind the fp16x3 scale bounds (host copy of the blob is still at hand)
+        auto seg_host = [&](int i) { return blob + hdr[3 + 3 * i]; };
+        auto max_row_l1 = [&](int i, int r0, int r1) {
+            const float *W = seg_host(i); const int cols = exp[i].cols;
+            double best = 0;
+            for (int r = r0; r < r1; ++r) { double a = 0; for (int c = 0; c < cols; ++c) a += fabs((double)W[(size_t)r * cols + c]); if (a > best) best = a; }
+            return (float)(best * 1.0001);
+        };
+        auto max_abs = [&](int i) { const float *W = seg_host(i); float b = 0.f; for (int k = 0; k < exp[i].rows * exp[i].cols; ++k) b = fmaxf(b, fabsf(W[k])); return b; };
+        m->wd_l1 = max_row_l1(FC_WD, 0, 512);
+        m->fc_w2_l1 = max_row_l1(FC_W2, 0, 512); m->fc_b2_max = max_abs(FC_B2);
+        for (int s = 0; s < 4; ++s) {
+            m->wx_l1[s] = max_row_l1(M2_WX, s * 512, (s + 1) * 512);
+            m->m2_w2_l1[s] = max_row_l1(M2_BASE + s * 10, 0, 256); m->m2_t2_max[s] = max_abs(M2_BASE + s * 10 + 1);
+        }
+    }
     *out = m;
     const char *fe = getenv("CMF_FUSED_SC1");
     if (fe && fe[0] == '0') m->fused_sc1 = 0;
     const char *env = getenv("CMF_MODE");            // "fp32" (default) | "tf32x3"
-    if (env && !strcmp(env, "tf32x3")) { int rc = cmf_model_set_mode(m, 1); if (rc) { cmf_model_destroy(m); *out = nullptr; return rc; } }
+    if (env && (!strcmp(env, "tf32x3") || !strcmp(env, "fp16x3"))) {
+        int rc = cmf_model_set_mode(m, !strcmp(env, "fp16x3") ? 2 : 1);
+        if (rc) { cmf_model_destroy(m); *out = nullptr; return rc; }
+    }
     return CMF_OK;
 }
 
@@ -491,7 +569,7 @@ extern "C" void cmf_model_destroy(cmf_model *m) {
     if (m->d_blob) cudaFree(m->d_blob);
     if (m->d_in) cudaFree(m->d_in);
     if (m->d_out) cudaFree(m->d_out);
-    if (m->tc_buf) cudaFree(m->tc_buf);
+    for (int f = 0; f < 2; ++f) if (m->tcw[f].buf) cudaFree(m->tcw[f].buf);
     for (cudaEvent_t e : m->pool) cudaEventDestroy(e);
     delete m;
 }
@@ -572,8 +650,8 @@ extern "C" int cmf_model_forward_host(cmf_model *m, int b, int n, const float *p
 
 extern "C" int cmf_model_set_mode(cmf_model *m, int mode) {
     CMF_REQUIRE(m, "null model");
-    CMF_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (strict fp32 FMA) or 1 (tcgen05 3xTF32)");
-    if (mode == 1) { int rc = ensure_tc_weights(m); if (rc) return rc; }
+    CMF_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (strict fp32 FMA), 1 (tcgen05 3xTF32) or 2 (tcgen05 3xFP16)");
+    if (mode) { int rc = ensure_tc_weights(m, mode - 1); if (rc) return rc; }
     m->tc = mode;
     return CMF_OK;
 }

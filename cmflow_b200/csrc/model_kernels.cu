@@ -460,6 +460,50 @@ int cmf_launch_scatter_ft(int b, int n, const float *ft_planar, float *E, int ld
     return CMF_OK;
 }
 
+// ---- per-pair maxima for the fp16x3 operand scales ------------------------------------------------
+__global__ void __launch_bounds__(256)
+pair_absmax_kernel(int n, const float *__restrict__ X, int ld, int width4, unsigned int *__restrict__ out) {
+    const int b = blockIdx.x;
+    const long long total = (long long)n * width4;
+    float mx = 0.f;
+    for (long long t = (long long)blockIdx.y * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.y * blockDim.x) {
+        const int i = (int)(t / width4), c4 = (int)(t - (long long)i * width4);
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(X + ((size_t)b * n + i) * ld) + c4);
+        mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(out + b, __float_as_uint(mx));
+}
+int cmf_launch_pair_absmax(int b, int n, const float *X, int ld, int width, unsigned int *out, cudaStream_t st) {
+    if ((width & 3) || (ld & 3)) { cmf_set_error("pair_absmax: width / ld must be multiples of 4"); return CMF_ERR_INVALID; }
+    const int split = cmf_divup((long long)n * (width / 4), 256 * 8) < 1 ? 1 : cmf_divup((long long)n * (width / 4), 256 * 8);
+    pair_absmax_kernel<<<dim3(b, split), 256, 0, st>>>(n, X, ld, width / 4, out);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+__global__ void __launch_bounds__(256)
+pair_dirmax_kernel(int n, int k, const float *__restrict__ xyzq, const float *__restrict__ xyzc, const int *__restrict__ nbr,
+                   unsigned int *__restrict__ out) {
+    const int b = blockIdx.x;
+    const float *pq = xyzq + (size_t)b * 3 * n, *pc = xyzc + (size_t)b * 3 * n;
+    float mx = 0.f;
+    for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < n * k; t += gridDim.y * blockDim.x) {
+        const int i = t / k;
+        const int j = __ldg(nbr + (size_t)b * n * k + t);
+        mx = fmaxf(mx, fmaxf(fabsf(__fsub_rn(__ldg(pc + j), __ldg(pq + i))),
+                             fmaxf(fabsf(__fsub_rn(__ldg(pc + n + j), __ldg(pq + n + i))), fabsf(__fsub_rn(__ldg(pc + 2 * n + j), __ldg(pq + 2 * n + i))))));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(out + b, __float_as_uint(mx));
+}
+int cmf_launch_pair_dirmax(int b, int n, const float *xyzq_planar, const float *xyzc_planar, const int *nbr, int k, unsigned int *out, cudaStream_t st) {
+    pair_dirmax_kernel<<<dim3(b, cmf_divup((long long)n * k, 256 * 8)), 256, 0, st>>>(n, k, xyzq_planar, xyzc_planar, nbr, out);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
 // =================================================================================================
 // FeatureCorrelator (radarflow_util.py:185-237) after hoisting conv0 over the concat:
 //   conv0([f1_i ; g1 ; f2_j ; g2 ; dir]) = U1[i] + U2[j] + Wd.dir      (U1,U2 carry the per-cloud constants and the bias)

@@ -54,3 +54,8 @@ int cmf_launch_gru_gates(int b, const float *gi, const float *gh, const float *h
 int cmf_launch_kabsch(int b, int n, const float *pc1, const float *pc_or_flow, int second_is_flow, const float *w,
                       int normalise, float eps, float stat_thres, float *trans, float *sf_agg, uint8_t *mask,
                       cudaStream_t st);
+
+// fp16x3 mode: out[b] = max(out[b], bits(max |X[(b*N+i)*ld + c]|, c < width))  (uint bit patterns; caller zeroes)
+int cmf_launch_pair_absmax(int b, int n, const float *X, int ld, int width, unsigned int *out, cudaStream_t st);
+// out[b] = max over points i and their k neighbours j of max(|xc_j - xq_i| per component)
+int cmf_launch_pair_dirmax(int b, int n, const float *xyzq_planar, const float *xyzc_planar, const int *nbr, int k, unsigned int *out, cudaStream_t st);

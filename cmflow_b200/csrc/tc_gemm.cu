@@ -16,15 +16,15 @@
 //   stages (2 x 256 columns) so the epilogue of tile t overlaps the MMAs of tile t+1.  Persistent over tiles.
 #include <stdlib.h>
 
-#include "tc_gemm.cuh"
+#include "tc_dev.cuh"
+
+using namespace tcdev;
 
 namespace {
 
-// Geometry.  One pipeline STAGE holds K = 16 floats (64-byte rows, 64B swizzle): A 128x16 hi+lo (16 KB) + B 256x16 hi+lo (32 KB)
-// = 48 KB, four stages in flight (192 KB).  Finer stages than the swizzle-128 variant buy latency tolerance: the ring
-// holds the same bytes but a slot is recycled every 6 MMAs (768 clk) instead of every 12.
-// TcArgs.k_blocks counts 32-float blocks (what a producer thread handles per iteration = two stages).
-constexpr int BM = 128, BN = 256, SK = 16, PK = 32;
+// Geometry.  One pipeline STAGE holds 64-byte operand rows (64B swizzle): K = 16 floats (fmt 0, 3xTF32) or K = 32 halfs (fmt 1, 3xFP16):
+// A 128 rows hi+lo (16 KB) + B 256 rows hi+lo (32 KB) = 48 KB, four stages in flight (192 KB).
+// TcArgs.k_blocks counts 32-element blocks (what a producer thread handles per iteration = two stages in fmt 0, one in fmt 1).
 constexpr int TILE_A_FLOATS = BM * SK;              // 2048 floats =  8 KB
 constexpr int TILE_B_FLOATS = BN * SK;              // 4096 floats = 16 KB
 constexpr int STAGE_BYTES = (2 * TILE_A_FLOATS + 2 * TILE_B_FLOATS) * 4;   // 48 KB
@@ -32,35 +32,8 @@ constexpr int NSTAGE = 4;
 constexpr int NTHREADS = 512;
 constexpr int SMALL_BYTES = 512 * 16;               // rel-xyz / direction weights (C x 4 floats) of the gather producers
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + SMALL_BYTES;
-constexpr unsigned SPIN_LIMIT = 20000u;         // x 1 ms suspend hint = 20 s before a stuck wait traps
+constexpr uint32_t IDESC_TF32 = make_idesc(BM, BN, 0), IDESC_F16 = make_idesc(BM, BN, 1);
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    unsigned spins = 0;
-    while (!done) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
-        if (!done && ++spins > SPIN_LIMIT) __trap();        // never hang the GPU: fail the launch instead
-    }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -69,128 +42,13 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-// hi = round-to-nearest TF32 (low 13 mantissa bits zero), lo = x - hi (exact)
-__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
-    lo = x - hi;
-}
-
-// Float offset of element (row, kk) inside a K-major [rows x 16] tile with the 64-byte swizzle:
-// rows are 64 bytes, the 16-byte chunk index (2 bits) is XORed with address bits [7,9) = (row >> 1) & 3.
-__host__ __device__ __forceinline__ int sw_off(int row, int kk) { return row * SK + ((((kk >> 2) ^ ((row >> 1) & 3))) << 2) + (kk & 3); }
-
-// K-major, 64B-swizzled operand tile (tile base 1024-aligned): 8-row groups are 512 bytes apart.
-//   bits [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (=32) | [46,48) version=1 | [61,64) layout=4 (SWIZZLE_64B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
-}
-// kind::tf32, fp32 accumulate, A and B K-major, M=128, N=256:
-//   c_format[4,6)=1 (F32) | a_format[7,10)=2 (TF32) | b_format[10,13)=2 | n_dim[17,23)=N>>3 | m_dim[24,29)=M>>4
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-__device__ __forceinline__ float act_apply(float v, int act) {
-    if (act == 1) return fmaxf(v, 0.f);
-    if (act == 2) return v > 0.f ? v : 0.1f * v;
-    return v;
-}
-
-template <int KSAMP>
-__device__ __forceinline__ void maxk_groups(const uint32_t (&r)[32], float bias, long long cbase, int m, bool m_ok, const TcArgs &a) {
-#pragma unroll
-    for (int g0 = 0; g0 < 32; g0 += KSAMP) {
-        float mx = 0.f;                                            // relu output >= 0
-#pragma unroll
-        for (int e = 0; e < KSAMP; ++e) mx = fmaxf(mx, __uint_as_float(r[g0 + e]) + bias);
-        const long long c = cbase + g0;
-        if (c < a.cols && m_ok) a.Out[(size_t)(c / KSAMP) * a.ldo + m] = mx;
-    }
-}
-
-struct RowCtx {          // per-producer-thread description of its activation row for the current tile
-    bool valid;
-    const float *src0, *src1;      // PLAIN: src0 ; FC_H1: src0 = U1 row (centre point), src1 = U2 row (neighbour) ; SC2_Y1: src1 = P row
-    float dx, dy, dz;
-};
-
-__device__ __forceinline__ RowCtx make_row(const TcArgs &a, long long c) {
-    RowCtx r;
-    r.valid = c < a.cols;
-    r.src0 = r.src1 = nullptr; r.dx = r.dy = r.dz = 0.f;
-    if (!r.valid) return r;
-    if (a.prod == TC_PROD_PLAIN) { r.src0 = a.X + (size_t)c * a.ldx; return r; }
-    const long long bi = c / a.ksamp;
-    const int kk = (int)(c - bi * a.ksamp);
-    const int b = (int)(bi / a.n_pts), i = (int)(bi - (long long)b * a.n_pts);
-    const int j = __ldg(a.nbr + (size_t)bi * a.nbr_ld + a.nbr_off + kk);
-    const float *pq = a.xyz_q + (size_t)b * 3 * a.n_pts, *pc = a.xyz_c + (size_t)b * 3 * a.n_pts;
-    r.dx = __fsub_rn(__ldg(pc + j), __ldg(pq + i));
-    r.dy = __fsub_rn(__ldg(pc + a.n_pts + j), __ldg(pq + a.n_pts + i));
-    r.dz = __fsub_rn(__ldg(pc + 2 * a.n_pts + j), __ldg(pq + 2 * a.n_pts + i));
-    r.src0 = a.U1 ? a.U1 + (size_t)bi * 512 : nullptr;
-    r.src1 = a.U2 + ((size_t)b * a.n_pts + j) * a.ld_u2 + a.off_u2;
-    return r;
-}
-
-// One 32-float block of this thread's (gathered) row, BEFORE the tf32 split: 128 contiguous bytes.  For FC_H1 the
-// centre-point row is shared by the 8 consecutive rows of a point: each of those 8 lanes fetches one 16-byte chunk of it
-// (`u`) and the chunks are exchanged by shuffle at store time.
-template <int PROD>
-__device__ __forceinline__ void load_row(const RowCtx &r, int kb, int sub, float4 (&v)[8], float4 &u) {
-    if (!r.valid) return;
-    const float *src = (PROD == TC_PROD_PLAIN ? r.src0 : r.src1) + kb * PK;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = __ldg(reinterpret_cast<const float4 *>(src) + q);
-    if (PROD == TC_PROD_FC_H1) u = __ldg(reinterpret_cast<const float4 *>(r.src0 + kb * PK) + sub);
-}
-
-__device__ __forceinline__ float small_term(const float4 *sW, int ch, const RowCtx &r) {
-    const float4 w = sW[ch];                                   // shared-memory broadcast (all 32 lanes read the same channel)
-    return fmaf(w.z, r.dz, fmaf(w.y, r.dy, w.x * r.dx));
-}
-
-// transform + split + swizzled store of half a 32-block (chunks q0..q0+3) into one stage's B tiles
-template <int PROD>
-__device__ __forceinline__ void store_half(const float4 *sW, const RowCtx &r, int kb, int row, int lane, int half,
-                                           const float4 (&v)[8], const float4 &u, float *Bhi, float *Blo) {
-    const int k0 = kb * PK + half * SK;
-#pragma unroll
-    for (int qq = 0; qq < 4; ++qq) {
-        const int q = half * 4 + qq;
-        float x[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
-        if (PROD == TC_PROD_FC_H1) {
-            const int srcl = (lane & ~7) + q;                     // the lane of this point's group that holds chunk q of the centre row
-            const float uu[4] = {__shfl_sync(0xffffffffu, u.x, srcl), __shfl_sync(0xffffffffu, u.y, srcl),
-                                 __shfl_sync(0xffffffffu, u.z, srcl), __shfl_sync(0xffffffffu, u.w, srcl)};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) x[e] = act_apply(uu[e] + x[e] + small_term(sW, k0 + qq * 4 + e, r), 2);
-        } else if (PROD == TC_PROD_SC2_Y1) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e] + small_term(sW, k0 + qq * 4 + e, r), 0.f);
-        }
-        if (!r.valid) { x[0] = x[1] = x[2] = x[3] = 0.f; }
-        float4 h, l;
-        split_tf32(x[0], h.x, l.x); split_tf32(x[1], h.y, l.y); split_tf32(x[2], h.z, l.z); split_tf32(x[3], h.w, l.w);
-        const int off = sw_off(row, qq * 4);
-        *reinterpret_cast<float4 *>(Bhi + off) = h;
-        *reinterpret_cast<float4 *>(Blo + off) = l;
-    }
-}
-
-template <int PROD>
+template <int PROD, int F16>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -210,7 +68,8 @@ tc_gemm_kernel(const TcArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long col_tiles = (a.cols + BN - 1) / BN;
     const long long ntiles = col_tiles * a.m_blocks;
-    const int nks = a.k_blocks * 2;                               // 16-float stages per tile
+    constexpr int SPB = F16 ? 1 : 2;                              // pipeline stages per 32-element K block
+    const int nks = a.k_blocks * SPB;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
@@ -274,9 +133,15 @@ tc_gemm_kernel(const TcArgs a) {
 #pragma unroll
                     for (int k8 = 0; k8 < SK / 8; ++k8) {
                         const uint64_t adv = (uint64_t)(k8 * 32 >> 4);      // 32 bytes per K=8 step inside the swizzle atom
-                        tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, IDESC, (ks | k8) ? 1u : 0u);
-                        tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
-                        tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1u);
+                        if (F16) {
+                            tc_mma_f16(d_tmem, a_lo + adv, b_hi + adv, IDESC_F16, (ks | k8) ? 1u : 0u);
+                            tc_mma_f16(d_tmem, a_hi + adv, b_lo + adv, IDESC_F16, 1u);
+                            tc_mma_f16(d_tmem, a_hi + adv, b_hi + adv, IDESC_F16, 1u);
+                        } else {
+                            tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, IDESC_TF32, (ks | k8) ? 1u : 0u);
+                            tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, IDESC_TF32, 1u);
+                            tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, IDESC_TF32, 1u);
+                        }
                     }
                     tc_commit(empty_bar(stage));                              // frees the smem stage when these MMAs retire
                     if (ks == nks - 1) tc_commit(tfull_bar(acc));             // accumulator complete
@@ -297,54 +162,16 @@ tc_gemm_kernel(const TcArgs a) {
             const int m = mb * BM + q * 32 + lane;
             const bool m_ok = m < a.M;
             const float bias = (a.bias && m_ok) ? __ldg(a.bias + m) : 0.f;
-            // per-pair bias: track the pair of the current column incrementally (no division per element)
-            long long pair = 0, pair_end = 0x7fffffffffffffffLL;
-            float pb = 0.f;
-            if (a.pbias) {
-                pair = c0 / a.cols_per_pair; pair_end = (pair + 1) * (long long)a.cols_per_pair;
-                if (m_ok) pb = __ldg(a.pbias + (size_t)pair * a.pb_ld + m);
-            }
+            EpiState es = epi_begin(a, c0, m, m_ok);
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
 #pragma unroll 1
             for (int cc = 0; cc < BN; cc += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cc, r);
-                if (a.epi == TC_EPI_STORE && a.out_tiled) {
-                    // next GEMM's B operand, already TF32-split and swizzled: tile (col_tile, 16-block = m/16), row = column in tile
-                    float *tb = a.Out + ((size_t)ct * (a.M >> 4) + (m >> 4)) * (2 * TILE_B_FLOATS);
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const long long c = c0 + cc + e;
-                        if (c >= pair_end) {
-                            ++pair; pair_end += a.cols_per_pair;
-                            if (c < a.cols) pb = __ldg(a.pbias + (size_t)pair * a.pb_ld + m);
-                        }
-                        const float v = c < a.cols ? act_apply(__uint_as_float(r[e]) + bias + pb, a.act) : 0.f;
-                        float hi, lo;
-                        split_tf32(v, hi, lo);
-                        const int off = sw_off(cc + e, m & 15);
-                        tb[off] = hi;
-                        tb[TILE_B_FLOATS + off] = lo;
-                    }
-                } else if (a.epi == TC_EPI_STORE) {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const long long c = c0 + cc + e;
-                        if (c >= pair_end) {                                  // warp-uniform: crossed into the next frame pair
-                            ++pair; pair_end += a.cols_per_pair;
-                            if (m_ok && c < a.cols) pb = __ldg(a.pbias + (size_t)pair * a.pb_ld + m);
-                        }
-                        if (c < a.cols && m_ok) a.Out[(size_t)c * a.ldo + m] = act_apply(__uint_as_float(r[e]) + bias + pb, a.act);
-                    }
-                } else if (a.epi == TC_EPI_MAXK) {
-                    // relu(acc + bias) then max over each group of `ksamp` consecutive rows (one point's neighbours); ksamp | 32
-                    if (a.ksamp == 4) maxk_groups<4>(r, bias, c0 + cc, m, m_ok, a);
-                    else if (a.ksamp == 8) maxk_groups<8>(r, bias, c0 + cc, m, m_ok, a);
-                    else if (a.ksamp == 16) maxk_groups<16>(r, bias, c0 + cc, m, m_ok, a);
-                    else maxk_groups<32>(r, bias, c0 + cc, m, m_ok, a);
-                }
+                epilogue_chunk(a, r, ct, c0, cc, m, m_ok, bias, es, TILE_B_FLOATS);
             }
+            epi_end(a, es, m);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -368,10 +195,11 @@ tc_gemm_kernel(const TcArgs a) {
                     if (kb + 1 < a.k_blocks) load_row<PROD>(rc, kb + 1, lane & 7, vn, un);
                     else if (tn < ntiles) { rcn = make_row(a, (tn / a.m_blocks) * BN + row); load_row<PROD>(rcn, 0, lane & 7, vn, un); }
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
+                    for (int half = 0; half < SPB; ++half) {
                         mbar_wait(empty_bar(stage), phase ^ 1);
-                        float *Bhi = reinterpret_cast<float *>(smem + stage * STAGE_BYTES + 2 * TILE_A_FLOATS * 4);
-                        store_half<PROD>(sW, rc, kb, row, lane, half, v, u, Bhi, Bhi + TILE_B_FLOATS);
+                        uint8_t *Bb = smem + stage * STAGE_BYTES + 2 * TILE_A_FLOATS * 4;
+                        if (F16) store_row_f16<PROD>(sW, rc, kb, row, lane, v, u, Bb, Bb + TILE_B_FLOATS * 4);
+                        else store_half<PROD>(sW, rc, kb, row, lane, half, v, u, reinterpret_cast<float *>(Bb), reinterpret_cast<float *>(Bb) + TILE_B_FLOATS);
                         fence_async_smem();                                   // generic-proxy writes -> visible to the tensor core (async proxy)
                         __syncwarp();
                         if (lane == 0) mbar_arrive(full_bar(stage));
@@ -413,6 +241,49 @@ __global__ void tile_weights_kernel(const float *__restrict__ W, int ldw, int M,
     dst[TILE_A_FLOATS + off] = lo;
 }
 
+// fmt 1: per-row power-of-two scale (a_inv[m] = 1/scale; padded rows get 1)
+__global__ void weight_row_scale_kernel(const float *__restrict__ W, int ldw, int M, int K, int m_rows_padded, float *__restrict__ a_inv) {
+    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (m >= m_rows_padded) return;
+    float mx = 0.f;
+    if (m < M)
+        for (int k = lane; k < K; k += 32) mx = fmaxf(mx, fabsf(W[(size_t)m * ldw + k]));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    if (lane == 0) a_inv[m] = 1.f / pow2_scale(mx);
+}
+// W (M x K) -> tiles [m_block][32-block]{hi, lo}; tile = 128 rows x 32 halfs (64-byte rows), half element (r, kk) at byte sw_off_h(r, kk)
+__global__ void tile_weights_f16_kernel(const float *__restrict__ W, int ldw, int M, int K, int m_blocks, int nks, const float *__restrict__ a_inv,
+                                        float *__restrict__ Wt) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)m_blocks * nks * (BM * PK);
+    if (t >= total) return;
+    const int e = (int)(t % (BM * PK));
+    const long long tile = t / (BM * PK);
+    const int ks = (int)(tile % nks), mb = (int)(tile / nks);
+    const int r = e / PK, kk = e % PK;
+    const int m = mb * BM + r, k = ks * PK + kk;
+    const float x = (m < M && k < K) ? W[(size_t)m * ldw + k] * (1.f / a_inv[m]) : 0.f;      // exact: power-of-two scale
+    unsigned short hi, lo;
+    split_f16(x, hi, lo);
+    uint8_t *dst = reinterpret_cast<uint8_t *>(Wt + (size_t)tile * (2 * TILE_A_FLOATS));
+    const int off = sw_off_h(r, kk);
+    *reinterpret_cast<unsigned short *>(dst + off) = hi;
+    *reinterpret_cast<unsigned short *>(dst + TILE_A_FLOATS * 4 + off) = lo;
+}
+
+template <int PROD>
+cudaError_t set_smem1() {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<PROD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tc_gemm_kernel<PROD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+}
+template <int PROD>
+void launch1(const TcArgs &a, int grid, cudaStream_t st) {
+    if (a.fmt == 1) tc_gemm_kernel<PROD, 1><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
+    else tc_gemm_kernel<PROD, 0><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
+}
+
 }  // namespace
 
 size_t cmf_tc_act_tiled_floats(long long cols, int C) {
@@ -431,14 +302,24 @@ int cmf_tc_tile_weights(const float *W, int ldw, int M, int K, float *Wt, cudaSt
     return CMF_OK;
 }
 
+int cmf_tc_tile_weights_f16(const float *W, int ldw, int M, int K, float *Wt, float *a_inv, cudaStream_t st) {
+    const int mb = cmf_divup(M, BM), nks = cmf_divup(K, PK);
+    weight_row_scale_kernel<<<cmf_divup(mb * BM, 8), 256, 0, st>>>(W, ldw, M, K, mb * BM, a_inv);
+    CMF_LAUNCH_CHECK();
+    const long long total = (long long)mb * nks * (BM * PK);
+    tile_weights_f16_kernel<<<cmf_divup(total, 256), 256, 0, st>>>(W, ldw, M, K, mb, nks, a_inv, Wt);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
 int cmf_launch_tc_gemm(const TcArgs &a, cudaStream_t st) {
     static int num_sms = 0;
     static bool attr_set = false;
     if (!attr_set) {
-        CMF_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TC_PROD_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        CMF_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TC_PROD_FC_H1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        CMF_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TC_PROD_SC2_Y1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        CMF_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TC_PROD_TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CMF_CUDA(set_smem1<TC_PROD_PLAIN>());
+        CMF_CUDA(set_smem1<TC_PROD_FC_H1>());
+        CMF_CUDA(set_smem1<TC_PROD_SC2_Y1>());
+        CMF_CUDA(set_smem1<TC_PROD_TILED>());
         int dev = 0;
         CMF_CUDA(cudaGetDevice(&dev));
         CMF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -448,12 +329,14 @@ int cmf_launch_tc_gemm(const TcArgs &a, cudaStream_t st) {
     if (a.out_tiled && ((a.M & 127) || a.epi != TC_EPI_STORE)) { cmf_set_error("tc_gemm: tiled output needs M % 128 == 0 and the STORE epilogue"); return CMF_ERR_INVALID; }
     if (a.epi == TC_EPI_MAXK && a.ksamp != 4 && a.ksamp != 8 && a.ksamp != 16 && a.ksamp != 32) { cmf_set_error("tc_gemm: MAXK needs ksamp in {4,8,16,32}"); return CMF_ERR_INVALID; }
     if (a.prod == TC_PROD_FC_H1 && a.ksamp != 8) { cmf_set_error("tc_gemm: the flow-embedding producer assumes 8 neighbours per point"); return CMF_ERR_INVALID; }
+    if ((a.pbias || a.bs_mode || a.amax_out) && a.cols_per_pair <= 0) { cmf_set_error("tc_gemm: cols_per_pair must be set"); return CMF_ERR_INVALID; }
+    if (a.amax_out && a.amax_group <= 0) { cmf_set_error("tc_gemm: amax_group must be positive"); return CMF_ERR_INVALID; }
     const long long ntiles = ((a.cols + BN - 1) / BN) * a.m_blocks;
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
-    if (a.prod == TC_PROD_PLAIN) tc_gemm_kernel<TC_PROD_PLAIN><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
-    else if (a.prod == TC_PROD_FC_H1) tc_gemm_kernel<TC_PROD_FC_H1><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
-    else if (a.prod == TC_PROD_TILED) tc_gemm_kernel<TC_PROD_TILED><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
-    else tc_gemm_kernel<TC_PROD_SC2_Y1><<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
+    if (a.prod == TC_PROD_PLAIN) launch1<TC_PROD_PLAIN>(a, grid, st);
+    else if (a.prod == TC_PROD_FC_H1) launch1<TC_PROD_FC_H1>(a, grid, st);
+    else if (a.prod == TC_PROD_TILED) launch1<TC_PROD_TILED>(a, grid, st);
+    else launch1<TC_PROD_SC2_Y1>(a, grid, st);
     CMF_LAUNCH_CHECK();
     return CMF_OK;
 }
@@ -469,22 +352,33 @@ int cmf_launch_tc_auto(const TcArgs &a, cudaStream_t st) {
     return cmf_launch_tc_gemm(a, st);
 }
 
-// ---- test doorway: plain 3xTF32 GEMM through the C ABI (tests/test_gpu_tc_gemm.py) --------------------------------
+// ---- test doorway: plain split-precision GEMM through the C ABI (tests/test_gpu_tc_gemm.py) --------------------------------
 static long long *g_test_dbg = nullptr;
 extern "C" void cmf_test_tc_set_dbg(long long *dbg) { g_test_dbg = dbg; }      // device buffer long long[grid][8] or NULL
 
-extern "C" int cmf_test_tc_gemm(int M, int K, long long cols, const float *W, int ldw, const float *X, int ldx,
-                                const float *bias, int act, float *Out, int ldo, float *scratch_tiles, void *stream) {
+extern "C" int cmf_test_tc_gemm_fmt(int fmt, int M, int K, long long cols, const float *W, int ldw, const float *X, int ldx,
+                                    const float *bias, int act, float *Out, int ldo, float *scratch_tiles,
+                                    int cols_per_pair, const float *amax_in, unsigned int *amax_out, void *stream) {
     CMF_REQUIRE(W && X && Out && scratch_tiles, "null pointer");
+    CMF_REQUIRE(fmt == 0 || fmt == 1, "fmt must be 0 (3xTF32) or 1 (3xFP16)");
     CMF_REQUIRE((ldx & 3) == 0 && ldx >= cmf_divup(K, PK) * PK, "ldx must be a multiple of 4 and cover K padded to 32");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = cmf_tc_tile_weights(W, ldw, M, K, scratch_tiles, st);
+    float *a_inv = scratch_tiles + cmf_tc_tiled_floats(M, K);
+    int rc = fmt == 1 ? cmf_tc_tile_weights_f16(W, ldw, M, K, scratch_tiles, a_inv, st) : cmf_tc_tile_weights(W, ldw, M, K, scratch_tiles, st);
     if (rc) return rc;
     TcArgs a{};
     a.Wt = scratch_tiles; a.m_blocks = cmf_divup(M, BM); a.k_blocks = cmf_divup(K, PK); a.M = M; a.cols = cols;
     a.prod = TC_PROD_PLAIN; a.X = X; a.ldx = ldx;
-    a.epi = TC_EPI_STORE; a.Out = Out; a.ldo = ldo; a.bias = bias; a.pbias = nullptr; a.act = act; a.cols_per_pair = 1;
+    a.epi = TC_EPI_STORE; a.Out = Out; a.ldo = ldo; a.bias = bias; a.pbias = nullptr; a.act = act;
+    a.cols_per_pair = cols_per_pair > 0 ? cols_per_pair : 1;
+    a.fmt = fmt; a.a_inv = fmt == 1 ? a_inv : nullptr;
+    if (fmt == 1 && amax_in) { a.bs_mode = 1; a.bs_src[0] = amax_in; a.bs_coef[0] = 1.f; }
+    a.amax_out = amax_out; a.amax_group = 1 << 30; a.amax_ld = 0;
     a.dbg = g_test_dbg;
     return cmf_launch_tc_auto(a, st);
 }
-extern "C" size_t cmf_test_tc_tiled_floats(int M, int K) { return cmf_tc_tiled_floats(M, K); }
+extern "C" int cmf_test_tc_gemm(int M, int K, long long cols, const float *W, int ldw, const float *X, int ldx,
+                                const float *bias, int act, float *Out, int ldo, float *scratch_tiles, void *stream) {
+    return cmf_test_tc_gemm_fmt(0, M, K, cols, W, ldw, X, ldx, bias, act, Out, ldo, scratch_tiles, 1, nullptr, nullptr, stream);
+}
+extern "C" size_t cmf_test_tc_tiled_floats(int M, int K) { return cmf_tc_tiled_floats(M, K) + (size_t)cmf_divup(M, BM) * BM; }

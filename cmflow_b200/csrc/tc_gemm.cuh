@@ -27,14 +27,32 @@ struct TcArgs {
     // WSUM epilogue (flow embedding, radarflow_util.py:215-225): Out[point][m] = sum_k WeightNet(dir_ik)[m] * act(acc + bias)[column (point,k)]
     // WeightNet = 3 -> 8 -> 8 -> C, ReLU after every layer; dir = xyz_c[nbr] - xyz_q[point]; ksamp neighbours per point (pair kernel, TILED producer only)
     const float *wnA1, *wna1, *wnA2, *wna2, *wnA3, *wna3;
+    // ---- operand format ----------------------------------------------------------------------------------------------------------
+    // fmt 0: 3xTF32 (kind::tf32, K = 16 floats per 64-byte stage row).  fmt 1: 3xFP16 (kind::f16, K = 32 halfs per 64-byte stage row):
+    // same 22-bit split (11 + 11 significand bits) at twice the tensor rate and half the operand bytes; fp16's 5-bit exponent is
+    // handled by exact power-of-two scaling: weight row m is stored times 2^e(m) (a_inv[m] = 2^-e(m)), the activation rows of frame
+    // pair p times b_scale(p), and the epilogue multiplies the accumulator by a_inv[m] / b_scale(p) before bias / activation.
+    int fmt;
+    const float *a_inv;                                          // fmt 1: per-output-channel 1/scale of the tiled weights (NULL = 1)
+    // b_scale(p): bs_mode 0 -> 1; 1 -> pow2_scale(bound(p)), bound(p) = bs_const + sum_i bs_coef[i] * bs_src[i][p] (a rigorous
+    // per-pair bound on |activation| built from measured per-pair maxima of the upstream tensors); 2 -> bs_src[0][p] holds the scale
+    int bs_mode;
+    const float *bs_src[3]; float bs_coef[3]; float bs_const;
+    // tiled output (fmt 1): scale(p) = pow2_scale(out_mul * bound(p) + out_add) (out_mul = max_m |W[m]|_1, out_add = max_m |bias[m]|),
+    // also written to out_scale_store[p] for the consuming GEMM (bs_mode 2)
+    float out_mul, out_add; float *out_scale_store;
+    // row-major STORE epilogue: atomicMax of |out| per frame pair into amax_out[(m / amax_group) * amax_ld + p] (uint bits; NULL = off)
+    unsigned int *amax_out; int amax_group, amax_ld;
     // optional wait-time instrumentation (pair kernel): long long[gridDim.x][8] cycles = {total, mma:tempty, mma:full, mma:peer_full,
     // loader:empty, producer(warp 8):empty, epilogue(warp 4):tfull, tiles}; NULL in production
     long long *dbg;
 };
 
-size_t cmf_tc_tiled_floats(int M, int K);
-size_t cmf_tc_act_tiled_floats(long long cols, int C);                          // floats of a tiled activation buffer (cols x C channels)                                        // floats needed for the pre-tiled copy of an M x K matrix
+size_t cmf_tc_tiled_floats(int M, int K);                                      // floats needed for the pre-tiled copy of an M x K matrix (either format)
+size_t cmf_tc_act_tiled_floats(long long cols, int C);                          // floats of a tiled activation buffer (cols x C channels; sized for fmt 0, fmt 1 uses half)
 int cmf_tc_tile_weights(const float *W, int ldw, int M, int K, float *Wt, cudaStream_t st);
+// fmt 1: a_inv (M floats, rounded up to 128) receives 2^-e(m); Wt receives the fp16 hi/lo tiles of W[m][:] * 2^e(m)
+int cmf_tc_tile_weights_f16(const float *W, int ldw, int M, int K, float *Wt, float *a_inv, cudaStream_t st);
 int cmf_launch_tc_gemm(const TcArgs &a, cudaStream_t st);      // one CTA per 128 x 256 tile
 int cmf_launch_tc_gemm2(const TcArgs &a, cudaStream_t st);     // CTA pair (cta_group::2) per 256 x 256 tile; needs M % 256 == 0
 int cmf_tc_pair_enabled();

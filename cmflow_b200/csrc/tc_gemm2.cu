@@ -34,7 +34,7 @@ constexpr int NTHREADS = 512;
 constexpr int SMALL_BYTES = 512 * 16;
 constexpr int H2_BYTES = 2 * BN * 8 * 4;              // WSUM: WeightNet hidden vectors (8 floats) of the 256 columns, per accumulator stage
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 + 256 + SMALL_BYTES + H2_BYTES;
-constexpr uint32_t IDESC2 = make_idesc(256, BN);
+constexpr uint32_t IDESC2_TF32 = make_idesc(256, BN, 0), IDESC2_F16 = make_idesc(256, BN, 1);
 
 __device__ __forceinline__ void tc_commit2_mc(uint32_t bar) {      // arrive on `bar` in BOTH CTAs when all prior MMAs of this thread retire
     const uint16_t mask = 3;
@@ -46,7 +46,14 @@ __device__ __forceinline__ void tc_mma2_tf32(uint32_t d_tmem, uint64_t a_desc, u
                  ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-template <int PROD>
+__device__ __forceinline__ void tc_mma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// F16 = 0: 3xTF32, one pipeline stage = 16 floats of K;  F16 = 1: 3xFP16, one stage = 32 halfs of K (same bytes, see tc_dev.cuh)
+template <int PROD, int F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 tc_gemm2_kernel(const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -77,7 +84,8 @@ tc_gemm2_kernel(const TcArgs a) {
     const int m_pairs = a.m_blocks >> 1;
     const long long ntiles = col_tiles * m_pairs;
     const long long cl_id = blockIdx.x >> 1, n_cl = gridDim.x >> 1;
-    const int nks = a.k_blocks * 2;
+    constexpr int SPB = F16 ? 1 : 2;                              // pipeline stages per 32-element K block
+    const int nks = a.k_blocks * SPB;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
@@ -143,9 +151,15 @@ tc_gemm2_kernel(const TcArgs a) {
 #pragma unroll
                         for (int k8 = 0; k8 < SK / 8; ++k8) {
                             const uint64_t adv = (uint64_t)(k8 * 32 >> 4);
-                            tc_mma2_tf32(d_tmem, a_lo + adv, b_hi + adv, IDESC2, (ks | k8) ? 1u : 0u);
-                            tc_mma2_tf32(d_tmem, a_hi + adv, b_lo + adv, IDESC2, 1u);
-                            tc_mma2_tf32(d_tmem, a_hi + adv, b_hi + adv, IDESC2, 1u);
+                            if (F16) {
+                                tc_mma2_f16(d_tmem, a_lo + adv, b_hi + adv, IDESC2_F16, (ks | k8) ? 1u : 0u);
+                                tc_mma2_f16(d_tmem, a_hi + adv, b_lo + adv, IDESC2_F16, 1u);
+                                tc_mma2_f16(d_tmem, a_hi + adv, b_hi + adv, IDESC2_F16, 1u);
+                            } else {
+                                tc_mma2_tf32(d_tmem, a_lo + adv, b_hi + adv, IDESC2_TF32, (ks | k8) ? 1u : 0u);
+                                tc_mma2_tf32(d_tmem, a_hi + adv, b_lo + adv, IDESC2_TF32, 1u);
+                                tc_mma2_tf32(d_tmem, a_hi + adv, b_hi + adv, IDESC2_TF32, 1u);
+                            }
                         }
                         tc_commit2_mc(empty_bar(stage));
                         if (ks == nks - 1) tc_commit2_mc(tfull_bar(acc));
@@ -196,8 +210,13 @@ tc_gemm2_kernel(const TcArgs a) {
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cc, r);
                 if (a.epi == TC_EPI_WSUM) {
                     const float4 *hv = reinterpret_cast<const float4 *>(h2s + ((size_t)acc * BN + cc) * 8);
+                    if (es.track && c0 + cc >= es.pair_end) epi_advance(a, es, c0 + cc, m, m_ok);
+                    const bool one_pair = (c0 + cc + 32 <= a.cols) && (c0 + cc + 32 <= es.pair_end);
 #pragma unroll
-                    for (int g0 = 0; g0 < 32; g0 += 8) {             // one point = 8 consecutive columns
+                    for (int g0 = 0; g0 < 32; g0 += 8) {             // one point = 8 consecutive columns (always inside one frame pair)
+                        const long long c = c0 + cc + g0;
+                        float inv = es.inv;
+                        if (F16 && !one_pair && c < a.cols) inv = es.ainv * __frcp_rn(b_scale_of(a, c / a.cols_per_pair));
                         float sum = 0.f;
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
@@ -205,9 +224,8 @@ tc_gemm2_kernel(const TcArgs a) {
                             float w = w3c;
                             w = fmaf(w3a.x, ha.x, w); w = fmaf(w3a.y, ha.y, w); w = fmaf(w3a.z, ha.z, w); w = fmaf(w3a.w, ha.w, w);
                             w = fmaf(w3b.x, hb.x, w); w = fmaf(w3b.y, hb.y, w); w = fmaf(w3b.z, hb.z, w); w = fmaf(w3b.w, hb.w, w);
-                            sum = fmaf(fmaxf(w, 0.f), act_apply(__uint_as_float(r[g0 + e]) + bias, a.act), sum);
+                            sum = fmaf(fmaxf(w, 0.f), act_apply(fmaf(__uint_as_float(r[g0 + e]), inv, bias), a.act), sum);
                         }
-                        const long long c = c0 + cc + g0;
                         if (c < a.cols && m_ok) a.Out[(size_t)(c >> 3) * a.ldo + m] = sum;
                     }
                 } else {
@@ -216,6 +234,7 @@ tc_gemm2_kernel(const TcArgs a) {
             }
             tc_fence_before();
             __syncwarp();
+            epi_end(a, es, m);
             if (lane == 0) {
                 if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote(tempty_bar(acc), 0);
                 if (a.epi == TC_EPI_WSUM) mbar_arrive(h2empty_bar(acc));
@@ -228,7 +247,7 @@ tc_gemm2_kernel(const TcArgs a) {
         // Mapping: lane = (row-in-group-of-4, chunk): lane l handles 16-byte chunk q = l & 7 of rows  w*16 + 4*i + (l >> 3), i = 0..3.
         // Eight lanes read one 128-byte row slice -> every LDG.128 is fully coalesced (4 lines per warp instruction instead of 32),
         // and a thread's four channels are the same for all of its rows, so their rel-xyz weights are fetched once per iteration.
-        struct SCtx { const float *s1; const float *s0; float dx, dy, dz; int valid; };
+        struct SCtx { const float *s1; const float *s0; float dx, dy, dz; float scale; };      // scale = 0 marks an out-of-range row
         SCtx *sctx = reinterpret_cast<SCtx *>(h2s);                 // overlays the WSUM buffer (WSUM implies the TILED producer)
         const int p = threadIdx.x - 256;
         const int pw = p >> 5;                                     // producer warp 0..7 -> rows pw*16 .. pw*16+15
@@ -238,7 +257,7 @@ tc_gemm2_kernel(const TcArgs a) {
             if (p < HALF_N) {
                 const RowCtx rc = make_row(a, (tt / m_pairs) * BN + rank * HALF_N + p);
                 SCtx c;
-                c.s1 = (PROD == TC_PROD_PLAIN) ? rc.src0 : rc.src1; c.s0 = rc.src0; c.dx = rc.dx; c.dy = rc.dy; c.dz = rc.dz; c.valid = rc.valid ? 1 : 0;
+                c.s1 = (PROD == TC_PROD_PLAIN) ? rc.src0 : rc.src1; c.s0 = rc.src0; c.dx = rc.dx; c.dy = rc.dy; c.dz = rc.dz; c.scale = rc.valid ? rc.scale : 0.f;
                 sctx[buf * HALF_N + p] = c;
             }
         };
@@ -246,7 +265,7 @@ tc_gemm2_kernel(const TcArgs a) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const SCtx &c = sctx[buf * HALF_N + pw * 16 + i * 4 + rsub];
-                if (c.valid) {
+                if (c.scale != 0.f) {
                     v[i] = __ldg(reinterpret_cast<const float4 *>(c.s1 + kb * PK) + q);
                     if (PROD == TC_PROD_FC_H1) u[i] = __ldg(reinterpret_cast<const float4 *>(c.s0 + kb * PK) + q);
                 }
@@ -270,10 +289,10 @@ tc_gemm2_kernel(const TcArgs a) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) w4[e] = sW[kb * PK + q * 4 + e];
                     }
-                    const int st0 = stage, st1 = stage + 1;         // NSTAGE is even: a 32-block never wraps between its two stages
+                    const int st0 = stage, st1 = stage + SPB - 1;   // fmt 0: NSTAGE is even, a 32-block never wraps between its two stages
                     TIMED(dw0, mbar_wait(empty_bar(st0), phase ^ 1));
-                    TIMED(dw0, mbar_wait(empty_bar(st1), phase ^ 1));
-                    float *Bhi = reinterpret_cast<float *>(smem + (q < 4 ? st0 : st1) * STAGE_BYTES + 2 * TILE_A_FLOATS * 4);
+                    if (!F16) TIMED(dw0, mbar_wait(empty_bar(st1), phase ^ 1));
+                    float *Bhi = reinterpret_cast<float *>(smem + ((F16 || q < 4) ? st0 : st1) * STAGE_BYTES + 2 * TILE_A_FLOATS * 4);
                     float *Blo = Bhi + TILE_BH_FLOATS;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -288,17 +307,25 @@ tc_gemm2_kernel(const TcArgs a) {
 #pragma unroll
                             for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e] + fmaf(w4[e].z, c.dz, fmaf(w4[e].y, c.dy, w4[e].x * c.dx)), 0.f);
                         }
-                        if (!c.valid) { x[0] = x[1] = x[2] = x[3] = 0.f; }
-                        float4 h4, l4;
-                        split_tf32(x[0], h4.x, l4.x); split_tf32(x[1], h4.y, l4.y); split_tf32(x[2], h4.z, l4.z); split_tf32(x[3], h4.w, l4.w);
-                        const int off = sw_off(row, (q & 3) * 4);
-                        *reinterpret_cast<float4 *>(Bhi + off) = h4;
-                        *reinterpret_cast<float4 *>(Blo + off) = l4;
+                        if (c.scale == 0.f) { x[0] = x[1] = x[2] = x[3] = 0.f; }
+                        if (F16) {
+                            uint2 h2, l2;             // this thread's four halfs: bytes [8*(q&1), +8) of 16-byte chunk q>>1 of the 64-byte stage row
+                            split_f16x2(x[0] * c.scale, x[1] * c.scale, h2.x, l2.x); split_f16x2(x[2] * c.scale, x[3] * c.scale, h2.y, l2.y);
+                            const int off = sw_off_h(row, q * 4);
+                            *reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(Bhi) + off) = h2;
+                            *reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(Blo) + off) = l2;
+                        } else {
+                            float4 h4, l4;
+                            split_tf32(x[0], h4.x, l4.x); split_tf32(x[1], h4.y, l4.y); split_tf32(x[2], h4.z, l4.z); split_tf32(x[3], h4.w, l4.w);
+                            const int off = sw_off(row, (q & 3) * 4);
+                            *reinterpret_cast<float4 *>(Bhi + off) = h4;
+                            *reinterpret_cast<float4 *>(Blo + off) = l4;
+                        }
                     }
                     fence_async_smem();
                     __syncwarp();
-                    if (lane == 0) { mbar_arrive(full_bar(st0)); mbar_arrive(full_bar(st1)); }
-                    stage += 2;
+                    if (lane == 0) { mbar_arrive(full_bar(st0)); if (!F16) mbar_arrive(full_bar(st1)); }
+                    stage += SPB;
                     if (stage == NSTAGE) { stage = 0; phase ^= 1; }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) { v[i] = vn[i]; u[i] = un[i]; }
@@ -359,9 +386,16 @@ tc_gemm2_kernel(const TcArgs a) {
 
 template <int PROD>
 int launch2(const TcArgs &a, int n_clusters, cudaStream_t st) {
-    tc_gemm2_kernel<PROD><<<2 * n_clusters, NTHREADS, SMEM_BYTES, st>>>(a);      // cluster shape comes from __cluster_dims__(2,1,1)
+    if (a.fmt == 1) tc_gemm2_kernel<PROD, 1><<<2 * n_clusters, NTHREADS, SMEM_BYTES, st>>>(a);      // cluster shape comes from __cluster_dims__(2,1,1)
+    else tc_gemm2_kernel<PROD, 0><<<2 * n_clusters, NTHREADS, SMEM_BYTES, st>>>(a);
     CMF_LAUNCH_CHECK();
     return CMF_OK;
+}
+template <int PROD>
+cudaError_t set_smem2() {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm2_kernel<PROD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tc_gemm2_kernel<PROD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
 }
 
 }  // namespace
@@ -370,10 +404,10 @@ int cmf_launch_tc_gemm2(const TcArgs &a, cudaStream_t st) {
     static int num_sms = 0;
     static bool attr_set = false;
     if (!attr_set) {
-        CMF_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<TC_PROD_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        CMF_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<TC_PROD_FC_H1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        CMF_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<TC_PROD_SC2_Y1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        CMF_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<TC_PROD_TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CMF_CUDA(set_smem2<TC_PROD_PLAIN>());
+        CMF_CUDA(set_smem2<TC_PROD_FC_H1>());
+        CMF_CUDA(set_smem2<TC_PROD_SC2_Y1>());
+        CMF_CUDA(set_smem2<TC_PROD_TILED>());
         int dev = 0;
         CMF_CUDA(cudaGetDevice(&dev));
         CMF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -385,6 +419,8 @@ int cmf_launch_tc_gemm2(const TcArgs &a, cudaStream_t st) {
     if (a.epi == TC_EPI_MAXK && a.ksamp != 4 && a.ksamp != 8 && a.ksamp != 16 && a.ksamp != 32) { cmf_set_error("tc_gemm2: MAXK needs ksamp in {4,8,16,32}"); return CMF_ERR_INVALID; }
     if (a.prod == TC_PROD_FC_H1 && a.ksamp != 8) { cmf_set_error("tc_gemm2: the flow-embedding producer assumes 8 neighbours per point"); return CMF_ERR_INVALID; }
     if (a.epi == TC_EPI_WSUM && (a.prod != TC_PROD_TILED || a.ksamp != 8)) { cmf_set_error("tc_gemm2: WSUM needs the TILED producer and 8 neighbours per point"); return CMF_ERR_INVALID; }
+    if ((a.pbias || a.bs_mode || a.amax_out) && a.cols_per_pair <= 0) { cmf_set_error("tc_gemm2: cols_per_pair must be set"); return CMF_ERR_INVALID; }
+    if (a.amax_out && a.amax_group <= 0) { cmf_set_error("tc_gemm2: amax_group must be positive"); return CMF_ERR_INVALID; }
     const long long ntiles = ((a.cols + BN - 1) / BN) * (a.m_blocks >> 1);
     const int max_cl = num_sms / 2;
     const int n_cl = (int)(ntiles < max_cl ? ntiles : max_cl);

@@ -159,8 +159,10 @@ int cmf_model_forward_host(cmf_model *m, int b, int n,
                            void *stream);
 
 /* Arithmetic mode of the big 1x1-conv GEMMs: 0 = strict fp32 FMA (parity build, default), 1 = tcgen05 tensor cores with
- * 3xTF32 split precision (fp32 accumulate in TMEM; ~2^-22 relative per product).  The default can also be chosen with the
- * environment variable CMF_MODE=fp32|tf32x3 read at cmf_model_create(). */
+ * 3xTF32 split precision (fp32 accumulate in TMEM; ~2^-22 relative per product), 2 = tcgen05 with 3xFP16 split precision
+ * (same 22-bit split at twice the tensor rate; operands scaled by exact powers of two chosen per weight row / per frame pair
+ * from measured maxima).  The default can also be chosen with the environment variable CMF_MODE=fp32|tf32x3|fp16x3 read at
+ * cmf_model_create(). */
 int cmf_model_set_mode(cmf_model *m, int mode);
 int cmf_model_get_mode(const cmf_model *m);
 
@@ -183,6 +185,12 @@ const void *cmf_model_tap(const cmf_model *m, const char *name);
 int cmf_test_tc_gemm(int M, int K, long long cols, const float *W, int ldw, const float *X, int ldx,
                      const float *bias, int act, float *Out, int ldo, float *scratch_tiles, void *stream);
 size_t cmf_test_tc_tiled_floats(int M, int K);
+/* Same with the operand format chosen: fmt 0 = 3xTF32, 1 = 3xFP16 (power-of-two scaled).  For fmt 1, amax_in (device, one float per group of
+ * cols_per_pair consecutive rows of X: an upper bound on |X| in that group) selects the per-group activation scale (NULL = unscaled);
+ * amax_out (device, uint32 bit patterns, zeroed by the caller) receives max|Out| per group, or NULL. */
+int cmf_test_tc_gemm_fmt(int fmt, int M, int K, long long cols, const float *W, int ldw, const float *X, int ldx,
+                         const float *bias, int act, float *Out, int ldo, float *scratch_tiles,
+                         int cols_per_pair, const float *amax_in, unsigned int *amax_out, void *stream);
 /* Instrumented runs of cmf_test_tc_gemm: device buffer long long[grid][8] receiving per-role barrier wait cycles (NULL = off). */
 void cmf_test_tc_set_dbg(long long *dbg);
 
