@@ -29,11 +29,20 @@ constexpr int TILE_A_FLOATS = BM * SK;               // 2048 floats = 8 KB
 constexpr int TILE_BH_FLOATS = HALF_N * SK;          // 2048 floats = 8 KB (local half of B)
 constexpr int TILE_B_FLOATS = BN * SK;               // 4096 floats: the 256-row tile of the tiled activation FORMAT in global memory
 constexpr int STAGE_BYTES = (2 * TILE_A_FLOATS + 2 * TILE_BH_FLOATS) * 4;   // 32 KB
-constexpr int NSTAGE = 6;
 constexpr int NTHREADS = 512;
-constexpr int SMALL_BYTES = 512 * 16;
-constexpr int H2_BYTES = 2 * BN * 8 * 4;              // WSUM: WeightNet hidden vectors (8 floats) of the 256 columns, per accumulator stage
-constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 + 256 + SMALL_BYTES + H2_BYTES;
+// Shared-memory plan (bytes, after 1024-alignment):
+//   bulk-copied activations (TILED): 6 stages x 32 KB                          | barriers 256 | aux 16 KB = WSUM WeightNet hidden vectors
+//   produced activations:            4 stages x 32 KB + 72 KB cp.async staging | barriers 256 | aux 20 KB = rel-xyz weights 8 KB + row contexts 12 KB
+// The staging ring decouples the producers from global-memory latency: every producer thread keeps up to PF-1 K-blocks of its own
+// 16-byte row chunks in flight with cp.async (it reads back only what it copied itself, so cp.async.wait_group is the only
+// synchronisation), instead of a one-block-ahead register prefetch that left the loop latency-bound (~2100 clk per block measured
+// against 768 clk of tensor time).
+constexpr int NSTAGE_TILED = 6, NSTAGE_PROD = 4;
+constexpr int STG_BYTES = 72 * 1024;
+constexpr int RING_BYTES = NSTAGE_TILED * STAGE_BYTES + 8192;       // = NSTAGE_PROD * STAGE_BYTES + STG_BYTES = 204800
+static_assert(NSTAGE_PROD * STAGE_BYTES + STG_BYTES == RING_BYTES, "smem plan");
+constexpr int AUX_BYTES = 20 * 1024;                               // rel-xyz weights 8 KB + 3 tiles of row contexts 12 KB (or 16 KB of WSUM vectors)
+constexpr int SMEM_BYTES = RING_BYTES + 1024 + 256 + AUX_BYTES;
 constexpr uint32_t IDESC2_TF32 = make_idesc(256, BN, 0), IDESC2_F16 = make_idesc(256, BN, 1);
 
 __device__ __forceinline__ void tc_commit2_mc(uint32_t bar) {      // arrive on `bar` in BOTH CTAs when all prior MMAs of this thread retire
@@ -60,7 +69,8 @@ tc_gemm2_kernel(const TcArgs a) {
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (base - raw);
-    const uint32_t bar0 = base + NSTAGE * STAGE_BYTES;
+    constexpr int NSTAGE = PROD == TC_PROD_TILED ? NSTAGE_TILED : NSTAGE_PROD;
+    const uint32_t bar0 = base + RING_BYTES;
     auto full_bar = [&](int s) { return bar0 + 8 * s; };
     auto pfull_bar = [&](int s) { return bar0 + 48 + 8 * s; };
     auto empty_bar = [&](int s) { return bar0 + 96 + 8 * s; };
@@ -68,9 +78,9 @@ tc_gemm2_kernel(const TcArgs a) {
     auto tempty_bar = [&](int s) { return bar0 + 160 + 8 * s; };
     auto h2full_bar = [&](int s) { return bar0 + 176 + 8 * s; };
     auto h2empty_bar = [&](int s) { return bar0 + 208 + 8 * s; };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + NSTAGE * STAGE_BYTES + 240);
-    float *h2s = reinterpret_cast<float *>(smem + NSTAGE * STAGE_BYTES + 256 + SMALL_BYTES);
-    float4 *sW = reinterpret_cast<float4 *>(smem + NSTAGE * STAGE_BYTES + 256);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + RING_BYTES + 240);
+    float *h2s = reinterpret_cast<float *>(smem + RING_BYTES + 256);                 // TILED + WSUM only
+    float4 *sW = reinterpret_cast<float4 *>(smem + RING_BYTES + 256);                // gather producers only
     if (PROD == TC_PROD_FC_H1 || PROD == TC_PROD_SC2_Y1)
         for (int i = threadIdx.x; i < a.k_blocks * PK; i += NTHREADS) sW[i] = __ldg(reinterpret_cast<const float4 *>(a.Wsmall) + i);
 
@@ -243,15 +253,20 @@ tc_gemm2_kernel(const TcArgs a) {
         }
         if (a.dbg && warp == 4 && lane == 0) { a.dbg[(size_t)blockIdx.x * 8 + 6] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 7] = dw1; }
     } else if (warp >= 8 && PROD != TC_PROD_TILED) {
-        // ===== producers (256 threads): build this CTA's 128 activation rows, 32 floats (two stages) per iteration. =====
+        // ===== producers (256 threads): build this CTA's 128 activation rows, one 32-element K block per iteration. =====
         // Mapping: lane = (row-in-group-of-4, chunk): lane l handles 16-byte chunk q = l & 7 of rows  w*16 + 4*i + (l >> 3), i = 0..3.
-        // Eight lanes read one 128-byte row slice -> every LDG.128 is fully coalesced (4 lines per warp instruction instead of 32),
-        // and a thread's four channels are the same for all of its rows, so their rel-xyz weights are fetched once per iteration.
+        // Eight lanes read one 128-byte row slice -> fully coalesced 16-byte copies, and a thread's four channels are the same for all of
+        // its rows, so their rel-xyz weights are fetched once per iteration.  Global -> shared staging by cp.async, PF-1 blocks ahead.
         struct SCtx { const float *s1; const float *s0; float dx, dy, dz; float scale; };      // scale = 0 marks an out-of-range row
-        SCtx *sctx = reinterpret_cast<SCtx *>(h2s);                 // overlays the WSUM buffer (WSUM implies the TILED producer)
+        SCtx *sctx = reinterpret_cast<SCtx *>(smem + RING_BYTES + 256 + 8192);              // 3 tiles x 128 rows x 32 B (current, next, next but one)
+        constexpr int NSL = PROD == TC_PROD_FC_H1 ? 6 : 4;          // 16-byte slots per thread per block: 4 rows (+ 2 centre-point rows)
+        constexpr int PF = STG_BYTES / (NSL * 256 * 16);            // staging ring depth: 4 blocks (3 for the flow-embedding producer)
+        static_assert(PF >= 3, "staging ring too shallow");
         const int p = threadIdx.x - 256;
         const int pw = p >> 5;                                     // producer warp 0..7 -> rows pw*16 .. pw*16+15
         const int q = lane & 7, rsub = lane >> 3;
+        const uint32_t stg0 = base + NSTAGE * STAGE_BYTES + p * 16; // slot (ring r, i) of this thread at + (r*NSL + i) * 4096
+        const int pf = a.k_blocks + 1 < PF ? a.k_blocks + 1 : PF;   // look-ahead never reaches beyond the next tile
         int stage = 0; uint32_t phase = 0;
         auto fill_ctx = [&](long long tt, int buf) {               // threads p < 128: one row each
             if (p < HALF_N) {
@@ -261,46 +276,77 @@ tc_gemm2_kernel(const TcArgs a) {
                 sctx[buf * HALF_N + p] = c;
             }
         };
-        auto loadp = [&](int buf, int kb, float4 (&v)[4], float4 (&u)[4]) {
+        auto cp16 = [&](uint32_t dst, const float *src) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        };
+        auto issue = [&](int buf, int kb, int ring) {              // copies of K block kb of the tile whose contexts are in sctx[buf]
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const SCtx &c = sctx[buf * HALF_N + pw * 16 + i * 4 + rsub];
                 if (c.scale != 0.f) {
-                    v[i] = __ldg(reinterpret_cast<const float4 *>(c.s1 + kb * PK) + q);
-                    if (PROD == TC_PROD_FC_H1) u[i] = __ldg(reinterpret_cast<const float4 *>(c.s0 + kb * PK) + q);
+                    cp16(stg0 + (ring * NSL + i) * 4096, c.s1 + kb * PK + q * 4);
+                    // the centre-point row is shared by the 8 neighbour rows of a point: rows i = 0,1 and i = 2,3 of this thread
+                    if (PROD == TC_PROD_FC_H1 && (i & 1) == 0) cp16(stg0 + (ring * NSL + 4 + (i >> 1)) * 4096, c.s0 + kb * PK + q * 4);
                 }
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto lds16 = [&](uint32_t addr) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+            return v;
         };
         long long t = cl_id;
         if (t < ntiles) {
-            int buf = 0;
+            int buf = 0, ring = 0;                                  // buf = context slot of the current tile, ring = staging slot being consumed
             fill_ctx(t, 0);
+            if (t + n_cl < ntiles) fill_ctx(t + n_cl, 1);
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            float4 v[4], vn[4], u[4], un[4];
-            loadp(0, 0, v, u);
+            // prologue: blocks 0 .. pf-2 of the global block sequence (they may already belong to the next tile when k_blocks < pf-1)
+            {
+                int ib = 0, ikb = 0; long long it = t;
+                for (int g = 0; g < pf - 1; ++g) {
+                    if (it < ntiles) issue(ib, ikb, g); else asm volatile("cp.async.commit_group;" ::: "memory");
+                    if (++ikb == a.k_blocks) { ikb = 0; ib = ib == 2 ? 0 : ib + 1; it += n_cl; }
+                }
+            }
+            // look-ahead cursor: block (current + pf - 1)
+            int la_buf = 0, la_kb = pf - 1; long long la_t = t;
+            while (la_kb >= a.k_blocks) { la_kb -= a.k_blocks; la_buf = la_buf == 2 ? 0 : la_buf + 1; la_t += n_cl; }
             while (true) {
                 const long long tn = t + n_cl;
-                if (tn < ntiles) fill_ctx(tn, buf ^ 1);             // next tile's row contexts (read after the barrier at the end of this tile)
+                // contexts of the tile after next go into the slot the previous tile has vacated; published by the barrier that ends this tile
+                if (tn + n_cl < ntiles) fill_ctx(tn + n_cl, buf == 0 ? 2 : buf - 1);
                 for (int kb = 0; kb < a.k_blocks; ++kb) {
-                    if (kb + 1 < a.k_blocks) loadp(buf, kb + 1, vn, un);
+                    {   // keep pf-1 blocks in flight
+                        int lring = ring + pf - 1; if (lring >= pf) lring -= pf;
+                        if (la_t < ntiles) issue(la_buf, la_kb, lring); else asm volatile("cp.async.commit_group;" ::: "memory");
+                        if (++la_kb == a.k_blocks) { la_kb = 0; la_buf = la_buf == 2 ? 0 : la_buf + 1; la_t += n_cl; }
+                    }
                     // this thread's four channels of the 32-block and their rel-xyz weights
                     float4 w4[4];
                     if (PROD == TC_PROD_FC_H1 || PROD == TC_PROD_SC2_Y1) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) w4[e] = sW[kb * PK + q * 4 + e];
                     }
+                    if (pf == 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
+                    else if (pf == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+                    else asm volatile("cp.async.wait_group 1;" ::: "memory");
                     const int st0 = stage, st1 = stage + SPB - 1;   // fmt 0: NSTAGE is even, a 32-block never wraps between its two stages
                     TIMED(dw0, mbar_wait(empty_bar(st0), phase ^ 1));
                     if (!F16) TIMED(dw0, mbar_wait(empty_bar(st1), phase ^ 1));
                     float *Bhi = reinterpret_cast<float *>(smem + ((F16 || q < 4) ? st0 : st1) * STAGE_BYTES + 2 * TILE_A_FLOATS * 4);
                     float *Blo = Bhi + TILE_BH_FLOATS;
+                    float4 ucen = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int row = pw * 16 + i * 4 + rsub;
                         const SCtx &c = sctx[buf * HALF_N + row];
-                        float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+                        const float4 v = lds16(stg0 + (ring * NSL + i) * 4096);
+                        float x[4] = {v.x, v.y, v.z, v.w};
                         if (PROD == TC_PROD_FC_H1) {
-                            const float uu[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+                            if ((i & 1) == 0) ucen = lds16(stg0 + (ring * NSL + 4 + (i >> 1)) * 4096);
+                            const float uu[4] = {ucen.x, ucen.y, ucen.z, ucen.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) x[e] = act_apply(uu[e] + x[e] + fmaf(w4[e].z, c.dz, fmaf(w4[e].y, c.dy, w4[e].x * c.dx)), 2);
                         } else if (PROD == TC_PROD_SC2_Y1) {
@@ -327,14 +373,13 @@ tc_gemm2_kernel(const TcArgs a) {
                     if (lane == 0) { mbar_arrive(full_bar(st0)); if (!F16) mbar_arrive(full_bar(st1)); }
                     stage += SPB;
                     if (stage == NSTAGE) { stage = 0; phase ^= 1; }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { v[i] = vn[i]; u[i] = un[i]; }
+                    if (++ring == pf) ring = 0;
                 }
                 if (tn >= ntiles) break;
-                asm volatile("bar.sync 1, 256;" ::: "memory");     // next tile's contexts complete; everyone finished reading this tile's
-                t = tn; buf ^= 1;
-                loadp(buf, 0, v, u);
+                asm volatile("bar.sync 1, 256;" ::: "memory");     // all producers are done with this tile's contexts; the new ones are visible
+                t = tn; buf = buf == 2 ? 0 : buf + 1;
             }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         if (a.dbg && warp == 8 && lane == 0) a.dbg[(size_t)blockIdx.x * 8 + 5] = dw0;
     }
