@@ -257,43 +257,51 @@ tc_gemm2_kernel(const TcArgs a) {
         // Mapping: lane = (row-in-group-of-4, chunk): lane l handles 16-byte chunk q = l & 7 of rows  w*16 + 4*i + (l >> 3), i = 0..3.
         // Eight lanes read one 128-byte row slice -> fully coalesced 16-byte copies, and a thread's four channels are the same for all of
         // its rows, so their rel-xyz weights are fetched once per iteration.  Global -> shared staging by cp.async, PF-1 blocks ahead.
-        struct SCtx { const float *s1; const float *s0; float dx, dy, dz; float scale; };      // scale = 0 marks an out-of-range row
-        SCtx *sctx = reinterpret_cast<SCtx *>(smem + RING_BYTES + 256 + 8192);              // 3 tiles x 128 rows x 32 B (current, next, next but one)
+        // Row contexts of 3 tiles (current, next, next but one) in shared memory: gathered-row pointer (NULL = row out of range),
+        // centre-row pointer (flow embedding only) and {dx, dy, dz, scale}.
+        const float **cs1 = reinterpret_cast<const float **>(smem + RING_BYTES + 256 + 8192);          // [3][128]
+        const float **cs0 = cs1 + 3 * HALF_N;                                                           // [3][128]
+        float4 *cgeo = reinterpret_cast<float4 *>(cs0 + 3 * HALF_N);                                    // [3][128]
         constexpr int NSL = PROD == TC_PROD_FC_H1 ? 6 : 4;          // 16-byte slots per thread per block: 4 rows (+ 2 centre-point rows)
         constexpr int PF = STG_BYTES / (NSL * 256 * 16);            // staging ring depth: 4 blocks (3 for the flow-embedding producer)
         static_assert(PF >= 3, "staging ring too shallow");
         const int p = threadIdx.x - 256;
         const int pw = p >> 5;                                     // producer warp 0..7 -> rows pw*16 .. pw*16+15
         const int q = lane & 7, rsub = lane >> 3;
+        const int row0 = pw * 16 + rsub;                            // this thread's rows: row0 + 4*i
         const uint32_t stg0 = base + NSTAGE * STAGE_BYTES + p * 16; // slot (ring r, i) of this thread at + (r*NSL + i) * 4096
         const int pf = a.k_blocks + 1 < PF ? a.k_blocks + 1 : PF;   // look-ahead never reaches beyond the next tile
         int stage = 0; uint32_t phase = 0;
         auto fill_ctx = [&](long long tt, int buf) {               // threads p < 128: one row each
             if (p < HALF_N) {
                 const RowCtx rc = make_row(a, (tt / m_pairs) * BN + rank * HALF_N + p);
-                SCtx c;
-                c.s1 = (PROD == TC_PROD_PLAIN) ? rc.src0 : rc.src1; c.s0 = rc.src0; c.dx = rc.dx; c.dy = rc.dy; c.dz = rc.dz; c.scale = rc.valid ? rc.scale : 0.f;
-                sctx[buf * HALF_N + p] = c;
+                cs1[buf * HALF_N + p] = rc.valid ? ((PROD == TC_PROD_PLAIN) ? rc.src0 : rc.src1) : nullptr;
+                if (PROD == TC_PROD_FC_H1) cs0[buf * HALF_N + p] = rc.src0;
+                cgeo[buf * HALF_N + p] = make_float4(rc.dx, rc.dy, rc.dz, rc.valid ? rc.scale : 0.f);
             }
         };
-        auto cp16 = [&](uint32_t dst, const float *src) {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-        };
-        auto issue = [&](int buf, int kb, int ring) {              // copies of K block kb of the tile whose contexts are in sctx[buf]
+        // NOTE: the asm statements below carry no "memory" clobber on purpose -- they are volatile, so they keep their order among
+        // themselves (copy -> commit -> wait_group -> ld.shared), while the compiler stays free to hoist the plain shared-memory loads
+        // of contexts / weights above them and to interleave the four rows' arithmetic and stores.
+        auto cp16 = [&](uint32_t dst, const float *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src)); };
+        auto issue = [&](int buf, int kb, int ring) {              // copies of K block kb of the tile whose contexts are in slot `buf`
+            const float *s1[4], *s0[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s1[i] = cs1[buf * HALF_N + row0 + 4 * i];
+            if (PROD == TC_PROD_FC_H1) { s0[0] = cs0[buf * HALF_N + row0]; s0[1] = cs0[buf * HALF_N + row0 + 8]; }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const SCtx &c = sctx[buf * HALF_N + pw * 16 + i * 4 + rsub];
-                if (c.scale != 0.f) {
-                    cp16(stg0 + (ring * NSL + i) * 4096, c.s1 + kb * PK + q * 4);
+                if (s1[i]) {
+                    cp16(stg0 + (ring * NSL + i) * 4096, s1[i] + kb * PK + q * 4);
                     // the centre-point row is shared by the 8 neighbour rows of a point: rows i = 0,1 and i = 2,3 of this thread
-                    if (PROD == TC_PROD_FC_H1 && (i & 1) == 0) cp16(stg0 + (ring * NSL + 4 + (i >> 1)) * 4096, c.s0 + kb * PK + q * 4);
+                    if (PROD == TC_PROD_FC_H1 && (i & 1) == 0) cp16(stg0 + (ring * NSL + 4 + (i >> 1)) * 4096, s0[i >> 1] + kb * PK + q * 4);
                 }
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.commit_group;");
         };
         auto lds16 = [&](uint32_t addr) {
             float4 v;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
             return v;
         };
         long long t = cl_id;
@@ -302,25 +310,22 @@ tc_gemm2_kernel(const TcArgs a) {
             fill_ctx(t, 0);
             if (t + n_cl < ntiles) fill_ctx(t + n_cl, 1);
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            // prologue: blocks 0 .. pf-2 of the global block sequence (they may already belong to the next tile when k_blocks < pf-1)
-            {
-                int ib = 0, ikb = 0; long long it = t;
-                for (int g = 0; g < pf - 1; ++g) {
-                    if (it < ntiles) issue(ib, ikb, g); else asm volatile("cp.async.commit_group;" ::: "memory");
-                    if (++ikb == a.k_blocks) { ikb = 0; ib = ib == 2 ? 0 : ib + 1; it += n_cl; }
-                }
-            }
+            // prologue: blocks 0 .. pf-2 (pf - 1 <= k_blocks: all inside the first tile)
+            for (int g = 0; g < pf - 1; ++g) issue(0, g, g);
             // look-ahead cursor: block (current + pf - 1)
             int la_buf = 0, la_kb = pf - 1; long long la_t = t;
-            while (la_kb >= a.k_blocks) { la_kb -= a.k_blocks; la_buf = la_buf == 2 ? 0 : la_buf + 1; la_t += n_cl; }
+            if (la_kb >= a.k_blocks) { la_kb -= a.k_blocks; la_buf = 1; la_t += n_cl; }
             while (true) {
                 const long long tn = t + n_cl;
                 // contexts of the tile after next go into the slot the previous tile has vacated; published by the barrier that ends this tile
                 if (tn + n_cl < ntiles) fill_ctx(tn + n_cl, buf == 0 ? 2 : buf - 1);
+                float4 geo[4];                                      // {dx, dy, dz, scale} of this thread's four rows: fixed for the whole tile
+#pragma unroll
+                for (int i = 0; i < 4; ++i) geo[i] = cgeo[buf * HALF_N + row0 + 4 * i];
                 for (int kb = 0; kb < a.k_blocks; ++kb) {
                     {   // keep pf-1 blocks in flight
                         int lring = ring + pf - 1; if (lring >= pf) lring -= pf;
-                        if (la_t < ntiles) issue(la_buf, la_kb, lring); else asm volatile("cp.async.commit_group;" ::: "memory");
+                        if (la_t < ntiles) issue(la_buf, la_kb, lring); else asm volatile("cp.async.commit_group;");
                         if (++la_kb == a.k_blocks) { la_kb = 0; la_buf = la_buf == 2 ? 0 : la_buf + 1; la_t += n_cl; }
                     }
                     // this thread's four channels of the 32-block and their rel-xyz weights
@@ -332,31 +337,32 @@ tc_gemm2_kernel(const TcArgs a) {
                     if (pf == 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
                     else if (pf == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
                     else asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    float4 v[4], uc[2];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[i] = lds16(stg0 + (ring * NSL + i) * 4096);
+                    if (PROD == TC_PROD_FC_H1) { uc[0] = lds16(stg0 + (ring * NSL + 4) * 4096); uc[1] = lds16(stg0 + (ring * NSL + 5) * 4096); }
                     const int st0 = stage, st1 = stage + SPB - 1;   // fmt 0: NSTAGE is even, a 32-block never wraps between its two stages
                     TIMED(dw0, mbar_wait(empty_bar(st0), phase ^ 1));
                     if (!F16) TIMED(dw0, mbar_wait(empty_bar(st1), phase ^ 1));
                     float *Bhi = reinterpret_cast<float *>(smem + ((F16 || q < 4) ? st0 : st1) * STAGE_BYTES + 2 * TILE_A_FLOATS * 4);
                     float *Blo = Bhi + TILE_BH_FLOATS;
-                    float4 ucen = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const int row = pw * 16 + i * 4 + rsub;
-                        const SCtx &c = sctx[buf * HALF_N + row];
-                        const float4 v = lds16(stg0 + (ring * NSL + i) * 4096);
-                        float x[4] = {v.x, v.y, v.z, v.w};
+                        const int row = row0 + 4 * i;
+                        const float4 g = geo[i];
+                        float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
                         if (PROD == TC_PROD_FC_H1) {
-                            if ((i & 1) == 0) ucen = lds16(stg0 + (ring * NSL + 4 + (i >> 1)) * 4096);
-                            const float uu[4] = {ucen.x, ucen.y, ucen.z, ucen.w};
+                            const float uu[4] = {uc[i >> 1].x, uc[i >> 1].y, uc[i >> 1].z, uc[i >> 1].w};
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) x[e] = act_apply(uu[e] + x[e] + fmaf(w4[e].z, c.dz, fmaf(w4[e].y, c.dy, w4[e].x * c.dx)), 2);
+                            for (int e = 0; e < 4; ++e) x[e] = act_apply(uu[e] + x[e] + fmaf(w4[e].z, g.z, fmaf(w4[e].y, g.y, w4[e].x * g.x)), 2);
                         } else if (PROD == TC_PROD_SC2_Y1) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e] + fmaf(w4[e].z, c.dz, fmaf(w4[e].y, c.dy, w4[e].x * c.dx)), 0.f);
+                            for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e] + fmaf(w4[e].z, g.z, fmaf(w4[e].y, g.y, w4[e].x * g.x)), 0.f);
                         }
-                        if (c.scale == 0.f) { x[0] = x[1] = x[2] = x[3] = 0.f; }
+                        if (g.w == 0.f) { x[0] = x[1] = x[2] = x[3] = 0.f; }
                         if (F16) {
                             uint2 h2, l2;             // this thread's four halfs: bytes [8*(q&1), +8) of 16-byte chunk q>>1 of the 64-byte stage row
-                            split_f16x2(x[0] * c.scale, x[1] * c.scale, h2.x, l2.x); split_f16x2(x[2] * c.scale, x[3] * c.scale, h2.y, l2.y);
+                            split_f16x2(x[0] * g.w, x[1] * g.w, h2.x, l2.x); split_f16x2(x[2] * g.w, x[3] * g.w, h2.y, l2.y);
                             const int off = sw_off_h(row, q * 4);
                             *reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(Bhi) + off) = h2;
                             *reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(Blo) + off) = l2;
