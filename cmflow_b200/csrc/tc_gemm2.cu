@@ -115,6 +115,12 @@ tc_gemm2_kernel(const TcArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Row contexts of 3 tiles (current, next, next but one) in shared memory: gathered-row pointer (NULL = row out of range),
+    // centre-row pointer (flow embedding only) and {dx, dy, dz, scale}.  Written by warp 2 two tiles ahead of the producers.
+    const float **cs1 = reinterpret_cast<const float **>(smem + RING_BYTES + 256 + 8192);          // [3][128]
+    const float **cs0 = cs1 + 3 * HALF_N;                                                           // [3][128]
+    float4 *cgeo = reinterpret_cast<float4 *>(cs0 + 3 * HALF_N);                                    // [3][128]
+
     if (warp == 0) {
         // ===== bulk-copy issuer: this CTA's 128 weight rows (and, when pre-tiled, its half of the activation rows) =====
         if (lane == 0) {
@@ -180,6 +186,35 @@ tc_gemm2_kernel(const TcArgs a) {
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
             if (a.dbg && lane == 0) { a.dbg[(size_t)blockIdx.x * 8 + 1] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 2] = dw1; a.dbg[(size_t)blockIdx.x * 8 + 3] = dw2; }
+        }
+    } else if (warp == 2 && PROD != TC_PROD_TILED) {
+        // ===== context filler (idle after the TMEM allocation): neighbour index -> row pointers, rel-xyz, fp16 scale for the tile two
+        // ahead of the producers, so that those dependent global loads never sit on the producers' critical path =====
+        auto fill_ctx = [&](long long tt, int buf) {
+            RowCtx rc[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rc[k] = make_row(a, (tt / m_pairs) * BN + rank * HALF_N + lane + 32 * k);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = buf * HALF_N + lane + 32 * k;
+                cs1[r] = rc[k].valid ? ((PROD == TC_PROD_PLAIN) ? rc[k].src0 : rc[k].src1) : nullptr;
+                if (PROD == TC_PROD_FC_H1) cs0[r] = rc[k].src0;
+                cgeo[r] = make_float4(rc[k].dx, rc[k].dy, rc[k].dz, rc[k].valid ? rc[k].scale : 0.f);
+            }
+        };
+        long long t = cl_id;
+        if (t < ntiles) {
+            int buf = 0;
+            fill_ctx(t, 0);
+            if (t + n_cl < ntiles) fill_ctx(t + n_cl, 1);
+            asm volatile("bar.sync 1, 288;" ::: "memory");
+            while (true) {
+                const long long tn = t + n_cl;
+                if (tn + n_cl < ntiles) fill_ctx(tn + n_cl, buf == 0 ? 2 : buf - 1);    // the slot the previous tile has vacated
+                if (tn >= ntiles) break;
+                asm volatile("bar.sync 1, 288;" ::: "memory");                           // ends the producers' tile t; publishes tile t + 2
+                t = tn; buf = buf == 2 ? 0 : buf + 1;
+            }
         }
     } else if (warp == 3) {
         // ===== forwarder (peer CTA only): tell the leader when this CTA's half of a stage is complete =====
@@ -257,11 +292,6 @@ tc_gemm2_kernel(const TcArgs a) {
         // Mapping: lane = (row-in-group-of-4, chunk): lane l handles 16-byte chunk q = l & 7 of rows  w*16 + 4*i + (l >> 3), i = 0..3.
         // Eight lanes read one 128-byte row slice -> fully coalesced 16-byte copies, and a thread's four channels are the same for all of
         // its rows, so their rel-xyz weights are fetched once per iteration.  Global -> shared staging by cp.async, PF-1 blocks ahead.
-        // Row contexts of 3 tiles (current, next, next but one) in shared memory: gathered-row pointer (NULL = row out of range),
-        // centre-row pointer (flow embedding only) and {dx, dy, dz, scale}.
-        const float **cs1 = reinterpret_cast<const float **>(smem + RING_BYTES + 256 + 8192);          // [3][128]
-        const float **cs0 = cs1 + 3 * HALF_N;                                                           // [3][128]
-        float4 *cgeo = reinterpret_cast<float4 *>(cs0 + 3 * HALF_N);                                    // [3][128]
         constexpr int NSL = PROD == TC_PROD_FC_H1 ? 6 : 4;          // 16-byte slots per thread per block: 4 rows (+ 2 centre-point rows)
         constexpr int PF = STG_BYTES / (NSL * 256 * 16);            // staging ring depth: 4 blocks (3 for the flow-embedding producer)
         static_assert(PF >= 3, "staging ring too shallow");
@@ -272,14 +302,6 @@ tc_gemm2_kernel(const TcArgs a) {
         const uint32_t stg0 = base + NSTAGE * STAGE_BYTES + p * 16; // slot (ring r, i) of this thread at + (r*NSL + i) * 4096
         const int pf = a.k_blocks + 1 < PF ? a.k_blocks + 1 : PF;   // look-ahead never reaches beyond the next tile
         int stage = 0; uint32_t phase = 0;
-        auto fill_ctx = [&](long long tt, int buf) {               // threads p < 128: one row each
-            if (p < HALF_N) {
-                const RowCtx rc = make_row(a, (tt / m_pairs) * BN + rank * HALF_N + p);
-                cs1[buf * HALF_N + p] = rc.valid ? ((PROD == TC_PROD_PLAIN) ? rc.src0 : rc.src1) : nullptr;
-                if (PROD == TC_PROD_FC_H1) cs0[buf * HALF_N + p] = rc.src0;
-                cgeo[buf * HALF_N + p] = make_float4(rc.dx, rc.dy, rc.dz, rc.valid ? rc.scale : 0.f);
-            }
-        };
         // NOTE: the asm statements below carry no "memory" clobber on purpose -- they are volatile, so they keep their order among
         // themselves (copy -> commit -> wait_group -> ld.shared), while the compiler stays free to hoist the plain shared-memory loads
         // of contexts / weights above them and to interleave the four rows' arithmetic and stores.
@@ -307,9 +329,7 @@ tc_gemm2_kernel(const TcArgs a) {
         long long t = cl_id;
         if (t < ntiles) {
             int buf = 0, ring = 0;                                  // buf = context slot of the current tile, ring = staging slot being consumed
-            fill_ctx(t, 0);
-            if (t + n_cl < ntiles) fill_ctx(t + n_cl, 1);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, 288;" ::: "memory");          // contexts of the first two tiles are in place (warp 2)
             // prologue: blocks 0 .. pf-2 (pf - 1 <= k_blocks: all inside the first tile)
             for (int g = 0; g < pf - 1; ++g) issue(0, g, g);
             // look-ahead cursor: block (current + pf - 1)
@@ -317,8 +337,6 @@ tc_gemm2_kernel(const TcArgs a) {
             if (la_kb >= a.k_blocks) { la_kb -= a.k_blocks; la_buf = 1; la_t += n_cl; }
             while (true) {
                 const long long tn = t + n_cl;
-                // contexts of the tile after next go into the slot the previous tile has vacated; published by the barrier that ends this tile
-                if (tn + n_cl < ntiles) fill_ctx(tn + n_cl, buf == 0 ? 2 : buf - 1);
                 float4 geo[4];                                      // {dx, dy, dz, scale} of this thread's four rows: fixed for the whole tile
 #pragma unroll
                 for (int i = 0; i < 4; ++i) geo[i] = cgeo[buf * HALF_N + row0 + 4 * i];
@@ -382,7 +400,7 @@ tc_gemm2_kernel(const TcArgs a) {
                     if (++ring == pf) ring = 0;
                 }
                 if (tn >= ntiles) break;
-                asm volatile("bar.sync 1, 256;" ::: "memory");     // all producers are done with this tile's contexts; the new ones are visible
+                asm volatile("bar.sync 1, 288;" ::: "memory");     // producers are done with this tile's contexts; warp 2 has published tile t + 2
                 t = tn; buf = buf == 2 ? 0 : buf + 1;
             }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
