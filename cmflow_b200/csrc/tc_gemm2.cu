@@ -306,17 +306,21 @@ tc_gemm2_kernel(const TcArgs a) {
         // themselves (copy -> commit -> wait_group -> ld.shared), while the compiler stays free to hoist the plain shared-memory loads
         // of contexts / weights above them and to interleave the four rows' arithmetic and stores.
         auto cp16 = [&](uint32_t dst, const float *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src)); };
-        auto issue = [&](int buf, int kb, int ring) {              // copies of K block kb of the tile whose contexts are in slot `buf`
-            const float *s1[4], *s0[2];
+        // gathered-row (and centre-row) pointers of the LOOK-AHEAD tile live in registers: they change once per tile, not per K block
+        const float *ls1[4] = {nullptr, nullptr, nullptr, nullptr}, *ls0[2] = {nullptr, nullptr};
+        auto load_ptrs = [&](int buf) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) s1[i] = cs1[buf * HALF_N + row0 + 4 * i];
-            if (PROD == TC_PROD_FC_H1) { s0[0] = cs0[buf * HALF_N + row0]; s0[1] = cs0[buf * HALF_N + row0 + 8]; }
+            for (int i = 0; i < 4; ++i) ls1[i] = cs1[buf * HALF_N + row0 + 4 * i];
+            if (PROD == TC_PROD_FC_H1) { ls0[0] = cs0[buf * HALF_N + row0]; ls0[1] = cs0[buf * HALF_N + row0 + 8]; }
+        };
+        auto issue = [&](int kb, int ring) {                       // copies of K block kb of the look-ahead tile
+            const int koff = kb * PK + q * 4;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                if (s1[i]) {
-                    cp16(stg0 + (ring * NSL + i) * 4096, s1[i] + kb * PK + q * 4);
+                if (ls1[i]) {
+                    cp16(stg0 + (ring * NSL + i) * 4096, ls1[i] + koff);
                     // the centre-point row is shared by the 8 neighbour rows of a point: rows i = 0,1 and i = 2,3 of this thread
-                    if (PROD == TC_PROD_FC_H1 && (i & 1) == 0) cp16(stg0 + (ring * NSL + 4 + (i >> 1)) * 4096, s0[i >> 1] + kb * PK + q * 4);
+                    if (PROD == TC_PROD_FC_H1 && (i & 1) == 0) cp16(stg0 + (ring * NSL + 4 + (i >> 1)) * 4096, ls0[i >> 1] + koff);
                 }
             }
             asm volatile("cp.async.commit_group;");
@@ -331,10 +335,11 @@ tc_gemm2_kernel(const TcArgs a) {
             int buf = 0, ring = 0;                                  // buf = context slot of the current tile, ring = staging slot being consumed
             asm volatile("bar.sync 1, 288;" ::: "memory");          // contexts of the first two tiles are in place (warp 2)
             // prologue: blocks 0 .. pf-2 (pf - 1 <= k_blocks: all inside the first tile)
-            for (int g = 0; g < pf - 1; ++g) issue(0, g, g);
+            load_ptrs(0);
+            for (int g = 0; g < pf - 1; ++g) issue(g, g);
             // look-ahead cursor: block (current + pf - 1)
             int la_buf = 0, la_kb = pf - 1; long long la_t = t;
-            if (la_kb >= a.k_blocks) { la_kb -= a.k_blocks; la_buf = 1; la_t += n_cl; }
+            if (la_kb >= a.k_blocks) { la_kb -= a.k_blocks; la_buf = 1; la_t += n_cl; if (la_t < ntiles) load_ptrs(1); }
             while (true) {
                 const long long tn = t + n_cl;
                 float4 geo[4];                                      // {dx, dy, dz, scale} of this thread's four rows: fixed for the whole tile
@@ -343,8 +348,11 @@ tc_gemm2_kernel(const TcArgs a) {
                 for (int kb = 0; kb < a.k_blocks; ++kb) {
                     {   // keep pf-1 blocks in flight
                         int lring = ring + pf - 1; if (lring >= pf) lring -= pf;
-                        if (la_t < ntiles) issue(la_buf, la_kb, lring); else asm volatile("cp.async.commit_group;");
-                        if (++la_kb == a.k_blocks) { la_kb = 0; la_buf = la_buf == 2 ? 0 : la_buf + 1; la_t += n_cl; }
+                        if (la_t < ntiles) issue(la_kb, lring); else asm volatile("cp.async.commit_group;");
+                        if (++la_kb == a.k_blocks) {                // the cursor moves on to the next tile: fetch its row pointers
+                            la_kb = 0; la_buf = la_buf == 2 ? 0 : la_buf + 1; la_t += n_cl;
+                            if (la_t < ntiles) load_ptrs(la_buf);
+                        }
                     }
                     // this thread's four channels of the 32-block and their rel-xyz weights
                     float4 w4[4];
