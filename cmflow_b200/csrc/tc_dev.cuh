@@ -13,7 +13,7 @@
 namespace tcdev {
 
 constexpr int BM = 128, BN = 256, SK = 16, PK = 32;
-constexpr unsigned SPIN_LIMIT = 20000u;         // x 1 ms suspend hint = 20 s before a stuck wait traps
+constexpr unsigned SPIN_LIMIT = 2000u;          // x 1 ms suspend hint = 2 s before a stuck wait traps
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -367,14 +367,11 @@ tc_gemm2_kernel(const TcArgs a) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) v[i] = lds16(stg0 + (ring * NSL + i) * 4096);
                     if (PROD == TC_PROD_FC_H1) { uc[0] = lds16(stg0 + (ring * NSL + 4) * 4096); uc[1] = lds16(stg0 + (ring * NSL + 5) * 4096); }
-                    const int st0 = stage, st1 = stage + SPB - 1;   // fmt 0: NSTAGE is even, a 32-block never wraps between its two stages
-                    TIMED(dw0, mbar_wait(empty_bar(st0), phase ^ 1));
-                    if (!F16) TIMED(dw0, mbar_wait(empty_bar(st1), phase ^ 1));
-                    float *Bhi = reinterpret_cast<float *>(smem + ((F16 || q < 4) ? st0 : st1) * STAGE_BYTES + 2 * TILE_A_FLOATS * 4);
-                    float *Blo = Bhi + TILE_BH_FLOATS;
+                    // arithmetic first (results in registers), THEN wait for the stage to be free: after the tensor core releases a stage
+                    // only the stores, the proxy fence and the arrive remain on the critical path of the ring
+                    uint4 hh[4], ll[4];                             // fmt 0: four hi / lo floats; fmt 1: .x,.y = four hi halfs, ll .x,.y = four lo halfs
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const int row = row0 + 4 * i;
                         const float4 g = geo[i];
                         float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
                         if (PROD == TC_PROD_FC_H1) {
@@ -387,17 +384,31 @@ tc_gemm2_kernel(const TcArgs a) {
                         }
                         if (g.w == 0.f) { x[0] = x[1] = x[2] = x[3] = 0.f; }
                         if (F16) {
-                            uint2 h2, l2;             // this thread's four halfs: bytes [8*(q&1), +8) of 16-byte chunk q>>1 of the 64-byte stage row
-                            split_f16x2(x[0] * g.w, x[1] * g.w, h2.x, l2.x); split_f16x2(x[2] * g.w, x[3] * g.w, h2.y, l2.y);
-                            const int off = sw_off_h(row, q * 4);
-                            *reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(Bhi) + off) = h2;
-                            *reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(Blo) + off) = l2;
+                            split_f16x2(x[0] * g.w, x[1] * g.w, hh[i].x, ll[i].x); split_f16x2(x[2] * g.w, x[3] * g.w, hh[i].y, ll[i].y);
                         } else {
-                            float4 h4, l4;
-                            split_tf32(x[0], h4.x, l4.x); split_tf32(x[1], h4.y, l4.y); split_tf32(x[2], h4.z, l4.z); split_tf32(x[3], h4.w, l4.w);
-                            const int off = sw_off(row, (q & 3) * 4);
-                            *reinterpret_cast<float4 *>(Bhi + off) = h4;
-                            *reinterpret_cast<float4 *>(Blo + off) = l4;
+                            float h[4], l[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) split_tf32(x[e], h[e], l[e]);
+                            hh[i] = make_uint4(__float_as_uint(h[0]), __float_as_uint(h[1]), __float_as_uint(h[2]), __float_as_uint(h[3]));
+                            ll[i] = make_uint4(__float_as_uint(l[0]), __float_as_uint(l[1]), __float_as_uint(l[2]), __float_as_uint(l[3]));
+                        }
+                    }
+                    const int st0 = stage, st1 = stage + SPB - 1;   // fmt 0: NSTAGE is even, a 32-block never wraps between its two stages
+                    TIMED(dw0, mbar_wait(empty_bar(st0), phase ^ 1));
+                    if (!F16) TIMED(dw0, mbar_wait(empty_bar(st1), phase ^ 1));
+                    uint8_t *Bhi = smem + ((F16 || q < 4) ? st0 : st1) * STAGE_BYTES + 2 * TILE_A_FLOATS * 4;
+                    uint8_t *Blo = Bhi + TILE_BH_FLOATS * 4;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = row0 + 4 * i;
+                        if (F16) {                    // this thread's four halfs: bytes [8*(q&1), +8) of 16-byte chunk q>>1 of the 64-byte stage row
+                            const int off = sw_off_h(row, q * 4);
+                            *reinterpret_cast<uint2 *>(Bhi + off) = make_uint2(hh[i].x, hh[i].y);
+                            *reinterpret_cast<uint2 *>(Blo + off) = make_uint2(ll[i].x, ll[i].y);
+                        } else {
+                            const int off = sw_off(row, (q & 3) * 4) * 4;
+                            *reinterpret_cast<uint4 *>(Bhi + off) = hh[i];
+                            *reinterpret_cast<uint4 *>(Blo + off) = ll[i];
                         }
                     }
                     fence_async_smem();
