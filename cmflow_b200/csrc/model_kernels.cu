@@ -20,7 +20,7 @@ constexpr int G_BN = 128;
 constexpr int G_BK = 16;
 
 template <int BM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 gemm_nt_kernel(const GemmBatch gb) {
     const GemmArgs &g = gb.g[blockIdx.z];
     const int m0 = blockIdx.y * BM;
@@ -35,11 +35,13 @@ gemm_nt_kernel(const GemmBatch gb) {
     const int tm = tid & 15, tc = tid >> 4;
     const int lrow = tid >> 2, lkq = (tid & 3) * 4;     // loader mapping: 64 rows x 4 k-quads per pass
 
-    float acc[TM][8];
+    // accumulators as float2 pairs of adjacent columns: one FFMA2 (Blackwell packed fp32 FMA, scalar operand broadcast) does two of the
+    // tile's FMAs -- each half is an IEEE fma, so results are bit-identical with the scalar form at twice the FMA-pipe throughput
+    float2 acc[TM][4];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
 
     const int ktiles = (g.K + G_BK - 1) / G_BK;
     float4 ra[TMG], rb[2];
@@ -81,7 +83,8 @@ gemm_nt_kernel(const GemmBatch gb) {
         if (kt + 1 < ktiles) gload(kt + 1);
 #pragma unroll
         for (int k = 0; k < G_BK; ++k) {
-            float a[TM], b[8];
+            float a[TM];
+            float2 b[4];
 #pragma unroll
             for (int r = 0; r < TMG; ++r) {
                 const float4 v = *reinterpret_cast<const float4 *>(&As[buf][k][tm * 4 + 64 * r]);
@@ -90,12 +93,12 @@ gemm_nt_kernel(const GemmBatch gb) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const float4 v = *reinterpret_cast<const float4 *>(&Bs[buf][k][tc * 4 + 64 * r]);
-                b[r * 4 + 0] = v.x; b[r * 4 + 1] = v.y; b[r * 4 + 2] = v.z; b[r * 4 + 3] = v.w;
+                b[r * 2 + 0] = make_float2(v.x, v.y); b[r * 2 + 1] = make_float2(v.z, v.w);
             }
 #pragma unroll
             for (int i = 0; i < TM; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(make_float2(a[i], a[i]), b[j], acc[i][j]);
         }
         if (kt + 1 < ktiles) sstore(buf ^ 1);
         __syncthreads();
@@ -111,7 +114,8 @@ gemm_nt_kernel(const GemmBatch gb) {
         for (int r = 0; r < TMG; ++r) {
             const int m = m0 + 64 * r + tm * 4;
             if (m >= g.M) continue;
-            float4 v = make_float4(acc[r * 4 + 0][j], acc[r * 4 + 1][j], acc[r * 4 + 2][j], acc[r * 4 + 3][j]);
+            float4 v = (j & 1) ? make_float4(acc[r * 4 + 0][j >> 1].y, acc[r * 4 + 1][j >> 1].y, acc[r * 4 + 2][j >> 1].y, acc[r * 4 + 3][j >> 1].y)
+                               : make_float4(acc[r * 4 + 0][j >> 1].x, acc[r * 4 + 1][j >> 1].x, acc[r * 4 + 2][j >> 1].x, acc[r * 4 + 3][j >> 1].x);
             if (g.bias) {
                 const float4 bb = __ldg(reinterpret_cast<const float4 *>(g.bias + m));
                 v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
@@ -340,28 +344,30 @@ setconv1_fused_kernel(int n, const float *__restrict__ xyz, const float *__restr
         x0[h][2] = __fsub_rn(__ldg(px + 2 * n + j), __ldg(px + 2 * n + i));
         x0[h][3] = __ldg(pf + j); x0[h][4] = __ldg(pf + n + j); x0[h][5] = __ldg(pf + 2 * n + j);
     }
-    float h1[2][32], h2[2][32];
+    // the thread's two columns ride in the two halves of a float2: every weight (scalar, broadcast) feeds one FFMA2 = two FMAs
+    float2 h1[32], h2[32];
 #pragma unroll
     for (int o = 0; o < 32; ++o) {
         const float4 wa = *reinterpret_cast<const float4 *>(&sW1[o * 8]), wb = *reinterpret_cast<const float4 *>(&sW1[o * 8 + 4]);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float a = sb1[o];
-            a = fmaf(wa.x, x0[h][0], a); a = fmaf(wa.y, x0[h][1], a); a = fmaf(wa.z, x0[h][2], a);
-            a = fmaf(wa.w, x0[h][3], a); a = fmaf(wb.x, x0[h][4], a); a = fmaf(wb.y, x0[h][5], a);
-            h1[h][o] = fmaxf(a, 0.f);
-        }
+        float2 a = make_float2(sb1[o], sb1[o]);
+        a = __ffma2_rn(make_float2(wa.x, wa.x), make_float2(x0[0][0], x0[1][0]), a);
+        a = __ffma2_rn(make_float2(wa.y, wa.y), make_float2(x0[0][1], x0[1][1]), a);
+        a = __ffma2_rn(make_float2(wa.z, wa.z), make_float2(x0[0][2], x0[1][2]), a);
+        a = __ffma2_rn(make_float2(wa.w, wa.w), make_float2(x0[0][3], x0[1][3]), a);
+        a = __ffma2_rn(make_float2(wb.x, wb.x), make_float2(x0[0][4], x0[1][4]), a);
+        a = __ffma2_rn(make_float2(wb.y, wb.y), make_float2(x0[0][5], x0[1][5]), a);
+        h1[o] = make_float2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f));
     }
 #pragma unroll
     for (int o = 0; o < 32; ++o) {
-        float a0 = sb2[o], a1 = a0;
+        float2 a = make_float2(sb2[o], sb2[o]);
 #pragma unroll
         for (int k = 0; k < 32; k += 4) {
             const float4 wv = *reinterpret_cast<const float4 *>(&sW2[o * 32 + k]);
-            a0 = fmaf(wv.x, h1[0][k], a0); a0 = fmaf(wv.y, h1[0][k + 1], a0); a0 = fmaf(wv.z, h1[0][k + 2], a0); a0 = fmaf(wv.w, h1[0][k + 3], a0);
-            a1 = fmaf(wv.x, h1[1][k], a1); a1 = fmaf(wv.y, h1[1][k + 1], a1); a1 = fmaf(wv.z, h1[1][k + 2], a1); a1 = fmaf(wv.w, h1[1][k + 3], a1);
+            a = __ffma2_rn(make_float2(wv.x, wv.x), h1[k], a); a = __ffma2_rn(make_float2(wv.y, wv.y), h1[k + 1], a);
+            a = __ffma2_rn(make_float2(wv.z, wv.z), h1[k + 2], a); a = __ffma2_rn(make_float2(wv.w, wv.w), h1[k + 3], a);
         }
-        h2[0][o] = fmaxf(a0, 0.f); h2[1][o] = fmaxf(a1, 0.f);
+        h2[o] = make_float2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f));
     }
     const int lane = threadIdx.x & 31;
 #pragma unroll 1
@@ -369,14 +375,14 @@ setconv1_fused_kernel(int n, const float *__restrict__ xyz, const float *__restr
         float r[2][8];
 #pragma unroll
         for (int o = 0; o < 8; ++o) {
-            float a0 = sb3[oc + o], a1 = a0;
+            float2 a = make_float2(sb3[oc + o], sb3[oc + o]);
 #pragma unroll
             for (int k = 0; k < 32; k += 4) {
                 const float4 wv = *reinterpret_cast<const float4 *>(&sW3[(oc + o) * 32 + k]);
-                a0 = fmaf(wv.x, h2[0][k], a0); a0 = fmaf(wv.y, h2[0][k + 1], a0); a0 = fmaf(wv.z, h2[0][k + 2], a0); a0 = fmaf(wv.w, h2[0][k + 3], a0);
-                a1 = fmaf(wv.x, h2[1][k], a1); a1 = fmaf(wv.y, h2[1][k + 1], a1); a1 = fmaf(wv.z, h2[1][k + 2], a1); a1 = fmaf(wv.w, h2[1][k + 3], a1);
+                a = __ffma2_rn(make_float2(wv.x, wv.x), h2[k], a); a = __ffma2_rn(make_float2(wv.y, wv.y), h2[k + 1], a);
+                a = __ffma2_rn(make_float2(wv.z, wv.z), h2[k + 2], a); a = __ffma2_rn(make_float2(wv.w, wv.w), h2[k + 3], a);
             }
-            r[0][o] = fmaxf(a0, 0.f); r[1][o] = fmaxf(a1, 0.f);
+            r[0][o] = fmaxf(a.x, 0.f); r[1][o] = fmaxf(a.y, 0.f);
         }
         // max over the K consecutive lanes of a point (K | 32, groups are lane-aligned because 128 and 256 are multiples of K)
         for (int off = 1; off < K; off <<= 1)
