@@ -90,6 +90,14 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t &hi, ui
     hi = *reinterpret_cast<const uint32_t *>(&h);
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
+// packed form: the residual of both halves in one FFMA2 (x - hi = fma(hi, -1, x), exact)
+__device__ __forceinline__ void split_f16x2(float2 x, uint32_t &hi, uint32_t &lo) {
+    const __half2 h = __floats2half2_rn(x.x, x.y);
+    const float2 d = __ffma2_rn(__half22float2(h), make_float2(-1.f, -1.f), x);
+    const __half2 l = __floats2half2_rn(d.x, d.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
 __device__ __forceinline__ void split_f16(float x, unsigned short &hi, unsigned short &lo) {
     const __half h = __float2half_rn(x);
     const __half l = __float2half_rn(x - __half2float(h));
@@ -347,15 +355,22 @@ __device__ __forceinline__ void epilogue_chunk(const TcArgs &a, const uint32_t (
             // (row>>1)&3 == (e>>1)&3 since cc % 8 == 0
             uint8_t *tb = reinterpret_cast<uint8_t *>(a.Out + ((size_t)ct * (a.M >> 5) + (m >> 5)) * (2 * (size_t)tile_b_floats)) + cc * 64 + (m & 7) * 2;
             const int kq = (m & 31) >> 3;
+            // the (power-of-two) output scale is folded into the un-scale and the bias: act(s v) = s act(v) for s > 0, every product exact.
+            // Two adjacent columns per packed-fp32 instruction.
+            const float2 inv2 = make_float2(es.inv * es.osc, es.inv * es.osc), badd2 = make_float2(badd * es.osc, badd * es.osc);
+            const float2 slope2 = make_float2(slope, slope);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                float v = fmaf(__uint_as_float(r[e]), es.inv, badd);
-                v = fmaxf(v, v * slope) * es.osc;
-                unsigned short hi, lo;
-                split_f16(v, hi, lo);
-                const int off = e * 64 + ((kq ^ ((e >> 1) & 3)) << 4);
-                *reinterpret_cast<unsigned short *>(tb + off) = hi;
-                *reinterpret_cast<unsigned short *>(tb + tile_b_floats * 4 + off) = lo;
+            for (int e = 0; e < 32; e += 2) {
+                float2 v = __ffma2_rn(make_float2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), inv2, badd2);
+                const float2 vs = __fmul2_rn(v, slope2);
+                v = make_float2(fmaxf(v.x, vs.x), fmaxf(v.y, vs.y));
+                uint32_t hi, lo;
+                split_f16x2(v, hi, lo);
+                const int off = e * 64 + ((kq ^ ((e >> 1) & 3)) << 4);        // e even: columns e and e + 1 share the swizzle term
+                *reinterpret_cast<unsigned short *>(tb + off) = (unsigned short)(hi & 0xffffu);
+                *reinterpret_cast<unsigned short *>(tb + off + 64) = (unsigned short)(hi >> 16);
+                *reinterpret_cast<unsigned short *>(tb + tile_b_floats * 4 + off) = (unsigned short)(lo & 0xffffu);
+                *reinterpret_cast<unsigned short *>(tb + tile_b_floats * 4 + off + 64) = (unsigned short)(lo >> 16);
             }
         } else if (a.out_tiled) {
             // tile (col_tile, 16-block m/16); element (row = column in tile, kk = m%16) at sw_off(row, kk)

@@ -81,8 +81,15 @@ tc_gemm2_kernel(const TcArgs a) {
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + RING_BYTES + 240);
     float *h2s = reinterpret_cast<float *>(smem + RING_BYTES + 256);                 // TILED + WSUM only
     float4 *sW = reinterpret_cast<float4 *>(smem + RING_BYTES + 256);                // gather producers only
+    // rel-xyz / direction weights, transposed for the producers: sW[(kb*3 + comp)*8 + q] = {W[c][comp], c = kb*32 + q*4 .. +3}.  A quarter
+    // warp (q = 0..7) reads 8 consecutive float4 = one 128-byte wavefront, broadcast to the four row groups (the channel-major float4
+    // layout put the 8 chunks 64 bytes apart: 4-way bank conflicts, 16 wavefronts per load -- 55 % of the kernel's shared-memory traffic).
     if (PROD == TC_PROD_FC_H1 || PROD == TC_PROD_SC2_Y1)
-        for (int i = threadIdx.x; i < a.k_blocks * PK; i += NTHREADS) sW[i] = __ldg(reinterpret_cast<const float4 *>(a.Wsmall) + i);
+        for (int i = threadIdx.x; i < a.k_blocks * 24; i += NTHREADS) {
+            const int kb_ = i / 24, comp = (i >> 3) % 3, q_ = i & 7;
+            const float *w = a.Wsmall + (size_t)(kb_ * PK + q_ * 4) * 4 + comp;
+            sW[i] = make_float4(__ldg(w), __ldg(w + 4), __ldg(w + 8), __ldg(w + 12));
+        }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long t_start = a.dbg ? clock64() : 0;
@@ -302,6 +309,10 @@ tc_gemm2_kernel(const TcArgs a) {
         const uint32_t stg0 = base + NSTAGE * STAGE_BYTES + p * 16; // slot (ring r, i) of this thread at + (r*NSL + i) * 4096
         const int pf = a.k_blocks + 1 < PF ? a.k_blocks + 1 : PF;   // look-ahead never reaches beyond the next tile
         int stage = 0; uint32_t phase = 0;
+        // staging slots start as zeros: rows beyond the last column are never copied, and their (stale but finite) slot contents are
+        // multiplied by a zero scale below instead of being selected away
+        for (int r = 0; r < PF * NSL; ++r)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(stg0 + r * 4096), "f"(0.f));
         // NOTE: the asm statements below carry no "memory" clobber on purpose -- they are volatile, so they keep their order among
         // themselves (copy -> commit -> wait_group -> ld.shared), while the compiler stays free to hoist the plain shared-memory loads
         // of contexts / weights above them and to interleave the four rows' arithmetic and stores.
@@ -342,9 +353,15 @@ tc_gemm2_kernel(const TcArgs a) {
             if (la_kb >= a.k_blocks) { la_kb -= a.k_blocks; la_buf = 1; la_t += n_cl; if (la_t < ntiles) load_ptrs(1); }
             while (true) {
                 const long long tn = t + n_cl;
-                float4 geo[4];                                      // {dx, dy, dz, scale} of this thread's four rows: fixed for the whole tile
+                // {s*dx, s*dy, s*dz, s} of this thread's four rows, fixed for the whole tile (s = power-of-two fp16 scale of the row's
+                // frame pair, 1 in TF32 mode, 0 for rows beyond the last column).  s > 0 commutes exactly with the affine term, ReLU /
+                // LeakyReLU and every rounding, so scaling the inputs gives bit-identical results to scaling the activated value.
+                float4 geo[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) geo[i] = cgeo[buf * HALF_N + row0 + 4 * i];
+                for (int i = 0; i < 4; ++i) {
+                    const float4 g = cgeo[buf * HALF_N + row0 + 4 * i];
+                    geo[i] = make_float4(g.x * g.w, g.y * g.w, g.z * g.w, g.w);
+                }
                 for (int kb = 0; kb < a.k_blocks; ++kb) {
                     {   // keep pf-1 blocks in flight
                         int lring = ring + pf - 1; if (lring >= pf) lring -= pf;
@@ -355,10 +372,10 @@ tc_gemm2_kernel(const TcArgs a) {
                         }
                     }
                     // this thread's four channels of the 32-block and their rel-xyz weights
-                    float4 w4[4];
+                    float4 wx = make_float4(0.f, 0.f, 0.f, 0.f), wy = wx, wz = wx;
                     if (PROD == TC_PROD_FC_H1 || PROD == TC_PROD_SC2_Y1) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) w4[e] = sW[kb * PK + q * 4 + e];
+                        const float4 *wp = sW + kb * 24 + q;
+                        wx = wp[0]; wy = wp[8]; wz = wp[16];
                     }
                     if (pf == 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
                     else if (pf == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
@@ -372,23 +389,33 @@ tc_gemm2_kernel(const TcArgs a) {
                     uint4 hh[4], ll[4];                             // fmt 0: four hi / lo floats; fmt 1: .x,.y = four hi halfs, ll .x,.y = four lo halfs
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
+                        // packed fp32 (FFMA2 / FMUL2 / FADD2): two channels per instruction
                         const float4 g = geo[i];
-                        float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+                        const float2 gx = make_float2(g.x, g.x), gy = make_float2(g.y, g.y), gz = make_float2(g.z, g.z), gs = make_float2(g.w, g.w);
+                        float2 xa = make_float2(v[i].x, v[i].y), xb = make_float2(v[i].z, v[i].w);
                         if (PROD == TC_PROD_FC_H1) {
-                            const float uu[4] = {uc[i >> 1].x, uc[i >> 1].y, uc[i >> 1].z, uc[i >> 1].w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) x[e] = act_apply(uu[e] + x[e] + fmaf(w4[e].z, g.z, fmaf(w4[e].y, g.y, w4[e].x * g.x)), 2);
-                        } else if (PROD == TC_PROD_SC2_Y1) {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e] + fmaf(w4[e].z, g.z, fmaf(w4[e].y, g.y, w4[e].x * g.x)), 0.f);
+                            xa = __fadd2_rn(make_float2(uc[i >> 1].x, uc[i >> 1].y), xa);
+                            xb = __fadd2_rn(make_float2(uc[i >> 1].z, uc[i >> 1].w), xb);
                         }
-                        if (g.w == 0.f) { x[0] = x[1] = x[2] = x[3] = 0.f; }
+                        if (PROD == TC_PROD_FC_H1 || PROD == TC_PROD_SC2_Y1) {
+                            float2 ta = __fmul2_rn(make_float2(wx.x, wx.y), gx), tb = __fmul2_rn(make_float2(wx.z, wx.w), gx);
+                            ta = __ffma2_rn(make_float2(wy.x, wy.y), gy, ta); tb = __ffma2_rn(make_float2(wy.z, wy.w), gy, tb);
+                            ta = __ffma2_rn(make_float2(wz.x, wz.y), gz, ta); tb = __ffma2_rn(make_float2(wz.z, wz.w), gz, tb);
+                            xa = __ffma2_rn(xa, gs, ta); xb = __ffma2_rn(xb, gs, tb);
+                            if (PROD == TC_PROD_FC_H1) {            // LeakyReLU(0.1) = max(v, 0.1 v)
+                                const float2 la = __fmul2_rn(xa, make_float2(0.1f, 0.1f)), lb = __fmul2_rn(xb, make_float2(0.1f, 0.1f));
+                                xa = make_float2(fmaxf(xa.x, la.x), fmaxf(xa.y, la.y)); xb = make_float2(fmaxf(xb.x, lb.x), fmaxf(xb.y, lb.y));
+                            } else {
+                                xa = make_float2(fmaxf(xa.x, 0.f), fmaxf(xa.y, 0.f)); xb = make_float2(fmaxf(xb.x, 0.f), fmaxf(xb.y, 0.f));
+                            }
+                        } else {
+                            xa = __fmul2_rn(xa, gs); xb = __fmul2_rn(xb, gs);
+                        }
                         if (F16) {
-                            split_f16x2(x[0] * g.w, x[1] * g.w, hh[i].x, ll[i].x); split_f16x2(x[2] * g.w, x[3] * g.w, hh[i].y, ll[i].y);
+                            split_f16x2(xa, hh[i].x, ll[i].x); split_f16x2(xb, hh[i].y, ll[i].y);
                         } else {
                             float h[4], l[4];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) split_tf32(x[e], h[e], l[e]);
+                            split_tf32(xa.x, h[0], l[0]); split_tf32(xa.y, h[1], l[1]); split_tf32(xb.x, h[2], l[2]); split_tf32(xb.y, h[3], l[3]);
                             hh[i] = make_uint4(__float_as_uint(h[0]), __float_as_uint(h[1]), __float_as_uint(h[2]), __float_as_uint(h[3]));
                             ll[i] = make_uint4(__float_as_uint(l[0]), __float_as_uint(l[1]), __float_as_uint(l[2]), __float_as_uint(l[3]));
                         }
