@@ -144,7 +144,9 @@ struct cmf_model {
     int fused_sc1 = 1;           // CMF_FUSED_SC1=0 falls back to the unfused (GEMM-per-layer) set-conv #1 for A/B testing
     // pre-tiled weights per operand format (index 0: 3xTF32, 1: 3xFP16 with per-row scales a_inv)
     struct TcW { const float *wt = nullptr, *ainv = nullptr; };
-    struct TcSet { float *buf = nullptr; TcW fc_wc, fc_wn, fc_w2, fc_w3, m2_wp, m2_w2[4], m2_w3[4], hd_w1; } tcw[2];
+    struct TcSet { float *buf = nullptr; TcW fc_wc, fc_wn, fc_w2, fc_w3, m2_wp, m2_w2[4], m2_w3[4], hd_w1;
+                   TcW m1_w2[4], m1_w3[4], m1_v[4][3], m2_v[4][3]; } tcw[2];      // narrow chains (tc_chain.cu, fmt 1 only)
+    int chain = 1;               // CMF_CHAIN=0: keep the fp32 FMA kernels for set-conv #1 / mlp2 in fp16x3 mode (A/B testing)
     // host-side norms for the fp16x3 scale bounds: max row L1 of the rel-xyz / direction columns, max row L1 and max |bias| of the layers
     // whose outputs are written pre-split (flow-embedding conv1, set-conv #2 layer 2)
     float wd_l1 = 0.f, wx_l1[4] = {0.f, 0.f, 0.f, 0.f}, fc_w2_l1 = 0.f, fc_b2_max = 0.f, m2_w2_l1[4] = {0.f, 0.f, 0.f, 0.f}, m2_t2_max[4] = {0.f, 0.f, 0.f, 0.f};
@@ -227,6 +229,15 @@ static int ensure_tc_weights(cmf_model *m, int fmt) {
         items.push_back({&S.m2_w2[s], M2_BASE + s * 10, 256, 512, 512});
         items.push_back({&S.m2_w3[s], M2_BASE + s * 10 + 2, 64, 256, 256});
     }
+    if (fmt == 1)
+        for (int s = 0; s < 4; ++s) {
+            items.push_back({&S.m1_w2[s], M1_BASE + s * 12 + 2, 32, 32, 32});
+            items.push_back({&S.m1_w3[s], M1_BASE + s * 12 + 4, 64, 32, 32});
+            for (int l = 0; l < 3; ++l) {
+                items.push_back({&S.m1_v[s][l], M1_BASE + s * 12 + 6 + l * 2, 64, 64, 64});
+                items.push_back({&S.m2_v[s][l], M2_BASE + s * 10 + 4 + l * 2, 64, 64, 64});
+            }
+        }
     auto ainv_floats = [](int M) { return (size_t)cmf_divup(M, 128) * 128; };
     size_t tot = 0;
     for (auto &it : items) tot += cmf_tc_tiled_floats(it.M, it.K) + ainv_floats(it.M);
@@ -291,6 +302,20 @@ static int run_mse_layer(cmf_model *m, int bc, int n, const float *pc, const flo
     const long long bn = (long long)bc * n;
     GemmBatch gb;
     gb.count = 4;
+    if (m->tc == 2 && m->chain) {
+        // tensor-core chains (tc_chain.cu): gather + 6->32->32->64 + max over K in one launch, the three 64->64 layers of mlp2 in another
+        const cmf_model::TcSet &T = m->tcw[1];
+        TcChainSc1W cw[4]; TcChainMlp2W mw[4];
+        for (int s = 0; s < 4; ++s) {
+            const int sb = M1_BASE + s * 12;
+            cw[s] = TcChainSc1W{m->seg[sb], m->seg[sb + 1], m->seg[sb + 3], m->seg[sb + 5], T.m1_w2[s].wt, T.m1_w2[s].ainv, T.m1_w3[s].wt, T.m1_w3[s].ainv};
+            for (int l = 0; l < 3; ++l) { mw[s].Vt[l] = T.m1_v[s][l].wt; mw[s].ainv[l] = T.m1_v[s][l].ainv; mw[s].c[l] = m->seg[sb + 7 + l * 2]; }
+        }
+        RUN(C_GEMM_SC1, 2.0 * 3264.0 * 60.0 * (double)bn, cmf_launch_setconv1_tc(bc, n, pc, ft, bq, cw, w.M64, st));
+        RUN(C_GEMM_POINTWISE, 2.0 * 3 * 4 * 64 * 64 * (double)bn, cmf_launch_mlp2_tc(bn, w.M64, 256, dest, ldd, mw, st));
+        RUN(C_REDUCE, 0, cmf_launch_globalmax(bc, n, 256, dest, ldd, G, st));
+        return CMF_OK;
+    }
     if (m->fused_sc1) {
         // gather + 3-layer MLP + max over neighbours in one kernel (all four scales)
         const float *segs[24];
@@ -454,7 +479,12 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
         RUN(C_REDUCE, 0, cmf_launch_maxk(bn, KS[s], 64, w.Y3, 64, w.M64 + s * 64, 256, st));
         }
     }
-    {
+    if (m->tc == 2 && m->chain) {
+        TcChainMlp2W mw[4];
+        for (int s = 0; s < 4; ++s)
+            for (int l = 0; l < 3; ++l) { mw[s].Vt[l] = T.m2_v[s][l].wt; mw[s].ainv[l] = T.m2_v[s][l].ainv; mw[s].c[l] = S(M2_BASE + s * 10 + 5 + l * 2); }
+        RUN(C_GEMM_POINTWISE, 2.0 * 3 * 4 * 64 * 64 * (double)bn, cmf_launch_mlp2_tc(bn, w.M64, 256, w.PROP, 256, mw, st));
+    } else {
         GemmBatch gb; gb.count = 4;
         const float *src[3] = {w.M64, w.Q1, w.Q2};
         float *dst[3] = {w.Q1, w.Q2, w.PROP};
@@ -553,6 +583,7 @@ extern "C" int cmf_model_create(cmf_model **out, const float *blob, size_t blob_
         }
     }
     *out = m;
+    { const char *ce = getenv("CMF_CHAIN"); if (ce && ce[0] == '0') m->chain = 0; }
     const char *fe = getenv("CMF_FUSED_SC1");
     if (fe && fe[0] == '0') m->fused_sc1 = 0;
     const char *env = getenv("CMF_MODE");            // "fp32" (default) | "tf32x3"

@@ -57,3 +57,13 @@ int cmf_launch_tc_gemm(const TcArgs &a, cudaStream_t st);      // one CTA per 12
 int cmf_launch_tc_gemm2(const TcArgs &a, cudaStream_t st);     // CTA pair (cta_group::2) per 256 x 256 tile; needs M % 256 == 0
 int cmf_tc_pair_enabled();
 int cmf_launch_tc_auto(const TcArgs &a, cudaStream_t st);      // pair kernel when M % 256 == 0 (unless CMF_TC2=0), else the one-CTA kernel
+
+// ---- narrow MLP chains with the activations as the A operand (tc_chain.cu; 3xFP16 only) ---------------------------------------------
+// Weight tiles come from cmf_tc_tile_weights_f16 (one 128-row block, K/32 blocks of {hi, lo}); ainv = its per-row un-scale.
+struct TcChainSc1W { const float *W1, *b1, *b2, *b3, *W2t, *ainv2, *W3t, *ainv3; };     // one scale of mse_layer: 32x8 fp32, biases, 32x32 / 64x32 tiles
+struct TcChainMlp2W { const float *Vt[3], *ainv[3], *c[3]; };                           // one scale of mlp2: three 64x64 tiles, biases
+// set-conv #1 up to the max over neighbours: out (bc*n, 256) = [scale0 64 | scale1 64 | scale2 64 | scale3 64]
+int cmf_launch_setconv1_tc(int bc, int n, const float *xyz_planar, const float *ft_planar, const int *idx60, const TcChainSc1W *w4, float *out,
+                           cudaStream_t st);
+// out[row][s*64 + o] = mlp2_s(in[row][s*64 .. +63]) for the four scales
+int cmf_launch_mlp2_tc(long long rows, const float *in, int ld_in, float *out, int ld_out, const TcChainMlp2W *w4, cudaStream_t st);
