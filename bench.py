@@ -125,7 +125,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        sample = 4
+        # bounded sample: ~1 s of CPU work per step at N=256 (the whole --steps K run stays within a few minutes)
+        sample = max(1, min(16, (16 * 256 * 256) // (args.points * args.points)))
         v, spp = time_cpu_port(sample, args.points, K, min(W, 1), cores)
         print(json.dumps({
             "impl": "reference", "metric": "frame-pairs/sec CMFlow forward", "value": v, "unit": "frame-pairs/s", "n_gpus": args.gpus,
@@ -240,18 +241,33 @@ def main():
         achieved = d["gflop_per_step"] / d["ms_per_step"]       # GFLOP/ms == TFLOP/s (algorithmic FLOPs: 2*M*K*cols, split passes not counted)
         tc = args.precision != "fp32"
         split = {"tf32x3": ("3xTF32", 6), "fp16x3": ("3xFP16", 3)}.get(args.precision)
+        peak_tf = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+        traffic, traffic_src = None, None
+        tj = os.path.join(ROOT, "profiles", "r01b_tc_gemm2_traffic.json")
+        if args.precision == "fp16x3" and B == 256 and N == 256 and os.path.exists(tj):      # the ncu capture is of exactly this workload
+            tjd = json.load(open(tj))
+            traffic, traffic_src = tjd["traffic_bytes_per_launch_avg"], tjd["source"]
+        # algorithmic bytes of the kernel: every (point, neighbour) column gathers one 512-channel fp32 layer-1 row (2 KB) and
+        # writes 256 channels (1 KB); 60 columns per point over the four scales, 4 launches
+        alg_bytes_launch = B * N * 60 * 3072 / max(1, d["launches_per_step"])
         roofline = {"kernel": (f"tc_gemm2_kernel<SC2_Y1> tcgen05 {split[0]}" if tc else "gemm_nt_kernel<128> fp32 FMA") +
                               " (set-conv #2 layer 2, 512->256 over N*K neighbour columns, gather fused)" ,
-                    "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"],
-                    "unit": "TFLOP/s", "frac": achieved / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]),
-                    "peak_source": peaks["source"] + " cuBLAS bf16 (sustained)", "traffic": None,
+                    "bound": "tensor", "achieved": achieved, "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                    "peak_source": peaks["source"] + " cuBLAS bf16 (sustained)", "traffic": traffic, "traffic_source": traffic_src,
+                    "ceiling": peak_tf / split[1] if tc else 74.5, "frac_of_ceiling": achieved / (peak_tf / split[1] if tc else 74.5),
+                    "hbm": {"algorithmic_bytes_per_launch": alg_bytes_launch,
+                            "achieved_gbs": alg_bytes_launch / (d["ms_per_step"] / max(1, d["launches_per_step"]) * 1e-3) / 1e9,
+                            "peak_gbs": peaks["hbm_gbs"], "frac": alg_bytes_launch / (d["ms_per_step"] / max(1, d["launches_per_step"]) * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                            "note": "not the binding bound (86 flop/B); gathered rows are served by L2, see profiles/r01b_tc_kernels_ncu_full.md"},
                     "launches_per_step": d["launches_per_step"], "avg_launch_ms": d["ms_per_step"] / max(1, d["launches_per_step"]),
                     "note": (f"{split[0]}: three MMAs per algorithmic MAC (kind::tf32 runs at half the bf16 rate) => ceiling = bf16 peak / {split[1]}" if tc else
                              "strict-fp32 FMA build (no tensor cores): the chip's fp32 FMA ceiling is 74.5 TFLOP/s, ~1/19 of this peak")}
         if not args.no_cpu_baseline and world == 1:
-            v, spp = time_cpu_port(4, N, 2, 1, cores)
+            cs = max(1, min(16, (16 * 256 * 256) // (N * N)))
+            v, spp = time_cpu_port(cs, N, 12, 1, cores)          # ~10-20 s of CPU work
             cpu = {"value": v, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
-                   "sample": f"4 pairs/step x 2 steps (N={N}), oracle/cmflow_oracle.py CPU port of the reference forward, {cores} threads"}
+                   "sample": f"{cs} pairs/step x 12 steps (N={N}), oracle/cmflow_oracle.py CPU port of the reference forward, {cores} threads"}
         h2d = 4 * B * 3 * N * 4
         d2h = B * 3 * N * 4 + B * N * 4 + B * 16 * 4 + B * N
         line = {

@@ -97,7 +97,7 @@ struct Work {
     unsigned int *AMAX;      // fp16x3 mode: per-pair max |x| of the tensors feeding a tensor-core GEMM (uint bit patterns of floats), AM_COUNT x bc
     float *SCL;              // fp16x3 mode: per-pair scales of the tiled intermediates (H2, Y2 x 4 scales), SC_COUNT x bc
 };
-enum { AM_F1 = 0, AM_F2, AM_E, AM_PROP, AM_U1, AM_U2, AM_DIR, AM_P0, AM_COUNT = AM_P0 + 4 };
+enum { AM_F1 = 0, AM_F2, AM_E, AM_PROP, AM_U1, AM_U2, AM_DIR, AM_HD1, AM_P0, AM_COUNT = AM_P0 + 4 };
 enum { SC_H2 = 0, SC_Y2, SC_COUNT = SC_Y2 + 4 };
 
 void carve(Arena &a, Work &w, int bc, int n) {
@@ -145,7 +145,8 @@ struct cmf_model {
     // pre-tiled weights per operand format (index 0: 3xTF32, 1: 3xFP16 with per-row scales a_inv)
     struct TcW { const float *wt = nullptr, *ainv = nullptr; };
     struct TcSet { float *buf = nullptr; TcW fc_wc, fc_wn, fc_w2, fc_w3, m2_wp, m2_w2[4], m2_w3[4], hd_w1;
-                   TcW m1_w2[4], m1_w3[4], m1_v[4][3], m2_v[4][3]; } tcw[2];      // narrow chains (tc_chain.cu, fmt 1 only)
+                   TcW m1_w2[4], m1_w3[4], m1_v[4][3], m2_v[4][3];
+                   TcW hd_w2; const float *hd_t2 = nullptr; } tcw[2];      // heads layer 2: [W2F 0; 0 W2M] (256 x 512) and its stacked bias      // narrow chains (tc_chain.cu, fmt 1 only)
     int chain = 1;               // CMF_CHAIN=0: keep the fp32 FMA kernels for set-conv #1 / mlp2 in fp16x3 mode (A/B testing)
     // host-side norms for the fp16x3 scale bounds: max row L1 of the rel-xyz / direction columns, max row L1 and max |bias| of the layers
     // whose outputs are written pre-split (flow-embedding conv1, set-conv #2 layer 2)
@@ -239,7 +240,7 @@ static int ensure_tc_weights(cmf_model *m, int fmt) {
             }
         }
     auto ainv_floats = [](int M) { return (size_t)cmf_divup(M, 128) * 128; };
-    size_t tot = 0;
+    size_t tot = cmf_tc_tiled_floats(256, 512) + ainv_floats(256) + 256;          // + block-diagonal heads layer 2
     for (auto &it : items) tot += cmf_tc_tiled_floats(it.M, it.K) + ainv_floats(it.M);
     cudaError_t e = cudaMalloc(&S.buf, tot * sizeof(float));
     if (e != cudaSuccess) { S.buf = nullptr; cmf_set_error("tc weights cudaMalloc failed: %s", cudaGetErrorString(e)); return CMF_ERR_NOMEM; }
@@ -251,6 +252,22 @@ static int ensure_tc_weights(cmf_model *m, int fmt) {
         if (rc) return rc;
         it.dst->wt = wt; it.dst->ainv = fmt ? ainv : nullptr;
         off += cmf_tc_tiled_floats(it.M, it.K) + ainv_floats(it.M);
+    }
+    {   // heads layer 2 (radarflow_util.py:246,274): the flow and motion branches read disjoint halves of the stacked layer-1 output, so
+        // both are one GEMM with the block-diagonal matrix [W2F 0; 0 W2M] (M = 256 suits the CTA-pair kernel; half of its MMAs multiply zeros)
+        float *tmp = nullptr;
+        CMF_CUDA(cudaMalloc(&tmp, (size_t)256 * 512 * sizeof(float)));
+        CMF_CUDA(cudaMemset(tmp, 0, (size_t)256 * 512 * sizeof(float)));
+        CMF_CUDA(cudaMemcpy2D(tmp, 512 * sizeof(float), m->seg[HD_W2F], 256 * sizeof(float), 256 * sizeof(float), 128, cudaMemcpyDeviceToDevice));
+        CMF_CUDA(cudaMemcpy2D(tmp + (size_t)128 * 512 + 256, 512 * sizeof(float), m->seg[HD_W2M], 256 * sizeof(float), 256 * sizeof(float), 128, cudaMemcpyDeviceToDevice));
+        float *wt = S.buf + off, *ainv = wt + cmf_tc_tiled_floats(256, 512), *bias = ainv + ainv_floats(256);
+        int rc = fmt ? cmf_tc_tile_weights_f16(tmp, 512, 256, 512, wt, ainv, 0) : cmf_tc_tile_weights(tmp, 512, 256, 512, wt, 0);
+        if (rc) { cudaFree(tmp); return rc; }
+        CMF_CUDA(cudaMemcpy(bias, m->seg[HD_T2F], 128 * sizeof(float), cudaMemcpyDeviceToDevice));
+        CMF_CUDA(cudaMemcpy(bias + 128, m->seg[HD_T2M], 128 * sizeof(float), cudaMemcpyDeviceToDevice));
+        CMF_CUDA(cudaDeviceSynchronize());
+        cudaFree(tmp);
+        S.hd_w2.wt = wt; S.hd_w2.ainv = fmt ? ainv : nullptr; S.hd_t2 = bias;
     }
     CMF_CUDA(cudaDeviceSynchronize());
     return CMF_OK;
@@ -511,17 +528,22 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
     if (m->tc) {
         if (F) RUN(C_REDUCE, 0, cmf_launch_pair_absmax(bc, n, w.PROP, 256, 256, AM(AM_PROP), st));
         TcArgs ta_ = tc_plain(T.hd_w1, F, 512, 256, w.PROP, 256, w.HD1, 512, nullptr, bn, CMF_ACT_RELU, w.PBH, 512, n);
-        tc_bound(ta_, 0.f, AM(AM_PROP), 1.f);
+        tc_bound(ta_, 0.f, AM(AM_PROP), 1.f); if (F) { ta_.amax_out = AM(AM_HD1); }
         RUN(C_GEMM_POINTWISE, tflops(ta_, 256), cmf_launch_tc_auto(ta_, st));
+        TcArgs tb_ = tc_plain(T.hd_w2, F, 256, 512, w.HD1, 512, w.HD2, 256, T.hd_t2, bn, CMF_ACT_RELU, nullptr, 0, n);
+        tc_bound(tb_, 0.f, AM(AM_HD1), 1.f);
+        RUN(C_GEMM_POINTWISE, tflops(tb_, 256), cmf_launch_tc_auto(tb_, st));
     } else {
         const GemmArgs ga_ = mk(S(HD_W1), 256, w.PROP, 256, w.HD1, 512, nullptr, 512, 256, bn, CMF_ACT_RELU, w.PBH, 512, n);
         RUN(C_GEMM_POINTWISE, gflops(ga_), cmf_launch_gemm1(ga_, st));
     }
     {
         GemmBatch gb; gb.count = 2;
-        gb.g[0] = mk(S(HD_W2F), 256, w.HD1, 512, w.HD2, 256, S(HD_T2F), 128, 256, bn, CMF_ACT_RELU);
-        gb.g[1] = mk(S(HD_W2M), 256, w.HD1 + 256, 512, w.HD2 + 128, 256, S(HD_T2M), 128, 256, bn, CMF_ACT_RELU);
-        RUN(C_GEMM_POINTWISE, gflops(gb), cmf_launch_gemm(gb, st));
+        if (!m->tc) {
+            gb.g[0] = mk(S(HD_W2F), 256, w.HD1, 512, w.HD2, 256, S(HD_T2F), 128, 256, bn, CMF_ACT_RELU);
+            gb.g[1] = mk(S(HD_W2M), 256, w.HD1 + 256, 512, w.HD2 + 128, 256, S(HD_T2M), 128, 256, bn, CMF_ACT_RELU);
+            RUN(C_GEMM_POINTWISE, gflops(gb), cmf_launch_gemm(gb, st));
+        }
         gb.g[0] = mk(S(HD_W3F), 128, w.HD2, 256, w.HD3, 128, S(HD_T3F), 64, 128, bn, CMF_ACT_RELU);
         gb.g[1] = mk(S(HD_W3M), 128, w.HD2 + 128, 256, w.HD3 + 64, 128, S(HD_T3M), 64, 128, bn, CMF_ACT_RELU);
         RUN(C_GEMM_POINTWISE, gflops(gb), cmf_launch_gemm(gb, st));

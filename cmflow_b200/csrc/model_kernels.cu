@@ -547,31 +547,48 @@ int cmf_launch_fc_build_h1(int b, int n, const float *xyz1_planar, const float *
 }
 
 // out[i][c] = sum_k WeightNet(dir_ik)[c] * src_row(i,k)[c]     (radarflow_util.py:223-225 and 233-235)
+// One CTA handles FCR_PTS consecutive points: thread (p, k) first runs the two hidden WeightNet layers (3 -> 8 -> 8) of its (point,
+// neighbour) pair in registers; then thread t owns channels 4t..4t+3, keeps its four rows of the last WeightNet layer (8 -> 512) in
+// registers for all FCR_PTS points (they used to be re-read per point: as many bytes as the gathered rows), and software-pipelines the
+// eight 2 KB row gathers of point p+1 under the arithmetic of point p.
+constexpr int FCR_PTS = 16;
 __global__ void __launch_bounds__(128)
-fc_reduce_kernel(int n, const float *__restrict__ xyzq, const float *__restrict__ xyzc, const int *__restrict__ knn,
+fc_reduce_kernel(long long points, int n, const float *__restrict__ xyzq, const float *__restrict__ xyzc, const int *__restrict__ knn,
                  WeightNetP wn, const float *__restrict__ src, int gather, float *__restrict__ out, int ldo) {
-    __shared__ float h1[8][8], h2[8][8];
-    __shared__ int sj[8];
-    const int bi = blockIdx.x, b = bi / n, i = bi - b * n, t = threadIdx.x;
-    const float *pq = xyzq + (size_t)b * 3 * n, *pc = xyzc + (size_t)b * 3 * n;
-    if (t < 64) {
-        const int k = t >> 3, u = t & 7;
-        const int j = __ldg(knn + (size_t)bi * 8 + k);
-        if (u == 0) sj[k] = j;
-        const float dx = __fsub_rn(__ldg(pc + j), __ldg(pq + i)), dy = __fsub_rn(__ldg(pc + n + j), __ldg(pq + n + i)),
-                    dz = __fsub_rn(__ldg(pc + 2 * n + j), __ldg(pq + 2 * n + i));
-        const float4 a = ld4(wn.A1 + u * 4);
-        h1[k][u] = fmaxf(fmaf(a.z, dz, fmaf(a.y, dy, fmaf(a.x, dx, __ldg(wn.a1 + u)))), 0.f);
-    }
-    __syncthreads();
-    if (t < 64) {
-        const int k = t >> 3, u = t & 7;
-        float s = __ldg(wn.a2 + u);
+    __shared__ __align__(16) float sh2[FCR_PTS][8][8];
+    __shared__ long long srow[FCR_PTS][8];
+    const int t = threadIdx.x;
+    const long long base = (long long)blockIdx.x * FCR_PTS;
+    {
+        const int p = t >> 3, k = t & 7;
+        const long long bi = base + p;
+        float h2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        long long row = 0;
+        if (bi < points) {
+            const long long b = bi / n; const int i = (int)(bi - b * n);
+            const float *pq = xyzq + (size_t)b * 3 * n, *pc = xyzc + (size_t)b * 3 * n;
+            const int j = __ldg(knn + (size_t)bi * 8 + k);
+            row = gather ? b * n + j : bi * 8 + k;
+            const float dx = __fsub_rn(__ldg(pc + j), __ldg(pq + i)), dy = __fsub_rn(__ldg(pc + n + j), __ldg(pq + n + i)),
+                        dz = __fsub_rn(__ldg(pc + 2 * n + j), __ldg(pq + 2 * n + i));
+            float h1[8];
 #pragma unroll
-        for (int v = 0; v < 8; ++v) s = fmaf(__ldg(wn.A2 + u * 8 + v), h1[k][v], s);
-        h2[k][u] = fmaxf(s, 0.f);
+            for (int u = 0; u < 8; ++u) {
+                const float4 a = ld4(wn.A1 + u * 4);
+                h1[u] = fmaxf(fmaf(a.z, dz, fmaf(a.y, dy, fmaf(a.x, dx, __ldg(wn.a1 + u)))), 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                float sacc = __ldg(wn.a2 + u);
+#pragma unroll
+                for (int v = 0; v < 8; ++v) sacc = fmaf(__ldg(wn.A2 + u * 8 + v), h1[v], sacc);
+                h2[u] = fmaxf(sacc, 0.f);
+            }
+        }
+        *reinterpret_cast<float4 *>(&sh2[p][k][0]) = make_float4(h2[0], h2[1], h2[2], h2[3]);
+        *reinterpret_cast<float4 *>(&sh2[p][k][4]) = make_float4(h2[4], h2[5], h2[6], h2[7]);
+        srow[p][k] = row;
     }
-    __syncthreads();
     float4 A3[4][2];
     float a3[4];
 #pragma unroll
@@ -579,24 +596,39 @@ fc_reduce_kernel(int n, const float *__restrict__ xyzq, const float *__restrict_
         A3[c][0] = ld4(wn.A3 + (t * 4 + c) * 8); A3[c][1] = ld4(wn.A3 + (t * 4 + c) * 8 + 4);
         a3[c] = __ldg(wn.a3 + t * 4 + c);
     }
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    __syncthreads();
+    const int np = (points - base) < FCR_PTS ? (int)(points - base) : FCR_PTS;
+    float4 cur[8], nxt[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float4 s = gather ? ld4(src + ((size_t)b * n + sj[k]) * 512 + t * 4) : ld4(src + ((size_t)bi * 8 + k) * 512 + t * 4);
-        const float sv[4] = {s.x, s.y, s.z, s.w};
+    for (int k = 0; k < 8; ++k) cur[k] = ld4(src + (size_t)srow[0][k] * 512 + t * 4);
+    for (int p = 0; p < np; ++p) {
+        if (p + 1 < np) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float w = a3[c];
-            w = fmaf(A3[c][0].x, h2[k][0], w); w = fmaf(A3[c][0].y, h2[k][1], w); w = fmaf(A3[c][0].z, h2[k][2], w); w = fmaf(A3[c][0].w, h2[k][3], w);
-            w = fmaf(A3[c][1].x, h2[k][4], w); w = fmaf(A3[c][1].y, h2[k][5], w); w = fmaf(A3[c][1].z, h2[k][6], w); w = fmaf(A3[c][1].w, h2[k][7], w);
-            acc[c] = fmaf(fmaxf(w, 0.f), sv[c], acc[c]);
+            for (int k = 0; k < 8; ++k) nxt[k] = ld4(src + (size_t)srow[p + 1][k] * 512 + t * 4);
         }
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float4 ha = *reinterpret_cast<const float4 *>(&sh2[p][k][0]), hb = *reinterpret_cast<const float4 *>(&sh2[p][k][4]);
+            const float sv[4] = {cur[k].x, cur[k].y, cur[k].z, cur[k].w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float w = a3[c];
+                w = fmaf(A3[c][0].x, ha.x, w); w = fmaf(A3[c][0].y, ha.y, w); w = fmaf(A3[c][0].z, ha.z, w); w = fmaf(A3[c][0].w, ha.w, w);
+                w = fmaf(A3[c][1].x, hb.x, w); w = fmaf(A3[c][1].y, hb.y, w); w = fmaf(A3[c][1].z, hb.z, w); w = fmaf(A3[c][1].w, hb.w, w);
+                acc[c] = fmaf(fmaxf(w, 0.f), sv[c], acc[c]);
+            }
+        }
+        *reinterpret_cast<float4 *>(out + (size_t)(base + p) * ldo + t * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
     }
-    *reinterpret_cast<float4 *>(out + (size_t)bi * ldo + t * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
 }
 int cmf_launch_fc_reduce(int b, int n, const float *xyzq_planar, const float *xyzc_planar, const int *knn,
                          WeightNetP wn, const float *src, int gather, float *out, int ldo, cudaStream_t st) {
-    fc_reduce_kernel<<<b * n, 128, 0, st>>>(n, xyzq_planar, xyzc_planar, knn, wn, src, gather, out, ldo);
+    const long long points = (long long)b * n;
+    if (points <= 0) return CMF_OK;
+    fc_reduce_kernel<<<cmf_divup(points, FCR_PTS), 128, 0, st>>>(points, n, xyzq_planar, xyzc_planar, knn, wn, src, gather, out, ldo);
     CMF_LAUNCH_CHECK();
     return CMF_OK;
 }
