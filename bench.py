@@ -98,7 +98,19 @@ def time_cpu_port(pairs, points, steps, warmup, threads):
     return pairs * steps / dt, dt / steps
 
 
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else that libraries print (NCCL's version banner...) was diverted to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -128,7 +140,7 @@ def main():
         # bounded sample: ~1 s of CPU work per step at N=256 (the whole --steps K run stays within a few minutes)
         sample = max(1, min(16, (16 * 256 * 256) // (args.points * args.points)))
         v, spp = time_cpu_port(sample, args.points, K, min(W, 1), cores)
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": "frame-pairs/sec CMFlow forward", "value": v, "unit": "frame-pairs/s", "n_gpus": args.gpus,
             "steps": K, "warmup": min(W, 1), "ms_per_step": spp * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic radar pairs, seeded random-init weights",
@@ -201,7 +213,7 @@ def main():
         for i in range(K):
             fwd_dev(i)
         torch.cuda.synchronize()
-        print(json.dumps({"ncu_harness": True, "launches_per_step": net.launches_per_forward()}))
+        emit({"ncu_harness": True, "launches_per_step": net.launches_per_forward()})
         return
     sampler = ClockSampler(local) if rank == 0 else None
     ms_dev = timed(fwd_dev, K)
@@ -261,7 +273,7 @@ def main():
                             "peak_gbs": peaks["hbm_gbs"], "frac": alg_bytes_launch / (d["ms_per_step"] / max(1, d["launches_per_step"]) * 1e-3) / 1e9 / peaks["hbm_gbs"],
                             "note": "not the binding bound (86 flop/B); gathered rows are served by L2, see profiles/r01b_tc_kernels_ncu_full.md"},
                     "launches_per_step": d["launches_per_step"], "avg_launch_ms": d["ms_per_step"] / max(1, d["launches_per_step"]),
-                    "note": (f"{split[0]}: three MMAs per algorithmic MAC (kind::tf32 runs at half the bf16 rate) => ceiling = bf16 peak / {split[1]}" if tc else
+                    "note": (f"{split[0]}: three MMAs per algorithmic MAC" + (" (kind::tf32 runs at half the bf16 rate)" if args.precision == "tf32x3" else "") + f" => ceiling = bf16 peak / {split[1]}" if tc else
                              "strict-fp32 FMA build (no tensor cores): the chip's fp32 FMA ceiling is 74.5 TFLOP/s, ~1/19 of this peak")}
         if not args.no_cpu_baseline and world == 1:
             cs = max(1, min(16, (16 * 256 * 256) // (N * N)))
@@ -282,7 +294,7 @@ def main():
             "clocks": clocks, "roofline": roofline, "kernels": prof, "cpu_baseline": cpu,
             "workspace_bytes": net.workspace_bytes(),
         }
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
