@@ -98,6 +98,46 @@ def time_cpu_port(pairs, points, steps, warmup, threads):
     return pairs * steps / dt, dt / steps
 
 
+def time_ref_cuda(pairs, points, steps, warmup, dev):
+    """Informational GPU baseline (north_star's "reference's own lib/src CUDA build"): the reference's ball-query kernel compiled UNMODIFIED
+    (oracle/_ref/libpointnet2_ref.so) under the PyTorch-eager, unfused model (oracle/cmflow_oracle.py evaluated on CUDA tensors: cuBLAS fp32
+    for the 1x1 convs, torch.gather grouping, square_distance + topk k-NN as radarflow_util.py:8-30,88-99).  Part of the baseline leg: rank 0,
+    N=1, bounded sample; the oracle stays the checker, never the product path."""
+    import types
+    from cmflow_b200.synth import make_pairs, synthetic_state_dict
+    from oracle import cmflow_oracle as O
+    from oracle import refcuda as R
+    if not R.available():
+        return None
+
+    def knn_point(nsample, xyz, new_xyz):            # radarflow_util.py:88-99 (square_distance + topk)
+        d = -2 * torch.matmul(new_xyz, xyz.permute(0, 2, 1))
+        d = d + torch.sum(new_xyz ** 2, -1).unsqueeze(-1) + torch.sum(xyz ** 2, -1).unsqueeze(1)
+        dist, idx = torch.topk(torch.clamp(d, min=0.0), nsample, dim=-1, largest=False, sorted=False)
+        return idx.int(), dist
+
+    sd = {k: v.to(dev) for k, v in synthetic_state_dict(0).items()}
+    pc1, pc2, ft1, ft2 = (t.to(dev) for t in make_pairs(pairs, points, seed=1234)[:4])
+    saved = O.P
+    O.P = types.SimpleNamespace(ball_query=R.ball_query, knn_point=knn_point)
+    try:
+        with torch.no_grad():
+            for _ in range(warmup):
+                O.cmflow_forward(sd, pc1, pc2, ft1, ft2)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                O.cmflow_forward(sd, pc1, pc2, ft1, ft2)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    finally:
+        O.P = saved
+    return {"value": pairs / (ms * 1e-3), "unit": "frame-pairs/s", "ms_per_step": ms, "kind": "reference lib/src ball-query kernel (unmodified, sm_100a) + PyTorch-eager fp32 model on the same GPU",
+            "sample": f"{pairs} pairs/step x {steps} steps (N={points}); the unfused model materialises 34 MB/pair of grouped tensors at K=32"}
+
+
 def emit(line):
     """The ONE JSON line goes to the real stdout; everything else that libraries print (NCCL's version banner...) was diverted to stderr."""
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
@@ -280,6 +320,12 @@ def main():
             v, spp = time_cpu_port(cs, N, 12, 1, cores)          # ~10-20 s of CPU work
             cpu = {"value": v, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
                    "sample": f"{cs} pairs/step x 12 steps (N={N}), oracle/cmflow_oracle.py CPU port of the reference forward, {cores} threads"}
+        ref_cuda = None
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                ref_cuda = time_ref_cuda(max(1, min(32, (32 * 256 * 256) // (N * N))), N, 5, 2, dev)
+            except Exception as e:                      # informational only
+                ref_cuda = {"unavailable": repr(e)[:200]}
         h2d = 4 * B * 3 * N * 4
         d2h = B * 3 * N * 4 + B * N * 4 + B * 16 * 4 + B * N
         line = {
@@ -291,7 +337,7 @@ def main():
             "e2e": {"value": total_pairs * K / (ms_host / 1e3), "unit": "frame-pairs/s", "ms_per_step": ms_host / K,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches * K, "launches_per_step": launches,
-            "clocks": clocks, "roofline": roofline, "kernels": prof, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roofline, "kernels": prof, "cpu_baseline": cpu, "ref_cuda_baseline": ref_cuda,
             "workspace_bytes": net.workspace_bytes(),
         }
         emit(line)

@@ -41,6 +41,9 @@ SIGNATURES = {
     "cmf_model_forward": [_vp, _i, _i] + [_vp] * 11,
     "cmf_model_forward_host": [_vp, _i, _i] + [_vp] * 11,
     "cmf_model_tap": [_vp, ctypes.c_char_p],
+    "cmf_model_set_raflow": [_vp, _f, _f],
+    "cmf_model_forward_raflow": [_vp, _i, _i] + [_vp] * 10,
+    "cmf_raflow_refine": [_i, _i, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp],
     "cmf_model_set_profiling": [_vp, _i],
     "cmf_model_set_mode": [_vp, _i],
     "cmf_model_get_mode": [_vp],

@@ -61,19 +61,32 @@ class _Head(nn.Module):           # FlowHead / MotionHead (radarflow_util.py:240
         self.conv2 = nn.Conv2d(64, cout, 1, bias=False)
 
 
+class _FlowDecoder(nn.Module):    # FlowDecoder (radarflow_util.py:321-337): parameter container of RaFlow.fd_layer
+    def __init__(self):
+        super().__init__()
+        self.mse = _MultiScale(1027, (512, 256, 64), (64, 64, 64))
+        self.fp = _Head(3)
+
+
 class _EngineModel(nn.Module):
     _temporal = False
+    _raflow = False
 
     def __init__(self, args):
         super().__init__()
         self.npoints = args.num_points
-        self.stat_thres = 0.5 if self._temporal else args.stat_thres      # cmflow_t.py:18 hard-codes 0.50
         self.mse_layer = _MultiScale(3, (32, 32, 64), (64, 64, 64))
         self.fc_layer = _Correlator()
-        self.mse_layer2 = _MultiScale(1027, (512, 256, 64), (64, 64, 64))
-        if self._temporal:
-            self.gru = nn.GRU(input_size=256, hidden_size=256, num_layers=1)
-        self.fp, self.mp = _Head(3), _Head(1)
+        if self._raflow:
+            self.rigid_thres, self.rigid_pcs = args.rigid_thres, 0.25           # raflow.py:16-17
+            self.stat_thres = 0.5                                               # unused
+            self.fd_layer = _FlowDecoder()
+        else:
+            self.stat_thres = 0.5 if self._temporal else args.stat_thres        # cmflow_t.py:18 hard-codes 0.50
+            self.mse_layer2 = _MultiScale(1027, (512, 256, 64), (64, 64, 64))
+            if self._temporal:
+                self.gru = nn.GRU(input_size=256, hidden_size=256, num_layers=1)
+            self.fp, self.mp = _Head(3), _Head(1)
         self._handle = None
         self.eval()
 
@@ -99,7 +112,7 @@ class _EngineModel(nn.Module):
 
     def _engine(self, device):
         if self._handle is None:
-            blob = _weights.pack(self.state_dict(), temporal=self._temporal)
+            blob = _weights.pack(self.state_dict(), temporal=self._temporal, raflow=self._raflow)
             L = lib()
             assert blob.size == L.cmf_model_blob_floats(int(self._temporal))
             h = ctypes.c_void_p()
@@ -107,6 +120,8 @@ class _EngineModel(nn.Module):
                 check(L.cmf_model_create(ctypes.byref(h), blob.ctypes.data_as(ctypes.c_void_p), blob.size,
                                          int(self._temporal), float(self.stat_thres)))
             self._handle = h
+            if self._raflow:
+                check(L.cmf_model_set_raflow(h, float(self.rigid_thres), float(self.rigid_pcs)))
             if getattr(self, "_mode", None) is not None:
                 check(L.cmf_model_set_mode(h, self._mode))
         return self._handle
@@ -202,3 +217,25 @@ class CMFlow_T(_EngineModel):
 
     def forward(self, pc1, pc2, feature1, feature2, label_m, mode, gfeat):
         return self._run(pc1, pc2, feature1, feature2, label_m, mode, gfeat)
+
+
+class RaFlow(_EngineModel):
+    """models/raflow.py:9 -- forward(pc1, pc2, feature1, feature2, interval) -> (output, sf_agg, pre_trans, mask_s)."""
+    _raflow = True
+
+    def forward(self, pc1, pc2, feature1, feature2, interval):
+        ins = [t.float().contiguous() for t in (pc1, pc2, feature1, feature2)]
+        if not ins[0].is_cuda:
+            raise CmfError("cmflow_b200 has no CPU path: inputs must be CUDA tensors")
+        B, _, N = ins[0].shape
+        dev = ins[0].device
+        dt = interval.to(dev).float().contiguous().view(-1)
+        if dt.numel() != B:
+            raise CmfError("interval must hold one value per frame pair")
+        h = self._engine(dev)
+        out = torch.empty(B, 3, N, device=dev); sf = torch.empty(B, 3, N, device=dev)
+        T = torch.empty(B, 4, 4, device=dev); mask = torch.empty(B, N, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().cmf_model_forward_raflow(h, B, N, dptr(ins[0]), dptr(ins[1]), dptr(ins[2]), dptr(ins[3]), dptr(dt),
+                                                 dptr(out), dptr(sf), dptr(T), dptr(mask), stream_ptr()))
+        return out, sf, T, mask.bool()

@@ -147,6 +147,8 @@ struct cmf_model {
     struct TcSet { float *buf = nullptr; TcW fc_wc, fc_wn, fc_w2, fc_w3, m2_wp, m2_w2[4], m2_w3[4], hd_w1;
                    TcW m1_w2[4], m1_w3[4], m1_v[4][3], m2_v[4][3];
                    TcW hd_w2; const float *hd_t2 = nullptr; } tcw[2];      // heads layer 2: [W2F 0; 0 W2M] (256 x 512) and its stacked bias      // narrow chains (tc_chain.cu, fmt 1 only)
+    // RaFlow (models/raflow.py): same backbone, no motion head (its weights are zero in the blob), SFR module instead of the Kabsch head
+    int raflow = 0; float rigid_thres = 0.15f, rigid_pcs = 0.25f;
     int chain = 1;               // CMF_CHAIN=0: keep the fp32 FMA kernels for set-conv #1 / mlp2 in fp16x3 mode (A/B testing)
     // host-side norms for the fp16x3 scale bounds: max row L1 of the rel-xyz / direction columns, max row L1 and max |bias| of the layers
     // whose outputs are written pre-split (flow-embedding conv1, set-conv #2 layer 2)
@@ -378,7 +380,7 @@ static int run_mse_layer(cmf_model *m, int bc, int n, const float *pc, const flo
 
 static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const float *pc2, const float *ft1,
                          const float *ft2, const float *gprev, float *sf_agg, float *stat_cls, float *pre_trans,
-                         uint8_t *mask, float *gfeat_out, cudaStream_t st) {
+                         uint8_t *mask, float *gfeat_out, cudaStream_t st, const float *interval = nullptr, float *raw_flow = nullptr) {
     Work &w = m->w;
     const long long bn = (long long)bc * n;
     auto S = [&](int i) { return m->seg[i]; };
@@ -548,6 +550,11 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
         gb.g[1] = mk(S(HD_W3M), 128, w.HD2 + 128, 256, w.HD3 + 64, 128, S(HD_T3M), 64, 128, bn, CMF_ACT_RELU);
         RUN(C_GEMM_POINTWISE, gflops(gb), cmf_launch_gemm(gb, st));
     }
+    if (m->raflow) {       // FlowPredictor read-out into the caller's `output`, then the SFR module (raflow.py:79-117); w.FLOW takes the unused scores
+        RUN(C_HEAD_KABSCH, 0, cmf_launch_head_final(bc, n, w.HD3, 128, S(HD_W4), S(HD_W4) + 192, raw_flow, w.FLOW, st));
+        RUN(C_HEAD_KABSCH, 0, cmf_launch_raflow_sfr(bc, n, pc1, ft1, raw_flow, interval, m->rigid_thres, m->rigid_pcs, sf_agg, pre_trans, mask, st));
+        return CMF_OK;
+    }
     RUN(C_HEAD_KABSCH, 0, cmf_launch_head_final(bc, n, w.HD3, 128, S(HD_W4), S(HD_W4) + 192, w.FLOW, stat_cls, st));
     // ego-motion head + refinement (cmflow.py:96-125); CMFlow-T omits the +1e-4 (cmflow_t.py:119)
     RUN(C_HEAD_KABSCH, 0, cmf_launch_kabsch(bc, n, pc1, w.FLOW, 1, stat_cls, 1, m->temporal ? 0.f : 1e-4f, m->stat_thres, pre_trans, sf_agg, mask, st));
@@ -640,6 +647,7 @@ extern "C" int cmf_model_forward(cmf_model *m, int b, int n, const float *pc1, c
     CMF_REQUIRE((long long)n * 32 * 512 < 2147483647LL / 2, "N too large for 32-bit column indices");
     CMF_REQUIRE(pc1 && pc2 && ft1 && ft2 && sf_agg && stat_cls && pre_trans && mask, "null pointer");
     CMF_REQUIRE(!m->temporal || gfeat_out, "CMFlow-T needs gfeat_out");
+    CMF_REQUIRE(!m->raflow, "this engine was switched to RaFlow: call cmf_model_forward_raflow");
     int rc = ensure_workspace(m, b, n);
     if (rc != CMF_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -654,6 +662,39 @@ extern "C" int cmf_model_forward(cmf_model *m, int b, int n, const float *pc1, c
                            gfeat_prev ? gfeat_prev + (size_t)b0 * 256 : nullptr,
                            sf_agg + b0 * pn, stat_cls + (size_t)b0 * n, pre_trans + (size_t)b0 * 16, mask + (size_t)b0 * n,
                            gfeat_out ? gfeat_out + (size_t)b0 * 256 : nullptr, st);
+        if (rc != CMF_OK) return rc;
+    }
+    return CMF_OK;
+}
+
+extern "C" int cmf_model_set_raflow(cmf_model *m, float rigid_thres, float rigid_pcs) {
+    CMF_REQUIRE(m, "null model");
+    CMF_REQUIRE(!m->temporal, "RaFlow has no temporal variant");
+    m->raflow = 1; m->rigid_thres = rigid_thres; m->rigid_pcs = rigid_pcs;
+    return CMF_OK;
+}
+
+extern "C" int cmf_model_forward_raflow(cmf_model *m, int b, int n, const float *pc1, const float *pc2, const float *ft1, const float *ft2,
+                                        const float *interval, float *output, float *sf_agg, float *pre_trans, uint8_t *mask_s, void *stream) {
+    CMF_REQUIRE(m, "null model");
+    CMF_REQUIRE(m->raflow, "call cmf_model_set_raflow first");
+    CMF_REQUIRE(b >= 0 && n >= 0, "negative size");
+    if (b == 0) return CMF_OK;
+    CMF_REQUIRE(n >= 8, "need at least 8 points per cloud (knn_point(8, ...): torch.topk raises below that)");
+    CMF_REQUIRE((long long)n * 32 * 512 < 2147483647LL / 2, "N too large for 32-bit column indices");
+    CMF_REQUIRE(pc1 && pc2 && ft1 && ft2 && interval && output && sf_agg && pre_trans && mask_s, "null pointer");
+    int rc = ensure_workspace(m, b, n);
+    if (rc != CMF_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    m->launches = 0;
+    for (int i = 0; i < 16; ++i) { m->work[i] = 0; m->nlaunch[i] = 0; }
+    m->prof.clear(); m->pool_used = 0;
+    m->last_b = b < m->cap_bc ? b : m->cap_bc; m->last_n = n;
+    const size_t pn = (size_t)3 * n;
+    for (int b0 = 0; b0 < b; b0 += m->cap_bc) {
+        const int bc = (b - b0) < m->cap_bc ? (b - b0) : m->cap_bc;
+        rc = forward_chunk(m, bc, n, pc1 + b0 * pn, pc2 + b0 * pn, ft1 + b0 * pn, ft2 + b0 * pn, nullptr, sf_agg + b0 * pn, nullptr,
+                           pre_trans + (size_t)b0 * 16, mask_s + (size_t)b0 * n, nullptr, st, interval + b0, output + b0 * pn);
         if (rc != CMF_OK) return rc;
     }
     return CMF_OK;

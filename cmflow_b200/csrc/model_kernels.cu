@@ -853,6 +853,122 @@ int cmf_launch_kabsch(int b, int n, const float *pc1, const float *pc_or_flow, i
     return CMF_OK;
 }
 
+// =================================================================================================
+// RaFlow's scene-flow refinement (SFR_module + rigid_transform_torch, models/raflow.py:79-156): one CTA per frame pair.
+//   T0 = rigid fit of (pc1, pc1 + output) over all points; rigid flow sf_rg = T0.[p;1] - p;
+//   mask_s = |(vel*interval - <sf_rg, p>/|p|) / vel| < rigid_thres  (vel = feature1 channel 0);
+//   if more than rigid_pcs of the points are inliers: T1 = fit over the inliers, inliers take T1's rigid flow; else T0 and the raw flow.
+// Reference quirks kept: centroids are divided by N even for the masked fit (raflow.py:129-130), all points are centred but only masked
+// columns enter H (:137-140), ROW 2 of V is negated on reflection (:151).  Moments in fp64, one pass per fit.
+// =================================================================================================
+__device__ __forceinline__ void raflow_fit(const double t[16], int n, float *sT /* 12 */) {
+    const double inv_n = 1.0 / (double)n;
+    const double cA[3] = {t[1] * inv_n, t[2] * inv_n, t[3] * inv_n}, cB[3] = {t[4] * inv_n, t[5] * inv_n, t[6] * inv_n};
+    double H[3][3], R[3][3];
+    // sum_i w_i (a_i - cA)(b_i - cB)^T = M_ab - cA m_b^T - m_a cB^T + m_0 cA cB^T
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) H[r][c] = t[7 + r * 3 + c] - cA[r] * t[4 + c] - t[1 + r] * cB[c] + t[0] * cA[r] * cB[c];
+    polar_rotation_3x3(H, R);
+    for (int r = 0; r < 3; ++r) {
+        const double tr = -(R[r][0] * cA[0] + R[r][1] * cA[1] + R[r][2] * cA[2]) + cB[r];
+        sT[r * 4 + 0] = (float)R[r][0]; sT[r * 4 + 1] = (float)R[r][1]; sT[r * 4 + 2] = (float)R[r][2]; sT[r * 4 + 3] = (float)tr;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+raflow_sfr_kernel(int n, const float *__restrict__ pc1, const float *__restrict__ ft1, const float *__restrict__ flow,
+                  const float *__restrict__ interval, float rigid_thres, float rigid_pcs,
+                  float *__restrict__ sf_agg, float *__restrict__ trans, uint8_t *__restrict__ mask) {
+    __shared__ double red[8][17];
+    __shared__ float sT0[12], sT1[12];
+    __shared__ int s_use1;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *pa = pc1 + (size_t)b * 3 * n, *pf = flow + (size_t)b * 3 * n, *pv = ft1 + (size_t)b * 3 * n;
+    uint8_t *pm = mask + (size_t)b * n;
+    const float dt = interval[b];
+    double m[17];
+    auto accumulate = [&](bool masked) {
+#pragma unroll
+        for (int i = 0; i < 17; ++i) m[i] = 0.0;
+        for (int i = tid; i < n; i += blockDim.x) {
+            const float ax = pa[i], ay = pa[n + i], az = pa[2 * n + i];
+            const float bx = __fadd_rn(ax, pf[i]), by = __fadd_rn(ay, pf[n + i]), bz = __fadd_rn(az, pf[2 * n + i]);   // pc1_warp (raflow.py:85)
+            double wi = 1.0;
+            if (masked) {
+                // rigid flow of T0 and its radial projection (raflow.py:92-98)
+                const float rx = __fsub_rn(fmaf(sT0[2], az, fmaf(sT0[1], ay, fmaf(sT0[0], ax, sT0[3]))), ax);
+                const float ry = __fsub_rn(fmaf(sT0[6], az, fmaf(sT0[5], ay, fmaf(sT0[4], ax, sT0[7]))), ay);
+                const float rz = __fsub_rn(fmaf(sT0[10], az, fmaf(sT0[9], ay, fmaf(sT0[8], ax, sT0[11]))), az);
+                const float proj = __fdiv_rn(fmaf(rz, az, fmaf(ry, ay, __fmul_rn(rx, ax))), sqrtf(fmaf(az, az, fmaf(ay, ay, __fmul_rn(ax, ax)))));
+                const float vel = pv[i];
+                const float ratio = fabsf(__fdiv_rn(__fsub_rn(__fmul_rn(vel, dt), proj), vel));
+                const bool in = ratio < rigid_thres;                      // NaN / inf (vel == 0) -> false, as in torch
+                pm[i] = in ? 1 : 0;
+                wi = in ? 1.0 : 0.0;
+                m[16] += wi;
+            }
+            const double A[3] = {ax, ay, az}, Bv[3] = {bx, by, bz};
+            m[0] += wi;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                m[1 + r] += wi * A[r];
+                m[4 + r] += wi * Bv[r];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) m[7 + r * 3 + c] += wi * A[r] * Bv[c];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 17; ++i) m[i] = warp_sum_d(m[i]);
+        if (lane == 0)
+#pragma unroll
+            for (int i = 0; i < 17; ++i) red[warp][i] = m[i];
+        __syncthreads();
+    };
+    accumulate(false);
+    if (tid == 0) {
+        double t[16];
+        for (int i = 0; i < 16; ++i) { t[i] = 0; for (int wv = 0; wv < 8; ++wv) t[i] += red[wv][i]; }
+        raflow_fit(t, n, sT0);
+    }
+    __syncthreads();
+    accumulate(true);
+    if (tid == 0) {
+        double t[17];
+        for (int i = 0; i < 17; ++i) { t[i] = 0; for (int wv = 0; wv < 8; ++wv) t[i] += red[wv][i]; }
+        // (mask_s[b].sum() / N) > rigid_pcs in float32 (raflow.py:104)
+        s_use1 = __fdiv_rn((float)t[16], (float)n) > rigid_pcs ? 1 : 0;
+        if (s_use1) raflow_fit(t, n, sT1);
+    }
+    __syncthreads();
+    const float *T = s_use1 ? sT1 : sT0;
+    if (tid < 16) trans[(size_t)b * 16 + tid] = tid < 12 ? T[tid] : (tid == 15 ? 1.f : 0.f);
+    float *so = sf_agg + (size_t)b * 3 * n;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float x = pa[i], y = pa[n + i], z = pa[2 * n + i];
+        const bool rigid = s_use1 && pm[i];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float rg = __fsub_rn(fmaf(T[r * 4 + 2], z, fmaf(T[r * 4 + 1], y, fmaf(T[r * 4 + 0], x, T[r * 4 + 3]))), r == 0 ? x : (r == 1 ? y : z));
+            so[r * n + i] = rigid ? rg : pf[r * n + i];
+        }
+    }
+}
+
+int cmf_launch_raflow_sfr(int b, int n, const float *pc1, const float *ft1, const float *flow, const float *interval,
+                          float rigid_thres, float rigid_pcs, float *sf_agg, float *trans, uint8_t *mask, cudaStream_t st) {
+    raflow_sfr_kernel<<<b, 256, 0, st>>>(n, pc1, ft1, flow, interval, rigid_thres, rigid_pcs, sf_agg, trans, mask);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
+extern "C" int cmf_raflow_refine(int b, int n, const float *pc1, const float *ft1, const float *flow, const float *interval,
+                                 float rigid_thres, float rigid_pcs, float *sf_agg, float *trans, uint8_t *mask, void *stream) {
+    CMF_REQUIRE(b >= 0 && n >= 1, "need b >= 0, n >= 1");
+    if (b == 0) return CMF_OK;
+    CMF_REQUIRE(pc1 && ft1 && flow && interval && sf_agg && trans && mask, "null pointer");
+    return cmf_launch_raflow_sfr(b, n, pc1, ft1, flow, interval, rigid_thres, rigid_pcs, sf_agg, trans, mask, (cudaStream_t)stream);
+}
+
 extern "C" int cmf_kabsch_refine(int b, int n, const float *pc1, const float *flow, const float *score,
                                  float eps, float stat_thres, float *trans, float *sf_agg, uint8_t *mask, void *stream) {
     CMF_REQUIRE(b >= 0 && n >= 1, "need b >= 0, n >= 1");

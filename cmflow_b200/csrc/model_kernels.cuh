@@ -55,6 +55,10 @@ int cmf_launch_kabsch(int b, int n, const float *pc1, const float *pc_or_flow, i
                       int normalise, float eps, float stat_thres, float *trans, float *sf_agg, uint8_t *mask,
                       cudaStream_t st);
 
+// RaFlow SFR module (models/raflow.py:79-117): flow (B,3,N) raw scene flow -> sf_agg, pre_trans (B,4,4), mask_s (B,N)
+int cmf_launch_raflow_sfr(int b, int n, const float *pc1, const float *ft1, const float *flow, const float *interval,
+                          float rigid_thres, float rigid_pcs, float *sf_agg, float *trans, uint8_t *mask, cudaStream_t st);
+
 // fp16x3 mode: out[b] = max(out[b], bits(max |X[(b*N+i)*ld + c]|, c < width))  (uint bit patterns; caller zeroes)
 int cmf_launch_pair_absmax(int b, int n, const float *X, int ld, int width, unsigned int *out, cudaStream_t st);
 // out[b] = max over points i and their k neighbours j of max(|xc_j - xq_i| per component)

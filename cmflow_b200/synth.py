@@ -127,3 +127,18 @@ def synthetic_state_dict(seed=0, temporal=False):
     head("fp", 3)
     head("mp", 1)
     return sd
+
+
+def raflow_state_dict(seed=0):
+    """Key layout of models/raflow.py:11-35: the CMFlow backbone with the decoder under fd_layer (FlowDecoder,
+    radarflow_util.py:321-337: fd_layer.mse = MultiScaleEncoder(1027 -> 512/256/64), fd_layer.fp = FlowPredictor) and no motion head."""
+    out = {}
+    for k, v in synthetic_state_dict(seed).items():
+        if k.startswith("mp."):
+            continue
+        if k.startswith("mse_layer2."):
+            k = "fd_layer.mse." + k[len("mse_layer2."):]
+        elif k.startswith("fp."):
+            k = "fd_layer.fp." + k[len("fp."):]
+        out[k] = v
+    return out

@@ -99,9 +99,33 @@ def segments(sd, temporal=False):
     return segs
 
 
-def pack(sd, temporal=False):
+def raflow_as_cmflow(sd):
+    """RaFlow's state_dict (models/raflow.py: mse_layer, fc_layer, fd_layer.mse, fd_layer.fp) in CMFlow's key layout: the decoder's
+    set-conv is CMFlow's mse_layer2, its FlowPredictor (radarflow_util.py:388-409) has FlowHead's shape, and the absent motion head
+    becomes zero weights with identity BatchNorm (its scores are never read: cmf_model_forward_raflow)."""
+    out = {}
+    for k, v in sd.items():
+        if k.startswith("fd_layer.mse."):
+            out["mse_layer2." + k[len("fd_layer.mse."):]] = v
+        elif k.startswith("fd_layer.fp."):
+            out["fp." + k[len("fd_layer.fp."):]] = v
+        else:
+            out[k] = v
+    last = 512
+    for i, co in enumerate((256, 128, 64)):
+        out[f"mp.sf_mlp.{i}.0.weight"] = torch.zeros(co, last, 1, 1)
+        out[f"mp.sf_mlp.{i}.1.weight"] = torch.ones(co); out[f"mp.sf_mlp.{i}.1.bias"] = torch.zeros(co)
+        out[f"mp.sf_mlp.{i}.1.running_mean"] = torch.zeros(co); out[f"mp.sf_mlp.{i}.1.running_var"] = torch.ones(co)
+        last = co
+    out["mp.conv2.weight"] = torch.zeros(1, 64, 1, 1)
+    return out
+
+
+def pack(sd, temporal=False, raflow=False):
     """state_dict (reference key layout, any device) -> contiguous float32 numpy blob."""
     sd = {k: v.detach().cpu() for k, v in sd.items()}
+    if raflow:
+        sd = raflow_as_cmflow(sd)
     segs = segments(sd, temporal)
     sizes = [(t.numel() + 3) // 4 * 4 for _, t in segs]
     blob = np.zeros(HDR + sum(sizes), dtype=np.float32)

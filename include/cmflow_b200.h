@@ -134,6 +134,20 @@ size_t cmf_model_blob_floats(int temporal);
 int cmf_model_create(cmf_model **out, const float *blob, size_t blob_floats, int temporal, float stat_thres);
 void cmf_model_destroy(cmf_model *m);
 
+/* RaFlow (models/raflow.py:11-164; the third model of models/model.py:21-27).  Same backbone as CMFlow -- pack the RaFlow state_dict with
+ * cmflow_b200/weights.py:pack(..., raflow=True) into a non-temporal blob -- but no motion head, and the scene-flow refinement of
+ * raflow.py:79-117 instead of the weighted Kabsch head.  cmf_model_set_raflow() switches an engine created with cmf_model_create(..., 0, ...)
+ * to that model (rigid_thres: configs.yaml:29 / raflow.py:16; rigid_pcs: raflow.py:17 = 0.25); afterwards only
+ * cmf_model_forward_raflow() may be called.  interval (B) seconds between the frames (main_util.py:139); outputs as RaFlow.forward returns
+ * them: output (B,3,N) initial flow, sf_agg (B,3,N), pre_trans (B,4,4), mask_s (B,N) uint8.  Device pointers; enqueues on `stream`. */
+int cmf_model_set_raflow(cmf_model *m, float rigid_thres, float rigid_pcs);
+int cmf_model_forward_raflow(cmf_model *m, int b, int n,
+                             const float *pc1, const float *pc2, const float *ft1, const float *ft2, const float *interval,
+                             float *output, float *sf_agg, float *pre_trans, uint8_t *mask_s, void *stream);
+/* The refinement alone (raflow.py:79-156) on a given initial flow: one CTA per pair, fp64 moments, 3x3 Jacobi SVD. */
+int cmf_raflow_refine(int b, int n, const float *pc1, const float *ft1, const float *flow, const float *interval,
+                      float rigid_thres, float rigid_pcs, float *sf_agg, float *trans, uint8_t *mask_s, void *stream);
+
 /* Workspace bytes the engine holds for the largest (B,N) seen so far (diagnostic). */
 size_t cmf_model_workspace_bytes(const cmf_model *m);
 

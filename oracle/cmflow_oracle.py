@@ -124,14 +124,14 @@ def weighted_kabsch(A, Bp, W):
     Vc[:, 2, :] = Vc[:, 2, :] * (-d.view(-1, 1))                           # :162
     R = Vc @ U.transpose(2, 1)                                             # :163
     t = -R @ cA + cB                                                       # :165
-    T = torch.zeros(A.shape[0], 4, 4, dtype=A.dtype)
+    T = torch.zeros(A.shape[0], 4, 4, dtype=A.dtype, device=A.device)
     T[:, :3, :3], T[:, :3, 3:], T[:, 3, 3] = R, t, 1.0                     # :167
     return T, H
 
 
 def rigid_to_flow(pc, T):
     """CMFlow.rigid_to_flow (models/cmflow.py:51-55)."""
-    h = torch.cat([pc, torch.ones(pc.shape[0], 1, pc.shape[2], dtype=pc.dtype)], 1)
+    h = torch.cat([pc, torch.ones(pc.shape[0], 1, pc.shape[2], dtype=pc.dtype, device=pc.device)], 1)
     return (T @ h)[:, :3] - pc
 
 
@@ -198,4 +198,80 @@ def cmflow_forward(sd, pc1, pc2, ft1, ft2, stat_thres=0.5, dtype=torch.float32, 
     if return_intermediates:
         out.update({"bq1": bq1, "bq2": bq2, "knn12": knn12, "knn11": knn11, "f1": f1, "f2": f2, "cor": cor,
                     "prop": prop, "flow": flow, "H": H, "weight": weight})
+    return out
+
+
+# ---- RaFlow (models/raflow.py) -------------------------------------------------------------------------------------------------
+def raflow_rigid_transform(A, Bp, M):
+    """RaFlow.rigid_transform_torch (models/raflow.py:119-156). A,Bp (B,3,N); M (B,N) 0/1 mask -> (B,4,4).
+    Quirks kept: the centroids are torch.mean over ALL N points of the masked coordinates (raflow.py:129-130: divided by N, not
+    by the number of masked points); every point is centred (:137-138) but only masked columns enter H (:140); reflection
+    handling negates ROW 2 of V (:151)."""
+    W = M.to(torch.bool).unsqueeze(2).to(A.dtype)
+    cA = (A.transpose(2, 1) * W).mean(1).unsqueeze(2)                       # :129,133
+    cB = (Bp.transpose(2, 1) * W).mean(1).unsqueeze(2)                      # :130,134
+    Am, Bm = A - cA, Bp - cB                                               # :137-138
+    H = Am @ (Bm.transpose(2, 1) * W)                                      # :140
+    U, _, Vh = torch.linalg.svd(H)                                         # :143
+    V = Vh.transpose(2, 1)
+    Z = V @ U.transpose(2, 1)                                              # :144
+    d = (torch.linalg.det(Z) < 0).to(A.dtype) * 2 - 1                      # :146-149
+    Vc = V.clone()
+    Vc[:, 2, :] = Vc[:, 2, :] * (-d.view(-1, 1))                           # :151
+    R = Vc @ U.transpose(2, 1)                                             # :152
+    t = -R @ cA + cB                                                       # :154
+    T = torch.zeros(A.shape[0], 4, 4, dtype=A.dtype, device=A.device)
+    T[:, :3, :3], T[:, :3, 3:], T[:, 3, 3] = R, t, 1.0                     # :156
+    return T
+
+
+def raflow_forward(sd, pc1, pc2, ft1, ft2, interval, rigid_thres=0.15, rigid_pcs=0.25, dtype=torch.float32,
+                   return_intermediates=False):
+    """RaFlow.forward(pc1, pc2, feature1, feature2, interval) (models/raflow.py:157-164) -> dict with output (B,3,N),
+    sf_agg (B,3,N), pre_trans (B,4,4), mask_s (B,N) bool.  interval (B,)."""
+    pc1, pc2 = pc1.float().contiguous(), pc2.float().contiguous()
+    f1in, f2in = ft1.to(dtype), ft2.to(dtype)
+    B, _, N = pc1.shape
+    x1t = pc1.permute(0, 2, 1).contiguous()
+    x2t = pc2.permute(0, 2, 1).contiguous()
+    bq1 = [P.ball_query(SA_RADIUS[l], SA_NSAMPLE[l], x1t, x1t) for l in range(4)]
+    bq2 = [P.ball_query(SA_RADIUS[l], SA_NSAMPLE[l], x2t, x2t) for l in range(4)]
+    # ROFE_module, raflow.py:47-77
+    f1 = multi_scale_encoder(sd, "mse_layer", pc1, f1in, dtype, bq1)          # :59
+    f2 = multi_scale_encoder(sd, "mse_layer", pc2, f2in, dtype, bq2)          # :60
+    g1 = f1.max(-1)[0].unsqueeze(2).expand(-1, -1, N)                         # :63
+    g2 = f2.max(-1)[0].unsqueeze(2).expand(-1, -1, pc2.shape[2])              # :64
+    pf1, pf2 = torch.cat([f1, g1], 1), torch.cat([f2, g2], 1)                 # :67-68
+    knn12 = P.knn_point(8, x2t, x1t)[0]
+    knn11 = P.knn_point(8, x1t, x1t)[0]
+    cor = feature_correlator(sd, pc1, pc2, pf1, pf2, dtype, knn12, knn11)     # :71
+    # FlowDecoder.forward, radarflow_util.py:339-350
+    emb = torch.cat([f1in, pf1, cor], 1)                                      # :341
+    prop = multi_scale_encoder(sd, "fd_layer.mse", pc1, emb, dtype, bq1)      # :343
+    gfeat = prop.max(-1)[0].unsqueeze(2).expand(-1, -1, N)                    # :344
+    output = _head(sd, "fd_layer.fp", torch.cat([prop, gfeat], 1), dtype)     # :345-348 (FlowPredictor :388-409)
+    # SFR_module, raflow.py:79-117
+    pcd = pc1.to(dtype)
+    warp = pcd + output                                                       # :85
+    ones = torch.ones(B, N, dtype=dtype, device=pc1.device)
+    trans = raflow_rigid_transform(pcd, warp, ones)                           # :89-90
+    sf_rg = rigid_to_flow(pcd, trans)                                         # :92
+    vel = f1in[:, 0]                                                          # :95
+    sf_proj = (sf_rg * pcd).sum(1) / torch.norm(pcd, dim=1)                   # :96
+    residual = vel * interval.to(dtype).unsqueeze(1) - sf_proj                # :97
+    mask_s = (residual / vel).abs() < rigid_thres                             # :98
+    pre_trans = torch.zeros_like(trans)
+    sf_agg = torch.zeros_like(output)
+    for b in range(B):                                                        # :103-114
+        if (mask_s[b].sum() / N) > rigid_pcs:
+            pre_trans[b] = raflow_rigid_transform(pcd[b:b + 1], warp[b:b + 1], mask_s[b:b + 1])[0]
+            sf_agg[b] = rigid_to_flow(pcd[b:b + 1], pre_trans[b:b + 1])[0]
+            keep = torch.logical_not(mask_s[b])
+            sf_agg[b][:, keep] = output[b][:, keep]
+        else:
+            pre_trans[b] = trans[b]
+            sf_agg[b] = output[b]
+    out = {"output": output, "sf_agg": sf_agg, "pre_trans": pre_trans, "mask_s": mask_s}
+    if return_intermediates:
+        out.update({"f1": f1, "f2": f2, "cor": cor, "prop": prop, "trans0": trans, "residual": residual, "vel": vel})
     return out

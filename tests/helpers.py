@@ -36,7 +36,7 @@ def stage_reference_weights(golden_dir, ref_root="/root/reference", parts=4):
     """Copy the reference's pretrained checkpoints next to the golden vectors (git-ignored; they travel to the GPU box with the
     repo snapshot, where /root/reference does not exist).  Split into a few files: large single files are not shipped."""
     out = os.path.join(golden_dir, "_weights")
-    for exp in ("cmflow_cvpr",):
+    for exp in ("cmflow_cvpr", "raflow_cvpr"):
         src = os.path.join(ref_root, "checkpoints", exp, "models", "model.best.t7")
         if not os.path.exists(src) or os.path.exists(os.path.join(out, f"{exp}.part0.t7")):
             continue
@@ -63,6 +63,9 @@ def case_weights(meta, golden_dir):
             # restore the reference's key order (load_state_dict does not care, packing does not either; kept for tidiness)
             return merged
         return None
+    if meta["model"] == "raflow":
+        from cmflow_b200.synth import raflow_state_dict
+        return raflow_state_dict(meta["weight_seed"])
     return synthetic_state_dict(meta["weight_seed"], temporal=(meta["model"] == "cmflow_t"))
 
 
@@ -86,4 +89,15 @@ def check_outputs(out, gold, rtol=FLOW_RTOL, stat_thres=0.5):
     assert errs["stat_cls"] <= rtol, errs            # probabilities in [0,1]: absolute == relative to range
     assert errs["pre_trans"] <= rtol, errs
     assert errs["sf_agg"] <= rtol, errs
+    return errs
+
+
+def check_raflow_outputs(out, gold, rtol=FLOW_RTOL):
+    """RaFlow.forward outputs (models/raflow.py:157-164): initial flow, aggregated flow, transform, rigid-inlier mask (exact: the
+    golden seeds keep every point's |residual / vel| at least 2e-4 away from the threshold)."""
+    errs = {"output": rel_err(out["output"], gold["output"]), "sf_agg": rel_err(out["sf_agg"], gold["sf_agg"]),
+            "pre_trans": rel_err(out["pre_trans"][:, :3, :], gold["pre_trans"][:, :3, :]),
+            "mask_mismatch": int((out["mask_s"].bool() != gold["mask_s"].bool()).sum())}
+    assert errs["mask_mismatch"] == 0, errs
+    assert errs["output"] <= rtol and errs["sf_agg"] <= rtol and errs["pre_trans"] <= rtol, errs
     return errs

@@ -43,3 +43,26 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
+
+
+def test_raflow_mirror_has_the_reference_key_layout():
+    """cmflow_b200.cmflow.RaFlow carries exactly the parameters / buffers of models/raflow.py (355 keys of checkpoints/raflow_cvpr)."""
+    import torch
+    from cmflow_b200 import weights
+    from cmflow_b200.cmflow import RaFlow
+    from cmflow_b200.synth import raflow_state_dict
+
+    class A:
+        num_points = 256
+        rigid_thres = 0.15
+
+    net = RaFlow(A())
+    sd = raflow_state_dict(5)
+    assert set(net.state_dict()) == set(sd) and len(sd) == 355
+    net.load_state_dict(sd, strict=True)
+    blob = weights.pack(net.state_dict(), raflow=True)
+    assert blob.size == weights.pack(weights.raflow_as_cmflow(sd)).size
+    ck = "/root/reference/checkpoints/raflow_cvpr/models/model.best.t7"
+    import os
+    if os.path.exists(ck):
+        net.load_state_dict(torch.load(ck, map_location="cpu", weights_only=True), strict=True)

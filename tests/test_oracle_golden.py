@@ -5,7 +5,7 @@ import torch
 
 from oracle import cmflow_oracle as O
 from oracle import pointops as P
-from tests.helpers import case_inputs, case_weights, check_outputs, knn_sets_equal, load_golden, rel_err
+from tests.helpers import case_inputs, case_weights, check_outputs, check_raflow_outputs, knn_sets_equal, load_golden, rel_err
 
 CASES = ["cmflow_synth_b2_n256.pt", "cmflow_synth_w1_b2_n256.pt", "cmflow_synth_b3_n200.pt", "cmflow_synth_b2_n40.pt",
          "cmflow_ckpt_b2_n256.pt"]
@@ -58,3 +58,21 @@ def test_oracle_fp64_truth_close_to_fp32(golden_dir):
     out = O.cmflow_forward(sd, pc1, pc2, ft1, ft2, dtype=torch.float64)
     out = {k: (v.float() if v.dtype == torch.float64 else v) for k, v in out.items()}
     check_outputs(out, gold)
+
+
+@pytest.mark.parametrize("name", ["raflow_synth_b3_n256.pt", "raflow_ckpt_b3_n256.pt"])
+def test_oracle_raflow_matches_reference(golden_dir, name):
+    """oracle.raflow_forward against the unmodified models/raflow.py (both SFR branches: > / < 25 % rigid inliers)."""
+    gold = load_golden(golden_dir, name)
+    sd = case_weights(gold["meta"], golden_dir)
+    if sd is None:
+        pytest.skip("reference checkpoint not available")
+    pc1, pc2, ft1, ft2, _ = case_inputs(gold["meta"])
+    out = O.raflow_forward(sd, pc1, pc2, ft1, ft2, gold["interval"], return_intermediates=True)
+    for key, val in (("f1_sub", out["f1"]), ("f2_sub", out["f2"]), ("cor_sub", out["cor"]), ("prop_sub", out["prop"])):
+        assert rel_err(val[0, :, ::4], gold[key], per_pair=False) <= 1e-4, key
+    frac = gold["mask_s"].float().mean(1)
+    assert (frac > 0.25).any() and (frac < 0.25).any()
+    print(name, check_raflow_outputs(out, gold))
+    out64 = O.raflow_forward(sd, pc1, pc2, ft1, ft2, gold["interval"], dtype=torch.float64)
+    check_raflow_outputs({k: (v.float() if v.dtype == torch.float64 else v) for k, v in out64.items()}, gold)
