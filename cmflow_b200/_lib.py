@@ -41,6 +41,9 @@ SIGNATURES = {
     "cmf_model_forward": [_vp, _i, _i] + [_vp] * 11,
     "cmf_model_forward_host": [_vp, _i, _i] + [_vp] * 11,
     "cmf_model_tap": [_vp, ctypes.c_char_p],
+    "cmf_eval_scene_flow_sums": [_i, _i, _vp, _vp, _vp, _vp, ctypes.c_double, ctypes.c_double, ctypes.c_double, _vp, _vp],
+    "cmf_eval_motion_seg_counts": [ctypes.c_longlong, _vp, _vp, _vp, _vp],
+    "cmf_eval_rpe_sums": [_i, _vp, _vp, _vp, _vp],
     "cmf_model_set_raflow": [_vp, _f, _f],
     "cmf_model_forward_raflow": [_vp, _i, _i] + [_vp] * 10,
     "cmf_raflow_refine": [_i, _i, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp],

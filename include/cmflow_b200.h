@@ -208,6 +208,22 @@ int cmf_test_tc_gemm_fmt(int fmt, int M, int K, long long cols, const float *W, 
 /* Instrumented runs of cmf_test_tc_gemm: device buffer long long[grid][8] receiving per-role barrier wait cycles (NULL = off). */
 void cmf_test_tc_set_dbg(long long *dbg);
 
+/* ------------------------------------------------------------------------------------------------
+ * Part 4 -- evaluation metrics of the reference's eval loop as device reductions
+ * (utils/eval_util.py:42-117, utils/odometry_util.py:34-142; callers main_util.py:175-193).
+ * Each call ADDS one batch's sums into a caller-zeroed device array of doubles; cmflow_b200/eval_util.py
+ * turns sums into the reference's dictionaries (and all-reduces them across ranks first when sharded).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* eval_scene_flow: pc (B,3,N), pred / labels (B,N,3), mask (B,N) float (1 = static).  sums11 += {points, sum error, #accs, #accr,
+ * sum re_error, sum re_error[mask==0], #(mask==0), sum re_error[mask==1], #(mask==1), #sas, #ras}; radar resolution as args.radar_res. */
+int cmf_eval_scene_flow_sums(int b, int n, const float *pc, const float *pred, const float *labels, const float *mask,
+                             double r_res, double theta_res, double phi_res, double *sums11, void *stream);
+/* eval_motion_seg: counts4 += {tp, tn, fp, fn} over `total` points (pre, gt float 0/1). */
+int cmf_eval_motion_seg_counts(long long total, const float *pre, const float *gt, double *counts4, void *stream);
+/* eval_trans_RPE: sums3 += {pairs, sum |translation of gt^-1 pred|, sum rotation angle of gt^-1 pred in degrees}; (B,4,4) each. */
+int cmf_eval_rpe_sums(int b, const float *gt_trans, const float *pred_trans, double *sums3, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
