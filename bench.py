@@ -158,6 +158,9 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="frame pairs per GPU per step")
     ap.add_argument("--points", type=int, default=256)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="cmflow", choices=["cmflow", "cmflow_t", "raflow"],
+                    help="cmflow = the headline workload (BASELINE.json configs[1-2]); cmflow_t = 3-frame clips with the GRU state carried "
+                         "(configs[3]: a step is the three forwards of a clip batch); raflow = models/raflow.py.  --points 4096 --batch 64 is configs[4]")
     ap.add_argument("--precision", default=os.environ.get("CMF_BENCH_PRECISION", "fp16x3"), choices=["fp32", "tf32x3", "fp16x3"],
                     help="fp32 = strict fp32 FMA kernels; tf32x3 / fp16x3 = tcgen05 tensor cores with a 22-bit hi/lo operand split "
                          "(3 MMAs per product, fp32 accumulate, fp32-class accuracy) in kind::tf32 or kind::f16")
@@ -172,7 +175,8 @@ def main():
     # host threads for the CPU arms: all cores up to 32 -- beyond that the small per-pair matmuls of this workload slow down
     # (measured on the 128-core GPU host: 0.37 pairs/s with 128 threads vs ~10 with 32); the count used is reported in `cores`
     cores = min(os.cpu_count() or 1, 32)
-    workload = f"CMFlow forward, synthetic radar pairs N={args.points}, batch={args.batch}/GPU, {args.gpus}xB200"
+    mname = {"cmflow": "CMFlow forward", "cmflow_t": "CMFlow-T temporal forward, 3-frame clips,", "raflow": "RaFlow forward"}[args.model]
+    workload = f"{mname} synthetic radar pairs N={args.points}, batch={args.batch}/GPU, {args.gpus}xB200"
 
     if args.impl == "reference":
         if rank != 0:
@@ -198,20 +202,26 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    from cmflow_b200.cmflow import CMFlow
-    from cmflow_b200.synth import make_pairs, synthetic_state_dict
+    from cmflow_b200.cmflow import CMFlow, CMFlow_T, RaFlow
+    from cmflow_b200.synth import make_pairs, raflow_state_dict, synthetic_state_dict
 
     class A:
         num_points = args.points
         stat_thres = 0.5
+        rigid_thres = 0.15
 
-    net = CMFlow(A())
-    net.load_state_dict(synthetic_state_dict(0))
+    if args.model == "cmflow_t":
+        net = CMFlow_T(A()); net.load_state_dict(synthetic_state_dict(0, temporal=True))
+    elif args.model == "raflow":
+        net = RaFlow(A()); net.load_state_dict(raflow_state_dict(0))
+    else:
+        net = CMFlow(A()); net.load_state_dict(synthetic_state_dict(0))
     net = net.to(dev)
+    FRAMES = 3 if args.model == "cmflow_t" else 1             # forwards per step
     net.set_precision(args.precision)
     B, N = args.batch, args.points
     NSETS = 4                                                  # rotate distinct input batches
-    host_sets = [tuple(t.pin_memory() for t in make_pairs(B, N, seed=1234 + 97 * rank + s)[:4]) for s in range(NSETS)]
+    host_sets = [tuple(t.pin_memory() for t in make_pairs(B, N, seed=1234 + 97 * rank + s, dense=(N >= 2048))[:4]) for s in range(NSETS)]
     dev_sets = [tuple(t.to(dev) for t in hs) for hs in host_sets]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -220,15 +230,34 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    interval = torch.full((args.batch,), 0.1, device=dev)
+
     def fwd_dev(i):
         with torch.no_grad():
+            if args.model == "cmflow_t":                      # one clip step: gfeat None -> carry -> carry (clip_util.py:218-233)
+                g = None
+                for f in range(FRAMES):
+                    out = net(*dev_sets[(i + f) % NSETS], None, "test", g)
+                    g = out[4]
+                return out
+            if args.model == "raflow":
+                return net(*dev_sets[i % NSETS], interval)
             return net(*dev_sets[i % NSETS], None, "test")
 
     out_host = None
 
     def fwd_host(i):
         nonlocal out_host
-        out_host = net.forward_host(*host_sets[i % NSETS], out=out_host)
+        if args.model == "raflow":                            # no host-buffer entry point for RaFlow: explicit pinned copies around the device call
+            ins = [t.to(dev, non_blocking=True) for t in host_sets[i % NSETS]]
+            with torch.no_grad():
+                res = net(*ins, interval)
+            out_host = [r.to("cpu", non_blocking=False) for r in res]
+            return out_host
+        g = None
+        for f in range(FRAMES):
+            out_host = net.forward_host(*host_sets[(i + f) % NSETS], gfeat=g, out=out_host)
+            g = out_host["gfeat"] if args.model == "cmflow_t" else None
         return out_host
 
     def timed(fn, steps):
@@ -262,7 +291,7 @@ def main():
         fwd_host(i)
     ms_host = timed(fwd_host, K)
     clocks = sampler.stop() if sampler else None
-    total_pairs = B * world
+    total_pairs = B * world * FRAMES
 
     # profiled pass: per-category device time (CUDA events around every launch, same stream)
     prof, cpu = None, None
@@ -326,8 +355,8 @@ def main():
                 ref_cuda = time_ref_cuda(max(1, min(32, (32 * 256 * 256) // (N * N))), N, 5, 2, dev)
             except Exception as e:                      # informational only
                 ref_cuda = {"unavailable": repr(e)[:200]}
-        h2d = 4 * B * 3 * N * 4
-        d2h = B * 3 * N * 4 + B * N * 4 + B * 16 * 4 + B * N
+        h2d = FRAMES * 4 * B * 3 * N * 4
+        d2h = FRAMES * (B * 3 * N * 4 + B * N * 4 + B * 16 * 4 + B * N)
         line = {
             "metric": "frame-pairs/sec CMFlow forward", "value": total_pairs * K / (ms_dev / 1e3), "unit": "frame-pairs/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
@@ -336,7 +365,7 @@ def main():
                        "l2": "256 MB flush between timed steps; 4 rotating input batches", "precision_mode": args.precision},
             "e2e": {"value": total_pairs * K / (ms_host / 1e3), "unit": "frame-pairs/s", "ms_per_step": ms_host / K,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches * K, "launches_per_step": launches,
+            "gpu_launches": launches * K * FRAMES, "launches_per_step": launches * FRAMES,
             "clocks": clocks, "roofline": roofline, "kernels": prof, "cpu_baseline": cpu, "ref_cuda_baseline": ref_cuda,
             "workspace_bytes": net.workspace_bytes(),
         }

@@ -96,77 +96,106 @@ extern "C" int cmf_ball_query(int b, int n, int m, float radius, int nsample,
 }
 
 // ------------------------------------------------------------------------------------------------
-// kNN, warp per query.  MODE 0: lib/src/interpolate_gpu.cu:9-57 (direct-form distance, ordered);
-//                       MODE 1: radarflow_util.py:88-99 knn_point (expanded-form distance).
-// Each lane keeps the KMAX best of the candidates it saw (ascending by (d, index): candidates arrive
-// in increasing index order and insertion is strict '<', exactly the reference's rule); k rounds of a
-// shuffle arg-min over the lane heads emit the global order.
+// kNN, k <= 32.  MODE 0: lib/src/interpolate_gpu.cu:9-57 (direct-form distance, ordered);
+//                MODE 1: radarflow_util.py:88-99 knn_point (expanded-form distance).
+// A warp answers KNN_QPW queries.  The k best of a query live ACROSS the warp, sorted: lane r holds the r-th best (d, index), and
+// tau = the k-th best distance is warp-uniform.  Candidates are taken 32 at a time (one per lane, staged in shared memory, |x|^2
+// precomputed once per CTA for the expanded form); a ballot of d < tau finds the few that matter -- about k ln(N/k) of N per query --
+// and each of those is inserted by one ballot (its rank) and one shuffle-up.  Order rule as the reference: ascending by (d, index),
+// because candidates arrive in increasing index order, hits of a batch are taken from the lowest lane up, and a new element goes
+// behind every element with d' <= d (the reference's strict '<').  No final merge: lane r writes result r.
+// (The earlier version kept k best PER LANE: with 32 private thresholds nearly every batch triggered an 8-step insertion in some
+// lane -- 74 instructions per batch at N=4096; this one spends ~13.)
 // ------------------------------------------------------------------------------------------------
 constexpr int KNN_THREADS = 256;
 constexpr int KNN_CHUNK = 2048;
+constexpr int KNN_QPW = 2;
 
-template <int KMAX, int MODE>
+template <int MODE>
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_warp_kernel(int nq, int mc, int k, const float *__restrict__ query, const float *__restrict__ cand,
                 float *__restrict__ dist_out, int *__restrict__ idx_out) {
     __shared__ __align__(16) float s[KNN_CHUNK * 3];
+    __shared__ float sn[MODE == 1 ? KNN_CHUNK : 1];
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = blockIdx.x * (KNN_THREADS / 32) + warp;
-    const bool valid = q < nq;
+    const int q0 = (blockIdx.x * (KNN_THREADS / 32) + warp) * KNN_QPW;
     cand += (size_t)b * mc * 3;
-    const float *qp = query + ((size_t)b * nq + (valid ? q : 0)) * 3;
-    const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
-    const float nqn = cmf_sqnorm3(qx, qy, qz);
-
-    float bd[KMAX];
-    int bi[KMAX];
+    float qx[KNN_QPW], qy[KNN_QPW], qz[KNN_QPW], nqn[KNN_QPW], bd[KNN_QPW], tau[KNN_QPW];
+    int bi[KNN_QPW];
 #pragma unroll
-    for (int j = 0; j < KMAX; ++j) { bd[j] = INFINITY; bi[j] = INT_MAX; }
+    for (int t = 0; t < KNN_QPW; ++t) {
+        const float *qp = query + ((size_t)b * nq + (q0 + t < nq ? q0 + t : 0)) * 3;
+        qx[t] = __ldg(qp); qy[t] = __ldg(qp + 1); qz[t] = __ldg(qp + 2);
+        nqn[t] = cmf_sqnorm3(qx[t], qy[t], qz[t]);
+        bd[t] = INFINITY; bi[t] = INT_MAX; tau[t] = INFINITY;
+    }
+    const bool any_valid = q0 < nq;
 
     for (int base = 0; base < mc; base += KNN_CHUNK) {
         __syncthreads();
         const int cn = min(KNN_CHUNK, mc - base);
         cmf_stage_floats(s, cand + (size_t)base * 3, cn * 3);
         __syncthreads();
-        if (!valid) continue;
-        for (int kk = lane; kk < cn; kk += 32) {
-            const float x = s[3 * kk], y = s[3 * kk + 1], z = s[3 * kk + 2];
-            float d;
-            if (MODE == 0) d = cmf_sqdist_ref(qx, qy, qz, x, y, z);
-            else d = cmf_sqdist_expanded(qx, qy, qz, nqn, x, y, z, cmf_sqnorm3(x, y, z));
-            if (d < bd[KMAX - 1]) {                         // also rejects inf / NaN like `d < 1e40`
-                float cd = d; int ci = base + kk; bool ins = false;
+        if (MODE == 1) {
+            for (int i = threadIdx.x; i < cn; i += KNN_THREADS) sn[i] = cmf_sqnorm3(s[3 * i], s[3 * i + 1], s[3 * i + 2]);
+            __syncthreads();
+        }
+        if (!any_valid) continue;
+        for (int j = 0; j < cn; j += 32) {
+            const int kk = j + lane;
+            const bool in = kk < cn;
+            const int ks = in ? kk : 0;
+            const float x = s[3 * ks], y = s[3 * ks + 1], z = s[3 * ks + 2];
+            const float xn = MODE == 1 ? sn[ks] : 0.f;
 #pragma unroll
-                for (int j = 0; j < KMAX; ++j) {
-                    bool sw = ins || (cd < bd[j]);
-                    float td = bd[j]; int ti = bi[j];
-                    if (sw) { bd[j] = cd; bi[j] = ci; cd = td; ci = ti; }
-                    ins = sw;
+            for (int t = 0; t < KNN_QPW; ++t) {
+                float d;
+                if (MODE == 0) d = cmf_sqdist_ref(qx[t], qy[t], qz[t], x, y, z);
+                else d = cmf_sqdist_expanded(qx[t], qy[t], qz[t], nqn[t], x, y, z, xn);
+                if (base == 0 && j == 0) {
+                    // first batch, empty list: every lane would hit and be inserted one by one -- sort the 32 candidates instead (bitonic
+                    // network over the lanes, ascending by (d, index)); inf / NaN / out-of-range lanes sort to the end as (inf, INT_MAX)
+                    float sd = (in && d < INFINITY) ? d : INFINITY;
+                    int si = (in && d < INFINITY) ? kk : INT_MAX;
+#pragma unroll
+                    for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+                        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                            const float od = __shfl_xor_sync(0xffffffffu, sd, stride);
+                            const int oi = __shfl_xor_sync(0xffffffffu, si, stride);
+                            const bool other_first = od < sd || (od == sd && oi < si);
+                            const bool want_min = ((lane & stride) == 0) == ((lane & size) == 0);
+                            if (want_min == other_first && (od != sd || oi != si)) { sd = od; si = oi; }
+                        }
+                    bd[t] = lane < k ? sd : INFINITY; bi[t] = lane < k ? si : INT_MAX;
+                    tau[t] = __shfl_sync(0xffffffffu, bd[t], k - 1);
+                    continue;
+                }
+                unsigned mask = __ballot_sync(0xffffffffu, in && d < tau[t]);      // also rejects inf / NaN like the reference's `d < best`
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float cd = __shfl_sync(0xffffffffu, d, src);
+                    if (!(cd < tau[t])) continue;                                  // tau fell while this batch was being inserted
+                    const int ci = base + j + src;
+                    const int pos = __popc(__ballot_sync(0xffffffffu, bd[t] <= cd));   // elements that stay in front (earlier index wins ties)
+                    const float pd = __shfl_up_sync(0xffffffffu, bd[t], 1);
+                    const int pi = __shfl_up_sync(0xffffffffu, bi[t], 1);
+                    if (lane > pos) { bd[t] = pd; bi[t] = pi; }
+                    else if (lane == pos) { bd[t] = cd; bi[t] = ci; }
+                    if (lane >= k) { bd[t] = INFINITY; bi[t] = INT_MAX; }
+                    tau[t] = __shfl_sync(0xffffffffu, bd[t], k - 1);
                 }
             }
         }
     }
-    if (!valid) return;
-    float *dout = dist_out ? dist_out + ((size_t)b * nq + q) * k : nullptr;
-    int *iout = idx_out + ((size_t)b * nq + q) * k;
-    for (int r = 0; r < k; ++r) {
-        float d = bd[0]; int i = bi[0];
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            float od = __shfl_xor_sync(0xffffffffu, d, off);
-            int oi = __shfl_xor_sync(0xffffffffu, i, off);
-            if (od < d || (od == d && oi < i)) { d = od; i = oi; }
-        }
-        if (i != INT_MAX && bi[0] == i) {                   // owner pops its head
-#pragma unroll
-            for (int j = 0; j < KMAX - 1; ++j) { bd[j] = bd[j + 1]; bi[j] = bi[j + 1]; }
-            bd[KMAX - 1] = INFINITY; bi[KMAX - 1] = INT_MAX;
-        }
-        if (lane == 0) {
-            iout[r] = (i == INT_MAX) ? 0 : i;               // unfilled slot: (1e40 -> inf, 0) in the reference
-            if (dout) dout[r] = d;
-        }
+    for (int t = 0; t < KNN_QPW; ++t) {
+        const int q = q0 + t;
+        if (q >= nq || lane >= k) continue;
+        idx_out[((size_t)b * nq + q) * k + lane] = (bi[t] == INT_MAX) ? 0 : bi[t];     // unfilled slot: (1e40 -> inf, 0) in the reference
+        if (dist_out) dist_out[((size_t)b * nq + q) * k + lane] = bd[t];
     }
 }
 
@@ -199,11 +228,8 @@ knn_thread_kernel(int nq, int mc, int k, const float *__restrict__ query, const 
 template <int MODE>
 static int launch_knn(int b, int nq, int mc, int k, const float *query, const float *cand,
                       float *dist, int *idx, cudaStream_t st) {
-    dim3 grid(cmf_divup(nq, KNN_THREADS / 32), b);
-    if (k <= 4) knn_warp_kernel<4, MODE><<<grid, KNN_THREADS, 0, st>>>(nq, mc, k, query, cand, dist, idx);
-    else if (k <= 8) knn_warp_kernel<8, MODE><<<grid, KNN_THREADS, 0, st>>>(nq, mc, k, query, cand, dist, idx);
-    else if (k <= 16) knn_warp_kernel<16, MODE><<<grid, KNN_THREADS, 0, st>>>(nq, mc, k, query, cand, dist, idx);
-    else knn_warp_kernel<32, MODE><<<grid, KNN_THREADS, 0, st>>>(nq, mc, k, query, cand, dist, idx);
+    dim3 grid(cmf_divup(nq, (KNN_THREADS / 32) * KNN_QPW), b);
+    knn_warp_kernel<MODE><<<grid, KNN_THREADS, 0, st>>>(nq, mc, k, query, cand, dist, idx);
     return 0;
 }
 
