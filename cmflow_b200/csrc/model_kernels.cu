@@ -199,6 +199,8 @@ ball_query_ms_kernel(int n, const float *__restrict__ xyz, int *__restrict__ idx
     constexpr int OFF[4] = {0, 4, 12, 28};
     float qx[MS_QPW], qy[MS_QPW], qz[MS_QPW];
     int cnt[MS_QPW][4], first[MS_QPW][4];
+    float rmax[MS_QPW];                     // r^2 of the largest radius whose row is still open (0 = all four rows full): the radii nest,
+                                            // so a candidate outside it hits nothing and one ballot dismisses the whole batch of 32
     bool all_done = true;
 #pragma unroll
     for (int t = 0; t < MS_QPW; ++t) {
@@ -207,6 +209,7 @@ ball_query_ms_kernel(int n, const float *__restrict__ xyz, int *__restrict__ idx
         qx[t] = __ldg(px + (valid ? q : 0)); qy[t] = __ldg(py + (valid ? q : 0)); qz[t] = __ldg(pz + (valid ? q : 0));
 #pragma unroll
         for (int s = 0; s < 4; ++s) { cnt[t][s] = valid ? 0 : KS[s]; first[t][s] = -1; }
+        rmax[t] = valid ? c_ms_r2[3] : 0.f;
         all_done = all_done && !valid;
     }
     for (int base = 0; base < n; base += MS_CHUNK) {
@@ -221,10 +224,11 @@ ball_query_ms_kernel(int n, const float *__restrict__ xyz, int *__restrict__ idx
             const int k = j + lane;
             const bool in = k < cn;
             const float cx = in ? sx[k] : 0.f, cy = in ? sy[k] : 0.f, cz = in ? sz[k] : 0.f;
-            bool any_open = false;
 #pragma unroll
             for (int t = 0; t < MS_QPW; ++t) {
                 const float d2 = cmf_sqdist_ref(qx[t], qy[t], qz[t], cx, cy, cz);
+                if (!__any_sync(0xffffffffu, in && d2 < rmax[t])) continue;      // nothing in this batch for any open row
+                float open_r2 = 0.f;
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
                     if (cnt[t][s] >= KS[s]) continue;               // warp-uniform
@@ -236,10 +240,14 @@ ball_query_ms_kernel(int n, const float *__restrict__ xyz, int *__restrict__ idx
                         if (hit && pos < KS[s]) idx60[((size_t)b * n + q0 + t) * 60 + OFF[s] + pos] = base + k;
                         cnt[t][s] += __popc(mask);
                     }
-                    any_open = any_open || (cnt[t][s] < KS[s]);
+                    if (cnt[t][s] < KS[s]) open_r2 = c_ms_r2[s];    // ascending s: ends as the largest open radius
                 }
+                rmax[t] = open_r2;
             }
-            if (!any_open) { all_done = true; break; }
+            bool open = false;
+#pragma unroll
+            for (int t = 0; t < MS_QPW; ++t) open = open || rmax[t] > 0.f;
+            if (!open) { all_done = true; break; }
         }
     }
 #pragma unroll
