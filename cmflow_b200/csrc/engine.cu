@@ -282,10 +282,14 @@ static size_t chunk_bytes(int bc, int n) {
 }
 
 static int ensure_workspace(cmf_model *m, int b, int n) {
-    // chunk size: as many pairs as fit the workspace arena (default 24 GiB of the 180 GB; CMF_WS_GB / CMF_CHUNK_PAIRS override).
+    // chunk size: as many pairs as fit the workspace arena (default 64 GiB of the 180 GB, at most half of what is free; CMF_WS_GB / CMF_CHUNK_PAIRS override).
     // Few large chunks amortise the per-launch prologue of the persistent tensor-core kernels (cluster launch, TMEM allocation,
     // pipeline fill: ~40 us each, ~14 such launches per chunk).
-    size_t budget = (size_t)24 << 30;
+    size_t budget = (size_t)64 << 30;                 // of the 180 GB: one chunk for B=256 at N=256 (15 GB) and for B=64 at N=4096 (49 GB)
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b / 2 < budget) budget = free_b / 2 > ((size_t)1 << 30) ? free_b / 2 : ((size_t)1 << 30);
+    }
     const char *wsenv = getenv("CMF_WS_GB");
     if (wsenv && atof(wsenv) > 0) budget = (size_t)(atof(wsenv) * (double)((size_t)1 << 30));
     int bc = b;

@@ -444,18 +444,30 @@ int cmf_launch_maxk(long long points, int K, int C, const float *Y, int ldy, flo
 }
 
 __global__ void __launch_bounds__(256)
-globalmax_kernel(int n, int C, const float *__restrict__ F, int ldf, float *__restrict__ G) {
+globalmax_kernel(int n, int C, const float *__restrict__ F, int ldf, float *__restrict__ G, int rows_per_slice) {
     __shared__ float red[4][64];
     const int b = blockIdx.x, c = blockIdx.y * 64 + (threadIdx.x & 63), rg = threadIdx.x >> 6;
+    const int r0 = blockIdx.z * rows_per_slice, r1 = min(n, r0 + rows_per_slice);
     float m = -FLT_MAX;
     if (c < C)
-        for (int i = rg; i < n; i += 4) m = fmaxf(m, __ldg(F + ((size_t)b * n + i) * ldf + c));
+        for (int i = r0 + rg; i < r1; i += 4) m = fmaxf(m, __ldg(F + ((size_t)b * n + i) * ldf + c));
     red[rg][threadIdx.x & 63] = m;
     __syncthreads();
-    if (rg == 0 && c < C) G[(size_t)b * C + c] = fmaxf(fmaxf(red[0][threadIdx.x], red[1][threadIdx.x]), fmaxf(red[2][threadIdx.x], red[3][threadIdx.x]));
+    if (rg == 0 && c < C) {
+        m = fmaxf(fmaxf(red[0][threadIdx.x], red[1][threadIdx.x]), fmaxf(red[2][threadIdx.x], red[3][threadIdx.x]));
+        float *g = G + (size_t)b * C + c;
+        if (gridDim.z == 1) *g = m;
+        // row slices combine by a sign-aware atomic max on the bit pattern; G was preset to 0xFFFFFFFF, which is below every float in both views
+        else if (m >= 0.f) atomicMax(reinterpret_cast<int *>(g), __float_as_int(m));
+        else atomicMin(reinterpret_cast<unsigned int *>(g), __float_as_uint(m));
+    }
 }
 int cmf_launch_globalmax(int b, int n, int C, const float *F, int ldf, float *G, cudaStream_t st) {
-    globalmax_kernel<<<dim3(b, cmf_divup(C, 64)), 256, 0, st>>>(n, C, F, ldf, G);
+    // few pairs with many points (the N=4096 configuration): split the rows over gridDim.z so that the grid still fills the chip
+    int slices = 1;
+    if ((long long)b * cmf_divup(C, 64) < 592 && n > 512) slices = cmf_divup(n, 256);
+    if (slices > 1) CMF_CUDA(cudaMemsetAsync(G, 0xFF, (size_t)b * C * sizeof(float), st));
+    globalmax_kernel<<<dim3(b, cmf_divup(C, 64), slices), 256, 0, st>>>(n, C, F, ldf, G, slices > 1 ? 256 : n);
     CMF_LAUNCH_CHECK();
     return CMF_OK;
 }

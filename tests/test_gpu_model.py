@@ -167,6 +167,17 @@ def test_dense_cloud_config_runs_and_matches_oracle_prefix():
     assert torch.equal(net.tap("bq1", (1, 4096, 60), torch.int32).cpu(), want)
     assert torch.equal(net.tap("knn12", (1, 4096, 8), torch.int32).cpu(), P.knn_point(8, x2t, x1t)[0])
     assert torch.isfinite(out["sf_agg"]).all()
+    # the whole forward against the CPU oracle at this size (unfused: 0.5 GB of grouped tensors for the one pair), strict and tensor-core builds
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    ref = O.cmflow_forward(sd, *inp[:4])
+    print("N=4096 fp32", check_outputs(out, ref))
+    net.set_precision("fp16x3")
+    print("N=4096 fp16x3", check_outputs(run(net, inp), ref))
+    # two pairs in one chunk == each pair alone (row-sliced global max, per-pair scales)
+    inp2 = make_pairs(2, 4096, seed=3, dense=True)
+    both = run(net, inp2)
+    one = run(net, tuple(t[:1].contiguous() for t in inp2))
+    assert torch.equal(both["sf_agg"][:1], one["sf_agg"]) and torch.equal(both["pre_trans"][:1], one["pre_trans"])
 
 
 def test_fused_setconv1_equals_layerwise(golden_dir, monkeypatch):
