@@ -60,6 +60,18 @@ __device__ __forceinline__ void tc_mma2_f16(uint32_t d_tmem, uint64_t a_desc, ui
                  "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// The hi x lo and hi x hi products use the same A tile back to back: the first keeps it in the tensor core's A collector, the second reads it
+// from there instead of from shared memory (4 KB less on the SM's shared-memory port per K=16 step, see profiles/r01b_tc_kernels_ncu_full.md).
+__device__ __forceinline__ void tc_mma2_f16_keep(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ void tc_mma2_f16_reuse(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+}
 
 // F16 = 0: 3xTF32, one pipeline stage = 16 floats of K;  F16 = 1: 3xFP16, one stage = 32 halfs of K (same bytes, see tc_dev.cuh)
 template <int PROD, int F16>
@@ -176,8 +188,8 @@ tc_gemm2_kernel(const TcArgs a) {
                             const uint64_t adv = (uint64_t)(k8 * 32 >> 4);
                             if (F16) {
                                 tc_mma2_f16(d_tmem, a_lo + adv, b_hi + adv, IDESC2_F16, (ks | k8) ? 1u : 0u);
-                                tc_mma2_f16(d_tmem, a_hi + adv, b_lo + adv, IDESC2_F16, 1u);
-                                tc_mma2_f16(d_tmem, a_hi + adv, b_hi + adv, IDESC2_F16, 1u);
+                                tc_mma2_f16_keep(d_tmem, a_hi + adv, b_lo + adv, IDESC2_F16);
+                                tc_mma2_f16_reuse(d_tmem, a_hi + adv, b_hi + adv, IDESC2_F16);
                             } else {
                                 tc_mma2_tf32(d_tmem, a_lo + adv, b_hi + adv, IDESC2_TF32, (ks | k8) ? 1u : 0u);
                                 tc_mma2_tf32(d_tmem, a_hi + adv, b_lo + adv, IDESC2_TF32, 1u);
