@@ -97,7 +97,7 @@ struct Work {
     unsigned int *AMAX;      // fp16x3 mode: per-pair max |x| of the tensors feeding a tensor-core GEMM (uint bit patterns of floats), AM_COUNT x bc
     float *SCL;              // fp16x3 mode: per-pair scales of the tiled intermediates (H2, Y2 x 4 scales), SC_COUNT x bc
 };
-enum { AM_F1 = 0, AM_F2, AM_E, AM_PROP, AM_U1, AM_U2, AM_DIR, AM_HD1, AM_P0, AM_COUNT = AM_P0 + 4 };
+enum { AM_F1 = 0, AM_F2, AM_E, AM_PROP, AM_U1, AM_U2, AM_DIR, AM_HD1, AM_COR, AM_FT, AM_P0, AM_COUNT = AM_P0 + 4 };
 enum { SC_H2 = 0, SC_Y2, SC_COUNT = SC_Y2 + 4 };
 
 void carve(Arena &a, Work &w, int bc, int n) {
@@ -320,7 +320,7 @@ static int ensure_workspace(cmf_model *m, int b, int n) {
 
 // set-conv over a small-channel cloud (mse_layer, C=3): PointLocalFeature x 4 scales (radarflow_util.py:144-162)
 static int run_mse_layer(cmf_model *m, int bc, int n, const float *pc, const float *ft, const int *bq,
-                         float *dest, int ldd, float *G, cudaStream_t st) {
+                         float *dest, int ldd, float *G, cudaStream_t st, unsigned int *amax_dest = nullptr) {
     Work &w = m->w;
     const long long bn = (long long)bc * n;
     GemmBatch gb;
@@ -335,7 +335,7 @@ static int run_mse_layer(cmf_model *m, int bc, int n, const float *pc, const flo
             for (int l = 0; l < 3; ++l) { mw[s].Vt[l] = T.m1_v[s][l].wt; mw[s].ainv[l] = T.m1_v[s][l].ainv; mw[s].c[l] = m->seg[sb + 7 + l * 2]; }
         }
         RUN(C_GEMM_SC1, 2.0 * 3264.0 * 60.0 * (double)bn, cmf_launch_setconv1_tc(bc, n, pc, ft, bq, cw, w.M64, st));
-        RUN(C_GEMM_POINTWISE, 2.0 * 3 * 4 * 64 * 64 * (double)bn, cmf_launch_mlp2_tc(bn, w.M64, 256, dest, ldd, mw, st));
+        RUN(C_GEMM_POINTWISE, 2.0 * 3 * 4 * 64 * 64 * (double)bn, cmf_launch_mlp2_tc(bn, w.M64, 256, dest, ldd, mw, amax_dest, n, st));
         RUN(C_REDUCE, 0, cmf_launch_globalmax(bc, n, 256, dest, ldd, G, st));
         return CMF_OK;
     }
@@ -404,9 +404,11 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
     RUN(C_SEARCH, 0, cmf_launch_knn_point8(bc, n, w.X1T, w.X1T, w.KNN11, st));
 
     // multi-scale encoders (cmflow.py:72-77); cloud 1 writes straight into the embedding rows E[:, 0:256]
-    { int rc = run_mse_layer(m, bc, n, pc1, ft1, w.BQ1, w.E, E_LD, w.G1, st); if (rc) return rc; }
-    { int rc = run_mse_layer(m, bc, n, pc2, ft2, w.BQ2, w.F2, 256, w.G2, st); if (rc) return rc; }
-    RUN(C_GATHER, 0, cmf_launch_scatter_ft(bc, n, ft1, w.E, E_LD, 768, E_LD - 771, st));
+    // fp16x3 + chain kernels: the per-pair maxima behind the consumer GEMMs' fp16 scales are taken by the producing kernels' epilogues
+    const bool fused_amax = F && m->chain;
+    { int rc = run_mse_layer(m, bc, n, pc1, ft1, w.BQ1, w.E, E_LD, w.G1, st, fused_amax ? AM(AM_F1) : nullptr); if (rc) return rc; }
+    { int rc = run_mse_layer(m, bc, n, pc2, ft2, w.BQ2, w.F2, 256, w.G2, st, fused_amax ? AM(AM_F2) : nullptr); if (rc) return rc; }
+    RUN(C_GATHER, 0, cmf_launch_scatter_ft(bc, n, ft1, w.E, E_LD, 768, E_LD - 771, st, fused_amax ? AM(AM_FT) : nullptr));
 
     // flow embedding (FeatureCorrelator, radarflow_util.py:185-237)
     bool fused_wsum = false;
@@ -414,8 +416,10 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
     { const GemmArgs ga_ = mk(S(FC_WNG), 256, w.G2, 256, w.PB2, 512, nullptr, 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     if (m->tc) {
         if (F) {    // per-pair maxima of the GEMM inputs (fp16 scales): encoder features, kNN direction components
-            RUN(C_REDUCE, 0, cmf_launch_pair_absmax(bc, n, w.E, E_LD, 256, AM(AM_F1), st));
-            RUN(C_REDUCE, 0, cmf_launch_pair_absmax(bc, n, w.F2, 256, 256, AM(AM_F2), st));
+            if (!fused_amax) {
+                RUN(C_REDUCE, 0, cmf_launch_pair_absmax(bc, n, w.E, E_LD, 256, AM(AM_F1), st));
+                RUN(C_REDUCE, 0, cmf_launch_pair_absmax(bc, n, w.F2, 256, 256, AM(AM_F2), st));
+            }
             RUN(C_REDUCE, 0, cmf_launch_pair_dirmax(bc, n, pc1, pc2, w.KNN12, 8, AM(AM_DIR), st));
         }
         {
@@ -460,14 +464,16 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
     WeightNetP wn1{S(WN1_BASE), S(WN1_BASE + 1), S(WN1_BASE + 2), S(WN1_BASE + 3), S(WN1_BASE + 4), S(WN1_BASE + 5)};
     WeightNetP wn2{S(WN2_BASE), S(WN2_BASE + 1), S(WN2_BASE + 2), S(WN2_BASE + 3), S(WN2_BASE + 4), S(WN2_BASE + 5)};
     if (!fused_wsum) RUN(C_REDUCE, 0, cmf_launch_fc_reduce(bc, n, pc1, pc2, w.KNN12, wn1, w.H1, 0, w.COST1, 512, st));
-    RUN(C_REDUCE, 0, cmf_launch_fc_reduce(bc, n, pc1, pc1, w.KNN11, wn2, w.COST1, 1, w.E + 256, E_LD, st));
+    RUN(C_REDUCE, 0, cmf_launch_fc_reduce(bc, n, pc1, pc1, w.KNN11, wn2, w.COST1, 1, w.E + 256, E_LD, st, fused_amax ? AM(AM_COR) : nullptr));
 
     // set-conv #2 (mse_layer2, cmflow.py:87-89)
     { const GemmArgs ga_ = mk(S(M2_WG), 256, w.G1, 256, w.PBM, 2048, S(M2_T1), 2048, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_SC2_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     if (m->tc) {
-        if (F) RUN(C_REDUCE, 0, cmf_launch_pair_absmax(bc, n, w.E, E_LD, E_LD, AM(AM_E), st));
+        if (F && !fused_amax) RUN(C_REDUCE, 0, cmf_launch_pair_absmax(bc, n, w.E, E_LD, E_LD, AM(AM_E), st));
         TcArgs ta_ = tc_plain(T.m2_wp, F, 2048, E_LD, w.E, E_LD, w.P, 2048, nullptr, bn, CMF_ACT_NONE, w.PBM, 2048, n);
-        tc_bound(ta_, 0.f, AM(AM_E), 1.f);
+        // E = [f1 | cor | ft]: max|E| <= max|f1| + max|cor| + max|ft| (a bound up to 3x loose costs < 2 of fp16's 5 exponent bits of headroom)
+        if (fused_amax) tc_bound(ta_, 0.f, AM(AM_F1), 1.f, AM(AM_COR), 1.f, AM(AM_FT), 1.f);
+        else tc_bound(ta_, 0.f, AM(AM_E), 1.f);
         if (F) { ta_.amax_out = AM(AM_P0); ta_.amax_group = 512; ta_.amax_ld = m->cap_bc; }     // one maximum per scale's 512 channels
         RUN(C_GEMM_SC2_HOIST, tflops(ta_, 771), cmf_launch_tc_auto(ta_, st));
     } else {
@@ -506,7 +512,7 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
         TcChainMlp2W mw[4];
         for (int s = 0; s < 4; ++s)
             for (int l = 0; l < 3; ++l) { mw[s].Vt[l] = T.m2_v[s][l].wt; mw[s].ainv[l] = T.m2_v[s][l].ainv; mw[s].c[l] = S(M2_BASE + s * 10 + 5 + l * 2); }
-        RUN(C_GEMM_POINTWISE, 2.0 * 3 * 4 * 64 * 64 * (double)bn, cmf_launch_mlp2_tc(bn, w.M64, 256, w.PROP, 256, mw, st));
+        RUN(C_GEMM_POINTWISE, 2.0 * 3 * 4 * 64 * 64 * (double)bn, cmf_launch_mlp2_tc(bn, w.M64, 256, w.PROP, 256, mw, F ? AM(AM_PROP) : nullptr, n, st));
     } else {
         GemmBatch gb; gb.count = 4;
         const float *src[3] = {w.M64, w.Q1, w.Q2};
@@ -532,7 +538,7 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
     // heads (FlowHead / MotionHead, radarflow_util.py:240-285), first layer stacked [fp ; mp]
     { const GemmArgs ga_ = mk(S(HD_W1G), 256, gvec, 256, w.PBH, 512, S(HD_T1), 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_POINTWISE, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     if (m->tc) {
-        if (F) RUN(C_REDUCE, 0, cmf_launch_pair_absmax(bc, n, w.PROP, 256, 256, AM(AM_PROP), st));
+        if (F && !fused_amax) RUN(C_REDUCE, 0, cmf_launch_pair_absmax(bc, n, w.PROP, 256, 256, AM(AM_PROP), st));
         TcArgs ta_ = tc_plain(T.hd_w1, F, 512, 256, w.PROP, 256, w.HD1, 512, nullptr, bn, CMF_ACT_RELU, w.PBH, 512, n);
         tc_bound(ta_, 0.f, AM(AM_PROP), 1.f); if (F) { ta_.amax_out = AM(AM_HD1); }
         RUN(C_GEMM_POINTWISE, tflops(ta_, 256), cmf_launch_tc_auto(ta_, st));

@@ -472,16 +472,25 @@ int cmf_launch_globalmax(int b, int n, int C, const float *F, int ldf, float *G,
     return CMF_OK;
 }
 
-__global__ void scatter_ft_kernel(int n, const float *__restrict__ ft, float *__restrict__ E, int lde, int off, int pad) {
+__global__ void scatter_ft_kernel(int n, const float *__restrict__ ft, float *__restrict__ E, int lde, int off, int pad, unsigned int *__restrict__ amax_out) {
     const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float *p = ft + (size_t)b * 3 * n;
-    float *o = E + ((size_t)b * n + i) * lde + off;
-    o[0] = __ldg(p + i); o[1] = __ldg(p + n + i); o[2] = __ldg(p + 2 * n + i);
-    for (int d = 0; d < pad; ++d) o[3 + d] = 0.f;
+    float m = 0.f;
+    if (i < n) {
+        const float *p = ft + (size_t)b * 3 * n;
+        float *o = E + ((size_t)b * n + i) * lde + off;
+        const float f0 = __ldg(p + i), f1 = __ldg(p + n + i), f2 = __ldg(p + 2 * n + i);
+        o[0] = f0; o[1] = f1; o[2] = f2;
+        for (int d = 0; d < pad; ++d) o[3 + d] = 0.f;
+        m = fmaxf(fabsf(f0), fmaxf(fabsf(f1), fabsf(f2)));
+    }
+    if (amax_out) {                                     // blockIdx.y = pair: the whole warp belongs to it
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sft));
+        if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_out + b, __float_as_uint(m));
+    }
 }
-int cmf_launch_scatter_ft(int b, int n, const float *ft_planar, float *E, int lde, int off, int pad, cudaStream_t st) {
-    scatter_ft_kernel<<<dim3(cmf_divup(n, 256), b), 256, 0, st>>>(n, ft_planar, E, lde, off, pad);
+int cmf_launch_scatter_ft(int b, int n, const float *ft_planar, float *E, int lde, int off, int pad, cudaStream_t st, unsigned int *amax_out) {
+    scatter_ft_kernel<<<dim3(cmf_divup(n, 256), b), 256, 0, st>>>(n, ft_planar, E, lde, off, pad, amax_out);
     CMF_LAUNCH_CHECK();
     return CMF_OK;
 }
@@ -574,8 +583,9 @@ int cmf_launch_fc_build_h1(int b, int n, const float *xyz1_planar, const float *
 constexpr int FCR_PTS = 16;
 __global__ void __launch_bounds__(128)
 fc_reduce_kernel(long long points, int n, const float *__restrict__ xyzq, const float *__restrict__ xyzc, const int *__restrict__ knn,
-                 WeightNetP wn, const float *__restrict__ src, int gather, float *__restrict__ out, int ldo) {
+                 WeightNetP wn, const float *__restrict__ src, int gather, float *__restrict__ out, int ldo, unsigned int *__restrict__ amax_out) {
     __shared__ __align__(16) float sh2[FCR_PTS][8][8];
+    __shared__ float samx[4];
     __shared__ long long srow[FCR_PTS][8];
     const int t = threadIdx.x;
     const long long base = (long long)blockIdx.x * FCR_PTS;
@@ -619,6 +629,8 @@ fc_reduce_kernel(long long points, int n, const float *__restrict__ xyzq, const 
     __syncthreads();
     const int np = (points - base) < FCR_PTS ? (int)(points - base) : FCR_PTS;
     float4 cur[8], nxt[8];
+    float amx = 0.f;                                   // |out| maximum of this thread (per-pair fp16 scale of the consumer GEMM)
+    const long long pair_first = base / n, pair_last = (base + np - 1) / n;
 #pragma unroll
     for (int k = 0; k < 8; ++k) cur[k] = ld4(src + (size_t)srow[0][k] * 512 + t * 4);
     for (int p = 0; p < np; ++p) {
@@ -640,15 +652,30 @@ fc_reduce_kernel(long long points, int n, const float *__restrict__ xyzq, const 
             }
         }
         *reinterpret_cast<float4 *>(out + (size_t)(base + p) * ldo + t * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        if (amax_out) {
+            const float m4 = fmaxf(fmaxf(fabsf(acc[0]), fabsf(acc[1])), fmaxf(fabsf(acc[2]), fabsf(acc[3])));
+            if (pair_first == pair_last) amx = fmaxf(amx, m4);
+            else if (m4 > 0.f) atomicMax(amax_out + (base + p) / n, __float_as_uint(m4));      // CTA straddles two pairs (N % 16 != 0): per point
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
     }
+    if (amax_out && pair_first == pair_last) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) amx = fmaxf(amx, __shfl_xor_sync(0xffffffffu, amx, off));
+        if ((t & 31) == 0) samx[t >> 5] = amx;
+        __syncthreads();
+        if (t == 0) {
+            const float m = fmaxf(fmaxf(samx[0], samx[1]), fmaxf(samx[2], samx[3]));
+            if (m > 0.f) atomicMax(amax_out + pair_first, __float_as_uint(m));
+        }
+    }
 }
 int cmf_launch_fc_reduce(int b, int n, const float *xyzq_planar, const float *xyzc_planar, const int *knn,
-                         WeightNetP wn, const float *src, int gather, float *out, int ldo, cudaStream_t st) {
+                         WeightNetP wn, const float *src, int gather, float *out, int ldo, cudaStream_t st, unsigned int *amax_out) {
     const long long points = (long long)b * n;
     if (points <= 0) return CMF_OK;
-    fc_reduce_kernel<<<cmf_divup(points, FCR_PTS), 128, 0, st>>>(points, n, xyzq_planar, xyzc_planar, knn, wn, src, gather, out, ldo);
+    fc_reduce_kernel<<<cmf_divup(points, FCR_PTS), 128, 0, st>>>(points, n, xyzq_planar, xyzc_planar, knn, wn, src, gather, out, ldo, amax_out);
     CMF_LAUNCH_CHECK();
     return CMF_OK;
 }

@@ -32,7 +32,8 @@ int cmf_launch_maxk(long long points, int K, int C, const float *Y, int ldy, flo
 // G[b][c] = max_i F[(b*N+i)*ldf + c]
 int cmf_launch_globalmax(int b, int n, int C, const float *F, int ldf, float *G, cudaStream_t st);
 // E[(b*N+i)*lde + off + d] = ft[b][d][i] for d<3, zeros for the `pad` columns that follow
-int cmf_launch_scatter_ft(int b, int n, const float *ft_planar, float *E, int lde, int off, int pad, cudaStream_t st);
+// amax_out (optional, here and in fc_reduce): per-pair atomicMax of |values written| (uint bit patterns; caller zeroes)
+int cmf_launch_scatter_ft(int b, int n, const float *ft_planar, float *E, int lde, int off, int pad, cudaStream_t st, unsigned int *amax_out = nullptr);
 
 // flow embedding (FeatureCorrelator) pieces
 int cmf_launch_fc_build_h1(int b, int n, const float *xyz1_planar, const float *xyz2_planar, const int *knn12,
@@ -40,7 +41,7 @@ int cmf_launch_fc_build_h1(int b, int n, const float *xyz1_planar, const float *
 struct WeightNetP { const float *A1, *a1, *A2, *a2, *A3, *a3; };   // 8x4, 8, 8x8, 8, 512x8, 512
 int cmf_launch_fc_reduce(int b, int n, const float *xyzq_planar, const float *xyzc_planar, const int *knn,
                          WeightNetP wn, const float *src, int gather /*0: src rows (b*N+i)*8+k ; 1: src rows b*N+j*/,
-                         float *out, int ldo, cudaStream_t st);
+                         float *out, int ldo, cudaStream_t st, unsigned int *amax_out = nullptr);
 // set-conv #2 first layer after hoisting: Y1[((b*N+i)*K + kk)][c] = relu(P[(b*N+j)*ldp + poff + c] + Wx[c][0..2] . rel)
 int cmf_launch_mse2_build_y1(int b, int n, int K, int koff, const float *xyz_planar, const int *idx60,
                              const float *P, int ldp, int poff, const float *Wx /*512x4 rows for this scale*/,

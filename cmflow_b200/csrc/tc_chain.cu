@@ -303,6 +303,7 @@ struct Mlp2Args {
     const float *in; int ld_in;
     float *out; int ld_out;
     long long rows;
+    unsigned int *amax_out; int rows_per_pair;        // optional: atomicMax of the (non-negative) outputs per frame pair, uint bit patterns
 };
 constexpr int ML_A = 0;                              // A operand: [kb 0: hi, lo][kb 1: hi, lo] = 4 tiles
 constexpr int ML_W = 4 * TILE_BYTES;                 // B operands: [layer][kb]{hi 4 KB, lo 4 KB} (64 rows each)
@@ -411,10 +412,25 @@ mlp2_tc_kernel(const Mlp2Args a) {
             }
             if (l < 2) {
                 rs = mlp2_store_row(base + ML_A, tid, h, mx, valid);       // all MMAs of layer l have retired: A is free
-            } else if (valid) {
-                float4 *dst = reinterpret_cast<float4 *>(a.out + (size_t)row * a.ld_out + s * 64);
+            } else {
+                if (valid) {
+                    float4 *dst = reinterpret_cast<float4 *>(a.out + (size_t)row * a.ld_out + s * 64);
 #pragma unroll
-                for (int q = 0; q < 16; ++q) dst[q] = make_float4(h[2 * q].x, h[2 * q].y, h[2 * q + 1].x, h[2 * q + 1].y);
+                    for (int q = 0; q < 16; ++q) dst[q] = make_float4(h[2 * q].x, h[2 * q].y, h[2 * q + 1].x, h[2 * q + 1].y);
+                }
+                if (a.amax_out) {          // the consumer GEMM's per-pair fp16 scale comes from here instead of a separate pass over the output
+                    const long long pair = valid ? row / a.rows_per_pair : -1;
+                    const long long p0 = __shfl_sync(0xffffffffu, pair, 0);
+                    const float v = valid ? mx : 0.f;
+                    if (__all_sync(0xffffffffu, pair == p0 || !valid) && p0 >= 0) {
+                        float wm = v;
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, off));
+                        if ((tid & 31) == 0 && wm > 0.f) atomicMax(a.amax_out + p0, __float_as_uint(wm));
+                    } else if (valid && v > 0.f) {
+                        atomicMax(a.amax_out + pair, __float_as_uint(v));
+                    }
+                }
             }
         }
         tc_fence_before();
@@ -455,7 +471,8 @@ int cmf_launch_setconv1_tc(int bc, int n, const float *xyz_planar, const float *
     return CMF_OK;
 }
 
-int cmf_launch_mlp2_tc(long long rows, const float *in, int ld_in, float *out, int ld_out, const TcChainMlp2W *w4, cudaStream_t st) {
+int cmf_launch_mlp2_tc(long long rows, const float *in, int ld_in, float *out, int ld_out, const TcChainMlp2W *w4, unsigned int *amax_out,
+                       int rows_per_pair, cudaStream_t st) {
     int rc = init_once();
     if (rc) return rc;
     if (rows <= 0) return CMF_OK;
@@ -464,6 +481,7 @@ int cmf_launch_mlp2_tc(long long rows, const float *in, int ld_in, float *out, i
     for (int s = 0; s < 4; ++s)
         for (int l = 0; l < 3; ++l) { a.Vt[s][l] = w4[s].Vt[l]; a.ainv[s][l] = w4[s].ainv[l]; a.c[s][l] = w4[s].c[l]; }
     a.in = in; a.ld_in = ld_in; a.out = out; a.ld_out = ld_out; a.rows = rows;
+    a.amax_out = amax_out; a.rows_per_pair = rows_per_pair > 0 ? rows_per_pair : 1;
     const long long items = ((rows + 127) / 128) * 4;
     const int grid = (int)(items < 2LL * g_num_sms ? items : 2LL * g_num_sms);
     mlp2_tc_kernel<<<grid, CH_THREADS, ML_SMEM, st>>>(a);

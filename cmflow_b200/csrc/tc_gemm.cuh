@@ -66,4 +66,6 @@ struct TcChainMlp2W { const float *Vt[3], *ainv[3], *c[3]; };                   
 int cmf_launch_setconv1_tc(int bc, int n, const float *xyz_planar, const float *ft_planar, const int *idx60, const TcChainSc1W *w4, float *out,
                            cudaStream_t st);
 // out[row][s*64 + o] = mlp2_s(in[row][s*64 .. +63]) for the four scales
-int cmf_launch_mlp2_tc(long long rows, const float *in, int ld_in, float *out, int ld_out, const TcChainMlp2W *w4, cudaStream_t st);
+// amax_out (optional): per-pair atomicMax of the outputs (uint bit patterns, caller zeroes), rows_per_pair rows per frame pair
+int cmf_launch_mlp2_tc(long long rows, const float *in, int ld_in, float *out, int ld_out, const TcChainMlp2W *w4, unsigned int *amax_out,
+                       int rows_per_pair, cudaStream_t st);
