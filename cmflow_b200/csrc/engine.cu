@@ -139,6 +139,10 @@ struct cmf_model {
     float *d_in = nullptr, *d_out = nullptr; size_t d_in_floats = 0, d_out_bytes = 0;
     int launches = 0;
     int last_b = 0, last_n = 0;
+    // host entry point: the kernel sequence of one (b, n, mode) forward between the staging buffers, captured once as a CUDA graph
+    // (39 launches -> 1 cudaGraphLaunch: the host path synchronises every call, so launch latency is not hidden behind the GPU there)
+    struct HostGraph { int b, n, mode, has_g; cudaGraphExec_t exec; };
+    std::vector<HostGraph> graphs;
     // tensor-core (tcgen05, 3xTF32) mode: pre-tiled hi/lo copies of the big weight matrices
     int tc = 0;
     int fused_sc1 = 1;           // CMF_FUSED_SC1=0 falls back to the unfused (GEMM-per-layer) set-conv #1 for A/B testing
@@ -160,6 +164,11 @@ struct cmf_model {
     std::vector<cudaEvent_t> pool; size_t pool_used = 0;
     double work[16] = {0}; int nlaunch[16] = {0}; float ms[16] = {0};
 };
+
+static void drop_graphs(cmf_model *m) {
+    for (auto &g : m->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    m->graphs.clear();
+}
 
 static void prof_events(cmf_model *m, cudaEvent_t *a, cudaEvent_t *b) {
     while (m->pool.size() < m->pool_used + 2) { cudaEvent_t e; cudaEventCreate(&e); m->pool.push_back(e); }
@@ -285,6 +294,7 @@ static int ensure_workspace(cmf_model *m, int b, int n) {
     // chunk size: as many pairs as fit the workspace arena (default 64 GiB of the 180 GB, at most half of what is free; CMF_WS_GB / CMF_CHUNK_PAIRS override).
     // Few large chunks amortise the per-launch prologue of the persistent tensor-core kernels (cluster launch, TMEM allocation,
     // pipeline fill: ~40 us each, ~14 such launches per chunk).
+    if (m->ws && m->cap_n == n && m->cap_bc >= b && !getenv("CMF_CHUNK_PAIRS")) return CMF_OK;      // whole batch fits what we hold (also the path taken under stream capture)
     size_t budget = (size_t)64 << 30;                 // of the 180 GB: one chunk for B=256 at N=256 (15 GB) and for B=64 at N=4096 (49 GB)
     {
         size_t free_b = 0, total_b = 0;
@@ -304,6 +314,7 @@ static int ensure_workspace(cmf_model *m, int b, int n) {
     if (m->ws && m->cap_n == n && m->cap_bc >= bc) return CMF_OK;
     if (m->ws && m->cap_n == n && m->cap_bc < bc && !env) { /* grow */ }
     if (m->ws) { cudaFree(m->ws); m->ws = nullptr; }
+    drop_graphs(m);                                   // captured graphs hold workspace pointers
     const size_t bytes = chunk_bytes(bc, n);
     cudaError_t e = cudaMalloc(&m->ws, bytes);
     if (e != cudaSuccess) {
@@ -635,6 +646,7 @@ extern "C" int cmf_model_create(cmf_model **out, const float *blob, size_t blob_
 
 extern "C" void cmf_model_destroy(cmf_model *m) {
     if (!m) return;
+    drop_graphs(m);
     if (m->ws) cudaFree(m->ws);
     if (m->d_blob) cudaFree(m->d_blob);
     if (m->d_in) cudaFree(m->d_in);
@@ -721,6 +733,7 @@ extern "C" int cmf_model_forward_host(cmf_model *m, int b, int n, const float *p
     const size_t pn = (size_t)b * 3 * n;
     const size_t in_floats = 4 * pn + (size_t)b * 256;
     const size_t out_bytes = (pn + (size_t)b * n + (size_t)b * 16 + (size_t)b * 256) * sizeof(float) + (size_t)b * n;
+    if (m->d_in_floats < in_floats || m->d_out_bytes < out_bytes) drop_graphs(m);     // ... and staging pointers
     if (m->d_in_floats < in_floats) {
         if (m->d_in) cudaFree(m->d_in);
         m->d_in = nullptr; m->d_in_floats = 0;
@@ -741,7 +754,37 @@ extern "C" int cmf_model_forward_host(cmf_model *m, int b, int n, const float *p
     CMF_CUDA(cudaMemcpyAsync(d_ft1, ft1, pn * sizeof(float), cudaMemcpyHostToDevice, st));
     CMF_CUDA(cudaMemcpyAsync(d_ft2, ft2, pn * sizeof(float), cudaMemcpyHostToDevice, st));
     if (gfeat_prev) CMF_CUDA(cudaMemcpyAsync(d_g, gfeat_prev, (size_t)b * 256 * sizeof(float), cudaMemcpyHostToDevice, st));
-    int rc = cmf_model_forward(m, b, n, d_pc1, d_pc2, d_ft1, d_ft2, gfeat_prev ? d_g : nullptr, d_sf, d_cls, d_tr, d_mask, d_go, st);
+    int rc = CMF_OK;
+    {
+        static const bool no_graph = getenv("CMF_NO_GRAPH") != nullptr;
+        const int has_g = gfeat_prev ? 1 : 0;
+        cmf_model::HostGraph *hg = nullptr;
+        for (auto &g : m->graphs) if (g.b == b && g.n == n && g.mode == m->tc && g.has_g == has_g) hg = &g;
+        if (no_graph || m->profiling || m->raflow) {
+            rc = cmf_model_forward(m, b, n, d_pc1, d_pc2, d_ft1, d_ft2, gfeat_prev ? d_g : nullptr, d_sf, d_cls, d_tr, d_mask, d_go, st);
+        } else if (!hg) {
+            // first call of this shape: eager (one-time attribute settings, weight tiling and allocations happen here, outside any capture)
+            rc = cmf_model_forward(m, b, n, d_pc1, d_pc2, d_ft1, d_ft2, gfeat_prev ? d_g : nullptr, d_sf, d_cls, d_tr, d_mask, d_go, st);
+            if (rc == CMF_OK) m->graphs.push_back({b, n, m->tc, has_g, nullptr});
+        } else {
+            if (!hg->exec) {
+                cudaGraph_t graph = nullptr;
+                const int launches = m->launches;
+                if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                    rc = cmf_model_forward(m, b, n, d_pc1, d_pc2, d_ft1, d_ft2, gfeat_prev ? d_g : nullptr, d_sf, d_cls, d_tr, d_mask, d_go, st);
+                    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+                    if (rc == CMF_OK && ce == cudaSuccess && graph) {
+                        if (cudaGraphInstantiate(&hg->exec, graph, 0) != cudaSuccess) hg->exec = nullptr;
+                    }
+                    if (graph) cudaGraphDestroy(graph);
+                    if (rc != CMF_OK) return rc;
+                }
+                if (!hg->exec) { cudaGetLastError(); hg->b = -1; m->launches = launches; }       // capture unavailable: this shape stays eager
+            }
+            if (hg->exec) CMF_CUDA(cudaGraphLaunch(hg->exec, st));
+            else rc = cmf_model_forward(m, b, n, d_pc1, d_pc2, d_ft1, d_ft2, gfeat_prev ? d_g : nullptr, d_sf, d_cls, d_tr, d_mask, d_go, st);
+        }
+    }
     if (rc != CMF_OK) return rc;
     CMF_CUDA(cudaMemcpyAsync(sf_agg, d_sf, pn * sizeof(float), cudaMemcpyDeviceToHost, st));
     CMF_CUDA(cudaMemcpyAsync(stat_cls, d_cls, (size_t)b * n * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -124,6 +124,29 @@ def test_host_entry_point_equals_device_entry_point(golden_dir):
     assert torch.equal(host["pre_trans"], dev["pre_trans"]) and torch.equal(host["mask"].bool(), dev["mask"])
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+def test_host_entry_point_graph_replay(precision):
+    """cmf_model_forward_host runs a shape eagerly once, captures its kernel sequence as a CUDA graph on the second call and replays it
+    afterwards: every call must equal the device entry point on that call's inputs (different inputs, same and different shapes, CMFlow-T
+    with and without a carried state)."""
+    net = CMFlow(Args()); net.load_state_dict(synthetic_state_dict(0)); net = net.to(DEV); net.set_precision(precision)
+    for seed, B, N in ((1, 3, 256), (2, 3, 256), (3, 3, 256), (4, 2, 200), (5, 3, 256), (6, 2, 200), (7, 2, 200)):
+        inp = make_pairs(B, N, seed=seed)
+        dev = run(net, inp)
+        host = net.forward_host(*[t.pin_memory() for t in inp[:4]])
+        assert torch.equal(host["sf_agg"], dev["sf_agg"]) and torch.equal(host["pre_trans"], dev["pre_trans"]), (seed, B, N)
+        assert torch.equal(host["stat_cls"], dev["stat_cls"]) and torch.equal(host["mask"].bool(), dev["mask"])
+    nett = CMFlow_T(Args()); nett.load_state_dict(synthetic_state_dict(3, temporal=True)); nett = nett.to(DEV); nett.set_precision(precision)
+    inp = make_pairs(2, 256, seed=9)
+    for rep in range(3):
+        g_dev, g_host = None, None
+        for step in range(3):
+            dev = run(nett, inp, g_dev)
+            host = nett.forward_host(*[t.pin_memory() for t in inp[:4]], gfeat=g_host)
+            assert torch.equal(host["sf_agg"], dev["sf_agg"]) and torch.equal(host["gfeat"], dev["gfeat"].cpu()), (rep, step)
+            g_dev, g_host = dev["gfeat"], host["gfeat"].clone()
+
+
 def test_kabsch_matches_reference_golden(golden_dir):
     gold = load_golden(golden_dir, "kabsch_n128.pt")
     A, Bp, W = gold["A"].to(DEV), gold["B"].to(DEV), gold["W"].to(DEV)
