@@ -423,8 +423,13 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
 
     // flow embedding (FeatureCorrelator, radarflow_util.py:185-237)
     bool fused_wsum = false;
-    { const GemmArgs ga_ = mk(S(FC_WCG), 256, w.G1, 256, w.PB1, 512, S(FC_B1), 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
-    { const GemmArgs ga_ = mk(S(FC_WNG), 256, w.G2, 256, w.PB2, 512, nullptr, 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
+    {   // per-pair bias vectors (the broadcast global-max features times their column blocks): flow embedding x2 and set-conv #2, one batched launch
+        GemmBatch gb; gb.count = 3;
+        gb.g[0] = mk(S(FC_WCG), 256, w.G1, 256, w.PB1, 512, S(FC_B1), 512, 256, bc, CMF_ACT_NONE);
+        gb.g[1] = mk(S(FC_WNG), 256, w.G2, 256, w.PB2, 512, nullptr, 512, 256, bc, CMF_ACT_NONE);
+        gb.g[2] = mk(S(M2_WG), 256, w.G1, 256, w.PBM, 2048, S(M2_T1), 2048, 256, bc, CMF_ACT_NONE);
+        RUN(C_GEMM_FC_HOIST, gflops(gb), cmf_launch_gemm(gb, st));
+    }
     if (m->tc) {
         if (F) {    // per-pair maxima of the GEMM inputs (fp16 scales): encoder features, kNN direction components
             if (!fused_amax) {
@@ -478,7 +483,6 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
     RUN(C_REDUCE, 0, cmf_launch_fc_reduce(bc, n, pc1, pc1, w.KNN11, wn2, w.COST1, 1, w.E + 256, E_LD, st, fused_amax ? AM(AM_COR) : nullptr));
 
     // set-conv #2 (mse_layer2, cmflow.py:87-89)
-    { const GemmArgs ga_ = mk(S(M2_WG), 256, w.G1, 256, w.PBM, 2048, S(M2_T1), 2048, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_SC2_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     if (m->tc) {
         if (F && !fused_amax) RUN(C_REDUCE, 0, cmf_launch_pair_absmax(bc, n, w.E, E_LD, E_LD, AM(AM_E), st));
         TcArgs ta_ = tc_plain(T.m2_wp, F, 2048, E_LD, w.E, E_LD, w.P, 2048, nullptr, bn, CMF_ACT_NONE, w.PBM, 2048, n);

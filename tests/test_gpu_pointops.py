@@ -165,3 +165,43 @@ def test_query_and_group_matches_reference_composition():
     gx = P.group_points(xyz.transpose(1, 2).contiguous(), idx) - xyz.transpose(1, 2).unsqueeze(-1)
     want = torch.cat([gx, P.group_points(feats, idx)], 1)
     assert torch.equal(out.cpu(), want)
+
+
+@pytest.mark.parametrize("case", ["all_equal", "grid_ties", "few_candidates", "inf_nan", "chunk_boundary"])
+def test_knn_adversarial_order_and_ties(case):
+    """The warp-distributed k-NN list against the C restatement (and the reference's own kernel) where ORDER is decided by ties:
+    identical points (every distance equal: index order), integer-grid clouds (many exact ties at every rank), fewer candidates than k
+    (unfilled slots -> index 0), non-finite coordinates (never selected), and candidates that straddle the 2048-point staging chunk."""
+    g = torch.Generator().manual_seed(5)
+    B = 2
+    if case == "all_equal":
+        known = torch.ones(B, 300, 3) * torch.tensor([3.0, -2.0, 0.5]); unk = torch.randn(B, 70, 3, generator=g)
+    elif case == "grid_ties":
+        known = torch.randint(-3, 4, (B, 500, 3), generator=g).float(); unk = torch.randint(-3, 4, (B, 130, 3), generator=g).float()
+    elif case == "few_candidates":
+        known = torch.randn(B, 5, 3, generator=g); unk = torch.randn(B, 33, 3, generator=g)
+    elif case == "inf_nan":
+        known = torch.randn(B, 200, 3, generator=g)
+        known[0, 3, 0] = float("inf"); known[0, 40, 1] = float("nan"); known[1, 0, 2] = float("-inf"); known[1, 199] = float("nan")
+        unk = torch.randn(B, 64, 3, generator=g)
+    else:
+        known = torch.randn(B, 2048 + 37, 3, generator=g) * 5
+        known[:, 2040:2060] = known[:, :20]                      # exact duplicates on both sides of the chunk boundary
+        unk = known[:, :40].clone()
+    from cmflow_b200 import pointnet2_cuda as K
+    N, M = known.shape[1], unk.shape[1]
+    for k in (1, 3, 8, 32):
+        d2w, iw = P.knn(k, unk, known)
+        d2 = torch.empty(B, M, k, device=DEV); idx = torch.empty(B, M, k, dtype=torch.int32, device=DEV)
+        K.knn_wrapper(B, M, N, k, unk.to(DEV), known.to(DEV), d2, idx)
+        assert torch.equal(idx.cpu(), iw), (case, k)
+        assert torch.equal(d2.cpu().nan_to_num(posinf=1e30), d2w.nan_to_num(posinf=1e30)), (case, k)
+        if R.available():
+            d2r, ir = R.knn(k, unk.to(DEV), known.to(DEV))
+            assert torch.equal(idx, ir), (case, k, "reference kernel")
+        if k <= N and case != "inf_nan":                         # the model's k-NN (expanded-form distance, radarflow_util.py:88-99)
+            ipw, dpw = P.knn_point(k, known, unk)
+            ip = torch.empty(B, M, k, dtype=torch.int32, device=DEV); dp = torch.empty(B, M, k, device=DEV)
+            kd, ud = known.to(DEV), unk.to(DEV)
+            check(lib().cmf_knn_point(B, N, M, k, dptr(kd), dptr(ud), dptr(ip), dptr(dp), stream_ptr()))
+            assert torch.equal(ip.cpu(), ipw) and torch.equal(dp.cpu(), dpw), (case, k, "knn_point")
