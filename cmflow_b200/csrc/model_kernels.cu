@@ -619,12 +619,15 @@ fc_reduce_kernel(long long points, int n, const float *__restrict__ xyzq, const 
         *reinterpret_cast<float4 *>(&sh2[p][k][4]) = make_float4(h2[4], h2[5], h2[6], h2[7]);
         srow[p][k] = row;
     }
-    float4 A3[4][2];
-    float a3[4];
+    // last WeightNet layer of this thread's four channels, paired for packed fp32: P[h][j] = (A3[2h][j], A3[2h+1][j])
+    float2 P[2][8], a3p[2];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        A3[c][0] = ld4(wn.A3 + (t * 4 + c) * 8); A3[c][1] = ld4(wn.A3 + (t * 4 + c) * 8 + 4);
-        a3[c] = __ldg(wn.a3 + t * 4 + c);
+    for (int h = 0; h < 2; ++h) {
+        const float4 r0a = ld4(wn.A3 + (t * 4 + 2 * h) * 8), r0b = ld4(wn.A3 + (t * 4 + 2 * h) * 8 + 4);
+        const float4 r1a = ld4(wn.A3 + (t * 4 + 2 * h + 1) * 8), r1b = ld4(wn.A3 + (t * 4 + 2 * h + 1) * 8 + 4);
+        P[h][0] = make_float2(r0a.x, r1a.x); P[h][1] = make_float2(r0a.y, r1a.y); P[h][2] = make_float2(r0a.z, r1a.z); P[h][3] = make_float2(r0a.w, r1a.w);
+        P[h][4] = make_float2(r0b.x, r1b.x); P[h][5] = make_float2(r0b.y, r1b.y); P[h][6] = make_float2(r0b.z, r1b.z); P[h][7] = make_float2(r0b.w, r1b.w);
+        a3p[h] = make_float2(__ldg(wn.a3 + t * 4 + 2 * h), __ldg(wn.a3 + t * 4 + 2 * h + 1));
     }
     __syncthreads();
     const int np = (points - base) < FCR_PTS ? (int)(points - base) : FCR_PTS;
@@ -638,19 +641,21 @@ fc_reduce_kernel(long long points, int n, const float *__restrict__ xyzq, const 
 #pragma unroll
             for (int k = 0; k < 8; ++k) nxt[k] = ld4(src + (size_t)srow[p + 1][k] * 512 + t * 4);
         }
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float2 acc2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const float4 ha = *reinterpret_cast<const float4 *>(&sh2[p][k][0]), hb = *reinterpret_cast<const float4 *>(&sh2[p][k][4]);
-            const float sv[4] = {cur[k].x, cur[k].y, cur[k].z, cur[k].w};
+            const float hv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+            const float2 sv[2] = {make_float2(cur[k].x, cur[k].y), make_float2(cur[k].z, cur[k].w)};
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float w = a3[c];
-                w = fmaf(A3[c][0].x, ha.x, w); w = fmaf(A3[c][0].y, ha.y, w); w = fmaf(A3[c][0].z, ha.z, w); w = fmaf(A3[c][0].w, ha.w, w);
-                w = fmaf(A3[c][1].x, hb.x, w); w = fmaf(A3[c][1].y, hb.y, w); w = fmaf(A3[c][1].z, hb.z, w); w = fmaf(A3[c][1].w, hb.w, w);
-                acc[c] = fmaf(fmaxf(w, 0.f), sv[c], acc[c]);
+            for (int h = 0; h < 2; ++h) {
+                float2 w = a3p[h];                      // same fma order per channel as the scalar form: bit-identical
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w = __ffma2_rn(P[h][j], make_float2(hv[j], hv[j]), w);
+                acc2[h] = __ffma2_rn(make_float2(fmaxf(w.x, 0.f), fmaxf(w.y, 0.f)), sv[h], acc2[h]);
             }
         }
+        const float acc[4] = {acc2[0].x, acc2[0].y, acc2[1].x, acc2[1].y};
         *reinterpret_cast<float4 *>(out + (size_t)(base + p) * ldo + t * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         if (amax_out) {
             const float m4 = fmaxf(fmaxf(fabsf(acc[0]), fabsf(acc[1])), fmaxf(fabsf(acc[2]), fabsf(acc[3])));
