@@ -203,6 +203,20 @@ def test_dense_cloud_config_runs_and_matches_oracle_prefix():
     assert torch.equal(both["sf_agg"][:1], one["sf_agg"]) and torch.equal(both["pre_trans"][:1], one["pre_trans"])
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+@pytest.mark.parametrize("B,N", [(2, 8), (3, 33), (1, 129)])
+def test_tiny_and_ragged_clouds_match_oracle(B, N, precision):
+    """Smallest legal cloud (N = 8 = the k of knn_point), N below the largest nsample, N not a multiple of any tile: whole forward against the
+    CPU oracle.  (Tiles of the tensor-core kernels are mostly padding here; every row / column guard is exercised.)"""
+    sd = synthetic_state_dict(0)
+    net = CMFlow(Args()); net.load_state_dict(sd); net = net.to(DEV); net.set_precision(precision)
+    inp = make_pairs(B, N, seed=21 + N)
+    out = run(net, inp)
+    ref = O.cmflow_forward(sd, *inp[:4], return_intermediates=True)
+    assert knn_sets_equal(net.tap("knn12", (B, N, 8), torch.int32).cpu(), ref["knn12"].long().sort(-1)[0])
+    print(B, N, precision, check_outputs(out, ref))
+
+
 def test_fused_setconv1_equals_layerwise(golden_dir, monkeypatch):
     """The fused gather+MLP+max kernel of set-conv #1 against the GEMM-per-layer path (same fp32 FMAs, bias added first
     instead of last): agreement to fp32 rounding."""
