@@ -16,7 +16,7 @@
 //   full_local[s]  : local  -- bulk copy expect_tx + 8 producer warps                      (count 1 + 8, or 1 when B is bulk-copied)
 //   peer_full[s]   : leader -- remote arrive by the peer's forwarder                        (count 1)
 //   empty[s]       : both   -- tcgen05.commit.cta_group::2 multicast from the leader        (count 1)
-//   tfull[a]       : both   -- commit multicast after the last K stage of a tile            (count 1)
+//   tfull[a]       : both   -- commit multicast by each of the two MMA issuers after its last K stage of a tile (count 2)
 //   tempty[a]      : leader -- 4 local + 4 remote epilogue warps                            (count 8)
 #include "tc_dev.cuh"
 
@@ -122,7 +122,8 @@ tc_gemm2_kernel(const TcArgs a) {
             mbar_init(pfull_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); mbar_init(h2full_bar(s), 8); mbar_init(h2empty_bar(s), 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 2); mbar_init(tempty_bar(s), 8); mbar_init(h2full_bar(s), 8); mbar_init(h2empty_bar(s), 4); }
+        *reinterpret_cast<volatile uint32_t *>(smem + RING_BYTES + 232) = 0u;       // issuers' turn counter
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -166,20 +167,28 @@ tc_gemm2_kernel(const TcArgs a) {
             }
             if (a.dbg) a.dbg[(size_t)blockIdx.x * 8 + 4] = dw0;
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer (leader CTA only): one instruction stream drives both SMs' tensor cores =====
-        if (leader) {
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (long long t = cl_id; t < ntiles; t += n_cl) {
-                TIMED(dw0, mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1));
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int ks = 0; ks < nks; ++ks) {
+    } else if (leader && (warp == 1 || warp == 3)) {
+        // ===== MMA issuers (leader CTA only): two warps drive both SMs' tensor cores, stage by stage in turn =====
+        // tcgen05.mma issue blocks at the tensor pipe's own rate (~118 clk per M256xN256xK16 MMA measured): with ONE issuer everything else
+        // it does per stage -- waiting for the operands, fences, the multicast commits: ~45 % of the stage period -- was tensor-pipe idle time.
+        // Warp 1 takes the even stages, warp 3 (idle in the leader otherwise) the odd ones; while one is blocked in its six MMAs the other
+        // waits for / fences / commits its own stage.  `turn` (shared memory, polled) hands the pipe over in stage order, so the MMAs still
+        // enter the pipe -- and accumulate -- in exactly the single-issuer order: results stay bit-reproducible.
+        const int me = warp == 3 ? 1 : 0;
+        volatile uint32_t *turn = reinterpret_cast<volatile uint32_t *>(smem + RING_BYTES + 232);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        uint32_t g = 0;                                             // running stage number over all tiles of this cluster
+        for (long long t = cl_id; t < ntiles; t += n_cl) {
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int ks = 0; ks < nks; ++ks, ++g) {
+                if ((int)(g & 1u) == me) {
+                    if (ks == 0) { TIMED(dw0, mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1)); }     // the tile's first MMA overwrites the accumulator
                     TIMED(dw1, mbar_wait(full_bar(stage), phase));                 // my half
                     TIMED(dw2, mbar_wait_cluster(pfull_bar(stage), phase));        // the peer's half (relayed)
                     tc_fence_after();
                     if (lane == 0) {
+                        while (*turn != g) { }                                      // the other issuer has handed the pipe over
                         const uint32_t sa = base + stage * STAGE_BYTES;
                         const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + TILE_A_FLOATS * 4);
                         const uint64_t b_hi = make_desc(sa + 2 * TILE_A_FLOATS * 4), b_lo = make_desc(sa + 2 * TILE_A_FLOATS * 4 + TILE_BH_FLOATS * 4);
@@ -196,16 +205,20 @@ tc_gemm2_kernel(const TcArgs a) {
                                 tc_mma2_tf32(d_tmem, a_hi + adv, b_hi + adv, IDESC2_TF32, 1u);
                             }
                         }
+                        *turn = g + 1;
                         tc_commit2_mc(empty_bar(stage));
-                        if (ks == nks - 1) tc_commit2_mc(tfull_bar(acc));
+                        // the accumulator is complete when BOTH issuers' MMAs of the tile have retired: each commits after its last stage
+                        if (ks >= nks - 2 || nks == 1) tc_commit2_mc(tfull_bar(acc));
                     }
                     __syncwarp();
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                } else if (nks == 1 && lane == 0) {
+                    tc_commit2_mc(tfull_bar(acc));                                  // no stage of mine in this tile: still owe my arrival
                 }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
-            if (a.dbg && lane == 0) { a.dbg[(size_t)blockIdx.x * 8 + 1] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 2] = dw1; a.dbg[(size_t)blockIdx.x * 8 + 3] = dw2; }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (a.dbg && lane == 0 && me == 0) { a.dbg[(size_t)blockIdx.x * 8 + 1] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 2] = dw1; a.dbg[(size_t)blockIdx.x * 8 + 3] = dw2; }
     } else if (warp == 2 && PROD != TC_PROD_TILED) {
         // ===== context filler (idle after the TMEM allocation): neighbour index -> row pointers, rel-xyz, fp16 scale for the tile two
         // ahead of the producers, so that those dependent global loads never sit on the producers' critical path =====
@@ -235,18 +248,21 @@ tc_gemm2_kernel(const TcArgs a) {
                 t = tn; buf = buf == 2 ? 0 : buf + 1;
             }
         }
-    } else if (warp == 3) {
-        // ===== forwarder (peer CTA only): tell the leader when this CTA's half of a stage is complete =====
-        if (!leader) {
-            int stage = 0; uint32_t phase = 0;
-            for (long long t = cl_id; t < ntiles; t += n_cl)
-                for (int ks = 0; ks < nks; ++ks) {
+    } else if (warp == 1 || warp == 3) {
+        // ===== forwarders (peer CTA: its warps 1 and 3, alternating stages): tell the leader when this CTA's half of a stage is complete =====
+        // (the relay is a serial wait -> remote arrive per stage; a release.cluster arrive on it was the pair kernel's critical path)
+        const int me = warp == 3 ? 1 : 0;
+        int stage = 0; uint32_t phase = 0;
+        uint32_t g = 0;
+        for (long long t = cl_id; t < ntiles; t += n_cl)
+            for (int ks = 0; ks < nks; ++ks, ++g) {
+                if ((int)(g & 1u) == me) {
                     mbar_wait(full_bar(stage), phase);
-                    if (lane == 0) mbar_arrive_remote(pfull_bar(stage), 0);
+                    if (lane == 0) mbar_arrive_remote_relaxed(pfull_bar(stage), 0);
                     __syncwarp();
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
-        }
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
     } else if (warp >= 4 && warp < 8) {
         // ===== epilogue: this CTA's 128 accumulator rows x 256 columns =====
         const int q = warp & 3;
