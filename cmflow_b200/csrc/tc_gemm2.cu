@@ -289,24 +289,34 @@ tc_gemm2_kernel(const TcArgs a) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cc, r);
                 if (a.epi == TC_EPI_WSUM) {
+                    // h2s holds the WeightNet hidden vectors of column PAIRS interleaved ([pair][j][2]): one 128-bit broadcast read brings
+                    // (h[e][j], h[e+1][j], h[e][j+1], h[e+1][j+1]), and the last WeightNet layer of two columns is 8 FFMA2 instead of 16 FFMA
                     const float4 *hv = reinterpret_cast<const float4 *>(h2s + ((size_t)acc * BN + cc) * 8);
                     if (es.track && c0 + cc >= es.pair_end) epi_advance(a, es, c0 + cc, m, m_ok);
                     const bool one_pair = (c0 + cc + 32 <= a.cols) && (c0 + cc + 32 <= es.pair_end);
+                    const float slope = act_slope(a.act);
 #pragma unroll
                     for (int g0 = 0; g0 < 32; g0 += 8) {             // one point = 8 consecutive columns (always inside one frame pair)
                         const long long c = c0 + cc + g0;
                         float inv = es.inv;
                         if (F16 && !one_pair && c < a.cols) inv = es.ainv * __frcp_rn(b_scale_of(a, c / a.cols_per_pair));
-                        float sum = 0.f;
+                        const float2 inv2 = make_float2(inv, inv), bias2 = make_float2(bias, bias), slope2 = make_float2(slope, slope);
+                        float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float4 ha = hv[(g0 + e) * 2], hb = hv[(g0 + e) * 2 + 1];      // broadcast reads
-                            float w = w3c;
-                            w = fmaf(w3a.x, ha.x, w); w = fmaf(w3a.y, ha.y, w); w = fmaf(w3a.z, ha.z, w); w = fmaf(w3a.w, ha.w, w);
-                            w = fmaf(w3b.x, hb.x, w); w = fmaf(w3b.y, hb.y, w); w = fmaf(w3b.z, hb.z, w); w = fmaf(w3b.w, hb.w, w);
-                            sum = fmaf(fmaxf(w, 0.f), act_apply(fmaf(__uint_as_float(r[g0 + e]), inv, bias), a.act), sum);
+                        for (int e = 0; e < 8; e += 2) {
+                            const float4 *hp = hv + ((g0 + e) >> 1) * 4;                    // broadcast reads
+                            const float4 q0 = hp[0], q1 = hp[1], q2 = hp[2], q3 = hp[3];
+                            float2 w = make_float2(w3c, w3c);                               // per column the same fma chain as the scalar form
+                            w = __ffma2_rn(make_float2(q0.x, q0.y), make_float2(w3a.x, w3a.x), w); w = __ffma2_rn(make_float2(q0.z, q0.w), make_float2(w3a.y, w3a.y), w);
+                            w = __ffma2_rn(make_float2(q1.x, q1.y), make_float2(w3a.z, w3a.z), w); w = __ffma2_rn(make_float2(q1.z, q1.w), make_float2(w3a.w, w3a.w), w);
+                            w = __ffma2_rn(make_float2(q2.x, q2.y), make_float2(w3b.x, w3b.x), w); w = __ffma2_rn(make_float2(q2.z, q2.w), make_float2(w3b.y, w3b.y), w);
+                            w = __ffma2_rn(make_float2(q3.x, q3.y), make_float2(w3b.z, w3b.z), w); w = __ffma2_rn(make_float2(q3.z, q3.w), make_float2(w3b.w, w3b.w), w);
+                            float2 v = __ffma2_rn(make_float2(__uint_as_float(r[g0 + e]), __uint_as_float(r[g0 + e + 1])), inv2, bias2);
+                            const float2 vs = __fmul2_rn(v, slope2);
+                            v = make_float2(fmaxf(v.x, vs.x), fmaxf(v.y, vs.y));           // act as max(v, slope * v)
+                            sum2 = __ffma2_rn(make_float2(fmaxf(w.x, 0.f), fmaxf(w.y, 0.f)), v, sum2);
                         }
-                        if (c < a.cols && m_ok) a.Out[(size_t)(c >> 3) * a.ldo + m] = sum;
+                        if (c < a.cols && m_ok) a.Out[(size_t)(c >> 3) * a.ldo + m] = sum2.x + sum2.y;
                     }
                 } else {
                     epilogue_chunk(a, r, ct, c0, cc, m, m_ok, bias, es, TILE_B_FLOATS);
@@ -510,9 +520,9 @@ tc_gemm2_kernel(const TcArgs a) {
                 }
             }
             mbar_wait(h2empty_bar(acc), acc_phase ^ 1);
-            float4 *dst = reinterpret_cast<float4 *>(h2s + ((size_t)acc * BN + p) * 8);
-            dst[0] = make_float4(h2[0], h2[1], h2[2], h2[3]);
-            dst[1] = make_float4(h2[4], h2[5], h2[6], h2[7]);
+            float *dst = h2s + ((((size_t)acc * BN + p) >> 1) * 16) + (p & 1);            // [column pair][j][2]
+#pragma unroll
+            for (int u = 0; u < 8; ++u) dst[u * 2] = h2[u];
             __syncwarp();
             if (lane == 0) mbar_arrive(h2full_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
