@@ -324,7 +324,7 @@ def main():
         split = {"tf32x3": ("3xTF32", 6), "fp16x3": ("3xFP16", 3)}.get(args.precision)
         peak_tf = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
         traffic, traffic_src = None, None
-        tj = os.path.join(ROOT, "profiles", "r01b_tc_gemm2_traffic.json")
+        tj = os.path.join(ROOT, "profiles", "r01f_tc_gemm2_traffic.json")
         if args.precision == "fp16x3" and B == 256 and N == 256 and os.path.exists(tj):      # the ncu capture is of exactly this workload
             tjd = json.load(open(tj))
             traffic, traffic_src = tjd["traffic_bytes_per_launch_avg"], tjd["source"]
