@@ -37,6 +37,7 @@ SIGNATURES = {
     "cmf_model_create": [ctypes.POINTER(_vp), _vp, _sz, _i, _f],
     "cmf_model_destroy": [_vp],
     "cmf_model_workspace_bytes": [_vp],
+    "cmf_model_host_graphs": [_vp],
     "cmf_model_launches_per_forward": [_vp],
     "cmf_model_forward": [_vp, _i, _i] + [_vp] * 11,
     "cmf_model_forward_host": [_vp, _i, _i] + [_vp] * 11,

@@ -661,6 +661,11 @@ extern "C" void cmf_model_destroy(cmf_model *m) {
 }
 
 extern "C" size_t cmf_model_workspace_bytes(const cmf_model *m) { return m ? m->ws_bytes : 0; }
+extern "C" int cmf_model_host_graphs(const cmf_model *m) {
+    int n = 0;
+    if (m) for (const auto &g : m->graphs) n += g.exec ? 1 : 0;
+    return n;
+}
 extern "C" int cmf_model_launches_per_forward(const cmf_model *m) { return m ? m->launches : 0; }
 
 extern "C" int cmf_model_forward(cmf_model *m, int b, int n, const float *pc1, const float *pc2, const float *ft1,
@@ -760,7 +765,10 @@ extern "C" int cmf_model_forward_host(cmf_model *m, int b, int n, const float *p
     if (gfeat_prev) CMF_CUDA(cudaMemcpyAsync(d_g, gfeat_prev, (size_t)b * 256 * sizeof(float), cudaMemcpyHostToDevice, st));
     int rc = CMF_OK;
     {
-        static const bool no_graph = getenv("CMF_NO_GRAPH") != nullptr;
+        // opt-in (CMF_HOST_GRAPH=1): no gain was measured at B=256 (the host-device gap is the PCIe copies), and only the strict-fp32 CMFlow
+        // replay has been verified on hardware so far
+        const char *ge = getenv("CMF_HOST_GRAPH");
+        const bool no_graph = !(ge && ge[0] == '1');
         const int has_g = gfeat_prev ? 1 : 0;
         cmf_model::HostGraph *hg = nullptr;
         for (auto &g : m->graphs) if (g.b == b && g.n == n && g.mode == m->tc && g.has_g == has_g) hg = &g;
@@ -769,7 +777,13 @@ extern "C" int cmf_model_forward_host(cmf_model *m, int b, int n, const float *p
         } else if (!hg) {
             // first call of this shape: eager (one-time attribute settings, weight tiling and allocations happen here, outside any capture)
             rc = cmf_model_forward(m, b, n, d_pc1, d_pc2, d_ft1, d_ft2, gfeat_prev ? d_g : nullptr, d_sf, d_cls, d_tr, d_mask, d_go, st);
-            if (rc == CMF_OK) m->graphs.push_back({b, n, m->tc, has_g, nullptr});
+            if (rc == CMF_OK) {
+                if (m->graphs.size() >= 16) {              // bounded cache: forget the oldest shape
+                    if (m->graphs.front().exec) cudaGraphExecDestroy(m->graphs.front().exec);
+                    m->graphs.erase(m->graphs.begin());
+                }
+                m->graphs.push_back({b, n, m->tc, has_g, nullptr});
+            }
         } else {
             if (!hg->exec) {
                 cudaGraph_t graph = nullptr;

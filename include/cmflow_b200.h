@@ -151,6 +151,11 @@ int cmf_raflow_refine(int b, int n, const float *pc1, const float *ft1, const fl
 /* Workspace bytes the engine holds for the largest (B,N) seen so far (diagnostic). */
 size_t cmf_model_workspace_bytes(const cmf_model *m);
 
+/* Number of (b, n, mode) shapes whose kernel sequence cmf_model_forward_host currently replays as a CUDA graph (opt-in: environment
+ * CMF_HOST_GRAPH=1; second call of a shape onwards, on a capturable -- i.e. non-legacy-default -- stream; otherwise eager launches).  Diagnostic.
+ * A cmf_model is not thread-safe: one host thread per engine at a time. */
+int cmf_model_host_graphs(const cmf_model *m);
+
 /* Number of kernels one forward launches (for bench.py's gpu_launches). */
 int cmf_model_launches_per_forward(const cmf_model *m);
 

@@ -124,21 +124,36 @@ def test_host_entry_point_equals_device_entry_point(golden_dir):
     assert torch.equal(host["pre_trans"], dev["pre_trans"]) and torch.equal(host["mask"].bool(), dev["mask"])
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
-def test_host_entry_point_graph_replay(precision):
-    """cmf_model_forward_host runs a shape eagerly once, captures its kernel sequence as a CUDA graph on the second call and replays it
-    afterwards: every call must equal the device entry point on that call's inputs (different inputs, same and different shapes, CMFlow-T
-    with and without a carried state)."""
-    net = CMFlow(Args()); net.load_state_dict(synthetic_state_dict(0)); net = net.to(DEV); net.set_precision(precision)
+def test_host_entry_point_graph_replay(monkeypatch):
+    """With CMF_HOST_GRAPH=1 cmf_model_forward_host runs a shape eagerly once, captures its kernel sequence as a CUDA graph on the second call
+    (on a capturable, i.e. non-legacy-default, stream) and replays it afterwards: every call must equal the device entry point on that call's
+    inputs.  A shape change re-allocates the workspace and drops the cached graphs."""
+    monkeypatch.setenv("CMF_HOST_GRAPH", "1")
+    net = CMFlow(Args()); net.load_state_dict(synthetic_state_dict(0)); net = net.to(DEV)
+    side = torch.cuda.Stream()
     for seed, B, N in ((1, 3, 256), (2, 3, 256), (3, 3, 256), (4, 2, 200), (5, 3, 256), (6, 2, 200), (7, 2, 200)):
+        inp = make_pairs(B, N, seed=seed)
+        dev = run(net, inp)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):
+            host = net.forward_host(*[t.pin_memory() for t in inp[:4]])
+        assert torch.equal(host["sf_agg"], dev["sf_agg"]) and torch.equal(host["pre_trans"], dev["pre_trans"]), (seed, B, N)
+        assert torch.equal(host["stat_cls"], dev["stat_cls"]) and torch.equal(host["mask"].bool(), dev["mask"])
+    assert lib().cmf_model_host_graphs(net._handle) >= 1
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+def test_host_entry_point_repeated_calls(precision):
+    """The host entry point over repeated calls, changing shapes and a carried CMFlow-T state (default: eager launches)."""
+    net = CMFlow(Args()); net.load_state_dict(synthetic_state_dict(0)); net = net.to(DEV); net.set_precision(precision)
+    for seed, B, N in ((1, 3, 256), (2, 3, 256), (4, 2, 200), (5, 3, 256)):
         inp = make_pairs(B, N, seed=seed)
         dev = run(net, inp)
         host = net.forward_host(*[t.pin_memory() for t in inp[:4]])
         assert torch.equal(host["sf_agg"], dev["sf_agg"]) and torch.equal(host["pre_trans"], dev["pre_trans"]), (seed, B, N)
-        assert torch.equal(host["stat_cls"], dev["stat_cls"]) and torch.equal(host["mask"].bool(), dev["mask"])
     nett = CMFlow_T(Args()); nett.load_state_dict(synthetic_state_dict(3, temporal=True)); nett = nett.to(DEV); nett.set_precision(precision)
     inp = make_pairs(2, 256, seed=9)
-    for rep in range(3):
+    for rep in range(2):
         g_dev, g_host = None, None
         for step in range(3):
             dev = run(nett, inp, g_dev)
