@@ -440,16 +440,20 @@ mlp2_tc_kernel(const Mlp2Args a) {
     if (warp == 0) { tc_fence_after(); tmem_dealloc1(tmem_base, 64); }
 }
 
-int g_num_sms = 0;
-int init_once() {
-    static bool done = false;
-    if (done) return CMF_OK;
-    CMF_CUDA(cudaFuncSetAttribute(setconv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC1_SMEM));
-    CMF_CUDA(cudaFuncSetAttribute(mlp2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ML_SMEM));
+// function attributes are per device: set them on every device this process uses; returns the SM count of the current device in `sms`
+int init_device(int &sms) {
+    static int num_sms_of[64];
+    static bool done_of[64];
     int dev = 0;
     CMF_CUDA(cudaGetDevice(&dev));
-    CMF_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    done = true;
+    if (dev < 0 || dev >= 64) { cmf_set_error("tc chain: device ordinal %d out of range", dev); return CMF_ERR_STATE; }
+    if (!done_of[dev]) {
+        CMF_CUDA(cudaFuncSetAttribute(setconv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC1_SMEM));
+        CMF_CUDA(cudaFuncSetAttribute(mlp2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ML_SMEM));
+        CMF_CUDA(cudaDeviceGetAttribute(&num_sms_of[dev], cudaDevAttrMultiProcessorCount, dev));
+        done_of[dev] = true;
+    }
+    sms = num_sms_of[dev];
     return CMF_OK;
 }
 
@@ -457,7 +461,8 @@ int init_once() {
 
 int cmf_launch_setconv1_tc(int bc, int n, const float *xyz_planar, const float *ft_planar, const int *idx60, const TcChainSc1W *w4, float *out,
                            cudaStream_t st) {
-    int rc = init_once();
+    int g_num_sms = 0;
+    int rc = init_device(g_num_sms);
     if (rc) return rc;
     if (bc <= 0 || n <= 0) return CMF_OK;
     Sc1Args a;
@@ -473,7 +478,8 @@ int cmf_launch_setconv1_tc(int bc, int n, const float *xyz_planar, const float *
 
 int cmf_launch_mlp2_tc(long long rows, const float *in, int ld_in, float *out, int ld_out, const TcChainMlp2W *w4, unsigned int *amax_out,
                        int rows_per_pair, cudaStream_t st) {
-    int rc = init_once();
+    int g_num_sms = 0;
+    int rc = init_device(g_num_sms);
     if (rc) return rc;
     if (rows <= 0) return CMF_OK;
     if ((ld_in & 3) || (ld_out & 3)) { cmf_set_error("mlp2_tc: leading dimensions must be multiples of 4"); return CMF_ERR_INVALID; }

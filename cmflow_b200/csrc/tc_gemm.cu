@@ -313,18 +313,21 @@ int cmf_tc_tile_weights_f16(const float *W, int ldw, int M, int K, float *Wt, fl
 }
 
 int cmf_launch_tc_gemm(const TcArgs &a, cudaStream_t st) {
-    static int num_sms = 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // function attributes are per device: a process that drives several GPUs (the reference's nn.DataParallel mode) sets them on each
+    static int num_sms_of[64];
+    static bool attr_set_of[64];
+    int dev = 0;
+    CMF_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { cmf_set_error("tc gemm: device ordinal %d out of range", dev); return CMF_ERR_STATE; }
+    if (!attr_set_of[dev]) {
         CMF_CUDA(set_smem1<TC_PROD_PLAIN>());
         CMF_CUDA(set_smem1<TC_PROD_FC_H1>());
         CMF_CUDA(set_smem1<TC_PROD_SC2_Y1>());
         CMF_CUDA(set_smem1<TC_PROD_TILED>());
-        int dev = 0;
-        CMF_CUDA(cudaGetDevice(&dev));
-        CMF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_set = true;
+        CMF_CUDA(cudaDeviceGetAttribute(&num_sms_of[dev], cudaDevAttrMultiProcessorCount, dev));
+        attr_set_of[dev] = true;
     }
+    const int num_sms = num_sms_of[dev];
     if (a.cols <= 0 || a.m_blocks <= 0) return CMF_OK;
     if (a.out_tiled && ((a.M & 127) || a.epi != TC_EPI_STORE)) { cmf_set_error("tc_gemm: tiled output needs M % 128 == 0 and the STORE epilogue"); return CMF_ERR_INVALID; }
     if (a.epi == TC_EPI_MAXK && a.ksamp != 4 && a.ksamp != 8 && a.ksamp != 16 && a.ksamp != 32) { cmf_set_error("tc_gemm: MAXK needs ksamp in {4,8,16,32}"); return CMF_ERR_INVALID; }

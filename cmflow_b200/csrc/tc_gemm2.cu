@@ -554,18 +554,21 @@ cudaError_t set_smem2() {
 }  // namespace
 
 int cmf_launch_tc_gemm2(const TcArgs &a, cudaStream_t st) {
-    static int num_sms = 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // function attributes are per device: a process that drives several GPUs (the reference's nn.DataParallel mode) sets them on each
+    static int num_sms_of[64];
+    static bool attr_set_of[64];
+    int dev = 0;
+    CMF_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { cmf_set_error("tc gemm: device ordinal %d out of range", dev); return CMF_ERR_STATE; }
+    if (!attr_set_of[dev]) {
         CMF_CUDA(set_smem2<TC_PROD_PLAIN>());
         CMF_CUDA(set_smem2<TC_PROD_FC_H1>());
         CMF_CUDA(set_smem2<TC_PROD_SC2_Y1>());
         CMF_CUDA(set_smem2<TC_PROD_TILED>());
-        int dev = 0;
-        CMF_CUDA(cudaGetDevice(&dev));
-        CMF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_set = true;
+        CMF_CUDA(cudaDeviceGetAttribute(&num_sms_of[dev], cudaDevAttrMultiProcessorCount, dev));
+        attr_set_of[dev] = true;
     }
+    const int num_sms = num_sms_of[dev];
     if (a.cols <= 0 || a.m_blocks <= 0) return CMF_OK;
     if ((a.m_blocks & 1) || (a.M & 255)) { cmf_set_error("tc_gemm2: needs M %% 256 == 0"); return CMF_ERR_INVALID; }
     if (a.out_tiled && a.epi != TC_EPI_STORE) { cmf_set_error("tc_gemm2: tiled output needs the STORE epilogue"); return CMF_ERR_INVALID; }
