@@ -1,19 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- frame-pairs/s of the CMFlow forward hot path (BASELINE.json metric) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 256] [--points 256] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 256] [--points 256] [--model cmflow|cmflow_t|raflow]
+                    [--precision fp16x3|tf32x3|fp32] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 One "step" = one CMFlow.forward over a batch of synthetic radar frame pairs (BASELINE.json configs[1]:
 N=256 points, batch=256 per GPU; weak scaling: every rank runs its own 256 pairs, no data-path collective --
-SURVEY.md 8e).  Rank 0 prints ONE JSON line.
+SURVEY.md 8e).  Rank 0 prints ONE JSON line on stdout (everything else, e.g. NCCL's banner, goes to stderr).
+The other BASELINE.json configurations are reachable for the record (--model cmflow_t: a step is the three forwards
+of a clip batch; --points 4096 --batch 64: the dense cloud), but the bench line is configs[1].
 
   value  : device-resident throughput (inputs in HBM before the timed region), CUDA events, max over ranks
   e2e    : same metric through the public host-buffer call (cmf_model_forward_host): pinned H2D of the four
            input tensors + forward + D2H of the four outputs inside the timed region, every step
   roofline / kernels : per-kernel-category device time measured live with CUDA events on the launching stream
-           in a separate profiled pass of the same workload (event pairs around every launch)
+           in a separate profiled pass of the same workload (event pairs around every launch).  roofline = the
+           dominant kernel (set-conv #2 layer 2): algorithmic TFLOP/s against the measured cuBLAS bf16 rate
+           (`frac`), against that rate / 3 (`frac_of_ceiling`: the 3-MMA split), `traffic` = DRAM bytes per launch
+           from the committed ncu capture, and `hbm` = SURVEY 8d's algorithmic bytes over the launch time
   cpu_baseline : the oracle (CPU port of the reference's PyTorch path) on a bounded sample, rank 0, N=1 only
+  ref_cuda_baseline : informational -- the reference's own ball-query kernel (compiled unmodified) under the
+           PyTorch-eager unfused model on the same GPU (north_star's "reference's own lib/src CUDA build")
   --impl reference : the reference arm = that same CPU port timed with all host threads (the reference's
            Python cannot travel to the GPU box and ships no CPU kernels of its own -- SURVEY.md 8c)
 """
