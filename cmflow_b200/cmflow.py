@@ -4,10 +4,11 @@ key layout (models/cmflow.py:9-197, models/cmflow_t.py:10-211), running on the B
     net = CMFlow(args).cuda(); net.load_state_dict(torch.load("checkpoints/cmflow_cvpr/models/model.best.t7"))
     sf_agg, stat_cls, pre_trans, mask = net(pc1, pc2, feature1, feature2, None, 'test')
 
-Only the inference path is implemented (label_m=None or mode != 'train'); the training branch that feeds
-pseudo labels to the Kabsch head (cmflow.py:181-182) is out of scope and raises.  There is no CPU path.
+Inference only (BatchNorm running statistics, no autograd through the engine); mode='train' with label_m feeds the
+pseudo labels to the Kabsch head exactly as cmflow.py:181-182 does.  There is no CPU path.
 """
 import ctypes
+import warnings
 
 import numpy as np
 import torch
@@ -66,6 +67,38 @@ class _FlowDecoder(nn.Module):    # FlowDecoder (radarflow_util.py:321-337): par
         super().__init__()
         self.mse = _MultiScale(1027, (512, 256, 64), (64, 64, 64))
         self.fp = _Head(3)
+
+
+def _check_inputs(pc1, pc2, feature1, feature2, host=False):
+    """The engine reads raw pointers: every input must be (B,3,N) with ONE B and N (the engine has no N1 != N2 path), fp32, contiguous, and
+    all on the same side (device or host).  Returns the four tensors ready to pass."""
+    ins = []
+    for name, t in (("pc1", pc1), ("pc2", pc2), ("feature1", feature1), ("feature2", feature2)):
+        if not torch.is_tensor(t):
+            raise CmfError(f"{name} must be a tensor")
+        if t.is_cuda == host:
+            raise CmfError(f"{name}: " + ("forward_host takes host tensors" if host else "cmflow_b200 has no CPU path: inputs must be CUDA tensors"))
+        ins.append(t.float().contiguous())
+    shape = tuple(ins[0].shape)
+    if len(shape) != 3 or shape[1] != 3:
+        raise CmfError(f"pc1 must be (B,3,N), got {shape}")
+    for name, t in zip(("pc2", "feature1", "feature2"), ins[1:]):
+        if tuple(t.shape) != shape:
+            raise CmfError(f"{name} has shape {tuple(t.shape)}, expected {shape} like pc1 (one B and N for both clouds)")
+        if not host and t.device != ins[0].device:
+            raise CmfError(f"{name} is on {t.device}, pc1 on {ins[0].device}")
+    return ins
+
+
+def _check_gfeat(gfeat, B, host, device=None):
+    if gfeat is None:
+        return None
+    g = gfeat.float().contiguous()
+    if tuple(g.shape) != (B, 256):
+        raise CmfError(f"gfeat must be ({B},256), got {tuple(g.shape)}")
+    if g.is_cuda == host or (not host and g.device != device):
+        raise CmfError("gfeat must live where the inputs live")
+    return g
 
 
 class _EngineModel(nn.Module):
@@ -163,39 +196,59 @@ class _EngineModel(nn.Module):
         torch.cuda.synchronize()
         return torch.as_tensor(_Raw(), device="cuda").clone()
 
+    def _warn_training(self):
+        if self.training and not getattr(self, "_warned_training", False):
+            self._warned_training = True
+            warnings.warn("cmflow_b200 engines run inference only: BatchNorm uses its running statistics and no gradients flow, "
+                          "even after .train()", RuntimeWarning, stacklevel=3)
+
     def _run(self, pc1, pc2, feature1, feature2, label_m, mode, gfeat):
-        if mode == 'train' and label_m is not None:
-            raise NotImplementedError("cmflow_b200 implements the inference path only (label_m=None)")
-        ins = [t.float().contiguous() for t in (pc1, pc2, feature1, feature2)]
-        if not ins[0].is_cuda:
-            raise CmfError("cmflow_b200 has no CPU path: inputs must be CUDA tensors")
+        self._warn_training()
+        ins = _check_inputs(pc1, pc2, feature1, feature2)
         B, _, N = ins[0].shape
         dev = ins[0].device
         h = self._engine(dev)
         sf = torch.empty(B, 3, N, device=dev); cls = torch.empty(B, 1, N, device=dev)
         T = torch.empty(B, 4, 4, device=dev); mask = torch.empty(B, N, dtype=torch.uint8, device=dev)
         gout = torch.empty(B, 256, device=dev) if self._temporal else None
-        gprev = gfeat.float().contiguous() if (self._temporal and gfeat is not None) else None
+        gprev = _check_gfeat(gfeat, B, False, dev) if self._temporal else None
+        lab = None
+        if mode == 'train' and label_m is not None:
+            # models/cmflow.py:181-182 (cmflow_t.py:196-197): the pseudo motion labels replace the predicted scores in the ego-motion
+            # head and in the refinement mask; stat_cls (returned) stays the network's own
+            lab = label_m.to(dev).float().contiguous()
+            if lab.numel() != B * N:
+                raise CmfError(f"label_m must hold B*N = {B * N} values, got {tuple(label_m.shape)}")
         with torch.cuda.device(dev):
-            check(lib().cmf_model_forward(h, B, N, dptr(ins[0]), dptr(ins[1]), dptr(ins[2]), dptr(ins[3]), dptr(gprev),
-                                          dptr(sf), dptr(cls), dptr(T), dptr(mask), dptr(gout), stream_ptr()))
+            if lab is not None:
+                check(lib().cmf_model_forward_labelled(h, B, N, dptr(ins[0]), dptr(ins[1]), dptr(ins[2]), dptr(ins[3]), dptr(gprev), dptr(lab),
+                                                       dptr(sf), dptr(cls), dptr(T), dptr(mask), dptr(gout), stream_ptr()))
+            else:
+                check(lib().cmf_model_forward(h, B, N, dptr(ins[0]), dptr(ins[1]), dptr(ins[2]), dptr(ins[3]), dptr(gprev),
+                                              dptr(sf), dptr(cls), dptr(T), dptr(mask), dptr(gout), stream_ptr()))
         return sf, cls, T, mask.bool(), gout
 
     def forward_host(self, pc1, pc2, feature1, feature2, gfeat=None, out=None):
         """End-to-end call on HOST tensors (pinned for full speed): H2D, forward, D2H, synchronise
         (cmf_model_forward_host).  Returns CPU tensors; pass `out` (dict of pinned tensors) to reuse buffers."""
-        ins = [t.float().contiguous() for t in (pc1, pc2, feature1, feature2)]
-        if ins[0].is_cuda:
-            raise CmfError("forward_host takes host tensors")
+        self._warn_training()
+        ins = _check_inputs(pc1, pc2, feature1, feature2, host=True)
         B, _, N = ins[0].shape
         dev = torch.device("cuda", torch.cuda.current_device())
         h = self._engine(dev)
+        want = {"sf_agg": ((B, 3, N), torch.float32), "stat_cls": ((B, 1, N), torch.float32), "pre_trans": ((B, 4, 4), torch.float32),
+                "mask": ((B, N), torch.uint8), "gfeat": ((B, 256), torch.float32)}
+        if out is not None:
+            for k, (shp, dt) in want.items():
+                t = out.get(k)
+                if t is None or t.is_cuda or tuple(t.shape) != shp or t.dtype != dt or not t.is_contiguous():
+                    raise CmfError(f"out[{k!r}] must be a contiguous host tensor of shape {shp}, dtype {dt}")
         if out is None:
             out = {"sf_agg": torch.empty(B, 3, N).pin_memory(), "stat_cls": torch.empty(B, 1, N).pin_memory(),
                    "pre_trans": torch.empty(B, 4, 4).pin_memory(), "mask": torch.empty(B, N, dtype=torch.uint8).pin_memory(),
                    "gfeat": torch.empty(B, 256).pin_memory()}
         hp = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
-        gprev = gfeat.float().contiguous() if (self._temporal and gfeat is not None) else None
+        gprev = _check_gfeat(gfeat, B, True) if self._temporal else None
         check(lib().cmf_model_forward_host(h, B, N, hp(ins[0]), hp(ins[1]), hp(ins[2]), hp(ins[3]), hp(gprev),
                                            hp(out["sf_agg"]), hp(out["stat_cls"]), hp(out["pre_trans"]), hp(out["mask"]),
                                            hp(out["gfeat"]), stream_ptr()))
@@ -224,9 +277,8 @@ class RaFlow(_EngineModel):
     _raflow = True
 
     def forward(self, pc1, pc2, feature1, feature2, interval):
-        ins = [t.float().contiguous() for t in (pc1, pc2, feature1, feature2)]
-        if not ins[0].is_cuda:
-            raise CmfError("cmflow_b200 has no CPU path: inputs must be CUDA tensors")
+        self._warn_training()
+        ins = _check_inputs(pc1, pc2, feature1, feature2)
         B, _, N = ins[0].shape
         dev = ins[0].device
         dt = interval.to(dev).float().contiguous().view(-1)

@@ -128,6 +128,7 @@ void carve(Arena &a, Work &w, int bc, int n) {
 }  // namespace
 
 struct cmf_model {
+    int device = 0;              // ordinal the engine was created on: every entry point switches to it (and back) for its own duration
     int temporal = 0;
     float stat_thres = 0.5f;
     float *d_blob = nullptr;
@@ -141,7 +142,7 @@ struct cmf_model {
     int last_b = 0, last_n = 0;
     // host entry point: the kernel sequence of one (b, n, mode) forward between the staging buffers, captured once as a CUDA graph
     // (39 launches -> 1 cudaGraphLaunch: the host path synchronises every call, so launch latency is not hidden behind the GPU there)
-    struct HostGraph { int b, n, mode, has_g; cudaGraphExec_t exec; };
+    struct HostGraph { int b, n, mode, has_g; cudaGraphExec_t exec; bool failed; };
     std::vector<HostGraph> graphs;
     // tensor-core (tcgen05, 3xTF32) mode: pre-tiled hi/lo copies of the big weight matrices
     int tc = 0;
@@ -163,6 +164,16 @@ struct cmf_model {
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> pool; size_t pool_used = 0;
     double work[16] = {0}; int nlaunch[16] = {0}; float ms[16] = {0};
+};
+
+// Every allocation, weight-tiling kernel and launch of an engine belongs to the device it was created on.  A caller that holds the
+// model on cuda:1 while cuda:0 is current (single-process multi-GPU) must not have them land on the wrong GPU.
+struct DeviceScope {
+    int prev = -1; bool switched = false;
+    explicit DeviceScope(const cmf_model *m) {
+        if (m && cudaGetDevice(&prev) == cudaSuccess && prev != m->device) switched = cudaSetDevice(m->device) == cudaSuccess;
+    }
+    ~DeviceScope() { if (switched) cudaSetDevice(prev); }
 };
 
 static void drop_graphs(cmf_model *m) {
@@ -395,7 +406,8 @@ static int run_mse_layer(cmf_model *m, int bc, int n, const float *pc, const flo
 
 static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const float *pc2, const float *ft1,
                          const float *ft2, const float *gprev, float *sf_agg, float *stat_cls, float *pre_trans,
-                         uint8_t *mask, float *gfeat_out, cudaStream_t st, const float *interval = nullptr, float *raw_flow = nullptr) {
+                         uint8_t *mask, float *gfeat_out, cudaStream_t st, const float *interval = nullptr, float *raw_flow = nullptr,
+                         const float *label_m = nullptr) {
     Work &w = m->w;
     const long long bn = (long long)bc * n;
     auto S = [&](int i) { return m->seg[i]; };
@@ -582,7 +594,8 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
     }
     RUN(C_HEAD_KABSCH, 0, cmf_launch_head_final(bc, n, w.HD3, 128, S(HD_W4), S(HD_W4) + 192, w.FLOW, stat_cls, st));
     // ego-motion head + refinement (cmflow.py:96-125); CMFlow-T omits the +1e-4 (cmflow_t.py:119)
-    RUN(C_HEAD_KABSCH, 0, cmf_launch_kabsch(bc, n, pc1, w.FLOW, 1, stat_cls, 1, m->temporal ? 0.f : 1e-4f, m->stat_thres, pre_trans, sf_agg, mask, st));
+    // mode='train' with pseudo labels (cmflow.py:181-182): the labels take the scores' place in the weights AND in the refinement mask
+    RUN(C_HEAD_KABSCH, 0, cmf_launch_kabsch(bc, n, pc1, w.FLOW, 1, label_m ? label_m : stat_cls, 1, m->temporal ? 0.f : 1e-4f, m->stat_thres, pre_trans, sf_agg, mask, st));
     return CMF_OK;
 }
 
@@ -602,6 +615,7 @@ extern "C" int cmf_model_create(cmf_model **out, const float *blob, size_t blob_
     CMF_REQUIRE(hdr[0] == MAGIC, "bad blob magic");
     CMF_REQUIRE(hdr[1] == (int)exp.size() && hdr[2] == (temporal ? 1 : 0), "blob segment count / model kind mismatch");
     cmf_model *m = new cmf_model();
+    CMF_CUDA(cudaGetDevice(&m->device));
     m->temporal = temporal ? 1 : 0;
     m->stat_thres = stat_thres;
     cudaError_t e = cudaMalloc(&m->d_blob, blob_floats * sizeof(float));
@@ -650,6 +664,7 @@ extern "C" int cmf_model_create(cmf_model **out, const float *blob, size_t blob_
 
 extern "C" void cmf_model_destroy(cmf_model *m) {
     if (!m) return;
+    DeviceScope dev_(m);
     drop_graphs(m);
     if (m->ws) cudaFree(m->ws);
     if (m->d_blob) cudaFree(m->d_blob);
@@ -668,10 +683,11 @@ extern "C" int cmf_model_host_graphs(const cmf_model *m) {
 }
 extern "C" int cmf_model_launches_per_forward(const cmf_model *m) { return m ? m->launches : 0; }
 
-extern "C" int cmf_model_forward(cmf_model *m, int b, int n, const float *pc1, const float *pc2, const float *ft1,
-                                 const float *ft2, const float *gfeat_prev, float *sf_agg, float *stat_cls,
-                                 float *pre_trans, uint8_t *mask, float *gfeat_out, void *stream) {
+static int forward_impl(cmf_model *m, int b, int n, const float *pc1, const float *pc2, const float *ft1,
+                        const float *ft2, const float *gfeat_prev, const float *label_m, float *sf_agg, float *stat_cls,
+                        float *pre_trans, uint8_t *mask, float *gfeat_out, void *stream) {
     CMF_REQUIRE(m, "null model");
+    DeviceScope dev_(m);
     CMF_REQUIRE(b >= 0 && n >= 0, "negative size");
     if (b == 0) return CMF_OK;
     CMF_REQUIRE(n >= 8, "need at least 8 points per cloud (knn_point(8, ...): torch.topk raises below that)");
@@ -692,10 +708,24 @@ extern "C" int cmf_model_forward(cmf_model *m, int b, int n, const float *pc1, c
         rc = forward_chunk(m, bc, n, pc1 + b0 * pn, pc2 + b0 * pn, ft1 + b0 * pn, ft2 + b0 * pn,
                            gfeat_prev ? gfeat_prev + (size_t)b0 * 256 : nullptr,
                            sf_agg + b0 * pn, stat_cls + (size_t)b0 * n, pre_trans + (size_t)b0 * 16, mask + (size_t)b0 * n,
-                           gfeat_out ? gfeat_out + (size_t)b0 * 256 : nullptr, st);
+                           gfeat_out ? gfeat_out + (size_t)b0 * 256 : nullptr, st, nullptr, nullptr,
+                           label_m ? label_m + (size_t)b0 * n : nullptr);
         if (rc != CMF_OK) return rc;
     }
     return CMF_OK;
+}
+
+extern "C" int cmf_model_forward(cmf_model *m, int b, int n, const float *pc1, const float *pc2, const float *ft1,
+                                 const float *ft2, const float *gfeat_prev, float *sf_agg, float *stat_cls,
+                                 float *pre_trans, uint8_t *mask, float *gfeat_out, void *stream) {
+    return forward_impl(m, b, n, pc1, pc2, ft1, ft2, gfeat_prev, nullptr, sf_agg, stat_cls, pre_trans, mask, gfeat_out, stream);
+}
+
+extern "C" int cmf_model_forward_labelled(cmf_model *m, int b, int n, const float *pc1, const float *pc2, const float *ft1,
+                                          const float *ft2, const float *gfeat_prev, const float *label_m, float *sf_agg, float *stat_cls,
+                                          float *pre_trans, uint8_t *mask, float *gfeat_out, void *stream) {
+    CMF_REQUIRE(label_m, "null label_m (use cmf_model_forward)");
+    return forward_impl(m, b, n, pc1, pc2, ft1, ft2, gfeat_prev, label_m, sf_agg, stat_cls, pre_trans, mask, gfeat_out, stream);
 }
 
 extern "C" int cmf_model_set_raflow(cmf_model *m, float rigid_thres, float rigid_pcs) {
@@ -708,6 +738,7 @@ extern "C" int cmf_model_set_raflow(cmf_model *m, float rigid_thres, float rigid
 extern "C" int cmf_model_forward_raflow(cmf_model *m, int b, int n, const float *pc1, const float *pc2, const float *ft1, const float *ft2,
                                         const float *interval, float *output, float *sf_agg, float *pre_trans, uint8_t *mask_s, void *stream) {
     CMF_REQUIRE(m, "null model");
+    DeviceScope dev_(m);
     CMF_REQUIRE(m->raflow, "call cmf_model_set_raflow first");
     CMF_REQUIRE(b >= 0 && n >= 0, "negative size");
     if (b == 0) return CMF_OK;
@@ -735,6 +766,7 @@ extern "C" int cmf_model_forward_host(cmf_model *m, int b, int n, const float *p
                                       const float *ft2, const float *gfeat_prev, float *sf_agg, float *stat_cls,
                                       float *pre_trans, uint8_t *mask, float *gfeat_out, void *stream) {
     CMF_REQUIRE(m, "null model");
+    DeviceScope dev_(m);
     CMF_REQUIRE(b >= 0 && n >= 0, "negative size");
     if (b == 0) return CMF_OK;
     CMF_REQUIRE(pc1 && pc2 && ft1 && ft2 && sf_agg && stat_cls && pre_trans && mask, "null pointer");
@@ -782,10 +814,10 @@ extern "C" int cmf_model_forward_host(cmf_model *m, int b, int n, const float *p
                     if (m->graphs.front().exec) cudaGraphExecDestroy(m->graphs.front().exec);
                     m->graphs.erase(m->graphs.begin());
                 }
-                m->graphs.push_back({b, n, m->tc, has_g, nullptr});
+                m->graphs.push_back({b, n, m->tc, has_g, nullptr, false});
             }
         } else {
-            if (!hg->exec) {
+            if (!hg->exec && !hg->failed) {
                 cudaGraph_t graph = nullptr;
                 const int launches = m->launches;
                 if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
@@ -797,7 +829,7 @@ extern "C" int cmf_model_forward_host(cmf_model *m, int b, int n, const float *p
                     if (graph) cudaGraphDestroy(graph);
                     if (rc != CMF_OK) return rc;
                 }
-                if (!hg->exec) { cudaGetLastError(); hg->b = -1; m->launches = launches; }       // capture unavailable: this shape stays eager
+                if (!hg->exec) { cudaGetLastError(); hg->failed = true; m->launches = launches; }  // capture unavailable: the entry keeps its key and routes this shape to the eager path from now on
             }
             if (hg->exec) CMF_CUDA(cudaGraphLaunch(hg->exec, st));
             else rc = cmf_model_forward(m, b, n, d_pc1, d_pc2, d_ft1, d_ft2, gfeat_prev ? d_g : nullptr, d_sf, d_cls, d_tr, d_mask, d_go, st);
@@ -815,6 +847,7 @@ extern "C" int cmf_model_forward_host(cmf_model *m, int b, int n, const float *p
 
 extern "C" int cmf_model_set_mode(cmf_model *m, int mode) {
     CMF_REQUIRE(m, "null model");
+    DeviceScope dev_(m);
     CMF_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (strict fp32 FMA), 1 (tcgen05 3xTF32) or 2 (tcgen05 3xFP16)");
     if (mode) { int rc = ensure_tc_weights(m, mode - 1); if (rc) return rc; }
     m->tc = mode;
@@ -832,6 +865,7 @@ extern "C" const char *cmf_model_profile_name(int cat) { return (cat >= 0 && cat
 
 extern "C" int cmf_model_read_profile(cmf_model *m, float *ms, int *launches, double *work) {
     CMF_REQUIRE(m && ms && launches && work, "null pointer");
+    DeviceScope dev_(m);
     for (int i = 0; i < C_COUNT; ++i) { ms[i] = 0.f; launches[i] = m->nlaunch[i]; work[i] = m->work[i]; }
     for (const auto &r : m->prof) {
         CMF_CUDA(cudaEventSynchronize(r.e1));

@@ -13,7 +13,21 @@
 namespace tcdev {
 
 constexpr int BM = 128, BN = 256, SK = 16, PK = 32;
-constexpr unsigned SPIN_LIMIT = 2000u;          // x 1 ms suspend hint = 2 s before a stuck wait traps
+// Watchdog of the mbarrier waits: a wait that has not completed WATCHDOG_NS of wall-clock (%globaltimer) after it began traps, so that a
+// protocol bug fails the launch instead of hanging the GPU.  NOTE: a trap poisons the CUDA context (sticky error for every later call of
+// the process), so the budget is generous -- time-slicing, MPS, compute-sanitizer or a debugger can stretch a legitimate wait a lot.
+// Compile with -DCMF_NO_WATCHDOG to remove it.
+constexpr unsigned long long WATCHDOG_NS = 30ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void watchdog(unsigned &spins, unsigned long long &t0) {
+#ifndef CMF_NO_WATCHDOG
+    if ((++spins & 63u) == 0u) {                 // the suspend-time hint bounds a try_wait from above only: look at the clock every 64 wake-ups
+        const unsigned long long now = global_ns();
+        if (t0 == 0ull) t0 = now;
+        else if (now - t0 > WATCHDOG_NS) __trap();
+    }
+#endif
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -39,21 +53,21 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    unsigned spins = 0;
+    unsigned spins = 0; unsigned long long t0 = 0ull;
     while (!done) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
-        if (!done && ++spins > SPIN_LIMIT) __trap();        // never hang the GPU: fail the launch instead
+        if (!done) watchdog(spins, t0);                     // never hang the GPU: fail the launch instead
     }
 }
 // same, acquiring at cluster scope (the arrive came from the peer CTA)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    unsigned spins = 0;
+    unsigned spins = 0; unsigned long long t0 = 0ull;
     while (!done) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
-        if (!done && ++spins > SPIN_LIMIT) __trap();
+        if (!done) watchdog(spins, t0);
     }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {

@@ -129,7 +129,8 @@ typedef struct cmf_model cmf_model;
  * cmflow_b200/weights.py (BatchNorm folded into conv scale/bias in float64 on the host). */
 size_t cmf_model_blob_floats(int temporal);
 
-/* Create an engine on the current device.  `blob` is a HOST pointer to cmf_model_blob_floats() floats;
+/* Create an engine on the current device (every later call on the engine switches to that device for its own duration and
+ * restores the caller's).  `blob` is a HOST pointer to cmf_model_blob_floats() floats;
  * it is copied to the device.  stat_thres as models/cmflow.py:18. */
 int cmf_model_create(cmf_model **out, const float *blob, size_t blob_floats, int temporal, float stat_thres);
 void cmf_model_destroy(cmf_model *m);
@@ -168,6 +169,15 @@ int cmf_model_forward(cmf_model *m, int b, int n,
                       const float *gfeat_prev,
                       float *sf_agg, float *stat_cls, float *pre_trans, uint8_t *mask, float *gfeat_out,
                       void *stream);
+
+/* mode='train' with pseudo motion labels (models/cmflow.py:181-182, cmflow_t.py:196-197): label_m (B,N) device floats replace the
+ * predicted scores in the ego-motion head's weights and in the refinement mask (cmflow.py:188); stat_cls still returns the
+ * network's own scores.  Inference arithmetic otherwise (BatchNorm running statistics; no gradients). */
+int cmf_model_forward_labelled(cmf_model *m, int b, int n,
+                               const float *pc1, const float *pc2, const float *ft1, const float *ft2,
+                               const float *gfeat_prev, const float *label_m,
+                               float *sf_agg, float *stat_cls, float *pre_trans, uint8_t *mask, float *gfeat_out,
+                               void *stream);
 
 /* Same with HOST buffers (pinned for full speed): copies inputs H2D, runs the forward, copies the four
  * outputs D2H and synchronises `stream`.  This is the end-to-end call bench.py times as `e2e`. */
