@@ -41,7 +41,11 @@ SIGNATURES = {
     "cmf_model_launches_per_forward": [_vp],
     "cmf_model_forward": [_vp, _i, _i] + [_vp] * 11,
     "cmf_model_forward_host": [_vp, _i, _i] + [_vp] * 11,
-    "cmf_model_forward_labelled": [_vp, _i, _i] + [_vp] * 12,
+    "cmf_model_forward2": [_vp, _i, _i, _i] + [_vp] * 12,
+    "cmf_model_forward_raflow2": [_vp, _i, _i, _i] + [_vp] * 10,
+    "cmf_model_forward_host2": [_vp, _i, _i, _i] + [_vp] * 11,
+    "cmf_model_submit_host": [_vp, _i, _i, _i, _i] + [_vp] * 11,
+    "cmf_model_wait_host": [_vp, _i],
     "cmf_model_tap": [_vp, ctypes.c_char_p],
     "cmf_eval_scene_flow_sums": [_i, _i, _vp, _vp, _vp, _vp, ctypes.c_double, ctypes.c_double, ctypes.c_double, _vp, _vp],
     "cmf_eval_motion_seg_counts": [ctypes.c_longlong, _vp, _vp, _vp, _vp],

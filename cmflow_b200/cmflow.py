@@ -70,8 +70,9 @@ class _FlowDecoder(nn.Module):    # FlowDecoder (radarflow_util.py:321-337): par
 
 
 def _check_inputs(pc1, pc2, feature1, feature2, host=False):
-    """The engine reads raw pointers: every input must be (B,3,N) with ONE B and N (the engine has no N1 != N2 path), fp32, contiguous, and
-    all on the same side (device or host).  Returns the four tensors ready to pass."""
+    """The engine reads raw pointers: pc1 / feature1 must be (B,3,N1) and pc2 / feature2 (B,3,N2) with one B (N1 != N2 is fine: the
+    reference's evaluation loop feeds un-resampled clouds, dataset/vod.py:92-93), fp32, contiguous, all on the same side (device or host).
+    Returns the four tensors ready to pass."""
     ins = []
     for name, t in (("pc1", pc1), ("pc2", pc2), ("feature1", feature1), ("feature2", feature2)):
         if not torch.is_tensor(t):
@@ -79,14 +80,19 @@ def _check_inputs(pc1, pc2, feature1, feature2, host=False):
         if t.is_cuda == host:
             raise CmfError(f"{name}: " + ("forward_host takes host tensors" if host else "cmflow_b200 has no CPU path: inputs must be CUDA tensors"))
         ins.append(t.float().contiguous())
-    shape = tuple(ins[0].shape)
-    if len(shape) != 3 or shape[1] != 3:
-        raise CmfError(f"pc1 must be (B,3,N), got {shape}")
-    for name, t in zip(("pc2", "feature1", "feature2"), ins[1:]):
-        if tuple(t.shape) != shape:
-            raise CmfError(f"{name} has shape {tuple(t.shape)}, expected {shape} like pc1 (one B and N for both clouds)")
-        if not host and t.device != ins[0].device:
-            raise CmfError(f"{name} is on {t.device}, pc1 on {ins[0].device}")
+    s1, s2 = tuple(ins[0].shape), tuple(ins[1].shape)
+    if len(s1) != 3 or s1[1] != 3:
+        raise CmfError(f"pc1 must be (B,3,N), got {s1}")
+    if len(s2) != 3 or s2[1] != 3 or s2[0] != s1[0]:
+        raise CmfError(f"pc2 must be ({s1[0]},3,N2), got {s2}")
+    if tuple(ins[2].shape) != s1:
+        raise CmfError(f"feature1 has shape {tuple(ins[2].shape)}, expected {s1} like pc1")
+    if tuple(ins[3].shape) != s2:
+        raise CmfError(f"feature2 has shape {tuple(ins[3].shape)}, expected {s2} like pc2")
+    if not host:
+        for name, t in zip(("pc2", "feature1", "feature2"), ins[1:]):
+            if t.device != ins[0].device:
+                raise CmfError(f"{name} is on {t.device}, pc1 on {ins[0].device}")
     return ins
 
 
@@ -220,17 +226,11 @@ class _EngineModel(nn.Module):
             if lab.numel() != B * N:
                 raise CmfError(f"label_m must hold B*N = {B * N} values, got {tuple(label_m.shape)}")
         with torch.cuda.device(dev):
-            if lab is not None:
-                check(lib().cmf_model_forward_labelled(h, B, N, dptr(ins[0]), dptr(ins[1]), dptr(ins[2]), dptr(ins[3]), dptr(gprev), dptr(lab),
-                                                       dptr(sf), dptr(cls), dptr(T), dptr(mask), dptr(gout), stream_ptr()))
-            else:
-                check(lib().cmf_model_forward(h, B, N, dptr(ins[0]), dptr(ins[1]), dptr(ins[2]), dptr(ins[3]), dptr(gprev),
-                                              dptr(sf), dptr(cls), dptr(T), dptr(mask), dptr(gout), stream_ptr()))
+            check(lib().cmf_model_forward2(h, B, N, ins[1].shape[2], dptr(ins[0]), dptr(ins[1]), dptr(ins[2]), dptr(ins[3]), dptr(gprev), dptr(lab),
+                                           dptr(sf), dptr(cls), dptr(T), dptr(mask), dptr(gout), stream_ptr()))
         return sf, cls, T, mask.bool(), gout
 
-    def forward_host(self, pc1, pc2, feature1, feature2, gfeat=None, out=None):
-        """End-to-end call on HOST tensors (pinned for full speed): H2D, forward, D2H, synchronise
-        (cmf_model_forward_host).  Returns CPU tensors; pass `out` (dict of pinned tensors) to reuse buffers."""
+    def _host_args(self, pc1, pc2, feature1, feature2, gfeat, out):
         self._warn_training()
         ins = _check_inputs(pc1, pc2, feature1, feature2, host=True)
         B, _, N = ins[0].shape
@@ -238,21 +238,39 @@ class _EngineModel(nn.Module):
         h = self._engine(dev)
         want = {"sf_agg": ((B, 3, N), torch.float32), "stat_cls": ((B, 1, N), torch.float32), "pre_trans": ((B, 4, 4), torch.float32),
                 "mask": ((B, N), torch.uint8), "gfeat": ((B, 256), torch.float32)}
-        if out is not None:
+        if out is None:
+            out = {k: torch.empty(shp, dtype=dt).pin_memory() for k, (shp, dt) in want.items()}
+        else:
             for k, (shp, dt) in want.items():
                 t = out.get(k)
                 if t is None or t.is_cuda or tuple(t.shape) != shp or t.dtype != dt or not t.is_contiguous():
                     raise CmfError(f"out[{k!r}] must be a contiguous host tensor of shape {shp}, dtype {dt}")
-        if out is None:
-            out = {"sf_agg": torch.empty(B, 3, N).pin_memory(), "stat_cls": torch.empty(B, 1, N).pin_memory(),
-                   "pre_trans": torch.empty(B, 4, 4).pin_memory(), "mask": torch.empty(B, N, dtype=torch.uint8).pin_memory(),
-                   "gfeat": torch.empty(B, 256).pin_memory()}
         hp = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
         gprev = _check_gfeat(gfeat, B, True) if self._temporal else None
-        check(lib().cmf_model_forward_host(h, B, N, hp(ins[0]), hp(ins[1]), hp(ins[2]), hp(ins[3]), hp(gprev),
-                                           hp(out["sf_agg"]), hp(out["stat_cls"]), hp(out["pre_trans"]), hp(out["mask"]),
-                                           hp(out["gfeat"]), stream_ptr()))
+        args = (B, N, ins[1].shape[2], hp(ins[0]), hp(ins[1]), hp(ins[2]), hp(ins[3]), hp(gprev),
+                hp(out["sf_agg"]), hp(out["stat_cls"]), hp(out["pre_trans"]), hp(out["mask"]), hp(out["gfeat"]), stream_ptr())
+        return h, args, out, (ins, gprev)
+
+    def forward_host(self, pc1, pc2, feature1, feature2, gfeat=None, out=None):
+        """End-to-end call on HOST tensors (pinned for full speed): H2D, forward, D2H, synchronise
+        (cmf_model_forward_host2).  Returns CPU tensors; pass `out` (dict of pinned tensors) to reuse buffers."""
+        h, args, out, _keep = self._host_args(pc1, pc2, feature1, feature2, gfeat, out)
+        check(lib().cmf_model_forward_host2(h, *args))
         return out
+
+    def submit_host(self, slot, pc1, pc2, feature1, feature2, gfeat=None, out=None):
+        """Pipelined form of forward_host (cmf_model_submit_host): enqueue upload, kernels and download of one call on staging slot 0 or 1
+        and return at once; wait_host(slot) blocks until `out` is filled.  Alternating the two slots overlaps the copies of neighbouring
+        calls with the kernels.  Inputs and `out` must be pinned and stay untouched until the wait."""
+        h, args, out, keep = self._host_args(pc1, pc2, feature1, feature2, gfeat, out)
+        check(lib().cmf_model_submit_host(h, int(slot), *args))
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[int(slot)] = keep                  # the host input tensors must outlive the asynchronous copies
+        return out
+
+    def wait_host(self, slot):
+        check(lib().cmf_model_wait_host(self._handle, int(slot)))
+        getattr(self, "_inflight", {}).pop(int(slot), None)
 
 
 class CMFlow(_EngineModel):
@@ -288,6 +306,6 @@ class RaFlow(_EngineModel):
         out = torch.empty(B, 3, N, device=dev); sf = torch.empty(B, 3, N, device=dev)
         T = torch.empty(B, 4, 4, device=dev); mask = torch.empty(B, N, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            check(lib().cmf_model_forward_raflow(h, B, N, dptr(ins[0]), dptr(ins[1]), dptr(ins[2]), dptr(ins[3]), dptr(dt),
+            check(lib().cmf_model_forward_raflow2(h, B, N, ins[1].shape[2], dptr(ins[0]), dptr(ins[1]), dptr(ins[2]), dptr(ins[3]), dptr(dt),
                                                  dptr(out), dptr(sf), dptr(T), dptr(mask), stream_ptr()))
         return out, sf, T, mask.bool()

@@ -100,22 +100,33 @@ struct Work {
 enum { AM_F1 = 0, AM_F2, AM_E, AM_PROP, AM_U1, AM_U2, AM_DIR, AM_HD1, AM_COR, AM_FT, AM_P0, AM_COUNT = AM_P0 + 4 };
 enum { SC_H2 = 0, SC_Y2, SC_COUNT = SC_Y2 + 4 };
 
-void carve(Arena &a, Work &w, int bc, int n) {
+// What a mode does not touch is not allocated: the strict-fp32 pipeline materialises the gathered layer-1 tensors (Y1: 4.3 GB at 256 pairs of
+// 256 points) that the tensor-core pipelines build inside their GEMM producers, and the unfused set-conv #1 scratch exists only for its A/B switch.
+struct CarveOpts { int mode; bool unfused_sc1, need_h1; };
+void carve(Arena &a, Work &w, int bc, int n, const CarveOpts &o) {
     const size_t bn = (size_t)bc * n;
+    const bool tc = o.mode != 0;
+    w = Work{};
     w.X1T = a.take<float>(bn * 3); w.X2T = a.take<float>(bn * 3);
     w.BQ1 = a.take<int>(bn * 60); w.BQ2 = a.take<int>(bn * 60);
     w.KNN12 = a.take<int>(bn * 8); w.KNN11 = a.take<int>(bn * 8);
     w.E = a.take<float>(bn * E_LD); w.F2 = a.take<float>(bn * 256);
     w.G1 = a.take<float>((size_t)bc * 256); w.G2 = a.take<float>((size_t)bc * 256);
-    w.X0 = a.take<float>(bn * 60 * 8); w.T32a = a.take<float>(bn * 60 * 32); w.T32b = a.take<float>(bn * 60 * 32);
-    w.T64 = a.take<float>(bn * 60 * 64);
+    if (o.unfused_sc1) {
+        w.X0 = a.take<float>(bn * 60 * 8); w.T32a = a.take<float>(bn * 60 * 32); w.T32b = a.take<float>(bn * 60 * 32);
+        w.T64 = a.take<float>(bn * 60 * 64);
+    }
     w.M64 = a.take<float>(bn * 256); w.Q1 = a.take<float>(bn * 256); w.Q2 = a.take<float>(bn * 256);
     w.PB1 = a.take<float>((size_t)bc * 512); w.PB2 = a.take<float>((size_t)bc * 512);
     w.U1 = a.take<float>(bn * 512); w.U2 = a.take<float>(bn * 512);
-    w.H1 = a.take<float>(bn * 8 * 512); w.H2 = a.take<float>(cmf_tc_act_tiled_floats((long long)bn * 8, 512));   // H2: row-major (fp32 mode) or tiled hi/lo (tc mode)
+    if (o.need_h1) w.H1 = a.take<float>(bn * 8 * 512);
+    // H2 / Y2: row-major fp32 (strict mode) or tiled hi/lo: 3xTF32 tiles hold two floats per element, 3xFP16 tiles two halfs
+    const size_t h2_tiled = cmf_tc_act_tiled_floats((long long)bn * 8, 512), y2_tiled = cmf_tc_act_tiled_floats((long long)bn * 32, 256);
+    w.H2 = a.take<float>(o.mode == 1 ? h2_tiled : (o.mode == 2 ? h2_tiled / 2 : bn * 8 * 512));
     w.COST1 = a.take<float>(bn * 512);
     w.PBM = a.take<float>((size_t)bc * 2048); w.P = a.take<float>(bn * 2048);
-    w.Y1 = a.take<float>(bn * 32 * 512); w.Y2 = a.take<float>(cmf_tc_act_tiled_floats((long long)bn * 32, 256)); w.Y3 = a.take<float>(bn * 32 * 64);
+    if (!tc) { w.Y1 = a.take<float>(bn * 32 * 512); w.Y3 = a.take<float>(bn * 32 * 64); }
+    w.Y2 = a.take<float>(o.mode == 1 ? y2_tiled : (o.mode == 2 ? y2_tiled / 2 : bn * 32 * 256));
     w.PROP = a.take<float>(bn * 256); w.GP = a.take<float>((size_t)bc * 256);
     w.GI = a.take<float>((size_t)bc * 768); w.GH = a.take<float>((size_t)bc * 768);
     w.GNEW = a.take<float>((size_t)bc * 256); w.ZERO = a.take<float>((size_t)bc * 256);
@@ -134,15 +145,17 @@ struct cmf_model {
     float *d_blob = nullptr;
     std::vector<const float *> seg;
     std::vector<SegShape> shape;
-    char *ws = nullptr; size_t ws_bytes = 0; int cap_bc = 0, cap_n = 0;
+    char *ws = nullptr; size_t ws_bytes = 0; int cap_bc = 0, cap_n = 0, ws_mode = 0;     // arena carved for cap_bc pairs x cap_n points in arithmetic mode ws_mode
     Work w{};
-    // staging for the host entry point
-    float *d_in = nullptr, *d_out = nullptr; size_t d_in_floats = 0, d_out_bytes = 0;
+    // staging for the host entry points: two slots so that copies of neighbouring calls overlap the kernels (cmf_model_submit_host)
+    struct HostSlot { float *d_in = nullptr; char *d_out = nullptr; size_t in_floats = 0, out_bytes = 0;
+                      cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr; bool busy = false; } slots[2];
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     int launches = 0;
     int last_b = 0, last_n = 0;
     // host entry point: the kernel sequence of one (b, n, mode) forward between the staging buffers, captured once as a CUDA graph
     // (39 launches -> 1 cudaGraphLaunch: the host path synchronises every call, so launch latency is not hidden behind the GPU there)
-    struct HostGraph { int b, n, mode, has_g; cudaGraphExec_t exec; bool failed; };
+    struct HostGraph { int slot, b, n, n2, mode, has_g; cudaGraphExec_t exec; bool failed; };
     std::vector<HostGraph> graphs;
     // tensor-core (tcgen05, 3xTF32) mode: pre-tiled hi/lo copies of the big weight matrices
     int tc = 0;
@@ -295,9 +308,14 @@ static int ensure_tc_weights(cmf_model *m, int fmt) {
     return CMF_OK;
 }
 
-static size_t chunk_bytes(int bc, int n) {
+static bool wsum_fused(const cmf_model *m) { return m->tc && cmf_tc_pair_enabled() && !getenv("CMF_NO_WSUM"); }
+static CarveOpts carve_opts(const cmf_model *m) {
+    const bool chain = m->tc == 2 && m->chain;
+    return CarveOpts{m->tc, !chain && !m->fused_sc1, !wsum_fused(m)};
+}
+static size_t chunk_bytes(const cmf_model *m, int bc, int n) {
     Arena a; Work w;
-    carve(a, w, bc, n);
+    carve(a, w, bc, n, carve_opts(m));
     return a.off + 256;
 }
 
@@ -305,11 +323,22 @@ static int ensure_workspace(cmf_model *m, int b, int n) {
     // chunk size: as many pairs as fit the workspace arena (default 64 GiB of the 180 GB, at most half of what is free; CMF_WS_GB / CMF_CHUNK_PAIRS override).
     // Few large chunks amortise the per-launch prologue of the persistent tensor-core kernels (cluster launch, TMEM allocation,
     // pipeline fill: ~40 us each, ~14 such launches per chunk).
-    if (m->ws && m->cap_n == n && m->cap_bc >= b && !getenv("CMF_CHUNK_PAIRS")) return CMF_OK;      // whole batch fits what we hold (also the path taken under stream capture)
-    size_t budget = (size_t)64 << 30;                 // of the 180 GB: one chunk for B=256 at N=256 (15 GB) and for B=64 at N=4096 (49 GB)
+    // `n` = the larger of the two clouds.  The arena is carved for (cap_bc pairs, cap_n points) and serves every call that needs no more:
+    // the reference's evaluation loop feeds one pair at a time with a different point count per frame (dataset/vod.py:92-93,
+    // main.py:203), which must not cost a cudaFree + cudaMalloc per frame.
+    const bool env_chunk = getenv("CMF_CHUNK_PAIRS") != nullptr;
+    if (m->ws && m->ws_mode != m->tc) { cudaFree(m->ws); m->ws = nullptr; m->ws_bytes = 0; m->cap_bc = m->cap_n = 0; drop_graphs(m); }   // carved for another mode
+    if (m->ws && n <= m->cap_n && b <= m->cap_bc && !env_chunk) return CMF_OK;       // (also the path taken under stream capture)
+    int n_cap = n;
+    if (m->ws && n > m->cap_n && n < 2048) n_cap = (n + 127) & ~127;                  // growing point counts: leave headroom instead of growing again next frame
+    if (n_cap < m->cap_n) n_cap = m->cap_n;
+    size_t budget = (size_t)64 << 30;                 // of the 180 GB: one chunk for B=256 at N=256 and for B=64 at N=4096
     {
         size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b / 2 < budget) budget = free_b / 2 > ((size_t)1 << 30) ? free_b / 2 : ((size_t)1 << 30);
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            free_b += m->ws_bytes;                    // what we hold is ours to re-use
+            if (free_b / 2 < budget) budget = free_b / 2 > ((size_t)1 << 30) ? free_b / 2 : ((size_t)1 << 30);
+        }
     }
     const char *wsenv = getenv("CMF_WS_GB");
     if (wsenv && atof(wsenv) > 0) budget = (size_t)(atof(wsenv) * (double)((size_t)1 << 30));
@@ -317,25 +346,25 @@ static int ensure_workspace(cmf_model *m, int b, int n) {
     const char *env = getenv("CMF_CHUNK_PAIRS");
     if (env && atoi(env) > 0) bc = atoi(env) < b ? atoi(env) : b;
     else {
-        const size_t per = chunk_bytes(1, n);
+        const size_t per = chunk_bytes(m, 1, n_cap);
         size_t fit = budget / per;
         if (fit < 1) fit = 1;
         if ((size_t)bc > fit) bc = (int)fit;
     }
-    if (m->ws && m->cap_n == n && m->cap_bc >= bc) return CMF_OK;
-    if (m->ws && m->cap_n == n && m->cap_bc < bc && !env) { /* grow */ }
-    if (m->ws) { cudaFree(m->ws); m->ws = nullptr; }
+    if (m->ws && n_cap <= m->cap_n && m->cap_bc >= bc) return CMF_OK;
+    if (bc < m->cap_bc && n_cap == m->cap_n) bc = m->cap_bc;                           // never shrink the pair capacity at the same point count
+    if (m->ws) { cudaFree(m->ws); m->ws = nullptr; m->ws_bytes = 0; }
     drop_graphs(m);                                   // captured graphs hold workspace pointers
-    const size_t bytes = chunk_bytes(bc, n);
+    const size_t bytes = chunk_bytes(m, bc, n_cap);
     cudaError_t e = cudaMalloc(&m->ws, bytes);
     if (e != cudaSuccess) {
         cmf_set_error("cmf_model: workspace cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
-        m->cap_bc = m->cap_n = 0; m->ws_bytes = 0;
+        m->cap_bc = m->cap_n = 0; m->ws_bytes = 0; m->ws = nullptr;
         return CMF_ERR_NOMEM;
     }
-    m->ws_bytes = bytes; m->cap_bc = bc; m->cap_n = n;
+    m->ws_bytes = bytes; m->cap_bc = bc; m->cap_n = n_cap; m->ws_mode = m->tc;
     Arena a; a.base = m->ws;
-    carve(a, m->w, bc, n);
+    carve(a, m->w, bc, n_cap, carve_opts(m));
     CMF_CUDA(cudaMemset(m->w.ZERO, 0, (size_t)bc * 256 * sizeof(float)));
     return CMF_OK;
 }
@@ -404,12 +433,14 @@ static int run_mse_layer(cmf_model *m, int bc, int n, const float *pc, const flo
     return CMF_OK;
 }
 
-static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const float *pc2, const float *ft1,
+// n = points of cloud 1 (the queries; every output is per point of cloud 1), n2 = points of cloud 2.  The reference's evaluation loop
+// feeds clouds of different sizes (dataset/vod.py:92-93 resamples to num_points only when training; main.py:203 evaluates one pair at a time).
+static int forward_chunk(cmf_model *m, int bc, int n, int n2, const float *pc1, const float *pc2, const float *ft1,
                          const float *ft2, const float *gprev, float *sf_agg, float *stat_cls, float *pre_trans,
                          uint8_t *mask, float *gfeat_out, cudaStream_t st, const float *interval = nullptr, float *raw_flow = nullptr,
                          const float *label_m = nullptr) {
     Work &w = m->w;
-    const long long bn = (long long)bc * n;
+    const long long bn = (long long)bc * n, bn2 = (long long)bc * n2;
     auto S = [&](int i) { return m->seg[i]; };
     const int F = m->tc == 2 ? 1 : 0;                                   // operand format of the tensor-core GEMMs (0: 3xTF32, 1: 3xFP16)
     const cmf_model::TcSet &T = m->tcw[F];
@@ -420,17 +451,17 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
 
     // neighbour search
     RUN(C_SEARCH, 0, cmf_launch_transpose3(bc, n, pc1, w.X1T, st));
-    RUN(C_SEARCH, 0, cmf_launch_transpose3(bc, n, pc2, w.X2T, st));
+    RUN(C_SEARCH, 0, cmf_launch_transpose3(bc, n2, pc2, w.X2T, st));
     RUN(C_SEARCH, 0, cmf_launch_ball_query_ms(bc, n, pc1, w.BQ1, st));
-    RUN(C_SEARCH, 0, cmf_launch_ball_query_ms(bc, n, pc2, w.BQ2, st));
-    RUN(C_SEARCH, 0, cmf_launch_knn_point8(bc, n, w.X2T, w.X1T, w.KNN12, st));
-    RUN(C_SEARCH, 0, cmf_launch_knn_point8(bc, n, w.X1T, w.X1T, w.KNN11, st));
+    RUN(C_SEARCH, 0, cmf_launch_ball_query_ms(bc, n2, pc2, w.BQ2, st));
+    RUN(C_SEARCH, 0, cmf_launch_knn_point8(bc, n2, n, w.X2T, w.X1T, w.KNN12, st));
+    RUN(C_SEARCH, 0, cmf_launch_knn_point8(bc, n, n, w.X1T, w.X1T, w.KNN11, st));
 
     // multi-scale encoders (cmflow.py:72-77); cloud 1 writes straight into the embedding rows E[:, 0:256]
     // fp16x3 + chain kernels: the per-pair maxima behind the consumer GEMMs' fp16 scales are taken by the producing kernels' epilogues
     const bool fused_amax = F && m->chain;
     { int rc = run_mse_layer(m, bc, n, pc1, ft1, w.BQ1, w.E, E_LD, w.G1, st, fused_amax ? AM(AM_F1) : nullptr); if (rc) return rc; }
-    { int rc = run_mse_layer(m, bc, n, pc2, ft2, w.BQ2, w.F2, 256, w.G2, st, fused_amax ? AM(AM_F2) : nullptr); if (rc) return rc; }
+    { int rc = run_mse_layer(m, bc, n2, pc2, ft2, w.BQ2, w.F2, 256, w.G2, st, fused_amax ? AM(AM_F2) : nullptr); if (rc) return rc; }
     RUN(C_GATHER, 0, cmf_launch_scatter_ft(bc, n, ft1, w.E, E_LD, 768, E_LD - 771, st, fused_amax ? AM(AM_FT) : nullptr));
 
     // flow embedding (FeatureCorrelator, radarflow_util.py:185-237)
@@ -446,9 +477,9 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
         if (F) {    // per-pair maxima of the GEMM inputs (fp16 scales): encoder features, kNN direction components
             if (!fused_amax) {
                 RUN(C_REDUCE, 0, cmf_launch_pair_absmax(bc, n, w.E, E_LD, 256, AM(AM_F1), st));
-                RUN(C_REDUCE, 0, cmf_launch_pair_absmax(bc, n, w.F2, 256, 256, AM(AM_F2), st));
+                RUN(C_REDUCE, 0, cmf_launch_pair_absmax(bc, n2, w.F2, 256, 256, AM(AM_F2), st));
             }
-            RUN(C_REDUCE, 0, cmf_launch_pair_dirmax(bc, n, pc1, pc2, w.KNN12, 8, AM(AM_DIR), st));
+            RUN(C_REDUCE, 0, cmf_launch_pair_dirmax(bc, n, n2, pc1, pc2, w.KNN12, 8, AM(AM_DIR), st));
         }
         {
             TcArgs ta_ = tc_plain(T.fc_wc, F, 512, 256, w.E, E_LD, w.U1, 512, nullptr, bn, CMF_ACT_NONE, w.PB1, 512, n);
@@ -456,27 +487,27 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
             RUN(C_GEMM_FC_HOIST, tflops(ta_, 256), cmf_launch_tc_auto(ta_, st));
         }
         {
-            TcArgs ta_ = tc_plain(T.fc_wn, F, 512, 256, w.F2, 256, w.U2, 512, nullptr, bn, CMF_ACT_NONE, w.PB2, 512, n);
+            TcArgs ta_ = tc_plain(T.fc_wn, F, 512, 256, w.F2, 256, w.U2, 512, nullptr, bn2, CMF_ACT_NONE, w.PB2, 512, n2);
             tc_bound(ta_, 0.f, AM(AM_F2), 1.f); if (F) { ta_.amax_out = AM(AM_U2); }
             RUN(C_GEMM_FC_HOIST, tflops(ta_, 256), cmf_launch_tc_auto(ta_, st));
         }
         {   // conv1 with the gather + hoisted conv0 epilogue fused into the B-operand producer (no H1 round trip)
             TcArgs ta_ = tc_plain(T.fc_w2, F, 512, 512, nullptr, 0, w.H2, 512, S(FC_B2), bn * 8, CMF_ACT_LEAKY, nullptr, 0, (long long)n * 8);
             ta_.prod = TC_PROD_FC_H1; ta_.U1 = w.U1; ta_.U2 = w.U2; ta_.ld_u2 = 512; ta_.off_u2 = 0; ta_.Wsmall = S(FC_WD);
-            ta_.xyz_q = pc1; ta_.xyz_c = pc2; ta_.nbr = w.KNN12; ta_.nbr_ld = 8; ta_.nbr_off = 0; ta_.ksamp = 8; ta_.n_pts = n;
+            ta_.xyz_q = pc1; ta_.xyz_c = pc2; ta_.nbr = w.KNN12; ta_.nbr_ld = 8; ta_.nbr_off = 0; ta_.ksamp = 8; ta_.n_pts = n; ta_.n_cand = n2;
             ta_.out_tiled = 1;                 // conv2's B operand is written split + swizzled, ready for a bulk copy
             // |leaky(U1[i] + U2[j] + Wd.dir)| <= max|U1| + max|U2| + max_c |Wd[c]|_1 * max|dir component|
             tc_bound(ta_, 0.f, AM(AM_U1), 1.f, AM(AM_U2), 1.f, AM(AM_DIR), m->wd_l1);
             ta_.out_mul = m->fc_w2_l1; ta_.out_add = m->fc_b2_max; ta_.out_scale_store = F ? SC(SC_H2) : nullptr;
             RUN(C_GEMM_FC_MLP, tflops(ta_, 512), cmf_launch_tc_auto(ta_, st));
         }
-        fused_wsum = cmf_tc_pair_enabled() && !getenv("CMF_NO_WSUM");
+        fused_wsum = wsum_fused(m);
         {
             TcArgs ta_ = tc_plain(T.fc_w3, F, 512, 512, nullptr, 0, fused_wsum ? w.COST1 : w.H1, 512, S(FC_B3), bn * 8, CMF_ACT_LEAKY, nullptr, 0, (long long)n * 8);
             ta_.prod = TC_PROD_TILED; ta_.Xt = w.H2;
             tc_scaled(ta_, SC(SC_H2));
             if (fused_wsum) {        // conv2 + LeakyReLU + WeightNet1 weighting + sum over the 8 neighbours in the TMEM epilogue
-                ta_.epi = TC_EPI_WSUM; ta_.ksamp = 8; ta_.n_pts = n; ta_.xyz_q = pc1; ta_.xyz_c = pc2; ta_.nbr = w.KNN12; ta_.nbr_ld = 8; ta_.nbr_off = 0;
+                ta_.epi = TC_EPI_WSUM; ta_.ksamp = 8; ta_.n_pts = n; ta_.n_cand = n2; ta_.xyz_q = pc1; ta_.xyz_c = pc2; ta_.nbr = w.KNN12; ta_.nbr_ld = 8; ta_.nbr_off = 0;
                 ta_.wnA1 = S(WN1_BASE); ta_.wna1 = S(WN1_BASE + 1); ta_.wnA2 = S(WN1_BASE + 2); ta_.wna2 = S(WN1_BASE + 3);
                 ta_.wnA3 = S(WN1_BASE + 4); ta_.wna3 = S(WN1_BASE + 5);
             }
@@ -484,15 +515,15 @@ static int forward_chunk(cmf_model *m, int bc, int n, const float *pc1, const fl
         }
     } else {
     { const GemmArgs ga_ = mk(S(FC_WC), 256, w.E, E_LD, w.U1, 512, nullptr, 512, 256, bn, CMF_ACT_NONE, w.PB1, 512, n); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
-    { const GemmArgs ga_ = mk(S(FC_WN), 256, w.F2, 256, w.U2, 512, nullptr, 512, 256, bn, CMF_ACT_NONE, w.PB2, 512, n); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
-    RUN(C_GATHER, 0, cmf_launch_fc_build_h1(bc, n, pc1, pc2, w.KNN12, w.U1, w.U2, S(FC_WD), w.H1, st));
+    { const GemmArgs ga_ = mk(S(FC_WN), 256, w.F2, 256, w.U2, 512, nullptr, 512, 256, bn2, CMF_ACT_NONE, w.PB2, 512, n2); RUN(C_GEMM_FC_HOIST, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
+    RUN(C_GATHER, 0, cmf_launch_fc_build_h1(bc, n, n2, pc1, pc2, w.KNN12, w.U1, w.U2, S(FC_WD), w.H1, st));
     { const GemmArgs ga_ = mk(S(FC_W2), 512, w.H1, 512, w.H2, 512, S(FC_B2), 512, 512, bn * 8, CMF_ACT_LEAKY); RUN(C_GEMM_FC_MLP, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     { const GemmArgs ga_ = mk(S(FC_W3), 512, w.H2, 512, w.H1, 512, S(FC_B3), 512, 512, bn * 8, CMF_ACT_LEAKY); RUN(C_GEMM_FC_MLP, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
     }
     WeightNetP wn1{S(WN1_BASE), S(WN1_BASE + 1), S(WN1_BASE + 2), S(WN1_BASE + 3), S(WN1_BASE + 4), S(WN1_BASE + 5)};
     WeightNetP wn2{S(WN2_BASE), S(WN2_BASE + 1), S(WN2_BASE + 2), S(WN2_BASE + 3), S(WN2_BASE + 4), S(WN2_BASE + 5)};
-    if (!fused_wsum) RUN(C_REDUCE, 0, cmf_launch_fc_reduce(bc, n, pc1, pc2, w.KNN12, wn1, w.H1, 0, w.COST1, 512, st));
-    RUN(C_REDUCE, 0, cmf_launch_fc_reduce(bc, n, pc1, pc1, w.KNN11, wn2, w.COST1, 1, w.E + 256, E_LD, st, fused_amax ? AM(AM_COR) : nullptr));
+    if (!fused_wsum) RUN(C_REDUCE, 0, cmf_launch_fc_reduce(bc, n, n2, pc1, pc2, w.KNN12, wn1, w.H1, 0, w.COST1, 512, st));
+    RUN(C_REDUCE, 0, cmf_launch_fc_reduce(bc, n, n, pc1, pc1, w.KNN11, wn2, w.COST1, 1, w.E + 256, E_LD, st, fused_amax ? AM(AM_COR) : nullptr));
 
     // set-conv #2 (mse_layer2, cmflow.py:87-89)
     if (m->tc) {
@@ -668,8 +699,13 @@ extern "C" void cmf_model_destroy(cmf_model *m) {
     drop_graphs(m);
     if (m->ws) cudaFree(m->ws);
     if (m->d_blob) cudaFree(m->d_blob);
-    if (m->d_in) cudaFree(m->d_in);
-    if (m->d_out) cudaFree(m->d_out);
+    for (auto &hs : m->slots) {
+        if (hs.busy && hs.ev_out) cudaEventSynchronize(hs.ev_out);
+        if (hs.d_in) cudaFree(hs.d_in);
+        if (hs.d_out) cudaFree(hs.d_out);
+        if (hs.ev_in) { cudaEventDestroy(hs.ev_in); cudaEventDestroy(hs.ev_done); cudaEventDestroy(hs.ev_out); }
+    }
+    if (m->s_h2d) { cudaStreamDestroy(m->s_h2d); cudaStreamDestroy(m->s_d2h); }
     for (int f = 0; f < 2; ++f) if (m->tcw[f].buf) cudaFree(m->tcw[f].buf);
     for (cudaEvent_t e : m->pool) cudaEventDestroy(e);
     delete m;
@@ -683,33 +719,42 @@ extern "C" int cmf_model_host_graphs(const cmf_model *m) {
 }
 extern "C" int cmf_model_launches_per_forward(const cmf_model *m) { return m ? m->launches : 0; }
 
-static int forward_impl(cmf_model *m, int b, int n, const float *pc1, const float *pc2, const float *ft1,
-                        const float *ft2, const float *gfeat_prev, const float *label_m, float *sf_agg, float *stat_cls,
-                        float *pre_trans, uint8_t *mask, float *gfeat_out, void *stream) {
+// Shared body of the device entry points.  n = points of cloud 1, n2 = points of cloud 2 (0 = same as n).
+struct FwdArgs {
+    const float *pc1, *pc2, *ft1, *ft2, *gfeat_prev, *label_m, *interval;
+    float *sf_agg, *stat_cls, *pre_trans; uint8_t *mask; float *gfeat_out, *raw_flow;
+};
+static int forward_impl(cmf_model *m, int b, int n, int n2, const FwdArgs &f, void *stream) {
     CMF_REQUIRE(m, "null model");
     DeviceScope dev_(m);
-    CMF_REQUIRE(b >= 0 && n >= 0, "negative size");
+    if (n2 == 0) n2 = n;
+    CMF_REQUIRE(b >= 0 && n >= 0 && n2 >= 0, "negative size");
     if (b == 0) return CMF_OK;
-    CMF_REQUIRE(n >= 8, "need at least 8 points per cloud (knn_point(8, ...): torch.topk raises below that)");
-    CMF_REQUIRE((long long)n * 32 * 512 < 2147483647LL / 2, "N too large for 32-bit column indices");
-    CMF_REQUIRE(pc1 && pc2 && ft1 && ft2 && sf_agg && stat_cls && pre_trans && mask, "null pointer");
-    CMF_REQUIRE(!m->temporal || gfeat_out, "CMFlow-T needs gfeat_out");
-    CMF_REQUIRE(!m->raflow, "this engine was switched to RaFlow: call cmf_model_forward_raflow");
-    int rc = ensure_workspace(m, b, n);
+    CMF_REQUIRE(n >= 8 && n2 >= 8, "need at least 8 points per cloud (knn_point(8, ...): torch.topk raises below that)");
+    const int nmax = n > n2 ? n : n2;
+    CMF_REQUIRE((long long)nmax * 32 * 512 < 2147483647LL / 2, "N too large for 32-bit column indices");
+    CMF_REQUIRE(f.pc1 && f.pc2 && f.ft1 && f.ft2 && f.sf_agg && f.pre_trans && f.mask, "null pointer");
+    if (m->raflow) CMF_REQUIRE(f.interval && f.raw_flow, "RaFlow engine: call cmf_model_forward_raflow (interval, output)");
+    else {
+        CMF_REQUIRE(!f.interval, "this engine is not a RaFlow engine: call cmf_model_set_raflow first");
+        CMF_REQUIRE(f.stat_cls, "null pointer");
+        CMF_REQUIRE(!m->temporal || f.gfeat_out, "CMFlow-T needs gfeat_out");
+    }
+    int rc = ensure_workspace(m, b, nmax);
     if (rc != CMF_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     m->launches = 0;
     for (int i = 0; i < 16; ++i) { m->work[i] = 0; m->nlaunch[i] = 0; }
     m->prof.clear(); m->pool_used = 0;
     m->last_b = b < m->cap_bc ? b : m->cap_bc; m->last_n = n;
-    const size_t pn = (size_t)3 * n;
+    const size_t pn = (size_t)3 * n, pn2 = (size_t)3 * n2;
     for (int b0 = 0; b0 < b; b0 += m->cap_bc) {
         const int bc = (b - b0) < m->cap_bc ? (b - b0) : m->cap_bc;
-        rc = forward_chunk(m, bc, n, pc1 + b0 * pn, pc2 + b0 * pn, ft1 + b0 * pn, ft2 + b0 * pn,
-                           gfeat_prev ? gfeat_prev + (size_t)b0 * 256 : nullptr,
-                           sf_agg + b0 * pn, stat_cls + (size_t)b0 * n, pre_trans + (size_t)b0 * 16, mask + (size_t)b0 * n,
-                           gfeat_out ? gfeat_out + (size_t)b0 * 256 : nullptr, st, nullptr, nullptr,
-                           label_m ? label_m + (size_t)b0 * n : nullptr);
+        rc = forward_chunk(m, bc, n, n2, f.pc1 + b0 * pn, f.pc2 + b0 * pn2, f.ft1 + b0 * pn, f.ft2 + b0 * pn2,
+                           f.gfeat_prev ? f.gfeat_prev + (size_t)b0 * 256 : nullptr,
+                           f.sf_agg + b0 * pn, f.stat_cls ? f.stat_cls + (size_t)b0 * n : nullptr, f.pre_trans + (size_t)b0 * 16, f.mask + (size_t)b0 * n,
+                           f.gfeat_out ? f.gfeat_out + (size_t)b0 * 256 : nullptr, st, f.interval ? f.interval + b0 : nullptr,
+                           f.raw_flow ? f.raw_flow + b0 * pn : nullptr, f.label_m ? f.label_m + (size_t)b0 * n : nullptr);
         if (rc != CMF_OK) return rc;
     }
     return CMF_OK;
@@ -718,14 +763,13 @@ static int forward_impl(cmf_model *m, int b, int n, const float *pc1, const floa
 extern "C" int cmf_model_forward(cmf_model *m, int b, int n, const float *pc1, const float *pc2, const float *ft1,
                                  const float *ft2, const float *gfeat_prev, float *sf_agg, float *stat_cls,
                                  float *pre_trans, uint8_t *mask, float *gfeat_out, void *stream) {
-    return forward_impl(m, b, n, pc1, pc2, ft1, ft2, gfeat_prev, nullptr, sf_agg, stat_cls, pre_trans, mask, gfeat_out, stream);
+    return forward_impl(m, b, n, n, FwdArgs{pc1, pc2, ft1, ft2, gfeat_prev, nullptr, nullptr, sf_agg, stat_cls, pre_trans, mask, gfeat_out, nullptr}, stream);
 }
 
-extern "C" int cmf_model_forward_labelled(cmf_model *m, int b, int n, const float *pc1, const float *pc2, const float *ft1,
-                                          const float *ft2, const float *gfeat_prev, const float *label_m, float *sf_agg, float *stat_cls,
-                                          float *pre_trans, uint8_t *mask, float *gfeat_out, void *stream) {
-    CMF_REQUIRE(label_m, "null label_m (use cmf_model_forward)");
-    return forward_impl(m, b, n, pc1, pc2, ft1, ft2, gfeat_prev, label_m, sf_agg, stat_cls, pre_trans, mask, gfeat_out, stream);
+extern "C" int cmf_model_forward2(cmf_model *m, int b, int n1, int n2, const float *pc1, const float *pc2, const float *ft1,
+                                  const float *ft2, const float *gfeat_prev, const float *label_m, float *sf_agg, float *stat_cls,
+                                  float *pre_trans, uint8_t *mask, float *gfeat_out, void *stream) {
+    return forward_impl(m, b, n1, n2, FwdArgs{pc1, pc2, ft1, ft2, gfeat_prev, label_m, nullptr, sf_agg, stat_cls, pre_trans, mask, gfeat_out, nullptr}, stream);
 }
 
 extern "C" int cmf_model_set_raflow(cmf_model *m, float rigid_thres, float rigid_pcs) {
@@ -737,111 +781,182 @@ extern "C" int cmf_model_set_raflow(cmf_model *m, float rigid_thres, float rigid
 
 extern "C" int cmf_model_forward_raflow(cmf_model *m, int b, int n, const float *pc1, const float *pc2, const float *ft1, const float *ft2,
                                         const float *interval, float *output, float *sf_agg, float *pre_trans, uint8_t *mask_s, void *stream) {
-    CMF_REQUIRE(m, "null model");
-    DeviceScope dev_(m);
-    CMF_REQUIRE(m->raflow, "call cmf_model_set_raflow first");
-    CMF_REQUIRE(b >= 0 && n >= 0, "negative size");
-    if (b == 0) return CMF_OK;
-    CMF_REQUIRE(n >= 8, "need at least 8 points per cloud (knn_point(8, ...): torch.topk raises below that)");
-    CMF_REQUIRE((long long)n * 32 * 512 < 2147483647LL / 2, "N too large for 32-bit column indices");
-    CMF_REQUIRE(pc1 && pc2 && ft1 && ft2 && interval && output && sf_agg && pre_trans && mask_s, "null pointer");
-    int rc = ensure_workspace(m, b, n);
-    if (rc != CMF_OK) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    m->launches = 0;
-    for (int i = 0; i < 16; ++i) { m->work[i] = 0; m->nlaunch[i] = 0; }
-    m->prof.clear(); m->pool_used = 0;
-    m->last_b = b < m->cap_bc ? b : m->cap_bc; m->last_n = n;
-    const size_t pn = (size_t)3 * n;
-    for (int b0 = 0; b0 < b; b0 += m->cap_bc) {
-        const int bc = (b - b0) < m->cap_bc ? (b - b0) : m->cap_bc;
-        rc = forward_chunk(m, bc, n, pc1 + b0 * pn, pc2 + b0 * pn, ft1 + b0 * pn, ft2 + b0 * pn, nullptr, sf_agg + b0 * pn, nullptr,
-                           pre_trans + (size_t)b0 * 16, mask_s + (size_t)b0 * n, nullptr, st, interval + b0, output + b0 * pn);
-        if (rc != CMF_OK) return rc;
+    CMF_REQUIRE(m && m->raflow, "call cmf_model_set_raflow first");
+    CMF_REQUIRE(interval && output, "null pointer");
+    return forward_impl(m, b, n, n, FwdArgs{pc1, pc2, ft1, ft2, nullptr, nullptr, interval, sf_agg, nullptr, pre_trans, mask_s, nullptr, output}, stream);
+}
+
+extern "C" int cmf_model_forward_raflow2(cmf_model *m, int b, int n1, int n2, const float *pc1, const float *pc2, const float *ft1, const float *ft2,
+                                         const float *interval, float *output, float *sf_agg, float *pre_trans, uint8_t *mask_s, void *stream) {
+    CMF_REQUIRE(m && m->raflow, "call cmf_model_set_raflow first");
+    CMF_REQUIRE(interval && output, "null pointer");
+    return forward_impl(m, b, n1, n2, FwdArgs{pc1, pc2, ft1, ft2, nullptr, nullptr, interval, sf_agg, nullptr, pre_trans, mask_s, nullptr, output}, stream);
+}
+
+// ---- host entry point -----------------------------------------------------------------------------------------------------------------
+// Two staging slots (device input / output buffers, one copy stream each way, events): the H2D copy of call i+1 and the D2H copy of
+// call i-1 overlap the kernels of call i when the caller uses the split submit / wait form (cmf_model_submit_host / cmf_model_wait_host);
+// cmf_model_forward_host is submit + wait of one call.
+static int host_slot_reserve(cmf_model *m, cmf_model::HostSlot &hs, size_t in_floats, size_t out_bytes) {
+    if (hs.in_floats < in_floats || hs.out_bytes < out_bytes) drop_graphs(m);         // captured graphs hold staging pointers
+    if (hs.in_floats < in_floats) {
+        if (hs.d_in) cudaFree(hs.d_in);
+        hs.d_in = nullptr; hs.in_floats = 0;
+        CMF_CUDA(cudaMalloc(&hs.d_in, in_floats * sizeof(float)));
+        hs.in_floats = in_floats;
     }
+    if (hs.out_bytes < out_bytes) {
+        if (hs.d_out) cudaFree(hs.d_out);
+        hs.d_out = nullptr; hs.out_bytes = 0;
+        CMF_CUDA(cudaMalloc(&hs.d_out, out_bytes));
+        hs.out_bytes = out_bytes;
+    }
+    if (!hs.ev_in) {
+        CMF_CUDA(cudaEventCreateWithFlags(&hs.ev_in, cudaEventDisableTiming));
+        CMF_CUDA(cudaEventCreateWithFlags(&hs.ev_done, cudaEventDisableTiming));
+        CMF_CUDA(cudaEventCreateWithFlags(&hs.ev_out, cudaEventDisableTiming));
+    }
+    return CMF_OK;
+}
+
+// The kernel sequence between the staging buffers of one slot: eager, or (CMF_HOST_GRAPH=1) captured once per (slot, shape, mode) and replayed.
+static int host_run(cmf_model *m, int slot, int b, int n, int n2, const FwdArgs &f, cudaStream_t st) {
+    const char *ge = getenv("CMF_HOST_GRAPH");
+    const bool use_graph = ge && ge[0] == '1' && !m->profiling && !m->raflow;
+    if (!use_graph) return forward_impl(m, b, n, n2, f, st);
+    const int has_g = f.gfeat_prev ? 1 : 0;
+    cmf_model::HostGraph *hg = nullptr;
+    for (auto &g : m->graphs) if (g.slot == slot && g.b == b && g.n == n && g.n2 == n2 && g.mode == m->tc && g.has_g == has_g) hg = &g;
+    if (!hg) {
+        // first call of this shape: eager (one-time attribute settings, weight tiling and allocations happen here, outside any capture)
+        int rc = forward_impl(m, b, n, n2, f, st);
+        if (rc == CMF_OK) {
+            if (m->graphs.size() >= 32) {              // bounded cache: forget the oldest shape
+                if (m->graphs.front().exec) cudaGraphExecDestroy(m->graphs.front().exec);
+                m->graphs.erase(m->graphs.begin());
+            }
+            m->graphs.push_back({slot, b, n, n2, m->tc, has_g, nullptr, false});
+        }
+        return rc;
+    }
+    if (!hg->exec && !hg->failed) {
+        cudaGraph_t graph = nullptr;
+        const int launches = m->launches;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            int rc = forward_impl(m, b, n, n2, f, st);
+            const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc == CMF_OK && ce == cudaSuccess && graph) {
+                if (cudaGraphInstantiate(&hg->exec, graph, 0) != cudaSuccess) hg->exec = nullptr;
+            }
+            if (graph) cudaGraphDestroy(graph);
+            if (rc != CMF_OK) return rc;
+        }
+        if (!hg->exec) { cudaGetLastError(); hg->failed = true; m->launches = launches; }  // capture unavailable: the entry keeps its key and routes this shape to the eager path from now on
+    }
+    if (hg->exec) { CMF_CUDA(cudaGraphLaunch(hg->exec, st)); return CMF_OK; }
+    return forward_impl(m, b, n, n2, f, st);
+}
+
+struct HostIo {
+    const float *pc1, *pc2, *ft1, *ft2, *gfeat_prev;
+    float *sf_agg, *stat_cls, *pre_trans; uint8_t *mask; float *gfeat_out;
+};
+
+static int host_submit(cmf_model *m, int slot, int b, int n, int n2, const HostIo &io, cudaStream_t st, bool pipelined) {
+    cmf_model::HostSlot &hs = m->slots[slot];
+    const size_t p1 = (size_t)b * 3 * n, p2 = (size_t)b * 3 * n2;
+    const size_t in_floats = 2 * p1 + 2 * p2 + (size_t)b * 256;
+    const size_t out_bytes = (p1 + (size_t)b * n + (size_t)b * 16 + (size_t)b * 256) * sizeof(float) + (size_t)b * n;
+    int rc = host_slot_reserve(m, hs, in_floats, out_bytes);
+    if (rc != CMF_OK) return rc;
+    float *d_pc1 = hs.d_in, *d_pc2 = d_pc1 + p1, *d_ft1 = d_pc2 + p2, *d_ft2 = d_ft1 + p1, *d_g = d_ft2 + p2;
+    float *d_sf = reinterpret_cast<float *>(hs.d_out), *d_cls = d_sf + p1, *d_tr = d_cls + (size_t)b * n, *d_go = d_tr + (size_t)b * 16;
+    uint8_t *d_mask = reinterpret_cast<uint8_t *>(d_go + (size_t)b * 256);
+    cudaStream_t s_in = st, s_out = st;
+    if (pipelined) {
+        if (!m->s_h2d) { CMF_CUDA(cudaStreamCreateWithFlags(&m->s_h2d, cudaStreamNonBlocking)); CMF_CUDA(cudaStreamCreateWithFlags(&m->s_d2h, cudaStreamNonBlocking)); }
+        s_in = m->s_h2d; s_out = m->s_d2h;
+        // the slot's previous outputs must have left before its buffers are overwritten: the caller waited on that slot (cmf_model_wait_host)
+    }
+    CMF_CUDA(cudaMemcpyAsync(d_pc1, io.pc1, p1 * sizeof(float), cudaMemcpyHostToDevice, s_in));
+    CMF_CUDA(cudaMemcpyAsync(d_pc2, io.pc2, p2 * sizeof(float), cudaMemcpyHostToDevice, s_in));
+    CMF_CUDA(cudaMemcpyAsync(d_ft1, io.ft1, p1 * sizeof(float), cudaMemcpyHostToDevice, s_in));
+    CMF_CUDA(cudaMemcpyAsync(d_ft2, io.ft2, p2 * sizeof(float), cudaMemcpyHostToDevice, s_in));
+    if (io.gfeat_prev) CMF_CUDA(cudaMemcpyAsync(d_g, io.gfeat_prev, (size_t)b * 256 * sizeof(float), cudaMemcpyHostToDevice, s_in));
+    if (pipelined) { CMF_CUDA(cudaEventRecord(hs.ev_in, s_in)); CMF_CUDA(cudaStreamWaitEvent(st, hs.ev_in, 0)); }
+    rc = host_run(m, slot, b, n, n2, FwdArgs{d_pc1, d_pc2, d_ft1, d_ft2, io.gfeat_prev ? d_g : nullptr, nullptr, nullptr, d_sf, d_cls, d_tr, d_mask, d_go, nullptr}, st);
+    if (rc != CMF_OK) return rc;
+    if (pipelined) { CMF_CUDA(cudaEventRecord(hs.ev_done, st)); CMF_CUDA(cudaStreamWaitEvent(s_out, hs.ev_done, 0)); }
+    CMF_CUDA(cudaMemcpyAsync(io.sf_agg, d_sf, p1 * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+    CMF_CUDA(cudaMemcpyAsync(io.stat_cls, d_cls, (size_t)b * n * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+    CMF_CUDA(cudaMemcpyAsync(io.pre_trans, d_tr, (size_t)b * 16 * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+    CMF_CUDA(cudaMemcpyAsync(io.mask, d_mask, (size_t)b * n, cudaMemcpyDeviceToHost, s_out));
+    if (m->temporal && io.gfeat_out) CMF_CUDA(cudaMemcpyAsync(io.gfeat_out, d_go, (size_t)b * 256 * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+    CMF_CUDA(cudaEventRecord(hs.ev_out, s_out));
+    hs.busy = true;
+    return CMF_OK;
+}
+
+static int host_check(cmf_model *m, int b, int n, int n2, const HostIo &io) {
+    CMF_REQUIRE(m, "null model");
+    CMF_REQUIRE(!m->raflow, "the host entry points serve CMFlow / CMFlow-T engines");
+    CMF_REQUIRE(b >= 0 && n >= 0 && n2 >= 0, "negative size");
+    CMF_REQUIRE(b == 0 || (io.pc1 && io.pc2 && io.ft1 && io.ft2 && io.sf_agg && io.stat_cls && io.pre_trans && io.mask), "null pointer");
     return CMF_OK;
 }
 
 extern "C" int cmf_model_forward_host(cmf_model *m, int b, int n, const float *pc1, const float *pc2, const float *ft1,
                                       const float *ft2, const float *gfeat_prev, float *sf_agg, float *stat_cls,
                                       float *pre_trans, uint8_t *mask, float *gfeat_out, void *stream) {
-    CMF_REQUIRE(m, "null model");
+    const HostIo io{pc1, pc2, ft1, ft2, gfeat_prev, sf_agg, stat_cls, pre_trans, mask, gfeat_out};
+    int rc = host_check(m, b, n, n, io);
+    if (rc != CMF_OK || b == 0) return rc;
     DeviceScope dev_(m);
-    CMF_REQUIRE(b >= 0 && n >= 0, "negative size");
-    if (b == 0) return CMF_OK;
-    CMF_REQUIRE(pc1 && pc2 && ft1 && ft2 && sf_agg && stat_cls && pre_trans && mask, "null pointer");
-    cudaStream_t st = (cudaStream_t)stream;
-    const size_t pn = (size_t)b * 3 * n;
-    const size_t in_floats = 4 * pn + (size_t)b * 256;
-    const size_t out_bytes = (pn + (size_t)b * n + (size_t)b * 16 + (size_t)b * 256) * sizeof(float) + (size_t)b * n;
-    if (m->d_in_floats < in_floats || m->d_out_bytes < out_bytes) drop_graphs(m);     // ... and staging pointers
-    if (m->d_in_floats < in_floats) {
-        if (m->d_in) cudaFree(m->d_in);
-        m->d_in = nullptr; m->d_in_floats = 0;
-        CMF_CUDA(cudaMalloc(&m->d_in, in_floats * sizeof(float)));
-        m->d_in_floats = in_floats;
-    }
-    if (m->d_out_bytes < out_bytes) {
-        if (m->d_out) cudaFree(m->d_out);
-        m->d_out = nullptr; m->d_out_bytes = 0;
-        CMF_CUDA(cudaMalloc(&m->d_out, out_bytes));
-        m->d_out_bytes = out_bytes;
-    }
-    float *d_pc1 = m->d_in, *d_pc2 = d_pc1 + pn, *d_ft1 = d_pc2 + pn, *d_ft2 = d_ft1 + pn, *d_g = d_ft2 + pn;
-    float *d_sf = m->d_out, *d_cls = d_sf + pn, *d_tr = d_cls + (size_t)b * n, *d_go = d_tr + (size_t)b * 16;
-    uint8_t *d_mask = reinterpret_cast<uint8_t *>(d_go + (size_t)b * 256);
-    CMF_CUDA(cudaMemcpyAsync(d_pc1, pc1, pn * sizeof(float), cudaMemcpyHostToDevice, st));
-    CMF_CUDA(cudaMemcpyAsync(d_pc2, pc2, pn * sizeof(float), cudaMemcpyHostToDevice, st));
-    CMF_CUDA(cudaMemcpyAsync(d_ft1, ft1, pn * sizeof(float), cudaMemcpyHostToDevice, st));
-    CMF_CUDA(cudaMemcpyAsync(d_ft2, ft2, pn * sizeof(float), cudaMemcpyHostToDevice, st));
-    if (gfeat_prev) CMF_CUDA(cudaMemcpyAsync(d_g, gfeat_prev, (size_t)b * 256 * sizeof(float), cudaMemcpyHostToDevice, st));
-    int rc = CMF_OK;
-    {
-        // opt-in (CMF_HOST_GRAPH=1): no gain was measured at B=256 (the host-device gap is the PCIe copies), and only the strict-fp32 CMFlow
-        // replay has been verified on hardware so far
-        const char *ge = getenv("CMF_HOST_GRAPH");
-        const bool no_graph = !(ge && ge[0] == '1');
-        const int has_g = gfeat_prev ? 1 : 0;
-        cmf_model::HostGraph *hg = nullptr;
-        for (auto &g : m->graphs) if (g.b == b && g.n == n && g.mode == m->tc && g.has_g == has_g) hg = &g;
-        if (no_graph || m->profiling || m->raflow) {
-            rc = cmf_model_forward(m, b, n, d_pc1, d_pc2, d_ft1, d_ft2, gfeat_prev ? d_g : nullptr, d_sf, d_cls, d_tr, d_mask, d_go, st);
-        } else if (!hg) {
-            // first call of this shape: eager (one-time attribute settings, weight tiling and allocations happen here, outside any capture)
-            rc = cmf_model_forward(m, b, n, d_pc1, d_pc2, d_ft1, d_ft2, gfeat_prev ? d_g : nullptr, d_sf, d_cls, d_tr, d_mask, d_go, st);
-            if (rc == CMF_OK) {
-                if (m->graphs.size() >= 16) {              // bounded cache: forget the oldest shape
-                    if (m->graphs.front().exec) cudaGraphExecDestroy(m->graphs.front().exec);
-                    m->graphs.erase(m->graphs.begin());
-                }
-                m->graphs.push_back({b, n, m->tc, has_g, nullptr, false});
-            }
-        } else {
-            if (!hg->exec && !hg->failed) {
-                cudaGraph_t graph = nullptr;
-                const int launches = m->launches;
-                if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-                    rc = cmf_model_forward(m, b, n, d_pc1, d_pc2, d_ft1, d_ft2, gfeat_prev ? d_g : nullptr, d_sf, d_cls, d_tr, d_mask, d_go, st);
-                    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
-                    if (rc == CMF_OK && ce == cudaSuccess && graph) {
-                        if (cudaGraphInstantiate(&hg->exec, graph, 0) != cudaSuccess) hg->exec = nullptr;
-                    }
-                    if (graph) cudaGraphDestroy(graph);
-                    if (rc != CMF_OK) return rc;
-                }
-                if (!hg->exec) { cudaGetLastError(); hg->failed = true; m->launches = launches; }  // capture unavailable: the entry keeps its key and routes this shape to the eager path from now on
-            }
-            if (hg->exec) CMF_CUDA(cudaGraphLaunch(hg->exec, st));
-            else rc = cmf_model_forward(m, b, n, d_pc1, d_pc2, d_ft1, d_ft2, gfeat_prev ? d_g : nullptr, d_sf, d_cls, d_tr, d_mask, d_go, st);
-        }
-    }
+    if (m->slots[0].busy) { CMF_CUDA(cudaEventSynchronize(m->slots[0].ev_out)); m->slots[0].busy = false; }
+    rc = host_submit(m, 0, b, n, n, io, (cudaStream_t)stream, false);
     if (rc != CMF_OK) return rc;
-    CMF_CUDA(cudaMemcpyAsync(sf_agg, d_sf, pn * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CMF_CUDA(cudaMemcpyAsync(stat_cls, d_cls, (size_t)b * n * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CMF_CUDA(cudaMemcpyAsync(pre_trans, d_tr, (size_t)b * 16 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CMF_CUDA(cudaMemcpyAsync(mask, d_mask, (size_t)b * n, cudaMemcpyDeviceToHost, st));
-    if (m->temporal && gfeat_out) CMF_CUDA(cudaMemcpyAsync(gfeat_out, d_go, (size_t)b * 256 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CMF_CUDA(cudaStreamSynchronize(st));
+    CMF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    m->slots[0].busy = false;
+    return CMF_OK;
+}
+
+extern "C" int cmf_model_forward_host2(cmf_model *m, int b, int n1, int n2, const float *pc1, const float *pc2, const float *ft1,
+                                       const float *ft2, const float *gfeat_prev, float *sf_agg, float *stat_cls,
+                                       float *pre_trans, uint8_t *mask, float *gfeat_out, void *stream) {
+    const HostIo io{pc1, pc2, ft1, ft2, gfeat_prev, sf_agg, stat_cls, pre_trans, mask, gfeat_out};
+    if (n2 == 0) n2 = n1;
+    int rc = host_check(m, b, n1, n2, io);
+    if (rc != CMF_OK || b == 0) return rc;
+    DeviceScope dev_(m);
+    if (m->slots[0].busy) { CMF_CUDA(cudaEventSynchronize(m->slots[0].ev_out)); m->slots[0].busy = false; }
+    rc = host_submit(m, 0, b, n1, n2, io, (cudaStream_t)stream, false);
+    if (rc != CMF_OK) return rc;
+    CMF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    m->slots[0].busy = false;
+    return CMF_OK;
+}
+
+extern "C" int cmf_model_submit_host(cmf_model *m, int slot, int b, int n1, int n2, const float *pc1, const float *pc2, const float *ft1,
+                                     const float *ft2, const float *gfeat_prev, float *sf_agg, float *stat_cls,
+                                     float *pre_trans, uint8_t *mask, float *gfeat_out, void *stream) {
+    const HostIo io{pc1, pc2, ft1, ft2, gfeat_prev, sf_agg, stat_cls, pre_trans, mask, gfeat_out};
+    if (n2 == 0) n2 = n1;
+    int rc = host_check(m, b, n1, n2, io);
+    if (rc != CMF_OK || b == 0) return rc;
+    CMF_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+    CMF_REQUIRE(!m->slots[slot].busy, "slot still in flight: call cmf_model_wait_host(slot) first");
+    DeviceScope dev_(m);
+    return host_submit(m, slot, b, n1, n2, io, (cudaStream_t)stream, true);
+}
+
+extern "C" int cmf_model_wait_host(cmf_model *m, int slot) {
+    CMF_REQUIRE(m, "null model");
+    CMF_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+    DeviceScope dev_(m);
+    cmf_model::HostSlot &hs = m->slots[slot];
+    if (!hs.busy) return CMF_OK;
+    CMF_CUDA(cudaEventSynchronize(hs.ev_out));
+    hs.busy = false;
     return CMF_OK;
 }
 

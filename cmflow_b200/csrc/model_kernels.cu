@@ -276,8 +276,8 @@ extern "C" int cmf_ball_query_ms(int b, int n, const float *xyz_planar, int *idx
     return cmf_launch_ball_query_ms(b, n, xyz_planar, idx60, (cudaStream_t)stream);
 }
 
-int cmf_launch_knn_point8(int b, int n, const float *cand_aos, const float *query_aos, int *idx, cudaStream_t st) {
-    return cmf_knn_point(b, n, n, 8, cand_aos, query_aos, idx, nullptr, (void *)st);
+int cmf_launch_knn_point8(int b, int n_cand, int n_query, const float *cand_aos, const float *query_aos, int *idx, cudaStream_t st) {
+    return cmf_knn_point(b, n_cand, n_query, 8, cand_aos, query_aos, idx, nullptr, (void *)st);
 }
 
 // ---- mse_layer (C=3) input rows -----------------------------------------------------------------
@@ -518,23 +518,23 @@ int cmf_launch_pair_absmax(int b, int n, const float *X, int ld, int width, unsi
     return CMF_OK;
 }
 __global__ void __launch_bounds__(256)
-pair_dirmax_kernel(int n, int k, const float *__restrict__ xyzq, const float *__restrict__ xyzc, const int *__restrict__ nbr,
+pair_dirmax_kernel(int n, int nc, int k, const float *__restrict__ xyzq, const float *__restrict__ xyzc, const int *__restrict__ nbr,
                    unsigned int *__restrict__ out) {
     const int b = blockIdx.x;
-    const float *pq = xyzq + (size_t)b * 3 * n, *pc = xyzc + (size_t)b * 3 * n;
+    const float *pq = xyzq + (size_t)b * 3 * n, *pc = xyzc + (size_t)b * 3 * nc;
     float mx = 0.f;
     for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < n * k; t += gridDim.y * blockDim.x) {
         const int i = t / k;
         const int j = __ldg(nbr + (size_t)b * n * k + t);
         mx = fmaxf(mx, fmaxf(fabsf(__fsub_rn(__ldg(pc + j), __ldg(pq + i))),
-                             fmaxf(fabsf(__fsub_rn(__ldg(pc + n + j), __ldg(pq + n + i))), fabsf(__fsub_rn(__ldg(pc + 2 * n + j), __ldg(pq + 2 * n + i))))));
+                             fmaxf(fabsf(__fsub_rn(__ldg(pc + nc + j), __ldg(pq + n + i))), fabsf(__fsub_rn(__ldg(pc + 2 * nc + j), __ldg(pq + 2 * n + i))))));
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
     if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(out + b, __float_as_uint(mx));
 }
-int cmf_launch_pair_dirmax(int b, int n, const float *xyzq_planar, const float *xyzc_planar, const int *nbr, int k, unsigned int *out, cudaStream_t st) {
-    pair_dirmax_kernel<<<dim3(b, cmf_divup((long long)n * k, 256 * 8)), 256, 0, st>>>(n, k, xyzq_planar, xyzc_planar, nbr, out);
+int cmf_launch_pair_dirmax(int b, int n, int n_cand, const float *xyzq_planar, const float *xyzc_planar, const int *nbr, int k, unsigned int *out, cudaStream_t st) {
+    pair_dirmax_kernel<<<dim3(b, cmf_divup((long long)n * k, 256 * 8)), 256, 0, st>>>(n, n_cand, k, xyzq_planar, xyzc_planar, nbr, out);
     CMF_LAUNCH_CHECK();
     return CMF_OK;
 }
@@ -547,19 +547,19 @@ __device__ __forceinline__ float4 ld4(const float *p) { return __ldg(reinterpret
 __device__ __forceinline__ float leaky01(float v) { return v > 0.f ? v : 0.1f * v; }
 
 __global__ void __launch_bounds__(128)
-fc_build_h1_kernel(int n, const float *__restrict__ xyz1, const float *__restrict__ xyz2, const int *__restrict__ knn12,
+fc_build_h1_kernel(int n, int n2, const float *__restrict__ xyz1, const float *__restrict__ xyz2, const int *__restrict__ knn12,
                    const float *__restrict__ U1, const float *__restrict__ U2, const float *__restrict__ Wd,
                    float *__restrict__ H1) {
     const int bi = blockIdx.x, b = bi / n, i = bi - b * n, t = threadIdx.x;
-    const float *p1 = xyz1 + (size_t)b * 3 * n, *p2 = xyz2 + (size_t)b * 3 * n;
+    const float *p1 = xyz1 + (size_t)b * 3 * n, *p2 = xyz2 + (size_t)b * 3 * n2;
     const float qx = __ldg(p1 + i), qy = __ldg(p1 + n + i), qz = __ldg(p1 + 2 * n + i);
     const float4 u1 = ld4(U1 + (size_t)bi * 512 + t * 4);
     const float4 w0 = ld4(Wd + (t * 4 + 0) * 4), w1 = ld4(Wd + (t * 4 + 1) * 4), w2 = ld4(Wd + (t * 4 + 2) * 4), w3 = ld4(Wd + (t * 4 + 3) * 4);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int j = __ldg(knn12 + (size_t)bi * 8 + k);
-        const float dx = __fsub_rn(__ldg(p2 + j), qx), dy = __fsub_rn(__ldg(p2 + n + j), qy), dz = __fsub_rn(__ldg(p2 + 2 * n + j), qz);
-        const float4 u2 = ld4(U2 + ((size_t)b * n + j) * 512 + t * 4);
+        const float dx = __fsub_rn(__ldg(p2 + j), qx), dy = __fsub_rn(__ldg(p2 + n2 + j), qy), dz = __fsub_rn(__ldg(p2 + 2 * n2 + j), qz);
+        const float4 u2 = ld4(U2 + ((size_t)b * n2 + j) * 512 + t * 4);
         float4 v;
         v.x = leaky01(u1.x + u2.x + fmaf(w0.z, dz, fmaf(w0.y, dy, w0.x * dx)));
         v.y = leaky01(u1.y + u2.y + fmaf(w1.z, dz, fmaf(w1.y, dy, w1.x * dx)));
@@ -568,9 +568,9 @@ fc_build_h1_kernel(int n, const float *__restrict__ xyz1, const float *__restric
         *reinterpret_cast<float4 *>(H1 + ((size_t)bi * 8 + k) * 512 + t * 4) = v;
     }
 }
-int cmf_launch_fc_build_h1(int b, int n, const float *xyz1_planar, const float *xyz2_planar, const int *knn12,
+int cmf_launch_fc_build_h1(int b, int n, int n2, const float *xyz1_planar, const float *xyz2_planar, const int *knn12,
                            const float *U1, const float *U2, const float *Wd, float *H1, cudaStream_t st) {
-    fc_build_h1_kernel<<<b * n, 128, 0, st>>>(n, xyz1_planar, xyz2_planar, knn12, U1, U2, Wd, H1);
+    fc_build_h1_kernel<<<b * n, 128, 0, st>>>(n, n2, xyz1_planar, xyz2_planar, knn12, U1, U2, Wd, H1);
     CMF_LAUNCH_CHECK();
     return CMF_OK;
 }
@@ -582,7 +582,7 @@ int cmf_launch_fc_build_h1(int b, int n, const float *xyz1_planar, const float *
 // eight 2 KB row gathers of point p+1 under the arithmetic of point p.
 constexpr int FCR_PTS = 16;
 __global__ void __launch_bounds__(128)
-fc_reduce_kernel(long long points, int n, const float *__restrict__ xyzq, const float *__restrict__ xyzc, const int *__restrict__ knn,
+fc_reduce_kernel(long long points, int n, int nc, const float *__restrict__ xyzq, const float *__restrict__ xyzc, const int *__restrict__ knn,
                  WeightNetP wn, const float *__restrict__ src, int gather, float *__restrict__ out, int ldo, unsigned int *__restrict__ amax_out) {
     __shared__ __align__(16) float sh2[FCR_PTS][8][8];
     __shared__ float samx[4];
@@ -596,11 +596,11 @@ fc_reduce_kernel(long long points, int n, const float *__restrict__ xyzq, const 
         long long row = 0;
         if (bi < points) {
             const long long b = bi / n; const int i = (int)(bi - b * n);
-            const float *pq = xyzq + (size_t)b * 3 * n, *pc = xyzc + (size_t)b * 3 * n;
+            const float *pq = xyzq + (size_t)b * 3 * n, *pc = xyzc + (size_t)b * 3 * nc;
             const int j = __ldg(knn + (size_t)bi * 8 + k);
-            row = gather ? b * n + j : bi * 8 + k;
-            const float dx = __fsub_rn(__ldg(pc + j), __ldg(pq + i)), dy = __fsub_rn(__ldg(pc + n + j), __ldg(pq + n + i)),
-                        dz = __fsub_rn(__ldg(pc + 2 * n + j), __ldg(pq + 2 * n + i));
+            row = gather ? b * nc + j : bi * 8 + k;
+            const float dx = __fsub_rn(__ldg(pc + j), __ldg(pq + i)), dy = __fsub_rn(__ldg(pc + nc + j), __ldg(pq + n + i)),
+                        dz = __fsub_rn(__ldg(pc + 2 * nc + j), __ldg(pq + 2 * n + i));
             float h1[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -676,11 +676,11 @@ fc_reduce_kernel(long long points, int n, const float *__restrict__ xyzq, const 
         }
     }
 }
-int cmf_launch_fc_reduce(int b, int n, const float *xyzq_planar, const float *xyzc_planar, const int *knn,
+int cmf_launch_fc_reduce(int b, int n, int n_cand, const float *xyzq_planar, const float *xyzc_planar, const int *knn,
                          WeightNetP wn, const float *src, int gather, float *out, int ldo, cudaStream_t st, unsigned int *amax_out) {
     const long long points = (long long)b * n;
     if (points <= 0) return CMF_OK;
-    fc_reduce_kernel<<<cmf_divup(points, FCR_PTS), 128, 0, st>>>(points, n, xyzq_planar, xyzc_planar, knn, wn, src, gather, out, ldo, amax_out);
+    fc_reduce_kernel<<<cmf_divup(points, FCR_PTS), 128, 0, st>>>(points, n, n_cand, xyzq_planar, xyzc_planar, knn, wn, src, gather, out, ldo, amax_out);
     CMF_LAUNCH_CHECK();
     return CMF_OK;
 }

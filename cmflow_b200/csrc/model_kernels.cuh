@@ -19,7 +19,7 @@ int cmf_launch_gemm1(const GemmArgs &g, cudaStream_t st);
 
 int cmf_launch_transpose3(int b, int n, const float *planar, float *aos, cudaStream_t st);
 int cmf_launch_ball_query_ms(int b, int n, const float *xyz_planar, int *idx60, cudaStream_t st);
-int cmf_launch_knn_point8(int b, int n, const float *cand_aos, const float *query_aos, int *idx, cudaStream_t st);
+int cmf_launch_knn_point8(int b, int n_cand, int n_query, const float *cand_aos, const float *query_aos, int *idx, cudaStream_t st);
 
 // mse_layer input rows: X0[scale s][(b*N+i)*K_s + kk][0..7] = [xyz_j - xyz_i, ft_j, 0, 0]
 int cmf_launch_build_x0(int b, int n, const float *xyz_planar, const float *ft_planar, const int *idx60,
@@ -36,10 +36,11 @@ int cmf_launch_globalmax(int b, int n, int C, const float *F, int ldf, float *G,
 int cmf_launch_scatter_ft(int b, int n, const float *ft_planar, float *E, int lde, int off, int pad, cudaStream_t st, unsigned int *amax_out = nullptr);
 
 // flow embedding (FeatureCorrelator) pieces
-int cmf_launch_fc_build_h1(int b, int n, const float *xyz1_planar, const float *xyz2_planar, const int *knn12,
+int cmf_launch_fc_build_h1(int b, int n, int n2, const float *xyz1_planar, const float *xyz2_planar, const int *knn12,
                            const float *U1, const float *U2, const float *Wd /*512x4*/, float *H1, cudaStream_t st);
 struct WeightNetP { const float *A1, *a1, *A2, *a2, *A3, *a3; };   // 8x4, 8, 8x8, 8, 512x8, 512
-int cmf_launch_fc_reduce(int b, int n, const float *xyzq_planar, const float *xyzc_planar, const int *knn,
+// n = points of the query cloud (rows of out), n_cand = points of the candidate cloud (xyzc, and src when gather = 1)
+int cmf_launch_fc_reduce(int b, int n, int n_cand, const float *xyzq_planar, const float *xyzc_planar, const int *knn,
                          WeightNetP wn, const float *src, int gather /*0: src rows (b*N+i)*8+k ; 1: src rows b*N+j*/,
                          float *out, int ldo, cudaStream_t st, unsigned int *amax_out = nullptr);
 // set-conv #2 first layer after hoisting: Y1[((b*N+i)*K + kk)][c] = relu(P[(b*N+j)*ldp + poff + c] + Wx[c][0..2] . rel)
@@ -63,4 +64,4 @@ int cmf_launch_raflow_sfr(int b, int n, const float *pc1, const float *ft1, cons
 // fp16x3 mode: out[b] = max(out[b], bits(max |X[(b*N+i)*ld + c]|, c < width))  (uint bit patterns; caller zeroes)
 int cmf_launch_pair_absmax(int b, int n, const float *X, int ld, int width, unsigned int *out, cudaStream_t st);
 // out[b] = max over points i and their k neighbours j of max(|xc_j - xq_i| per component)
-int cmf_launch_pair_dirmax(int b, int n, const float *xyzq_planar, const float *xyzc_planar, const int *nbr, int k, unsigned int *out, cudaStream_t st);
+int cmf_launch_pair_dirmax(int b, int n, int n_cand, const float *xyzq_planar, const float *xyzc_planar, const int *nbr, int k, unsigned int *out, cudaStream_t st);

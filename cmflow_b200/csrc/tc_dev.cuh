@@ -205,12 +205,13 @@ __device__ __forceinline__ RowCtx make_row(const TcArgs &a, long long c) {
     const int kk = (int)(c - bi * a.ksamp);
     const int b = (int)(bi / a.n_pts), i = (int)(bi - (long long)b * a.n_pts);
     const int j = __ldg(a.nbr + (size_t)bi * a.nbr_ld + a.nbr_off + kk);
-    const float *pq = a.xyz_q + (size_t)b * 3 * a.n_pts, *pc = a.xyz_c + (size_t)b * 3 * a.n_pts;
+    const int nc = a.n_cand ? a.n_cand : a.n_pts;                      // candidate cloud may hold a different number of points (N1 != N2)
+    const float *pq = a.xyz_q + (size_t)b * 3 * a.n_pts, *pc = a.xyz_c + (size_t)b * 3 * nc;
     r.dx = __fsub_rn(__ldg(pc + j), __ldg(pq + i));
-    r.dy = __fsub_rn(__ldg(pc + a.n_pts + j), __ldg(pq + a.n_pts + i));
-    r.dz = __fsub_rn(__ldg(pc + 2 * a.n_pts + j), __ldg(pq + 2 * a.n_pts + i));
+    r.dy = __fsub_rn(__ldg(pc + nc + j), __ldg(pq + a.n_pts + i));
+    r.dz = __fsub_rn(__ldg(pc + 2 * nc + j), __ldg(pq + 2 * a.n_pts + i));
     r.src0 = a.U1 ? a.U1 + (size_t)bi * 512 : nullptr;
-    r.src1 = a.U2 + ((size_t)b * a.n_pts + j) * a.ld_u2 + a.off_u2;
+    r.src1 = a.U2 + ((size_t)b * nc + j) * a.ld_u2 + a.off_u2;
     if (a.bs_mode) r.scale = b_scale_of(a, b);
     return r;
 }

@@ -17,7 +17,8 @@ struct TcArgs {
     const float *X; int ldx;                                     // PLAIN: row c = X + c*ldx
     const float *U1, *U2, *Wsmall;                               // FC_H1: leaky(U1[i]+U2[j]+Wd.dir); SC2_Y1: relu(P[j]+Wx.rel) with U2=P, Wsmall=Wx/Wd (C x 4)
     const float *xyz_q, *xyz_c; const int *nbr;                  // planar (B,3,N) clouds of the query / candidate points, neighbour table
-    int n_pts, ksamp, nbr_ld, nbr_off, ld_u2, off_u2;            // points per cloud, neighbours per point, table row stride/offset, gathered-row stride/offset
+    int n_pts, ksamp, nbr_ld, nbr_off, ld_u2, off_u2;            // points per (query) cloud, neighbours per point, table row stride/offset, gathered-row stride/offset
+    int n_cand;                                                  // points per candidate cloud (xyz_c, U2 rows) when it differs from n_pts; 0 = same
     const float *Xt;                                             // TILED: activations already split + swizzled by a previous tc GEMM (out_tiled)
     // epilogue
     int epi;

@@ -502,9 +502,10 @@ tc_gemm2_kernel(const TcArgs a) {
                 const long long bi = c >> 3;
                 const int b = (int)(bi / a.n_pts), i = (int)(bi - (long long)b * a.n_pts);
                 const int j = __ldg(a.nbr + (size_t)bi * a.nbr_ld + a.nbr_off + (int)(c & 7));
-                const float *pq = a.xyz_q + (size_t)b * 3 * a.n_pts, *pc = a.xyz_c + (size_t)b * 3 * a.n_pts;
-                const float dx = __fsub_rn(__ldg(pc + j), __ldg(pq + i)), dy = __fsub_rn(__ldg(pc + a.n_pts + j), __ldg(pq + a.n_pts + i)),
-                            dz = __fsub_rn(__ldg(pc + 2 * a.n_pts + j), __ldg(pq + 2 * a.n_pts + i));
+                const int nc = a.n_cand ? a.n_cand : a.n_pts;
+                const float *pq = a.xyz_q + (size_t)b * 3 * a.n_pts, *pc = a.xyz_c + (size_t)b * 3 * nc;
+                const float dx = __fsub_rn(__ldg(pc + j), __ldg(pq + i)), dy = __fsub_rn(__ldg(pc + nc + j), __ldg(pq + a.n_pts + i)),
+                            dz = __fsub_rn(__ldg(pc + 2 * nc + j), __ldg(pq + 2 * a.n_pts + i));
                 float h1[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {

@@ -53,6 +53,21 @@ def make_pairs(B, N, seed=1234, dense=False, device="cpu"):
     return tuple(out)
 
 
+def make_padded_pairs(B, N, n_unique, seed):
+    """Pairs whose clouds hold n_unique distinct points padded to N by duplicate sampling, exactly as the training loader does
+    (dataset/vod.py:102-110: arange(npts) followed by np.random.choice(npts, N - npts, replace=True); positions AND features are
+    indexed with the same sample).  Returns the pairs and the (B,N) maps point -> unique id of each cloud."""
+    pc1, pc2, ft1, ft2, T = make_pairs(B, n_unique, seed=seed)
+    g = torch.Generator().manual_seed(seed + 7)
+    out, maps = [], []
+    for pc, ft in ((pc1, ft1), (pc2, ft2)):
+        idx = torch.stack([torch.cat([torch.arange(n_unique), torch.randint(0, n_unique, (N - n_unique,), generator=g)]) for _ in range(B)])
+        gi = idx[:, None, :].expand(B, 3, N)
+        out.append((torch.gather(pc, 2, gi).contiguous(), torch.gather(ft, 2, gi).contiguous()))
+        maps.append(idx)
+    return (out[0][0], out[1][0], out[0][1], out[1][1], T), maps, (pc1, pc2)
+
+
 def _conv(g, cout, cin, bias, gain=1.0):
     # std = gain / sqrt(fan_in): keeps activations O(1) through the ~20 stacked layers so that the
     # motion scores are spread around the 0.5 threshold and the Kabsch system is well conditioned.

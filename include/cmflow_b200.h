@@ -170,14 +170,20 @@ int cmf_model_forward(cmf_model *m, int b, int n,
                       float *sf_agg, float *stat_cls, float *pre_trans, uint8_t *mask, float *gfeat_out,
                       void *stream);
 
-/* mode='train' with pseudo motion labels (models/cmflow.py:181-182, cmflow_t.py:196-197): label_m (B,N) device floats replace the
- * predicted scores in the ego-motion head's weights and in the refinement mask (cmflow.py:188); stat_cls still returns the
- * network's own scores.  Inference arithmetic otherwise (BatchNorm running statistics; no gradients). */
-int cmf_model_forward_labelled(cmf_model *m, int b, int n,
-                               const float *pc1, const float *pc2, const float *ft1, const float *ft2,
-                               const float *gfeat_prev, const float *label_m,
-                               float *sf_agg, float *stat_cls, float *pre_trans, uint8_t *mask, float *gfeat_out,
-                               void *stream);
+/* General device-resident form.  n1 / n2 = points of cloud 1 / cloud 2 (n2 = 0 means n1): the reference's evaluation loop feeds
+ * un-resampled clouds of different sizes, one pair at a time (dataset/vod.py:92-93 resamples only when training; main.py:203), and
+ * FeatureCorrelator.forward handles N1 != N2 (radarflow_util.py:185-237).  pc2, ft2 are (B,3,n2); every output is per point of cloud 1.
+ * label_m (B,n1) device floats or NULL: mode='train' with pseudo motion labels (models/cmflow.py:181-182, cmflow_t.py:196-197) -- the
+ * labels replace the predicted scores in the ego-motion head's weights and in the refinement mask (cmflow.py:188); stat_cls still
+ * returns the network's own scores.  Inference arithmetic otherwise (BatchNorm running statistics; no gradients). */
+int cmf_model_forward2(cmf_model *m, int b, int n1, int n2,
+                       const float *pc1, const float *pc2, const float *ft1, const float *ft2,
+                       const float *gfeat_prev, const float *label_m,
+                       float *sf_agg, float *stat_cls, float *pre_trans, uint8_t *mask, float *gfeat_out,
+                       void *stream);
+int cmf_model_forward_raflow2(cmf_model *m, int b, int n1, int n2,
+                              const float *pc1, const float *pc2, const float *ft1, const float *ft2, const float *interval,
+                              float *output, float *sf_agg, float *pre_trans, uint8_t *mask_s, void *stream);
 
 /* Same with HOST buffers (pinned for full speed): copies inputs H2D, runs the forward, copies the four
  * outputs D2H and synchronises `stream`.  This is the end-to-end call bench.py times as `e2e`. */
@@ -186,6 +192,24 @@ int cmf_model_forward_host(cmf_model *m, int b, int n,
                            const float *gfeat_prev,
                            float *sf_agg, float *stat_cls, float *pre_trans, uint8_t *mask, float *gfeat_out,
                            void *stream);
+
+int cmf_model_forward_host2(cmf_model *m, int b, int n1, int n2,
+                            const float *pc1, const float *pc2, const float *ft1, const float *ft2,
+                            const float *gfeat_prev,
+                            float *sf_agg, float *stat_cls, float *pre_trans, uint8_t *mask, float *gfeat_out,
+                            void *stream);
+
+/* Pipelined host form: the engine owns two staging slots (device buffers + copy streams).  cmf_model_submit_host(slot, ...) enqueues the
+ * H2D copies of this call on the engine's upload stream, the kernels on `stream` (after the upload) and the D2H copies on the engine's
+ * download stream (after the kernels) and returns without waiting; cmf_model_wait_host(slot) blocks until that call's outputs are in the
+ * host buffers.  Alternating slots 0,1 overlaps the upload of call i+1 and the download of call i-1 with the kernels of call i.
+ * Host buffers must be pinned for the copies to be asynchronous, and stay untouched until the slot has been waited on. */
+int cmf_model_submit_host(cmf_model *m, int slot, int b, int n1, int n2,
+                          const float *pc1, const float *pc2, const float *ft1, const float *ft2,
+                          const float *gfeat_prev,
+                          float *sf_agg, float *stat_cls, float *pre_trans, uint8_t *mask, float *gfeat_out,
+                          void *stream);
+int cmf_model_wait_host(cmf_model *m, int slot);
 
 /* Arithmetic mode of the big 1x1-conv GEMMs: 0 = strict fp32 FMA (parity build, default), 1 = tcgen05 tensor cores with
  * 3xTF32 split precision (fp32 accumulate in TMEM; ~2^-22 relative per product), 2 = tcgen05 with 3xFP16 split precision

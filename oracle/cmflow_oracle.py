@@ -148,7 +148,7 @@ def gru_step(sd, x, h, dtype):
 
 
 def cmflow_forward(sd, pc1, pc2, ft1, ft2, stat_thres=0.5, dtype=torch.float32, temporal=False, gfeat_prev=None,
-                   return_intermediates=False):
+                   return_intermediates=False, label_m=None):
     """CMFlow.forward(pc1,pc2,feature1,feature2,label_m=None,mode='test') (models/cmflow.py:171-197) and, with
     temporal=True, CMFlow_T.forward(..., gfeat) (models/cmflow_t.py:185-211).
 
@@ -183,8 +183,10 @@ def cmflow_forward(sd, pc1, pc2, ft1, ft2, stat_thres=0.5, dtype=torch.float32, 
     final = torch.cat([prop, gexp], 1)                                        # :91
     flow = _head(sd, "fp", final, dtype)                                      # :177
     stat_cls = torch.sigmoid(_head(sd, "mp", final, dtype))                   # :178
-    mask = (stat_cls > stat_thres).squeeze(1)                                 # :188
-    score = stat_cls.squeeze(1)
+    # mode='train' with pseudo labels: scores = label_m.unsqueeze(1) (:181-182); otherwise the predicted scores (:184-185)
+    scores = stat_cls if label_m is None else label_m.to(dtype).unsqueeze(1)
+    mask = (scores > stat_thres).squeeze(1)                                   # :188
+    score = scores.squeeze(1)
     if not temporal:
         score = score + 1e-4                                                  # cmflow.py:105 (absent in cmflow_t.py:119)
     weight = score / score.sum(1, keepdim=True)                               # :106
