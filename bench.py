@@ -19,11 +19,18 @@ of a clip batch; --points 4096 --batch 64: the dense cloud), but the bench line 
            dominant kernel (set-conv #2 layer 2): algorithmic TFLOP/s against the measured cuBLAS bf16 rate
            (`frac`), against that rate / 3 (`frac_of_ceiling`: the 3-MMA split), `traffic` = DRAM bytes per launch
            from the committed ncu capture, and `hbm` = SURVEY 8d's algorithmic bytes over the launch time
-  cpu_baseline : the oracle (CPU port of the reference's PyTorch path) on a bounded sample, rank 0, N=1 only
-  ref_cuda_baseline : informational -- the reference's own ball-query kernel (compiled unmodified) under the
-           PyTorch-eager unfused model on the same GPU (north_star's "reference's own lib/src CUDA build")
-  --impl reference : the reference arm = that same CPU port timed with all host threads (the reference's
-           Python cannot travel to the GPU box and ships no CPU kernels of its own -- SURVEY.md 8c)
+  sustained : >= 5 s of back-to-back device-resident forwards (no flush, no host gaps) with the clocks sampled: the
+           steady-state number under the power cap, next to the short timed region of `value`
+  latency_b1 : one pair per call (the reference's evaluation shape, main.py:203): device ms and end-to-end host ms,
+           eager launches and CUDA-graph replay (CMF_HOST_GRAPH=1)
+  cpu_baseline : the `--impl reference` arm run as a subprocess on a bounded sample, rank 0, N=1 only
+  ref_cuda_baseline : north_star's "reference's own lib/src CUDA build" on the same GPU: the UNMODIFIED reference Python
+           (models/cmflow.py, radarflow_util.py, lib/pointnet2_utils.py, staged under oracle/_ref/py) over the reference's
+           own lib/src kernels compiled for sm_100a (oracle/_ref/libpointnet2_ref.so), cuDNN / cuBLAS with TF32 off, at
+           the SAME batch and point count as the bench line
+  --impl reference : the reference arm = the unmodified reference Python on the host cores (its pointnet2_cuda module
+           answered by the C restatement oracle/pointops_oracle.c, `.cuda()` a no-op), all host threads, bounded
+           sample per step; falls back to the oracle port (kind "port") if the staged reference is missing
 """
 import argparse
 import json
@@ -89,61 +96,95 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def time_cpu_port(pairs, points, steps, warmup, threads):
-    """The oracle (CPU port of the reference forward) on `pairs` synthetic pairs per step."""
-    from cmflow_b200.synth import make_pairs, synthetic_state_dict
-    from oracle import cmflow_oracle as O
+def time_cpu_reference(pairs, points, steps, warmup, threads, model="cmflow"):
+    """The reference's CPU path on `pairs` synthetic pairs per step: the unmodified reference Python when it is staged
+    (oracle/ref_model.py), else the oracle port.  Returns (pairs/s, s/step, kind)."""
+    from cmflow_b200.synth import make_pairs, raflow_state_dict, synthetic_state_dict
+    from oracle import ref_model as RM
     torch.set_num_threads(threads)
-    sd = synthetic_state_dict(0)
+    sd = raflow_state_dict(0) if model == "raflow" else synthetic_state_dict(0, temporal=(model == "cmflow_t"))
     pc1, pc2, ft1, ft2, _ = make_pairs(pairs, points, seed=1234)
+    frames = 3 if model == "cmflow_t" else 1
+    interval = torch.full((pairs,), 0.1)
+    if RM.available("cpu"):
+        net = RM.build_model(RM.load("cpu"), model, sd, "cpu")
+        kind = "reference"
+
+        def step():
+            if model == "cmflow_t":
+                g = None
+                for _ in range(frames):
+                    g = net(pc1, pc2, ft1, ft2, None, "test", g)[4]
+            elif model == "raflow":
+                net(pc1, pc2, ft1, ft2, interval)
+            else:
+                net(pc1, pc2, ft1, ft2, None, "test")
+    else:
+        from oracle import cmflow_oracle as O
+        kind = "port"
+
+        def step():
+            if model == "cmflow_t":
+                g = None
+                for _ in range(frames):
+                    g = O.cmflow_forward(sd, pc1, pc2, ft1, ft2, temporal=True, gfeat_prev=g)["gfeat"]
+            elif model == "raflow":
+                O.raflow_forward(sd, pc1, pc2, ft1, ft2, interval)
+            else:
+                O.cmflow_forward(sd, pc1, pc2, ft1, ft2)
     with torch.no_grad():
         for _ in range(warmup):
-            O.cmflow_forward(sd, pc1, pc2, ft1, ft2)
+            step()
         t0 = time.perf_counter()
         for _ in range(steps):
-            O.cmflow_forward(sd, pc1, pc2, ft1, ft2)
+            step()
         dt = time.perf_counter() - t0
-    return pairs * steps / dt, dt / steps
+    return pairs * frames * steps / dt, dt / steps, kind
 
 
-def time_ref_cuda(pairs, points, steps, warmup, dev):
-    """Informational GPU baseline (north_star's "reference's own lib/src CUDA build"): the reference's ball-query kernel compiled UNMODIFIED
-    (oracle/_ref/libpointnet2_ref.so) under the PyTorch-eager, unfused model (oracle/cmflow_oracle.py evaluated on CUDA tensors: cuBLAS fp32
-    for the 1x1 convs, torch.gather grouping, square_distance + topk k-NN as radarflow_util.py:8-30,88-99).  Part of the baseline leg: rank 0,
-    N=1, bounded sample; the oracle stays the checker, never the product path."""
-    import types
-    from cmflow_b200.synth import make_pairs, synthetic_state_dict
-    from oracle import cmflow_oracle as O
-    from oracle import refcuda as R
-    if not R.available():
+def time_ref_cuda(pairs, points, steps, warmup, dev, model="cmflow"):
+    """north_star's "reference's own lib/src CUDA build": the UNMODIFIED reference Python over the reference's own kernels
+    (oracle/ref_model.py: load("cuda")), TF32 off, same batch and point count as the bench line.  Rank 0, N=1; the oracle stays the
+    checker / baseline, never the product path."""
+    from cmflow_b200.synth import make_pairs, raflow_state_dict, synthetic_state_dict
+    from oracle import ref_model as RM
+    if not RM.available("cuda"):
         return None
+    RM.strict_fp32()
+    sd = raflow_state_dict(0) if model == "raflow" else synthetic_state_dict(0, temporal=(model == "cmflow_t"))
+    net = RM.build_model(RM.load("cuda"), model, sd, "cuda")
+    pc1, pc2, ft1, ft2 = (t.to(dev) for t in make_pairs(pairs, points, seed=1234, dense=(points >= 2048))[:4])
+    frames = 3 if model == "cmflow_t" else 1
+    interval = torch.full((pairs,), 0.1, device=dev)
 
-    def knn_point(nsample, xyz, new_xyz):            # radarflow_util.py:88-99 (square_distance + topk)
-        d = -2 * torch.matmul(new_xyz, xyz.permute(0, 2, 1))
-        d = d + torch.sum(new_xyz ** 2, -1).unsqueeze(-1) + torch.sum(xyz ** 2, -1).unsqueeze(1)
-        dist, idx = torch.topk(torch.clamp(d, min=0.0), nsample, dim=-1, largest=False, sorted=False)
-        return idx.int(), dist
-
-    sd = {k: v.to(dev) for k, v in synthetic_state_dict(0).items()}
-    pc1, pc2, ft1, ft2 = (t.to(dev) for t in make_pairs(pairs, points, seed=1234)[:4])
-    saved = O.P
-    O.P = types.SimpleNamespace(ball_query=R.ball_query, knn_point=knn_point)
-    try:
-        with torch.no_grad():
-            for _ in range(warmup):
-                O.cmflow_forward(sd, pc1, pc2, ft1, ft2)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(steps):
-                O.cmflow_forward(sd, pc1, pc2, ft1, ft2)
-            e1.record()
-            torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
-    finally:
-        O.P = saved
-    return {"value": pairs / (ms * 1e-3), "unit": "frame-pairs/s", "ms_per_step": ms, "kind": "reference lib/src ball-query kernel (unmodified, sm_100a) + PyTorch-eager fp32 model on the same GPU",
-            "sample": f"{pairs} pairs/step x {steps} steps (N={points}); the unfused model materialises 34 MB/pair of grouped tensors at K=32"}
+    def step():
+        if model == "cmflow_t":
+            g = None
+            for _ in range(frames):
+                g = net(pc1, pc2, ft1, ft2, None, "test", g)[4]
+        elif model == "raflow":
+            net(pc1, pc2, ft1, ft2, interval)
+        else:
+            net(pc1, pc2, ft1, ft2, None, "test")
+    with torch.no_grad():
+        for _ in range(warmup):
+            step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    peak = torch.cuda.max_memory_allocated()
+    del net
+    torch.cuda.empty_cache()
+    return {"value": pairs * frames / (ms * 1e-3), "unit": "frame-pairs/s", "ms_per_step": ms,
+            "kind": "reference python + lib/src: unmodified models/*.py, radarflow_util.py, lib/pointnet2_utils.py over the reference's lib/src "
+                    "kernels compiled for sm_100a; cuDNN/cuBLAS fp32 with allow_tf32=False",
+            "sample": f"{pairs} pairs/step x {steps} steps (N={points}), {warmup} warm-up", "peak_memory_bytes": peak}
 
 
 def emit(line):
@@ -173,12 +214,14 @@ def main():
                     help="fp32 = strict fp32 FMA kernels; tf32x3 / fp16x3 = tcgen05 tensor cores with a 22-bit hi/lo operand split "
                          "(3 MMAs per product, fp32 accumulate, fp32-class accuracy) in kind::tf32 or kind::f16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-sample", type=int, default=0, help="--impl reference: pairs per step (default: 16 at N=256)")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the sustained / latency_b1 / reference-CUDA legs")
     ap.add_argument("--ncu", action="store_true", help="profiler harness: W+K device forwards only, prints no bench line")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    W = max(args.warmup, 3) if (args.impl == "ours" and not args.ncu) else args.warmup
+    W = max(args.warmup, 3) if not args.ncu else args.warmup
     K = args.steps
     # host threads for the CPU arms: all cores up to 32 -- beyond that the small per-pair matmuls of this workload slow down
     # (measured on the 128-core GPU host: 0.37 pairs/s with 128 threads vs ~10 with 32); the count used is reported in `cores`
@@ -186,19 +229,24 @@ def main():
     mname = {"cmflow": "CMFlow forward", "cmflow_t": "CMFlow-T temporal forward, 3-frame clips,", "raflow": "RaFlow forward"}[args.model]
     workload = f"{mname} synthetic radar pairs N={args.points}, batch={args.batch}/GPU, {args.gpus}xB200"
 
+    config = {"workload": workload, "points": args.points, "pairs_per_gpu": args.batch, "global_batch": args.batch * args.gpus * (3 if args.model == "cmflow_t" else 1),
+              "parallelism": f"dp{args.gpus}",
+              "l2": "GPU arm: 256 MB flush between timed steps, 4 rotating input batches (a step's working set is the multi-GB workspace)"}
     if args.impl == "reference":
         if rank != 0:
             return
-        # bounded sample: ~1 s of CPU work per step at N=256 (the whole --steps K run stays within a few minutes)
-        sample = max(1, min(16, (16 * 256 * 256) // (args.points * args.points)))
-        v, spp = time_cpu_port(sample, args.points, K, min(W, 1), cores)
+        # bounded sample of the workload per step: ~1 s of CPU work at N=256 (the whole --steps K run stays within a few minutes)
+        sample = args.ref_sample or max(1, min(16, (16 * 256 * 256) // (args.points * args.points)))
+        v, spp, kind = time_cpu_reference(sample, args.points, K, W, cores, args.model)
         emit(({
             "impl": "reference", "metric": "frame-pairs/sec CMFlow forward", "value": v, "unit": "frame-pairs/s", "n_gpus": args.gpus,
-            "steps": K, "warmup": min(W, 1), "ms_per_step": spp * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic radar pairs, seeded random-init weights",
-            "config": {"workload": workload, "points": args.points, "pairs_per_step": sample},
-            "cpu_baseline": {"value": v, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample} pairs/step x {K} steps, oracle/cmflow_oracle.py (CPU port of the reference forward), {cores} threads"},
+            "steps": K, "warmup": W, "ms_per_step": spp * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic radar pairs (cmflow_b200/synth.py), seeded random-init weights of the CMFlow architecture",
+            "config": config,
+            "cpu_baseline": {"value": v, "unit": "frame-pairs/s", "cores": cores, "kind": kind,
+                             "sample": f"{sample} of the workload's {args.batch} pairs per step x {K} steps, "
+                                       + ("unmodified reference Python (models/cmflow.py ...) on CPU, pointnet2_cuda answered by oracle/pointops_oracle.c"
+                                          if kind == "reference" else "oracle/cmflow_oracle.py (CPU port of the reference forward)") + f", {cores} threads"},
             "e2e": {"value": v, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -298,8 +346,96 @@ def main():
     for i in range(W):
         fwd_host(i)
     ms_host = timed(fwd_host, K)
+
+    # pipelined end-to-end form (public API: submit_host / wait_host on two staging slots): upload of step i+1 and download of step
+    # i-1 overlap the kernels of step i.  All K steps inside ONE timed region (steps overlap, so there are no per-step events and no
+    # flush in between: a step's working set -- the multi-GB workspace -- is far larger than the 126 MB L2 anyway).
+    ms_pipe = None
+    if args.model == "cmflow":
+        outs = [None, None]
+
+        def pipelined(steps):
+            for i in range(steps):
+                slot = i & 1
+                if i >= 2:
+                    net.wait_host(slot)
+                outs[slot] = net.submit_host(slot, *host_sets[i % NSETS], out=outs[slot])
+            net.wait_host(0); net.wait_host(1)
+        pipelined(max(W, 2))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        pipelined(K)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_pipe = t.item()
     clocks = sampler.stop() if sampler else None
     total_pairs = B * world * FRAMES
+
+    # sustained leg: >= 5 s of back-to-back device-resident forwards, clocks sampled throughout
+    sustained = None
+    if not args.no_extra_legs:
+        s2 = ClockSampler(local) if rank == 0 else None
+        per = max(1e-3, ms_dev / K)
+        n_sus = max(K, int(5200.0 / per) + 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(n_sus):
+            fwd_dev(i)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sustained = {"seconds": t.item() / 1e3, "steps": n_sus, "ms_per_step": t.item() / n_sus,
+                     "value": total_pairs * n_sus / (t.item() / 1e3), "unit": "frame-pairs/s", "clocks": s2.stop() if s2 else None}
+
+    # one pair per call -- the reference's evaluation shape (main.py:203: batch_size=1): device latency and end-to-end host latency,
+    # eager launches vs CUDA-graph replay of the kernel sequence (CMF_HOST_GRAPH=1; needs a capturable, i.e. non-default, stream)
+    latency = None
+    if rank == 0 and not args.no_extra_legs and args.model == "cmflow":
+        one_dev = [tuple(t[:1].contiguous() for t in ds) for ds in dev_sets]
+        one_host = [tuple(t[:1].contiguous().pin_memory() for t in hs) for hs in host_sets]
+        side = torch.cuda.Stream(device=dev)
+        REP = 200
+
+        def lat(fn):
+            with torch.cuda.stream(side):
+                for i in range(20):
+                    fn(i)
+                side.synchronize()
+                ts = []
+                for i in range(REP):
+                    t0 = time.perf_counter()
+                    fn(i)
+                    side.synchronize()
+                    ts.append((time.perf_counter() - t0) * 1e3)
+            ts.sort()
+            return {"p50_ms": ts[len(ts) // 2], "mean_ms": sum(ts) / len(ts), "p95_ms": ts[int(len(ts) * 0.95)]}
+
+        def dev_call(i):
+            with torch.no_grad():
+                net(*one_dev[i % NSETS], None, "test")
+        oh = None
+
+        def host_call(i):
+            nonlocal oh
+            oh = net.forward_host(*one_host[i % NSETS], out=oh)
+        latency = {"pairs": 1, "points": N, "device": lat(dev_call), "launches": net.launches_per_forward()}
+        os.environ["CMF_HOST_GRAPH"] = "0"
+        latency["host_eager"] = lat(host_call)
+        os.environ["CMF_HOST_GRAPH"] = "1"
+        latency["host_graph"] = lat(host_call)
+        from cmflow_b200._lib import lib as _cl
+        latency["graphs_cached"] = _cl().cmf_model_host_graphs(net._handle)
+        os.environ["CMF_HOST_GRAPH"] = "0"
+        latency["note"] = "wall clock around call + stream synchronise on a side stream, 200 calls; device = cmf_model_forward2 on resident inputs, host_* = cmf_model_forward_host2 (pinned H2D + forward + D2H)"
+        fwd_dev(0)                                     # back to the bench shape for the profiled pass
+        torch.cuda.synchronize()
 
     # profiled pass: per-category device time (CUDA events around every launch, same stream)
     prof, cpu = None, None
@@ -325,56 +461,81 @@ def main():
             v["share"] = v["ms_per_step"] / tot_ms
             if v["gflop_per_step"] > 0:
                 v["tflops"] = v["gflop_per_step"] / v["ms_per_step"]
-        dom = "gemm_setconv2_l2"
+        # dominant kernel = the GEMM category with the most device time (set-conv #2's layer-2 kernel; with layer 3 + max fused into it when the
+        # engine runs the fused kernel)
+        gemm_cats = {k: v for k, v in prof.items() if v["gflop_per_step"] > 0}
+        dom = max(gemm_cats, key=lambda k: gemm_cats[k]["ms_per_step"])
         d = prof[dom]
         achieved = d["gflop_per_step"] / d["ms_per_step"]       # GFLOP/ms == TFLOP/s (algorithmic FLOPs: 2*M*K*cols, split passes not counted)
         tc = args.precision != "fp32"
         split = {"tf32x3": ("3xTF32", 6), "fp16x3": ("3xFP16", 3)}.get(args.precision)
         peak_tf = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+        launch_ms = d["ms_per_step"] / max(1, d["launches_per_step"])
         traffic, traffic_src = None, None
-        tj = os.path.join(ROOT, "profiles", "r01f_tc_gemm2_traffic.json")
-        if args.precision == "fp16x3" and B == 256 and N == 256 and os.path.exists(tj):      # the ncu capture is of exactly this workload
-            tjd = json.load(open(tj))
-            traffic, traffic_src = tjd["traffic_bytes_per_launch_avg"], tjd["source"]
-        # algorithmic bytes of the kernel: every (point, neighbour) column gathers one 512-channel fp32 layer-1 row (2 KB) and
-        # writes 256 channels (1 KB); 60 columns per point over the four scales, 4 launches
-        alg_bytes_launch = B * N * 60 * 3072 / max(1, d["launches_per_step"])
-        roofline = {"kernel": (f"tc_gemm2_kernel<SC2_Y1> tcgen05 {split[0]}" if tc else "gemm_nt_kernel<128> fp32 FMA") +
-                              " (set-conv #2 layer 2, 512->256 over N*K neighbour columns, gather fused)" ,
+        for tj in ("r02_dominant_traffic.json", "r01f_tc_gemm2_traffic.json"):
+            tj = os.path.join(ROOT, "profiles", tj)
+            if args.precision == "fp16x3" and B == 256 and N == 256 and os.path.exists(tj):  # an ncu capture of exactly this workload
+                tjd = json.load(open(tj))
+                if tjd.get("category", "gemm_setconv2_l2") == dom:
+                    traffic, traffic_src = tjd["traffic_bytes_per_launch_avg"], tjd["source"]
+                    break
+        # the fused set-conv #2 stage (mse_layer2) moves 1,055 KB in + 262 KB out per pair at N=256 (scaled by N/256)
+        stage_cats = [c for c in prof if c.startswith("gemm_setconv2")]
+        stage_ms = sum(prof[c]["ms_per_step"] for c in stage_cats)
+        stage_bytes = (1055 + 262) * 1024 * (N / 256.0) * B * FRAMES
+        kname = {"gemm_setconv2_l2": "tc_gemm2_kernel<SC2_Y1> (set-conv #2 layer 2, 512->256 over N*K neighbour columns, neighbour gather fused)",
+                 "gemm_setconv2_l2l3": "sc2_fused_kernel (set-conv #2 layers 2+3 and the max over neighbours in one kernel, neighbour gather fused)"}.get(dom, dom)
+        roofline = {"kernel": (f"{kname}, tcgen05 {split[0]}" if tc else "gemm_nt_kernel<128> fp32 FMA (" + dom + ")"), "category": dom,
                     "bound": "tensor", "achieved": achieved, "peak": peak_tf,
                     "unit": "TFLOP/s", "frac": achieved / peak_tf,
                     "peak_source": peaks["source"] + " cuBLAS bf16 (sustained)", "traffic": traffic, "traffic_source": traffic_src,
                     "ceiling": peak_tf / split[1] if tc else 74.5, "frac_of_ceiling": achieved / (peak_tf / split[1] if tc else 74.5),
-                    "hbm": {"algorithmic_bytes_per_launch": alg_bytes_launch,
-                            "achieved_gbs": alg_bytes_launch / (d["ms_per_step"] / max(1, d["launches_per_step"]) * 1e-3) / 1e9,
-                            "peak_gbs": peaks["hbm_gbs"], "frac": alg_bytes_launch / (d["ms_per_step"] / max(1, d["launches_per_step"]) * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                            "note": "not the binding bound (86 flop/B); gathered rows are served by L2, see profiles/r01b_tc_kernels_ncu_full.md"},
-                    "launches_per_step": d["launches_per_step"], "avg_launch_ms": d["ms_per_step"] / max(1, d["launches_per_step"]),
+                    "hbm": {"measured_traffic_gbs": (traffic / (launch_ms * 1e-3) / 1e9) if traffic else None,
+                            "measured_traffic_frac": (traffic / (launch_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if traffic else None,
+                            "peak_gbs": peaks["hbm_gbs"],
+                            "stage": {"categories": stage_cats, "ms_per_step": stage_ms, "algorithmic_bytes_per_step": stage_bytes,
+                                      "algorithmic_gbs": stage_bytes / (stage_ms * 1e-3) / 1e9 if stage_ms > 0 else None,
+                                      "algorithmic_frac": stage_bytes / (stage_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if stage_ms > 0 else None,
+                                      "note": "SURVEY.md 8d compulsory bytes of the fused mse_layer2 stage (1,055 KB in + 262 KB out per pair) over the device "
+                                              "time of the stage's kernels; the stage is tensor-bound (~6,000 flop/B), so this fraction is small by construction"},
+                            "note": "measured_traffic = dram bytes of the dominant kernel (ncu, profiles/) over its live launch time"},
+                    "launches_per_step": d["launches_per_step"], "avg_launch_ms": launch_ms,
                     "note": (f"{split[0]}: three MMAs per algorithmic MAC" + (" (kind::tf32 runs at half the bf16 rate)" if args.precision == "tf32x3" else "") + f" => ceiling = bf16 peak / {split[1]}" if tc else
                              "strict-fp32 FMA build (no tensor cores): the chip's fp32 FMA ceiling is 74.5 TFLOP/s, ~1/19 of this peak")}
-        if not args.no_cpu_baseline and world == 1:
-            cs = max(1, min(16, (16 * 256 * 256) // (N * N)))
-            v, spp = time_cpu_port(cs, N, 12, 1, cores)          # ~10-20 s of CPU work
-            cpu = {"value": v, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
-                   "sample": f"{cs} pairs/step x 12 steps (N={N}), oracle/cmflow_oracle.py CPU port of the reference forward, {cores} threads"}
+        whole_gflop = sum(v["gflop_per_step"] for v in prof.values())
+        roofline["whole_step"] = {"gflop_per_step": whole_gflop, "tflops": whole_gflop / (ms_dev / K), "frac": whole_gflop / (ms_dev / K) / peak_tf}
         ref_cuda = None
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and not args.no_extra_legs and world == 1:
             try:
-                ref_cuda = time_ref_cuda(max(1, min(32, (32 * 256 * 256) // (N * N))), N, 5, 2, dev)
-            except Exception as e:                      # informational only
-                ref_cuda = {"unavailable": repr(e)[:200]}
+                ref_cuda = time_ref_cuda(B, N, 3, 2, dev, args.model)
+            except Exception as e:                      # a baseline leg must not take the bench line down with it
+                ref_cuda = {"unavailable": repr(e)[:300]}
+        if not args.no_cpu_baseline and world == 1:
+            # the reference arm as a subprocess (its CPU shims patch torch.Tensor.cuda -- not in this process): bounded sample, ~10-20 s
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "8", "--warmup", "1", "--points", str(N),
+                                    "--batch", str(B), "--model", args.model], capture_output=True, text=True, timeout=900)
+                cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+            except Exception as e:
+                cpu = {"unavailable": repr(e)[:300]}
         h2d = FRAMES * 4 * B * 3 * N * 4
         d2h = FRAMES * (B * 3 * N * 4 + B * N * 4 + B * 16 * 4 + B * N)
+        e2e_serial = {"value": total_pairs * K / (ms_host / 1e3), "unit": "frame-pairs/s", "ms_per_step": ms_host / K,
+                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": "forward_host (cmf_model_forward_host2): upload, kernels, download, synchronise per call"}
+        e2e = e2e_serial
+        if ms_pipe is not None:
+            e2e = {"value": total_pairs * K / (ms_pipe / 1e3), "unit": "frame-pairs/s", "ms_per_step": ms_pipe / K,
+                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "api": "submit_host / wait_host (cmf_model_submit_host): two staging slots, the upload of step i+1 and the download of step i-1 "
+                          "overlap the kernels of step i; every step's inputs come from pinned host memory and every step's outputs land in host memory"}
         line = {
             "metric": "frame-pairs/sec CMFlow forward", "value": total_pairs * K / (ms_dev / 1e3), "unit": "frame-pairs/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": (f"f32 ({split[0]} split on tcgen05 tensor cores, fp32 accumulate)" if tc else "f32"), "data": "synthetic radar pairs (cmflow_b200/synth.py), seeded random-init weights of the CMFlow architecture",
-            "config": {"workload": workload, "points": N, "pairs_per_gpu": B, "global_batch": total_pairs, "parallelism": f"dp{world}",
-                       "l2": "256 MB flush between timed steps; 4 rotating input batches", "precision_mode": args.precision},
-            "e2e": {"value": total_pairs * K / (ms_host / 1e3), "unit": "frame-pairs/s", "ms_per_step": ms_host / K,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "config": config, "precision_mode": args.precision,
+            "e2e": e2e, "e2e_serial": e2e_serial,
             "gpu_launches": launches * K * FRAMES, "launches_per_step": launches * FRAMES,
-            "clocks": clocks, "roofline": roofline, "kernels": prof, "cpu_baseline": cpu, "ref_cuda_baseline": ref_cuda,
+            "clocks": clocks, "sustained": sustained, "latency_b1": latency, "roofline": roofline, "kernels": prof, "cpu_baseline": cpu, "ref_cuda_baseline": ref_cuda,
             "workspace_bytes": net.workspace_bytes(),
         }
         emit(line)
