@@ -156,16 +156,24 @@ def time_ref_cuda(pairs, points, steps, warmup, dev, model="cmflow"):
     pc1, pc2, ft1, ft2 = (t.to(dev) for t in make_pairs(pairs, points, seed=1234, dense=(points >= 2048))[:4])
     frames = 3 if model == "cmflow_t" else 1
     interval = torch.full((pairs,), 0.1, device=dev)
+    # The reference cannot take the whole batch in one call: its grouped tensor (B,1030,N,32) passes 2^31 elements at B=256, N=256 --
+    # lib/src/group_points_gpu.cu:47-66 indexes it with 32-bit ints and cuDNN refuses such tensors.  The step therefore feeds the same
+    # pairs in the largest power-of-two slices that stay below 2^31 elements (128 pairs at N=256).
+    chunk = 1
+    while chunk * 2 <= pairs and chunk * 2 * 1030 * points * 32 < 2 ** 31:
+        chunk *= 2
 
     def step():
-        if model == "cmflow_t":
-            g = None
-            for _ in range(frames):
-                g = net(pc1, pc2, ft1, ft2, None, "test", g)[4]
-        elif model == "raflow":
-            net(pc1, pc2, ft1, ft2, interval)
-        else:
-            net(pc1, pc2, ft1, ft2, None, "test")
+        for lo in range(0, pairs, chunk):
+            a, b, c, d = (t[lo:lo + chunk] for t in (pc1, pc2, ft1, ft2))
+            if model == "cmflow_t":
+                g = None
+                for _ in range(frames):
+                    g = net(a, b, c, d, None, "test", g)[4]
+            elif model == "raflow":
+                net(a, b, c, d, interval[lo:lo + chunk])
+            else:
+                net(a, b, c, d, None, "test")
     with torch.no_grad():
         for _ in range(warmup):
             step()
@@ -184,7 +192,8 @@ def time_ref_cuda(pairs, points, steps, warmup, dev, model="cmflow"):
     return {"value": pairs * frames / (ms * 1e-3), "unit": "frame-pairs/s", "ms_per_step": ms,
             "kind": "reference python + lib/src: unmodified models/*.py, radarflow_util.py, lib/pointnet2_utils.py over the reference's lib/src "
                     "kernels compiled for sm_100a; cuDNN/cuBLAS fp32 with allow_tf32=False",
-            "sample": f"{pairs} pairs/step x {steps} steps (N={points}), {warmup} warm-up", "peak_memory_bytes": peak}
+            "sample": f"{pairs} pairs/step (fed as slices of {chunk}: the reference's 32-bit indexing and cuDNN stop at 2^31 elements per tensor) x {steps} steps (N={points}), {warmup} warm-up",
+            "peak_memory_bytes": peak}
 
 
 def emit(line):

@@ -198,7 +198,8 @@ def test_rank_deficient_kabsch_is_optimal_and_orthonormal():
     W[2] = 0.0; W[2, 40:42] = 1.0                                  # two points: rank 1
     W = W / W.sum(1, keepdim=True)
     T = torch.empty(nb, 4, 4, device=DEV)
-    check(lib().cmf_weighted_kabsch(nb, N, dptr(A.to(DEV)), dptr(Bp.to(DEV)), dptr(W.to(DEV)), dptr(T), stream_ptr()))
+    Ad, Bd, Wd = A.to(DEV), Bp.to(DEV), W.to(DEV)                  # keep the device copies alive across the asynchronous launch
+    check(lib().cmf_weighted_kabsch(nb, N, dptr(Ad), dptr(Bd), dptr(Wd), dptr(T), stream_ptr()))
     T = T.cpu().double()
     Rg, tg = T[:, :3, :3], T[:, :3, 3:]
     assert torch.isfinite(T).all()
