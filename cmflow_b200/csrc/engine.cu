@@ -102,7 +102,7 @@ enum { SC_H2 = 0, SC_Y2, SC_COUNT = SC_Y2 + 4 };
 
 // What a mode does not touch is not allocated: the strict-fp32 pipeline materialises the gathered layer-1 tensors (Y1: 4.3 GB at 256 pairs of
 // 256 points) that the tensor-core pipelines build inside their GEMM producers, and the unfused set-conv #1 scratch exists only for its A/B switch.
-struct CarveOpts { int mode; bool unfused_sc1, need_h1; };
+struct CarveOpts { int mode; bool unfused_sc1, need_h1, need_y2; };
 void carve(Arena &a, Work &w, int bc, int n, const CarveOpts &o) {
     const size_t bn = (size_t)bc * n;
     const bool tc = o.mode != 0;
@@ -126,7 +126,7 @@ void carve(Arena &a, Work &w, int bc, int n, const CarveOpts &o) {
     w.COST1 = a.take<float>(bn * 512);
     w.PBM = a.take<float>((size_t)bc * 2048); w.P = a.take<float>(bn * 2048);
     if (!tc) { w.Y1 = a.take<float>(bn * 32 * 512); w.Y3 = a.take<float>(bn * 32 * 64); }
-    w.Y2 = a.take<float>(o.mode == 1 ? y2_tiled : (o.mode == 2 ? y2_tiled / 2 : bn * 32 * 256));
+    if (o.need_y2) w.Y2 = a.take<float>(o.mode == 1 ? y2_tiled : (o.mode == 2 ? y2_tiled / 2 : bn * 32 * 256));
     w.PROP = a.take<float>(bn * 256); w.GP = a.take<float>((size_t)bc * 256);
     w.GI = a.take<float>((size_t)bc * 768); w.GH = a.take<float>((size_t)bc * 768);
     w.GNEW = a.take<float>((size_t)bc * 256); w.ZERO = a.take<float>((size_t)bc * 256);
@@ -145,7 +145,7 @@ struct cmf_model {
     float *d_blob = nullptr;
     std::vector<const float *> seg;
     std::vector<SegShape> shape;
-    char *ws = nullptr; size_t ws_bytes = 0; int cap_bc = 0, cap_n = 0, ws_mode = 0;     // arena carved for cap_bc pairs x cap_n points in arithmetic mode ws_mode
+    char *ws = nullptr; size_t ws_bytes = 0; int cap_bc = 0, cap_n = 0, ws_mode = -1;    // arena carved for cap_bc pairs x cap_n points under carve signature ws_mode (mode + fusion switches)
     Work w{};
     // staging for the host entry points: two slots so that copies of neighbouring calls overlap the kernels (cmf_model_submit_host)
     struct HostSlot { float *d_in = nullptr; char *d_out = nullptr; size_t in_floats = 0, out_bytes = 0;
@@ -222,10 +222,10 @@ static GemmArgs mk(const float *W, int ldw, const float *X, int ldx, float *Out,
         ++m->launches;                                              \
     } while (0)
 
-enum { C_SEARCH = 0, C_GEMM_SC1, C_GEMM_FC_HOIST, C_GEMM_FC_MLP, C_GEMM_SC2_HOIST, C_GEMM_SC2_L2, C_GEMM_SC2_L3,
+enum { C_SEARCH = 0, C_GEMM_SC1, C_GEMM_FC_HOIST, C_GEMM_FC_MLP, C_GEMM_SC2_HOIST, C_GEMM_SC2_L2, C_GEMM_SC2_L3, C_GEMM_SC2_L2L3,
        C_GEMM_POINTWISE, C_GATHER, C_REDUCE, C_HEAD_KABSCH, C_COUNT };
 static const char *const kCatNames[C_COUNT] = {"search", "gemm_setconv1", "gemm_flowembed_hoist", "gemm_flowembed_mlp",
-    "gemm_setconv2_hoist", "gemm_setconv2_l2", "gemm_setconv2_l3", "gemm_pointwise", "gather_build", "reduce", "head_kabsch"};
+    "gemm_setconv2_hoist", "gemm_setconv2_l2", "gemm_setconv2_l3", "gemm_setconv2_l2l3", "gemm_pointwise", "gather_build", "reduce", "head_kabsch"};
 static double gflops(const GemmArgs &g) { return 2.0 * g.M * (double)g.K * g.cols; }
 static double gflops(const GemmBatch &gb) { double f = 0; for (int i = 0; i < gb.count; ++i) f += gflops(gb.g[i]); return f; }
 
@@ -308,10 +308,18 @@ static int ensure_tc_weights(cmf_model *m, int fmt) {
     return CMF_OK;
 }
 
+static bool sc2_fused(const cmf_model *m) {              // CMF_SC2_FUSED=0: the two-kernel set-conv #2 of round 1 (A/B testing)
+    const char *e = getenv("CMF_SC2_FUSED");
+    return m->tc == 2 && cmf_tc_pair_enabled() && !(e && e[0] == '0');
+}
 static bool wsum_fused(const cmf_model *m) { return m->tc && cmf_tc_pair_enabled() && !getenv("CMF_NO_WSUM"); }
 static CarveOpts carve_opts(const cmf_model *m) {
     const bool chain = m->tc == 2 && m->chain;
-    return CarveOpts{m->tc, !chain && !m->fused_sc1, !wsum_fused(m)};
+    return CarveOpts{m->tc, !chain && !m->fused_sc1, !wsum_fused(m), !sc2_fused(m)};
+}
+static int carve_sig(const cmf_model *m) {
+    const CarveOpts o = carve_opts(m);
+    return o.mode | (o.unfused_sc1 ? 8 : 0) | (o.need_h1 ? 16 : 0) | (o.need_y2 ? 32 : 0);
 }
 static size_t chunk_bytes(const cmf_model *m, int bc, int n) {
     Arena a; Work w;
@@ -327,7 +335,7 @@ static int ensure_workspace(cmf_model *m, int b, int n) {
     // the reference's evaluation loop feeds one pair at a time with a different point count per frame (dataset/vod.py:92-93,
     // main.py:203), which must not cost a cudaFree + cudaMalloc per frame.
     const bool env_chunk = getenv("CMF_CHUNK_PAIRS") != nullptr;
-    if (m->ws && m->ws_mode != m->tc) { cudaFree(m->ws); m->ws = nullptr; m->ws_bytes = 0; m->cap_bc = m->cap_n = 0; drop_graphs(m); }   // carved for another mode
+    if (m->ws && m->ws_mode != carve_sig(m)) { cudaFree(m->ws); m->ws = nullptr; m->ws_bytes = 0; m->cap_bc = m->cap_n = 0; drop_graphs(m); }   // carved for another mode
     if (m->ws && n <= m->cap_n && b <= m->cap_bc && !env_chunk) return CMF_OK;       // (also the path taken under stream capture)
     int n_cap = n;
     if (m->ws && n > m->cap_n && n < 2048) n_cap = (n + 127) & ~127;                  // growing point counts: leave headroom instead of growing again next frame
@@ -362,7 +370,7 @@ static int ensure_workspace(cmf_model *m, int b, int n) {
         m->cap_bc = m->cap_n = 0; m->ws_bytes = 0; m->ws = nullptr;
         return CMF_ERR_NOMEM;
     }
-    m->ws_bytes = bytes; m->cap_bc = bc; m->cap_n = n_cap; m->ws_mode = m->tc;
+    m->ws_bytes = bytes; m->cap_bc = bc; m->cap_n = n_cap; m->ws_mode = carve_sig(m);
     Arena a; a.base = m->ws;
     carve(a, m->w, bc, n_cap, carve_opts(m));
     CMF_CUDA(cudaMemset(m->w.ZERO, 0, (size_t)bc * 256 * sizeof(float)));
@@ -550,6 +558,11 @@ static int forward_chunk(cmf_model *m, int bc, int n, int n2, const float *pc1, 
                 // |relu(P[j] + Wx.rel)| <= max|P (this scale)| + max_c |Wx[c]|_1 * radius   (every rel component is below the ball radius)
                 tc_bound(ta_, m->wx_l1[s] * RADII[s], AM(AM_P0 + s), 1.f);
                 ta_.out_mul = m->m2_w2_l1[s]; ta_.out_add = m->m2_t2_max[s]; ta_.out_scale_store = F ? SC(SC_Y2 + s) : nullptr;
+                if (sc2_fused(m)) {      // layers 2 + 3 + max over K in one kernel: the 256-channel layer-2 output stays in tensor memory
+                    RUN(C_GEMM_SC2_L2L3, tflops(ta_, 512) + 2.0 * 64 * 256.0 * (double)ta_.cols,
+                        cmf_launch_sc2_fused(ta_, T.m2_w3[s].wt, T.m2_w3[s].ainv, S(sb + 3), w.M64 + s * 64, 256, st));
+                    continue;
+                }
                 RUN(C_GEMM_SC2_L2, tflops(ta_, 512), cmf_launch_tc_auto(ta_, st));
             }
             {   // layer 3 (256->64) with ReLU + max over the K neighbours fused into the TMEM epilogue; B operand bulk-copied
@@ -997,7 +1010,7 @@ extern "C" const void *cmf_model_tap(const cmf_model *m, const char *name) {
     struct { const char *n; const void *p; } tab[] = {
         {"E", w.E}, {"f2", w.F2}, {"g1", w.G1}, {"g2", w.G2}, {"prop", w.PROP}, {"flow", w.FLOW},
         {"bq1", w.BQ1}, {"bq2", w.BQ2}, {"knn12", w.KNN12}, {"knn11", w.KNN11}, {"gp", w.GP}, {"P", w.P},
-        {"cost1", w.COST1}, {"u1", w.U1}, {"u2", w.U2}, {"hd3", w.HD3}};
+        {"cost1", w.COST1}, {"u1", w.U1}, {"u2", w.U2}, {"hd3", w.HD3}, {"m64", w.M64}};
     for (auto &t : tab)
         if (!strcmp(t.n, name)) return t.p;
     return nullptr;

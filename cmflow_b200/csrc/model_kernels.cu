@@ -820,8 +820,31 @@ __device__ void polar_rotation_3x3(const double H[3][3], double R[3][3]) {
         double detV = V[0][0] * (V[1][1] * V[2][2] - V[1][2] * V[2][1]) - V[0][1] * (V[1][0] * V[2][2] - V[1][2] * V[2][0]) + V[0][2] * (V[1][0] * V[2][1] - V[1][1] * V[2][0]);
         U[0][bad] = cx; U[1][bad] = cy; U[2][bad] = cz;      // det(U) = +1 with (a,b,bad) cyclic
         if (detV < 0) { U[0][bad] = -cx; U[1][bad] = -cy; U[2][bad] = -cz; }
-    } else if (nbad >= 2) {                                  // rank <= 1: rotation undefined; return identity-like V V^T
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) U[r][c] = V[r][c];
+    } else if (nbad >= 2) {
+        // rank <= 1: V U^T is not unique (the reference's answer depends on LAPACK's choice of the null-space bases).  Any rotation that takes
+        // the one defined left singular vector u to its right partner v is optimal; return the smallest such rotation (identity for H = 0).
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[r][c] = (r == c) ? 1.0 : 0.0;
+        if (nbad == 3) return;
+        int gc = 0;
+        for (int c = 0; c < 3; ++c) if (nrm[c] > 1e-13 * nmax && nrm[c] > 0) gc = c;
+        const double u[3] = {U[0][gc], U[1][gc], U[2][gc]}, v[3] = {V[0][gc], V[1][gc], V[2][gc]};
+        const double cth = u[0] * v[0] + u[1] * v[1] + u[2] * v[2];
+        if (cth > -1.0 + 1e-12) {                            // Rodrigues: R = I + [k]x + [k]x^2 / (1 + cos), k = u x v
+            const double k[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+            const double Kx[3][3] = {{0, -k[2], k[1]}, {k[2], 0, -k[0]}, {-k[1], k[0], 0}};
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) {
+                    double k2 = 0; for (int j = 0; j < 3; ++j) k2 += Kx[r][j] * Kx[j][c];
+                    R[r][c] += Kx[r][c] + k2 / (1.0 + cth);
+                }
+        } else {                                             // u = -v: half turn about any axis n perpendicular to u, R = 2 n n^T - I
+            const int ax = fabs(u[0]) < fabs(u[1]) ? (fabs(u[0]) < fabs(u[2]) ? 0 : 2) : (fabs(u[1]) < fabs(u[2]) ? 1 : 2);
+            double e[3] = {0, 0, 0}; e[ax] = 1.0;
+            double n[3] = {u[1] * e[2] - u[2] * e[1], u[2] * e[0] - u[0] * e[2], u[0] * e[1] - u[1] * e[0]};
+            const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[r][c] = 2.0 * n[r] * n[c] / (nn * nn) - (r == c ? 1.0 : 0.0);
+        }
+        return;
     }
     double Z[3][3];
     for (int r = 0; r < 3; ++r)

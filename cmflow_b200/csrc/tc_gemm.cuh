@@ -57,6 +57,10 @@ int cmf_tc_tile_weights_f16(const float *W, int ldw, int M, int K, float *Wt, fl
 int cmf_launch_tc_gemm(const TcArgs &a, cudaStream_t st);      // one CTA per 128 x 256 tile
 int cmf_launch_tc_gemm2(const TcArgs &a, cudaStream_t st);     // CTA pair (cta_group::2) per 256 x 256 tile; needs M % 256 == 0
 int cmf_tc_pair_enabled();
+// set-conv #2 layers 2 + 3 + max over the K neighbours in one kernel (tc_sc2.cu; 3xFP16 only).  l2 = the layer-2 arguments exactly as for
+// cmf_launch_tc_gemm2 with the SC2_Y1 producer (its Out / out_tiled / out_scale_store are ignored); Wt3 = tiled 64 x 256 layer-3 weights with
+// per-channel un-scale a_inv3 and bias3; out[point][0..63] (row stride ldo floats) = max_k relu(W3 relu(W2 x_k + b2) + b3)
+int cmf_launch_sc2_fused(const TcArgs &l2, const float *Wt3, const float *a_inv3, const float *bias3, float *out, int ldo, cudaStream_t st);
 int cmf_launch_tc_auto(const TcArgs &a, cudaStream_t st);      // pair kernel when M % 256 == 0 (unless CMF_TC2=0), else the one-CTA kernel
 
 // ---- narrow MLP chains with the activations as the A operand (tc_chain.cu; 3xFP16 only) ---------------------------------------------

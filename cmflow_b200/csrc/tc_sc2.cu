@@ -1,0 +1,532 @@
+// tc_sc2.cu -- set-conv #2 (mse_layer2, radarflow_util.py:144-155) after the hoisted first layer: neighbour gather + layer 2 (512 -> 256)
+// + layer 3 (256 -> 64) + max over the K neighbours in ONE kernel (3xFP16 split precision, fp32 accumulation in TMEM).
+//
+// Round 1 ran this stage as two kernels per scale: layer 2 wrote its 256-channel output pre-split to HBM (4 GB per step at 256 pairs)
+// and a second, HBM-bound kernel read it back for layer 3 + max.  Here layer 2's output never leaves the SM pair:
+//
+//   * ORIENTATION.  The ACTIVATIONS are the A operand (M = 256 neighbour columns per CTA pair, 128 per CTA), the weights the B operand
+//     (N = 256 output channels, 128 rows staged by each CTA: cta_group::2 splits B across the pair).  The shared-memory stage of a
+//     CTA holds the same bytes as in tc_gemm2.cu -- 128 weight rows + 128 activation rows, hi and lo -- only the two descriptors swap
+//     places in the MMA.  The accumulator D2[128 lanes x 256 columns] of a CTA then has one LANE per neighbour column and the 256
+//     channels of that column along the TMEM columns.
+//   * LAYER 3 READS ITS A OPERAND FROM TMEM.  An epilogue thread owns one lane = one neighbour column: it loads 16 channels at a time,
+//     applies un-scale / bias / ReLU, splits into fp16 hi + lo and writes the 8 + 8 packed 32-bit words back over the 16 fp32 columns it
+//     just read (tcgen05.st): D2 turns IN PLACE into the K-major fp16 A operand of layer 3, one K=16 step per 16 columns (hi at +0,
+//     lo at +8).  tcgen05.mma with A in TMEM and W3 (64 x 256, resident in shared memory, 32 rows per CTA) as B accumulates
+//     D3[128 x 64]; max over a point's K consecutive lanes by warp shuffles; one 256-byte row per point goes to HBM.
+//   * TMEM BUDGET.  Two 256-column D2 buffers use all 512 columns, so D3 has no columns of its own: it lives in columns 0..63 of the SAME
+//     buffer.  The epilogue first takes channels 0..63 into registers (already converted: 64 packed words), which frees those columns
+//     for D3; channels 64..255 are converted in place and multiplied first; when the K steps of channels 64..127 have retired, their
+//     columns take the held channels 0..63 for the last four K steps.
+//   * Layer-3 MMAs are issued by the first MMA-issuer warp between its main-loop stages; all of its waits poll for pending layer-3 work
+//     (the main loop's next-but-one tile needs the buffer back, so a blocking wait there would deadlock).
+//
+// Cluster of 2 CTAs, 512 threads each -- roles as in tc_gemm2.cu: w0 bulk-copy issuer (weights), w1 / w3 MMA issuers (leader) or
+// forwarders (peer), w2 row-context filler, w4-7 epilogue, w8-15 producers (gather + rel-xyz term + ReLU + fp16 split).
+#include "tc_dev.cuh"
+
+using namespace tcdev;
+
+namespace {
+
+constexpr int HALF_ROWS = 128;                       // activation rows (neighbour columns) per CTA
+constexpr int TILE_BYTES = 128 * 64;                 // 128 rows x 32 halfs: 8 KB
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;          // W hi, W lo, X hi, X lo: 32 KB
+constexpr int NSTAGE = 4;
+constexpr int NTHREADS = 512;
+constexpr int PF = 3;                                // cp.async staging ring depth (K blocks)
+constexpr int STG_BYTES = PF * 4 * 256 * 16;         // 48 KB: 4 rows x 16 bytes per producer thread per K block
+constexpr int W3_KB = 8;                             // 256 channels = 8 K blocks of 32
+constexpr int W3_BYTES = W3_KB * 2 * 2048;           // this CTA's 32 rows of W3: per K block {hi 2 KB, lo 2 KB}
+constexpr int OFF_STG = NSTAGE * STAGE_BYTES;        // 131072
+constexpr int OFF_W3 = OFF_STG + STG_BYTES;          // 180224
+constexpr int OFF_BAR = OFF_W3 + W3_BYTES;           // 212992
+constexpr int OFF_SW = OFF_BAR + 256;                // rel-xyz weights: 16 K blocks x 24 float4 = 6 KB
+constexpr int OFF_CS1 = OFF_SW + 6144;               // gathered-row pointers [3][128]
+constexpr int OFF_GEO = OFF_CS1 + 3 * HALF_ROWS * 8; // {dx, dy, dz, scale} [3][128]
+constexpr int OFF_AB2 = OFF_GEO + 3 * HALF_ROWS * 16;// {a_inv, bias} of the 256 layer-2 channels (float2)
+constexpr int OFF_AB3 = OFF_AB2 + 256 * 8;           // {a_inv, bias} of the 64 layer-3 channels
+constexpr int SMEM_BYTES = OFF_AB3 + 64 * 8 + 1024;  // + alignment slack = 232192 <= 232448
+static_assert(SMEM_BYTES <= 232448, "shared-memory plan exceeds 227 KB");
+constexpr uint32_t IDESC_L2 = make_idesc(256, 256, 1), IDESC_L3 = make_idesc(256, 64, 1);
+
+struct Sc2Args {
+    TcArgs g;                        // layer 2: tiled W2 (Wt, a_inv, bias), SC2_Y1 producer fields, scales (bs_*, out_mul / out_add), cols, cols_per_pair, ksamp
+    const float *Wt3, *a_inv3, *bias3;   // layer 3: tiled W3 (one 128-row block, 8 K blocks), per-channel un-scale, bias
+    float *out; int ldo;             // out[point][0..63]
+};
+
+__device__ __forceinline__ void commit2_mc(uint32_t bar) {       // arrive on `bar` in BOTH CTAs when all prior MMAs of this thread retire
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mma2_ss(uint32_t d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma2_ss_keep(uint32_t d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ void mma2_ss_reuse(uint32_t d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+}
+// A operand in tensor memory (K-major, two fp16 per 32-bit column, one lane per row), B from shared memory
+__device__ __forceinline__ void mma2_ts(uint32_t d, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// non-blocking probe of an mbarrier phase (bounded suspend: returns false when the phase has not completed within ~0.5 us)
+__device__ __forceinline__ bool mbar_probe(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity), "r"(500u) : "memory");
+    return done != 0;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+sc2_fused_kernel(const Sc2Args s) {
+    const TcArgs &a = s.g;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *smem = smem_raw + (base - raw);
+    const uint32_t bar0 = base + OFF_BAR;
+    auto full_bar = [&](int i) { return bar0 + 8 * i; };                 // [4] local: bulk copy (expect_tx) + 8 producer warps
+    auto pfull_bar = [&](int i) { return bar0 + 32 + 8 * i; };           // [4] leader: the peer's half of the stage is complete
+    auto empty_bar = [&](int i) { return bar0 + 64 + 8 * i; };           // [4] both: stage consumed (MMA commit, multicast)
+    auto tfull_bar = [&](int i) { return bar0 + 96 + 8 * i; };           // [2] both: layer-2 accumulator complete (2 issuers)
+    auto tempty_bar = [&](int i) { return bar0 + 112 + 8 * i; };         // [2] leader: 4 + 4 epilogue warps have drained the buffer
+    auto a3r_bar = [&](int acc, int g) { return bar0 + 128 + 8 * (acc * 3 + g); };   // [2][3] leader: layer-3 operand group written (4 + 4 warps)
+    auto g1done_bar = [&](int i) { return bar0 + 176 + 8 * i; };         // [2] both: the K steps of channels 64..127 have retired
+    auto d3full_bar = [&](int i) { return bar0 + 192 + 8 * i; };         // [2] both: layer-3 accumulator complete
+    const uint32_t w3_bar = bar0 + 208;                                  // local: resident W3 slice has landed
+    volatile uint32_t *turn = reinterpret_cast<volatile uint32_t *>(smem + OFF_BAR + 232);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 240);
+    float4 *sW = reinterpret_cast<float4 *>(smem + OFF_SW);
+    const float **cs1 = reinterpret_cast<const float **>(smem + OFF_CS1);
+    float4 *cgeo = reinterpret_cast<float4 *>(smem + OFF_GEO);
+    float2 *sAB2 = reinterpret_cast<float2 *>(smem + OFF_AB2);
+    float2 *sAB3 = reinterpret_cast<float2 *>(smem + OFF_AB3);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const long long ntiles = (a.cols + 255) / 256;                       // M = 256 output channels: one 256-row tile covers them all
+    const long long cl_id = blockIdx.x >> 1, n_cl = gridDim.x >> 1;
+    const int nks = a.k_blocks;                                          // K blocks of 32 (512 / 32 = 16)
+
+    // rel-xyz weights transposed for the producers: sW[(kb*3 + comp)*8 + q] = {Wx[c][comp], c = kb*32 + q*4 .. +3} (see tc_gemm2.cu)
+    for (int i = threadIdx.x; i < nks * 24; i += NTHREADS) {
+        const int kb_ = i / 24, comp = (i >> 3) % 3, q_ = i & 7;
+        const float *w = a.Wsmall + (size_t)(kb_ * PK + q_ * 4) * 4 + comp;
+        sW[i] = make_float4(__ldg(w), __ldg(w + 4), __ldg(w + 8), __ldg(w + 12));
+    }
+    for (int i = threadIdx.x; i < 256; i += NTHREADS) sAB2[i] = make_float2(__ldg(a.a_inv + i), a.bias ? __ldg(a.bias + i) : 0.f);
+    if (threadIdx.x < 64) sAB3[threadIdx.x] = make_float2(__ldg(s.a_inv3 + threadIdx.x), s.bias3 ? __ldg(s.bias3 + threadIdx.x) : 0.f);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(full_bar(i), 1 + 8); mbar_init(pfull_bar(i), 1); mbar_init(empty_bar(i), 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(tfull_bar(i), 2); mbar_init(tempty_bar(i), 8); mbar_init(g1done_bar(i), 1); mbar_init(d3full_bar(i), 1);
+            for (int g = 0; g < 3; ++g) mbar_init(a3r_bar(i, g), 8);
+        }
+        mbar_init(w3_bar, 1);
+        *turn = 0u;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    cluster_sync_all();                         // both CTAs: barriers initialised, TMEM allocated, tables visible
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== bulk-copy issuer: the resident W3 slice once, then this CTA's 128 rows of W2 per stage =====
+        if (lane == 0) {
+            mbar_arrive_expect_tx(w3_bar, W3_BYTES);
+            for (int kb = 0; kb < W3_KB; ++kb)
+                for (int hl = 0; hl < 2; ++hl)
+                    bulk_g2s(base + OFF_W3 + (kb * 2 + hl) * 2048,
+                             reinterpret_cast<const uint8_t *>(s.Wt3) + (size_t)(kb * 2 + hl) * TILE_BYTES + rank * 2048, 2048, w3_bar);
+            int stage = 0; uint32_t phase = 0;
+            for (long long t = cl_id; t < ntiles; t += n_cl)
+                for (int ks = 0; ks < nks; ++ks) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint8_t *src = reinterpret_cast<const uint8_t *>(a.Wt) + ((size_t)rank * nks + ks) * (2 * TILE_BYTES);
+                    mbar_arrive_expect_tx(full_bar(stage), 2 * TILE_BYTES);
+                    bulk_g2s(base + stage * STAGE_BYTES, src, 2 * TILE_BYTES, full_bar(stage));
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+        }
+    } else if (leader && (warp == 1 || warp == 3)) {
+        // ===== MMA issuers (leader CTA): two warps alternate stages (see tc_gemm2.cu); warp 1 also issues layer 3 =====
+        const int me = warp == 3 ? 1 : 0;
+        const long long my_tiles = cl_id < ntiles ? (ntiles - cl_id + n_cl - 1) / n_cl : 0;
+        long long l3_tile = 0; int l3_grp = 0;                      // next layer-3 group to issue (issuer 0 only)
+        bool w3_ready = false;
+        // one pending layer-3 group, if its operand has been written: group 0 = K steps 4..7 (channels 64..127, in place), group 1 = K steps
+        // 8..15 (channels 128..255), group 2 = K steps 0..3 (channels 0..63, parked in the columns of group 0 once that has retired)
+        auto serve_l3 = [&]() -> bool {
+            if (me != 0 || l3_tile >= my_tiles) return false;
+            const int acc3 = (int)(l3_tile & 1);
+            const uint32_t ph3 = (uint32_t)((l3_tile >> 1) & 1);
+            if (!mbar_probe(a3r_bar(acc3, l3_grp), ph3)) return false;
+            if (!w3_ready) { mbar_wait(w3_bar, 0); w3_ready = true; }
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t d3 = tmem_base + acc3 * 256;
+                const int ks0 = l3_grp == 0 ? 4 : (l3_grp == 1 ? 8 : 0), ks1 = l3_grp == 0 ? 8 : (l3_grp == 1 ? 16 : 4);
+                for (int ks = ks0; ks < ks1; ++ks) {
+                    const uint32_t a_hi = tmem_base + acc3 * 256 + (l3_grp == 2 ? 64 : 0) + 16 * ks, a_lo = a_hi + 8;
+                    const uint32_t wb = base + OFF_W3 + (ks >> 1) * 4096;
+                    const uint64_t b_hi = make_desc(wb) + (uint64_t)((ks & 1) * 2), b_lo = make_desc(wb + 2048) + (uint64_t)((ks & 1) * 2);
+                    mma2_ts(d3, a_lo, b_hi, IDESC_L3, (l3_grp == 0 && ks == ks0) ? 0u : 1u);
+                    mma2_ts(d3, a_hi, b_lo, IDESC_L3, 1u);
+                    mma2_ts(d3, a_hi, b_hi, IDESC_L3, 1u);
+                }
+                if (l3_grp == 0) commit2_mc(g1done_bar(acc3));
+                if (l3_grp == 2) commit2_mc(d3full_bar(acc3));
+            }
+            __syncwarp();
+            if (++l3_grp == 3) { l3_grp = 0; ++l3_tile; }
+            return true;
+        };
+        // issuer 0 never blocks without looking after layer 3: the buffer the main loop waits for comes back only when its layer 3 is done
+        auto wait_serving = [&](uint32_t bar, uint32_t parity) {
+            unsigned spins = 0; unsigned long long t0 = 0ull;
+            while (!mbar_probe(bar, parity)) { if (!serve_l3()) watchdog(spins, t0); }
+        };
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        uint32_t g = 0;
+        for (long long t = cl_id; t < ntiles; t += n_cl) {
+            const uint32_t d2 = tmem_base + acc * 256;
+            for (int ks = 0; ks < nks; ++ks, ++g) {
+                if ((int)(g & 1u) == me) {
+                    if (me == 0) {
+                        if (ks == 0) wait_serving(tempty_bar(acc), acc_phase ^ 1);
+                        wait_serving(full_bar(stage), phase);
+                        wait_serving(pfull_bar(stage), phase);
+                    } else {
+                        if (ks == 0) mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1);
+                        mbar_wait(full_bar(stage), phase);
+                        mbar_wait_cluster(pfull_bar(stage), phase);
+                    }
+                    tc_fence_after();
+                    {
+                        unsigned spins = 0; unsigned long long t0 = 0ull;
+                        while (*turn != g) { if (!serve_l3()) watchdog(spins, t0); }       // the other issuer hands the pipe over in stage order
+                    }
+                    if (lane == 0) {
+                        const uint32_t sa = base + stage * STAGE_BYTES;
+                        const uint64_t w_hi = make_desc(sa), w_lo = make_desc(sa + TILE_BYTES);
+                        const uint64_t x_hi = make_desc(sa + 2 * TILE_BYTES), x_lo = make_desc(sa + 3 * TILE_BYTES);
+#pragma unroll
+                        for (int k16 = 0; k16 < 2; ++k16) {
+                            const uint64_t adv = (uint64_t)(k16 * 2);             // 32 bytes = 16 halfs, in 16-byte descriptor units
+                            mma2_ss(d2, x_lo + adv, w_hi + adv, IDESC_L2, (ks | k16) ? 1u : 0u);
+                            mma2_ss_keep(d2, x_hi + adv, w_lo + adv, IDESC_L2);
+                            mma2_ss_reuse(d2, x_hi + adv, w_hi + adv, IDESC_L2);
+                        }
+                        *turn = g + 1;
+                        commit2_mc(empty_bar(stage));
+                        if (ks >= nks - 2 || nks == 1) commit2_mc(tfull_bar(acc));       // both issuers' MMAs of the tile must have retired
+                    }
+                    __syncwarp();
+                    serve_l3();
+                } else if (nks == 1 && lane == 0) {
+                    commit2_mc(tfull_bar(acc));
+                }
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (me == 0) {                                      // drain: layer 3 of the last tile(s)
+            unsigned spins = 0; unsigned long long t0 = 0ull;
+            while (l3_tile < my_tiles) { if (!serve_l3()) watchdog(spins, t0); }
+        }
+    } else if (warp == 2) {
+        // ===== row-context filler: neighbour index -> gathered-row pointer, rel-xyz, fp16 scale, two tiles ahead of the producers =====
+        auto fill_ctx = [&](long long tt, int buf) {
+            RowCtx rc[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rc[k] = make_row(a, tt * 256 + rank * HALF_ROWS + lane + 32 * k);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = buf * HALF_ROWS + lane + 32 * k;
+                cs1[r] = rc[k].valid ? rc[k].src1 : nullptr;
+                cgeo[r] = make_float4(rc[k].dx, rc[k].dy, rc[k].dz, rc[k].valid ? rc[k].scale : 0.f);
+            }
+        };
+        long long t = cl_id;
+        if (t < ntiles) {
+            int buf = 0;
+            fill_ctx(t, 0);
+            if (t + n_cl < ntiles) fill_ctx(t + n_cl, 1);
+            asm volatile("bar.sync 1, 288;" ::: "memory");
+            while (true) {
+                const long long tn = t + n_cl;
+                if (tn + n_cl < ntiles) fill_ctx(tn + n_cl, buf == 0 ? 2 : buf - 1);
+                if (tn >= ntiles) break;
+                asm volatile("bar.sync 1, 288;" ::: "memory");
+                t = tn; buf = buf == 2 ? 0 : buf + 1;
+            }
+        }
+    } else if (warp == 1 || warp == 3) {
+        // ===== forwarders (peer CTA): relay "my half of stage s is complete" to the leader =====
+        const int me = warp == 3 ? 1 : 0;
+        int stage = 0; uint32_t phase = 0;
+        uint32_t g = 0;
+        for (long long t = cl_id; t < ntiles; t += n_cl)
+            for (int ks = 0; ks < nks; ++ks, ++g) {
+                if ((int)(g & 1u) == me) {
+                    mbar_wait(full_bar(stage), phase);
+                    if (lane == 0) mbar_arrive_remote_relaxed(pfull_bar(stage), 0);
+                    __syncwarp();
+                }
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+    } else if (warp >= 4 && warp < 8) {
+        // ===== epilogue: this thread owns lane q*32 + lane of the CTA's accumulator = one neighbour column =====
+        const int q = warp & 3;
+        const int K = a.ksamp;
+        int acc = 0; uint32_t acc_phase = 0;
+        auto arrive_leader = [&](uint32_t bar) { if (lane == 0) { if (leader) mbar_arrive(bar); else mbar_arrive_remote(bar, 0); } };
+        for (long long t = cl_id; t < ntiles; t += n_cl) {
+            const long long c = t * 256 + rank * HALF_ROWS + q * 32 + lane;
+            const bool valid = c < a.cols;
+            const long long pair = (valid ? c : a.cols - 1) / a.cols_per_pair;
+            const float osc = out_scale_of(a, pair);                               // power of two: layer-3 operand scale of this pair
+            const float k2 = __frcp_rn(b_scale_of(a, pair)) * osc;                  // accumulator un-scale (times a_inv[ch]) with the output scale folded in
+            const float2 k2v = make_float2(k2, k2), oscv = make_float2(osc, osc);
+            const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
+            // 16 accumulator columns (channels ch0 .. ch0+15) -> relu(acc * a_inv * k2 + bias * osc) -> 8 packed hi + 8 packed lo words
+            auto convert16 = [&](const uint32_t (&r)[16], int ch0, uint32_t *hi, uint32_t *lo) {
+                const float4 *ab = reinterpret_cast<const float4 *>(sAB2 + ch0);      // {a_inv[c], bias[c], a_inv[c+1], bias[c+1]}: broadcast reads
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 w = ab[i];
+                    float2 v = __ffma2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])),
+                                          __fmul2_rn(make_float2(w.x, w.z), k2v), __fmul2_rn(make_float2(w.y, w.w), oscv));
+                    v = make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f));
+                    split_f16x2(v, hi[i], lo[i]);
+                }
+            };
+            mbar_wait_cluster(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            uint32_t Hh[32], Hl[32];                                 // channels 0..63, converted; they leave their columns to D3
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                uint32_t r[16];
+                tmem_ld16(tcol + 16 * ks, r);
+                convert16(r, 16 * ks, Hh + 8 * ks, Hl + 8 * ks);
+            }
+#pragma unroll 1
+            for (int grp = 0; grp < 2; ++grp) {
+                const int ks0 = grp == 0 ? 4 : 8, ks1 = grp == 0 ? 8 : 16;
+#pragma unroll 2
+                for (int ks = ks0; ks < ks1; ++ks) {
+                    uint32_t r[16], hi[8], lo[8];
+                    tmem_ld16(tcol + 16 * ks, r);
+                    convert16(r, 16 * ks, hi, lo);
+                    tmem_st8(tcol + 16 * ks, hi);                    // in place: the 16 fp32 columns become K step ks of layer 3's A operand
+                    tmem_st8(tcol + 16 * ks + 8, lo);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                arrive_leader(a3r_bar(acc, grp));
+            }
+            mbar_wait_cluster(g1done_bar(acc), acc_phase);           // the K steps that read columns 64..127 have retired
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                tmem_st8(tcol + 64 + 16 * ks, Hh + 8 * ks);
+                tmem_st8(tcol + 64 + 16 * ks + 8, Hl + 8 * ks);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            arrive_leader(a3r_bar(acc, 2));
+            mbar_wait_cluster(d3full_bar(acc), acc_phase);
+            tc_fence_after();
+            // layer-3 epilogue: un-scale, bias, ReLU, max over the point's K consecutive lanes, one 256-byte row per point
+            const float inv3 = __frcp_rn(osc);
+            float *orow = s.out + (size_t)(c / K) * s.ldo;
+            const bool writer = valid && (lane & (K - 1)) == 0;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t r[32];
+                tmem_ld32(tcol + 32 * half, r);
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float2 ab = sAB3[32 * half + i];
+                    v[i] = fmaxf(fmaf(__uint_as_float(r[i]), ab.x * inv3, ab.y), 0.f);
+                }
+                for (int off = 1; off < K; off <<= 1) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], off));
+                }
+                if (writer) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4 *>(orow + 32 * half + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            arrive_leader(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ===== producers (256 threads): this CTA's 128 activation rows, one 32-channel K block per iteration (as tc_gemm2.cu, SC2_Y1) =====
+        constexpr int NSL = 4;
+        const int p = threadIdx.x - 256;
+        const int pw = p >> 5;
+        const int q = lane & 7, rsub = lane >> 3;
+        const int row0 = pw * 16 + rsub;                            // this thread's rows: row0 + 4*i
+        const uint32_t stg0 = base + OFF_STG + p * 16;              // slot (ring r, i) of this thread at + (r*NSL + i) * 4096
+        const int pf = a.k_blocks + 1 < PF ? a.k_blocks + 1 : PF;
+        int stage = 0; uint32_t phase = 0;
+        for (int r = 0; r < PF * NSL; ++r)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(stg0 + r * 4096), "f"(0.f));
+        auto cp16 = [&](uint32_t dst, const float *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src)); };
+        const float *ls1[4] = {nullptr, nullptr, nullptr, nullptr};
+        auto load_ptrs = [&](int buf) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ls1[i] = cs1[buf * HALF_ROWS + row0 + 4 * i];
+        };
+        auto issue = [&](int kb, int ring) {
+            const int koff = kb * PK + q * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (ls1[i]) cp16(stg0 + (ring * NSL + i) * 4096, ls1[i] + koff);
+            asm volatile("cp.async.commit_group;");
+        };
+        auto lds16 = [&](uint32_t addr) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+            return v;
+        };
+        long long t = cl_id;
+        if (t < ntiles) {
+            int buf = 0, ring = 0;
+            asm volatile("bar.sync 1, 288;" ::: "memory");          // contexts of the first two tiles are in place (warp 2)
+            load_ptrs(0);
+            for (int g = 0; g < pf - 1; ++g) issue(g, g);
+            int la_buf = 0, la_kb = pf - 1; long long la_t = t;
+            if (la_kb >= a.k_blocks) { la_kb -= a.k_blocks; la_buf = 1; la_t += n_cl; if (la_t < ntiles) load_ptrs(1); }
+            while (true) {
+                const long long tn = t + n_cl;
+                float4 geo[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 g = cgeo[buf * HALF_ROWS + row0 + 4 * i];
+                    geo[i] = make_float4(g.x * g.w, g.y * g.w, g.z * g.w, g.w);
+                }
+                for (int kb = 0; kb < a.k_blocks; ++kb) {
+                    {
+                        int lring = ring + pf - 1; if (lring >= pf) lring -= pf;
+                        if (la_t < ntiles) issue(la_kb, lring); else asm volatile("cp.async.commit_group;");
+                        if (++la_kb == a.k_blocks) {
+                            la_kb = 0; la_buf = la_buf == 2 ? 0 : la_buf + 1; la_t += n_cl;
+                            if (la_t < ntiles) load_ptrs(la_buf);
+                        }
+                    }
+                    const float4 *wp = sW + kb * 24 + q;
+                    const float4 wx = wp[0], wy = wp[8], wz = wp[16];
+                    if (pf == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+                    else asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    float4 v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[i] = lds16(stg0 + (ring * NSL + i) * 4096);
+                    uint2 hh[4], ll[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 g = geo[i];
+                        const float2 gx = make_float2(g.x, g.x), gy = make_float2(g.y, g.y), gz = make_float2(g.z, g.z), gs = make_float2(g.w, g.w);
+                        float2 xa = make_float2(v[i].x, v[i].y), xb = make_float2(v[i].z, v[i].w);
+                        float2 ta = __fmul2_rn(make_float2(wx.x, wx.y), gx), tb = __fmul2_rn(make_float2(wx.z, wx.w), gx);
+                        ta = __ffma2_rn(make_float2(wy.x, wy.y), gy, ta); tb = __ffma2_rn(make_float2(wy.z, wy.w), gy, tb);
+                        ta = __ffma2_rn(make_float2(wz.x, wz.y), gz, ta); tb = __ffma2_rn(make_float2(wz.z, wz.w), gz, tb);
+                        xa = __ffma2_rn(xa, gs, ta); xb = __ffma2_rn(xb, gs, tb);
+                        xa = make_float2(fmaxf(xa.x, 0.f), fmaxf(xa.y, 0.f)); xb = make_float2(fmaxf(xb.x, 0.f), fmaxf(xb.y, 0.f));
+                        split_f16x2(xa, hh[i].x, ll[i].x); split_f16x2(xb, hh[i].y, ll[i].y);
+                    }
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    uint8_t *Xhi = smem + stage * STAGE_BYTES + 2 * TILE_BYTES;
+                    uint8_t *Xlo = Xhi + TILE_BYTES;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int off = sw_off_h(row0 + 4 * i, q * 4);
+                        *reinterpret_cast<uint2 *>(Xhi + off) = hh[i];
+                        *reinterpret_cast<uint2 *>(Xlo + off) = ll[i];
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full_bar(stage));
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    if (++ring == pf) ring = 0;
+                }
+                if (tn >= ntiles) break;
+                asm volatile("bar.sync 1, 288;" ::: "memory");
+                t = tn; buf = buf == 2 ? 0 : buf + 1;
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                         // nobody frees TMEM / exits while the pair still uses it
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+}  // namespace
+
+int cmf_launch_sc2_fused(const TcArgs &l2, const float *Wt3, const float *a_inv3, const float *bias3, float *out, int ldo, cudaStream_t st) {
+    static int num_sms_of[64];
+    static bool attr_set_of[64];
+    int dev = 0;
+    CMF_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { cmf_set_error("sc2 fused: device ordinal %d out of range", dev); return CMF_ERR_STATE; }
+    if (!attr_set_of[dev]) {
+        CMF_CUDA(cudaFuncSetAttribute(sc2_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CMF_CUDA(cudaDeviceGetAttribute(&num_sms_of[dev], cudaDevAttrMultiProcessorCount, dev));
+        attr_set_of[dev] = true;
+    }
+    if (l2.cols <= 0) return CMF_OK;
+    if (l2.fmt != 1 || l2.prod != TC_PROD_SC2_Y1 || l2.M != 256 || l2.m_blocks != 2 || l2.k_blocks != 16 || l2.bs_mode != 1) {
+        cmf_set_error("sc2 fused: needs the 3xFP16 format, the set-conv #2 producer, a 512 -> 256 layer and bound-based scales"); return CMF_ERR_INVALID;
+    }
+    if (l2.ksamp != 4 && l2.ksamp != 8 && l2.ksamp != 16 && l2.ksamp != 32) { cmf_set_error("sc2 fused: ksamp must be 4, 8, 16 or 32"); return CMF_ERR_INVALID; }
+    if (l2.cols % l2.ksamp != 0 || l2.cols_per_pair <= 0 || (ldo & 3)) { cmf_set_error("sc2 fused: cols must be points x ksamp, ldo a multiple of 4"); return CMF_ERR_INVALID; }
+    Sc2Args s;
+    s.g = l2; s.Wt3 = Wt3; s.a_inv3 = a_inv3; s.bias3 = bias3; s.out = out; s.ldo = ldo;
+    const long long ntiles = (l2.cols + 255) / 256;
+    const int max_cl = num_sms_of[dev] / 2;
+    const int n_cl = (int)(ntiles < max_cl ? ntiles : max_cl);
+    sc2_fused_kernel<<<2 * n_cl, NTHREADS, SMEM_BYTES, st>>>(s);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
