@@ -91,12 +91,47 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *r) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// non-blocking probe of an mbarrier phase (bounded suspend: returns false when the phase has not completed within ~0.5 us)
+// bounded wait on an mbarrier phase: returns as soon as the phase completes, or false after ~0.2 us
 __device__ __forceinline__ bool mbar_probe(uint32_t bar, uint32_t parity) {
     uint32_t done;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(bar), "r"(parity), "r"(500u) : "memory");
+                 : "=r"(done) : "r"(bar), "r"(parity), "r"(200u) : "memory");
     return done != 0;
+}
+// truly non-blocking test of an mbarrier phase
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
+
+// max over the K consecutive lanes of a point for 64 channels, as a halving butterfly: at the stage with lane offset `off` a lane keeps one
+// half of its channels and trades the other half with its partner, so the stages cost 32 + 16 + ... shuffles instead of 64 each, and the K
+// lanes of a point end up with 64 / K channels apiece -- together one contiguous 256-byte row.
+template <int K>
+__device__ __forceinline__ void maxk_store(float (&v)[64], int lane, bool valid, float *orow) {
+    int ch0 = 0;
+#pragma unroll
+    for (int off = 1, n = 64; off < K; off <<= 1, n >>= 1) {
+        const bool up = (lane & off) != 0;                   // this lane keeps the upper half of its n channels
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = up ? v[i] : v[i + n / 2];
+            const float keep = up ? v[i + n / 2] : v[i];
+            v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, off));
+        }
+        ch0 += up ? n / 2 : 0;
+    }
+    constexpr int CNT = 64 / K;                              // 16, 8, 4 or 2 channels left in this lane
+    if (valid) {
+        if (CNT >= 4) {
+#pragma unroll
+            for (int i = 0; i < CNT; i += 4) *reinterpret_cast<float4 *>(orow + ch0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+            *reinterpret_cast<float2 *>(orow + ch0) = make_float2(v[0], v[1]);
+        }
+    }
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
@@ -127,6 +162,11 @@ sc2_fused_kernel(const Sc2Args s) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
+    // optional wait-time instrumentation (a.dbg = long long[gridDim.x][8]): {total, issuer0: tempty, full + peer, turn | epilogue warp 4: tfull,
+    // g1done, d3full | producer warp 8: empty}
+    const long long t_start = a.dbg ? clock64() : 0;
+    long long dw0 = 0, dw1 = 0, dw2 = 0;
+#define TIMED(acc_, stmt_) do { if (a.dbg) { const long long c0_ = clock64(); stmt_; acc_ += clock64() - c0_; } else { stmt_; } } while (0)
     const long long ntiles = (a.cols + 255) / 256;                       // M = 256 output channels: one 256-row tile covers them all
     const long long cl_id = blockIdx.x >> 1, n_cl = gridDim.x >> 1;
     const int nks = a.k_blocks;                                          // K blocks of 32 (512 / 32 = 16)
@@ -181,33 +221,41 @@ sc2_fused_kernel(const Sc2Args s) {
         // ===== MMA issuers (leader CTA): two warps alternate stages (see tc_gemm2.cu); warp 1 also issues layer 3 =====
         const int me = warp == 3 ? 1 : 0;
         const long long my_tiles = cl_id < ntiles ? (ntiles - cl_id + n_cl - 1) / n_cl : 0;
-        long long l3_tile = 0; int l3_grp = 0;                      // next layer-3 group to issue (issuer 0 only)
+        long long l3_tile = 0; int l3_grp = 0, l3_ks = 4; bool l3_open = false;     // next layer-3 K step to issue (issuer 0 only)
         bool w3_ready = false;
-        // one pending layer-3 group, if its operand has been written: group 0 = K steps 4..7 (channels 64..127, in place), group 1 = K steps
-        // 8..15 (channels 128..255), group 2 = K steps 0..3 (channels 0..63, parked in the columns of group 0 once that has retired)
+        // Layer-3 service, ONE K step (three MMAs) per call so that it never holds up a main-loop stage for long.  Groups: 0 = K steps 4..7
+        // (channels 64..127, in place), 1 = K steps 8..15 (channels 128..255), 2 = K steps 0..3 (channels 0..63, parked in the columns of
+        // group 0 once that has retired).  Non-blocking: returns false when the next group's operand has not been written yet.
         auto serve_l3 = [&]() -> bool {
             if (me != 0 || l3_tile >= my_tiles) return false;
             const int acc3 = (int)(l3_tile & 1);
-            const uint32_t ph3 = (uint32_t)((l3_tile >> 1) & 1);
-            if (!mbar_probe(a3r_bar(acc3, l3_grp), ph3)) return false;
-            if (!w3_ready) { mbar_wait(w3_bar, 0); w3_ready = true; }
-            tc_fence_after();
+            if (!l3_open) {
+                if (!mbar_test(a3r_bar(acc3, l3_grp), (uint32_t)((l3_tile >> 1) & 1))) return false;
+                if (!w3_ready) { mbar_wait(w3_bar, 0); w3_ready = true; }
+                tc_fence_after();
+                l3_open = true;
+            }
+            const int ks = l3_ks;
+            const int ks_end = l3_grp == 0 ? 8 : (l3_grp == 1 ? 16 : 4);
             if (lane == 0) {
                 const uint32_t d3 = tmem_base + acc3 * 256;
-                const int ks0 = l3_grp == 0 ? 4 : (l3_grp == 1 ? 8 : 0), ks1 = l3_grp == 0 ? 8 : (l3_grp == 1 ? 16 : 4);
-                for (int ks = ks0; ks < ks1; ++ks) {
-                    const uint32_t a_hi = tmem_base + acc3 * 256 + (l3_grp == 2 ? 64 : 0) + 16 * ks, a_lo = a_hi + 8;
-                    const uint32_t wb = base + OFF_W3 + (ks >> 1) * 4096;
-                    const uint64_t b_hi = make_desc(wb) + (uint64_t)((ks & 1) * 2), b_lo = make_desc(wb + 2048) + (uint64_t)((ks & 1) * 2);
-                    mma2_ts(d3, a_lo, b_hi, IDESC_L3, (l3_grp == 0 && ks == ks0) ? 0u : 1u);
-                    mma2_ts(d3, a_hi, b_lo, IDESC_L3, 1u);
-                    mma2_ts(d3, a_hi, b_hi, IDESC_L3, 1u);
+                const uint32_t a_hi = tmem_base + acc3 * 256 + (l3_grp == 2 ? 64 : 0) + 16 * ks, a_lo = a_hi + 8;
+                const uint32_t wb = base + OFF_W3 + (ks >> 1) * 4096;
+                const uint64_t b_hi = make_desc(wb) + (uint64_t)((ks & 1) * 2), b_lo = make_desc(wb + 2048) + (uint64_t)((ks & 1) * 2);
+                mma2_ts(d3, a_lo, b_hi, IDESC_L3, (l3_grp == 0 && ks == 4) ? 0u : 1u);
+                mma2_ts(d3, a_hi, b_lo, IDESC_L3, 1u);
+                mma2_ts(d3, a_hi, b_hi, IDESC_L3, 1u);
+                if (ks + 1 == ks_end) {
+                    if (l3_grp == 0) commit2_mc(g1done_bar(acc3));
+                    if (l3_grp == 2) commit2_mc(d3full_bar(acc3));
                 }
-                if (l3_grp == 0) commit2_mc(g1done_bar(acc3));
-                if (l3_grp == 2) commit2_mc(d3full_bar(acc3));
             }
             __syncwarp();
-            if (++l3_grp == 3) { l3_grp = 0; ++l3_tile; }
+            if (++l3_ks == ks_end) {
+                l3_open = false;
+                if (++l3_grp == 3) { l3_grp = 0; ++l3_tile; }
+                l3_ks = l3_grp == 0 ? 4 : (l3_grp == 1 ? 8 : 0);
+            }
             return true;
         };
         // issuer 0 never blocks without looking after layer 3: the buffer the main loop waits for comes back only when its layer 3 is done
@@ -223,9 +271,9 @@ sc2_fused_kernel(const Sc2Args s) {
             for (int ks = 0; ks < nks; ++ks, ++g) {
                 if ((int)(g & 1u) == me) {
                     if (me == 0) {
-                        if (ks == 0) wait_serving(tempty_bar(acc), acc_phase ^ 1);
-                        wait_serving(full_bar(stage), phase);
-                        wait_serving(pfull_bar(stage), phase);
+                        if (ks == 0) TIMED(dw0, wait_serving(tempty_bar(acc), acc_phase ^ 1));
+                        TIMED(dw1, wait_serving(full_bar(stage), phase));
+                        TIMED(dw1, wait_serving(pfull_bar(stage), phase));
                     } else {
                         if (ks == 0) mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1);
                         mbar_wait(full_bar(stage), phase);
@@ -234,7 +282,9 @@ sc2_fused_kernel(const Sc2Args s) {
                     tc_fence_after();
                     {
                         unsigned spins = 0; unsigned long long t0 = 0ull;
+                        const long long c0_ = a.dbg ? clock64() : 0;
                         while (*turn != g) { if (!serve_l3()) watchdog(spins, t0); }       // the other issuer hands the pipe over in stage order
+                        if (a.dbg) dw2 += clock64() - c0_;
                     }
                     if (lane == 0) {
                         const uint32_t sa = base + stage * STAGE_BYTES;
@@ -263,6 +313,7 @@ sc2_fused_kernel(const Sc2Args s) {
         if (me == 0) {                                      // drain: layer 3 of the last tile(s)
             unsigned spins = 0; unsigned long long t0 = 0ull;
             while (l3_tile < my_tiles) { if (!serve_l3()) watchdog(spins, t0); }
+            if (a.dbg && lane == 0) { a.dbg[(size_t)blockIdx.x * 8 + 1] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 2] = dw1; a.dbg[(size_t)blockIdx.x * 8 + 3] = dw2; }
         }
     } else if (warp == 2) {
         // ===== row-context filler: neighbour index -> gathered-row pointer, rel-xyz, fp16 scale, two tiles ahead of the producers =====
@@ -331,7 +382,7 @@ sc2_fused_kernel(const Sc2Args s) {
                     split_f16x2(v, hi[i], lo[i]);
                 }
             };
-            mbar_wait_cluster(tfull_bar(acc), acc_phase);
+            TIMED(dw0, mbar_wait_cluster(tfull_bar(acc), acc_phase));
             tc_fence_after();
             uint32_t Hh[32], Hl[32];                                 // channels 0..63, converted; they leave their columns to D3
 #pragma unroll
@@ -356,7 +407,7 @@ sc2_fused_kernel(const Sc2Args s) {
                 __syncwarp();
                 arrive_leader(a3r_bar(acc, grp));
             }
-            mbar_wait_cluster(g1done_bar(acc), acc_phase);           // the K steps that read columns 64..127 have retired
+            TIMED(dw1, mbar_wait_cluster(g1done_bar(acc), acc_phase));   // the K steps that read columns 64..127 have retired
             tc_fence_after();
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
@@ -367,36 +418,34 @@ sc2_fused_kernel(const Sc2Args s) {
             tc_fence_before();
             __syncwarp();
             arrive_leader(a3r_bar(acc, 2));
-            mbar_wait_cluster(d3full_bar(acc), acc_phase);
+            TIMED(dw2, mbar_wait_cluster(d3full_bar(acc), acc_phase));
             tc_fence_after();
-            // layer-3 epilogue: un-scale, bias, ReLU, max over the point's K consecutive lanes, one 256-byte row per point
-            const float inv3 = __frcp_rn(osc);
-            float *orow = s.out + (size_t)(c / K) * s.ldo;
-            const bool writer = valid && (lane & (K - 1)) == 0;
+            // layer-3 epilogue: un-scale, bias, ReLU, max over the point's K consecutive lanes (halving butterfly), one 256-byte row per point
+            {
+                const float inv3 = __frcp_rn(osc);
+                float v[64];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t r[32];
-                tmem_ld32(tcol + 32 * half, r);
-                float v[32];
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t r[32];
+                    tmem_ld32(tcol + 32 * half, r);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float2 ab = sAB3[32 * half + i];
-                    v[i] = fmaxf(fmaf(__uint_as_float(r[i]), ab.x * inv3, ab.y), 0.f);
+                    for (int i = 0; i < 32; ++i) {
+                        const float2 ab = sAB3[32 * half + i];
+                        v[32 * half + i] = fmaxf(fmaf(__uint_as_float(r[i]), ab.x * inv3, ab.y), 0.f);
+                    }
                 }
-                for (int off = 1; off < K; off <<= 1) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], off));
-                }
-                if (writer) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4 *>(orow + 32 * half + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                }
+                float *orow = s.out + (size_t)(c / K) * s.ldo;
+                if (K == 4) maxk_store<4>(v, lane, valid, orow);
+                else if (K == 8) maxk_store<8>(v, lane, valid, orow);
+                else if (K == 16) maxk_store<16>(v, lane, valid, orow);
+                else maxk_store<32>(v, lane, valid, orow);
             }
             tc_fence_before();
             __syncwarp();
             arrive_leader(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (a.dbg && warp == 4 && lane == 0) { a.dbg[(size_t)blockIdx.x * 8 + 4] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 5] = dw1; a.dbg[(size_t)blockIdx.x * 8 + 6] = dw2; }
     } else {
         // ===== producers (256 threads): this CTA's 128 activation rows, one 32-channel K block per iteration (as tc_gemm2.cu, SC2_Y1) =====
         constexpr int NSL = 4;
@@ -472,7 +521,7 @@ sc2_fused_kernel(const Sc2Args s) {
                         xa = make_float2(fmaxf(xa.x, 0.f), fmaxf(xa.y, 0.f)); xb = make_float2(fmaxf(xb.x, 0.f), fmaxf(xb.y, 0.f));
                         split_f16x2(xa, hh[i].x, ll[i].x); split_f16x2(xb, hh[i].y, ll[i].y);
                     }
-                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    TIMED(dw0, mbar_wait(empty_bar(stage), phase ^ 1));
                     uint8_t *Xhi = smem + stage * STAGE_BYTES + 2 * TILE_BYTES;
                     uint8_t *Xlo = Xhi + TILE_BYTES;
 #pragma unroll
@@ -493,7 +542,10 @@ sc2_fused_kernel(const Sc2Args s) {
             }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
+        if (a.dbg && warp == 8 && lane == 0) a.dbg[(size_t)blockIdx.x * 8 + 7] = dw0;
     }
+    if (a.dbg && threadIdx.x == 0) a.dbg[(size_t)blockIdx.x * 8 + 0] = clock64() - t_start;
+#undef TIMED
     tc_fence_before();
     cluster_sync_all();                         // nobody frees TMEM / exits while the pair still uses it
     if (warp == 2) {
