@@ -21,8 +21,16 @@
 //   * Layer-3 MMAs are issued by the first MMA-issuer warp between its main-loop stages; all of its waits poll for pending layer-3 work
 //     (the main loop's next-but-one tile needs the buffer back, so a blocking wait there would deadlock).
 //
+//   * THE NEIGHBOUR GATHER IS TMA.  The hoisted layer-1 matrix P (one 512-float row slice per point and scale) is described by a 2-D tensor
+//     map (box = 32 floats x 1 row); cp.async.bulk.tensor.2d ... tile::gather4 fetches four arbitrary rows x 128 bytes per instruction into a
+//     staging ring, completing on an mbarrier by byte count.  Each producer warp issues the four gathers of its own 16 rows (one elected
+//     lane, two K blocks ahead) and waits only on its own barrier, so the 256 producer threads just wait, transform and store: no per-thread
+//     address arithmetic, no cp.async groups, nothing of their own in flight at the proxy fence.
+//
 // Cluster of 2 CTAs, 512 threads each -- roles as in tc_gemm2.cu: w0 bulk-copy issuer (weights), w1 / w3 MMA issuers (leader) or
 // forwarders (peer), w2 row-context filler, w4-7 epilogue, w8-15 producers (gather + rel-xyz term + ReLU + fp16 split).
+#include <cuda.h>
+
 #include "tc_dev.cuh"
 
 using namespace tcdev;
@@ -34,19 +42,20 @@ constexpr int TILE_BYTES = 128 * 64;                 // 128 rows x 32 halfs: 8 K
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;          // W hi, W lo, X hi, X lo: 32 KB
 constexpr int NSTAGE = 4;
 constexpr int NTHREADS = 512;
-constexpr int PF = 3;                                // cp.async staging ring depth (K blocks)
-constexpr int STG_BYTES = PF * 4 * 256 * 16;         // 48 KB: 4 rows x 16 bytes per producer thread per K block
+constexpr int PF = 3;                                // staging ring depth (K blocks): two gathers in flight per producer warp
+constexpr int STG_BYTES = PF * HALF_ROWS * 128;      // 48 KB: [ring][128 rows][32 floats], rows in tile order
 constexpr int W3_KB = 8;                             // 256 channels = 8 K blocks of 32
 constexpr int W3_BYTES = W3_KB * 2 * 2048;           // this CTA's 32 rows of W3: per K block {hi 2 KB, lo 2 KB}
 constexpr int OFF_STG = NSTAGE * STAGE_BYTES;        // 131072
 constexpr int OFF_W3 = OFF_STG + STG_BYTES;          // 180224
 constexpr int OFF_BAR = OFF_W3 + W3_BYTES;           // 212992
 constexpr int OFF_SW = OFF_BAR + 256;                // rel-xyz weights: 16 K blocks x 24 float4 = 6 KB
-constexpr int OFF_CS1 = OFF_SW + 6144;               // gathered-row pointers [3][128]
-constexpr int OFF_GEO = OFF_CS1 + 3 * HALF_ROWS * 8; // {dx, dy, dz, scale} [3][128]
+constexpr int OFF_CS1 = OFF_SW + 6144;               // gathered-row indices (rows of P) [3][128] int
+constexpr int OFF_GEO = OFF_CS1 + 3 * HALF_ROWS * 4; // {dx, dy, dz, scale} [3][128]
 constexpr int OFF_AB2 = OFF_GEO + 3 * HALF_ROWS * 16;// {a_inv, bias} of the 256 layer-2 channels (float2)
 constexpr int OFF_AB3 = OFF_AB2 + 256 * 8;           // {a_inv, bias} of the 64 layer-3 channels
-constexpr int SMEM_BYTES = OFF_AB3 + 64 * 8 + 1024;  // + alignment slack = 232192 <= 232448
+constexpr int OFF_SBAR = OFF_AB3 + 64 * 8;           // staging barriers [PF][8 producer warps]
+constexpr int SMEM_BYTES = OFF_SBAR + PF * 8 * 8 + 1024;  // + alignment slack
 static_assert(SMEM_BYTES <= 232448, "shared-memory plan exceeds 227 KB");
 constexpr uint32_t IDESC_L2 = make_idesc(256, 256, 1), IDESC_L3 = make_idesc(256, 64, 1);
 
@@ -85,19 +94,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// the same load without the wait: tmem_ld16_done() is the wait plus a register dependency, so that one load can be in flight under
+// the arithmetic on the previous one
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_done(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]) :: "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// bounded wait on an mbarrier phase: returns as soon as the phase completes, or false after ~0.2 us
-__device__ __forceinline__ bool mbar_probe(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(bar), "r"(parity), "r"(200u) : "memory");
-    return done != 0;
-}
 // truly non-blocking test of an mbarrier phase
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
     uint32_t done;
@@ -135,7 +151,7 @@ __device__ __forceinline__ void maxk_store(float (&v)[64], int lane, bool valid,
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
-sc2_fused_kernel(const Sc2Args s) {
+sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
     const TcArgs &a = s.g;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -147,14 +163,14 @@ sc2_fused_kernel(const Sc2Args s) {
     auto empty_bar = [&](int i) { return bar0 + 64 + 8 * i; };           // [4] both: stage consumed (MMA commit, multicast)
     auto tfull_bar = [&](int i) { return bar0 + 96 + 8 * i; };           // [2] both: layer-2 accumulator complete (2 issuers)
     auto tempty_bar = [&](int i) { return bar0 + 112 + 8 * i; };         // [2] leader: 4 + 4 epilogue warps have drained the buffer
-    auto a3r_bar = [&](int acc, int g) { return bar0 + 128 + 8 * (acc * 3 + g); };   // [2][3] leader: layer-3 operand group written (4 + 4 warps)
-    auto g1done_bar = [&](int i) { return bar0 + 176 + 8 * i; };         // [2] both: the K steps of channels 64..127 have retired
-    auto d3full_bar = [&](int i) { return bar0 + 192 + 8 * i; };         // [2] both: layer-3 accumulator complete
-    const uint32_t w3_bar = bar0 + 208;                                  // local: resident W3 slice has landed
+    auto a3r_bar = [&](int acc, int g) { return bar0 + 128 + 8 * (acc * 4 + g); };   // [2][4] leader: layer-3 operand group written (4 + 4 warps)
+    auto g1done_bar = [&](int i) { return bar0 + 192 + 8 * i; };         // [2] both: the K steps of channels 64..127 have retired
+    auto d3full_bar = [&](int i) { return bar0 + 208 + 8 * i; };         // [2] both: layer-3 accumulator complete
+    const uint32_t w3_bar = bar0 + 224;                                  // local: resident W3 slice has landed
     volatile uint32_t *turn = reinterpret_cast<volatile uint32_t *>(smem + OFF_BAR + 232);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 240);
     float4 *sW = reinterpret_cast<float4 *>(smem + OFF_SW);
-    const float **cs1 = reinterpret_cast<const float **>(smem + OFF_CS1);
+    int *cidx = reinterpret_cast<int *>(smem + OFF_CS1);
     float4 *cgeo = reinterpret_cast<float4 *>(smem + OFF_GEO);
     float2 *sAB2 = reinterpret_cast<float2 *>(smem + OFF_AB2);
     float2 *sAB3 = reinterpret_cast<float2 *>(smem + OFF_AB3);
@@ -184,9 +200,10 @@ sc2_fused_kernel(const Sc2Args s) {
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(full_bar(i), 1 + 8); mbar_init(pfull_bar(i), 1); mbar_init(empty_bar(i), 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull_bar(i), 2); mbar_init(tempty_bar(i), 8); mbar_init(g1done_bar(i), 1); mbar_init(d3full_bar(i), 1);
-            for (int g = 0; g < 3; ++g) mbar_init(a3r_bar(i, g), 8);
+            for (int g = 0; g < 4; ++g) mbar_init(a3r_bar(i, g), 8);
         }
         mbar_init(w3_bar, 1);
+        for (int i = 0; i < PF * 8; ++i) mbar_init(base + OFF_SBAR + 8 * i, 1);
         *turn = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -198,7 +215,6 @@ sc2_fused_kernel(const Sc2Args s) {
     cluster_sync_all();                         // both CTAs: barriers initialised, TMEM allocated, tables visible
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-
     if (warp == 0) {
         // ===== bulk-copy issuer: the resident W3 slice once, then this CTA's 128 rows of W2 per stage =====
         if (lane == 0) {
@@ -223,9 +239,9 @@ sc2_fused_kernel(const Sc2Args s) {
         const long long my_tiles = cl_id < ntiles ? (ntiles - cl_id + n_cl - 1) / n_cl : 0;
         long long l3_tile = 0; int l3_grp = 0, l3_ks = 4; bool l3_open = false;     // next layer-3 K step to issue (issuer 0 only)
         bool w3_ready = false;
-        // Layer-3 service, ONE K step (three MMAs) per call so that it never holds up a main-loop stage for long.  Groups: 0 = K steps 4..7
-        // (channels 64..127, in place), 1 = K steps 8..15 (channels 128..255), 2 = K steps 0..3 (channels 0..63, parked in the columns of
-        // group 0 once that has retired).  Non-blocking: returns false when the next group's operand has not been written yet.
+        // Layer-3 service, ONE K step (three MMAs) per call so that it never holds up a main-loop stage for long.  Operand groups of four K
+        // steps: 0 = K steps 4..7 (channels 64..127, in place), 1 = 8..11, 2 = 12..15, 3 = K steps 0..3 (channels 0..63, parked in the columns
+        // of group 0 once that has retired).  Non-blocking: returns false when the next group's operand has not been written yet.
         auto serve_l3 = [&]() -> bool {
             if (me != 0 || l3_tile >= my_tiles) return false;
             const int acc3 = (int)(l3_tile & 1);
@@ -236,10 +252,10 @@ sc2_fused_kernel(const Sc2Args s) {
                 l3_open = true;
             }
             const int ks = l3_ks;
-            const int ks_end = l3_grp == 0 ? 8 : (l3_grp == 1 ? 16 : 4);
+            const int ks_end = l3_grp == 3 ? 4 : 8 + 4 * l3_grp;
             if (lane == 0) {
                 const uint32_t d3 = tmem_base + acc3 * 256;
-                const uint32_t a_hi = tmem_base + acc3 * 256 + (l3_grp == 2 ? 64 : 0) + 16 * ks, a_lo = a_hi + 8;
+                const uint32_t a_hi = tmem_base + acc3 * 256 + (l3_grp == 3 ? 64 : 0) + 16 * ks, a_lo = a_hi + 8;
                 const uint32_t wb = base + OFF_W3 + (ks >> 1) * 4096;
                 const uint64_t b_hi = make_desc(wb) + (uint64_t)((ks & 1) * 2), b_lo = make_desc(wb + 2048) + (uint64_t)((ks & 1) * 2);
                 mma2_ts(d3, a_lo, b_hi, IDESC_L3, (l3_grp == 0 && ks == 4) ? 0u : 1u);
@@ -247,21 +263,23 @@ sc2_fused_kernel(const Sc2Args s) {
                 mma2_ts(d3, a_hi, b_hi, IDESC_L3, 1u);
                 if (ks + 1 == ks_end) {
                     if (l3_grp == 0) commit2_mc(g1done_bar(acc3));
-                    if (l3_grp == 2) commit2_mc(d3full_bar(acc3));
+                    if (l3_grp == 3) commit2_mc(d3full_bar(acc3));
                 }
             }
             __syncwarp();
             if (++l3_ks == ks_end) {
                 l3_open = false;
-                if (++l3_grp == 3) { l3_grp = 0; ++l3_tile; }
-                l3_ks = l3_grp == 0 ? 4 : (l3_grp == 1 ? 8 : 0);
+                if (++l3_grp == 4) { l3_grp = 0; ++l3_tile; }
+                l3_ks = l3_grp == 3 ? 0 : 4 + 4 * l3_grp;
             }
             return true;
         };
         // issuer 0 never blocks without looking after layer 3: the buffer the main loop waits for comes back only when its layer 3 is done
+        // (spinning on the non-blocking test: a failed try_wait suspends the warp for microseconds whatever its time hint says, which
+        // throttled the layer-3 service to one K step per 2.6 us -- measured -- and starved the main loop of accumulator buffers)
         auto wait_serving = [&](uint32_t bar, uint32_t parity) {
             unsigned spins = 0; unsigned long long t0 = 0ull;
-            while (!mbar_probe(bar, parity)) { if (!serve_l3()) watchdog(spins, t0); }
+            while (!mbar_test(bar, parity)) { if (!serve_l3()) { __nanosleep(40); watchdog(spins, t0); } }
         };
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
@@ -302,7 +320,7 @@ sc2_fused_kernel(const Sc2Args s) {
                         if (ks >= nks - 2 || nks == 1) commit2_mc(tfull_bar(acc));       // both issuers' MMAs of the tile must have retired
                     }
                     __syncwarp();
-                    serve_l3();
+                    for (int i = 0; i < 4 && serve_l3(); ++i) { }      // a tile has 16 layer-3 K steps and this issuer only eight stages of its own
                 } else if (nks == 1 && lane == 0) {
                     commit2_mc(tfull_bar(acc));
                 }
@@ -324,7 +342,8 @@ sc2_fused_kernel(const Sc2Args s) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int r = buf * HALF_ROWS + lane + 32 * k;
-                cs1[r] = rc[k].valid ? rc[k].src1 : nullptr;
+                // row of P this column gathers; columns beyond the last one read row 0 (any valid row) and are zeroed by their scale
+                cidx[r] = rc[k].valid ? (int)((rc[k].src1 - (a.U2 + a.off_u2)) / a.ld_u2) : 0;
                 cgeo[r] = make_float4(rc[k].dx, rc[k].dy, rc[k].dz, rc[k].valid ? rc[k].scale : 0.f);
             }
         };
@@ -384,29 +403,37 @@ sc2_fused_kernel(const Sc2Args s) {
             };
             TIMED(dw0, mbar_wait_cluster(tfull_bar(acc), acc_phase));
             tc_fence_after();
-            uint32_t Hh[32], Hl[32];                                 // channels 0..63, converted; they leave their columns to D3
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                uint32_t r[16];
-                tmem_ld16(tcol + 16 * ks, r);
-                convert16(r, 16 * ks, Hh + 8 * ks, Hl + 8 * ks);
-            }
+            // channels 0..63 leave their columns to D3 at once: raw into registers first, converted while layer 3 already runs on the others
+            uint32_t H0[16], H1[16], H2[16], H3[16];
+            tmem_ld16_issue(tcol, H0); tmem_ld16_issue(tcol + 16, H1); tmem_ld16_issue(tcol + 32, H2); tmem_ld16_issue(tcol + 48, H3);
+            uint32_t ra[16], rb[16];
+            tmem_ld16_issue(tcol + 64, ra);
+            tmem_ld16_done(H0); tmem_ld16_done(H1); tmem_ld16_done(H2); tmem_ld16_done(H3); tmem_ld16_done(ra);
+            // channels 64..255 in place, four K steps per group; the load of K step ks+1 is in flight under the arithmetic of K step ks
 #pragma unroll 1
-            for (int grp = 0; grp < 2; ++grp) {
-                const int ks0 = grp == 0 ? 4 : 8, ks1 = grp == 0 ? 8 : 16;
-#pragma unroll 2
-                for (int ks = ks0; ks < ks1; ++ks) {
-                    uint32_t r[16], hi[8], lo[8];
-                    tmem_ld16(tcol + 16 * ks, r);
-                    convert16(r, 16 * ks, hi, lo);
+            for (int grp = 0; grp < 3; ++grp) {
+#pragma unroll
+                for (int j = 0; j < 4; j += 2) {
+                    const int ks = 4 + 4 * grp + j;
+                    uint32_t hi[8], lo[8];
+                    tmem_ld16_issue(tcol + 16 * (ks + 1), rb);
+                    convert16(ra, 16 * ks, hi, lo);
                     tmem_st8(tcol + 16 * ks, hi);                    // in place: the 16 fp32 columns become K step ks of layer 3's A operand
                     tmem_st8(tcol + 16 * ks + 8, lo);
+                    tmem_ld16_done(rb);
+                    if (ks + 2 < 16) tmem_ld16_issue(tcol + 16 * (ks + 2), ra);
+                    convert16(rb, 16 * (ks + 1), hi, lo);
+                    tmem_st8(tcol + 16 * (ks + 1), hi);
+                    tmem_st8(tcol + 16 * (ks + 1) + 8, lo);
+                    if (ks + 2 < 16) tmem_ld16_done(ra);
                 }
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 arrive_leader(a3r_bar(acc, grp));
             }
+            uint32_t Hh[32], Hl[32];
+            convert16(H0, 0, Hh, Hl); convert16(H1, 16, Hh + 8, Hl + 8); convert16(H2, 32, Hh + 16, Hl + 16); convert16(H3, 48, Hh + 24, Hl + 24);
             TIMED(dw1, mbar_wait_cluster(g1done_bar(acc), acc_phase));   // the K steps that read columns 64..127 have retired
             tc_fence_after();
 #pragma unroll
@@ -417,7 +444,7 @@ sc2_fused_kernel(const Sc2Args s) {
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            arrive_leader(a3r_bar(acc, 2));
+            arrive_leader(a3r_bar(acc, 3));
             TIMED(dw2, mbar_wait_cluster(d3full_bar(acc), acc_phase));
             tc_fence_after();
             // layer-3 epilogue: un-scale, bias, ReLU, max over the point's K consecutive lanes (halving butterfly), one 256-byte row per point
@@ -448,28 +475,28 @@ sc2_fused_kernel(const Sc2Args s) {
         if (a.dbg && warp == 4 && lane == 0) { a.dbg[(size_t)blockIdx.x * 8 + 4] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 5] = dw1; a.dbg[(size_t)blockIdx.x * 8 + 6] = dw2; }
     } else {
         // ===== producers (256 threads): this CTA's 128 activation rows, one 32-channel K block per iteration (as tc_gemm2.cu, SC2_Y1) =====
-        constexpr int NSL = 4;
         const int p = threadIdx.x - 256;
         const int pw = p >> 5;
         const int q = lane & 7, rsub = lane >> 3;
         const int row0 = pw * 16 + rsub;                            // this thread's rows: row0 + 4*i
-        const uint32_t stg0 = base + OFF_STG + p * 16;              // slot (ring r, i) of this thread at + (r*NSL + i) * 4096
-        const int pf = a.k_blocks + 1 < PF ? a.k_blocks + 1 : PF;
+        const uint32_t stg_w = base + OFF_STG + pw * 2048;          // this warp's 16 rows of ring slot r at + r * 16384
+        const uint32_t stg_t = stg_w + rsub * 128 + q * 16;         // this thread's 16-byte chunk of row 4*i + rsub at + i * 512
+        const uint32_t sbar_w = base + OFF_SBAR + pw * 8;           // this warp's barrier of ring slot r at + r * 64
         int stage = 0; uint32_t phase = 0;
-        for (int r = 0; r < PF * NSL; ++r)
-            asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(stg0 + r * 4096), "f"(0.f));
-        auto cp16 = [&](uint32_t dst, const float *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src)); };
-        const float *ls1[4] = {nullptr, nullptr, nullptr, nullptr};
-        auto load_ptrs = [&](int buf) {
+        // four rows x 128 bytes per instruction, rows picked by index: the warp's 16 rows of K block kb of the tile whose contexts sit in `lbuf`
+        auto issue = [&](int kb, int ring, int lbuf) {
+            if (lane == 0) {
+                const int4 *ip = reinterpret_cast<const int4 *>(cidx + lbuf * HALF_ROWS + pw * 16);
+                const uint32_t dst = stg_w + ring * 16384, bar = sbar_w + ring * 64;
+                const int col = a.off_u2 + kb * PK;
+                mbar_arrive_expect_tx(bar, 2048);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) ls1[i] = cs1[buf * HALF_ROWS + row0 + 4 * i];
-        };
-        auto issue = [&](int kb, int ring) {
-            const int koff = kb * PK + q * 4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (ls1[i]) cp16(stg0 + (ring * NSL + i) * 4096, ls1[i] + koff);
-            asm volatile("cp.async.commit_group;");
+                for (int i = 0; i < 4; ++i) {
+                    const int4 id = ip[i];
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                                 ::"r"(dst + i * 512), "l"(&tmapP), "r"(col), "r"(id.x), "r"(id.y), "r"(id.z), "r"(id.w), "r"(bar) : "memory");
+                }
+            }
         };
         auto lds16 = [&](uint32_t addr) {
             float4 v;
@@ -478,12 +505,10 @@ sc2_fused_kernel(const Sc2Args s) {
         };
         long long t = cl_id;
         if (t < ntiles) {
-            int buf = 0, ring = 0;
+            int buf = 0, ring = 0; uint32_t rphase = 0;             // ring slot being consumed and the parity of its barrier
             asm volatile("bar.sync 1, 288;" ::: "memory");          // contexts of the first two tiles are in place (warp 2)
-            load_ptrs(0);
-            for (int g = 0; g < pf - 1; ++g) issue(g, g);
-            int la_buf = 0, la_kb = pf - 1; long long la_t = t;
-            if (la_kb >= a.k_blocks) { la_kb -= a.k_blocks; la_buf = 1; la_t += n_cl; if (la_t < ntiles) load_ptrs(1); }
+            for (int g = 0; g < PF - 1; ++g) issue(g, g, 0);        // k_blocks = 16 >= PF - 1: all inside the first tile
+            int la_buf = 0, la_kb = PF - 1; long long la_t = t;     // look-ahead cursor: K block (current + PF - 1)
             while (true) {
                 const long long tn = t + n_cl;
                 float4 geo[4];
@@ -493,21 +518,18 @@ sc2_fused_kernel(const Sc2Args s) {
                     geo[i] = make_float4(g.x * g.w, g.y * g.w, g.z * g.w, g.w);
                 }
                 for (int kb = 0; kb < a.k_blocks; ++kb) {
-                    {
-                        int lring = ring + pf - 1; if (lring >= pf) lring -= pf;
-                        if (la_t < ntiles) issue(la_kb, lring); else asm volatile("cp.async.commit_group;");
-                        if (++la_kb == a.k_blocks) {
-                            la_kb = 0; la_buf = la_buf == 2 ? 0 : la_buf + 1; la_t += n_cl;
-                            if (la_t < ntiles) load_ptrs(la_buf);
-                        }
+                    {   // keep PF - 1 K blocks in flight: refill the slot consumed in the previous iteration (its reads are done: their
+                        // results were stored below, and the proxy fence there orders them before this asynchronous write)
+                        int lring = ring + PF - 1; if (lring >= PF) lring -= PF;
+                        if (la_t < ntiles) issue(la_kb, lring, la_buf);
+                        if (++la_kb == a.k_blocks) { la_kb = 0; la_buf = la_buf == 2 ? 0 : la_buf + 1; la_t += n_cl; }
                     }
                     const float4 *wp = sW + kb * 24 + q;
                     const float4 wx = wp[0], wy = wp[8], wz = wp[16];
-                    if (pf == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
-                    else asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    mbar_wait(sbar_w + ring * 64, rphase);
                     float4 v[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) v[i] = lds16(stg0 + (ring * NSL + i) * 4096);
+                    for (int i = 0; i < 4; ++i) v[i] = lds16(stg_t + ring * 16384 + i * 512);
                     uint2 hh[4], ll[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -534,13 +556,12 @@ sc2_fused_kernel(const Sc2Args s) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(full_bar(stage));
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                    if (++ring == pf) ring = 0;
+                    if (++ring == PF) { ring = 0; rphase ^= 1; }
                 }
                 if (tn >= ntiles) break;
                 asm volatile("bar.sync 1, 288;" ::: "memory");
                 t = tn; buf = buf == 2 ? 0 : buf + 1;
             }
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         if (a.dbg && warp == 8 && lane == 0) a.dbg[(size_t)blockIdx.x * 8 + 7] = dw0;
     }
@@ -555,6 +576,28 @@ sc2_fused_kernel(const Sc2Args s) {
 }
 
 }  // namespace
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links no libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_row_gather_map(CUtensorMap *tm, const float *base, long long rows, int ld) {
+    static EncodeTiledFn enc = nullptr;
+    if (!enc) {
+        cudaDriverEntryPointQueryResult q;
+        void *fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+            cmf_set_error("sc2 fused: cuTensorMapEncodeTiled is not available from this driver"); return CMF_ERR_STATE;
+        }
+        enc = (EncodeTiledFn)fn;
+    }
+    // rows x ld floats, row pitch ld * 4 bytes; box = 32 floats x 1 row: tile::gather4 fetches four such boxes at four row indices
+    const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows}, gstride[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {32, 1}, estr[2] = {1, 1};
+    const CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) { cmf_set_error("sc2 fused: cuTensorMapEncodeTiled failed (%d)", (int)rc); return CMF_ERR_CUDA; }
+    return CMF_OK;
+}
 
 int cmf_launch_sc2_fused(const TcArgs &l2, const float *Wt3, const float *a_inv3, const float *bias3, float *out, int ldo, cudaStream_t st) {
     static int num_sms_of[64];
@@ -573,12 +616,18 @@ int cmf_launch_sc2_fused(const TcArgs &l2, const float *Wt3, const float *a_inv3
     }
     if (l2.ksamp != 4 && l2.ksamp != 8 && l2.ksamp != 16 && l2.ksamp != 32) { cmf_set_error("sc2 fused: ksamp must be 4, 8, 16 or 32"); return CMF_ERR_INVALID; }
     if (l2.cols % l2.ksamp != 0 || l2.cols_per_pair <= 0 || (ldo & 3)) { cmf_set_error("sc2 fused: cols must be points x ksamp, ldo a multiple of 4"); return CMF_ERR_INVALID; }
+    if ((l2.ld_u2 & 3) || (l2.off_u2 & 31) || (reinterpret_cast<uintptr_t>(l2.U2) & 15)) { cmf_set_error("sc2 fused: gathered matrix must be 16-byte aligned, ld a multiple of 4, offset a multiple of 32"); return CMF_ERR_INVALID; }
+    CUtensorMap tmapP;
+    {   // the gathered matrix: one row per point of the (query = candidate) cloud, l2.cols / ksamp of them
+        int rc = make_row_gather_map(&tmapP, l2.U2, l2.cols / l2.ksamp, l2.ld_u2);
+        if (rc != CMF_OK) return rc;
+    }
     Sc2Args s;
     s.g = l2; s.Wt3 = Wt3; s.a_inv3 = a_inv3; s.bias3 = bias3; s.out = out; s.ldo = ldo;
     const long long ntiles = (l2.cols + 255) / 256;
     const int max_cl = num_sms_of[dev] / 2;
     const int n_cl = (int)(ntiles < max_cl ? ntiles : max_cl);
-    sc2_fused_kernel<<<2 * n_cl, NTHREADS, SMEM_BYTES, st>>>(s);
+    sc2_fused_kernel<<<2 * n_cl, NTHREADS, SMEM_BYTES, st>>>(s, tmapP);
     CMF_LAUNCH_CHECK();
     return CMF_OK;
 }
