@@ -30,6 +30,7 @@
 // Cluster of 2 CTAs, 512 threads each -- roles as in tc_gemm2.cu: w0 bulk-copy issuer (weights), w1 / w3 MMA issuers (leader) or
 // forwarders (peer), w2 row-context filler, w4-7 epilogue, w8-15 producers (gather + rel-xyz term + ReLU + fp16 split).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "tc_dev.cuh"
 
@@ -55,7 +56,8 @@ constexpr int OFF_GEO = OFF_CS1 + 3 * HALF_ROWS * 4; // {dx, dy, dz, scale} [3][
 constexpr int OFF_AB2 = OFF_GEO + 3 * HALF_ROWS * 16;// {a_inv, bias} of the 256 layer-2 channels (float2)
 constexpr int OFF_AB3 = OFF_AB2 + 256 * 8;           // {a_inv, bias} of the 64 layer-3 channels
 constexpr int OFF_SBAR = OFF_AB3 + 64 * 8;           // staging barriers [PF][8 producer warps]
-constexpr int SMEM_BYTES = OFF_SBAR + PF * 8 * 8 + 1024;  // + alignment slack
+constexpr int OFF_CBAR = OFF_SBAR + PF * 8 * 8;      // row-context barriers: ready[3] (filled, count 1), free[3] (8 producer warps are done with it)
+constexpr int SMEM_BYTES = OFF_CBAR + 6 * 8 + 1024;  // + alignment slack
 static_assert(SMEM_BYTES <= 232448, "shared-memory plan exceeds 227 KB");
 constexpr uint32_t IDESC_L2 = make_idesc(256, 256, 1), IDESC_L3 = make_idesc(256, 64, 1);
 
@@ -63,6 +65,7 @@ struct Sc2Args {
     TcArgs g;                        // layer 2: tiled W2 (Wt, a_inv, bias), SC2_Y1 producer fields, scales (bs_*, out_mul / out_add), cols, cols_per_pair, ksamp
     const float *Wt3, *a_inv3, *bias3;   // layer 3: tiled W3 (one 128-row block, 8 K blocks), per-channel un-scale, bias
     float *out; int ldo;             // out[point][0..63]
+    int expt;                        // timing experiments (results invalid): 1 = no layer 3 at all, 3 = conversions but no layer-3 MMAs
 };
 
 __device__ __forceinline__ void commit2_mc(uint32_t bar) {       // arrive on `bar` in BOTH CTAs when all prior MMAs of this thread retire
@@ -167,6 +170,8 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
     auto g1done_bar = [&](int i) { return bar0 + 192 + 8 * i; };         // [2] both: the K steps of channels 64..127 have retired
     auto d3full_bar = [&](int i) { return bar0 + 208 + 8 * i; };         // [2] both: layer-3 accumulator complete
     const uint32_t w3_bar = bar0 + 224;                                  // local: resident W3 slice has landed
+    auto ctx_ready_bar = [&](int i) { return base + OFF_CBAR + 8 * i; };
+    auto ctx_free_bar = [&](int i) { return base + OFF_CBAR + 24 + 8 * i; };
     volatile uint32_t *turn = reinterpret_cast<volatile uint32_t *>(smem + OFF_BAR + 232);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 240);
     float4 *sW = reinterpret_cast<float4 *>(smem + OFF_SW);
@@ -204,6 +209,7 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
         }
         mbar_init(w3_bar, 1);
         for (int i = 0; i < PF * 8; ++i) mbar_init(base + OFF_SBAR + 8 * i, 1);
+        for (int i = 0; i < 3; ++i) { mbar_init(base + OFF_CBAR + 8 * i, 1); mbar_init(base + OFF_CBAR + 24 + 8 * i, 8); }
         *turn = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -234,16 +240,75 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                 }
         }
     } else if (leader && (warp == 1 || warp == 3)) {
-        // ===== MMA issuers (leader CTA): two warps alternate stages (see tc_gemm2.cu); warp 1 also issues layer 3 =====
+        // ===== MMA issuers (leader CTA): two warps alternate stages (see tc_gemm2.cu); layer 3 is issued by warp 2 =====
         const int me = warp == 3 ? 1 : 0;
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        uint32_t g = 0;
+        for (long long t = cl_id; t < ntiles; t += n_cl) {
+            const uint32_t d2 = tmem_base + acc * 256;
+            for (int ks = 0; ks < nks; ++ks, ++g) {
+                if ((int)(g & 1u) == me) {
+                    if (ks == 0) TIMED(dw0, mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1));
+                    TIMED(dw1, mbar_wait(full_bar(stage), phase));
+                    TIMED(dw1, mbar_wait_cluster(pfull_bar(stage), phase));
+                    tc_fence_after();
+                    {
+                        unsigned spins = 0; unsigned long long t0 = 0ull;
+                        const long long c0_ = a.dbg ? clock64() : 0;
+                        while (*turn != g) watchdog(spins, t0);                            // the other issuer hands the pipe over in stage order
+                        if (a.dbg) dw2 += clock64() - c0_;
+                    }
+                    if (lane == 0) {
+                        const uint32_t sa = base + stage * STAGE_BYTES;
+                        const uint64_t w_hi = make_desc(sa), w_lo = make_desc(sa + TILE_BYTES);
+                        const uint64_t x_hi = make_desc(sa + 2 * TILE_BYTES), x_lo = make_desc(sa + 3 * TILE_BYTES);
+#pragma unroll
+                        for (int k16 = 0; k16 < 2; ++k16) {
+                            const uint64_t adv = (uint64_t)(k16 * 2);             // 32 bytes = 16 halfs, in 16-byte descriptor units
+                            mma2_ss(d2, x_lo + adv, w_hi + adv, IDESC_L2, (ks | k16) ? 1u : 0u);
+                            mma2_ss_keep(d2, x_hi + adv, w_lo + adv, IDESC_L2);
+                            mma2_ss_reuse(d2, x_hi + adv, w_hi + adv, IDESC_L2);
+                        }
+                        *turn = g + 1;
+                        commit2_mc(empty_bar(stage));
+                        if (ks >= nks - 2 || nks == 1) commit2_mc(tfull_bar(acc));       // both issuers' MMAs of the tile must have retired
+                    }
+                    __syncwarp();
+                } else if (nks == 1 && lane == 0) {
+                    commit2_mc(tfull_bar(acc));
+                }
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (me == 0 && a.dbg && lane == 0) { a.dbg[(size_t)blockIdx.x * 8 + 1] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 2] = dw1; a.dbg[(size_t)blockIdx.x * 8 + 3] = dw2; }
+    } else if (warp == 2) {
+        // ===== row contexts (neighbour index -> row of P, rel-xyz, fp16 scale) and, in the leader CTA, the layer-3 MMA issue =====
+        auto fill_ctx = [&](long long tt, int buf) {
+            RowCtx rc[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rc[k] = make_row(a, tt * 256 + rank * HALF_ROWS + lane + 32 * k);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = buf * HALF_ROWS + lane + 32 * k;
+                // row of P this column gathers; columns beyond the last one read row 0 (any valid row) and are zeroed by their scale
+                cidx[r] = rc[k].valid ? (int)((rc[k].src1 - (a.U2 + a.off_u2)) / a.ld_u2) : 0;
+                cgeo[r] = make_float4(rc[k].dx, rc[k].dy, rc[k].dz, rc[k].valid ? rc[k].scale : 0.f);
+            }
+        };
+        // One non-blocking loop: fill the row contexts of up to three tiles ahead of the producers and -- leader CTA -- issue layer 3.
+        // (A dedicated layer-3 issuer: tcgen05.mma issue blocks at the tensor pipe's rate, so when the first main-loop issuer also carried the
+        // 48 small layer-3 MMAs of every tile its own stages came late and the whole ring slowed down by a quarter -- measured.)
         const long long my_tiles = cl_id < ntiles ? (ntiles - cl_id + n_cl - 1) / n_cl : 0;
+        const long long l3_tiles = (leader && s.expt == 0) ? my_tiles : 0;
         long long l3_tile = 0; int l3_grp = 0, l3_ks = 4; bool l3_open = false;     // next layer-3 K step to issue (issuer 0 only)
         bool w3_ready = false;
         // Layer-3 service, ONE K step (three MMAs) per call so that it never holds up a main-loop stage for long.  Operand groups of four K
         // steps: 0 = K steps 4..7 (channels 64..127, in place), 1 = 8..11, 2 = 12..15, 3 = K steps 0..3 (channels 0..63, parked in the columns
         // of group 0 once that has retired).  Non-blocking: returns false when the next group's operand has not been written yet.
         auto serve_l3 = [&]() -> bool {
-            if (me != 0 || l3_tile >= my_tiles) return false;
+            if (l3_tile >= l3_tiles) return false;
             const int acc3 = (int)(l3_tile & 1);
             if (!l3_open) {
                 if (!mbar_test(a3r_bar(acc3, l3_grp), (uint32_t)((l3_tile >> 1) & 1))) return false;
@@ -274,92 +339,21 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
             }
             return true;
         };
-        // issuer 0 never blocks without looking after layer 3: the buffer the main loop waits for comes back only when its layer 3 is done
-        // (spinning on the non-blocking test: a failed try_wait suspends the warp for microseconds whatever its time hint says, which
-        // throttled the layer-3 service to one K step per 2.6 us -- measured -- and starved the main loop of accumulator buffers)
-        auto wait_serving = [&](uint32_t bar, uint32_t parity) {
-            unsigned spins = 0; unsigned long long t0 = 0ull;
-            while (!mbar_test(bar, parity)) { if (!serve_l3()) { __nanosleep(40); watchdog(spins, t0); } }
-        };
-        int stage = 0; uint32_t phase = 0;
-        int acc = 0; uint32_t acc_phase = 0;
-        uint32_t g = 0;
-        for (long long t = cl_id; t < ntiles; t += n_cl) {
-            const uint32_t d2 = tmem_base + acc * 256;
-            for (int ks = 0; ks < nks; ++ks, ++g) {
-                if ((int)(g & 1u) == me) {
-                    if (me == 0) {
-                        if (ks == 0) TIMED(dw0, wait_serving(tempty_bar(acc), acc_phase ^ 1));
-                        TIMED(dw1, wait_serving(full_bar(stage), phase));
-                        TIMED(dw1, wait_serving(pfull_bar(stage), phase));
-                    } else {
-                        if (ks == 0) mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1);
-                        mbar_wait(full_bar(stage), phase);
-                        mbar_wait_cluster(pfull_bar(stage), phase);
-                    }
-                    tc_fence_after();
-                    {
-                        unsigned spins = 0; unsigned long long t0 = 0ull;
-                        const long long c0_ = a.dbg ? clock64() : 0;
-                        while (*turn != g) { if (!serve_l3()) watchdog(spins, t0); }       // the other issuer hands the pipe over in stage order
-                        if (a.dbg) dw2 += clock64() - c0_;
-                    }
-                    if (lane == 0) {
-                        const uint32_t sa = base + stage * STAGE_BYTES;
-                        const uint64_t w_hi = make_desc(sa), w_lo = make_desc(sa + TILE_BYTES);
-                        const uint64_t x_hi = make_desc(sa + 2 * TILE_BYTES), x_lo = make_desc(sa + 3 * TILE_BYTES);
-#pragma unroll
-                        for (int k16 = 0; k16 < 2; ++k16) {
-                            const uint64_t adv = (uint64_t)(k16 * 2);             // 32 bytes = 16 halfs, in 16-byte descriptor units
-                            mma2_ss(d2, x_lo + adv, w_hi + adv, IDESC_L2, (ks | k16) ? 1u : 0u);
-                            mma2_ss_keep(d2, x_hi + adv, w_lo + adv, IDESC_L2);
-                            mma2_ss_reuse(d2, x_hi + adv, w_hi + adv, IDESC_L2);
-                        }
-                        *turn = g + 1;
-                        commit2_mc(empty_bar(stage));
-                        if (ks >= nks - 2 || nks == 1) commit2_mc(tfull_bar(acc));       // both issuers' MMAs of the tile must have retired
-                    }
+        long long fi = 0;                                                   // next local tile whose contexts are to be filled
+        unsigned spins = 0; unsigned long long t0w = 0ull;
+        while (fi < my_tiles || l3_tile < l3_tiles) {
+            bool did = false;
+            if (fi < my_tiles) {
+                const int slot = (int)(fi % 3);
+                if (fi < 3 || mbar_test(ctx_free_bar(slot), (uint32_t)(((fi / 3) - 1) & 1))) {
+                    fill_ctx(cl_id + fi * n_cl, slot);
                     __syncwarp();
-                    for (int i = 0; i < 4 && serve_l3(); ++i) { }      // a tile has 16 layer-3 K steps and this issuer only eight stages of its own
-                } else if (nks == 1 && lane == 0) {
-                    commit2_mc(tfull_bar(acc));
+                    if (lane == 0) mbar_arrive(ctx_ready_bar(slot));
+                    ++fi; did = true;
                 }
-                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        }
-        if (me == 0) {                                      // drain: layer 3 of the last tile(s)
-            unsigned spins = 0; unsigned long long t0 = 0ull;
-            while (l3_tile < my_tiles) { if (!serve_l3()) watchdog(spins, t0); }
-            if (a.dbg && lane == 0) { a.dbg[(size_t)blockIdx.x * 8 + 1] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 2] = dw1; a.dbg[(size_t)blockIdx.x * 8 + 3] = dw2; }
-        }
-    } else if (warp == 2) {
-        // ===== row-context filler: neighbour index -> gathered-row pointer, rel-xyz, fp16 scale, two tiles ahead of the producers =====
-        auto fill_ctx = [&](long long tt, int buf) {
-            RowCtx rc[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) rc[k] = make_row(a, tt * 256 + rank * HALF_ROWS + lane + 32 * k);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int r = buf * HALF_ROWS + lane + 32 * k;
-                // row of P this column gathers; columns beyond the last one read row 0 (any valid row) and are zeroed by their scale
-                cidx[r] = rc[k].valid ? (int)((rc[k].src1 - (a.U2 + a.off_u2)) / a.ld_u2) : 0;
-                cgeo[r] = make_float4(rc[k].dx, rc[k].dy, rc[k].dz, rc[k].valid ? rc[k].scale : 0.f);
-            }
-        };
-        long long t = cl_id;
-        if (t < ntiles) {
-            int buf = 0;
-            fill_ctx(t, 0);
-            if (t + n_cl < ntiles) fill_ctx(t + n_cl, 1);
-            asm volatile("bar.sync 1, 288;" ::: "memory");
-            while (true) {
-                const long long tn = t + n_cl;
-                if (tn + n_cl < ntiles) fill_ctx(tn + n_cl, buf == 0 ? 2 : buf - 1);
-                if (tn >= ntiles) break;
-                asm volatile("bar.sync 1, 288;" ::: "memory");
-                t = tn; buf = buf == 2 ? 0 : buf + 1;
-            }
+            if (serve_l3()) did = true;
+            if (!did) { __nanosleep(64); watchdog(spins, t0w); }
         }
     } else if (warp == 1 || warp == 3) {
         // ===== forwarders (peer CTA): relay "my half of stage s is complete" to the leader =====
@@ -403,6 +397,11 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
             };
             TIMED(dw0, mbar_wait_cluster(tfull_bar(acc), acc_phase));
             tc_fence_after();
+            if (s.expt == 1) {
+                tc_fence_before(); __syncwarp(); arrive_leader(tempty_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
             // channels 0..63 leave their columns to D3 at once: raw into registers first, converted while layer 3 already runs on the others
             uint32_t H0[16], H1[16], H2[16], H3[16];
             tmem_ld16_issue(tcol, H0); tmem_ld16_issue(tcol + 16, H1); tmem_ld16_issue(tcol + 32, H2); tmem_ld16_issue(tcol + 48, H3);
@@ -431,6 +430,11 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                 tc_fence_before();
                 __syncwarp();
                 arrive_leader(a3r_bar(acc, grp));
+            }
+            if (s.expt == 3) {
+                tc_fence_before(); __syncwarp(); arrive_leader(tempty_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
             }
             uint32_t Hh[32], Hl[32];
             convert16(H0, 0, Hh, Hl); convert16(H1, 16, Hh + 8, Hl + 8); convert16(H2, 32, Hh + 16, Hl + 16); convert16(H3, 48, Hh + 24, Hl + 24);
@@ -506,7 +510,8 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
         long long t = cl_id;
         if (t < ntiles) {
             int buf = 0, ring = 0; uint32_t rphase = 0;             // ring slot being consumed and the parity of its barrier
-            asm volatile("bar.sync 1, 288;" ::: "memory");          // contexts of the first two tiles are in place (warp 2)
+            long long ti = 0, la_i = 0;                             // local tile numbers of the current tile and of the look-ahead cursor
+            mbar_wait(ctx_ready_bar(0), 0);                         // contexts of the first tile are in place (warp 2)
             for (int g = 0; g < PF - 1; ++g) issue(g, g, 0);        // k_blocks = 16 >= PF - 1: all inside the first tile
             int la_buf = 0, la_kb = PF - 1; long long la_t = t;     // look-ahead cursor: K block (current + PF - 1)
             while (true) {
@@ -522,7 +527,10 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                         // results were stored below, and the proxy fence there orders them before this asynchronous write)
                         int lring = ring + PF - 1; if (lring >= PF) lring -= PF;
                         if (la_t < ntiles) issue(la_kb, lring, la_buf);
-                        if (++la_kb == a.k_blocks) { la_kb = 0; la_buf = la_buf == 2 ? 0 : la_buf + 1; la_t += n_cl; }
+                        if (++la_kb == a.k_blocks) {                // the cursor moves on to the next tile: its contexts must have been filled
+                            la_kb = 0; la_buf = la_buf == 2 ? 0 : la_buf + 1; la_t += n_cl; ++la_i;
+                            if (la_t < ntiles) mbar_wait(ctx_ready_bar(la_buf), (uint32_t)((la_i / 3) & 1));
+                        }
                     }
                     const float4 *wp = sW + kb * 24 + q;
                     const float4 wx = wp[0], wy = wp[8], wz = wp[16];
@@ -558,9 +566,11 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                     if (++ring == PF) { ring = 0; rphase ^= 1; }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ctx_free_bar(buf));      // this warp is done with the tile's contexts
                 if (tn >= ntiles) break;
-                asm volatile("bar.sync 1, 288;" ::: "memory");
-                t = tn; buf = buf == 2 ? 0 : buf + 1;
+                t = tn; buf = buf == 2 ? 0 : buf + 1; ++ti;
+                mbar_wait(ctx_ready_bar(buf), (uint32_t)((ti / 3) & 1));
             }
         }
         if (a.dbg && warp == 8 && lane == 0) a.dbg[(size_t)blockIdx.x * 8 + 7] = dw0;
@@ -624,6 +634,7 @@ int cmf_launch_sc2_fused(const TcArgs &l2, const float *Wt3, const float *a_inv3
     }
     Sc2Args s;
     s.g = l2; s.Wt3 = Wt3; s.a_inv3 = a_inv3; s.bias3 = bias3; s.out = out; s.ldo = ldo;
+    { const char *e = getenv("CMF_SC2_EXPT"); s.expt = e ? atoi(e) : 0; }
     const long long ntiles = (l2.cols + 255) / 256;
     const int max_cl = num_sms_of[dev] / 2;
     const int n_cl = (int)(ntiles < max_cl ? ntiles : max_cl);
