@@ -211,6 +211,7 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
         for (int i = 0; i < PF * 8; ++i) mbar_init(base + OFF_SBAR + 8 * i, 1);
         for (int i = 0; i < 3; ++i) { mbar_init(base + OFF_CBAR + 8 * i, 1); mbar_init(base + OFF_CBAR + 24 + 8 * i, 8); }
         *turn = 0u;
+        *reinterpret_cast<volatile uint32_t *>(smem + OFF_BAR + 248) = 0u;     // layer-3 cursor
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -240,8 +241,51 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                 }
         }
     } else if (leader && (warp == 1 || warp == 3)) {
-        // ===== MMA issuers (leader CTA): two warps alternate stages (see tc_gemm2.cu); layer 3 is issued by warp 2 =====
+        // ===== MMA issuers (leader CTA): two warps alternate stages (see tc_gemm2.cu) =====
+        // Layer 3 is issued by whichever issuer owns the pipe (`turn`), in whole operand groups of four K steps (twelve MMAs), right after
+        // its main-loop stage and before the hand-over.  Measured alternatives: a third issuing thread -- or the same thread after the
+        // hand-over -- interleaves its small MMAs one-to-one with the other issuer's big ones in the in-order pipe, every one of them then
+        // waits a full main MMA (~200 clk) and the 48 of a tile stretch the tile's layer-3 chain beyond the next tile's main loop.
         const int me = warp == 3 ? 1 : 0;
+        const long long my_tiles = cl_id < ntiles ? (ntiles - cl_id + n_cl - 1) / n_cl : 0;
+        const long long l3_tiles = (s.expt == 0 || s.expt == 4) ? my_tiles : 0;
+        volatile uint32_t *l3s = reinterpret_cast<volatile uint32_t *>(smem + OFF_BAR + 248);    // next layer-3 group: tile * 4 + group (owned with `turn`)
+        bool w3_ready = false;
+        // groups: 0 = K steps 4..7 (channels 64..127, in place), 1 = 8..11, 2 = 12..15, 3 = K steps 0..3 (channels 0..63, parked in the columns
+        // of group 0 once that has retired).  Non-blocking; only the owner of the pipe calls it.
+        auto serve_l3 = [&]() {
+            while (true) {
+                const uint32_t st = *l3s;
+                const long long l3_tile = st >> 2; const int l3_grp = (int)(st & 3u);
+                if (l3_tile >= l3_tiles) return;
+                const int acc3 = (int)(l3_tile & 1);
+                if (!mbar_test(a3r_bar(acc3, l3_grp), (uint32_t)((l3_tile >> 1) & 1))) return;
+                if (!w3_ready) { mbar_wait(w3_bar, 0); w3_ready = true; }
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t d3 = tmem_base + acc3 * 256;
+                    const int ks0 = l3_grp == 3 ? 0 : 4 + 4 * l3_grp;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int ks = ks0 + j;
+                        const uint32_t a_hi = tmem_base + acc3 * 256 + (l3_grp == 3 ? 64 : 0) + 16 * ks, a_lo = a_hi + 8;
+                        const uint32_t wb = base + OFF_W3 + (ks >> 1) * 4096;
+                        const uint64_t b_hi = make_desc(wb) + (uint64_t)((ks & 1) * 2), b_lo = make_desc(wb + 2048) + (uint64_t)((ks & 1) * 2);
+                        if (s.expt != 4) {
+                            mma2_ts(d3, a_lo, b_hi, IDESC_L3, (l3_grp == 0 && j == 0) ? 0u : 1u);
+                            mma2_ts(d3, a_hi, b_lo, IDESC_L3, 1u);
+                            mma2_ts(d3, a_hi, b_hi, IDESC_L3, 1u);
+                        } else {
+                            mma2_ts(d3, a_hi, b_hi, IDESC_L3, (l3_grp == 0 && j == 0) ? 0u : 1u);      // timing experiment: one MMA per K step
+                        }
+                    }
+                    if (l3_grp == 0) commit2_mc(g1done_bar(acc3));
+                    if (l3_grp == 3) commit2_mc(d3full_bar(acc3));
+                    *l3s = st + 1;                              // (tile, 3) + 1 = (tile + 1, 0)
+                }
+                __syncwarp();
+            }
+        };
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         uint32_t g = 0;
@@ -249,16 +293,28 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
             const uint32_t d2 = tmem_base + acc * 256;
             for (int ks = 0; ks < nks; ++ks, ++g) {
                 if ((int)(g & 1u) == me) {
-                    if (ks == 0) TIMED(dw0, mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1));
-                    TIMED(dw1, mbar_wait(full_bar(stage), phase));
-                    TIMED(dw1, mbar_wait_cluster(pfull_bar(stage), phase));
-                    tc_fence_after();
-                    {
+                    {   // my operands (both halves) and the pipe; once the pipe is mine, pending layer-3 groups go out while I wait
                         unsigned spins = 0; unsigned long long t0 = 0ull;
                         const long long c0_ = a.dbg ? clock64() : 0;
-                        while (*turn != g) watchdog(spins, t0);                            // the other issuer hands the pipe over in stage order
-                        if (a.dbg) dw2 += clock64() - c0_;
+                        bool have_full = false, have_peer = false;
+                        while (true) {
+                            if (!have_full) have_full = mbar_test(full_bar(stage), phase);
+                            if (!have_peer) have_peer = mbar_test(pfull_bar(stage), phase);
+                            const bool mine = *turn == g;
+                            if (have_full && have_peer && mine) break;
+                            if (mine) serve_l3();
+                            watchdog(spins, t0);
+                        }
+                        if (a.dbg) dw1 += clock64() - c0_;
                     }
+                    if (ks == 0) {
+                        // the accumulator buffer comes back only when ITS layer 3 is done, and layer 3 is issued by the owner of the pipe: me
+                        unsigned spins = 0; unsigned long long t0 = 0ull;
+                        const long long c0_ = a.dbg ? clock64() : 0;
+                        while (!mbar_test(tempty_bar(acc), acc_phase ^ 1)) { serve_l3(); watchdog(spins, t0); }
+                        if (a.dbg) dw0 += clock64() - c0_;
+                    }
+                    tc_fence_after();
                     if (lane == 0) {
                         const uint32_t sa = base + stage * STAGE_BYTES;
                         const uint64_t w_hi = make_desc(sa), w_lo = make_desc(sa + TILE_BYTES);
@@ -270,10 +326,13 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                             mma2_ss_keep(d2, x_hi + adv, w_lo + adv, IDESC_L2);
                             mma2_ss_reuse(d2, x_hi + adv, w_hi + adv, IDESC_L2);
                         }
-                        *turn = g + 1;
                         commit2_mc(empty_bar(stage));
                         if (ks >= nks - 2 || nks == 1) commit2_mc(tfull_bar(acc));       // both issuers' MMAs of the tile must have retired
                     }
+                    __syncwarp();
+                    serve_l3();                                                          // whole groups, still owning the pipe
+                    __threadfence_block();
+                    if (lane == 0) *turn = g + 1;
                     __syncwarp();
                 } else if (nks == 1 && lane == 0) {
                     commit2_mc(tfull_bar(acc));
@@ -282,9 +341,14 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (me == 0 && a.dbg && lane == 0) { a.dbg[(size_t)blockIdx.x * 8 + 1] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 2] = dw1; a.dbg[(size_t)blockIdx.x * 8 + 3] = dw2; }
+        if (me == 0) {                                      // drain: layer 3 of the last tile(s), once the other issuer has finished too
+            unsigned spins = 0; unsigned long long t0 = 0ull;
+            while (*turn != g) watchdog(spins, t0);
+            while ((long long)(*l3s >> 2) < l3_tiles) { serve_l3(); watchdog(spins, t0); }
+            if (a.dbg && lane == 0) { a.dbg[(size_t)blockIdx.x * 8 + 1] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 2] = dw1; a.dbg[(size_t)blockIdx.x * 8 + 3] = dw2; }
+        }
     } else if (warp == 2) {
-        // ===== row contexts (neighbour index -> row of P, rel-xyz, fp16 scale) and, in the leader CTA, the layer-3 MMA issue =====
+        // ===== row contexts: neighbour index -> row of P, rel-xyz, fp16 scale, up to three tiles ahead of the producers =====
         auto fill_ctx = [&](long long tt, int buf) {
             RowCtx rc[4];
 #pragma unroll
@@ -297,63 +361,15 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                 cgeo[r] = make_float4(rc[k].dx, rc[k].dy, rc[k].dz, rc[k].valid ? rc[k].scale : 0.f);
             }
         };
-        // One non-blocking loop: fill the row contexts of up to three tiles ahead of the producers and -- leader CTA -- issue layer 3.
-        // (A dedicated layer-3 issuer: tcgen05.mma issue blocks at the tensor pipe's rate, so when the first main-loop issuer also carried the
-        // 48 small layer-3 MMAs of every tile its own stages came late and the whole ring slowed down by a quarter -- measured.)
         const long long my_tiles = cl_id < ntiles ? (ntiles - cl_id + n_cl - 1) / n_cl : 0;
-        const long long l3_tiles = (leader && s.expt == 0) ? my_tiles : 0;
-        long long l3_tile = 0; int l3_grp = 0, l3_ks = 4; bool l3_open = false;     // next layer-3 K step to issue (issuer 0 only)
-        bool w3_ready = false;
-        // Layer-3 service, ONE K step (three MMAs) per call so that it never holds up a main-loop stage for long.  Operand groups of four K
-        // steps: 0 = K steps 4..7 (channels 64..127, in place), 1 = 8..11, 2 = 12..15, 3 = K steps 0..3 (channels 0..63, parked in the columns
-        // of group 0 once that has retired).  Non-blocking: returns false when the next group's operand has not been written yet.
-        auto serve_l3 = [&]() -> bool {
-            if (l3_tile >= l3_tiles) return false;
-            const int acc3 = (int)(l3_tile & 1);
-            if (!l3_open) {
-                if (!mbar_test(a3r_bar(acc3, l3_grp), (uint32_t)((l3_tile >> 1) & 1))) return false;
-                if (!w3_ready) { mbar_wait(w3_bar, 0); w3_ready = true; }
-                tc_fence_after();
-                l3_open = true;
-            }
-            const int ks = l3_ks;
-            const int ks_end = l3_grp == 3 ? 4 : 8 + 4 * l3_grp;
-            if (lane == 0) {
-                const uint32_t d3 = tmem_base + acc3 * 256;
-                const uint32_t a_hi = tmem_base + acc3 * 256 + (l3_grp == 3 ? 64 : 0) + 16 * ks, a_lo = a_hi + 8;
-                const uint32_t wb = base + OFF_W3 + (ks >> 1) * 4096;
-                const uint64_t b_hi = make_desc(wb) + (uint64_t)((ks & 1) * 2), b_lo = make_desc(wb + 2048) + (uint64_t)((ks & 1) * 2);
-                mma2_ts(d3, a_lo, b_hi, IDESC_L3, (l3_grp == 0 && ks == 4) ? 0u : 1u);
-                mma2_ts(d3, a_hi, b_lo, IDESC_L3, 1u);
-                mma2_ts(d3, a_hi, b_hi, IDESC_L3, 1u);
-                if (ks + 1 == ks_end) {
-                    if (l3_grp == 0) commit2_mc(g1done_bar(acc3));
-                    if (l3_grp == 3) commit2_mc(d3full_bar(acc3));
-                }
-            }
-            __syncwarp();
-            if (++l3_ks == ks_end) {
-                l3_open = false;
-                if (++l3_grp == 4) { l3_grp = 0; ++l3_tile; }
-                l3_ks = l3_grp == 3 ? 0 : 4 + 4 * l3_grp;
-            }
-            return true;
-        };
         long long fi = 0;                                                   // next local tile whose contexts are to be filled
-        unsigned spins = 0; unsigned long long t0w = 0ull;
-        while (fi < my_tiles || l3_tile < l3_tiles) {
-            bool did = false;
-            if (fi < my_tiles) {
-                const int slot = (int)(fi % 3);
-                if (fi < 3 || mbar_test(ctx_free_bar(slot), (uint32_t)(((fi / 3) - 1) & 1))) {
-                    fill_ctx(cl_id + fi * n_cl, slot);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(ctx_ready_bar(slot));
-                    ++fi; did = true;
-                }
-            }
-            if (serve_l3()) did = true;
-            if (!did) { __nanosleep(64); watchdog(spins, t0w); }
+        while (fi < my_tiles) {                                             // up to three tiles ahead of the producers
+            const int slot = (int)(fi % 3);
+            if (fi >= 3) mbar_wait(ctx_free_bar(slot), (uint32_t)(((fi / 3) - 1) & 1));
+            fill_ctx(cl_id + fi * n_cl, slot);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ctx_ready_bar(slot));
+            ++fi;
         }
     } else if (warp == 1 || warp == 3) {
         // ===== forwarders (peer CTA): relay "my half of stage s is complete" to the leader =====
