@@ -31,6 +31,7 @@ SIGNATURES = {
     "cmf_three_interpolate_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "cmf_knn_point": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "cmf_ball_query_ms": [_i, _i, _vp, _vp, _vp],
+    "cmf_kde_density": [_i, _i, _i, _vp, _vp, _f, _vp, _vp],
     "cmf_kabsch_refine": [_i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp],
     "cmf_weighted_kabsch": [_i, _i, _vp, _vp, _vp, _vp, _vp],
     "cmf_model_blob_floats": [_i],

@@ -483,3 +483,44 @@ extern "C" int cmf_furthest_point_sampling(int b, int n, int m, const float *dat
     CMF_LAUNCH_CHECK();
     return CMF_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Kernel-density estimate of the training losses (utils/util.py:172-182 compute_density_loss; caller losses/radar_loss.py:39-40):
+//   density[b][i] = mean_j exp(-d2(xyz1_i, xyz2_j) / (2 bw^2)) / (2.5 bw),  d2 = the clamped expanded form of utils/util.py:148-170.
+// One thread per query, candidates staged in shared memory; the reference materialises the (B,N,M) distance matrix.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+kde_density_kernel(int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2, float inv2bw2, float norm, float *__restrict__ out) {
+    __shared__ float4 sc[512];
+    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float *q = xyz1 + ((size_t)b * n + (i < n ? i : 0)) * 3;
+    const float qx = __ldg(q), qy = __ldg(q + 1), qz = __ldg(q + 2);
+    const float nq = cmf_sqnorm3(qx, qy, qz);
+    float acc = 0.f;
+    for (int base = 0; base < m; base += 512) {
+        const int cn = min(512, m - base);
+        __syncthreads();
+        for (int j = threadIdx.x; j < cn; j += blockDim.x) {
+            const float *c = xyz2 + ((size_t)b * m + base + j) * 3;
+            const float x = __ldg(c), y = __ldg(c + 1), z = __ldg(c + 2);
+            sc[j] = make_float4(x, y, z, cmf_sqnorm3(x, y, z));
+        }
+        __syncthreads();
+        for (int j = 0; j < cn; ++j) {
+            const float4 c = sc[j];
+            acc += __expf(-cmf_sqdist_expanded(qx, qy, qz, nq, c.x, c.y, c.z, c.w) * inv2bw2) * norm;
+        }
+    }
+    if (i < n) out[(size_t)b * n + i] = acc / (float)m;
+}
+
+extern "C" int cmf_kde_density(int b, int n, int m, const float *xyz1, const float *xyz2, float bandwidth, float *density, void *stream) {
+    CMF_REQUIRE(b >= 0 && n >= 0 && m >= 0, "negative size");
+    if (b == 0 || n == 0) return CMF_OK;
+    CMF_REQUIRE(m >= 1 && bandwidth > 0.f, "need at least one candidate and a positive bandwidth");
+    CMF_REQUIRE(xyz1 && xyz2 && density, "null pointer");
+    CMF_REQUIRE(b <= 65535, "batch > 65535");
+    kde_density_kernel<<<dim3(cmf_divup(n, 128), b), 128, 0, (cudaStream_t)stream>>>(n, m, xyz1, xyz2, 1.f / (2.f * bandwidth * bandwidth), 1.f / (2.5f * bandwidth), density);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}

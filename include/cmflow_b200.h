@@ -102,6 +102,11 @@ int cmf_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out
 int cmf_knn_point(int b, int n, int s, int k, const float *xyz, const float *new_xyz,
                   int *idx, float *dist, void *stream);
 
+/* Kernel-density estimate used by the soft chamfer loss (utils/util.py:172-182 compute_density_loss, called at losses/radar_loss.py:39-40):
+ * density (B,N) = mean over the M candidates of exp(-d2 / (2 bw^2)) / (2.5 bw), d2 = the clamped expanded-form squared distance of
+ * utils/util.py:148-170.  xyz1 (B,N,3) queries, xyz2 (B,M,3) candidates.  No (B,N,M) matrix is materialised. */
+int cmf_kde_density(int b, int n, int m, const float *xyz1, const float *xyz2, float bandwidth, float *density, void *stream);
+
 /* Multi-radius ball query of a cloud against itself, all four CMFlow scales in ONE pass over the
  * candidates (models/cmflow.py:21-22,35-36: r = 2,4,8,16; K = 4,8,16,32; QueryAndGroup.forward,
  * lib/pointnet2_utils.py:277).  xyz_planar (B,3,N) (the model's input layout) -> idx (B,N,60) int32:
