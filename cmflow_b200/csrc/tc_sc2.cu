@@ -68,26 +68,36 @@ struct Sc2Args {
     int expt;                        // timing experiments (results invalid): 1 = no layer 3 at all, 3 = conversions but no layer-3 MMAs
 };
 
-__device__ __forceinline__ void commit2_mc(uint32_t bar) {       // arrive on `bar` in BOTH CTAs when all prior MMAs of this thread retire
+// ISSUE DISCIPLINE.  The whole issuer warp executes these in uniform control flow and the instruction is predicated on `el`, the flag of the one
+// lane elected at role start (elect.sync).  Under an `if (lane == 0)` the compiler must assume per-thread operands: it wraps EVERY tcgen05.mma
+// in an ELECT / 5 x R2UR.BROADCAST / branch loop, ~100 clk of issue per MMA -- which is what made "MMA issue block at the pipe's rate" in round 1
+// and made a 32-clk layer-3 MMA cost 115.  With uniform operands the descriptors live in uniform registers and the MMAs issue back to back.
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t el;
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\tselp.u32 %0, 1, 0, e;\n\t}" : "=r"(el));
+    return el;
+}
+__device__ __forceinline__ void commit2_mc(uint32_t el, uint32_t bar) {       // arrive on `bar` in BOTH CTAs when all prior MMAs of the elected thread retire
     const uint16_t mask = 3;
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(bar), "h"(mask), "r"(el) : "memory");
 }
-__device__ __forceinline__ void mma2_ss(uint32_t d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+__device__ __forceinline__ void mma2_ss(uint32_t el, uint32_t d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(el) : "memory");
 }
-__device__ __forceinline__ void mma2_ss_keep(uint32_t d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
-                 "tcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+__device__ __forceinline__ void mma2_ss_keep(uint32_t el, uint32_t d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, 1, 0;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(el) : "memory");
 }
-__device__ __forceinline__ void mma2_ss_reuse(uint32_t d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
-                 "tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+__device__ __forceinline__ void mma2_ss_reuse(uint32_t el, uint32_t d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, 1, 0;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(el) : "memory");
 }
 // A operand in tensor memory (K-major, two fp16 per 32-bit column, one lane per row), B from shared memory
-__device__ __forceinline__ void mma2_ts(uint32_t d, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+__device__ __forceinline__ void mma2_ts(uint32_t el, uint32_t d, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(el) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -180,7 +190,7 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
     float2 *sAB2 = reinterpret_cast<float2 *>(smem + OFF_AB2);
     float2 *sAB3 = reinterpret_cast<float2 *>(smem + OFF_AB3);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;      // broadcast: the compiler then knows the role branches are warp-uniform
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     // optional wait-time instrumentation (a.dbg = long long[gridDim.x][8]): {total, issuer0: tempty, full + peer, turn | epilogue warp 4: tfull,
@@ -247,6 +257,7 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
         // hand-over -- interleaves its small MMAs one-to-one with the other issuer's big ones in the in-order pipe, every one of them then
         // waits a full main MMA (~200 clk) and the 48 of a tile stretch the tile's layer-3 chain beyond the next tile's main loop.
         const int me = warp == 3 ? 1 : 0;
+        const uint32_t el = elect_one();                   // the one lane of this warp that issues (and commits) every MMA
         const long long my_tiles = cl_id < ntiles ? (ntiles - cl_id + n_cl - 1) / n_cl : 0;
         const long long l3_tiles = (s.expt == 0 || s.expt == 4) ? my_tiles : 0;
         volatile uint32_t *l3s = reinterpret_cast<volatile uint32_t *>(smem + OFF_BAR + 248);    // next layer-3 group: tile * 4 + group (owned with `turn`)
@@ -255,34 +266,33 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
         // of group 0 once that has retired).  Non-blocking; only the owner of the pipe calls it.
         auto serve_l3 = [&]() {
             while (true) {
-                const uint32_t st = *l3s;
+                const uint32_t st = __shfl_sync(0xffffffffu, *l3s, 0);              // (broadcast: warp-uniform for the compiler)
                 const long long l3_tile = st >> 2; const int l3_grp = (int)(st & 3u);
                 if (l3_tile >= l3_tiles) return;
                 const int acc3 = (int)(l3_tile & 1);
                 if (!mbar_test(a3r_bar(acc3, l3_grp), (uint32_t)((l3_tile >> 1) & 1))) return;
                 if (!w3_ready) { mbar_wait(w3_bar, 0); w3_ready = true; }
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t d3 = tmem_base + acc3 * 256;
-                    const int ks0 = l3_grp == 3 ? 0 : 4 + 4 * l3_grp;
+                const uint32_t d3 = tmem_base + acc3 * 256;
+                const int ks0 = l3_grp == 3 ? 0 : 4 + 4 * l3_grp;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int ks = ks0 + j;
-                        const uint32_t a_hi = tmem_base + acc3 * 256 + (l3_grp == 3 ? 64 : 0) + 16 * ks, a_lo = a_hi + 8;
-                        const uint32_t wb = base + OFF_W3 + (ks >> 1) * 4096;
-                        const uint64_t b_hi = make_desc(wb) + (uint64_t)((ks & 1) * 2), b_lo = make_desc(wb + 2048) + (uint64_t)((ks & 1) * 2);
-                        if (s.expt != 4) {
-                            mma2_ts(d3, a_lo, b_hi, IDESC_L3, (l3_grp == 0 && j == 0) ? 0u : 1u);
-                            mma2_ts(d3, a_hi, b_lo, IDESC_L3, 1u);
-                            mma2_ts(d3, a_hi, b_hi, IDESC_L3, 1u);
-                        } else {
-                            mma2_ts(d3, a_hi, b_hi, IDESC_L3, (l3_grp == 0 && j == 0) ? 0u : 1u);      // timing experiment: one MMA per K step
-                        }
+                for (int j = 0; j < 4; ++j) {
+                    const int ks = ks0 + j;
+                    const uint32_t a_hi = tmem_base + acc3 * 256 + (l3_grp == 3 ? 64 : 0) + 16 * ks, a_lo = a_hi + 8;
+                    const uint32_t wb = base + OFF_W3 + (ks >> 1) * 4096;
+                    const uint64_t b_hi = make_desc(wb) + (uint64_t)((ks & 1) * 2), b_lo = make_desc(wb + 2048) + (uint64_t)((ks & 1) * 2);
+                    if (s.expt != 4) {
+                        mma2_ts(el, d3, a_lo, b_hi, IDESC_L3, (l3_grp == 0 && j == 0) ? 0u : 1u);
+                        mma2_ts(el, d3, a_hi, b_lo, IDESC_L3, 1u);
+                        mma2_ts(el, d3, a_hi, b_hi, IDESC_L3, 1u);
+                    } else {
+                        mma2_ts(el, d3, a_hi, b_hi, IDESC_L3, (l3_grp == 0 && j == 0) ? 0u : 1u);      // timing experiment: one MMA per K step
                     }
-                    if (l3_grp == 0) commit2_mc(g1done_bar(acc3));
-                    if (l3_grp == 3) commit2_mc(d3full_bar(acc3));
-                    *l3s = st + 1;                              // (tile, 3) + 1 = (tile + 1, 0)
                 }
+                if (l3_grp == 0) commit2_mc(el, g1done_bar(acc3));
+                if (l3_grp == 3) commit2_mc(el, d3full_bar(acc3));
+                __syncwarp();
+                if (lane == 0) *l3s = st + 1;                   // (tile, 3) + 1 = (tile + 1, 0)
                 __syncwarp();
             }
         };
@@ -315,27 +325,27 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                         if (a.dbg) dw0 += clock64() - c0_;
                     }
                     tc_fence_after();
-                    if (lane == 0) {
+                    {
                         const uint32_t sa = base + stage * STAGE_BYTES;
                         const uint64_t w_hi = make_desc(sa), w_lo = make_desc(sa + TILE_BYTES);
                         const uint64_t x_hi = make_desc(sa + 2 * TILE_BYTES), x_lo = make_desc(sa + 3 * TILE_BYTES);
 #pragma unroll
                         for (int k16 = 0; k16 < 2; ++k16) {
                             const uint64_t adv = (uint64_t)(k16 * 2);             // 32 bytes = 16 halfs, in 16-byte descriptor units
-                            mma2_ss(d2, x_lo + adv, w_hi + adv, IDESC_L2, (ks | k16) ? 1u : 0u);
-                            mma2_ss_keep(d2, x_hi + adv, w_lo + adv, IDESC_L2);
-                            mma2_ss_reuse(d2, x_hi + adv, w_hi + adv, IDESC_L2);
+                            mma2_ss(el, d2, x_lo + adv, w_hi + adv, IDESC_L2, (ks | k16) ? 1u : 0u);
+                            mma2_ss_keep(el, d2, x_hi + adv, w_lo + adv, IDESC_L2);
+                            mma2_ss_reuse(el, d2, x_hi + adv, w_hi + adv, IDESC_L2);
                         }
-                        commit2_mc(empty_bar(stage));
-                        if (ks >= nks - 2 || nks == 1) commit2_mc(tfull_bar(acc));       // both issuers' MMAs of the tile must have retired
+                        commit2_mc(el, empty_bar(stage));
+                        if (ks >= nks - 2 || nks == 1) commit2_mc(el, tfull_bar(acc));   // both issuers' MMAs of the tile must have retired
                     }
                     __syncwarp();
                     serve_l3();                                                          // whole groups, still owning the pipe
                     __threadfence_block();
                     if (lane == 0) *turn = g + 1;
                     __syncwarp();
-                } else if (nks == 1 && lane == 0) {
-                    commit2_mc(tfull_bar(acc));
+                } else if (nks == 1) {
+                    commit2_mc(el, tfull_bar(acc));
                 }
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
