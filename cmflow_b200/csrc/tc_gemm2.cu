@@ -45,32 +45,41 @@ constexpr int AUX_BYTES = 20 * 1024;                               // rel-xyz we
 constexpr int SMEM_BYTES = RING_BYTES + 1024 + 256 + AUX_BYTES;
 constexpr uint32_t IDESC2_TF32 = make_idesc(256, BN, 0), IDESC2_F16 = make_idesc(256, BN, 1);
 
-__device__ __forceinline__ void tc_commit2_mc(uint32_t bar) {      // arrive on `bar` in BOTH CTAs when all prior MMAs of this thread retire
-    const uint16_t mask = 3;
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+// ISSUE DISCIPLINE (see tc_sc2.cu): the whole issuer warp runs the issue code in uniform control flow and every tcgen05 instruction is
+// predicated on `el`, the flag of the lane elected at role start.  Under `if (lane == 0)` the compiler wraps each MMA in an
+// ELECT / R2UR.BROADCAST / branch loop (~100 clk of issue per MMA).
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t el;
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\tselp.u32 %0, 1, 0, e;\n\t}" : "=r"(el));
+    return el;
 }
-__device__ __forceinline__ void tc_mma2_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+__device__ __forceinline__ void tc_commit2_mc(uint32_t el, uint32_t bar) {      // arrive on `bar` in BOTH CTAs when all prior MMAs of the elected thread retire
+    const uint16_t mask = 3;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(bar), "h"(mask), "r"(el) : "memory");
+}
+__device__ __forceinline__ void tc_mma2_tf32(uint32_t el, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(el) : "memory");
 }
 
-__device__ __forceinline__ void tc_mma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+__device__ __forceinline__ void tc_mma2_f16(uint32_t el, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(el) : "memory");
 }
 // The hi x lo and hi x hi products use the same A tile back to back: the first keeps it in the tensor core's A collector, the second reads it
 // from there instead of from shared memory (4 KB less on the SM's shared-memory port per K=16 step, see profiles/r01b_tc_kernels_ncu_full.md).
-__device__ __forceinline__ void tc_mma2_f16_keep(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
-                 "tcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+__device__ __forceinline__ void tc_mma2_f16_keep(uint32_t el, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, 1, 0;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(el) : "memory");
 }
-__device__ __forceinline__ void tc_mma2_f16_reuse(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
-                 "tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+__device__ __forceinline__ void tc_mma2_f16_reuse(uint32_t el, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, 1, 0;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(el) : "memory");
 }
 
 // F16 = 0: 3xTF32, one pipeline stage = 16 floats of K;  F16 = 1: 3xFP16, one stage = 32 halfs of K (same bytes, see tc_dev.cuh)
@@ -103,7 +112,7 @@ tc_gemm2_kernel(const TcArgs a) {
             sW[i] = make_float4(__ldg(w), __ldg(w + 4), __ldg(w + 8), __ldg(w + 12));
         }
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;      // broadcast: warp-uniform role branches for the compiler
     const long long t_start = a.dbg ? clock64() : 0;
     long long dw0 = 0, dw1 = 0, dw2 = 0;                             // per-role accumulated wait cycles (instrumented runs only)
 #define TIMED(acc_, stmt_) do { if (a.dbg) { const long long c0_ = clock64(); stmt_; acc_ += clock64() - c0_; } else { stmt_; } } while (0)
@@ -175,6 +184,7 @@ tc_gemm2_kernel(const TcArgs a) {
         // waits for / fences / commits its own stage.  `turn` (shared memory, polled) hands the pipe over in stage order, so the MMAs still
         // enter the pipe -- and accumulate -- in exactly the single-issuer order: results stay bit-reproducible.
         const int me = warp == 3 ? 1 : 0;
+        const uint32_t el = elect_one();                            // the one lane of this warp that issues (and commits) every MMA
         volatile uint32_t *turn = reinterpret_cast<volatile uint32_t *>(smem + RING_BYTES + 232);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
@@ -187,8 +197,9 @@ tc_gemm2_kernel(const TcArgs a) {
                     TIMED(dw1, mbar_wait(full_bar(stage), phase));                 // my half
                     TIMED(dw2, mbar_wait_cluster(pfull_bar(stage), phase));        // the peer's half (relayed)
                     tc_fence_after();
-                    if (lane == 0) {
-                        while (*turn != g) { }                                      // the other issuer has handed the pipe over
+                    {
+                        unsigned spins = 0; unsigned long long t0 = 0ull;
+                        while (*turn != g) watchdog(spins, t0);                     // the other issuer has handed the pipe over
                         const uint32_t sa = base + stage * STAGE_BYTES;
                         const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + TILE_A_FLOATS * 4);
                         const uint64_t b_hi = make_desc(sa + 2 * TILE_A_FLOATS * 4), b_lo = make_desc(sa + 2 * TILE_A_FLOATS * 4 + TILE_BH_FLOATS * 4);
@@ -196,23 +207,24 @@ tc_gemm2_kernel(const TcArgs a) {
                         for (int k8 = 0; k8 < SK / 8; ++k8) {
                             const uint64_t adv = (uint64_t)(k8 * 32 >> 4);
                             if (F16) {
-                                tc_mma2_f16(d_tmem, a_lo + adv, b_hi + adv, IDESC2_F16, (ks | k8) ? 1u : 0u);
-                                tc_mma2_f16_keep(d_tmem, a_hi + adv, b_lo + adv, IDESC2_F16);
-                                tc_mma2_f16_reuse(d_tmem, a_hi + adv, b_hi + adv, IDESC2_F16);
+                                tc_mma2_f16(el, d_tmem, a_lo + adv, b_hi + adv, IDESC2_F16, (ks | k8) ? 1u : 0u);
+                                tc_mma2_f16_keep(el, d_tmem, a_hi + adv, b_lo + adv, IDESC2_F16);
+                                tc_mma2_f16_reuse(el, d_tmem, a_hi + adv, b_hi + adv, IDESC2_F16);
                             } else {
-                                tc_mma2_tf32(d_tmem, a_lo + adv, b_hi + adv, IDESC2_TF32, (ks | k8) ? 1u : 0u);
-                                tc_mma2_tf32(d_tmem, a_hi + adv, b_lo + adv, IDESC2_TF32, 1u);
-                                tc_mma2_tf32(d_tmem, a_hi + adv, b_hi + adv, IDESC2_TF32, 1u);
+                                tc_mma2_tf32(el, d_tmem, a_lo + adv, b_hi + adv, IDESC2_TF32, (ks | k8) ? 1u : 0u);
+                                tc_mma2_tf32(el, d_tmem, a_hi + adv, b_lo + adv, IDESC2_TF32, 1u);
+                                tc_mma2_tf32(el, d_tmem, a_hi + adv, b_hi + adv, IDESC2_TF32, 1u);
                             }
                         }
-                        *turn = g + 1;
-                        tc_commit2_mc(empty_bar(stage));
+                        __syncwarp();
+                        if (lane == 0) *turn = g + 1;
+                        tc_commit2_mc(el, empty_bar(stage));
                         // the accumulator is complete when BOTH issuers' MMAs of the tile have retired: each commits after its last stage
-                        if (ks >= nks - 2 || nks == 1) tc_commit2_mc(tfull_bar(acc));
+                        if (ks >= nks - 2 || nks == 1) tc_commit2_mc(el, tfull_bar(acc));
                     }
                     __syncwarp();
-                } else if (nks == 1 && lane == 0) {
-                    tc_commit2_mc(tfull_bar(acc));                                  // no stage of mine in this tile: still owe my arrival
+                } else if (nks == 1) {
+                    tc_commit2_mc(el, tfull_bar(acc));                              // no stage of mine in this tile: still owe my arrival
                 }
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
