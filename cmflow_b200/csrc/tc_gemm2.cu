@@ -9,14 +9,14 @@
 // half the producer stores / gathers per MAC, and -- for M = 256 layers -- every activation row is produced exactly once.
 //
 // Cluster of 2 CTAs, 512 threads each: w0 bulk-copy issuer, w1 MMA issuer (leader CTA only), w2 TMEM allocator,
-// w3 forwarder (peer CTA only: relays "my half of stage s is full" to the leader), w4-7 epilogue (own 128 accumulator rows),
+// w1 / w3 forwarders (peer CTA only: relay "my half of stage s is full" to the leader, alternating stages), w4-7 epilogue (own 128 accumulator rows),
 // w8-15 producers (128 rows per CTA; lane = (row, 16-byte chunk) so that eight lanes read one 128-byte row slice: coalesced gathers).
 // 6-stage ring of 32 KB stages (K = 16 per stage).
 // Protocol (barriers at identical offsets in both CTAs):
 //   full_local[s]  : local  -- bulk copy expect_tx + 8 producer warps                      (count 1 + 8, or 1 when B is bulk-copied)
 //   peer_full[s]   : leader -- remote arrive by the peer's forwarder                        (count 1)
 //   empty[s]       : both   -- tcgen05.commit.cta_group::2 multicast from the leader        (count 1)
-//   tfull[a]       : both   -- commit multicast by each of the two MMA issuers after its last K stage of a tile (count 2)
+//   tfull[a]       : both   -- commit multicast by the MMA issuer after the last K stage of a tile (count 1)
 //   tempty[a]      : leader -- 4 local + 4 remote epilogue warps                            (count 8)
 #include "tc_dev.cuh"
 
@@ -48,6 +48,9 @@ constexpr uint32_t IDESC2_TF32 = make_idesc(256, BN, 0), IDESC2_F16 = make_idesc
 // ISSUE DISCIPLINE (see tc_sc2.cu): the whole issuer warp runs the issue code in uniform control flow and every tcgen05 instruction is
 // predicated on `el`, the flag of the lane elected at role start.  Under `if (lane == 0)` the compiler wraps each MMA in an
 // ELECT / R2UR.BROADCAST / branch loop (~100 clk of issue per MMA).
+// CAUTION: ptxas turns `@el tcgen05.mma` into ONE unguarded UTCHMMA per pass of the warp through the code (operands broadcast from the elected
+// lane).  The issuer warp must therefore be CONVERGED there: if its lanes drift apart (per-lane polling results), every divergent group issues
+// the MMA again -- with stale uniform registers (observed: launch failure).  Poll with warp-uniform votes / __syncwarp() before issuing.
 __device__ __forceinline__ uint32_t elect_one() {
     uint32_t el;
     asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\tselp.u32 %0, 1, 0, e;\n\t}" : "=r"(el));
@@ -131,8 +134,7 @@ tc_gemm2_kernel(const TcArgs a) {
             mbar_init(pfull_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 2); mbar_init(tempty_bar(s), 8); mbar_init(h2full_bar(s), 8); mbar_init(h2empty_bar(s), 4); }
-        *reinterpret_cast<volatile uint32_t *>(smem + RING_BYTES + 232) = 0u;       // issuers' turn counter
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); mbar_init(h2full_bar(s), 8); mbar_init(h2empty_bar(s), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -176,61 +178,48 @@ tc_gemm2_kernel(const TcArgs a) {
             }
             if (a.dbg) a.dbg[(size_t)blockIdx.x * 8 + 4] = dw0;
         }
-    } else if (leader && (warp == 1 || warp == 3)) {
-        // ===== MMA issuers (leader CTA only): two warps drive both SMs' tensor cores, stage by stage in turn =====
-        // tcgen05.mma issue blocks at the tensor pipe's own rate (~118 clk per M256xN256xK16 MMA measured): with ONE issuer everything else
-        // it does per stage -- waiting for the operands, fences, the multicast commits: ~45 % of the stage period -- was tensor-pipe idle time.
-        // Warp 1 takes the even stages, warp 3 (idle in the leader otherwise) the odd ones; while one is blocked in its six MMAs the other
-        // waits for / fences / commits its own stage.  `turn` (shared memory, polled) hands the pipe over in stage order, so the MMAs still
-        // enter the pipe -- and accumulate -- in exactly the single-issuer order: results stay bit-reproducible.
-        const int me = warp == 3 ? 1 : 0;
+    } else if (leader && warp == 1) {
+        // ===== MMA issuer (leader CTA only): ONE warp drives both SMs' tensor cores =====
+        // Round 1 alternated two issuer warps because the issue itself was slow (per-MMA ELECT / R2UR loops under `if (lane == 0)`, ~100 clk
+        // each).  With the elect-predicated, warp-uniform issue the six MMAs and two commits of a stage take a few tens of cycles, so one
+        // warp keeps the pipe fed -- and a single issuing thread is what makes the accumulation order (hence the result bits) reproducible:
+        // MMAs of DIFFERENT warps reach the tensor pipe through their own sub-partition queues and may interleave differently from run to
+        // run even when a shared-memory turn counter orders their issue (measured: run-to-run differences of a few ulp).
         const uint32_t el = elect_one();                            // the one lane of this warp that issues (and commits) every MMA
-        volatile uint32_t *turn = reinterpret_cast<volatile uint32_t *>(smem + RING_BYTES + 232);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        uint32_t g = 0;                                             // running stage number over all tiles of this cluster
         for (long long t = cl_id; t < ntiles; t += n_cl) {
             const uint32_t d_tmem = tmem_base + acc * BN;
-            for (int ks = 0; ks < nks; ++ks, ++g) {
-                if ((int)(g & 1u) == me) {
-                    if (ks == 0) { TIMED(dw0, mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1)); }     // the tile's first MMA overwrites the accumulator
-                    TIMED(dw1, mbar_wait(full_bar(stage), phase));                 // my half
-                    TIMED(dw2, mbar_wait_cluster(pfull_bar(stage), phase));        // the peer's half (relayed)
-                    tc_fence_after();
-                    {
-                        unsigned spins = 0; unsigned long long t0 = 0ull;
-                        while (*turn != g) watchdog(spins, t0);                     // the other issuer has handed the pipe over
-                        const uint32_t sa = base + stage * STAGE_BYTES;
-                        const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + TILE_A_FLOATS * 4);
-                        const uint64_t b_hi = make_desc(sa + 2 * TILE_A_FLOATS * 4), b_lo = make_desc(sa + 2 * TILE_A_FLOATS * 4 + TILE_BH_FLOATS * 4);
+            for (int ks = 0; ks < nks; ++ks) {
+                if (ks == 0) { TIMED(dw0, mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1)); }     // the tile's first MMA overwrites the accumulator
+                TIMED(dw1, mbar_wait(full_bar(stage), phase));                 // my half
+                TIMED(dw2, mbar_wait_cluster(pfull_bar(stage), phase));        // the peer's half (relayed)
+                __syncwarp();                                                  // converged warp: ptxas issues an elect-predicated MMA ONCE PER WARP PASS
+                tc_fence_after();
+                const uint32_t sa = base + stage * STAGE_BYTES;
+                const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + TILE_A_FLOATS * 4);
+                const uint64_t b_hi = make_desc(sa + 2 * TILE_A_FLOATS * 4), b_lo = make_desc(sa + 2 * TILE_A_FLOATS * 4 + TILE_BH_FLOATS * 4);
 #pragma unroll
-                        for (int k8 = 0; k8 < SK / 8; ++k8) {
-                            const uint64_t adv = (uint64_t)(k8 * 32 >> 4);
-                            if (F16) {
-                                tc_mma2_f16(el, d_tmem, a_lo + adv, b_hi + adv, IDESC2_F16, (ks | k8) ? 1u : 0u);
-                                tc_mma2_f16_keep(el, d_tmem, a_hi + adv, b_lo + adv, IDESC2_F16);
-                                tc_mma2_f16_reuse(el, d_tmem, a_hi + adv, b_hi + adv, IDESC2_F16);
-                            } else {
-                                tc_mma2_tf32(el, d_tmem, a_lo + adv, b_hi + adv, IDESC2_TF32, (ks | k8) ? 1u : 0u);
-                                tc_mma2_tf32(el, d_tmem, a_hi + adv, b_lo + adv, IDESC2_TF32, 1u);
-                                tc_mma2_tf32(el, d_tmem, a_hi + adv, b_hi + adv, IDESC2_TF32, 1u);
-                            }
-                        }
-                        __syncwarp();
-                        if (lane == 0) *turn = g + 1;
-                        tc_commit2_mc(el, empty_bar(stage));
-                        // the accumulator is complete when BOTH issuers' MMAs of the tile have retired: each commits after its last stage
-                        if (ks >= nks - 2 || nks == 1) tc_commit2_mc(el, tfull_bar(acc));
+                for (int k8 = 0; k8 < SK / 8; ++k8) {
+                    const uint64_t adv = (uint64_t)(k8 * 32 >> 4);
+                    if (F16) {
+                        tc_mma2_f16(el, d_tmem, a_lo + adv, b_hi + adv, IDESC2_F16, (ks | k8) ? 1u : 0u);
+                        tc_mma2_f16_keep(el, d_tmem, a_hi + adv, b_lo + adv, IDESC2_F16);
+                        tc_mma2_f16_reuse(el, d_tmem, a_hi + adv, b_hi + adv, IDESC2_F16);
+                    } else {
+                        tc_mma2_tf32(el, d_tmem, a_lo + adv, b_hi + adv, IDESC2_TF32, (ks | k8) ? 1u : 0u);
+                        tc_mma2_tf32(el, d_tmem, a_hi + adv, b_lo + adv, IDESC2_TF32, 1u);
+                        tc_mma2_tf32(el, d_tmem, a_hi + adv, b_hi + adv, IDESC2_TF32, 1u);
                     }
-                    __syncwarp();
-                } else if (nks == 1) {
-                    tc_commit2_mc(el, tfull_bar(acc));                              // no stage of mine in this tile: still owe my arrival
                 }
+                tc_commit2_mc(el, empty_bar(stage));
+                if (ks == nks - 1) tc_commit2_mc(el, tfull_bar(acc));          // the accumulator is complete when the tile's last MMAs retire
+                __syncwarp();
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (a.dbg && lane == 0 && me == 0) { a.dbg[(size_t)blockIdx.x * 8 + 1] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 2] = dw1; a.dbg[(size_t)blockIdx.x * 8 + 3] = dw2; }
+        if (a.dbg && lane == 0) { a.dbg[(size_t)blockIdx.x * 8 + 1] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 2] = dw1; a.dbg[(size_t)blockIdx.x * 8 + 3] = dw2; }
     } else if (warp == 2 && PROD != TC_PROD_TILED) {
         // ===== context filler (idle after the TMEM allocation): neighbour index -> row pointers, rel-xyz, fp16 scale for the tile two
         // ahead of the producers, so that those dependent global loads never sit on the producers' critical path =====
@@ -260,7 +249,7 @@ tc_gemm2_kernel(const TcArgs a) {
                 t = tn; buf = buf == 2 ? 0 : buf + 1;
             }
         }
-    } else if (warp == 1 || warp == 3) {
+    } else if (!leader && (warp == 1 || warp == 3)) {
         // ===== forwarders (peer CTA: its warps 1 and 3, alternating stages): tell the leader when this CTA's half of a stage is complete =====
         // (the relay is a serial wait -> remote arrive per stage; a release.cluster arrive on it was the pair kernel's critical path)
         const int me = warp == 3 ? 1 : 0;

@@ -18,7 +18,7 @@
 //     buffer.  The epilogue first takes channels 0..63 into registers (already converted: 64 packed words), which frees those columns
 //     for D3; channels 64..255 are converted in place and multiplied first; when the K steps of channels 64..127 have retired, their
 //     columns take the held channels 0..63 for the last four K steps.
-//   * Layer-3 MMAs are issued by the first MMA-issuer warp between its main-loop stages; all of its waits poll for pending layer-3 work
+//   * Layer-3 MMAs are issued by the (single) MMA-issuer warp between its main-loop stages; all of its waits poll for pending layer-3 work
 //     (the main loop's next-but-one tile needs the buffer back, so a blocking wait there would deadlock).
 //
 //   * THE NEIGHBOUR GATHER IS TMA.  The hoisted layer-1 matrix P (one 512-float row slice per point and scale) is described by a 2-D tensor
@@ -27,7 +27,7 @@
 //     lane, two K blocks ahead) and waits only on its own barrier, so the 256 producer threads just wait, transform and store: no per-thread
 //     address arithmetic, no cp.async groups, nothing of their own in flight at the proxy fence.
 //
-// Cluster of 2 CTAs, 512 threads each -- roles as in tc_gemm2.cu: w0 bulk-copy issuer (weights), w1 / w3 MMA issuers (leader) or
+// Cluster of 2 CTAs, 512 threads each -- roles as in tc_gemm2.cu: w0 bulk-copy issuer (weights), w1 MMA issuer (leader) / w1 + w3
 // forwarders (peer), w2 row-context filler, w4-7 epilogue, w8-15 producers (gather + rel-xyz term + ReLU + fp16 split).
 #include <cuda.h>
 #include <stdlib.h>
@@ -72,6 +72,9 @@ struct Sc2Args {
 // lane elected at role start (elect.sync).  Under an `if (lane == 0)` the compiler must assume per-thread operands: it wraps EVERY tcgen05.mma
 // in an ELECT / 5 x R2UR.BROADCAST / branch loop, ~100 clk of issue per MMA -- which is what made "MMA issue block at the pipe's rate" in round 1
 // and made a 32-clk layer-3 MMA cost 115.  With uniform operands the descriptors live in uniform registers and the MMAs issue back to back.
+// CAUTION: ptxas turns `@el tcgen05.mma` into ONE unguarded UTCHMMA per pass of the warp through the code (operands broadcast from the elected
+// lane), so the issuer warp must be CONVERGED wherever it issues: it polls its barriers with warp-uniform votes (mbar_test_warp), never per lane
+// (lanes that drifted apart re-issued MMAs with stale uniform registers: launch failure).
 __device__ __forceinline__ uint32_t elect_one() {
     uint32_t el;
     asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\tselp.u32 %0, 1, 0, e;\n\t}" : "=r"(el));
@@ -134,6 +137,9 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     return done != 0;
 }
+// the same as a warp-uniform decision (true only when EVERY lane has observed -- and acquired -- the phase): the issuer warp polls with this, so
+// that its lanes never drift apart and the compiler sees uniform control flow around the MMA issue
+__device__ __forceinline__ bool mbar_test_warp(uint32_t bar, uint32_t parity) { return __all_sync(0xffffffffu, mbar_test(bar, parity)) != 0; }
 
 // max over the K consecutive lanes of a point for 64 channels, as a halving butterfly: at the stage with lane offset `off` a lane keeps one
 // half of its channels and trades the other half with its partner, so the stages cost 32 + 16 + ... shuffles instead of 64 each, and the K
@@ -174,7 +180,7 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
     auto full_bar = [&](int i) { return bar0 + 8 * i; };                 // [4] local: bulk copy (expect_tx) + 8 producer warps
     auto pfull_bar = [&](int i) { return bar0 + 32 + 8 * i; };           // [4] leader: the peer's half of the stage is complete
     auto empty_bar = [&](int i) { return bar0 + 64 + 8 * i; };           // [4] both: stage consumed (MMA commit, multicast)
-    auto tfull_bar = [&](int i) { return bar0 + 96 + 8 * i; };           // [2] both: layer-2 accumulator complete (2 issuers)
+    auto tfull_bar = [&](int i) { return bar0 + 96 + 8 * i; };           // [2] both: layer-2 accumulator complete
     auto tempty_bar = [&](int i) { return bar0 + 112 + 8 * i; };         // [2] leader: 4 + 4 epilogue warps have drained the buffer
     auto a3r_bar = [&](int acc, int g) { return bar0 + 128 + 8 * (acc * 4 + g); };   // [2][4] leader: layer-3 operand group written (4 + 4 warps)
     auto g1done_bar = [&](int i) { return bar0 + 192 + 8 * i; };         // [2] both: the K steps of channels 64..127 have retired
@@ -182,7 +188,6 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
     const uint32_t w3_bar = bar0 + 224;                                  // local: resident W3 slice has landed
     auto ctx_ready_bar = [&](int i) { return base + OFF_CBAR + 8 * i; };
     auto ctx_free_bar = [&](int i) { return base + OFF_CBAR + 24 + 8 * i; };
-    volatile uint32_t *turn = reinterpret_cast<volatile uint32_t *>(smem + OFF_BAR + 232);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 240);
     float4 *sW = reinterpret_cast<float4 *>(smem + OFF_SW);
     int *cidx = reinterpret_cast<int *>(smem + OFF_CS1);
@@ -214,14 +219,12 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(full_bar(i), 1 + 8); mbar_init(pfull_bar(i), 1); mbar_init(empty_bar(i), 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(tfull_bar(i), 2); mbar_init(tempty_bar(i), 8); mbar_init(g1done_bar(i), 1); mbar_init(d3full_bar(i), 1);
+            mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 8); mbar_init(g1done_bar(i), 1); mbar_init(d3full_bar(i), 1);
             for (int g = 0; g < 4; ++g) mbar_init(a3r_bar(i, g), 8);
         }
         mbar_init(w3_bar, 1);
         for (int i = 0; i < PF * 8; ++i) mbar_init(base + OFF_SBAR + 8 * i, 1);
         for (int i = 0; i < 3; ++i) { mbar_init(base + OFF_CBAR + 8 * i, 1); mbar_init(base + OFF_CBAR + 24 + 8 * i, 8); }
-        *turn = 0u;
-        *reinterpret_cast<volatile uint32_t *>(smem + OFF_BAR + 248) = 0u;     // layer-3 cursor
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -250,27 +253,27 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
         }
-    } else if (leader && (warp == 1 || warp == 3)) {
-        // ===== MMA issuers (leader CTA): two warps alternate stages (see tc_gemm2.cu) =====
-        // Layer 3 is issued by whichever issuer owns the pipe (`turn`), in whole operand groups of four K steps (twelve MMAs), right after
-        // its main-loop stage and before the hand-over.  Measured alternatives: a third issuing thread -- or the same thread after the
-        // hand-over -- interleaves its small MMAs one-to-one with the other issuer's big ones in the in-order pipe, every one of them then
-        // waits a full main MMA (~200 clk) and the 48 of a tile stretch the tile's layer-3 chain beyond the next tile's main loop.
-        const int me = warp == 3 ? 1 : 0;
+    } else if (leader && warp == 1) {
+        // ===== MMA issuer (leader CTA): one warp issues the main loop AND layer 3 =====
+        // A single issuing thread fixes the order in which the MMAs enter the in-order tensor pipe, hence the accumulation order and the result
+        // bits (two alternating issuer warps -- round 1 -- are reproducible only while the issue itself is slow: MMAs of different warps may
+        // interleave differently from run to run).  Layer 3 goes out in whole operand groups of four K steps (twelve MMAs) between main-loop
+        // stages and whenever the issuer would otherwise wait.  Measured alternative: a second thread issuing layer 3 interleaves its small
+        // MMAs one-to-one with the big ones, every one of them then waits a full main MMA (~200 clk) and the 48 of a tile stretch the tile's
+        // layer-3 chain beyond the next tile's main loop.
         const uint32_t el = elect_one();                   // the one lane of this warp that issues (and commits) every MMA
         const long long my_tiles = cl_id < ntiles ? (ntiles - cl_id + n_cl - 1) / n_cl : 0;
         const long long l3_tiles = (s.expt == 0 || s.expt == 4) ? my_tiles : 0;
-        volatile uint32_t *l3s = reinterpret_cast<volatile uint32_t *>(smem + OFF_BAR + 248);    // next layer-3 group: tile * 4 + group (owned with `turn`)
+        long long l3_next = 0;                              // next layer-3 group: local tile * 4 + group
         bool w3_ready = false;
         // groups: 0 = K steps 4..7 (channels 64..127, in place), 1 = 8..11, 2 = 12..15, 3 = K steps 0..3 (channels 0..63, parked in the columns
-        // of group 0 once that has retired).  Non-blocking; only the owner of the pipe calls it.
+        // of group 0 once that has retired).  Non-blocking.
         auto serve_l3 = [&]() {
             while (true) {
-                const uint32_t st = __shfl_sync(0xffffffffu, *l3s, 0);              // (broadcast: warp-uniform for the compiler)
-                const long long l3_tile = st >> 2; const int l3_grp = (int)(st & 3u);
+                const long long l3_tile = l3_next >> 2; const int l3_grp = (int)(l3_next & 3);
                 if (l3_tile >= l3_tiles) return;
                 const int acc3 = (int)(l3_tile & 1);
-                if (!mbar_test(a3r_bar(acc3, l3_grp), (uint32_t)((l3_tile >> 1) & 1))) return;
+                if (!mbar_test_warp(a3r_bar(acc3, l3_grp), (uint32_t)((l3_tile >> 1) & 1))) return;
                 if (!w3_ready) { mbar_wait(w3_bar, 0); w3_ready = true; }
                 tc_fence_after();
                 const uint32_t d3 = tmem_base + acc3 * 256;
@@ -291,70 +294,58 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                 }
                 if (l3_grp == 0) commit2_mc(el, g1done_bar(acc3));
                 if (l3_grp == 3) commit2_mc(el, d3full_bar(acc3));
-                __syncwarp();
-                if (lane == 0) *l3s = st + 1;                   // (tile, 3) + 1 = (tile + 1, 0)
-                __syncwarp();
+                ++l3_next;                                  // (tile, 3) + 1 = (tile + 1, 0)
             }
         };
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        uint32_t g = 0;
         for (long long t = cl_id; t < ntiles; t += n_cl) {
             const uint32_t d2 = tmem_base + acc * 256;
-            for (int ks = 0; ks < nks; ++ks, ++g) {
-                if ((int)(g & 1u) == me) {
-                    {   // my operands (both halves) and the pipe; once the pipe is mine, pending layer-3 groups go out while I wait
-                        unsigned spins = 0; unsigned long long t0 = 0ull;
-                        const long long c0_ = a.dbg ? clock64() : 0;
-                        bool have_full = false, have_peer = false;
-                        while (true) {
-                            if (!have_full) have_full = mbar_test(full_bar(stage), phase);
-                            if (!have_peer) have_peer = mbar_test(pfull_bar(stage), phase);
-                            const bool mine = *turn == g;
-                            if (have_full && have_peer && mine) break;
-                            if (mine) serve_l3();
-                            watchdog(spins, t0);
-                        }
-                        if (a.dbg) dw1 += clock64() - c0_;
+            for (int ks = 0; ks < nks; ++ks) {
+                {   // the stage's operands (both halves); pending layer-3 groups go out while I wait
+                    unsigned spins = 0; unsigned long long t0 = 0ull;
+                    const long long c0_ = a.dbg ? clock64() : 0;
+                    bool have_full = false, have_peer = false;
+                    while (true) {
+                        if (!have_full) have_full = mbar_test_warp(full_bar(stage), phase);
+                        if (!have_peer) have_peer = mbar_test_warp(pfull_bar(stage), phase);
+                        if (have_full && have_peer) break;
+                        serve_l3();
+                        watchdog(spins, t0);
                     }
-                    if (ks == 0) {
-                        // the accumulator buffer comes back only when ITS layer 3 is done, and layer 3 is issued by the owner of the pipe: me
-                        unsigned spins = 0; unsigned long long t0 = 0ull;
-                        const long long c0_ = a.dbg ? clock64() : 0;
-                        while (!mbar_test(tempty_bar(acc), acc_phase ^ 1)) { serve_l3(); watchdog(spins, t0); }
-                        if (a.dbg) dw0 += clock64() - c0_;
-                    }
-                    tc_fence_after();
-                    {
-                        const uint32_t sa = base + stage * STAGE_BYTES;
-                        const uint64_t w_hi = make_desc(sa), w_lo = make_desc(sa + TILE_BYTES);
-                        const uint64_t x_hi = make_desc(sa + 2 * TILE_BYTES), x_lo = make_desc(sa + 3 * TILE_BYTES);
-#pragma unroll
-                        for (int k16 = 0; k16 < 2; ++k16) {
-                            const uint64_t adv = (uint64_t)(k16 * 2);             // 32 bytes = 16 halfs, in 16-byte descriptor units
-                            mma2_ss(el, d2, x_lo + adv, w_hi + adv, IDESC_L2, (ks | k16) ? 1u : 0u);
-                            mma2_ss_keep(el, d2, x_hi + adv, w_lo + adv, IDESC_L2);
-                            mma2_ss_reuse(el, d2, x_hi + adv, w_hi + adv, IDESC_L2);
-                        }
-                        commit2_mc(el, empty_bar(stage));
-                        if (ks >= nks - 2 || nks == 1) commit2_mc(el, tfull_bar(acc));   // both issuers' MMAs of the tile must have retired
-                    }
-                    __syncwarp();
-                    serve_l3();                                                          // whole groups, still owning the pipe
-                    __threadfence_block();
-                    if (lane == 0) *turn = g + 1;
-                    __syncwarp();
-                } else if (nks == 1) {
-                    commit2_mc(el, tfull_bar(acc));
+                    if (a.dbg) dw1 += clock64() - c0_;
                 }
+                if (ks == 0) {
+                    // the accumulator buffer comes back only when ITS layer 3 is done, and layer 3 is issued here
+                    unsigned spins = 0; unsigned long long t0 = 0ull;
+                    const long long c0_ = a.dbg ? clock64() : 0;
+                    while (!mbar_test_warp(tempty_bar(acc), acc_phase ^ 1)) { serve_l3(); watchdog(spins, t0); }
+                    if (a.dbg) dw0 += clock64() - c0_;
+                }
+                __syncwarp();
+                tc_fence_after();
+                {
+                    const uint32_t sa = base + stage * STAGE_BYTES;
+                    const uint64_t w_hi = make_desc(sa), w_lo = make_desc(sa + TILE_BYTES);
+                    const uint64_t x_hi = make_desc(sa + 2 * TILE_BYTES), x_lo = make_desc(sa + 3 * TILE_BYTES);
+#pragma unroll
+                    for (int k16 = 0; k16 < 2; ++k16) {
+                        const uint64_t adv = (uint64_t)(k16 * 2);             // 32 bytes = 16 halfs, in 16-byte descriptor units
+                        mma2_ss(el, d2, x_lo + adv, w_hi + adv, IDESC_L2, (ks | k16) ? 1u : 0u);
+                        mma2_ss_keep(el, d2, x_hi + adv, w_lo + adv, IDESC_L2);
+                        mma2_ss_reuse(el, d2, x_hi + adv, w_hi + adv, IDESC_L2);
+                    }
+                    commit2_mc(el, empty_bar(stage));
+                    if (ks == nks - 1) commit2_mc(el, tfull_bar(acc));
+                }
+                serve_l3();                                                          // whole groups between main-loop stages
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (me == 0) {                                      // drain: layer 3 of the last tile(s), once the other issuer has finished too
+        {                                                   // drain: layer 3 of the last tile(s)
             unsigned spins = 0; unsigned long long t0 = 0ull;
-            while (*turn != g) watchdog(spins, t0);
-            while ((long long)(*l3s >> 2) < l3_tiles) { serve_l3(); watchdog(spins, t0); }
+            while ((l3_next >> 2) < l3_tiles) { serve_l3(); watchdog(spins, t0); }
             if (a.dbg && lane == 0) { a.dbg[(size_t)blockIdx.x * 8 + 1] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 2] = dw1; a.dbg[(size_t)blockIdx.x * 8 + 3] = dw2; }
         }
     } else if (warp == 2) {
@@ -381,7 +372,7 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
             if (lane == 0) mbar_arrive(ctx_ready_bar(slot));
             ++fi;
         }
-    } else if (warp == 1 || warp == 3) {
+    } else if (!leader && (warp == 1 || warp == 3)) {
         // ===== forwarders (peer CTA): relay "my half of stage s is complete" to the leader =====
         const int me = warp == 3 ? 1 : 0;
         int stage = 0; uint32_t phase = 0;
@@ -503,7 +494,7 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (a.dbg && warp == 4 && lane == 0) { a.dbg[(size_t)blockIdx.x * 8 + 4] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 5] = dw1; a.dbg[(size_t)blockIdx.x * 8 + 6] = dw2; }
-    } else {
+    } else if (warp >= 8) {
         // ===== producers (256 threads): this CTA's 128 activation rows, one 32-channel K block per iteration (as tc_gemm2.cu, SC2_Y1) =====
         const int p = threadIdx.x - 256;
         const int pw = p >> 5;
