@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcmflow_b200.so")
+# CMF_LIB: developer A/B switch -- another build of the SAME library (cmflow_b200.build.build_variant), never a different implementation
+LIB_PATH = os.environ.get("CMF_LIB") or os.path.join(_HERE, "libcmflow_b200.so")
 _lib = None
 
 _vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t

@@ -57,5 +57,25 @@ def build(verbose=False, force=False, ptxas_v=False):
     return LIB
 
 
+def build_variant(tag, defines, files):
+    """Developer A/B builds: libcmflow_b200_<tag>.so with `files` (basenames under csrc/) recompiled under extra -D defines, every other
+    object shared with the main build.  Select it at run time with CMF_LIB=<path> (see _lib.py)."""
+    build()
+    vobj = os.path.join(HERE, "_obj_" + tag)
+    os.makedirs(vobj, exist_ok=True)
+    objs = []
+    for s in sources():
+        base = os.path.basename(s)
+        if base in files:
+            o = os.path.join(vobj, base[:-3] + ".o")
+            subprocess.check_call(["nvcc"] + ARCH + FLAGS + ["-D" + d for d in defines] + ["-c", s, "-o", o])
+        else:
+            o = os.path.join(OBJ, base[:-3] + ".o")
+        objs.append(o)
+    out = os.path.join(HERE, "libcmflow_b200_%s.so" % tag)
+    subprocess.check_call(["nvcc", "-shared"] + ARCH + ["-o", out] + objs)
+    return out
+
+
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv, force="--force" in sys.argv, ptxas_v="--ptxas" in sys.argv))

@@ -570,7 +570,7 @@ static int forward_chunk(cmf_model *m, int bc, int n, int n2, const float *pc1, 
                         cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
                         double av[8] = {0}; int nb = 0;
                         for (int b = 0; b < 512; b += 2) if (h[b * 8]) { ++nb; for (int k = 0; k < 8; ++k) av[k] += (double)h[b * 8 + k]; }
-                        if (nb) fprintf(stderr, "sc2 fused K=%d leaders=%d cycles: total %.0f | issuer0 tempty %.0f full %.0f turn %.0f | epilogue tfull %.0f g1done %.0f d3full %.0f | producer empty %.0f\n",
+                        if (nb) fprintf(stderr, "sc2 fused K=%d leaders=%d cycles: total %.0f | issuer tempty %.0f operands %.0f | producer gather %.0f | epilogue tfull %.0f g1done %.0f d3full %.0f | producer empty %.0f\n",
                                         KS[s], nb, av[0] / nb, av[1] / nb, av[2] / nb, av[3] / nb, av[4] / nb, av[5] / nb, av[6] / nb, av[7] / nb);
                     }
                     continue;

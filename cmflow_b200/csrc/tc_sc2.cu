@@ -41,9 +41,18 @@ namespace {
 constexpr int HALF_ROWS = 128;                       // activation rows (neighbour columns) per CTA
 constexpr int TILE_BYTES = 128 * 64;                 // 128 rows x 32 halfs: 8 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;          // W hi, W lo, X hi, X lo: 32 KB
-constexpr int NSTAGE = 4;
+#ifndef SC2_NSTAGE
+#define SC2_NSTAGE 4
+#endif
+#ifndef SC2_POLL_SLEEP
+#define SC2_POLL_SLEEP 0
+#endif
+#ifndef SC2_PF
+#define SC2_PF 3
+#endif
+constexpr int NSTAGE = SC2_NSTAGE;
 constexpr int NTHREADS = 512;
-constexpr int PF = 3;                                // staging ring depth (K blocks): two gathers in flight per producer warp
+constexpr int PF = SC2_PF;                           // staging ring depth (K blocks): PF - 1 gathers in flight per producer warp
 constexpr int STG_BYTES = PF * HALF_ROWS * 128;      // 48 KB: [ring][128 rows][32 floats], rows in tile order
 constexpr int W3_KB = 8;                             // 256 channels = 8 K blocks of 32
 constexpr int W3_BYTES = W3_KB * 2 * 2048;           // this CTA's 32 rows of W3: per K block {hi 2 KB, lo 2 KB}
@@ -102,15 +111,7 @@ __device__ __forceinline__ void mma2_ts(uint32_t el, uint32_t d, uint32_t a_tmem
     asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
                  "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(el) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-// the same load without the wait: tmem_ld16_done() is the wait plus a register dependency, so that one load can be in flight under
+// TMEM load without the wait: tmem_ld16_done() is the wait plus a register dependency, so that one load can be in flight under
 // the arithmetic on the previous one
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -198,7 +199,7 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;      // broadcast: the compiler then knows the role branches are warp-uniform
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
-    // optional wait-time instrumentation (a.dbg = long long[gridDim.x][8]): {total, issuer0: tempty, full + peer, turn | epilogue warp 4: tfull,
+    // optional wait-time instrumentation (a.dbg = long long[gridDim.x][8]): {total, issuer: tempty, full + peer | producer warp 8: gathered rows | epilogue warp 4: tfull,
     // g1done, d3full | producer warp 8: empty}
     const long long t_start = a.dbg ? clock64() : 0;
     long long dw0 = 0, dw1 = 0, dw2 = 0;
@@ -311,6 +312,7 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                         if (!have_peer) have_peer = mbar_test_warp(pfull_bar(stage), phase);
                         if (have_full && have_peer) break;
                         serve_l3();
+                        if (SC2_POLL_SLEEP) __nanosleep(SC2_POLL_SLEEP);                 // an always-eligible polling warp takes issue slots from the producers of its scheduler
                         watchdog(spins, t0);
                     }
                     if (a.dbg) dw1 += clock64() - c0_;
@@ -346,7 +348,7 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
         {                                                   // drain: layer 3 of the last tile(s)
             unsigned spins = 0; unsigned long long t0 = 0ull;
             while ((l3_next >> 2) < l3_tiles) { serve_l3(); watchdog(spins, t0); }
-            if (a.dbg && lane == 0) { a.dbg[(size_t)blockIdx.x * 8 + 1] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 2] = dw1; a.dbg[(size_t)blockIdx.x * 8 + 3] = dw2; }
+            if (a.dbg && lane == 0) { a.dbg[(size_t)blockIdx.x * 8 + 1] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 2] = dw1; }
         }
     } else if (warp == 2) {
         // ===== row contexts: neighbour index -> row of P, rel-xyz, fp16 scale, up to three tiles ahead of the producers =====
@@ -505,6 +507,9 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
         const uint32_t sbar_w = base + OFF_SBAR + pw * 8;           // this warp's barrier of ring slot r at + r * 64
         int stage = 0; uint32_t phase = 0;
         // four rows x 128 bytes per instruction, rows picked by index: the warp's 16 rows of K block kb of the tile whose contexts sit in `lbuf`
+        // four rows x 128 bytes per instruction, rows picked by index: the warp's 16 rows of K block kb of the tile whose contexts sit in `lbuf`.
+        // (Measured alternative: holding the 16 indices in registers for the whole tile instead of re-reading them from shared memory per K block
+        // made the kernel 5 % SLOWER -- 16 more live registers in a 128-register kernel.)
         auto issue = [&](int kb, int ring, int lbuf) {
             if (lane == 0) {
                 const int4 *ip = reinterpret_cast<const int4 *>(cidx + lbuf * HALF_ROWS + pw * 16);
@@ -551,7 +556,7 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                     }
                     const float4 *wp = sW + kb * 24 + q;
                     const float4 wx = wp[0], wy = wp[8], wz = wp[16];
-                    mbar_wait(sbar_w + ring * 64, rphase);
+                    TIMED(dw1, mbar_wait(sbar_w + ring * 64, rphase));
                     float4 v[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) v[i] = lds16(stg_t + ring * 16384 + i * 512);
@@ -590,7 +595,7 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                 mbar_wait(ctx_ready_bar(buf), (uint32_t)((ti / 3) & 1));
             }
         }
-        if (a.dbg && warp == 8 && lane == 0) a.dbg[(size_t)blockIdx.x * 8 + 7] = dw0;
+        if (a.dbg && warp == 8 && lane == 0) { a.dbg[(size_t)blockIdx.x * 8 + 7] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 3] = dw1; }
     }
     if (a.dbg && threadIdx.x == 0) a.dbg[(size_t)blockIdx.x * 8 + 0] = clock64() - t_start;
 #undef TIMED
