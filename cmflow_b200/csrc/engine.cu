@@ -561,17 +561,21 @@ static int forward_chunk(cmf_model *m, int bc, int n, int n2, const float *pc1, 
                 if (sc2_fused(m)) {      // layers 2 + 3 + max over K in one kernel: the 256-channel layer-2 output stays in tensor memory
                     static long long *dbg_buf = nullptr;                 // CMF_SC2_DBG=1: per-role wait cycles of the fused kernel on stderr (diagnostic)
                     const bool dbg = getenv("CMF_SC2_DBG") != nullptr;
-                    if (dbg) { if (!dbg_buf) cudaMalloc(&dbg_buf, 512 * 8 * sizeof(long long)); cudaMemsetAsync(dbg_buf, 0, 512 * 8 * sizeof(long long), st); ta_.dbg = dbg_buf; }
+                    if (dbg) { if (!dbg_buf) cudaMalloc(&dbg_buf, 512 * 16 * sizeof(long long)); cudaMemsetAsync(dbg_buf, 0, 512 * 16 * sizeof(long long), st); ta_.dbg = dbg_buf; }
                     RUN(C_GEMM_SC2_L2L3, tflops(ta_, 512) + 2.0 * 64 * 256.0 * (double)ta_.cols,
                         cmf_launch_sc2_fused(ta_, T.m2_w3[s].wt, T.m2_w3[s].ainv, S(sb + 3), w.M64 + s * 64, 256, st));
                     if (dbg) {
-                        std::vector<long long> h(512 * 8);
+                        std::vector<long long> h(512 * 16);
                         cudaStreamSynchronize(st);
                         cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-                        double av[8] = {0}; int nb = 0;
-                        for (int b = 0; b < 512; b += 2) if (h[b * 8]) { ++nb; for (int k = 0; k < 8; ++k) av[k] += (double)h[b * 8 + k]; }
-                        if (nb) fprintf(stderr, "sc2 fused K=%d leaders=%d cycles: total %.0f | issuer tempty %.0f operands %.0f | producer gather %.0f | epilogue tfull %.0f g1done %.0f d3full %.0f | producer empty %.0f\n",
-                                        KS[s], nb, av[0] / nb, av[1] / nb, av[2] / nb, av[3] / nb, av[4] / nb, av[5] / nb, av[6] / nb, av[7] / nb);
+                        double av[16] = {0}; int nb = 0;
+                        for (int b = 0; b < 512; b += 2) if (h[b * 16]) { ++nb; for (int k = 0; k < 16; ++k) av[k] += (double)h[b * 16 + k]; }
+                        if (nb) {
+                            fprintf(stderr, "sc2 fused K=%d leaders=%d cycles: total %.0f | issuer tempty %.0f operands %.0f | producer gather %.0f | epilogue tfull %.0f g1done %.0f d3full %.0f | producer empty %.0f\n",
+                                    KS[s], nb, av[0] / nb, av[1] / nb, av[2] / nb, av[3] / nb, av[4] / nb, av[5] / nb, av[6] / nb, av[7] / nb);
+                            if (av[9] > 0) fprintf(stderr, "    producer sections (SC2_PROD_PROFILE build): gather issue %.0f | loads + arithmetic %.0f | stores %.0f | proxy fence %.0f | arrive + bookkeeping %.0f\n",
+                                                   av[8] / nb, av[9] / nb, av[10] / nb, av[11] / nb, av[12] / nb);
+                        }
                     }
                     continue;
                 }

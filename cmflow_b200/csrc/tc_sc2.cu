@@ -22,10 +22,12 @@
 //     (the main loop's next-but-one tile needs the buffer back, so a blocking wait there would deadlock).
 //
 //   * THE NEIGHBOUR GATHER IS TMA.  The hoisted layer-1 matrix P (one 512-float row slice per point and scale) is described by a 2-D tensor
-//     map (box = 32 floats x 1 row); cp.async.bulk.tensor.2d ... tile::gather4 fetches four arbitrary rows x 128 bytes per instruction into a
-//     staging ring, completing on an mbarrier by byte count.  Each producer warp issues the four gathers of its own 16 rows (one elected
-//     lane, two K blocks ahead) and waits only on its own barrier, so the 256 producer threads just wait, transform and store: no per-thread
-//     address arithmetic, no cp.async groups, nothing of their own in flight at the proxy fence.
+//     map (box = 64 floats x 1 row); cp.async.bulk.tensor.2d ... tile::gather4 fetches four arbitrary rows x 256 bytes per instruction -- two
+//     K blocks of each row -- into a staging ring, completing on an mbarrier by byte count.  Each producer warp issues the four gathers of
+//     its own 16 rows (one elected lane, one group of two K blocks ahead) and waits only on its own barrier, so the 256 producer threads
+//     just wait, transform and store: no per-thread address arithmetic, no cp.async groups, nothing of their own in flight at the proxy
+//     fence.  A gather instruction costs its warp ~150 clk whatever the box width: with one K block per gather the issue alone was 46 % of
+//     the producers' busy time and the kernel ran at the producers' pace, not the tensor pipe's.
 //
 // Cluster of 2 CTAs, 512 threads each -- roles as in tc_gemm2.cu: w0 bulk-copy issuer (weights), w1 MMA issuer (leader) / w1 + w3
 // forwarders (peer), w2 row-context filler, w4-7 epilogue, w8-15 producers (gather + rel-xyz term + ReLU + fp16 split).
@@ -42,23 +44,32 @@ constexpr int HALF_ROWS = 128;                       // activation rows (neighbo
 constexpr int TILE_BYTES = 128 * 64;                 // 128 rows x 32 halfs: 8 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;          // W hi, W lo, X hi, X lo: 32 KB
 #ifndef SC2_NSTAGE
-#define SC2_NSTAGE 4
+#define SC2_NSTAGE 3
 #endif
 #ifndef SC2_POLL_SLEEP
 #define SC2_POLL_SLEEP 0
 #endif
 #ifndef SC2_PF
-#define SC2_PF 3
+#define SC2_PF 2
+#endif
+#ifndef SC2_GK
+#define SC2_GK 2
 #endif
 constexpr int NSTAGE = SC2_NSTAGE;
 constexpr int NTHREADS = 512;
-constexpr int PF = SC2_PF;                           // staging ring depth (K blocks): PF - 1 gathers in flight per producer warp
-constexpr int STG_BYTES = PF * HALF_ROWS * 128;      // 48 KB: [ring][128 rows][32 floats], rows in tile order
+// Gather granularity.  One tile::gather4 instruction costs the issuing warp ~150 clk whatever its box width (measured with the section
+// timers below: four 32-float boxes per K block were 46 % of a producer warp's busy time), so a gather fetches GK K blocks of a row at
+// once (box = 32 * GK floats) and the staging ring holds PF such groups: 4 instructions per warp per GK K blocks.
+constexpr int GK = SC2_GK;                           // K blocks per gather
+constexpr int PF = SC2_PF;                           // staging ring depth in gather groups: PF - 1 groups in flight per producer warp
+constexpr int ROW_BYTES = 128 * GK;                  // staged bytes per row and group
+constexpr int SLOT_BYTES = HALF_ROWS * ROW_BYTES;    // 32 KB: [128 rows][32 * GK floats], rows in tile order
+constexpr int STG_BYTES = PF * SLOT_BYTES;           // 64 KB
 constexpr int W3_KB = 8;                             // 256 channels = 8 K blocks of 32
 constexpr int W3_BYTES = W3_KB * 2 * 2048;           // this CTA's 32 rows of W3: per K block {hi 2 KB, lo 2 KB}
-constexpr int OFF_STG = NSTAGE * STAGE_BYTES;        // 131072
-constexpr int OFF_W3 = OFF_STG + STG_BYTES;          // 180224
-constexpr int OFF_BAR = OFF_W3 + W3_BYTES;           // 212992
+constexpr int OFF_STG = NSTAGE * STAGE_BYTES;        // 98304
+constexpr int OFF_W3 = OFF_STG + STG_BYTES;          // 163840
+constexpr int OFF_BAR = OFF_W3 + W3_BYTES;           // 196608
 constexpr int OFF_SW = OFF_BAR + 256;                // rel-xyz weights: 16 K blocks x 24 float4 = 6 KB
 constexpr int OFF_CS1 = OFF_SW + 6144;               // gathered-row indices (rows of P) [3][128] int
 constexpr int OFF_GEO = OFF_CS1 + 3 * HALF_ROWS * 4; // {dx, dy, dz, scale} [3][128]
@@ -199,7 +210,7 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;      // broadcast: the compiler then knows the role branches are warp-uniform
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
-    // optional wait-time instrumentation (a.dbg = long long[gridDim.x][8]): {total, issuer: tempty, full + peer | producer warp 8: gathered rows | epilogue warp 4: tfull,
+    // optional wait-time instrumentation (a.dbg = long long[gridDim.x][16]): {total, issuer: tempty, full + peer | producer warp 8: gathered rows | epilogue warp 4: tfull,
     // g1done, d3full | producer warp 8: empty}
     const long long t_start = a.dbg ? clock64() : 0;
     long long dw0 = 0, dw1 = 0, dw2 = 0;
@@ -348,7 +359,7 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
         {                                                   // drain: layer 3 of the last tile(s)
             unsigned spins = 0; unsigned long long t0 = 0ull;
             while ((l3_next >> 2) < l3_tiles) { serve_l3(); watchdog(spins, t0); }
-            if (a.dbg && lane == 0) { a.dbg[(size_t)blockIdx.x * 8 + 1] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 2] = dw1; }
+            if (a.dbg && lane == 0) { a.dbg[(size_t)blockIdx.x * 16 + 1] = dw0; a.dbg[(size_t)blockIdx.x * 16 + 2] = dw1; }
         }
     } else if (warp == 2) {
         // ===== row contexts: neighbour index -> row of P, rel-xyz, fp16 scale, up to three tiles ahead of the producers =====
@@ -495,33 +506,39 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
             arrive_leader(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (a.dbg && warp == 4 && lane == 0) { a.dbg[(size_t)blockIdx.x * 8 + 4] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 5] = dw1; a.dbg[(size_t)blockIdx.x * 8 + 6] = dw2; }
+        if (a.dbg && warp == 4 && lane == 0) { a.dbg[(size_t)blockIdx.x * 16 + 4] = dw0; a.dbg[(size_t)blockIdx.x * 16 + 5] = dw1; a.dbg[(size_t)blockIdx.x * 16 + 6] = dw2; }
     } else if (warp >= 8) {
         // ===== producers (256 threads): this CTA's 128 activation rows, one 32-channel K block per iteration (as tc_gemm2.cu, SC2_Y1) =====
-        const int p = threadIdx.x - 256;
-        const int pw = p >> 5;
+        const int pw = warp - 8;                                    // warp-uniform (warp is a broadcast value)
+        const uint32_t el = elect_one();                            // the lane that issues this warp's gathers
         const int q = lane & 7, rsub = lane >> 3;
         const int row0 = pw * 16 + rsub;                            // this thread's rows: row0 + 4*i
-        const uint32_t stg_w = base + OFF_STG + pw * 2048;          // this warp's 16 rows of ring slot r at + r * 16384
-        const uint32_t stg_t = stg_w + rsub * 128 + q * 16;         // this thread's 16-byte chunk of row 4*i + rsub at + i * 512
+        const uint32_t stg_w = base + OFF_STG + pw * 16 * ROW_BYTES; // this warp's 16 rows of ring slot r at + r * SLOT_BYTES
+        const uint32_t stg_t = stg_w + rsub * ROW_BYTES + q * 16;   // this thread's 16-byte chunk of row 4*i + rsub at + i * 4 * ROW_BYTES, K block h of the group at + h * 128
         const uint32_t sbar_w = base + OFF_SBAR + pw * 8;           // this warp's barrier of ring slot r at + r * 64
         int stage = 0; uint32_t phase = 0;
-        // four rows x 128 bytes per instruction, rows picked by index: the warp's 16 rows of K block kb of the tile whose contexts sit in `lbuf`
-        // four rows x 128 bytes per instruction, rows picked by index: the warp's 16 rows of K block kb of the tile whose contexts sit in `lbuf`.
-        // (Measured alternative: holding the 16 indices in registers for the whole tile instead of re-reading them from shared memory per K block
-        // made the kernel 5 % SLOWER -- 16 more live registers in a 128-register kernel.)
-        auto issue = [&](int kb, int ring, int lbuf) {
-            if (lane == 0) {
-                const int4 *ip = reinterpret_cast<const int4 *>(cidx + lbuf * HALF_ROWS + pw * 16);
-                const uint32_t dst = stg_w + ring * 16384, bar = sbar_w + ring * 64;
-                const int col = a.off_u2 + kb * PK;
-                mbar_arrive_expect_tx(bar, 2048);
+#ifdef SC2_PROD_PROFILE
+        long long ps0 = 0, ps1 = 0, ps2 = 0, ps3 = 0, ps4 = 0;      // producer sections: gather issue | loads + arithmetic | stores | proxy fence | arrive
+#endif
+        // four rows x (128 * GK) bytes per instruction, rows picked by index: the warp's 16 rows of gather group kg (K blocks kg * GK ...) of the
+        // tile whose contexts sit in `lbuf`.  (Measured alternative: holding the 16 indices in registers for the whole tile instead of re-reading
+        // them from shared memory per gather made the kernel 5 % SLOWER -- 16 more live registers in a 128-register kernel.)
+        // Issued like the MMAs (see ISSUE DISCIPLINE): the whole warp runs this in uniform control flow with warp-uniform operands and the
+        // instructions are predicated on the elected lane.  Under `if (lane == 0)` every UTMALDG sat in an ELECT / 7 x R2UR.BROADCAST /
+        // branch loop: ~180 clk per gather, 46 % of a producer warp's busy time (section timers, SC2_PROD_PROFILE).
+        auto issue = [&](int kg, int ring, int lbuf) {
+            const int4 *ip = reinterpret_cast<const int4 *>(cidx + lbuf * HALF_ROWS + pw * 16);      // warp-uniform address: broadcast loads
+            const uint32_t dst = stg_w + ring * SLOT_BYTES, bar = sbar_w + ring * 64;
+            const int col = a.off_u2 + kg * (PK * GK);
+            __syncwarp();
+            asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+                         ::"r"(bar), "r"(16 * ROW_BYTES), "r"(el) : "memory");
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int4 id = ip[i];
-                    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-                                 ::"r"(dst + i * 512), "l"(&tmapP), "r"(col), "r"(id.x), "r"(id.y), "r"(id.z), "r"(id.w), "r"(bar) : "memory");
-                }
+            for (int i = 0; i < 4; ++i) {
+                const int4 id = ip[i];
+                asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %8, 0;\n\t"
+                             "@q cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n\t}"
+                             ::"r"(dst + i * 4 * ROW_BYTES), "l"(&tmapP), "r"(col), "r"(id.x), "r"(id.y), "r"(id.z), "r"(id.w), "r"(bar), "r"(el) : "memory");
             }
         };
         auto lds16 = [&](uint32_t addr) {
@@ -534,8 +551,9 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
             int buf = 0, ring = 0; uint32_t rphase = 0;             // ring slot being consumed and the parity of its barrier
             long long ti = 0, la_i = 0;                             // local tile numbers of the current tile and of the look-ahead cursor
             mbar_wait(ctx_ready_bar(0), 0);                         // contexts of the first tile are in place (warp 2)
-            for (int g = 0; g < PF - 1; ++g) issue(g, g, 0);        // k_blocks = 16 >= PF - 1: all inside the first tile
-            int la_buf = 0, la_kb = PF - 1; long long la_t = t;     // look-ahead cursor: K block (current + PF - 1)
+            const int n_groups = a.k_blocks / GK;                   // 8 gather groups per tile
+            for (int g = 0; g < PF - 1; ++g) issue(g, g, 0);        // n_groups >= PF - 1: all inside the first tile
+            int la_buf = 0, la_kg = PF - 1; long long la_t = t;     // look-ahead cursor: gather group (current + PF - 1)
             while (true) {
                 const long long tn = t + n_cl;
                 float4 geo[4];
@@ -545,21 +563,32 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                     geo[i] = make_float4(g.x * g.w, g.y * g.w, g.z * g.w, g.w);
                 }
                 for (int kb = 0; kb < a.k_blocks; ++kb) {
-                    {   // keep PF - 1 K blocks in flight: refill the slot consumed in the previous iteration (its reads are done: their
+#ifdef SC2_PROD_PROFILE
+                    const long long pc0 = clock64();
+#endif
+                    const int hk = kb % GK;                           // K block within its gather group
+                    if (hk == 0) {
+                        // keep PF - 1 groups in flight: refill the slot consumed during the previous group (its reads are done: their
                         // results were stored below, and the proxy fence there orders them before this asynchronous write)
                         int lring = ring + PF - 1; if (lring >= PF) lring -= PF;
-                        if (la_t < ntiles) issue(la_kb, lring, la_buf);
-                        if (++la_kb == a.k_blocks) {                // the cursor moves on to the next tile: its contexts must have been filled
-                            la_kb = 0; la_buf = la_buf == 2 ? 0 : la_buf + 1; la_t += n_cl; ++la_i;
+                        if (la_t < ntiles) issue(la_kg, lring, la_buf);
+                        if (++la_kg == n_groups) {                  // the cursor moves on to the next tile: its contexts must have been filled
+                            la_kg = 0; la_buf = la_buf == 2 ? 0 : la_buf + 1; la_t += n_cl; ++la_i;
                             if (la_t < ntiles) mbar_wait(ctx_ready_bar(la_buf), (uint32_t)((la_i / 3) & 1));
                         }
                     }
                     const float4 *wp = sW + kb * 24 + q;
                     const float4 wx = wp[0], wy = wp[8], wz = wp[16];
-                    TIMED(dw1, mbar_wait(sbar_w + ring * 64, rphase));
+#ifdef SC2_PROD_PROFILE
+                    const long long pc1 = clock64(); ps0 += pc1 - pc0;
+#endif
+                    if (hk == 0) { TIMED(dw1, mbar_wait(sbar_w + ring * 64, rphase)); }      // the whole group lands on one barrier
+#ifdef SC2_PROD_PROFILE
+                    const long long pc2 = clock64();
+#endif
                     float4 v[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) v[i] = lds16(stg_t + ring * 16384 + i * 512);
+                    for (int i = 0; i < 4; ++i) v[i] = lds16(stg_t + ring * SLOT_BYTES + i * 4 * ROW_BYTES + hk * 128);
                     uint2 hh[4], ll[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -573,7 +602,13 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                         xa = make_float2(fmaxf(xa.x, 0.f), fmaxf(xa.y, 0.f)); xb = make_float2(fmaxf(xb.x, 0.f), fmaxf(xb.y, 0.f));
                         split_f16x2(xa, hh[i].x, ll[i].x); split_f16x2(xb, hh[i].y, ll[i].y);
                     }
+#ifdef SC2_PROD_PROFILE
+                    const long long pc3 = clock64(); ps1 += pc3 - pc2;
+#endif
                     TIMED(dw0, mbar_wait(empty_bar(stage), phase ^ 1));
+#ifdef SC2_PROD_PROFILE
+                    const long long pc4 = clock64();
+#endif
                     uint8_t *Xhi = smem + stage * STAGE_BYTES + 2 * TILE_BYTES;
                     uint8_t *Xlo = Xhi + TILE_BYTES;
 #pragma unroll
@@ -582,11 +617,20 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                         *reinterpret_cast<uint2 *>(Xhi + off) = hh[i];
                         *reinterpret_cast<uint2 *>(Xlo + off) = ll[i];
                     }
+#ifdef SC2_PROD_PROFILE
+                    const long long pc5 = clock64(); ps2 += pc5 - pc4;
+#endif
                     fence_async_smem();
+#ifdef SC2_PROD_PROFILE
+                    const long long pc6 = clock64(); ps3 += pc6 - pc5;
+#endif
                     __syncwarp();
                     if (lane == 0) mbar_arrive(full_bar(stage));
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                    if (++ring == PF) { ring = 0; rphase ^= 1; }
+                    if (hk == GK - 1 && ++ring == PF) { ring = 0; rphase ^= 1; }
+#ifdef SC2_PROD_PROFILE
+                    ps4 += clock64() - pc6;
+#endif
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(ctx_free_bar(buf));      // this warp is done with the tile's contexts
@@ -595,9 +639,15 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                 mbar_wait(ctx_ready_bar(buf), (uint32_t)((ti / 3) & 1));
             }
         }
-        if (a.dbg && warp == 8 && lane == 0) { a.dbg[(size_t)blockIdx.x * 8 + 7] = dw0; a.dbg[(size_t)blockIdx.x * 8 + 3] = dw1; }
+        if (a.dbg && warp == 8 && lane == 0) { a.dbg[(size_t)blockIdx.x * 16 + 7] = dw0; a.dbg[(size_t)blockIdx.x * 16 + 3] = dw1; }
+#ifdef SC2_PROD_PROFILE
+        if (a.dbg && warp == 8 && lane == 0) {
+            long long *d = a.dbg + (size_t)blockIdx.x * 16 + 8;
+            d[0] = ps0; d[1] = ps1; d[2] = ps2; d[3] = ps3; d[4] = ps4;
+        }
+#endif
     }
-    if (a.dbg && threadIdx.x == 0) a.dbg[(size_t)blockIdx.x * 8 + 0] = clock64() - t_start;
+    if (a.dbg && threadIdx.x == 0) a.dbg[(size_t)blockIdx.x * 16 + 0] = clock64() - t_start;
 #undef TIMED
     tc_fence_before();
     cluster_sync_all();                         // nobody frees TMEM / exits while the pair still uses it
@@ -622,9 +672,9 @@ static int make_row_gather_map(CUtensorMap *tm, const float *base, long long row
         }
         enc = (EncodeTiledFn)fn;
     }
-    // rows x ld floats, row pitch ld * 4 bytes; box = 32 floats x 1 row: tile::gather4 fetches four such boxes at four row indices
+    // rows x ld floats, row pitch ld * 4 bytes; box = 32 * GK floats x 1 row: tile::gather4 fetches four such boxes at four row indices
     const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows}, gstride[1] = {(cuuint64_t)ld * 4};
-    const cuuint32_t box[2] = {32, 1}, estr[2] = {1, 1};
+    const cuuint32_t box[2] = {32 * GK, 1}, estr[2] = {1, 1};
     const CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) { cmf_set_error("sc2 fused: cuTensorMapEncodeTiled failed (%d)", (int)rc); return CMF_ERR_CUDA; }
