@@ -111,7 +111,6 @@ void carve(Arena &a, Work &w, int bc, int n, const CarveOpts &o) {
     w.BQ1 = a.take<int>(bn * 60); w.BQ2 = a.take<int>(bn * 60);
     w.KNN12 = a.take<int>(bn * 8); w.KNN11 = a.take<int>(bn * 8);
     w.E = a.take<float>(bn * E_LD); w.F2 = a.take<float>(bn * 256);
-    w.G1 = a.take<float>((size_t)bc * 256); w.G2 = a.take<float>((size_t)bc * 256);
     if (o.unfused_sc1) {
         w.X0 = a.take<float>(bn * 60 * 8); w.T32a = a.take<float>(bn * 60 * 32); w.T32b = a.take<float>(bn * 60 * 32);
         w.T64 = a.take<float>(bn * 60 * 64);
@@ -127,13 +126,16 @@ void carve(Arena &a, Work &w, int bc, int n, const CarveOpts &o) {
     w.PBM = a.take<float>((size_t)bc * 2048); w.P = a.take<float>(bn * 2048);
     if (!tc) { w.Y1 = a.take<float>(bn * 32 * 512); w.Y3 = a.take<float>(bn * 32 * 64); }
     if (o.need_y2) w.Y2 = a.take<float>(o.mode == 1 ? y2_tiled : (o.mode == 2 ? y2_tiled / 2 : bn * 32 * 256));
-    w.PROP = a.take<float>(bn * 256); w.GP = a.take<float>((size_t)bc * 256);
+    w.PROP = a.take<float>(bn * 256);
     w.GI = a.take<float>((size_t)bc * 768); w.GH = a.take<float>((size_t)bc * 768);
     w.GNEW = a.take<float>((size_t)bc * 256); w.ZERO = a.take<float>((size_t)bc * 256);
     w.PBH = a.take<float>((size_t)bc * 512);
     w.HD1 = a.take<float>(bn * 512); w.HD2 = a.take<float>(bn * 256); w.HD3 = a.take<float>(bn * 128);
     w.FLOW = a.take<float>(bn * 3);
-    w.AMAX = a.take<unsigned int>((size_t)AM_COUNT * bc); w.SCL = a.take<float>((size_t)SC_COUNT * bc);
+    // cleared together at the top of a forward (one memset): the scale maxima and the three global max-pooled features (atomicMax targets)
+    w.AMAX = a.take<unsigned int>((size_t)AM_COUNT * bc);
+    w.G1 = a.take<float>((size_t)bc * 256); w.G2 = a.take<float>((size_t)bc * 256); w.GP = a.take<float>((size_t)bc * 256);
+    w.SCL = a.take<float>((size_t)SC_COUNT * bc);
 }
 
 }  // namespace
@@ -394,8 +396,8 @@ static int run_mse_layer(cmf_model *m, int bc, int n, const float *pc, const flo
             for (int l = 0; l < 3; ++l) { mw[s].Vt[l] = T.m1_v[s][l].wt; mw[s].ainv[l] = T.m1_v[s][l].ainv; mw[s].c[l] = m->seg[sb + 7 + l * 2]; }
         }
         RUN(C_GEMM_SC1, 2.0 * 3264.0 * 60.0 * (double)bn, cmf_launch_setconv1_tc(bc, n, pc, ft, bq, cw, w.M64, st));
-        RUN(C_GEMM_POINTWISE, 2.0 * 3 * 4 * 64 * 64 * (double)bn, cmf_launch_mlp2_tc(bn, w.M64, 256, dest, ldd, mw, amax_dest, n, st));
-        RUN(C_REDUCE, 0, cmf_launch_globalmax(bc, n, 256, dest, ldd, G, st));
+        // (the global max over the points -- G, zeroed with the scale maxima at the top of the forward -- is taken in mlp2's epilogue)
+        RUN(C_GEMM_POINTWISE, 2.0 * 3 * 4 * 64 * 64 * (double)bn, cmf_launch_mlp2_tc(bn, w.M64, 256, dest, ldd, mw, amax_dest, n, st, G));
         return CMF_OK;
     }
     if (m->fused_sc1) {
@@ -455,22 +457,23 @@ static int forward_chunk(cmf_model *m, int bc, int n, int n2, const float *pc1, 
     auto AM = [&](int slot) { return w.AMAX + (size_t)slot * m->cap_bc; };
     auto SC = [&](int slot) { return w.SCL + (size_t)slot * m->cap_bc; };
     static const float RADII[4] = {2.f, 4.f, 8.f, 16.f};               // models/cmflow.py:21,35
-    if (F) CMF_CUDA(cudaMemsetAsync(w.AMAX, 0, (size_t)AM_COUNT * m->cap_bc * sizeof(unsigned int), st));
+    if (F) CMF_CUDA(cudaMemsetAsync(w.AMAX, 0, (size_t)(reinterpret_cast<char *>(w.GP + (size_t)m->cap_bc * 256) - reinterpret_cast<char *>(w.AMAX)), st));   // AMAX, G1, G2, GP
 
-    // neighbour search
-    RUN(C_SEARCH, 0, cmf_launch_transpose3(bc, n, pc1, w.X1T, st));
-    RUN(C_SEARCH, 0, cmf_launch_transpose3(bc, n2, pc2, w.X2T, st));
-    RUN(C_SEARCH, 0, cmf_launch_ball_query_ms(bc, n, pc1, w.BQ1, st));
-    RUN(C_SEARCH, 0, cmf_launch_ball_query_ms(bc, n2, pc2, w.BQ2, st));
-    RUN(C_SEARCH, 0, cmf_launch_knn_point8(bc, n2, n, w.X2T, w.X1T, w.KNN12, st));
-    RUN(C_SEARCH, 0, cmf_launch_knn_point8(bc, n, n, w.X1T, w.X1T, w.KNN11, st));
-
-    // multi-scale encoders (cmflow.py:72-77); cloud 1 writes straight into the embedding rows E[:, 0:256]
     // fp16x3 + chain kernels: the per-pair maxima behind the consumer GEMMs' fp16 scales are taken by the producing kernels' epilogues
     const bool fused_amax = F && m->chain;
+    // neighbour search: two launches.  (1) both clouds' four-radius ball queries, the point-major coordinate copies the k-NN reads and the
+    // radar-feature columns of E; (2) the cross-frame and the self 8-NN of cloud 1's points, with the per-pair direction maximum (fp16 scale bound)
+    {
+        SearchPrologueArgs sp;
+        sp.n[0] = n; sp.n[1] = n2; sp.xyz[0] = pc1; sp.xyz[1] = pc2; sp.idx60[0] = w.BQ1; sp.idx60[1] = w.BQ2; sp.aos[0] = w.X1T; sp.aos[1] = w.X2T;
+        sp.ft = ft1; sp.E = w.E; sp.lde = E_LD; sp.off = 768; sp.pad = E_LD - 771; sp.amax_ft = fused_amax ? AM(AM_FT) : nullptr;
+        RUN(C_SEARCH, 0, cmf_launch_search_prologue(bc, sp, st));
+    }
+    RUN(C_SEARCH, 0, cmf_launch_knn_point8_dual(bc, n, w.X1T, n2, w.X2T, w.KNN12, n, w.X1T, w.KNN11, F ? AM(AM_DIR) : nullptr, st));
+
+    // multi-scale encoders (cmflow.py:72-77); cloud 1 writes straight into the embedding rows E[:, 0:256]
     { int rc = run_mse_layer(m, bc, n, pc1, ft1, w.BQ1, w.E, E_LD, w.G1, st, fused_amax ? AM(AM_F1) : nullptr); if (rc) return rc; }
     { int rc = run_mse_layer(m, bc, n2, pc2, ft2, w.BQ2, w.F2, 256, w.G2, st, fused_amax ? AM(AM_F2) : nullptr); if (rc) return rc; }
-    RUN(C_GATHER, 0, cmf_launch_scatter_ft(bc, n, ft1, w.E, E_LD, 768, E_LD - 771, st, fused_amax ? AM(AM_FT) : nullptr));
 
     // flow embedding (FeatureCorrelator, radarflow_util.py:185-237)
     bool fused_wsum = false;
@@ -479,7 +482,7 @@ static int forward_chunk(cmf_model *m, int bc, int n, int n2, const float *pc1, 
         gb.g[0] = mk(S(FC_WCG), 256, w.G1, 256, w.PB1, 512, S(FC_B1), 512, 256, bc, CMF_ACT_NONE);
         gb.g[1] = mk(S(FC_WNG), 256, w.G2, 256, w.PB2, 512, nullptr, 512, 256, bc, CMF_ACT_NONE);
         gb.g[2] = mk(S(M2_WG), 256, w.G1, 256, w.PBM, 2048, S(M2_T1), 2048, 256, bc, CMF_ACT_NONE);
-        RUN(C_GEMM_FC_HOIST, gflops(gb), cmf_launch_gemm(gb, st));
+        RUN(C_GEMM_FC_HOIST, gflops(gb), m->tc ? cmf_launch_pair_gemv(gb, st) : cmf_launch_gemm(gb, st));
     }
     if (m->tc) {
         if (F) {    // per-pair maxima of the GEMM inputs (fp16 scales): encoder features, kNN direction components
@@ -487,7 +490,6 @@ static int forward_chunk(cmf_model *m, int bc, int n, int n2, const float *pc1, 
                 RUN(C_REDUCE, 0, cmf_launch_pair_absmax(bc, n, w.E, E_LD, 256, AM(AM_F1), st));
                 RUN(C_REDUCE, 0, cmf_launch_pair_absmax(bc, n2, w.F2, 256, 256, AM(AM_F2), st));
             }
-            RUN(C_REDUCE, 0, cmf_launch_pair_dirmax(bc, n, n2, pc1, pc2, w.KNN12, 8, AM(AM_DIR), st));
         }
         {
             TcArgs ta_ = tc_plain(T.fc_wc, F, 512, 256, w.E, E_LD, w.U1, 512, nullptr, bn, CMF_ACT_NONE, w.PB1, 512, n);
@@ -599,7 +601,7 @@ static int forward_chunk(cmf_model *m, int bc, int n, int n2, const float *pc1, 
         TcChainMlp2W mw[4];
         for (int s = 0; s < 4; ++s)
             for (int l = 0; l < 3; ++l) { mw[s].Vt[l] = T.m2_v[s][l].wt; mw[s].ainv[l] = T.m2_v[s][l].ainv; mw[s].c[l] = S(M2_BASE + s * 10 + 5 + l * 2); }
-        RUN(C_GEMM_POINTWISE, 2.0 * 3 * 4 * 64 * 64 * (double)bn, cmf_launch_mlp2_tc(bn, w.M64, 256, w.PROP, 256, mw, F ? AM(AM_PROP) : nullptr, n, st));
+        RUN(C_GEMM_POINTWISE, 2.0 * 3 * 4 * 64 * 64 * (double)bn, cmf_launch_mlp2_tc(bn, w.M64, 256, w.PROP, 256, mw, F ? AM(AM_PROP) : nullptr, n, st, w.GP));
     } else {
         GemmBatch gb; gb.count = 4;
         const float *src[3] = {w.M64, w.Q1, w.Q2};
@@ -612,18 +614,20 @@ static int forward_chunk(cmf_model *m, int bc, int n, int n2, const float *pc1, 
             RUN(C_GEMM_POINTWISE, gflops(gb), cmf_launch_gemm(gb, st));
         }
     }
-    RUN(C_REDUCE, 0, cmf_launch_globalmax(bc, n, 256, w.PROP, 256, w.GP, st));
+    if (!(m->tc == 2 && m->chain)) RUN(C_REDUCE, 0, cmf_launch_globalmax(bc, n, 256, w.PROP, 256, w.GP, st));
     const float *gvec = w.GP;
     if (m->temporal) {            // CMFlow-T: GRU over the global feature (cmflow_t.py:94-105)
-        { const GemmArgs ga_ = mk(S(GRU_WIH), 256, w.GP, 256, w.GI, 768, S(GRU_BIH), 768, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_POINTWISE, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
-        { const GemmArgs ga_ = mk(S(GRU_WHH), 256, gprev ? gprev : w.ZERO, 256, w.GH, 768, S(GRU_BHH), 768, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_POINTWISE, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
+        GemmBatch gg; gg.count = 2;
+        gg.g[0] = mk(S(GRU_WIH), 256, w.GP, 256, w.GI, 768, S(GRU_BIH), 768, 256, bc, CMF_ACT_NONE);
+        gg.g[1] = mk(S(GRU_WHH), 256, gprev ? gprev : w.ZERO, 256, w.GH, 768, S(GRU_BHH), 768, 256, bc, CMF_ACT_NONE);
+        RUN(C_GEMM_POINTWISE, gflops(gg), m->tc ? cmf_launch_pair_gemv(gg, st) : cmf_launch_gemm(gg, st));
         float *gnew = gfeat_out ? gfeat_out : w.GNEW;
         RUN(C_HEAD_KABSCH, 0, cmf_launch_gru_gates(bc, w.GI, w.GH, gprev, gnew, st));
         gvec = gnew;
     }
 
     // heads (FlowHead / MotionHead, radarflow_util.py:240-285), first layer stacked [fp ; mp]
-    { const GemmArgs ga_ = mk(S(HD_W1G), 256, gvec, 256, w.PBH, 512, S(HD_T1), 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_POINTWISE, gflops(ga_), cmf_launch_gemm1(ga_, st)); }
+    { GemmBatch gh; gh.count = 1; gh.g[0] = mk(S(HD_W1G), 256, gvec, 256, w.PBH, 512, S(HD_T1), 512, 256, bc, CMF_ACT_NONE); RUN(C_GEMM_POINTWISE, gflops(gh), m->tc ? cmf_launch_pair_gemv(gh, st) : cmf_launch_gemm(gh, st)); }
     if (m->tc) {
         if (F && !fused_amax) RUN(C_REDUCE, 0, cmf_launch_pair_absmax(bc, n, w.PROP, 256, 256, AM(AM_PROP), st));
         TcArgs ta_ = tc_plain(T.hd_w1, F, 512, 256, w.PROP, 256, w.HD1, 512, nullptr, bn, CMF_ACT_RELU, w.PBH, 512, n);

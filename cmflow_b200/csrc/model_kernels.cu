@@ -158,6 +158,64 @@ int cmf_launch_gemm(const GemmBatch &gb, cudaStream_t st) {
     return CMF_OK;
 }
 
+// ---- few-column GEMMs (one column per frame pair: the per-pair bias vectors, the GRU gate pre-activations) -------------------------------
+// Out[c][m] = bias[m] + sum_k W[m][k] * X[c][k] for up to four problems in one launch.  With 256 columns the 128 x 128 tiles of gemm_nt_kernel
+// give a few dozen CTAs (36 us for 0.4 GFLOP); here a CTA takes 64 outputs x 16 columns and K in chunks of 64 through shared memory
+// (W chunk transposed, padded: conflict-free), so that a 3072-output batch is 768 CTAs.  fp32 FMA, k ascending: deterministic.
+constexpr int PG_O = 64, PG_C = 16, PG_K = 64;
+__global__ void __launch_bounds__(256)
+pair_gemv_kernel(const GemmBatch gb, int tiles0, int tiles1, int tiles2) {
+    __shared__ float sW[PG_K][PG_O + 1];
+    __shared__ float sX[PG_C][PG_K];
+    int ot = blockIdx.x, seg = 0;
+    if (ot >= tiles0) { ot -= tiles0; seg = 1; if (ot >= tiles1) { ot -= tiles1; seg = 2; if (ot >= tiles2) { ot -= tiles2; seg = 3; } } }
+    const GemmArgs &g = gb.g[seg];
+    const int o0 = ot * PG_O, c0 = blockIdx.y * PG_C;
+    if (c0 >= g.cols) return;
+    const int o = threadIdx.x & 63, cg = threadIdx.x >> 6;                 // this thread: output o0 + o, columns c0 + cg * 4 .. + 3
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int kc = 0; kc < g.K; kc += PG_K) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < PG_O * PG_K / 256; ++i) {
+            const int idx = threadIdx.x + i * 256, k = idx & (PG_K - 1), r = idx >> 6;
+            sW[k][r] = (o0 + r < g.M) ? __ldg(g.W + (size_t)(o0 + r) * g.ldw + kc + k) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < PG_C * PG_K / 256; ++i) {
+            const int idx = threadIdx.x + i * 256, k = idx & (PG_K - 1), c = idx >> 6;
+            sX[c][k] = (c0 + c < g.cols) ? __ldg(g.X + (size_t)(c0 + c) * g.ldx + kc + k) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 16
+        for (int k = 0; k < PG_K; ++k) {
+            const float w = sW[k][o];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = fmaf(w, sX[cg * 4 + j][k], acc[j]);
+        }
+    }
+    if (o0 + o >= g.M) return;
+    const float b = g.bias ? __ldg(g.bias + o0 + o) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c0 + cg * 4 + j;
+        if (c < g.cols) g.Out[(size_t)c * g.ldo + o0 + o] = acc[j] + b;
+    }
+}
+int cmf_launch_pair_gemv(const GemmBatch &gb, cudaStream_t st) {
+    int tiles[4] = {0, 0, 0, 0}, total = 0, maxC = 0;
+    for (int i = 0; i < gb.count; ++i) {
+        const GemmArgs &g = gb.g[i];
+        if ((g.K % PG_K) || g.act != CMF_ACT_NONE || g.pbias) { cmf_set_error("pair_gemv: K %% 64 == 0, no activation, no per-pair bias (K=%d)", g.K); return CMF_ERR_INVALID; }
+        tiles[i] = cmf_divup(g.M, PG_O); total += tiles[i];
+        if (g.cols > maxC) maxC = g.cols;
+    }
+    if (total == 0 || maxC == 0) return CMF_OK;
+    pair_gemv_kernel<<<dim3(total, cmf_divup(maxC, PG_C)), 256, 0, st>>>(gb, tiles[0], tiles[1], tiles[2]);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
 int cmf_launch_gemm1(const GemmArgs &g, cudaStream_t st) {
     GemmBatch gb;
     gb.g[0] = g;
@@ -168,29 +226,14 @@ int cmf_launch_gemm1(const GemmArgs &g, cudaStream_t st) {
 // =================================================================================================
 // small layout kernels
 // =================================================================================================
-__global__ void transpose3_kernel(int n, const float *__restrict__ planar, float *__restrict__ aos) {
-    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float *p = planar + (size_t)b * 3 * n;
-    float *o = aos + ((size_t)b * n + i) * 3;
-    o[0] = __ldg(p + i); o[1] = __ldg(p + n + i); o[2] = __ldg(p + 2 * n + i);
-}
-int cmf_launch_transpose3(int b, int n, const float *planar, float *aos, cudaStream_t st) {
-    transpose3_kernel<<<dim3(cmf_divup(n, 256), b), 256, 0, st>>>(n, planar, aos);
-    CMF_LAUNCH_CHECK();
-    return CMF_OK;
-}
-
 // ---- multi-radius ball query: one pass over the candidates for all four CMFlow scales -------------
 // (models/cmflow.py:21-22; semantics per scale = lib/src/ball_query_gpu.cu:9-45)
 constexpr int MS_CHUNK = 2048;
 constexpr int MS_QPW = 2;
 __constant__ float c_ms_r2[4] = {4.0f, 16.0f, 64.0f, 256.0f};     // radius*radius for 2,4,8,16 (exact in fp32)
 
-__global__ void __launch_bounds__(256)
-ball_query_ms_kernel(int n, const float *__restrict__ xyz, int *__restrict__ idx60) {
+__device__ __forceinline__ void ball_query_ms_body(int b, int n, const float *__restrict__ xyz, int *__restrict__ idx60) {
     __shared__ float sx[MS_CHUNK], sy[MS_CHUNK], sz[MS_CHUNK];
-    const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const float *px = xyz + (size_t)b * 3 * n, *py = px + n, *pz = py + n;
@@ -263,6 +306,50 @@ ball_query_ms_kernel(int n, const float *__restrict__ xyz, int *__restrict__ idx
         }
     }
 }
+__global__ void __launch_bounds__(256)
+ball_query_ms_kernel(int n, const float *__restrict__ xyz, int *__restrict__ idx60) { ball_query_ms_body(blockIdx.y, n, xyz, idx60); }
+
+// The engine's search prologue in ONE launch (blockIdx.z = cloud): the multi-radius ball query of both clouds, plus -- for the 16 points a
+// block queries -- the point-major copy of the coordinates the k-NN kernel reads and (cloud 1) the radar-feature columns of the embedding
+// matrix E with their per-pair |max| (what transpose3 x2 / ball_query_ms x2 / scatter_ft did in five launches).
+__global__ void __launch_bounds__(256)
+search_prologue_kernel(const SearchPrologueArgs a) {
+    const int z = blockIdx.z, b = blockIdx.y, n = z ? a.n[1] : a.n[0];         // (ternaries: no runtime indexing of the parameter struct)
+    const int p0 = blockIdx.x * 8 * MS_QPW;
+    if (p0 >= n) return;                                                      // block-uniform
+    const float *xyz_z = z ? a.xyz[1] : a.xyz[0];
+    const float *xyz = xyz_z + (size_t)b * 3 * n;
+    float *aos = z ? a.aos[1] : a.aos[0];
+    if (threadIdx.x < 3 * 8 * MS_QPW) {
+        const int q = p0 + threadIdx.x / 3, comp = threadIdx.x % 3;
+        if (q < n) aos[((size_t)b * n + q) * 3 + comp] = __ldg(xyz + (size_t)comp * n + q);
+    } else if (z == 0 && a.E && threadIdx.x >= 64 && threadIdx.x < 64 + 8 * MS_QPW) {      // lanes 0..15 of warp 2
+        const int i = p0 + (int)threadIdx.x - 64;
+        float m = 0.f;
+        if (i < n) {
+            const float *p = a.ft + (size_t)b * 3 * n;
+            float *o = a.E + ((size_t)b * n + i) * a.lde + a.off;
+            const float f0 = __ldg(p + i), f1 = __ldg(p + n + i), f2 = __ldg(p + 2 * n + i);
+            o[0] = f0; o[1] = f1; o[2] = f2;
+            for (int d = 0; d < a.pad; ++d) o[3 + d] = 0.f;
+            m = fmaxf(fabsf(f0), fmaxf(fabsf(f1), fabsf(f2)));
+        }
+        if (a.amax_ft) {
+#pragma unroll
+            for (int sft = 8; sft > 0; sft >>= 1) m = fmaxf(m, __shfl_xor_sync(0x0000ffffu, m, sft));
+            if (threadIdx.x == 64 && m > 0.f) atomicMax(a.amax_ft + b, __float_as_uint(m));
+        }
+    }
+    ball_query_ms_body(b, n, xyz_z, z ? a.idx60[1] : a.idx60[0]);
+}
+int cmf_launch_search_prologue(int b, const SearchPrologueArgs &a, cudaStream_t st) {
+    const int nmax = a.n[0] > a.n[1] ? a.n[0] : a.n[1];
+    if (b <= 0 || nmax <= 0) return CMF_OK;
+    search_prologue_kernel<<<dim3(cmf_divup(nmax, 8 * MS_QPW), b, 2), 256, 0, st>>>(a);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
 int cmf_launch_ball_query_ms(int b, int n, const float *xyz_planar, int *idx60, cudaStream_t st) {
     ball_query_ms_kernel<<<dim3(cmf_divup(n, 8 * MS_QPW), b), 256, 0, st>>>(n, xyz_planar, idx60);
     CMF_LAUNCH_CHECK();
@@ -472,29 +559,6 @@ int cmf_launch_globalmax(int b, int n, int C, const float *F, int ldf, float *G,
     return CMF_OK;
 }
 
-__global__ void scatter_ft_kernel(int n, const float *__restrict__ ft, float *__restrict__ E, int lde, int off, int pad, unsigned int *__restrict__ amax_out) {
-    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-    float m = 0.f;
-    if (i < n) {
-        const float *p = ft + (size_t)b * 3 * n;
-        float *o = E + ((size_t)b * n + i) * lde + off;
-        const float f0 = __ldg(p + i), f1 = __ldg(p + n + i), f2 = __ldg(p + 2 * n + i);
-        o[0] = f0; o[1] = f1; o[2] = f2;
-        for (int d = 0; d < pad; ++d) o[3 + d] = 0.f;
-        m = fmaxf(fabsf(f0), fmaxf(fabsf(f1), fabsf(f2)));
-    }
-    if (amax_out) {                                     // blockIdx.y = pair: the whole warp belongs to it
-#pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sft));
-        if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_out + b, __float_as_uint(m));
-    }
-}
-int cmf_launch_scatter_ft(int b, int n, const float *ft_planar, float *E, int lde, int off, int pad, cudaStream_t st, unsigned int *amax_out) {
-    scatter_ft_kernel<<<dim3(cmf_divup(n, 256), b), 256, 0, st>>>(n, ft_planar, E, lde, off, pad, amax_out);
-    CMF_LAUNCH_CHECK();
-    return CMF_OK;
-}
-
 // ---- per-pair maxima for the fp16x3 operand scales ------------------------------------------------
 __global__ void __launch_bounds__(256)
 pair_absmax_kernel(int n, const float *__restrict__ X, int ld, int width4, unsigned int *__restrict__ out) {
@@ -514,27 +578,6 @@ int cmf_launch_pair_absmax(int b, int n, const float *X, int ld, int width, unsi
     if ((width & 3) || (ld & 3)) { cmf_set_error("pair_absmax: width / ld must be multiples of 4"); return CMF_ERR_INVALID; }
     const int split = cmf_divup((long long)n * (width / 4), 256 * 8) < 1 ? 1 : cmf_divup((long long)n * (width / 4), 256 * 8);
     pair_absmax_kernel<<<dim3(b, split), 256, 0, st>>>(n, X, ld, width / 4, out);
-    CMF_LAUNCH_CHECK();
-    return CMF_OK;
-}
-__global__ void __launch_bounds__(256)
-pair_dirmax_kernel(int n, int nc, int k, const float *__restrict__ xyzq, const float *__restrict__ xyzc, const int *__restrict__ nbr,
-                   unsigned int *__restrict__ out) {
-    const int b = blockIdx.x;
-    const float *pq = xyzq + (size_t)b * 3 * n, *pc = xyzc + (size_t)b * 3 * nc;
-    float mx = 0.f;
-    for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < n * k; t += gridDim.y * blockDim.x) {
-        const int i = t / k;
-        const int j = __ldg(nbr + (size_t)b * n * k + t);
-        mx = fmaxf(mx, fmaxf(fabsf(__fsub_rn(__ldg(pc + j), __ldg(pq + i))),
-                             fmaxf(fabsf(__fsub_rn(__ldg(pc + nc + j), __ldg(pq + n + i))), fabsf(__fsub_rn(__ldg(pc + 2 * nc + j), __ldg(pq + 2 * n + i))))));
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(out + b, __float_as_uint(mx));
-}
-int cmf_launch_pair_dirmax(int b, int n, int n_cand, const float *xyzq_planar, const float *xyzc_planar, const int *nbr, int k, unsigned int *out, cudaStream_t st) {
-    pair_dirmax_kernel<<<dim3(b, cmf_divup((long long)n * k, 256 * 8)), 256, 0, st>>>(n, n_cand, k, xyzq_planar, xyzc_planar, nbr, out);
     CMF_LAUNCH_CHECK();
     return CMF_OK;
 }

@@ -16,10 +16,21 @@ struct GemmArgs {
 struct GemmBatch { GemmArgs g[4]; int count; };
 int cmf_launch_gemm(const GemmBatch &gb, cudaStream_t st);
 int cmf_launch_gemm1(const GemmArgs &g, cudaStream_t st);
+// the same for problems with few columns (one per frame pair): 64-output x 16-column CTAs; K % 64 == 0, no activation / per-pair bias
+int cmf_launch_pair_gemv(const GemmBatch &gb, cudaStream_t st);
 
-int cmf_launch_transpose3(int b, int n, const float *planar, float *aos, cudaStream_t st);
 int cmf_launch_ball_query_ms(int b, int n, const float *xyz_planar, int *idx60, cudaStream_t st);
 int cmf_launch_knn_point8(int b, int n_cand, int n_query, const float *cand_aos, const float *query_aos, int *idx, cudaStream_t st);
+// both clouds' ball queries + point-major coordinate copies + (optional, cloud 1) E[:, off .. off+2] = ft, zero pad, per-pair |max|: one launch
+struct SearchPrologueArgs {
+    int n[2]; const float *xyz[2]; int *idx60[2]; float *aos[2];
+    const float *ft; float *E; int lde, off, pad; unsigned int *amax_ft;
+};
+int cmf_launch_search_prologue(int b, const SearchPrologueArgs &a, cudaStream_t st);
+// the engine's two 8-NN searches of cloud-1 queries (against cloud 2 and against cloud 1) in one launch; dirmax (optional): per-pair
+// atomicMax of |candidate - query| components over the FIRST search's neighbours (uint bit patterns; caller zeroes)
+int cmf_launch_knn_point8_dual(int b, int n_query, const float *query_aos, int n_cand0, const float *cand0_aos, int *idx0,
+                               int n_cand1, const float *cand1_aos, int *idx1, unsigned int *dirmax0, cudaStream_t st);
 
 // mse_layer input rows: X0[scale s][(b*N+i)*K_s + kk][0..7] = [xyz_j - xyz_i, ft_j, 0, 0]
 int cmf_launch_build_x0(int b, int n, const float *xyz_planar, const float *ft_planar, const int *idx60,
@@ -31,9 +42,7 @@ int cmf_launch_setconv1_fused(int b, int n, const float *xyz_planar, const float
 int cmf_launch_maxk(long long points, int K, int C, const float *Y, int ldy, float *out, int ldo, cudaStream_t st);
 // G[b][c] = max_i F[(b*N+i)*ldf + c]
 int cmf_launch_globalmax(int b, int n, int C, const float *F, int ldf, float *G, cudaStream_t st);
-// E[(b*N+i)*lde + off + d] = ft[b][d][i] for d<3, zeros for the `pad` columns that follow
-// amax_out (optional, here and in fc_reduce): per-pair atomicMax of |values written| (uint bit patterns; caller zeroes)
-int cmf_launch_scatter_ft(int b, int n, const float *ft_planar, float *E, int lde, int off, int pad, cudaStream_t st, unsigned int *amax_out = nullptr);
+// amax_out (optional, in fc_reduce): per-pair atomicMax of |values written| (uint bit patterns; caller zeroes)
 
 // flow embedding (FeatureCorrelator) pieces
 int cmf_launch_fc_build_h1(int b, int n, int n2, const float *xyz1_planar, const float *xyz2_planar, const int *knn12,
@@ -64,4 +73,3 @@ int cmf_launch_raflow_sfr(int b, int n, const float *pc1, const float *ft1, cons
 // fp16x3 mode: out[b] = max(out[b], bits(max |X[(b*N+i)*ld + c]|, c < width))  (uint bit patterns; caller zeroes)
 int cmf_launch_pair_absmax(int b, int n, const float *X, int ld, int width, unsigned int *out, cudaStream_t st);
 // out[b] = max over points i and their k neighbours j of max(|xc_j - xq_i| per component)
-int cmf_launch_pair_dirmax(int b, int n, int n_cand, const float *xyzq_planar, const float *xyzc_planar, const int *nbr, int k, unsigned int *out, cudaStream_t st);

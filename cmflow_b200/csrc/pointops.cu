@@ -112,12 +112,10 @@ constexpr int KNN_CHUNK = 2048;
 constexpr int KNN_QPW = 2;
 
 template <int MODE>
-__global__ void __launch_bounds__(KNN_THREADS)
-knn_warp_kernel(int nq, int mc, int k, const float *__restrict__ query, const float *__restrict__ cand,
-                float *__restrict__ dist_out, int *__restrict__ idx_out) {
+__device__ __forceinline__ void knn_warp_body(int b, int nq, int mc, int k, const float *__restrict__ query, const float *__restrict__ cand,
+                                              float *__restrict__ dist_out, int *__restrict__ idx_out, unsigned int *__restrict__ dirmax) {
     __shared__ __align__(16) float s[KNN_CHUNK * 3];
     __shared__ float sn[MODE == 1 ? KNN_CHUNK : 1];
-    const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = (blockIdx.x * (KNN_THREADS / 32) + warp) * KNN_QPW;
     cand += (size_t)b * mc * 3;
@@ -197,6 +195,41 @@ knn_warp_kernel(int nq, int mc, int k, const float *__restrict__ query, const fl
         idx_out[((size_t)b * nq + q) * k + lane] = (bi[t] == INT_MAX) ? 0 : bi[t];     // unfilled slot: (1e40 -> inf, 0) in the reference
         if (dist_out) dist_out[((size_t)b * nq + q) * k + lane] = bd[t];
     }
+    if (dirmax) {          // engine only: per-pair max |candidate - query| component over the neighbours found (bound behind an fp16 operand scale)
+        float mx = 0.f;
+#pragma unroll
+        for (int t = 0; t < KNN_QPW; ++t) {
+            if (q0 + t >= nq || lane >= k) continue;
+            const float *cp = cand + (size_t)((bi[t] == INT_MAX) ? 0 : bi[t]) * 3;
+            mx = fmaxf(mx, fmaxf(fabsf(__fsub_rn(__ldg(cp), qx[t])), fmaxf(fabsf(__fsub_rn(__ldg(cp + 1), qy[t])), fabsf(__fsub_rn(__ldg(cp + 2), qz[t])))));
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        if (lane == 0 && mx > 0.f) atomicMax(dirmax + b, __float_as_uint(mx));
+    }
+}
+template <int MODE>
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_warp_kernel(int nq, int mc, int k, const float *__restrict__ query, const float *__restrict__ cand,
+                float *__restrict__ dist_out, int *__restrict__ idx_out) {
+    knn_warp_body<MODE>(blockIdx.y, nq, mc, k, query, cand, dist_out, idx_out, nullptr);
+}
+// two searches of the same queries against two candidate clouds (blockIdx.z) in one launch: the engine's cross-frame and self 8-NN
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_point_dual_kernel(int nq, int k, const float *__restrict__ query, int mc0, const float *__restrict__ cand0, int *__restrict__ idx0,
+                      int mc1, const float *__restrict__ cand1, int *__restrict__ idx1, unsigned int *__restrict__ dirmax0) {
+    if (blockIdx.z == 0) knn_warp_body<1>(blockIdx.y, nq, mc0, k, query, cand0, nullptr, idx0, dirmax0);
+    else knn_warp_body<1>(blockIdx.y, nq, mc1, k, query, cand1, nullptr, idx1, nullptr);
+}
+int cmf_launch_knn_point8_dual(int b, int n_query, const float *query_aos, int n_cand0, const float *cand0_aos, int *idx0,
+                               int n_cand1, const float *cand1_aos, int *idx1, unsigned int *dirmax0, cudaStream_t st) {
+    if (b <= 0 || n_query <= 0) return CMF_OK;
+    if (n_cand0 < 8 || n_cand1 < 8) { cmf_set_error("knn_point8_dual: fewer than 8 candidates (torch.topk raises too)"); return CMF_ERR_INVALID; }
+    if (b > 65535) { cmf_set_error("knn_point8_dual: batch > 65535"); return CMF_ERR_INVALID; }
+    dim3 grid(cmf_divup(n_query, (KNN_THREADS / 32) * KNN_QPW), b, 2);
+    knn_point_dual_kernel<<<grid, KNN_THREADS, 0, st>>>(n_query, 8, query_aos, n_cand0, cand0_aos, idx0, n_cand1, cand1_aos, idx1, dirmax0);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
 }
 
 // Fallback for 32 < k <= 200: one thread per query with local arrays, as the reference does.

@@ -23,26 +23,36 @@ namespace {
 constexpr int CH_THREADS = 128;
 constexpr int TILE_BYTES = 128 * 64;                 // one 128-row x 32-half operand tile (64-byte rows, 64B swizzle)
 
-__device__ __forceinline__ void tc_commit1(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+// ISSUE DISCIPLINE (see tc_sc2.cu): warp 0 runs the issue code in uniform control flow with warp-uniform operands and every tcgen05
+// instruction is predicated on `el`, the flag of its elected lane.  Under `if (tid == 0)` each MMA sat in an ELECT / R2UR.BROADCAST / branch
+// loop (~100 clk per MMA, with the CTA's other 127 threads waiting for the commit).  The warp must be converged where it issues.
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t el;
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\tselp.u32 %0, 1, 0, e;\n\t}" : "=r"(el));
+    return el;
 }
-__device__ __forceinline__ void tc_mma1_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+__device__ __forceinline__ void tc_commit1(uint32_t el, uint32_t bar) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(el) : "memory");
+}
+__device__ __forceinline__ void tc_mma1_f16(uint32_t el, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(el) : "memory");
 }
 // D = A * B^T over nkb 32-half K blocks, as a_lo*b_hi + a_hi*b_lo + a_hi*b_hi.  Tile kb of an operand sits kb*stride bytes on.
-__device__ __forceinline__ void issue_split_mma(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t a_stride, uint32_t b_hi, uint32_t b_lo,
+__device__ __forceinline__ void issue_split_mma(uint32_t el, uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t a_stride, uint32_t b_hi, uint32_t b_lo,
                                                 uint32_t b_stride, int nkb, uint32_t idesc) {
+#pragma unroll
     for (int kb = 0; kb < nkb; ++kb) {
         const uint64_t dah = make_desc(a_hi + kb * a_stride), dal = make_desc(a_lo + kb * a_stride);
         const uint64_t dbh = make_desc(b_hi + kb * b_stride), dbl = make_desc(b_lo + kb * b_stride);
 #pragma unroll
         for (int k16 = 0; k16 < 2; ++k16) {
             const uint64_t adv = (uint64_t)(k16 * 2);            // 32 bytes = 16 halfs, in 16-byte descriptor units
-            tc_mma1_f16(d_tmem, dal + adv, dbh + adv, idesc, (kb | k16) ? 1u : 0u);
-            tc_mma1_f16(d_tmem, dah + adv, dbl + adv, idesc, 1u);
-            tc_mma1_f16(d_tmem, dah + adv, dbh + adv, idesc, 1u);
+            tc_mma1_f16(el, d_tmem, dal + adv, dbh + adv, idesc, (kb | k16) ? 1u : 0u);
+            tc_mma1_f16(el, d_tmem, dah + adv, dbl + adv, idesc, 1u);
+            tc_mma1_f16(el, d_tmem, dah + adv, dbh + adv, idesc, 1u);
         }
     }
 }
@@ -119,7 +129,8 @@ setconv1_tc_kernel(const Sc1Args a) {
     float *sW1t = sf, *sb1 = sf + 192, *sb2 = sb1 + 32, *sainv2 = sb2 + 32, *sb3 = sainv2 + 32, *sainv3 = sb3 + 64, *sinv = sainv3 + 64;
     const uint32_t bar = base + SC1_BAR;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SC1_BAR + 8);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;      // warp: broadcast, so that `warp == 0` is provably uniform
+    const uint32_t el = elect_one();
 
     if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) tmem_alloc1(smem_u32(tmem_slot), 128);
@@ -225,10 +236,10 @@ setconv1_tc_kernel(const Sc1Args a) {
         tc_fence_before();
         __syncthreads();
         // ---- phase 2: D2[128 x 32] = A2 * W2^T ----
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
-            issue_split_mma(tmem_base, base + SC1_A2, base + SC1_A2 + TILE_BYTES, 0, base + SC1_W2, base + SC1_W2 + 2048, 0, 1, IDESC_128x32);
-            tc_commit1(bar);
+            issue_split_mma(el, tmem_base, base + SC1_A2, base + SC1_A2 + TILE_BYTES, 0, base + SC1_W2, base + SC1_W2 + 2048, 0, 1, IDESC_128x32);
+            tc_commit1(el, bar);
         }
         mbar_wait(bar, parity); parity ^= 1;
         tc_fence_after();
@@ -266,10 +277,10 @@ setconv1_tc_kernel(const Sc1Args a) {
         tc_fence_before();
         __syncthreads();
         // ---- phase 4: D3[128 (2 x 64 channels) x 128 columns] = W3dup * B3^T ----
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
-            issue_split_mma(tmem_base, base + SC1_W3, base + SC1_W3 + TILE_BYTES, 0, base + SC1_B3, base + SC1_B3 + TILE_BYTES, 0, 1, IDESC_128x128);
-            tc_commit1(bar);
+            issue_split_mma(el, tmem_base, base + SC1_W3, base + SC1_W3 + TILE_BYTES, 0, base + SC1_B3, base + SC1_B3 + TILE_BYTES, 0, 1, IDESC_128x128);
+            tc_commit1(el, bar);
         }
         mbar_wait(bar, parity); parity ^= 1;
         tc_fence_after();
@@ -304,6 +315,7 @@ struct Mlp2Args {
     float *out; int ld_out;
     long long rows;
     unsigned int *amax_out; int rows_per_pair;        // optional: atomicMax of the (non-negative) outputs per frame pair, uint bit patterns
+    unsigned int *gmax;                               // optional: per-pair, per-channel maximum over the pair's rows, (pairs, 256) uint bit patterns (caller zeroes)
 };
 constexpr int ML_A = 0;                              // A operand: [kb 0: hi, lo][kb 1: hi, lo] = 4 tiles
 constexpr int ML_W = 4 * TILE_BYTES;                 // B operands: [layer][kb]{hi 4 KB, lo 4 KB} (64 rows each)
@@ -336,7 +348,8 @@ mlp2_tc_kernel(const Mlp2Args a) {
     float *sainv = reinterpret_cast<float *>(smem + ML_F), *sc = sainv + 192;
     const uint32_t bar = base + ML_BAR;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + ML_BAR + 8);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const uint32_t el = elect_one();
 
     if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) tmem_alloc1(smem_u32(tmem_slot), 64);
@@ -385,11 +398,11 @@ mlp2_tc_kernel(const Mlp2Args a) {
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
-            if (tid == 0) {
+            if (warp == 0) {
                 tc_fence_after();
-                issue_split_mma(tmem_base, base + ML_A, base + ML_A + TILE_BYTES, 2 * TILE_BYTES, base + ML_W + l * 2 * 8192, base + ML_W + l * 2 * 8192 + 4096,
+                issue_split_mma(el, tmem_base, base + ML_A, base + ML_A + TILE_BYTES, 2 * TILE_BYTES, base + ML_W + l * 2 * 8192, base + ML_W + l * 2 * 8192 + 4096,
                                 8192, 2, IDESC_128x64);
-                tc_commit1(bar);
+                tc_commit1(el, bar);
             }
             mbar_wait(bar, parity); parity ^= 1;
             tc_fence_after();
@@ -417,6 +430,36 @@ mlp2_tc_kernel(const Mlp2Args a) {
                     float4 *dst = reinterpret_cast<float4 *>(a.out + (size_t)row * a.ld_out + s * 64);
 #pragma unroll
                     for (int q = 0; q < 16; ++q) dst[q] = make_float4(h[2 * q].x, h[2 * q].y, h[2 * q + 1].x, h[2 * q + 1].y);
+                }
+                if (a.gmax) {
+                    // The global max-pooled feature (cmflow.py:76, 89: max over the pair's points) is taken here instead of by a pass over the
+                    // output: the tile's 128 x 64 outputs go through shared memory (the A-operand tiles are free -- every MMA of the item has
+                    // retired), thread (c = tid & 63, half = tid >> 6) takes the maximum of channel c over 64 rows, one atomicMax per thread.
+                    // Outputs are ReLU values, so their uint bit patterns order like the floats and 0 is the identity.
+                    const long long row0 = row - tid, last = (row0 + 127 < a.rows ? row0 + 127 : a.rows - 1);
+                    const long long pfirst = row0 / a.rows_per_pair;
+                    if (pfirst == last / a.rows_per_pair) {                       // (block-uniform) the whole tile belongs to one frame pair
+                        float *sT = reinterpret_cast<float *>(smem + ML_A);       // [128 rows][64], 16-byte chunk q of row r at chunk q ^ (r & 15)
+                        __syncthreads();
+#pragma unroll
+                        for (int q = 0; q < 16; ++q)
+                            *reinterpret_cast<float4 *>(sT + tid * 64 + ((q ^ (tid & 15)) << 2)) =
+                                valid ? make_float4(h[2 * q].x, h[2 * q].y, h[2 * q + 1].x, h[2 * q + 1].y) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        __syncthreads();
+                        const int c = tid & 63, r0 = (tid >> 6) * 64;
+                        float cm = 0.f;
+#pragma unroll 16
+                        for (int i = 0; i < 64; ++i) { const int r = r0 + i; cm = fmaxf(cm, sT[r * 64 + ((((c >> 2) ^ (r & 15)) << 2) | (c & 3))]); }
+                        if (cm > 0.f) atomicMax(a.gmax + (size_t)pfirst * 256 + s * 64 + c, __float_as_uint(cm));
+                        __syncthreads();                                          // the next item's A rows overwrite sT
+                    } else if (valid) {                                           // a tile across a pair boundary (points per pair not a multiple of 128)
+                        unsigned int *g = a.gmax + (size_t)(row / a.rows_per_pair) * 256 + s * 64;
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) {
+                            if (h[q].x > 0.f) atomicMax(g + 2 * q, __float_as_uint(h[q].x));
+                            if (h[q].y > 0.f) atomicMax(g + 2 * q + 1, __float_as_uint(h[q].y));
+                        }
+                    }
                 }
                 if (a.amax_out) {          // the consumer GEMM's per-pair fp16 scale comes from here instead of a separate pass over the output
                     const long long pair = valid ? row / a.rows_per_pair : -1;
@@ -477,7 +520,7 @@ int cmf_launch_setconv1_tc(int bc, int n, const float *xyz_planar, const float *
 }
 
 int cmf_launch_mlp2_tc(long long rows, const float *in, int ld_in, float *out, int ld_out, const TcChainMlp2W *w4, unsigned int *amax_out,
-                       int rows_per_pair, cudaStream_t st) {
+                       int rows_per_pair, cudaStream_t st, float *gmax) {
     int g_num_sms = 0;
     int rc = init_device(g_num_sms);
     if (rc) return rc;
@@ -488,6 +531,7 @@ int cmf_launch_mlp2_tc(long long rows, const float *in, int ld_in, float *out, i
         for (int l = 0; l < 3; ++l) { a.Vt[s][l] = w4[s].Vt[l]; a.ainv[s][l] = w4[s].ainv[l]; a.c[s][l] = w4[s].c[l]; }
     a.in = in; a.ld_in = ld_in; a.out = out; a.ld_out = ld_out; a.rows = rows;
     a.amax_out = amax_out; a.rows_per_pair = rows_per_pair > 0 ? rows_per_pair : 1;
+    a.gmax = reinterpret_cast<unsigned int *>(gmax);
     const long long items = ((rows + 127) / 128) * 4;
     const int grid = (int)(items < 2LL * g_num_sms ? items : 2LL * g_num_sms);
     mlp2_tc_kernel<<<grid, CH_THREADS, ML_SMEM, st>>>(a);

@@ -72,5 +72,6 @@ int cmf_launch_setconv1_tc(int bc, int n, const float *xyz_planar, const float *
                            cudaStream_t st);
 // out[row][s*64 + o] = mlp2_s(in[row][s*64 .. +63]) for the four scales
 // amax_out (optional): per-pair atomicMax of the outputs (uint bit patterns, caller zeroes), rows_per_pair rows per frame pair
+// gmax (optional): (pairs, 256) per-pair per-channel maximum over the pair's rows = the global max-pooled feature; the caller zeroes it
 int cmf_launch_mlp2_tc(long long rows, const float *in, int ld_in, float *out, int ld_out, const TcChainMlp2W *w4, unsigned int *amax_out,
-                       int rows_per_pair, cudaStream_t st);
+                       int rows_per_pair, cudaStream_t st, float *gmax = nullptr);
