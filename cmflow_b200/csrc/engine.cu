@@ -575,6 +575,7 @@ static int forward_chunk(cmf_model *m, int bc, int n, int n2, const float *pc1, 
                         if (nb) {
                             fprintf(stderr, "sc2 fused K=%d leaders=%d cycles: total %.0f | issuer tempty %.0f operands %.0f | producer gather %.0f | epilogue tfull %.0f g1done %.0f d3full %.0f | producer empty %.0f\n",
                                     KS[s], nb, av[0] / nb, av[1] / nb, av[2] / nb, av[3] / nb, av[4] / nb, av[5] / nb, av[6] / nb, av[7] / nb);
+                            fprintf(stderr, "    issuer: of the operand wait, %.0f cycles were for the peer's half after its own was complete\n", av[13] / nb);
                             if (av[9] > 0) fprintf(stderr, "    producer sections (SC2_PROD_PROFILE build): gather issue %.0f | loads + arithmetic %.0f | stores %.0f | proxy fence %.0f | arrive + bookkeeping %.0f\n",
                                                    av[8] / nb, av[9] / nb, av[10] / nb, av[11] / nb, av[12] / nb);
                         }

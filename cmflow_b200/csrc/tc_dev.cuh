@@ -17,7 +17,10 @@ constexpr int BM = 128, BN = 256, SK = 16, PK = 32;
 // protocol bug fails the launch instead of hanging the GPU.  NOTE: a trap poisons the CUDA context (sticky error for every later call of
 // the process), so the budget is generous -- time-slicing, MPS, compute-sanitizer or a debugger can stretch a legitimate wait a lot.
 // Compile with -DCMF_NO_WATCHDOG to remove it.
-constexpr unsigned long long WATCHDOG_NS = 30ull * 1000ull * 1000ull * 1000ull;
+#ifndef CMF_WATCHDOG_MS
+#define CMF_WATCHDOG_MS 30000
+#endif
+constexpr unsigned long long WATCHDOG_NS = (unsigned long long)CMF_WATCHDOG_MS * 1000ull * 1000ull;
 __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void watchdog(unsigned &spins, unsigned long long &t0) {
 #ifndef CMF_NO_WATCHDOG

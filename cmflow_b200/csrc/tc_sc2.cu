@@ -55,8 +55,20 @@ constexpr int STAGE_BYTES = 4 * TILE_BYTES;          // W hi, W lo, X hi, X lo: 
 #ifndef SC2_GK
 #define SC2_GK 2
 #endif
+#ifndef SC2_PW
+#define SC2_PW 8
+#endif
 constexpr int NSTAGE = SC2_NSTAGE;
-constexpr int NTHREADS = 512;
+// Producer warps.  The producers' loop is a chain of waits, shared-memory loads, ~11 packed instructions per channel pair, stores, a proxy
+// fence and an arrive; with 8 producer warps (two per scheduler) those latencies set the kernel's pace, not the tensor pipe.  16 producer
+// warps (768 threads) halve the rows per thread and double the warps the schedulers can switch between; the register file is redistributed
+// by warpgroup with setmaxnreg: utility warps 48, epilogue 144, producers 72.  The pool is what the CTA was LAUNCHED with (768 x 80 registers
+// = 61,440 = 128 x (48 + 144 + 4 x 72)): an increase beyond what the other groups release never completes.
+constexpr int PW = SC2_PW;                           // producer warps: 8 or 16
+constexpr int RPW = HALF_ROWS / PW;                  // rows per producer warp: 16 or 8
+constexpr int RPT = RPW / 4;                         // rows per producer thread: 4 or 2
+constexpr int NTHREADS = 256 + 32 * PW;
+static_assert(PW == 8 || PW == 16, "8 or 16 producer warps");
 // Gather granularity.  One tile::gather4 instruction costs the issuing warp ~150 clk whatever its box width (measured with the section
 // timers below: four 32-float boxes per K block were 46 % of a producer warp's busy time), so a gather fetches GK K blocks of a row at
 // once (box = 32 * GK floats) and the staging ring holds PF such groups: 4 instructions per warp per GK K blocks.
@@ -75,8 +87,8 @@ constexpr int OFF_CS1 = OFF_SW + 6144;               // gathered-row indices (ro
 constexpr int OFF_GEO = OFF_CS1 + 3 * HALF_ROWS * 4; // {dx, dy, dz, scale} [3][128]
 constexpr int OFF_AB2 = OFF_GEO + 3 * HALF_ROWS * 16;// {a_inv, bias} of the 256 layer-2 channels (float2)
 constexpr int OFF_AB3 = OFF_AB2 + 256 * 8;           // {a_inv, bias} of the 64 layer-3 channels
-constexpr int OFF_SBAR = OFF_AB3 + 64 * 8;           // staging barriers [PF][8 producer warps]
-constexpr int OFF_CBAR = OFF_SBAR + PF * 8 * 8;      // row-context barriers: ready[3] (filled, count 1), free[3] (8 producer warps are done with it)
+constexpr int OFF_SBAR = OFF_AB3 + 64 * 8;           // staging barriers [PF][PW producer warps]
+constexpr int OFF_CBAR = OFF_SBAR + PF * PW * 8;     // row-context barriers: ready[3] (filled, count 1), free[3] (the PW producer warps are done with it)
 constexpr int SMEM_BYTES = OFF_CBAR + 6 * 8 + 1024;  // + alignment slack
 static_assert(SMEM_BYTES <= 232448, "shared-memory plan exceeds 227 KB");
 constexpr uint32_t IDESC_L2 = make_idesc(256, 256, 1), IDESC_L3 = make_idesc(256, 64, 1);
@@ -229,14 +241,14 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
     if (threadIdx.x < 64) sAB3[threadIdx.x] = make_float2(__ldg(s.a_inv3 + threadIdx.x), s.bias3 ? __ldg(s.bias3 + threadIdx.x) : 0.f);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NSTAGE; ++i) { mbar_init(full_bar(i), 1 + 8); mbar_init(pfull_bar(i), 1); mbar_init(empty_bar(i), 1); }
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(full_bar(i), 1 + PW); mbar_init(pfull_bar(i), 1); mbar_init(empty_bar(i), 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 8); mbar_init(g1done_bar(i), 1); mbar_init(d3full_bar(i), 1);
             for (int g = 0; g < 4; ++g) mbar_init(a3r_bar(i, g), 8);
         }
         mbar_init(w3_bar, 1);
-        for (int i = 0; i < PF * 8; ++i) mbar_init(base + OFF_SBAR + 8 * i, 1);
-        for (int i = 0; i < 3; ++i) { mbar_init(base + OFF_CBAR + 8 * i, 1); mbar_init(base + OFF_CBAR + 24 + 8 * i, 8); }
+        for (int i = 0; i < PF * PW; ++i) mbar_init(base + OFF_SBAR + 8 * i, 1);
+        for (int i = 0; i < 3; ++i) { mbar_init(base + OFF_CBAR + 8 * i, 1); mbar_init(base + OFF_CBAR + 24 + 8 * i, PW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -247,6 +259,10 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
     cluster_sync_all();                         // both CTAs: barriers initialised, TMEM allocated, tables visible
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Roles by warpgroup (warps 0-3 utility, 4-7 epilogue, 8.. producers): with 16 producer warps each group first takes its share of the
+    // register file (setmaxnreg must dominate the code it governs, and every warp of a group executes it with the same count).
+    if (warp < 4) {
+    if (PW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     if (warp == 0) {
         // ===== bulk-copy issuer: the resident W3 slice once, then this CTA's 128 rows of W2 per stage =====
         if (lane == 0) {
@@ -318,10 +334,11 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                     unsigned spins = 0; unsigned long long t0 = 0ull;
                     const long long c0_ = a.dbg ? clock64() : 0;
                     bool have_full = false, have_peer = false;
+                    long long cf_ = 0;
                     while (true) {
-                        if (!have_full) have_full = mbar_test_warp(full_bar(stage), phase);
-                        if (!have_peer) have_peer = mbar_test_warp(pfull_bar(stage), phase);
-                        if (have_full && have_peer) break;
+                        if (!have_full) { have_full = mbar_test_warp(full_bar(stage), phase); if (have_full && a.dbg) cf_ = clock64(); }
+                        if (!have_peer) { have_peer = mbar_test_warp(pfull_bar(stage), phase); if (have_peer && a.dbg && !have_full) cf_ = -1; }
+                        if (have_full && have_peer) { if (a.dbg && cf_ > 0) dw2 += clock64() - cf_; break; }      // dw2: waiting for the PEER's half after my own was complete
                         serve_l3();
                         if (SC2_POLL_SLEEP) __nanosleep(SC2_POLL_SLEEP);                 // an always-eligible polling warp takes issue slots from the producers of its scheduler
                         watchdog(spins, t0);
@@ -359,7 +376,7 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
         {                                                   // drain: layer 3 of the last tile(s)
             unsigned spins = 0; unsigned long long t0 = 0ull;
             while ((l3_next >> 2) < l3_tiles) { serve_l3(); watchdog(spins, t0); }
-            if (a.dbg && lane == 0) { a.dbg[(size_t)blockIdx.x * 16 + 1] = dw0; a.dbg[(size_t)blockIdx.x * 16 + 2] = dw1; }
+            if (a.dbg && lane == 0) { a.dbg[(size_t)blockIdx.x * 16 + 1] = dw0; a.dbg[(size_t)blockIdx.x * 16 + 2] = dw1; a.dbg[(size_t)blockIdx.x * 16 + 13] = dw2; }
         }
     } else if (warp == 2) {
         // ===== row contexts: neighbour index -> row of P, rel-xyz, fp16 scale, up to three tiles ahead of the producers =====
@@ -399,7 +416,9 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                 }
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
-    } else if (warp >= 4 && warp < 8) {
+    }
+    } else if (warp < 8) {
+        if (PW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
         // ===== epilogue: this thread owns lane q*32 + lane of the CTA's accumulator = one neighbour column =====
         const int q = warp & 3;
         const int K = a.ksamp;
@@ -507,15 +526,16 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (a.dbg && warp == 4 && lane == 0) { a.dbg[(size_t)blockIdx.x * 16 + 4] = dw0; a.dbg[(size_t)blockIdx.x * 16 + 5] = dw1; a.dbg[(size_t)blockIdx.x * 16 + 6] = dw2; }
-    } else if (warp >= 8) {
-        // ===== producers (256 threads): this CTA's 128 activation rows, one 32-channel K block per iteration (as tc_gemm2.cu, SC2_Y1) =====
+    } else {
+        if (PW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+        // ===== producers (PW warps): this CTA's 128 activation rows, one 32-channel K block per iteration (as tc_gemm2.cu, SC2_Y1) =====
         const int pw = warp - 8;                                    // warp-uniform (warp is a broadcast value)
         const uint32_t el = elect_one();                            // the lane that issues this warp's gathers
         const int q = lane & 7, rsub = lane >> 3;
-        const int row0 = pw * 16 + rsub;                            // this thread's rows: row0 + 4*i
-        const uint32_t stg_w = base + OFF_STG + pw * 16 * ROW_BYTES; // this warp's 16 rows of ring slot r at + r * SLOT_BYTES
+        const int row0 = pw * RPW + rsub;                           // this thread's rows: row0 + 4*i, i < RPT
+        const uint32_t stg_w = base + OFF_STG + pw * RPW * ROW_BYTES; // this warp's RPW rows of ring slot r at + r * SLOT_BYTES
         const uint32_t stg_t = stg_w + rsub * ROW_BYTES + q * 16;   // this thread's 16-byte chunk of row 4*i + rsub at + i * 4 * ROW_BYTES, K block h of the group at + h * 128
-        const uint32_t sbar_w = base + OFF_SBAR + pw * 8;           // this warp's barrier of ring slot r at + r * 64
+        const uint32_t sbar_w = base + OFF_SBAR + pw * 8;           // this warp's barrier of ring slot r at + r * PW * 8
         int stage = 0; uint32_t phase = 0;
 #ifdef SC2_PROD_PROFILE
         long long ps0 = 0, ps1 = 0, ps2 = 0, ps3 = 0, ps4 = 0;      // producer sections: gather issue | loads + arithmetic | stores | proxy fence | arrive
@@ -527,14 +547,14 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
         // instructions are predicated on the elected lane.  Under `if (lane == 0)` every UTMALDG sat in an ELECT / 7 x R2UR.BROADCAST /
         // branch loop: ~180 clk per gather, 46 % of a producer warp's busy time (section timers, SC2_PROD_PROFILE).
         auto issue = [&](int kg, int ring, int lbuf) {
-            const int4 *ip = reinterpret_cast<const int4 *>(cidx + lbuf * HALF_ROWS + pw * 16);      // warp-uniform address: broadcast loads
-            const uint32_t dst = stg_w + ring * SLOT_BYTES, bar = sbar_w + ring * 64;
+            const int4 *ip = reinterpret_cast<const int4 *>(cidx + lbuf * HALF_ROWS + pw * RPW);     // warp-uniform address: broadcast loads
+            const uint32_t dst = stg_w + ring * SLOT_BYTES, bar = sbar_w + ring * (PW * 8);
             const int col = a.off_u2 + kg * (PK * GK);
             __syncwarp();
             asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
-                         ::"r"(bar), "r"(16 * ROW_BYTES), "r"(el) : "memory");
+                         ::"r"(bar), "r"(RPW * ROW_BYTES), "r"(el) : "memory");
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < RPT; ++i) {
                 const int4 id = ip[i];
                 asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %8, 0;\n\t"
                              "@q cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n\t}"
@@ -556,9 +576,9 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
             int la_buf = 0, la_kg = PF - 1; long long la_t = t;     // look-ahead cursor: gather group (current + PF - 1)
             while (true) {
                 const long long tn = t + n_cl;
-                float4 geo[4];
+                float4 geo[RPT];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < RPT; ++i) {
                     const float4 g = cgeo[buf * HALF_ROWS + row0 + 4 * i];
                     geo[i] = make_float4(g.x * g.w, g.y * g.w, g.z * g.w, g.w);
                 }
@@ -582,16 +602,16 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
 #ifdef SC2_PROD_PROFILE
                     const long long pc1 = clock64(); ps0 += pc1 - pc0;
 #endif
-                    if (hk == 0) { TIMED(dw1, mbar_wait(sbar_w + ring * 64, rphase)); }      // the whole group lands on one barrier
+                    if (hk == 0) { TIMED(dw1, mbar_wait(sbar_w + ring * (PW * 8), rphase)); }      // the whole group lands on one barrier
 #ifdef SC2_PROD_PROFILE
                     const long long pc2 = clock64();
 #endif
-                    float4 v[4];
+                    float4 v[RPT];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) v[i] = lds16(stg_t + ring * SLOT_BYTES + i * 4 * ROW_BYTES + hk * 128);
-                    uint2 hh[4], ll[4];
+                    for (int i = 0; i < RPT; ++i) v[i] = lds16(stg_t + ring * SLOT_BYTES + i * 4 * ROW_BYTES + hk * 128);
+                    uint2 hh[RPT], ll[RPT];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < RPT; ++i) {
                         const float4 g = geo[i];
                         const float2 gx = make_float2(g.x, g.x), gy = make_float2(g.y, g.y), gz = make_float2(g.z, g.z), gs = make_float2(g.w, g.w);
                         float2 xa = make_float2(v[i].x, v[i].y), xb = make_float2(v[i].z, v[i].w);
@@ -612,7 +632,7 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                     uint8_t *Xhi = smem + stage * STAGE_BYTES + 2 * TILE_BYTES;
                     uint8_t *Xlo = Xhi + TILE_BYTES;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < RPT; ++i) {
                         const int off = sw_off_h(row0 + 4 * i, q * 4);
                         *reinterpret_cast<uint2 *>(Xhi + off) = hh[i];
                         *reinterpret_cast<uint2 *>(Xlo + off) = ll[i];
