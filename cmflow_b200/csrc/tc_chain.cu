@@ -318,10 +318,13 @@ struct Mlp2Args {
     unsigned int *gmax;                               // optional: per-pair, per-channel maximum over the pair's rows, (pairs, 256) uint bit patterns (caller zeroes)
 };
 constexpr int ML_A = 0;                              // A operand: [kb 0: hi, lo][kb 1: hi, lo] = 4 tiles
-constexpr int ML_W = 4 * TILE_BYTES;                 // B operands: [layer][kb]{hi 4 KB, lo 4 KB} (64 rows each)
-constexpr int ML_F = ML_W + 3 * 2 * 8192;            // floats: ainv[3][64], c[3][64]
-constexpr int ML_BAR = ML_F + 6 * 64 * 4;
-constexpr int ML_SMEM = ML_BAR + 16 + 1024;
+// B operands: a ring of TWO layers' weights, [slot][kb]{hi 4 KB, lo 4 KB} (64 rows each).  Holding all three layers (48 KB) made the CTA 83 KB: two
+// CTAs = 8 warps per SM for a kernel that is a chain of dependent phases per tile.  With the ring the next layer's 16 KB arrive by bulk copy
+// (L2 -> shared, mbarrier byte count) while the current layer runs, the CTA is 67 KB and three fit.
+constexpr int ML_W = 4 * TILE_BYTES;
+constexpr int ML_F = ML_W + 2 * 2 * 8192;            // floats: ainv[3][64], c[3][64]
+constexpr int ML_BAR = ML_F + 6 * 64 * 4;            // mma barrier, weight barriers [2], TMEM slot
+constexpr int ML_SMEM = ML_BAR + 32 + 1024;
 
 // 64 values of this thread's row (as 32 float2, all >= 0 or raw input) -> scale by the row's own power of two, split, store both K blocks
 __device__ __forceinline__ float mlp2_store_row(uint32_t a_base, int row, const float2 (&h)[32], float mx, bool valid) {
@@ -339,19 +342,19 @@ __device__ __forceinline__ float mlp2_store_row(uint32_t a_base, int row, const 
     return sc;
 }
 
-__global__ void __launch_bounds__(CH_THREADS, 2)
+__global__ void __launch_bounds__(CH_THREADS, 3)
 mlp2_tc_kernel(const Mlp2Args a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (base - raw);
     float *sainv = reinterpret_cast<float *>(smem + ML_F), *sc = sainv + 192;
-    const uint32_t bar = base + ML_BAR;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + ML_BAR + 8);
+    const uint32_t bar = base + ML_BAR, wbar = base + ML_BAR + 8;               // wbar + 8 * slot
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + ML_BAR + 24);
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const uint32_t el = elect_one();
 
-    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid == 0) { mbar_init(bar, 1); mbar_init(wbar, 1); mbar_init(wbar + 8, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) tmem_alloc1(smem_u32(tmem_slot), 64);
     tc_fence_before();
     __syncthreads();
@@ -362,6 +365,18 @@ mlp2_tc_kernel(const Mlp2Args a) {
 
     const long long ntile = (a.rows + 127) / 128, nitem = ntile * 4;           // item = scale * ntile + tile
     const long long i0 = nitem * blockIdx.x / gridDim.x, i1 = nitem * (blockIdx.x + 1) / gridDim.x;
+    // weight ring: element j = (item, layer) in processing order uses slot j & 1; its 16 KB are requested one element ahead
+    auto load_w = [&](long long item, int l, unsigned j) {                    // thread 0 only
+        const uint8_t *wt = reinterpret_cast<const uint8_t *>(a.Vt[(int)(item / ntile)][l]);
+        const uint32_t dst = base + ML_W + (j & 1u) * 16384, wb = wbar + 8 * (j & 1u);
+        mbar_arrive_expect_tx(wb, 16384);
+        for (int kb = 0; kb < 2; ++kb) {
+            bulk_g2s(dst + kb * 8192, wt + (size_t)kb * 2 * TILE_BYTES, 4096, wb);
+            bulk_g2s(dst + kb * 8192 + 4096, wt + (size_t)kb * 2 * TILE_BYTES + TILE_BYTES, 4096, wb);
+        }
+    };
+    unsigned wj = 0;
+    if (tid == 0 && i0 < i1) load_w(i0, 0, 0);
     int cur_s = -1;
     for (long long it = i0; it < i1; ++it) {
         const int s = (int)(it / ntile);
@@ -380,15 +395,9 @@ mlp2_tc_kernel(const Mlp2Args a) {
             }
         }
         if (s != cur_s) {
-            __syncthreads();
-            for (int l = 0; l < 3; ++l) {
-                const uint8_t *wt = reinterpret_cast<const uint8_t *>(a.Vt[s][l]);
-                for (int kb = 0; kb < 2; ++kb) {
-                    copy_g2s(smem + ML_W + (l * 2 + kb) * 8192, wt + (size_t)kb * 2 * TILE_BYTES, 4096);
-                    copy_g2s(smem + ML_W + (l * 2 + kb) * 8192 + 4096, wt + (size_t)kb * 2 * TILE_BYTES + TILE_BYTES, 4096);
-                }
+            __syncthreads();            // nobody still reads the previous scale's tables
+            for (int l = 0; l < 3; ++l)
                 if (tid < 64) { sainv[l * 64 + tid] = __ldg(a.ainv[s][l] + tid); sc[l * 64 + tid] = __ldg(a.c[s][l] + tid); }
-            }
             cur_s = s;
             // visibility: the barrier before the first MMA below
         }
@@ -399,11 +408,20 @@ mlp2_tc_kernel(const Mlp2Args a) {
             tc_fence_before();
             __syncthreads();
             if (warp == 0) {
+                // request the NEXT element's weights into the other slot: its last reader (the element before this one) has retired
+                if (tid == 0) {
+                    if (l < 2) load_w(it, l + 1, wj + 1);
+                    else if (it + 1 < i1) load_w(it + 1, 0, wj + 1);
+                }
+                __syncwarp();
+                mbar_wait(wbar + 8 * (wj & 1u), (wj >> 1) & 1u);                  // this element's weights have landed
+                __syncwarp();                                                     // converged warp for the elect-predicated issue
                 tc_fence_after();
-                issue_split_mma(el, tmem_base, base + ML_A, base + ML_A + TILE_BYTES, 2 * TILE_BYTES, base + ML_W + l * 2 * 8192, base + ML_W + l * 2 * 8192 + 4096,
-                                8192, 2, IDESC_128x64);
+                const uint32_t wb = base + ML_W + (wj & 1u) * 16384;
+                issue_split_mma(el, tmem_base, base + ML_A, base + ML_A + TILE_BYTES, 2 * TILE_BYTES, wb, wb + 4096, 8192, 2, IDESC_128x64);
                 tc_commit1(el, bar);
             }
+            ++wj;
             mbar_wait(bar, parity); parity ^= 1;
             tc_fence_after();
             const float inv = rs > 0.f ? __frcp_rn(rs) : 0.f;
@@ -533,7 +551,7 @@ int cmf_launch_mlp2_tc(long long rows, const float *in, int ld_in, float *out, i
     a.amax_out = amax_out; a.rows_per_pair = rows_per_pair > 0 ? rows_per_pair : 1;
     a.gmax = reinterpret_cast<unsigned int *>(gmax);
     const long long items = ((rows + 127) / 128) * 4;
-    const int grid = (int)(items < 2LL * g_num_sms ? items : 2LL * g_num_sms);
+    const int grid = (int)(items < 3LL * g_num_sms ? items : 3LL * g_num_sms);
     mlp2_tc_kernel<<<grid, CH_THREADS, ML_SMEM, st>>>(a);
     CMF_LAUNCH_CHECK();
     return CMF_OK;

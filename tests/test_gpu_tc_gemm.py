@@ -169,3 +169,25 @@ def test_fp16x3_is_batch_independent():
     small = run(net, tuple(t[:2] for t in big))
     for k in ("sf_agg", "stat_cls", "pre_trans", "mask"):
         assert torch.equal(small[k], whole[k][:2]), k
+
+
+@pytest.mark.parametrize("pairs", [6, 96])
+def test_fp16x3_is_run_to_run_reproducible(pairs):
+    """Every tensor-core stage accumulates in one fixed order (a single MMA-issuing thread per CTA pair): the same batch twice gives the same
+    bits, stage by stage.  (Two alternating issuer warps with a fast, elect-predicated issue did not: tests/determinism_probe.py.)"""
+    from cmflow_b200.synth import make_pairs, synthetic_state_dict
+    net = CMFlow(Args()); net.load_state_dict(synthetic_state_dict(0)); net = net.to(DEV)
+    net.set_precision("fp16x3")
+    N = 256
+    inp = make_pairs(pairs, N, seed=5)
+    taps = (("u1", 512), ("u2", 512), ("cost1", 512), ("P", 2048), ("prop", 256), ("hd3", 128))
+
+    def once():
+        out = run(net, inp)
+        out.update({k: net.tap(k, (pairs * N, c)).cpu() for k, c in taps})
+        return out
+    a = once()
+    for _ in range(2):
+        b = once()
+        for k in ("sf_agg", "stat_cls", "pre_trans", "mask") + tuple(k for k, _ in taps):
+            assert torch.equal(a[k], b[k]), k
