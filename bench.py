@@ -481,7 +481,7 @@ def main():
         peak_tf = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
         launch_ms = d["ms_per_step"] / max(1, d["launches_per_step"])
         traffic, traffic_src = None, None
-        for tj in ("r02_dominant_traffic.json", "r01f_tc_gemm2_traffic.json"):
+        for tj in ("r02b_dominant_traffic.json", "r02_dominant_traffic.json", "r01f_tc_gemm2_traffic.json"):
             tj = os.path.join(ROOT, "profiles", tj)
             if args.precision == "fp16x3" and B == 256 and N == 256 and os.path.exists(tj):  # an ncu capture of exactly this workload
                 tjd = json.load(open(tj))
