@@ -350,6 +350,150 @@ int cmf_launch_search_prologue(int b, const SearchPrologueArgs &a, cudaStream_t 
     return CMF_OK;
 }
 
+// ---- thread-per-query searches for small clouds (n <= ST_MAXN: the radar case, a few hundred points) ------------------------------------
+// With 256 candidates a warp-cooperative search spends ~700 warp instructions per query on ballots, shuffles and ordered insertion; one
+// THREAD per query -- the reference's own decomposition (lib/src/ball_query_gpu.cu:9-45, radarflow_util.py:88-99) -- walks the candidates
+// from shared memory (broadcast reads: every lane looks at the same candidate) at ~10-30 warp instructions per candidate for 32 queries.
+// Same distance functions and the same ordering rules as the warp kernels (first hits in index order; ascending by (d, index) with the
+// strict `<` of an insertion sort), so the results are bit-identical to them -- tests/test_gpu_pointops.py compares the two.
+constexpr int ST_THREADS = 128, ST_MAXN = 1024;
+
+__global__ void __launch_bounds__(ST_THREADS)
+search_prologue_thread_kernel(const SearchPrologueArgs a) {
+    __shared__ float sx[ST_MAXN], sy[ST_MAXN], sz[ST_MAXN];
+    __shared__ int srow[ST_THREADS * 61];                                       // a query's 60 neighbour slots, rows padded to 61: conflict-free
+    const int z = blockIdx.z, b = blockIdx.y, n = z ? a.n[1] : a.n[0];
+    const int q0 = blockIdx.x * ST_THREADS;
+    if (q0 >= n) return;                                                        // block-uniform
+    const float *px = (z ? a.xyz[1] : a.xyz[0]) + (size_t)b * 3 * n, *py = px + n, *pz = py + n;
+    int *idx60 = z ? a.idx60[1] : a.idx60[0];
+    for (int i = threadIdx.x; i < n; i += ST_THREADS) { sx[i] = __ldg(px + i); sy[i] = __ldg(py + i); sz[i] = __ldg(pz + i); }
+    const int q = q0 + threadIdx.x;
+    const bool valid = q < n;
+    if (z == 0 && a.E) {                                                        // cloud 1: the radar-feature columns of E and their per-pair |max|
+        float m = 0.f;
+        if (valid) {
+            const float *p = a.ft + (size_t)b * 3 * n;
+            float *o = a.E + ((size_t)b * n + q) * a.lde + a.off;
+            const float f0 = __ldg(p + q), f1 = __ldg(p + n + q), f2 = __ldg(p + 2 * n + q);
+            o[0] = f0; o[1] = f1; o[2] = f2;
+            for (int d = 0; d < a.pad; ++d) o[3 + d] = 0.f;
+            m = fmaxf(fabsf(f0), fmaxf(fabsf(f1), fabsf(f2)));
+        }
+        if (a.amax_ft) {
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sft));
+            if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(a.amax_ft + b, __float_as_uint(m));
+        }
+    }
+    __syncthreads();
+    constexpr int KS[4] = {4, 8, 16, 32};
+    constexpr int OFF[4] = {0, 4, 12, 28};
+    const float qx = valid ? sx[q] : 0.f, qy = valid ? sy[q] : 0.f, qz = valid ? sz[q] : 0.f;
+    int cnt[4], first[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) { cnt[s] = valid ? 0 : KS[s]; first[s] = -1; }
+    int *row = srow + threadIdx.x * 61;
+    for (int k = 0; k < n; ++k) {
+        const float d2 = cmf_sqdist_ref(qx, qy, qz, sx[k], sy[k], sz[k]);
+        if (d2 < c_ms_r2[3]) {                                                  // the radii nest: outside the largest one nothing hits
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                if (d2 < c_ms_r2[s] && cnt[s] < KS[s]) {
+                    row[OFF[s] + cnt[s]] = k;
+                    if (cnt[s] == 0) first[s] = k;
+                    ++cnt[s];
+                }
+        }
+        if ((k & 31) == 31 && __all_sync(0xffffffffu, cnt[0] >= KS[0] && cnt[1] >= KS[1] && cnt[2] >= KS[2] && cnt[3] >= KS[3])) break;
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        // a cloud queried against itself always hits itself, but keep the reference's "no hit -> 0" rule
+        const int fill = first[s] >= 0 ? first[s] : 0;
+        for (int l = first[s] >= 0 ? cnt[s] : 0; l < KS[s]; ++l) row[OFF[s] + l] = fill;
+    }
+    __syncthreads();
+    const int rows = min(ST_THREADS, n - q0);
+    int *dst = idx60 + ((size_t)b * n + q0) * 60;
+    for (int i = threadIdx.x; i < rows * 60; i += ST_THREADS) dst[i] = srow[(i / 60) * 61 + i % 60];      // coalesced
+}
+
+// the cross-frame and the self 8-NN of cloud 1's points (blockIdx.z), one thread per query; coordinates in the reference's planar layout
+__global__ void __launch_bounds__(ST_THREADS)
+knn_point8_thread_kernel(int nq, const float *__restrict__ xyzq, int mc0, const float *__restrict__ xyzc0, int *__restrict__ idx0,
+                         int mc1, const float *__restrict__ xyzc1, int *__restrict__ idx1, unsigned int *__restrict__ dirmax0) {
+    __shared__ float4 sc[ST_MAXN];                                              // candidate {x, y, z, |x|^2}
+    const int z = blockIdx.z, b = blockIdx.y, mc = z ? mc1 : mc0;
+    const float *pc = (z ? xyzc1 : xyzc0) + (size_t)b * 3 * mc;
+    for (int i = threadIdx.x; i < mc; i += ST_THREADS) {
+        const float x = __ldg(pc + i), y = __ldg(pc + mc + i), zz = __ldg(pc + 2 * mc + i);
+        sc[i] = make_float4(x, y, zz, cmf_sqnorm3(x, y, zz));
+    }
+    __syncthreads();
+    const int q = blockIdx.x * ST_THREADS + threadIdx.x;
+    const bool valid = q < nq;
+    const float *pq = xyzq + (size_t)b * 3 * nq;
+    const float qx = __ldg(pq + (valid ? q : 0)), qy = __ldg(pq + nq + (valid ? q : 0)), qz = __ldg(pq + 2 * nq + (valid ? q : 0));
+    const float nqn = cmf_sqnorm3(qx, qy, qz);
+    float bd[8]; int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { bd[j] = INFINITY; bi[j] = INT_MAX; }
+    for (int i = 0; i < mc; ++i) {
+        const float4 c = sc[i];
+        float cd = cmf_sqdist_expanded(qx, qy, qz, nqn, c.x, c.y, c.z, c.w);
+        if (cd < bd[7]) {                               // also rejects inf / NaN, like the reference's topk over finite values
+            int ci = i;
+            bool placed = false;                        // ordered insertion: behind every element with d' <= d (earlier index wins ties), then shift
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                placed = placed || (cd < bd[j]);
+                if (placed) { const float td = bd[j]; const int ti = bi[j]; bd[j] = cd; bi[j] = ci; cd = td; ci = ti; }
+            }
+        }
+    }
+    if (valid) {
+        int *o = (z ? idx1 : idx0) + ((size_t)b * nq + q) * 8;
+        int r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = bi[j] == INT_MAX ? 0 : bi[j];        // unfilled slot: (1e40 -> inf, 0) in the reference
+        reinterpret_cast<int4 *>(o)[0] = make_int4(r[0], r[1], r[2], r[3]);
+        reinterpret_cast<int4 *>(o)[1] = make_int4(r[4], r[5], r[6], r[7]);
+    }
+    if (z == 0 && dirmax0) {                            // per-pair max |candidate - query| component over the neighbours found (fp16 scale bound)
+        float mx = 0.f;
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 c = sc[bi[j] == INT_MAX ? 0 : bi[j]];
+                mx = fmaxf(mx, fmaxf(fabsf(__fsub_rn(c.x, qx)), fmaxf(fabsf(__fsub_rn(c.y, qy)), fabsf(__fsub_rn(c.z, qz)))));
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(dirmax0 + b, __float_as_uint(mx));
+    }
+}
+int cmf_search_small_ok(int n, int n2) { return n <= ST_MAXN && n2 <= ST_MAXN; }
+int cmf_launch_search_prologue_small(int b, const SearchPrologueArgs &a, cudaStream_t st) {
+    const int nmax = a.n[0] > a.n[1] ? a.n[0] : a.n[1];
+    if (b <= 0 || nmax <= 0) return CMF_OK;
+    if (nmax > ST_MAXN) { cmf_set_error("search prologue (thread per query): more than %d points", ST_MAXN); return CMF_ERR_INVALID; }
+    search_prologue_thread_kernel<<<dim3(cmf_divup(nmax, ST_THREADS), b, 2), ST_THREADS, 0, st>>>(a);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+int cmf_launch_knn_point8_dual_small(int b, int n_query, const float *xyzq_planar, int n_cand0, const float *xyzc0_planar, int *idx0,
+                                     int n_cand1, const float *xyzc1_planar, int *idx1, unsigned int *dirmax0, cudaStream_t st) {
+    if (b <= 0 || n_query <= 0) return CMF_OK;
+    if (n_cand0 < 8 || n_cand1 < 8) { cmf_set_error("knn_point8_dual: fewer than 8 candidates (torch.topk raises too)"); return CMF_ERR_INVALID; }
+    if (n_cand0 > ST_MAXN || n_cand1 > ST_MAXN) { cmf_set_error("knn (thread per query): more than %d candidates", ST_MAXN); return CMF_ERR_INVALID; }
+    knn_point8_thread_kernel<<<dim3(cmf_divup(n_query, ST_THREADS), b, 2), ST_THREADS, 0, st>>>(n_query, xyzq_planar, n_cand0, xyzc0_planar, idx0,
+                                                                                               n_cand1, xyzc1_planar, idx1, dirmax0);
+    CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
 int cmf_launch_ball_query_ms(int b, int n, const float *xyz_planar, int *idx60, cudaStream_t st) {
     ball_query_ms_kernel<<<dim3(cmf_divup(n, 8 * MS_QPW), b), 256, 0, st>>>(n, xyz_planar, idx60);
     CMF_LAUNCH_CHECK();

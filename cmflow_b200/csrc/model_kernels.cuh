@@ -27,6 +27,12 @@ struct SearchPrologueArgs {
     const float *ft; float *E; int lde, off, pad; unsigned int *amax_ft;
 };
 int cmf_launch_search_prologue(int b, const SearchPrologueArgs &a, cudaStream_t st);
+// thread-per-query forms of the two search launches for small clouds (cmf_search_small_ok: both clouds <= 1024 points); the k-NN reads the
+// planar coordinates, so `aos` is not written.  Bit-identical results to the warp-cooperative kernels.
+int cmf_search_small_ok(int n, int n2);
+int cmf_launch_search_prologue_small(int b, const SearchPrologueArgs &a, cudaStream_t st);
+int cmf_launch_knn_point8_dual_small(int b, int n_query, const float *xyzq_planar, int n_cand0, const float *xyzc0_planar, int *idx0,
+                                     int n_cand1, const float *xyzc1_planar, int *idx1, unsigned int *dirmax0, cudaStream_t st);
 // the engine's two 8-NN searches of cloud-1 queries (against cloud 2 and against cloud 1) in one launch; dirmax (optional): per-pair
 // atomicMax of |candidate - query| components over the FIRST search's neighbours (uint bit patterns; caller zeroes)
 int cmf_launch_knn_point8_dual(int b, int n_query, const float *query_aos, int n_cand0, const float *cand0_aos, int *idx0,

@@ -247,3 +247,26 @@ def test_fused_setconv1_equals_layerwise(golden_dir, monkeypatch):
     assert rel_err(f1, net0.tap("E", (3, 200, 800)).cpu()[..., :256]) < 2e-6
     assert rel_err(f2, net0.tap("f2", (3, 200, 256)).cpu()) < 2e-6
     assert rel_err(out["sf_agg"], out0["sf_agg"]) < 2e-5
+
+
+@pytest.mark.parametrize("B,N,n_unique", [(3, 256, 120), (2, 200, 200), (2, 33, 20), (1, 1000, 400), (2, 129, 129)])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+def test_thread_per_query_search_equals_warp_kernels(monkeypatch, B, N, n_unique, precision):
+    """Small clouds run the neighbour search with one thread per query, dense ones with the warp-cooperative kernels: same distance
+    functions, same ordering rules -> the same index tables bit for bit, ties included (duplicate-padded clouds as the training loader
+    makes them, dataset/vod.py:102-110), and the same forward."""
+    from cmflow_b200.synth import make_padded_pairs
+    net = CMFlow(Args()); net.load_state_dict(synthetic_state_dict(0)); net = net.to(DEV)
+    net.set_precision(precision)
+    inp = make_padded_pairs(B, N, n_unique, seed=3)[0] if n_unique < N else make_pairs(B, N, seed=3)
+
+    def once():
+        out = run(net, inp)
+        for k, c in (("bq1", 60), ("bq2", 60), ("knn12", 8), ("knn11", 8)):
+            out[k] = net.tap(k, (B, N, c), torch.int32).cpu()
+        return out
+    small = once()
+    monkeypatch.setenv("CMF_SEARCH_WARP", "1")
+    warp = once()
+    for k in ("bq1", "bq2", "knn12", "knn11", "sf_agg", "stat_cls", "pre_trans", "mask"):
+        assert torch.equal(small[k], warp[k]), k
