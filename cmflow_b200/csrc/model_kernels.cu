@@ -160,58 +160,82 @@ int cmf_launch_gemm(const GemmBatch &gb, cudaStream_t st) {
 
 // ---- few-column GEMMs (one column per frame pair: the per-pair bias vectors, the GRU gate pre-activations) -------------------------------
 // Out[c][m] = bias[m] + sum_k W[m][k] * X[c][k] for up to four problems in one launch.  With 256 columns the 128 x 128 tiles of gemm_nt_kernel
-// give a few dozen CTAs (36 us for 0.4 GFLOP); here a CTA takes 64 outputs x 16 columns and K in chunks of 64 through shared memory
-// (W chunk transposed, padded: conflict-free), so that a 3072-output batch is 768 CTAs.  fp32 FMA, k ascending: deterministic.
-constexpr int PG_O = 64, PG_C = 16, PG_K = 64;
-__global__ void __launch_bounds__(256)
+// give a few dozen CTAs (36 us for 0.4 GFLOP); here a CTA takes 64 outputs x 32 columns, K in chunks of 32 through shared memory (both
+// chunks transposed; 4 x 4 register tiles; the next chunk's loads in flight under the arithmetic), so that a 3072-output batch is 384 CTAs.
+// fp32 FMA, k ascending: deterministic.
+constexpr int PG_O = 64, PG_C = 32, PG_K = 32, PG_T = 128;
+__global__ void __launch_bounds__(PG_T)
 pair_gemv_kernel(const GemmBatch gb, int tiles0, int tiles1, int tiles2) {
-    __shared__ float sW[PG_K][PG_O + 1];
-    __shared__ float sX[PG_C][PG_K];
+    __shared__ __align__(16) float sW[PG_K][PG_O + 4];                     // W chunk transposed: sW[k][o], rows of 68 floats (16-byte aligned float4 reads)
+    __shared__ __align__(16) float sX[PG_K][PG_C + 4];                     // X chunk transposed: sX[k][c]
     int ot = blockIdx.x, seg = 0;
     if (ot >= tiles0) { ot -= tiles0; seg = 1; if (ot >= tiles1) { ot -= tiles1; seg = 2; if (ot >= tiles2) { ot -= tiles2; seg = 3; } } }
     const GemmArgs &g = gb.g[seg];
     const int o0 = ot * PG_O, c0 = blockIdx.y * PG_C;
     if (c0 >= g.cols) return;
-    const int o = threadIdx.x & 63, cg = threadIdx.x >> 6;                 // this thread: output o0 + o, columns c0 + cg * 4 .. + 3
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // this thread: outputs o0 + 4 * (tid & 15) .. + 3, columns c0 + 4 * (tid >> 4) .. + 3  (4 x 4 accumulators, two 128-bit shared loads per 16 FMAs)
+    const int to = (threadIdx.x & 15) * 4, tc = (threadIdx.x >> 4) * 4;
+    // loaders: W chunk = 64 rows x 32 k = 2048 floats = 16 per thread (row = idx >> 5, k = idx & 31: a warp reads one 128-byte row slice);
+    //          X chunk = 32 cols x 32 k = 1024 floats = 8 per thread
+    float wreg[16], xreg[8];
+    auto fetch = [&](int kc) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int idx = threadIdx.x + i * PG_T, k = idx & (PG_K - 1), r = idx >> 5;
+            wreg[i] = (o0 + r < g.M) ? __ldg(g.W + (size_t)(o0 + r) * g.ldw + kc + k) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = threadIdx.x + i * PG_T, k = idx & (PG_K - 1), c = idx >> 5;
+            xreg[i] = (c0 + c < g.cols) ? __ldg(g.X + (size_t)(c0 + c) * g.ldx + kc + k) : 0.f;
+        }
+    };
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    fetch(0);
     for (int kc = 0; kc < g.K; kc += PG_K) {
-        __syncthreads();
+        __syncthreads();                                                   // the previous chunk has been consumed
 #pragma unroll
-        for (int i = 0; i < PG_O * PG_K / 256; ++i) {
-            const int idx = threadIdx.x + i * 256, k = idx & (PG_K - 1), r = idx >> 6;
-            sW[k][r] = (o0 + r < g.M) ? __ldg(g.W + (size_t)(o0 + r) * g.ldw + kc + k) : 0.f;
-        }
+        for (int i = 0; i < 16; ++i) { const int idx = threadIdx.x + i * PG_T; sW[idx & (PG_K - 1)][idx >> 5] = wreg[i]; }
 #pragma unroll
-        for (int i = 0; i < PG_C * PG_K / 256; ++i) {
-            const int idx = threadIdx.x + i * 256, k = idx & (PG_K - 1), c = idx >> 6;
-            sX[c][k] = (c0 + c < g.cols) ? __ldg(g.X + (size_t)(c0 + c) * g.ldx + kc + k) : 0.f;
-        }
+        for (int i = 0; i < 8; ++i) { const int idx = threadIdx.x + i * PG_T; sX[idx & (PG_K - 1)][idx >> 5] = xreg[i]; }
         __syncthreads();
-#pragma unroll 16
+        if (kc + PG_K < g.K) fetch(kc + PG_K);                             // the next chunk's global loads fly under this chunk's arithmetic
+#pragma unroll 8
         for (int k = 0; k < PG_K; ++k) {
-            const float w = sW[k][o];
+            const float4 w = *reinterpret_cast<const float4 *>(&sW[k][to]);
+            const float4 x = *reinterpret_cast<const float4 *>(&sX[k][tc]);
+            const float wv[4] = {w.x, w.y, w.z, w.w}, xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j] = fmaf(w, sX[cg * 4 + j][k], acc[j]);
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
         }
     }
-    if (o0 + o >= g.M) return;
-    const float b = g.bias ? __ldg(g.bias + o0 + o) : 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int c = c0 + cg * 4 + j;
-        if (c < g.cols) g.Out[(size_t)c * g.ldo + o0 + o] = acc[j] + b;
+        const int c = c0 + tc + j;
+        if (c >= g.cols) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int o = o0 + to + i;
+            if (o < g.M) g.Out[(size_t)c * g.ldo + o] = acc[i][j] + (g.bias ? __ldg(g.bias + o) : 0.f);
+        }
     }
 }
 int cmf_launch_pair_gemv(const GemmBatch &gb, cudaStream_t st) {
     int tiles[4] = {0, 0, 0, 0}, total = 0, maxC = 0;
     for (int i = 0; i < gb.count; ++i) {
         const GemmArgs &g = gb.g[i];
-        if ((g.K % PG_K) || g.act != CMF_ACT_NONE || g.pbias) { cmf_set_error("pair_gemv: K %% 64 == 0, no activation, no per-pair bias (K=%d)", g.K); return CMF_ERR_INVALID; }
+        if ((g.K % PG_K) || g.act != CMF_ACT_NONE || g.pbias) { cmf_set_error("pair_gemv: K %% 32 == 0, no activation, no per-pair bias (K=%d)", g.K); return CMF_ERR_INVALID; }
         tiles[i] = cmf_divup(g.M, PG_O); total += tiles[i];
         if (g.cols > maxC) maxC = g.cols;
     }
     if (total == 0 || maxC == 0) return CMF_OK;
-    pair_gemv_kernel<<<dim3(total, cmf_divup(maxC, PG_C)), 256, 0, st>>>(gb, tiles[0], tiles[1], tiles[2]);
+    pair_gemv_kernel<<<dim3(total, cmf_divup(maxC, PG_C)), PG_T, 0, st>>>(gb, tiles[0], tiles[1], tiles[2]);
     CMF_LAUNCH_CHECK();
     return CMF_OK;
 }
@@ -360,14 +384,18 @@ constexpr int ST_THREADS = 128, ST_MAXN = 1024;
 
 __global__ void __launch_bounds__(ST_THREADS)
 search_prologue_thread_kernel(const SearchPrologueArgs a) {
-    __shared__ float sx[ST_MAXN], sy[ST_MAXN], sz[ST_MAXN];
-    __shared__ int srow[ST_THREADS * 61];                                       // a query's 60 neighbour slots, rows padded to 61: conflict-free
+    // dynamic shared memory sized by the launch for the larger cloud: candidates {x, y, z, -} and a 16-bit row buffer (indices < 1024): a query's
+    // 60 neighbour slots, rows padded to 61 halfwords.  ~12 KB per block at 256 points: every block of a 256-pair batch is resident at once.
+    extern __shared__ float4 st_smem[];
     const int z = blockIdx.z, b = blockIdx.y, n = z ? a.n[1] : a.n[0];
+    const int nmax = a.n[0] > a.n[1] ? a.n[0] : a.n[1];
+    float4 *sc = st_smem;
+    unsigned short *srow = reinterpret_cast<unsigned short *>(st_smem + nmax);
     const int q0 = blockIdx.x * ST_THREADS;
     if (q0 >= n) return;                                                        // block-uniform
     const float *px = (z ? a.xyz[1] : a.xyz[0]) + (size_t)b * 3 * n, *py = px + n, *pz = py + n;
     int *idx60 = z ? a.idx60[1] : a.idx60[0];
-    for (int i = threadIdx.x; i < n; i += ST_THREADS) { sx[i] = __ldg(px + i); sy[i] = __ldg(py + i); sz[i] = __ldg(pz + i); }
+    for (int i = threadIdx.x; i < n; i += ST_THREADS) sc[i] = make_float4(__ldg(px + i), __ldg(py + i), __ldg(pz + i), 0.f);
     const int q = q0 + threadIdx.x;
     const bool valid = q < n;
     if (z == 0 && a.E) {                                                        // cloud 1: the radar-feature columns of E and their per-pair |max|
@@ -389,18 +417,20 @@ search_prologue_thread_kernel(const SearchPrologueArgs a) {
     __syncthreads();
     constexpr int KS[4] = {4, 8, 16, 32};
     constexpr int OFF[4] = {0, 4, 12, 28};
-    const float qx = valid ? sx[q] : 0.f, qy = valid ? sy[q] : 0.f, qz = valid ? sz[q] : 0.f;
+    const float4 qv = valid ? sc[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float qx = qv.x, qy = qv.y, qz = qv.z;
     int cnt[4], first[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) { cnt[s] = valid ? 0 : KS[s]; first[s] = -1; }
-    int *row = srow + threadIdx.x * 61;
+    unsigned short *row = srow + threadIdx.x * 61;
     for (int k = 0; k < n; ++k) {
-        const float d2 = cmf_sqdist_ref(qx, qy, qz, sx[k], sy[k], sz[k]);
+        const float4 c = sc[k];                                                 // broadcast read
+        const float d2 = cmf_sqdist_ref(qx, qy, qz, c.x, c.y, c.z);
         if (d2 < c_ms_r2[3]) {                                                  // the radii nest: outside the largest one nothing hits
 #pragma unroll
             for (int s = 0; s < 4; ++s)
                 if (d2 < c_ms_r2[s] && cnt[s] < KS[s]) {
-                    row[OFF[s] + cnt[s]] = k;
+                    row[OFF[s] + cnt[s]] = (unsigned short)k;
                     if (cnt[s] == 0) first[s] = k;
                     ++cnt[s];
                 }
@@ -411,19 +441,20 @@ search_prologue_thread_kernel(const SearchPrologueArgs a) {
     for (int s = 0; s < 4; ++s) {
         // a cloud queried against itself always hits itself, but keep the reference's "no hit -> 0" rule
         const int fill = first[s] >= 0 ? first[s] : 0;
-        for (int l = first[s] >= 0 ? cnt[s] : 0; l < KS[s]; ++l) row[OFF[s] + l] = fill;
+        for (int l = first[s] >= 0 ? cnt[s] : 0; l < KS[s]; ++l) row[OFF[s] + l] = (unsigned short)fill;
     }
     __syncthreads();
     const int rows = min(ST_THREADS, n - q0);
     int *dst = idx60 + ((size_t)b * n + q0) * 60;
-    for (int i = threadIdx.x; i < rows * 60; i += ST_THREADS) dst[i] = srow[(i / 60) * 61 + i % 60];      // coalesced
+    for (int i = threadIdx.x; i < rows * 60; i += ST_THREADS) dst[i] = (int)srow[(i / 60) * 61 + i % 60];      // coalesced
 }
 
 // the cross-frame and the self 8-NN of cloud 1's points (blockIdx.z), one thread per query; coordinates in the reference's planar layout
 __global__ void __launch_bounds__(ST_THREADS)
 knn_point8_thread_kernel(int nq, const float *__restrict__ xyzq, int mc0, const float *__restrict__ xyzc0, int *__restrict__ idx0,
                          int mc1, const float *__restrict__ xyzc1, int *__restrict__ idx1, unsigned int *__restrict__ dirmax0) {
-    __shared__ float4 sc[ST_MAXN];                                              // candidate {x, y, z, |x|^2}
+    extern __shared__ float4 st_smem[];                                         // candidate {x, y, z, |x|^2}, sized by the launch
+    float4 *sc = st_smem;
     const int z = blockIdx.z, b = blockIdx.y, mc = z ? mc1 : mc0;
     const float *pc = (z ? xyzc1 : xyzc0) + (size_t)b * 3 * mc;
     for (int i = threadIdx.x; i < mc; i += ST_THREADS) {
@@ -474,12 +505,18 @@ knn_point8_thread_kernel(int nq, const float *__restrict__ xyzq, int mc0, const 
         if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(dirmax0 + b, __float_as_uint(mx));
     }
 }
-int cmf_search_small_ok(int n, int n2) { return n <= ST_MAXN && n2 <= ST_MAXN; }
+// Worth it when there are enough queries to fill the chip with 128-query blocks: one thread walks ALL candidates of its query, so with a
+// handful of pairs (the reference's one-pair evaluation calls) the warp-cooperative kernels have the shorter critical path.
+int cmf_search_small_ok(int b, int n, int n2) {
+    const int nmax = n > n2 ? n : n2;
+    return n <= ST_MAXN && n2 <= ST_MAXN && (long long)b * cmf_divup(nmax, ST_THREADS) >= 128;
+}
 int cmf_launch_search_prologue_small(int b, const SearchPrologueArgs &a, cudaStream_t st) {
     const int nmax = a.n[0] > a.n[1] ? a.n[0] : a.n[1];
     if (b <= 0 || nmax <= 0) return CMF_OK;
     if (nmax > ST_MAXN) { cmf_set_error("search prologue (thread per query): more than %d points", ST_MAXN); return CMF_ERR_INVALID; }
-    search_prologue_thread_kernel<<<dim3(cmf_divup(nmax, ST_THREADS), b, 2), ST_THREADS, 0, st>>>(a);
+    const size_t smem = (size_t)nmax * sizeof(float4) + (size_t)ST_THREADS * 61 * sizeof(unsigned short) + 16;
+    search_prologue_thread_kernel<<<dim3(cmf_divup(nmax, ST_THREADS), b, 2), ST_THREADS, smem, st>>>(a);
     CMF_LAUNCH_CHECK();
     return CMF_OK;
 }
@@ -488,7 +525,8 @@ int cmf_launch_knn_point8_dual_small(int b, int n_query, const float *xyzq_plana
     if (b <= 0 || n_query <= 0) return CMF_OK;
     if (n_cand0 < 8 || n_cand1 < 8) { cmf_set_error("knn_point8_dual: fewer than 8 candidates (torch.topk raises too)"); return CMF_ERR_INVALID; }
     if (n_cand0 > ST_MAXN || n_cand1 > ST_MAXN) { cmf_set_error("knn (thread per query): more than %d candidates", ST_MAXN); return CMF_ERR_INVALID; }
-    knn_point8_thread_kernel<<<dim3(cmf_divup(n_query, ST_THREADS), b, 2), ST_THREADS, 0, st>>>(n_query, xyzq_planar, n_cand0, xyzc0_planar, idx0,
+    const size_t smem = (size_t)(n_cand0 > n_cand1 ? n_cand0 : n_cand1) * sizeof(float4);
+    knn_point8_thread_kernel<<<dim3(cmf_divup(n_query, ST_THREADS), b, 2), ST_THREADS, smem, st>>>(n_query, xyzq_planar, n_cand0, xyzc0_planar, idx0,
                                                                                                n_cand1, xyzc1_planar, idx1, dirmax0);
     CMF_LAUNCH_CHECK();
     return CMF_OK;

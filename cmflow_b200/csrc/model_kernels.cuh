@@ -27,9 +27,10 @@ struct SearchPrologueArgs {
     const float *ft; float *E; int lde, off, pad; unsigned int *amax_ft;
 };
 int cmf_launch_search_prologue(int b, const SearchPrologueArgs &a, cudaStream_t st);
-// thread-per-query forms of the two search launches for small clouds (cmf_search_small_ok: both clouds <= 1024 points); the k-NN reads the
+// thread-per-query forms of the two search launches for batches of small clouds (cmf_search_small_ok: both clouds <= 1024 points and
+// at least 128 blocks of 128 queries); the k-NN reads the
 // planar coordinates, so `aos` is not written.  Bit-identical results to the warp-cooperative kernels.
-int cmf_search_small_ok(int n, int n2);
+int cmf_search_small_ok(int b, int n, int n2);
 int cmf_launch_search_prologue_small(int b, const SearchPrologueArgs &a, cudaStream_t st);
 int cmf_launch_knn_point8_dual_small(int b, int n_query, const float *xyzq_planar, int n_cand0, const float *xyzc0_planar, int *idx0,
                                      int n_cand1, const float *xyzc1_planar, int *idx1, unsigned int *dirmax0, cudaStream_t st);

@@ -265,7 +265,9 @@ def test_thread_per_query_search_equals_warp_kernels(monkeypatch, B, N, n_unique
         for k, c in (("bq1", 60), ("bq2", 60), ("knn12", 8), ("knn11", 8)):
             out[k] = net.tap(k, (B, N, c), torch.int32).cpu()
         return out
+    monkeypatch.setenv("CMF_SEARCH_THREAD", "1")          # (small batches take the warp kernels by default)
     small = once()
+    monkeypatch.delenv("CMF_SEARCH_THREAD")
     monkeypatch.setenv("CMF_SEARCH_WARP", "1")
     warp = once()
     for k in ("bq1", "bq2", "knn12", "knn11", "sf_agg", "stat_cls", "pre_trans", "mask"):
