@@ -513,7 +513,19 @@ static int forward_chunk(cmf_model *m, int bc, int n, int n2, const float *pc1, 
             // |leaky(U1[i] + U2[j] + Wd.dir)| <= max|U1| + max|U2| + max_c |Wd[c]|_1 * max|dir component|
             tc_bound(ta_, 0.f, AM(AM_U1), 1.f, AM(AM_U2), 1.f, AM(AM_DIR), m->wd_l1);
             ta_.out_mul = m->fc_w2_l1; ta_.out_add = m->fc_b2_max; ta_.out_scale_store = F ? SC(SC_H2) : nullptr;
+            static long long *fc_dbg = nullptr;                      // CMF_FC_DBG=1: per-role wait cycles of this launch on stderr (diagnostic)
+            const bool dbg = getenv("CMF_FC_DBG") != nullptr;
+            if (dbg) { if (!fc_dbg) cudaMalloc(&fc_dbg, 512 * 8 * sizeof(long long)); cudaMemsetAsync(fc_dbg, 0, 512 * 8 * sizeof(long long), st); ta_.dbg = fc_dbg; }
             RUN(C_GEMM_FC_MLP, tflops(ta_, 512), cmf_launch_tc_auto(ta_, st));
+            if (dbg) {
+                std::vector<long long> h(512 * 8);
+                cudaStreamSynchronize(st);
+                cudaMemcpy(h.data(), fc_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+                double av[8] = {0}; int nb = 0;
+                for (int b = 0; b < 512; b += 2) if (h[b * 8]) { ++nb; for (int k = 0; k < 8; ++k) av[k] += (double)h[b * 8 + k]; }
+                if (nb) fprintf(stderr, "fc conv1 leaders=%d cycles: total %.0f | issuer tempty %.0f full %.0f peer_full %.0f | loader empty %.0f | producer empty %.0f | epilogue tfull %.0f | tiles %.0f\n",
+                                nb, av[0] / nb, av[1] / nb, av[2] / nb, av[3] / nb, av[4] / nb, av[5] / nb, av[6] / nb, av[7] / nb);
+            }
         }
         fused_wsum = wsum_fused(m);
         {

@@ -61,6 +61,8 @@ int cmf_tc_pair_enabled();
 // cmf_launch_tc_gemm2 with the SC2_Y1 producer (its Out / out_tiled / out_scale_store are ignored); Wt3 = tiled 64 x 256 layer-3 weights with
 // per-channel un-scale a_inv3 and bias3; out[point][0..63] (row stride ldo floats) = max_k relu(W3 relu(W2 x_k + b2) + b3)
 int cmf_launch_sc2_fused(const TcArgs &l2, const float *Wt3, const float *a_inv3, const float *bias3, float *out, int ldo, cudaStream_t st);
+// 2-D tensor map (CUtensorMap *, passed as void * to keep <cuda.h> out of this header) over a row-major fp32 matrix, box = box_cols x box_rows
+int cmf_make_row_map(void *tensor_map, const float *base, long long rows, int ld, int box_cols, int box_rows);
 int cmf_launch_tc_auto(const TcArgs &a, cudaStream_t st);      // pair kernel when M % 256 == 0 (unless CMF_TC2=0), else the one-CTA kernel
 
 // ---- narrow MLP chains with the activations as the A operand (tc_chain.cu; 3xFP16 only) ---------------------------------------------

@@ -682,22 +682,24 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
 // cuTensorMapEncodeTiled through the runtime's driver entry point (the library links no libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int make_row_gather_map(CUtensorMap *tm, const float *base, long long rows, int ld) {
+int cmf_make_row_map(void *tm_, const float *base, long long rows, int ld, int box_cols, int box_rows) {
+    CUtensorMap *tm = reinterpret_cast<CUtensorMap *>(tm_);
     static EncodeTiledFn enc = nullptr;
     if (!enc) {
         cudaDriverEntryPointQueryResult q;
         void *fn = nullptr;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
-            cmf_set_error("sc2 fused: cuTensorMapEncodeTiled is not available from this driver"); return CMF_ERR_STATE;
+            cmf_set_error("tensor map: cuTensorMapEncodeTiled is not available from this driver"); return CMF_ERR_STATE;
         }
         enc = (EncodeTiledFn)fn;
     }
-    // rows x ld floats, row pitch ld * 4 bytes; box = 32 * GK floats x 1 row: tile::gather4 fetches four such boxes at four row indices
+    // rows x ld floats, row pitch ld * 4 bytes; box = box_cols floats x box_rows rows (tile::gather4 fetches four one-row boxes at four row indices);
+    // rows beyond the matrix read as zeros
     const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows}, gstride[1] = {(cuuint64_t)ld * 4};
-    const cuuint32_t box[2] = {32 * GK, 1}, estr[2] = {1, 1};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows}, estr[2] = {1, 1};
     const CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) { cmf_set_error("sc2 fused: cuTensorMapEncodeTiled failed (%d)", (int)rc); return CMF_ERR_CUDA; }
+    if (rc != CUDA_SUCCESS) { cmf_set_error("tensor map: cuTensorMapEncodeTiled failed (%d)", (int)rc); return CMF_ERR_CUDA; }
     return CMF_OK;
 }
 
@@ -721,7 +723,7 @@ int cmf_launch_sc2_fused(const TcArgs &l2, const float *Wt3, const float *a_inv3
     if ((l2.ld_u2 & 3) || (l2.off_u2 & 31) || (reinterpret_cast<uintptr_t>(l2.U2) & 15)) { cmf_set_error("sc2 fused: gathered matrix must be 16-byte aligned, ld a multiple of 4, offset a multiple of 32"); return CMF_ERR_INVALID; }
     CUtensorMap tmapP;
     {   // the gathered matrix: one row per point of the (query = candidate) cloud, l2.cols / ksamp of them
-        int rc = make_row_gather_map(&tmapP, l2.U2, l2.cols / l2.ksamp, l2.ld_u2);
+        int rc = cmf_make_row_map(&tmapP, l2.U2, l2.cols / l2.ksamp, l2.ld_u2, 32 * GK, 1);
         if (rc != CMF_OK) return rc;
     }
     Sc2Args s;
