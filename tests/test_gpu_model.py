@@ -124,12 +124,13 @@ def test_host_entry_point_equals_device_entry_point(golden_dir):
     assert torch.equal(host["pre_trans"], dev["pre_trans"]) and torch.equal(host["mask"].bool(), dev["mask"])
 
 
-def test_host_entry_point_graph_replay(monkeypatch):
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+def test_host_entry_point_graph_replay(monkeypatch, precision):
     """With CMF_HOST_GRAPH=1 cmf_model_forward_host runs a shape eagerly once, captures its kernel sequence as a CUDA graph on the second call
     (on a capturable, i.e. non-legacy-default, stream) and replays it afterwards: every call must equal the device entry point on that call's
     inputs.  A shape change re-allocates the workspace and drops the cached graphs."""
     monkeypatch.setenv("CMF_HOST_GRAPH", "1")
-    net = CMFlow(Args()); net.load_state_dict(synthetic_state_dict(0)); net = net.to(DEV)
+    net = CMFlow(Args()); net.load_state_dict(synthetic_state_dict(0)); net = net.to(DEV); net.set_precision(precision)
     side = torch.cuda.Stream()
     for seed, B, N in ((1, 3, 256), (2, 3, 256), (3, 3, 256), (4, 2, 200), (5, 3, 256), (6, 2, 200), (7, 2, 200)):
         inp = make_pairs(B, N, seed=seed)
@@ -140,6 +141,25 @@ def test_host_entry_point_graph_replay(monkeypatch):
         assert torch.equal(host["sf_agg"], dev["sf_agg"]) and torch.equal(host["pre_trans"], dev["pre_trans"]), (seed, B, N)
         assert torch.equal(host["stat_cls"], dev["stat_cls"]) and torch.equal(host["mask"].bool(), dev["mask"])
     assert lib().cmf_model_host_graphs(net._handle) >= 1
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+def test_host_entry_point_graph_replay_temporal(monkeypatch, precision):
+    """The same for CMFlow-T with its carried GRU state: the replayed graph must follow the state fed to each call."""
+    monkeypatch.setenv("CMF_HOST_GRAPH", "1")
+    nett = CMFlow_T(Args()); nett.load_state_dict(synthetic_state_dict(3, temporal=True)); nett = nett.to(DEV); nett.set_precision(precision)
+    side = torch.cuda.Stream()
+    inp = make_pairs(2, 256, seed=9)
+    for rep in range(2):
+        g_dev, g_host = None, None
+        for step in range(3):
+            dev = run(nett, inp, g_dev)
+            torch.cuda.synchronize()
+            with torch.cuda.stream(side):
+                host = nett.forward_host(*[t.pin_memory() for t in inp[:4]], gfeat=g_host)
+            assert torch.equal(host["sf_agg"], dev["sf_agg"]) and torch.equal(host["gfeat"], dev["gfeat"].cpu()), (rep, step)
+            g_dev, g_host = dev["gfeat"], host["gfeat"].clone()
+    assert lib().cmf_model_host_graphs(nett._handle) >= 1
 
 
 @pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
