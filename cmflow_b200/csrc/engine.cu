@@ -97,7 +97,7 @@ struct Work {
     unsigned int *AMAX;      // fp16x3 mode: per-pair max |x| of the tensors feeding a tensor-core GEMM (uint bit patterns of floats), AM_COUNT x bc
     float *SCL;              // fp16x3 mode: per-pair scales of the tiled intermediates (H2, Y2 x 4 scales), SC_COUNT x bc
 };
-enum { AM_F1 = 0, AM_F2, AM_E, AM_PROP, AM_U1, AM_U2, AM_DIR, AM_HD1, AM_COR, AM_FT, AM_P0, AM_COUNT = AM_P0 + 4 };
+enum { AM_F1 = 0, AM_F2, AM_E, AM_PROP, AM_U1, AM_U2, AM_DIR, AM_HD1, AM_HD2, AM_COR, AM_FT, AM_P0, AM_COUNT = AM_P0 + 4 };
 enum { SC_H2 = 0, SC_Y2, SC_COUNT = SC_Y2 + 4 };
 
 // What a mode does not touch is not allocated: the strict-fp32 pipeline materialises the gathered layer-1 tensors (Y1: 4.3 GB at 256 pairs of
@@ -166,7 +166,8 @@ struct cmf_model {
     struct TcW { const float *wt = nullptr, *ainv = nullptr; };
     struct TcSet { float *buf = nullptr; TcW fc_wc, fc_wn, fc_w2, fc_w3, m2_wp, m2_w2[4], m2_w3[4], hd_w1;
                    TcW m1_w2[4], m1_w3[4], m1_v[4][3], m2_v[4][3];
-                   TcW hd_w2; const float *hd_t2 = nullptr; } tcw[2];      // heads layer 2: [W2F 0; 0 W2M] (256 x 512) and its stacked bias      // narrow chains (tc_chain.cu, fmt 1 only)
+                   TcW hd_w2; const float *hd_t2 = nullptr;
+                   TcW hd_w3; const float *hd_t3 = nullptr; } tcw[2];      // heads layer 3: [W3F 0; 0 W3M] (128 x 256) and its stacked bias      // heads layer 2: [W2F 0; 0 W2M] (256 x 512) and its stacked bias      // narrow chains (tc_chain.cu, fmt 1 only)
     // RaFlow (models/raflow.py): same backbone, no motion head (its weights are zero in the blob), SFR module instead of the Kabsch head
     int raflow = 0; float rigid_thres = 0.15f, rigid_pcs = 0.25f;
     int chain = 1;               // CMF_CHAIN=0: keep the fp32 FMA kernels for set-conv #1 / mlp2 in fp16x3 mode (A/B testing)
@@ -277,7 +278,8 @@ static int ensure_tc_weights(cmf_model *m, int fmt) {
             }
         }
     auto ainv_floats = [](int M) { return (size_t)cmf_divup(M, 128) * 128; };
-    size_t tot = cmf_tc_tiled_floats(256, 512) + ainv_floats(256) + 256;          // + block-diagonal heads layer 2
+    size_t tot = cmf_tc_tiled_floats(256, 512) + ainv_floats(256) + 256            // + block-diagonal heads layer 2
+               + cmf_tc_tiled_floats(128, 256) + ainv_floats(128) + 128;           // + block-diagonal heads layer 3
     for (auto &it : items) tot += cmf_tc_tiled_floats(it.M, it.K) + ainv_floats(it.M);
     cudaError_t e = cudaMalloc(&S.buf, tot * sizeof(float));
     if (e != cudaSuccess) { S.buf = nullptr; cmf_set_error("tc weights cudaMalloc failed: %s", cudaGetErrorString(e)); return CMF_ERR_NOMEM; }
@@ -305,6 +307,22 @@ static int ensure_tc_weights(cmf_model *m, int fmt) {
         CMF_CUDA(cudaDeviceSynchronize());
         cudaFree(tmp);
         S.hd_w2.wt = wt; S.hd_w2.ainv = fmt ? ainv : nullptr; S.hd_t2 = bias;
+        off += cmf_tc_tiled_floats(256, 512) + ainv_floats(256) + 256;
+    }
+    {   // heads layer 3 (radarflow_util.py:247,275), the same way: [W3F 0; 0 W3M] (128 x 256) on the one-CTA tensor-core kernel
+        float *tmp = nullptr;
+        CMF_CUDA(cudaMalloc(&tmp, (size_t)128 * 256 * sizeof(float)));
+        CMF_CUDA(cudaMemset(tmp, 0, (size_t)128 * 256 * sizeof(float)));
+        CMF_CUDA(cudaMemcpy2D(tmp, 256 * sizeof(float), m->seg[HD_W3F], 128 * sizeof(float), 128 * sizeof(float), 64, cudaMemcpyDeviceToDevice));
+        CMF_CUDA(cudaMemcpy2D(tmp + (size_t)64 * 256 + 128, 256 * sizeof(float), m->seg[HD_W3M], 128 * sizeof(float), 128 * sizeof(float), 64, cudaMemcpyDeviceToDevice));
+        float *wt = S.buf + off, *ainv = wt + cmf_tc_tiled_floats(128, 256), *bias = ainv + ainv_floats(128);
+        int rc = fmt ? cmf_tc_tile_weights_f16(tmp, 256, 128, 256, wt, ainv, 0) : cmf_tc_tile_weights(tmp, 256, 128, 256, wt, 0);
+        if (rc) { cudaFree(tmp); return rc; }
+        CMF_CUDA(cudaMemcpy(bias, m->seg[HD_T3F], 64 * sizeof(float), cudaMemcpyDeviceToDevice));
+        CMF_CUDA(cudaMemcpy(bias + 64, m->seg[HD_T3M], 64 * sizeof(float), cudaMemcpyDeviceToDevice));
+        CMF_CUDA(cudaDeviceSynchronize());
+        cudaFree(tmp);
+        S.hd_w3.wt = wt; S.hd_w3.ainv = fmt ? ainv : nullptr; S.hd_t3 = bias;
     }
     CMF_CUDA(cudaDeviceSynchronize());
     return CMF_OK;
@@ -651,8 +669,11 @@ static int forward_chunk(cmf_model *m, int bc, int n, int n2, const float *pc1, 
         tc_bound(ta_, 0.f, AM(AM_PROP), 1.f); if (F) { ta_.amax_out = AM(AM_HD1); }
         RUN(C_GEMM_POINTWISE, tflops(ta_, 256), cmf_launch_tc_auto(ta_, st));
         TcArgs tb_ = tc_plain(T.hd_w2, F, 256, 512, w.HD1, 512, w.HD2, 256, T.hd_t2, bn, CMF_ACT_RELU, nullptr, 0, n);
-        tc_bound(tb_, 0.f, AM(AM_HD1), 1.f);
+        tc_bound(tb_, 0.f, AM(AM_HD1), 1.f); if (F) { tb_.amax_out = AM(AM_HD2); }
         RUN(C_GEMM_POINTWISE, tflops(tb_, 256), cmf_launch_tc_auto(tb_, st));
+        TcArgs tc_ = tc_plain(T.hd_w3, F, 128, 256, w.HD2, 256, w.HD3, 128, T.hd_t3, bn, CMF_ACT_RELU, nullptr, 0, n);
+        tc_bound(tc_, 0.f, AM(AM_HD2), 1.f);
+        RUN(C_GEMM_POINTWISE, tflops(tc_, 128), cmf_launch_tc_auto(tc_, st));
     } else {
         const GemmArgs ga_ = mk(S(HD_W1), 256, w.PROP, 256, w.HD1, 512, nullptr, 512, 256, bn, CMF_ACT_RELU, w.PBH, 512, n);
         RUN(C_GEMM_POINTWISE, gflops(ga_), cmf_launch_gemm1(ga_, st));
@@ -664,9 +685,11 @@ static int forward_chunk(cmf_model *m, int bc, int n, int n2, const float *pc1, 
             gb.g[1] = mk(S(HD_W2M), 256, w.HD1 + 256, 512, w.HD2 + 128, 256, S(HD_T2M), 128, 256, bn, CMF_ACT_RELU);
             RUN(C_GEMM_POINTWISE, gflops(gb), cmf_launch_gemm(gb, st));
         }
-        gb.g[0] = mk(S(HD_W3F), 128, w.HD2, 256, w.HD3, 128, S(HD_T3F), 64, 128, bn, CMF_ACT_RELU);
-        gb.g[1] = mk(S(HD_W3M), 128, w.HD2 + 128, 256, w.HD3 + 64, 128, S(HD_T3M), 64, 128, bn, CMF_ACT_RELU);
-        RUN(C_GEMM_POINTWISE, gflops(gb), cmf_launch_gemm(gb, st));
+        if (!m->tc) {
+            gb.g[0] = mk(S(HD_W3F), 128, w.HD2, 256, w.HD3, 128, S(HD_T3F), 64, 128, bn, CMF_ACT_RELU);
+            gb.g[1] = mk(S(HD_W3M), 128, w.HD2 + 128, 256, w.HD3 + 64, 128, S(HD_T3M), 64, 128, bn, CMF_ACT_RELU);
+            RUN(C_GEMM_POINTWISE, gflops(gb), cmf_launch_gemm(gb, st));
+        }
     }
     if (m->raflow) {       // FlowPredictor read-out into the caller's `output`, then the SFR module (raflow.py:79-117); w.FLOW takes the unused scores
         RUN(C_HEAD_KABSCH, 0, cmf_launch_head_final(bc, n, w.HD3, 128, S(HD_W4), S(HD_W4) + 192, raw_flow, w.FLOW, st));
