@@ -34,18 +34,26 @@ constexpr int SMALL_BYTES = 512 * 16;               // rel-xyz / direction weigh
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + SMALL_BYTES;
 constexpr uint32_t IDESC_TF32 = make_idesc(BM, BN, 0), IDESC_F16 = make_idesc(BM, BN, 1);
 
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+// ISSUE DISCIPLINE (see tc_sc2.cu): the issuer warp runs the issue code in uniform control flow with warp-uniform operands, every tcgen05
+// instruction predicated on `el`, the flag of its elected lane (under `if (lane == 0)` each MMA sat in an ELECT / R2UR.BROADCAST / branch loop).
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t el;
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\tselp.u32 %0, 1, 0, e;\n\t}" : "=r"(el));
+    return el;
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+__device__ __forceinline__ void tc_commit(uint32_t el, uint32_t bar) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(el) : "memory");
 }
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+__device__ __forceinline__ void tc_mma_tf32(uint32_t el, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(el) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t el, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(el) : "memory");
 }
 
 template <int PROD, int F16>
@@ -65,7 +73,7 @@ tc_gemm_kernel(const TcArgs a) {
     if (PROD == TC_PROD_FC_H1 || PROD == TC_PROD_SC2_Y1)
         for (int i = threadIdx.x; i < a.k_blocks * PK; i += NTHREADS) sW[i] = __ldg(reinterpret_cast<const float4 *>(a.Wsmall) + i);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;      // broadcast: warp-uniform role branches
     const long long col_tiles = (a.cols + BN - 1) / BN;
     const long long ntiles = col_tiles * a.m_blocks;
     constexpr int SPB = F16 ? 1 : 2;                              // pipeline stages per 32-element K block
@@ -117,6 +125,7 @@ tc_gemm_kernel(const TcArgs a) {
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
+        const uint32_t el = elect_one();
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -125,8 +134,9 @@ tc_gemm_kernel(const TcArgs a) {
             const uint32_t d_tmem = tmem_base + acc * BN;
             for (int ks = 0; ks < nks; ++ks) {
                 mbar_wait(full_bar(stage), phase);
+                __syncwarp();                                                 // converged warp: one elect-predicated MMA per pass of the warp
                 tc_fence_after();
-                if (lane == 0) {
+                {
                     const uint32_t sa = base + stage * STAGE_BYTES;
                     const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + TILE_A_FLOATS * 4);
                     const uint64_t b_hi = make_desc(sa + 2 * TILE_A_FLOATS * 4), b_lo = make_desc(sa + 2 * TILE_A_FLOATS * 4 + TILE_B_FLOATS * 4);
@@ -134,17 +144,17 @@ tc_gemm_kernel(const TcArgs a) {
                     for (int k8 = 0; k8 < SK / 8; ++k8) {
                         const uint64_t adv = (uint64_t)(k8 * 32 >> 4);      // 32 bytes per K=8 step inside the swizzle atom
                         if (F16) {
-                            tc_mma_f16(d_tmem, a_lo + adv, b_hi + adv, IDESC_F16, (ks | k8) ? 1u : 0u);
-                            tc_mma_f16(d_tmem, a_hi + adv, b_lo + adv, IDESC_F16, 1u);
-                            tc_mma_f16(d_tmem, a_hi + adv, b_hi + adv, IDESC_F16, 1u);
+                            tc_mma_f16(el, d_tmem, a_lo + adv, b_hi + adv, IDESC_F16, (ks | k8) ? 1u : 0u);
+                            tc_mma_f16(el, d_tmem, a_hi + adv, b_lo + adv, IDESC_F16, 1u);
+                            tc_mma_f16(el, d_tmem, a_hi + adv, b_hi + adv, IDESC_F16, 1u);
                         } else {
-                            tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, IDESC_TF32, (ks | k8) ? 1u : 0u);
-                            tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, IDESC_TF32, 1u);
-                            tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, IDESC_TF32, 1u);
+                            tc_mma_tf32(el, d_tmem, a_lo + adv, b_hi + adv, IDESC_TF32, (ks | k8) ? 1u : 0u);
+                            tc_mma_tf32(el, d_tmem, a_hi + adv, b_lo + adv, IDESC_TF32, 1u);
+                            tc_mma_tf32(el, d_tmem, a_hi + adv, b_hi + adv, IDESC_TF32, 1u);
                         }
                     }
-                    tc_commit(empty_bar(stage));                              // frees the smem stage when these MMAs retire
-                    if (ks == nks - 1) tc_commit(tfull_bar(acc));             // accumulator complete
+                    tc_commit(el, empty_bar(stage));                          // frees the smem stage when these MMAs retire
+                    if (ks == nks - 1) tc_commit(el, tfull_bar(acc));         // accumulator complete
                 }
                 __syncwarp();
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
