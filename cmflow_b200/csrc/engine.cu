@@ -487,7 +487,7 @@ static int forward_chunk(cmf_model *m, int bc, int n, int n2, const float *pc1, 
         sp.ft = ft1; sp.E = w.E; sp.lde = E_LD; sp.off = 768; sp.pad = E_LD - 771; sp.amax_ft = fused_amax ? AM(AM_FT) : nullptr;
         // batches of radar-sized clouds: one thread per query (the candidates of a pair fit in shared memory); dense clouds and calls with a
         // handful of pairs: warp-cooperative kernels.  CMF_SEARCH_WARP / CMF_SEARCH_THREAD force one or the other (tests)
-        const bool small = (cmf_search_small_ok(bc, n, n2) || getenv("CMF_SEARCH_THREAD")) && n <= 1024 && n2 <= 1024 && !getenv("CMF_SEARCH_WARP");
+        const bool small = (cmf_search_small_ok(bc, n, n2) || getenv("CMF_SEARCH_THREAD")) && n <= 65535 && n2 <= 65535 && !getenv("CMF_SEARCH_WARP");
         RUN(C_SEARCH, 0, small ? cmf_launch_search_prologue_small(bc, sp, st) : cmf_launch_search_prologue(bc, sp, st));
         if (small) RUN(C_SEARCH, 0, cmf_launch_knn_point8_dual_small(bc, n, pc1, n2, pc2, w.KNN12, n, pc1, w.KNN11, F ? AM(AM_DIR) : nullptr, st));
         else RUN(C_SEARCH, 0, cmf_launch_knn_point8_dual(bc, n, w.X1T, n2, w.X2T, w.KNN12, n, w.X1T, w.KNN11, F ? AM(AM_DIR) : nullptr, st));

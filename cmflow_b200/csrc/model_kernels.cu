@@ -374,28 +374,28 @@ int cmf_launch_search_prologue(int b, const SearchPrologueArgs &a, cudaStream_t 
     return CMF_OK;
 }
 
-// ---- thread-per-query searches for small clouds (n <= ST_MAXN: the radar case, a few hundred points) ------------------------------------
+// ---- thread-per-query searches (batches with enough queries to fill the chip; clouds of up to 65535 points) --------------------------
 // With 256 candidates a warp-cooperative search spends ~700 warp instructions per query on ballots, shuffles and ordered insertion; one
 // THREAD per query -- the reference's own decomposition (lib/src/ball_query_gpu.cu:9-45, radarflow_util.py:88-99) -- walks the candidates
 // from shared memory (broadcast reads: every lane looks at the same candidate) at ~10-30 warp instructions per candidate for 32 queries.
 // Same distance functions and the same ordering rules as the warp kernels (first hits in index order; ascending by (d, index) with the
 // strict `<` of an insertion sort), so the results are bit-identical to them -- tests/test_gpu_pointops.py compares the two.
-constexpr int ST_THREADS = 128, ST_MAXN = 1024;
+constexpr int ST_THREADS = 128, ST_CHUNK = 1024, ST_MAXN = 65535;      // candidates go through shared memory ST_CHUNK at a time; 16-bit row buffer
 
 __global__ void __launch_bounds__(ST_THREADS)
 search_prologue_thread_kernel(const SearchPrologueArgs a) {
-    // dynamic shared memory sized by the launch for the larger cloud: candidates {x, y, z, -} and a 16-bit row buffer (indices < 1024): a query's
-    // 60 neighbour slots, rows padded to 61 halfwords.  ~12 KB per block at 256 points: every block of a 256-pair batch is resident at once.
+    // dynamic shared memory: one chunk of candidates {x, y, z, -} (ST_CHUNK points or the whole cloud if smaller) and a 16-bit row buffer (indices
+    // < 65536): a query's 60 neighbour slots, rows padded to 61 halfwords.  ~20 KB per block at 256 points: every block of a 256-pair batch is resident.
     extern __shared__ float4 st_smem[];
     const int z = blockIdx.z, b = blockIdx.y, n = z ? a.n[1] : a.n[0];
     const int nmax = a.n[0] > a.n[1] ? a.n[0] : a.n[1];
+    const int chunk = nmax < ST_CHUNK ? nmax : ST_CHUNK;
     float4 *sc = st_smem;
-    unsigned short *srow = reinterpret_cast<unsigned short *>(st_smem + nmax);
+    unsigned short *srow = reinterpret_cast<unsigned short *>(st_smem + chunk);
     const int q0 = blockIdx.x * ST_THREADS;
     if (q0 >= n) return;                                                        // block-uniform
     const float *px = (z ? a.xyz[1] : a.xyz[0]) + (size_t)b * 3 * n, *py = px + n, *pz = py + n;
     int *idx60 = z ? a.idx60[1] : a.idx60[0];
-    for (int i = threadIdx.x; i < n; i += ST_THREADS) sc[i] = make_float4(__ldg(px + i), __ldg(py + i), __ldg(pz + i), 0.f);
     const int q = q0 + threadIdx.x;
     const bool valid = q < n;
     if (z == 0 && a.E) {                                                        // cloud 1: the radar-feature columns of E and their per-pair |max|
@@ -414,28 +414,36 @@ search_prologue_thread_kernel(const SearchPrologueArgs a) {
             if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(a.amax_ft + b, __float_as_uint(m));
         }
     }
-    __syncthreads();
     constexpr int KS[4] = {4, 8, 16, 32};
     constexpr int OFF[4] = {0, 4, 12, 28};
-    const float4 qv = valid ? sc[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float qx = qv.x, qy = qv.y, qz = qv.z;
+    const float qx = valid ? __ldg(px + q) : 0.f, qy = valid ? __ldg(py + q) : 0.f, qz = valid ? __ldg(pz + q) : 0.f;
     int cnt[4], first[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) { cnt[s] = valid ? 0 : KS[s]; first[s] = -1; }
     unsigned short *row = srow + threadIdx.x * 61;
-    for (int k = 0; k < n; ++k) {
-        const float4 c = sc[k];                                                 // broadcast read
-        const float d2 = cmf_sqdist_ref(qx, qy, qz, c.x, c.y, c.z);
-        if (d2 < c_ms_r2[3]) {                                                  // the radii nest: outside the largest one nothing hits
+    bool done = !valid;
+    for (int base = 0; base < n; base += chunk) {
+        if (__syncthreads_and(done)) break;                                     // (also: everybody is past the previous chunk)
+        const int cn = min(chunk, n - base);
+        for (int i = threadIdx.x; i < cn; i += ST_THREADS) sc[i] = make_float4(__ldg(px + base + i), __ldg(py + base + i), __ldg(pz + base + i), 0.f);
+        __syncthreads();
+        for (int k = 0; k < cn; ++k) {
+            const float4 c = sc[k];                                             // broadcast read
+            const float d2 = cmf_sqdist_ref(qx, qy, qz, c.x, c.y, c.z);
+            if (d2 < c_ms_r2[3]) {                                              // the radii nest: outside the largest one nothing hits
 #pragma unroll
-            for (int s = 0; s < 4; ++s)
-                if (d2 < c_ms_r2[s] && cnt[s] < KS[s]) {
-                    row[OFF[s] + cnt[s]] = (unsigned short)k;
-                    if (cnt[s] == 0) first[s] = k;
-                    ++cnt[s];
-                }
+                for (int s = 0; s < 4; ++s)
+                    if (d2 < c_ms_r2[s] && cnt[s] < KS[s]) {
+                        row[OFF[s] + cnt[s]] = (unsigned short)(base + k);
+                        if (cnt[s] == 0) first[s] = base + k;
+                        ++cnt[s];
+                    }
+            }
+            if ((k & 31) == 31) {
+                done = cnt[0] >= KS[0] && cnt[1] >= KS[1] && cnt[2] >= KS[2] && cnt[3] >= KS[3];
+                if (__all_sync(0xffffffffu, done)) break;
+            }
         }
-        if ((k & 31) == 31 && __all_sync(0xffffffffu, cnt[0] >= KS[0] && cnt[1] >= KS[1] && cnt[2] >= KS[2] && cnt[3] >= KS[3])) break;
     }
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
@@ -453,15 +461,11 @@ search_prologue_thread_kernel(const SearchPrologueArgs a) {
 __global__ void __launch_bounds__(ST_THREADS)
 knn_point8_thread_kernel(int nq, const float *__restrict__ xyzq, int mc0, const float *__restrict__ xyzc0, int *__restrict__ idx0,
                          int mc1, const float *__restrict__ xyzc1, int *__restrict__ idx1, unsigned int *__restrict__ dirmax0) {
-    extern __shared__ float4 st_smem[];                                         // candidate {x, y, z, |x|^2}, sized by the launch
+    extern __shared__ float4 st_smem[];                                         // one chunk of candidates {x, y, z, |x|^2}, sized by the launch
     float4 *sc = st_smem;
     const int z = blockIdx.z, b = blockIdx.y, mc = z ? mc1 : mc0;
+    const int mcmax = mc0 > mc1 ? mc0 : mc1, chunk = mcmax < ST_CHUNK ? mcmax : ST_CHUNK;
     const float *pc = (z ? xyzc1 : xyzc0) + (size_t)b * 3 * mc;
-    for (int i = threadIdx.x; i < mc; i += ST_THREADS) {
-        const float x = __ldg(pc + i), y = __ldg(pc + mc + i), zz = __ldg(pc + 2 * mc + i);
-        sc[i] = make_float4(x, y, zz, cmf_sqnorm3(x, y, zz));
-    }
-    __syncthreads();
     const int q = blockIdx.x * ST_THREADS + threadIdx.x;
     const bool valid = q < nq;
     const float *pq = xyzq + (size_t)b * 3 * nq;
@@ -470,16 +474,25 @@ knn_point8_thread_kernel(int nq, const float *__restrict__ xyzq, int mc0, const 
     float bd[8]; int bi[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { bd[j] = INFINITY; bi[j] = INT_MAX; }
-    for (int i = 0; i < mc; ++i) {
-        const float4 c = sc[i];
-        float cd = cmf_sqdist_expanded(qx, qy, qz, nqn, c.x, c.y, c.z, c.w);
-        if (cd < bd[7]) {                               // also rejects inf / NaN, like the reference's topk over finite values
-            int ci = i;
-            bool placed = false;                        // ordered insertion: behind every element with d' <= d (earlier index wins ties), then shift
+    for (int base = 0; base < mc; base += chunk) {
+        __syncthreads();                                                        // everybody is past the previous chunk
+        const int cn = min(chunk, mc - base);
+        for (int i = threadIdx.x; i < cn; i += ST_THREADS) {
+            const float x = __ldg(pc + base + i), y = __ldg(pc + mc + base + i), zz = __ldg(pc + 2 * mc + base + i);
+            sc[i] = make_float4(x, y, zz, cmf_sqnorm3(x, y, zz));
+        }
+        __syncthreads();
+        for (int i = 0; i < cn; ++i) {
+            const float4 c = sc[i];
+            float cd = cmf_sqdist_expanded(qx, qy, qz, nqn, c.x, c.y, c.z, c.w);
+            if (cd < bd[7]) {                           // also rejects inf / NaN, like the reference's topk over finite values
+                int ci = base + i;
+                bool placed = false;                    // ordered insertion: behind every element with d' <= d (earlier index wins ties), then shift
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                placed = placed || (cd < bd[j]);
-                if (placed) { const float td = bd[j]; const int ti = bi[j]; bd[j] = cd; bi[j] = ci; cd = td; ci = ti; }
+                for (int j = 0; j < 8; ++j) {
+                    placed = placed || (cd < bd[j]);
+                    if (placed) { const float td = bd[j]; const int ti = bi[j]; bd[j] = cd; bi[j] = ci; cd = td; ci = ti; }
+                }
             }
         }
     }
@@ -496,8 +509,8 @@ knn_point8_thread_kernel(int nq, const float *__restrict__ xyzq, int mc0, const 
         if (valid) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float4 c = sc[bi[j] == INT_MAX ? 0 : bi[j]];
-                mx = fmaxf(mx, fmaxf(fabsf(__fsub_rn(c.x, qx)), fmaxf(fabsf(__fsub_rn(c.y, qy)), fabsf(__fsub_rn(c.z, qz)))));
+                const int cj = bi[j] == INT_MAX ? 0 : bi[j];
+                mx = fmaxf(mx, fmaxf(fabsf(__fsub_rn(__ldg(pc + cj), qx)), fmaxf(fabsf(__fsub_rn(__ldg(pc + mc + cj), qy)), fabsf(__fsub_rn(__ldg(pc + 2 * mc + cj), qz)))));
             }
         }
 #pragma unroll
@@ -515,7 +528,7 @@ int cmf_launch_search_prologue_small(int b, const SearchPrologueArgs &a, cudaStr
     const int nmax = a.n[0] > a.n[1] ? a.n[0] : a.n[1];
     if (b <= 0 || nmax <= 0) return CMF_OK;
     if (nmax > ST_MAXN) { cmf_set_error("search prologue (thread per query): more than %d points", ST_MAXN); return CMF_ERR_INVALID; }
-    const size_t smem = (size_t)nmax * sizeof(float4) + (size_t)ST_THREADS * 61 * sizeof(unsigned short) + 16;
+    const size_t smem = (size_t)(nmax < ST_CHUNK ? nmax : ST_CHUNK) * sizeof(float4) + (size_t)ST_THREADS * 61 * sizeof(unsigned short) + 16;
     search_prologue_thread_kernel<<<dim3(cmf_divup(nmax, ST_THREADS), b, 2), ST_THREADS, smem, st>>>(a);
     CMF_LAUNCH_CHECK();
     return CMF_OK;
@@ -525,7 +538,8 @@ int cmf_launch_knn_point8_dual_small(int b, int n_query, const float *xyzq_plana
     if (b <= 0 || n_query <= 0) return CMF_OK;
     if (n_cand0 < 8 || n_cand1 < 8) { cmf_set_error("knn_point8_dual: fewer than 8 candidates (torch.topk raises too)"); return CMF_ERR_INVALID; }
     if (n_cand0 > ST_MAXN || n_cand1 > ST_MAXN) { cmf_set_error("knn (thread per query): more than %d candidates", ST_MAXN); return CMF_ERR_INVALID; }
-    const size_t smem = (size_t)(n_cand0 > n_cand1 ? n_cand0 : n_cand1) * sizeof(float4);
+    const int mcmax = n_cand0 > n_cand1 ? n_cand0 : n_cand1;
+    const size_t smem = (size_t)(mcmax < ST_CHUNK ? mcmax : ST_CHUNK) * sizeof(float4);
     knn_point8_thread_kernel<<<dim3(cmf_divup(n_query, ST_THREADS), b, 2), ST_THREADS, smem, st>>>(n_query, xyzq_planar, n_cand0, xyzc0_planar, idx0,
                                                                                                n_cand1, xyzc1_planar, idx1, dirmax0);
     CMF_LAUNCH_CHECK();

@@ -27,8 +27,8 @@ struct SearchPrologueArgs {
     const float *ft; float *E; int lde, off, pad; unsigned int *amax_ft;
 };
 int cmf_launch_search_prologue(int b, const SearchPrologueArgs &a, cudaStream_t st);
-// thread-per-query forms of the two search launches for batches of small clouds (cmf_search_small_ok: both clouds <= 1024 points and
-// at least 128 blocks of 128 queries); the k-NN reads the
+// thread-per-query forms of the two search launches (cmf_search_small_ok: at least 128 blocks of 128 queries, clouds of at most 65535
+// points); the k-NN reads the
 // planar coordinates, so `aos` is not written.  Bit-identical results to the warp-cooperative kernels.
 int cmf_search_small_ok(int b, int n, int n2);
 int cmf_launch_search_prologue_small(int b, const SearchPrologueArgs &a, cudaStream_t st);

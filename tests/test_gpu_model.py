@@ -269,7 +269,7 @@ def test_fused_setconv1_equals_layerwise(golden_dir, monkeypatch):
     assert rel_err(out["sf_agg"], out0["sf_agg"]) < 2e-5
 
 
-@pytest.mark.parametrize("B,N,n_unique", [(3, 256, 120), (2, 200, 200), (2, 33, 20), (1, 1000, 400), (2, 129, 129)])
+@pytest.mark.parametrize("B,N,n_unique", [(3, 256, 120), (2, 200, 200), (2, 33, 20), (1, 1000, 400), (2, 129, 129), (1, 2304, 1500), (1, 4096, 4096)])
 @pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
 def test_thread_per_query_search_equals_warp_kernels(monkeypatch, B, N, n_unique, precision):
     """Small clouds run the neighbour search with one thread per query, dense ones with the warp-cooperative kernels: same distance
