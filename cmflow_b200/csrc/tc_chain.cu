@@ -105,17 +105,16 @@ constexpr int SC1_BAR = SC1_F + SC1_F_FLOATS * 4;
 constexpr int SC1_SMEM = SC1_BAR + 16 + 1024;
 constexpr uint32_t IDESC_128x32 = make_idesc(128, 32, 1), IDESC_128x128 = make_idesc(128, 128, 1), IDESC_128x64 = make_idesc(128, 64, 1);
 
+// orow = the output row of the tile's first point (+ scale and channel offset); ncols = valid columns of the tile: 32-bit addressing inside the tile
 template <int K>
-__device__ __forceinline__ void sc1_maxk(const uint32_t (&r)[32], int col0, long long tile_col0, long long total_cols, int s, float ainv, float bias,
-                                         const float *sinv, int ch, float *out) {
+__device__ __forceinline__ void sc1_maxk(const uint32_t (&r)[32], int col0, int ncols, float ainv, float bias, const float *sinv, float *orow) {
 #pragma unroll
     for (int g0 = 0; g0 < 32; g0 += K) {
         float mx = __uint_as_float(r[g0]);
 #pragma unroll
         for (int e = 1; e < K; ++e) mx = fmaxf(mx, __uint_as_float(r[g0 + e]));
-        const long long c = tile_col0 + col0 + g0;
         // the K columns of a point share one scale (phase 3), so the max of the scaled accumulators is the scaled max
-        if (c < total_cols) out[(size_t)(c / K) * 256 + s * 64 + ch] = fmaxf(fmaf(mx, ainv * sinv[col0 + g0], bias), 0.f);
+        if (col0 + g0 < ncols) orow[((col0 + g0) / K) * 256] = fmaxf(fmaf(mx, ainv * sinv[col0 + g0], bias), 0.f);
     }
 }
 
@@ -162,7 +161,7 @@ setconv1_tc_kernel(const Sc1Args a) {
     };
     auto load_x = [&](int j, long long gp, float (&x)[6]) {
         if (j < 0) { x[0] = x[1] = x[2] = x[3] = x[4] = x[5] = 0.f; return; }
-        const long long b = gp / a.n; const int i = (int)(gp - b * a.n);
+        const unsigned b = (unsigned)gp / (unsigned)a.n; const int i = (int)((unsigned)gp - b * (unsigned)a.n);     // 32-bit: bc * n < 2^31 (launcher)
         const float *px = a.xyz + (size_t)b * 3 * a.n, *pf = a.ft + (size_t)b * 3 * a.n;
         x[0] = __fsub_rn(__ldg(px + j), __ldg(px + i));
         x[1] = __fsub_rn(__ldg(px + a.n + j), __ldg(px + a.n + i));
@@ -288,15 +287,17 @@ setconv1_tc_kernel(const Sc1Args a) {
         {
             const int ch = tid & 63, half = tid >> 6;
             const float ainv = sainv3[ch], bias = sb3[ch];
+            const int ncols = (int)(total_cols - tile_col0 < 128 ? total_cols - tile_col0 : 128);      // tile_col0 is a multiple of 128, hence of K
+            float *orow = a.out + (size_t)(tile_col0 >> (2 + s)) * 256 + s * 64 + ch;                  // K = 4 << s
 #pragma unroll 1
             for (int cc = 0; cc < 64; cc += 32) {
                 uint32_t r[32];
                 const int col0 = half * 64 + cc;
                 tmem_ld32(tmem_row + col0, r);
-                if (s == 0) sc1_maxk<4>(r, col0, tile_col0, total_cols, s, ainv, bias, sinv, ch, a.out);
-                else if (s == 1) sc1_maxk<8>(r, col0, tile_col0, total_cols, s, ainv, bias, sinv, ch, a.out);
-                else if (s == 2) sc1_maxk<16>(r, col0, tile_col0, total_cols, s, ainv, bias, sinv, ch, a.out);
-                else sc1_maxk<32>(r, col0, tile_col0, total_cols, s, ainv, bias, sinv, ch, a.out);
+                if (s == 0) sc1_maxk<4>(r, col0, ncols, ainv, bias, sinv, orow);
+                else if (s == 1) sc1_maxk<8>(r, col0, ncols, ainv, bias, sinv, orow);
+                else if (s == 2) sc1_maxk<16>(r, col0, ncols, ainv, bias, sinv, orow);
+                else sc1_maxk<32>(r, col0, ncols, ainv, bias, sinv, orow);
             }
         }
         tc_fence_before();          // the next tile's MMA (after its phase-1 barrier) overwrites these TMEM columns
@@ -526,6 +527,7 @@ int cmf_launch_setconv1_tc(int bc, int n, const float *xyz_planar, const float *
     int rc = init_device(g_num_sms);
     if (rc) return rc;
     if (bc <= 0 || n <= 0) return CMF_OK;
+    if ((long long)bc * n >= (1LL << 31)) { cmf_set_error("setconv1_tc: more than 2^31 points in one chunk"); return CMF_ERR_INVALID; }
     Sc1Args a;
     for (int s = 0; s < 4; ++s)
         a.w[s] = Sc1Scale{w4[s].W1, w4[s].b1, w4[s].b2, w4[s].b3, w4[s].W2t, w4[s].ainv2, w4[s].W3t, w4[s].ainv3};
