@@ -456,8 +456,8 @@ mlp2_tc_kernel(const Mlp2Args a) {
                     // retired), thread (c = tid & 63, half = tid >> 6) takes the maximum of channel c over 64 rows, one atomicMax per thread.
                     // Outputs are ReLU values, so their uint bit patterns order like the floats and 0 is the identity.
                     const long long row0 = row - tid, last = (row0 + 127 < a.rows ? row0 + 127 : a.rows - 1);
-                    const long long pfirst = row0 / a.rows_per_pair;
-                    if (pfirst == last / a.rows_per_pair) {                       // (block-uniform) the whole tile belongs to one frame pair
+                    const long long pfirst = div_i(row0, a.rows_per_pair);
+                    if (pfirst == div_i(last, a.rows_per_pair)) {                       // (block-uniform) the whole tile belongs to one frame pair
                         float *sT = reinterpret_cast<float *>(smem + ML_A);       // [128 rows][64], 16-byte chunk q of row r at chunk q ^ (r & 15)
                         __syncthreads();
 #pragma unroll
@@ -472,7 +472,7 @@ mlp2_tc_kernel(const Mlp2Args a) {
                         if (cm > 0.f) atomicMax(a.gmax + (size_t)pfirst * 256 + s * 64 + c, __float_as_uint(cm));
                         __syncthreads();                                          // the next item's A rows overwrite sT
                     } else if (valid) {                                           // a tile across a pair boundary (points per pair not a multiple of 128)
-                        unsigned int *g = a.gmax + (size_t)(row / a.rows_per_pair) * 256 + s * 64;
+                        unsigned int *g = a.gmax + (size_t)div_i(row, a.rows_per_pair) * 256 + s * 64;
 #pragma unroll
                         for (int q = 0; q < 32; ++q) {
                             if (h[q].x > 0.f) atomicMax(g + 2 * q, __float_as_uint(h[q].x));
@@ -481,7 +481,7 @@ mlp2_tc_kernel(const Mlp2Args a) {
                     }
                 }
                 if (a.amax_out) {          // the consumer GEMM's per-pair fp16 scale comes from here instead of a separate pass over the output
-                    const long long pair = valid ? row / a.rows_per_pair : -1;
+                    const long long pair = valid ? div_i(row, a.rows_per_pair) : -1;
                     const long long p0 = __shfl_sync(0xffffffffu, pair, 0);
                     const float v = valid ? mx : 0.f;
                     if (__all_sync(0xffffffffu, pair == p0 || !valid) && p0 >= 0) {

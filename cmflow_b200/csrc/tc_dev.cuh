@@ -34,6 +34,12 @@ __device__ __forceinline__ void watchdog(unsigned &spins, unsigned long long &t0
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// x / d for a non-negative 64-bit x and a positive int d: column / row counters fit 32 bits in practice, and a 64-bit division is ~100
+// instructions per call on the role warps' issue slots (the 32-bit one ~25)
+__device__ __forceinline__ long long div_i(long long x, int d) {
+    return (unsigned long long)x <= 0xffffffffull ? (long long)((unsigned)x / (unsigned)d) : x / d;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -201,12 +207,12 @@ __device__ __forceinline__ RowCtx make_row(const TcArgs &a, long long c) {
     if (!r.valid) return r;
     if (a.prod == TC_PROD_PLAIN) {
         r.src0 = a.X + (size_t)c * a.ldx;
-        if (a.bs_mode) r.scale = b_scale_of(a, c / a.cols_per_pair);
+        if (a.bs_mode) r.scale = b_scale_of(a, div_i(c, a.cols_per_pair));
         return r;
     }
-    const long long bi = c / a.ksamp;
+    const long long bi = div_i(c, a.ksamp);
     const int kk = (int)(c - bi * a.ksamp);
-    const int b = (int)(bi / a.n_pts), i = (int)(bi - (long long)b * a.n_pts);
+    const int b = (int)div_i(bi, a.n_pts), i = (int)(bi - (long long)b * a.n_pts);
     const int j = __ldg(a.nbr + (size_t)bi * a.nbr_ld + a.nbr_off + kk);
     const int nc = a.n_cand ? a.n_cand : a.n_pts;                      // candidate cloud may hold a different number of points (N1 != N2)
     const float *pq = a.xyz_q + (size_t)b * 3 * a.n_pts, *pc = a.xyz_c + (size_t)b * 3 * nc;
@@ -331,7 +337,7 @@ __device__ __forceinline__ EpiState epi_begin(const TcArgs &a, long long c0, int
     es.inv = es.ainv;
     es.track = a.pbias || a.bs_mode || a.amax_out;
     if (es.track) {
-        es.pair = c0 / a.cols_per_pair; es.pair_end = (es.pair + 1) * (long long)a.cols_per_pair;
+        es.pair = div_i(c0, a.cols_per_pair); es.pair_end = (es.pair + 1) * (long long)a.cols_per_pair;
         epi_load_pair(a, es, m, m_ok, c0 < a.cols);
     }
     return es;
@@ -350,7 +356,7 @@ __device__ __forceinline__ void maxk_groups(const uint32_t (&r)[32], float bias,
     for (int g0 = 0; g0 < 32; g0 += KSAMP) {
         const long long c = cbase + g0;
         float inv = es.inv;
-        if (!uniform && a.fmt == 1 && c < a.cols) inv = es.ainv * __frcp_rn(b_scale_of(a, c / a.cols_per_pair));   // a point's columns share a pair
+        if (!uniform && a.fmt == 1 && c < a.cols) inv = es.ainv * __frcp_rn(b_scale_of(a, div_i(c, a.cols_per_pair)));   // a point's columns share a pair
         float mx = 0.f;                                            // relu output >= 0
 #pragma unroll
         for (int e = 0; e < KSAMP; ++e) mx = fmaxf(mx, fmaf(__uint_as_float(r[g0 + e]), inv, bias));

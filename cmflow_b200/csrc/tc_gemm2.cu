@@ -300,7 +300,7 @@ tc_gemm2_kernel(const TcArgs a) {
                     for (int g0 = 0; g0 < 32; g0 += 8) {             // one point = 8 consecutive columns (always inside one frame pair)
                         const long long c = c0 + cc + g0;
                         float inv = es.inv;
-                        if (F16 && !one_pair && c < a.cols) inv = es.ainv * __frcp_rn(b_scale_of(a, c / a.cols_per_pair));
+                        if (F16 && !one_pair && c < a.cols) inv = es.ainv * __frcp_rn(b_scale_of(a, div_i(c, a.cols_per_pair)));
                         const float2 inv2 = make_float2(inv, inv), bias2 = make_float2(bias, bias), slope2 = make_float2(slope, slope);
                         float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -501,7 +501,7 @@ tc_gemm2_kernel(const TcArgs a) {
             float h2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (c < a.cols) {
                 const long long bi = c >> 3;
-                const int b = (int)(bi / a.n_pts), i = (int)(bi - (long long)b * a.n_pts);
+                const int b = (int)div_i(bi, a.n_pts), i = (int)(bi - (long long)b * a.n_pts);
                 const int j = __ldg(a.nbr + (size_t)bi * a.nbr_ld + a.nbr_off + (int)(c & 7));
                 const int nc = a.n_cand ? a.n_cand : a.n_pts;
                 const float *pq = a.xyz_q + (size_t)b * 3 * a.n_pts, *pc = a.xyz_c + (size_t)b * 3 * nc;

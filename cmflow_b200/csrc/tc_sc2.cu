@@ -427,7 +427,7 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
         for (long long t = cl_id; t < ntiles; t += n_cl) {
             const long long c = t * 256 + rank * HALF_ROWS + q * 32 + lane;
             const bool valid = c < a.cols;
-            const long long pair = (valid ? c : a.cols - 1) / a.cols_per_pair;
+            const long long pair = div_i(valid ? c : a.cols - 1, a.cols_per_pair);
             const float osc = out_scale_of(a, pair);                               // power of two: layer-3 operand scale of this pair
             const float k2 = __frcp_rn(b_scale_of(a, pair)) * osc;                  // accumulator un-scale (times a_inv[ch]) with the output scale folded in
             const float2 k2v = make_float2(k2, k2), oscv = make_float2(osc, osc);
@@ -514,7 +514,7 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                         v[32 * half + i] = fmaxf(fmaf(__uint_as_float(r[i]), ab.x * inv3, ab.y), 0.f);
                     }
                 }
-                float *orow = s.out + (size_t)(c / K) * s.ldo;
+                float *orow = s.out + (size_t)div_i(c, K) * s.ldo;
                 if (K == 4) maxk_store<4>(v, lane, valid, orow);
                 else if (K == 8) maxk_store<8>(v, lane, valid, orow);
                 else if (K == 16) maxk_store<16>(v, lane, valid, orow);
