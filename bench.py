@@ -19,9 +19,9 @@ of a clip batch; --points 4096 --batch 64: the dense cloud), but the bench line 
            dominant kernel (set-conv #2 layer 2): algorithmic TFLOP/s against the measured cuBLAS bf16 rate
            (`frac`), against that rate / 3 (`frac_of_ceiling`: the 3-MMA split), `traffic` = DRAM bytes per launch
            from the committed ncu capture, and `hbm` = SURVEY 8d's algorithmic bytes over the launch time
-  sustained : >= 5 s of back-to-back device-resident forwards (no flush, no host gaps) with the clocks sampled: the
+  sustained : (N=1 only) >= 5 s of back-to-back device-resident forwards (no flush, no host gaps) with the clocks sampled: the
            steady-state number under the power cap, next to the short timed region of `value`
-  latency_b1 : one pair per call (the reference's evaluation shape, main.py:203): device ms and end-to-end host ms,
+  latency_b1 : (N=1 only) one pair per call (the reference's evaluation shape, main.py:203): device ms and end-to-end host ms,
            eager launches and CUDA-graph replay (CMF_HOST_GRAPH=1)
   cpu_baseline : the `--impl reference` arm run as a subprocess on a bounded sample, rank 0, N=1 only
   ref_cuda_baseline : north_star's "reference's own lib/src CUDA build" on the same GPU: the UNMODIFIED reference Python
@@ -386,7 +386,7 @@ def main():
 
     # sustained leg: >= 5 s of back-to-back device-resident forwards, clocks sampled throughout
     sustained = None
-    if not args.no_extra_legs:
+    if not args.no_extra_legs and world == 1:        # an N=1 leg: at N>1 the line is the scaling measurement, kept short
         s2 = ClockSampler(local) if rank == 0 else None
         per = max(1e-3, ms_dev / K)
         n_sus = max(K, int(5200.0 / per) + 1)
@@ -406,7 +406,7 @@ def main():
     # one pair per call -- the reference's evaluation shape (main.py:203: batch_size=1): device latency and end-to-end host latency,
     # eager launches vs CUDA-graph replay of the kernel sequence (CMF_HOST_GRAPH=1; needs a capturable, i.e. non-default, stream)
     latency = None
-    if rank == 0 and not args.no_extra_legs and args.model == "cmflow":
+    if rank == 0 and world == 1 and not args.no_extra_legs and args.model == "cmflow":
         one_dev = [tuple(t[:1].contiguous() for t in ds) for ds in dev_sets]
         one_host = [tuple(t[:1].contiguous().pin_memory() for t in hs) for hs in host_sets]
         side = torch.cuda.Stream(device=dev)

@@ -41,6 +41,7 @@ SIGNATURES = {
     "cmf_model_workspace_bytes": [_vp],
     "cmf_model_host_graphs": [_vp],
     "cmf_model_launches_per_forward": [_vp],
+    "cmf_watchdog_read": [_vp],
     "cmf_model_forward": [_vp, _i, _i] + [_vp] * 11,
     "cmf_model_forward_host": [_vp, _i, _i] + [_vp] * 11,
     "cmf_model_forward2": [_vp, _i, _i, _i] + [_vp] * 12,
@@ -89,9 +90,24 @@ def lib():
     return _lib
 
 
+def watchdog_record():
+    """None, or where a tensor-core kernel's mbarrier watchdog fired (see cmf_watchdog_read): readable after the launch failure."""
+    out = (ctypes.c_ulonglong * 4)()
+    lib().cmf_watchdog_read(out)
+    if not out[0]:
+        return None
+    fam = {1: "tc_gemm (one-CTA GEMM)", 2: "tc_gemm2 (CTA-pair GEMM)", 3: "tc_sc2 (fused set-conv #2)", 4: "tc_chain (set-conv #1 / mlp2)"}.get(out[0], str(out[0]))
+    return {"kernel_family": fam, "block": out[1] >> 32, "thread": out[1] & 0xffffffff, "warp": (out[1] & 0xffffffff) >> 5,
+            "grid": out[2] >> 32, "block_size": out[2] & 0xffffffff, "waited_s": out[3] / 1e9}
+
+
 def check(rc):
     if rc != 0:
-        raise CmfError(lib().cmf_last_error().decode())
+        msg = lib().cmf_last_error().decode()
+        wd = watchdog_record()
+        if wd:
+            msg += f" [mbarrier watchdog fired: {wd}]"
+        raise CmfError(msg)
 
 
 def stream_ptr():

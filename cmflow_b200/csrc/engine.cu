@@ -140,6 +140,8 @@ void carve(Arena &a, Work &w, int bc, int n, const CarveOpts &o) {
 
 }  // namespace
 
+static unsigned long long *g_wd_host[64];          // per device: host-mapped watchdog record (tc_dev.cuh), installed by the first engine created there
+
 struct cmf_model {
     int device = 0;              // ordinal the engine was created on: every entry point switches to it (and back) for its own duration
     int temporal = 0;
@@ -738,6 +740,19 @@ extern "C" int cmf_model_create(cmf_model **out, const float *blob, size_t blob_
         off += pad4((size_t)sr * sc);
     }
     m->shape = exp;
+    {   // watchdog record of this device's tensor-core kernels: host-mapped, so that it can be read after a trap has poisoned the context
+        int dev = m->device;
+        if (dev >= 0 && dev < 64 && !g_wd_host[dev]) {
+            unsigned long long *h = nullptr, *d = nullptr;
+            if (cudaHostAlloc(&h, 4 * sizeof(unsigned long long), cudaHostAllocMapped) == cudaSuccess &&
+                cudaHostGetDevicePointer(reinterpret_cast<void **>(&d), h, 0) == cudaSuccess) {
+                h[0] = h[1] = h[2] = h[3] = 0ull;
+                if (cmf_wd_set_tc_gemm(d) == CMF_OK && cmf_wd_set_tc_gemm2(d) == CMF_OK && cmf_wd_set_tc_sc2(d) == CMF_OK && cmf_wd_set_tc_chain(d) == CMF_OK)
+                    g_wd_host[dev] = h;
+            }
+            cudaGetLastError();          // the record is a diagnostic: never fail the create over it
+        }
+    }
     {   // norms behind the fp16x3 scale bounds (host copy of the blob is still at hand)
         auto seg_host = [&](int i) { return blob + hdr[3 + 3 * i]; };
         auto max_row_l1 = [&](int i, int r0, int r1) {
@@ -791,6 +806,16 @@ extern "C" int cmf_model_host_graphs(const cmf_model *m) {
     return n;
 }
 extern "C" int cmf_model_launches_per_forward(const cmf_model *m) { return m ? m->launches : 0; }
+
+// {0 = no watchdog fired on any device of this process | translation unit (1 tc_gemm, 2 tc_gemm2, 3 tc_sc2, 4 tc_chain), block << 32 | thread,
+//  grid << 32 | block size, nanoseconds waited}: readable after the launch failure the trap causes
+extern "C" int cmf_watchdog_read(unsigned long long *out4) {
+    CMF_REQUIRE(out4, "null pointer");
+    out4[0] = out4[1] = out4[2] = out4[3] = 0ull;
+    for (int d = 0; d < 64; ++d)
+        if (g_wd_host[d] && g_wd_host[d][0]) { for (int k = 0; k < 4; ++k) out4[k] = g_wd_host[d][k]; break; }
+    return CMF_OK;
+}
 
 // Shared body of the device entry points.  n = points of cloud 1, n2 = points of cloud 2 (0 = same as n).
 struct FwdArgs {

@@ -14,6 +14,7 @@
 //
 // Small tiles, no K pipeline: a CTA runs gather / FMA / epilogue phases and MMA phases back to back; 4 (set-conv) or 2 (mlp2) CTAs per
 // SM overlap one another's phases.
+#define CMF_WD_TU 4
 #include "tc_dev.cuh"
 
 using namespace tcdev;
@@ -556,5 +557,11 @@ int cmf_launch_mlp2_tc(long long rows, const float *in, int ld_in, float *out, i
     const int grid = (int)(items < 3LL * g_num_sms ? items : 3LL * g_num_sms);
     mlp2_tc_kernel<<<grid, CH_THREADS, ML_SMEM, st>>>(a);
     CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
+// installs the host-mapped watchdog record of this translation unit's kernels (tc_dev.cuh) on the current device
+int cmf_wd_set_tc_chain(unsigned long long *dev_ptr) {
+    CMF_CUDA(cudaMemcpyToSymbol(tcdev::g_cmf_wd_record, &dev_ptr, sizeof(dev_ptr)));
     return CMF_OK;
 }

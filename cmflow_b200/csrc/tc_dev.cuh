@@ -22,12 +22,27 @@ constexpr int BM = 128, BN = 256, SK = 16, PK = 32;
 #endif
 constexpr unsigned long long WATCHDOG_NS = (unsigned long long)CMF_WATCHDOG_MS * 1000ull * 1000ull;
 __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// Where a watchdog fired: a trap poisons the context, so the thread first leaves {translation unit + 1, block << 32 | thread, grid << 32 | block size,
+// waited ns} in a host-mapped record (one per translation unit that includes this header: CMF_WD_TU names it; cmf_wd_set_* installs the pointer,
+// cmf_watchdog_read() -- callable after the failure -- returns it).  threadIdx.x >> 5 is the role warp, blockDim.x tells the kernel families apart.
+#ifndef CMF_WD_TU
+#define CMF_WD_TU 0
+#endif
+static __device__ unsigned long long *g_cmf_wd_record = nullptr;
 __device__ __forceinline__ void watchdog(unsigned &spins, unsigned long long &t0) {
 #ifndef CMF_NO_WATCHDOG
     if ((++spins & 63u) == 0u) {                 // the suspend-time hint bounds a try_wait from above only: look at the clock every 64 wake-ups
         const unsigned long long now = global_ns();
         if (t0 == 0ull) t0 = now;
-        else if (now - t0 > WATCHDOG_NS) __trap();
+        else if (now - t0 > WATCHDOG_NS) {
+            unsigned long long *r = g_cmf_wd_record;
+            if (r) {
+                r[1] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x; r[2] = ((unsigned long long)gridDim.x << 32) | blockDim.x; r[3] = now - t0;
+                r[0] = CMF_WD_TU + 1;
+                __threadfence_system();
+            }
+            __trap();
+        }
     }
 #endif
 }

@@ -16,6 +16,7 @@
 //   stages (2 x 256 columns) so the epilogue of tile t overlaps the MMAs of tile t+1.  Persistent over tiles.
 #include <stdlib.h>
 
+#define CMF_WD_TU 1
 #include "tc_dev.cuh"
 
 using namespace tcdev;
@@ -395,3 +396,9 @@ extern "C" int cmf_test_tc_gemm(int M, int K, long long cols, const float *W, in
     return cmf_test_tc_gemm_fmt(0, M, K, cols, W, ldw, X, ldx, bias, act, Out, ldo, scratch_tiles, 1, nullptr, nullptr, stream);
 }
 extern "C" size_t cmf_test_tc_tiled_floats(int M, int K) { return cmf_tc_tiled_floats(M, K) + (size_t)cmf_divup(M, BM) * BM; }
+
+// installs the host-mapped watchdog record of this translation unit's kernels (tc_dev.cuh) on the current device
+int cmf_wd_set_tc_gemm(unsigned long long *dev_ptr) {
+    CMF_CUDA(cudaMemcpyToSymbol(tcdev::g_cmf_wd_record, &dev_ptr, sizeof(dev_ptr)));
+    return CMF_OK;
+}

@@ -63,7 +63,12 @@ int cmf_tc_pair_enabled();
 int cmf_launch_sc2_fused(const TcArgs &l2, const float *Wt3, const float *a_inv3, const float *bias3, float *out, int ldo, cudaStream_t st);
 // 2-D tensor map (CUtensorMap *, passed as void * to keep <cuda.h> out of this header) over a row-major fp32 matrix, box = box_cols x box_rows
 int cmf_make_row_map(void *tensor_map, const float *base, long long rows, int ld, int box_cols, int box_rows);
-int cmf_launch_tc_auto(const TcArgs &a, cudaStream_t st);      // pair kernel when M % 256 == 0 (unless CMF_TC2=0), else the one-CTA kernel
+int cmf_launch_tc_auto(const TcArgs &a, cudaStream_t st);
+// watchdog record (tc_dev.cuh): one setter per translation unit with mbarrier waits
+int cmf_wd_set_tc_gemm(unsigned long long *dev_ptr);
+int cmf_wd_set_tc_gemm2(unsigned long long *dev_ptr);
+int cmf_wd_set_tc_sc2(unsigned long long *dev_ptr);
+int cmf_wd_set_tc_chain(unsigned long long *dev_ptr);      // pair kernel when M % 256 == 0 (unless CMF_TC2=0), else the one-CTA kernel
 
 // ---- narrow MLP chains with the activations as the A operand (tc_chain.cu; 3xFP16 only) ---------------------------------------------
 // Weight tiles come from cmf_tc_tile_weights_f16 (one 128-row block, K/32 blocks of {hi, lo}); ainv = its per-row un-scale.

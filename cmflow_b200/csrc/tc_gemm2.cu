@@ -18,6 +18,7 @@
 //   empty[s]       : both   -- tcgen05.commit.cta_group::2 multicast from the leader        (count 1)
 //   tfull[a]       : both   -- commit multicast by the MMA issuer after the last K stage of a tile (count 1)
 //   tempty[a]      : leader -- 4 local + 4 remote epilogue warps                            (count 8)
+#define CMF_WD_TU 2
 #include "tc_dev.cuh"
 
 using namespace tcdev;
@@ -586,4 +587,10 @@ int cmf_launch_tc_gemm2(const TcArgs &a, cudaStream_t st) {
     if (a.prod == TC_PROD_FC_H1) return launch2<TC_PROD_FC_H1>(a, n_cl, st);
     if (a.prod == TC_PROD_TILED) return launch2<TC_PROD_TILED>(a, n_cl, st);
     return launch2<TC_PROD_SC2_Y1>(a, n_cl, st);
+}
+
+// installs the host-mapped watchdog record of this translation unit's kernels (tc_dev.cuh) on the current device
+int cmf_wd_set_tc_gemm2(unsigned long long *dev_ptr) {
+    CMF_CUDA(cudaMemcpyToSymbol(tcdev::g_cmf_wd_record, &dev_ptr, sizeof(dev_ptr)));
+    return CMF_OK;
 }

@@ -34,6 +34,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#define CMF_WD_TU 3
 #include "tc_dev.cuh"
 
 using namespace tcdev;
@@ -734,5 +735,11 @@ int cmf_launch_sc2_fused(const TcArgs &l2, const float *Wt3, const float *a_inv3
     const int n_cl = (int)(ntiles < max_cl ? ntiles : max_cl);
     sc2_fused_kernel<<<2 * n_cl, NTHREADS, SMEM_BYTES, st>>>(s, tmapP);
     CMF_LAUNCH_CHECK();
+    return CMF_OK;
+}
+
+// installs the host-mapped watchdog record of this translation unit's kernels (tc_dev.cuh) on the current device
+int cmf_wd_set_tc_sc2(unsigned long long *dev_ptr) {
+    CMF_CUDA(cudaMemcpyToSymbol(tcdev::g_cmf_wd_record, &dev_ptr, sizeof(dev_ptr)));
     return CMF_OK;
 }

@@ -165,6 +165,12 @@ int cmf_model_host_graphs(const cmf_model *m);
 /* Number of kernels one forward launches (for bench.py's gpu_launches). */
 int cmf_model_launches_per_forward(const cmf_model *m);
 
+/* Diagnostics of a hung launch.  The tensor-core kernels bound every mbarrier wait by a wall-clock watchdog (30 s) that traps instead of
+ * hanging the GPU; the resulting launch failure is sticky for the process.  Before trapping, the waiting thread records where it was:
+ * out4 = {0 if no watchdog fired | 1 + kernel family (0 one-CTA GEMM, 1 CTA-pair GEMM, 2 fused set-conv #2, 3 chain kernels),
+ * block << 32 | thread, grid << 32 | block size, nanoseconds waited}.  Callable after the failure (the record lives in host memory). */
+int cmf_watchdog_read(unsigned long long *out4);
+
 /* Device-resident forward. pc1,pc2,ft1,ft2 (B,3,N) fp32.  gfeat_prev (B,256) or NULL (CMFlow-T only;
  * NULL = zeros, cmflow_t.py:97-98).  Outputs: sf_agg (B,3,N), stat_cls (B,N) [the reference's (B,1,N)],
  * pre_trans (B,4,4), mask (B,N) uint8, gfeat_out (B,256) (CMFlow-T only, else may be NULL).
