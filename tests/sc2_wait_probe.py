@@ -1,3 +1,5 @@
+"""Developer probe (not a test): per-role barrier wait cycles of the fused set-conv #2 kernel at the bench point (CMF_SC2_DBG=1; with a
+library built with -DSC2_PROD_PROFILE also the sections of a producer iteration).   python tests/sc2_wait_probe.py"""
 import os, sys, torch
 sys.path.insert(0, ".")
 from cmflow_b200.cmflow import CMFlow
