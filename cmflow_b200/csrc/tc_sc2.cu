@@ -303,7 +303,7 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
                 if (l3_tile >= l3_tiles) return;
                 const int acc3 = (int)(l3_tile & 1);
                 if (!mbar_test_warp(a3r_bar(acc3, l3_grp), (uint32_t)((l3_tile >> 1) & 1))) return;
-                if (!w3_ready) { mbar_wait(w3_bar, 0); w3_ready = true; }
+                if (!w3_ready) { mbar_wait(w3_bar, 0); w3_ready = true; __syncwarp(); }      // (per-lane wait loop: converge before issuing)
                 tc_fence_after();
                 const uint32_t d3 = tmem_base + acc3 * 256;
                 const int ks0 = l3_grp == 3 ? 0 : 4 + 4 * l3_grp;
