@@ -34,6 +34,7 @@ def test_version_and_error_plumbing_without_gpu():
     rc = L.cmf_ball_query(1, 4, 4, 1.0, 2, None, None, None, None)
     assert rc == 1 and b"null pointer" in L.cmf_last_error()
     assert L.cmf_ball_query(0, 4, 4, 1.0, 2, None, None, None, None) == 0     # empty batch is a no-op
+    assert _lib.watchdog_record() is None                                      # nothing has hung: the record is empty (and needs no GPU to read)
 
 
 def test_product_package_never_imports_the_oracle():
