@@ -30,7 +30,7 @@
 //     the producers' busy time and the kernel ran at the producers' pace, not the tensor pipe's.
 //
 // Cluster of 2 CTAs, 512 threads each -- roles as in tc_gemm2.cu: w0 bulk-copy issuer (weights), w1 MMA issuer (leader) / w1 + w3
-// forwarders (peer), w2 row-context filler, w4-7 epilogue, w8-15 producers (gather + rel-xyz term + ReLU + fp16 split).
+// forwarders (peer), w2 row-context filler, w4-7 epilogue, w8.. producers (PW = 8 warps; gather + rel-xyz term + ReLU + fp16 split).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -202,9 +202,9 @@ sc2_fused_kernel(const Sc2Args s, const __grid_constant__ CUtensorMap tmapP) {
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (base - raw);
     const uint32_t bar0 = base + OFF_BAR;
-    auto full_bar = [&](int i) { return bar0 + 8 * i; };                 // [4] local: bulk copy (expect_tx) + 8 producer warps
-    auto pfull_bar = [&](int i) { return bar0 + 32 + 8 * i; };           // [4] leader: the peer's half of the stage is complete
-    auto empty_bar = [&](int i) { return bar0 + 64 + 8 * i; };           // [4] both: stage consumed (MMA commit, multicast)
+    auto full_bar = [&](int i) { return bar0 + 8 * i; };                 // [NSTAGE <= 4] local: bulk copy (expect_tx) + PW producer warps
+    auto pfull_bar = [&](int i) { return bar0 + 32 + 8 * i; };           // [NSTAGE <= 4] leader: the peer's half of the stage is complete
+    auto empty_bar = [&](int i) { return bar0 + 64 + 8 * i; };           // [NSTAGE <= 4] both: stage consumed (MMA commit, multicast)
     auto tfull_bar = [&](int i) { return bar0 + 96 + 8 * i; };           // [2] both: layer-2 accumulator complete
     auto tempty_bar = [&](int i) { return bar0 + 112 + 8 * i; };         // [2] leader: 4 + 4 epilogue warps have drained the buffer
     auto a3r_bar = [&](int acc, int g) { return bar0 + 128 + 8 * (acc * 4 + g); };   // [2][4] leader: layer-3 operand group written (4 + 4 warps)
